@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the REAL reference code.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+
+The reference modules (Tiny-NewsRec/model_bert.py, model_bert_2.py,
+tnlrv3/modeling.py, metrics.py, dataloader.py) are imported through
+``ref_shim`` and executed on CPU fp32 in ``eval()`` mode; weights come from
+``tinyrec.synth`` (deterministic per (seed, key)) and are loaded with
+``load_state_dict(strict=True)``, which also pins the state_dict key names.
+Fixtures hold inputs + reference outputs (+ a weight checksum), never weights.
+"""
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_shim  # noqa: E402
+import tinyrec.synth as synth  # noqa: E402
+
+ref_modeling = ref_shim.install()
+import model_bert as ref_mb  # noqa: E402
+import model_bert_2 as ref_mb2  # noqa: E402
+import metrics as ref_metrics  # noqa: E402
+
+torch.set_grad_enabled(True)
+
+
+def checksum(sd):
+    return np.array([float(v.double().sum()) for v in sd.values()], dtype=np.float64)
+
+
+def rand_news(rng, n, L, all_pad_row=None, full_row=None):
+    lens = rng.integers(2, L + 1, size=n)
+    if full_row is not None:
+        lens[full_row] = L
+    ids = rng.integers(1000, 30522, size=(n, L))
+    mask = (np.arange(L)[None, :] < lens[:, None]).astype(np.int64)
+    ids = ids * mask
+    ids[:, 0] = 101 * mask[:, 0]
+    if all_pad_row is not None:
+        ids[all_pad_row] = 0
+        mask[all_pad_row] = 0
+    return np.concatenate([ids, mask], axis=1).astype(np.int64)
+
+
+def grad_summary(name, g):
+    g = g.detach()
+    out = {f"gsum/{name}": np.float64(g.double().sum()), f"gabs/{name}": np.float64(g.double().abs().sum())}
+    if g.numel() <= 4096:
+        out[f"gfull/{name}"] = g.numpy().astype(np.float32)
+    else:
+        out[f"gslice/{name}"] = g[:16, :16].numpy().astype(np.float32)
+    return out
+
+
+def gen_relpos():
+    rel = torch.arange(-600, 601)
+    b = ref_modeling.relative_position_bucket(rel, num_buckets=32, max_distance=128)
+    np.savez_compressed(os.path.join(HERE, "relpos.npz"), rel=rel.numpy(), bucket=b.numpy())
+
+
+def gen_encoder():
+    seed, layers, n, L = 7, 2, 5, 12
+    args = ref_shim.make_args(num_student_layers=layers)
+    ne = ref_mb.NewsEncoder(args, is_teacher=False).eval()
+    sd = synth.model_bert_state("", layers, seed, noisy=True)
+    sd = {k[len("news_encoder."):]: v for k, v in sd.items() if k.startswith("news_encoder.")}
+    ne.load_state_dict(sd, strict=True)
+    rng = np.random.default_rng(11)
+    x = rand_news(rng, n, L, all_pad_row=3, full_row=0)
+    xt = torch.from_numpy(x)
+    with torch.no_grad():
+        vec = ne(xt)
+        outs = ne.bert_model(xt[:, :L], xt[:, L:])
+        hidden = torch.stack(outs[3], 0)           # [layers+1, n, L, E]
+    np.savez_compressed(os.path.join(HERE, "encoder.npz"), seed=seed, layers=layers, x=x,
+                        news_vec=vec.numpy(), hidden=hidden.numpy().astype(np.float32),
+                        wsum=checksum(sd))
+
+
+def gen_modelbert():
+    seed, layers, B, H, K, L = 3, 1, 3, 4, 2, 10
+    rng = np.random.default_rng(5)
+    hist = rand_news(rng, B * H, L).reshape(B, H, 2 * L)
+    cand = rand_news(rng, B * K, L).reshape(B, K, 2 * L)
+    hmask = np.array([[0, 0, 1, 1], [0, 0, 0, 0], [1, 1, 1, 1]], dtype=np.float32)
+    hist[0, :2] = 0
+    hist[1, :] = 0
+    out = dict(seed=seed, layers=layers, history=hist, candidate=cand, history_mask=hmask)
+    sd = synth.model_bert_state("", layers, seed, noisy=True)
+    for ulm in (False, True):
+        args = ref_shim.make_args(num_student_layers=layers, user_log_length=H, user_log_mask=ulm)
+        m = ref_mb.ModelBert(args, is_teacher=False).eval()
+        m.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            score, hv, cv, uv = m(torch.from_numpy(hist), torch.from_numpy(hmask), torch.from_numpy(cand))
+        tag = "mask" if ulm else "pad"
+        out.update({f"score_{tag}": score.numpy(), f"hist_{tag}": hv.numpy(), f"cand_{tag}": cv.numpy(),
+                    f"user_{tag}": uv.numpy()})
+    # PLM-NR / teacher form with CE loss (model_bert_2.py:192-213)
+    args = ref_shim.make_args(num_hidden_layers=layers, user_log_length=H, user_log_mask=False)
+    m2 = ref_mb2.ModelBert(args).eval()
+    m2.load_state_dict(sd, strict=True)
+    label = np.array([1, 0, 1], dtype=np.int64)
+    with torch.no_grad():
+        loss, score = m2(torch.from_numpy(hist), torch.from_numpy(hmask), torch.from_numpy(cand),
+                         torch.from_numpy(label))
+    out.update(plmnr_label=label, plmnr_loss=np.float64(loss), plmnr_score=score.numpy(), wsum=checksum(sd))
+    np.savez_compressed(os.path.join(HERE, "modelbert.npz"), **out)
+
+
+def gen_kd():
+    seed, layers, M, B, H, K, L, D = 9, 2, 3, 3, 4, 3, 9, 256
+    trainable = [1]
+    rng = np.random.default_rng(21)
+    hist = rand_news(rng, B * H, L).reshape(B, H, 2 * L)
+    cand = rand_news(rng, B * K, L).reshape(B, K, 2 * L)
+    hmask = np.array([[0, 1, 1, 1], [0, 0, 0, 1], [1, 1, 1, 1]], dtype=np.float32)
+    hist[0, :1] = 0
+    hist[1, :3] = 0
+    label = np.array([2, 0, 1], dtype=np.int64)
+    th = [rng.standard_normal((B, H, D)).astype(np.float32) * 0.3 for _ in range(M)]
+    tc = [rng.standard_normal((B, K, D)).astype(np.float32) * 0.3 for _ in range(M)]
+    out = dict(seed=seed, layers=layers, M=M, history=hist, candidate=cand, history_mask=hmask, label=label,
+               trainable=np.array(trainable), temperature=2.0, coef=0.2,
+               **{f"th{i}": th[i] for i in range(M)}, **{f"tc{i}": tc[i] for i in range(M)})
+    sd = synth.kd_model_state(layers, M, seed, noisy=True)
+    for ulm in (False, True):
+        args = ref_shim.make_args(num_student_layers=layers, user_log_length=H, user_log_mask=ulm,
+                                  num_teachers=M, temperature=2.0, coef=0.2)
+        m = ref_mb.Model(args).eval()
+        m.load_state_dict(sd, strict=True)
+        # freeze policy of run.py:101-112
+        for p in m.teachers.parameters():
+            p.requires_grad = False
+        for p in m.student.news_encoder.bert_model.parameters():
+            p.requires_grad = False
+        for i, layer in enumerate(m.student.news_encoder.bert_model.bert.encoder.layer):
+            if i in trainable:
+                for p in layer.parameters():
+                    p.requires_grad = True
+        res = m(torch.from_numpy(hist), torch.from_numpy(hmask), torch.from_numpy(cand),
+                torch.from_numpy(label), [torch.from_numpy(t) for t in th], [torch.from_numpy(t) for t in tc])
+        tag = "mask" if ulm else "pad"
+        for nm, v in zip(("total", "distill", "emb", "target"), res[:4]):
+            out[f"{nm}_{tag}"] = np.float64(v.detach())
+        out[f"score_{tag}"] = res[4].detach().numpy()
+        if not ulm:
+            res[0].backward()
+            names = []
+            for nm, p in m.named_parameters():
+                if p.requires_grad:
+                    names.append(nm)
+                    out.update(grad_summary(nm, p.grad))
+            out["trainable_names"] = np.array(names)
+    out["wsum"] = checksum(sd)
+    np.savez_compressed(os.path.join(HERE, "kd.npz"), **out)
+
+
+def gen_metrics():
+    from sklearn.metrics import roc_auc_score
+    rng = np.random.default_rng(99)
+    ptr, scores, labels, vals = [0], [], [], []
+    for i in range(60):
+        C = int(rng.integers(2, 70))
+        s = rng.standard_normal(C).astype(np.float32)
+        if i % 3 == 0:
+            s = np.round(s, 1)               # ties
+        if i % 10 == 9 and C <= 16:
+            s[:] = 0.5                       # all tied
+        y = (rng.random(C) < 0.2).astype(np.int64)
+        if i == 7:
+            y[:] = 0                         # skipped impression (run.py:348)
+        elif i == 8:
+            y[:] = 1
+        elif y.sum() == 0:
+            y[0] = 1
+        elif y.sum() == C:
+            y[0] = 0
+        if y.mean() == 0 or y.mean() == 1:
+            vals.append([np.nan] * 4)
+        else:
+            vals.append([roc_auc_score(y, s), ref_metrics.mrr_score(y, s), ref_metrics.ndcg_score(y, s, k=5),
+                         ref_metrics.ndcg_score(y, s, k=10)])
+        scores.append(s)
+        labels.append(y)
+        ptr.append(ptr[-1] + C)
+    np.savez_compressed(os.path.join(HERE, "metrics.npz"), ptr=np.array(ptr), score=np.concatenate(scores),
+                        label=np.concatenate(labels), vals=np.array(vals, dtype=np.float64))
+
+
+def gen_adam():
+    g = torch.Generator().manual_seed(4)
+    p = torch.randn(1000, generator=g)
+    p0 = p.clone()
+    p.requires_grad_(True)
+    opt = torch.optim.Adam([p], lr=1e-4, amsgrad=True)          # run.py:134
+    grads, ps = [], []
+    for step in range(5):
+        gr = torch.randn(1000, generator=g) * (10.0 if step == 1 else 0.1)   # spike so vmax matters
+        p.grad = gr.clone()
+        opt.step()
+        grads.append(gr.numpy())
+        ps.append(p.detach().clone().numpy())
+    np.savez_compressed(os.path.join(HERE, "adam.npz"), p0=p0.numpy(), grads=np.stack(grads), params=np.stack(ps))
+
+
+def gen_batching():
+    """dataloader.py needs `streaming` -> tensorflow; a stub module is enough because
+    only the numpy/python batch assembly (`_process`) is exercised."""
+    tf = types.ModuleType("tensorflow")
+    tf.io = types.SimpleNamespace(gfile=types.SimpleNamespace())
+    sys.modules.setdefault("tensorflow", tf)
+    import dataloader as ref_dl
+    rng = np.random.default_rng(3)
+    n_news, L, D, M, H, npratio = 40, 6, 8, 2, 5, 4
+    news_index = {f"N{i}": i for i in range(1, n_news + 1)}
+    news_combined = rng.integers(0, 1000, size=(n_news + 1, 2 * L)).astype(np.int32)
+    news_combined[0] = 0
+    teacher = [rng.standard_normal((n_news + 1, D)).astype(np.float32) for _ in range(M)]
+    args = types.SimpleNamespace(npratio=npratio, user_log_length=H, batch_size=4, shuffle_buffer_size=1,
+                                 num_teachers=M)
+    dl = ref_dl.DataLoaderTrain(data_dir="", filename_pat="", args=args, world_size=1, worker_rank=0,
+                                cuda_device_idx=0, news_index=news_index, news_combined=news_combined,
+                                teacher_embs=teacher, word_dict=None, enable_gpu=False)
+    lines, clicks_all, pos_all, neg_all = [], [], [], []
+    for b in range(4):
+        nclick = [0, 3, 5, 9][b]
+        clicks = [f"N{int(i)}" for i in rng.integers(1, n_news + 1, size=nclick)]
+        if b == 1:
+            clicks[1] = "NX_unknown"
+        pos = [f"N{int(rng.integers(1, n_news + 1))}"]
+        neg = [f"N{int(i)}" for i in rng.integers(1, n_news + 1, size=npratio)]
+        clicks_all.append(" ".join(clicks)); pos_all.append(pos[0]); neg_all.append(" ".join(neg))
+        lines.append("\t".join(["0", "U1", "t", " ".join(clicks), " ".join(pos), " ".join(neg)]).encode())
+    random.seed(123)
+    uf, lm, nf, lab, thb, tcb = dl._process(lines)
+    np.savez_compressed(
+        os.path.join(HERE, "batching.npz"), news_combined=news_combined, t0=teacher[0], t1=teacher[1],
+        clicks=np.array(clicks_all), pos=np.array(pos_all), neg=np.array(neg_all), H=H, npratio=npratio,
+        user_feature=uf.numpy(), log_mask=lm.numpy(), news_feature=nf.numpy(), label=lab.numpy(),
+        th0=thb[0].numpy(), th1=thb[1].numpy(), tc0=tcb[0].numpy(), tc1=tcb[1].numpy())
+
+
+if __name__ == "__main__":
+    gen_relpos()
+    gen_encoder()
+    gen_modelbert()
+    gen_kd()
+    gen_metrics()
+    gen_adam()
+    gen_batching()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
