@@ -1,0 +1,117 @@
+/*
+ * tinyrec.h -- C ABI of libtinyrec.so: the B200 (sm_100a) kernels behind the
+ * Tiny-NewsRec training / scoring hot path.
+ *
+ * The reference (yflyl613/Tiny-NewsRec) is pure Python/PyTorch and has no FFI or
+ * operator registry: its boundary for this path is the nn.Module API consumed by
+ * Tiny-NewsRec/run.py.  Each entry point below therefore cites the
+ * reference *torch call site* it replaces (paths relative to /root/reference).
+ * The Python modules in tiny-newsrec_b200/ keep the reference signatures and bind
+ * these functions with ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named h_*; the caller owns all
+ *     memory (kernels never allocate or free device memory);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *     device synchronisation inside;
+ *   - return 0 on success, non-zero on error; `tnr_last_error()` returns a
+ *     thread-local message.  There is no CPU fallback and no other backend: a
+ *     device that is not sm_100 is an error;
+ *   - "bf16" buffers are raw uint16 bfloat16, row-major; `ld*` are leading
+ *     dimensions in ELEMENTS.
+ */
+#ifndef TINYREC_H_
+#define TINYREC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNR_ABI_VERSION 1
+
+const char* tnr_last_error(void);
+int tnr_abi_version(void);
+/* Fails unless the current device is compute capability 10.x. Returns SM count in *num_sms. */
+int tnr_device_check(int* num_sms);
+
+/* ------------------------------------------------------------------ GEMM */
+enum { TNR_ACT_NONE = 0, TNR_ACT_GELU = 1, TNR_ACT_TANH = 2, TNR_ACT_DGELU = 3 };
+enum { TNR_BF16 = 0, TNR_F32 = 1 };
+
+/* C[M,N] = epilogue( A[M,K] . B[N,K]^T )       bf16 operands, fp32 accumulate in TMEM
+ * (tcgen05.mma kind::f16, TMA-fed, warp-specialised persistent kernel).
+ *   a_mn_major = 0: A memory is [M,K] row-major (lda >= K).
+ *   a_mn_major = 1: A memory is [K,M] row-major (lda >= M)  -- A used transposed (wgrad).
+ *   b_mn_major = 0: B memory is [N,K] row-major (nn.Linear weight [out,in]).
+ *   b_mn_major = 1: B memory is [K,N] row-major (dgrad through weight; wgrad activations).
+ * epilogue:  v = acc (+ bias[n]);  GELU: (aux <- bf16(v) if aux) v = gelu_erf(v);
+ *            TANH: v = tanh(v);  DGELU: v *= gelu_erf'(aux[m,n]);  v += residual[m,n];
+ *            c_dtype bf16 | f32;  split_k > 1 or accumulate: fp32 atomic add into C.
+ * Replaces torch nn.Linear call sites: tnlrv3/modeling.py:236-248 (QKV), transformers
+ * BertSelfOutput/BertIntermediate/BertOutput dense (used at modeling.py:287,305-306),
+ * model_bert.py:24 (att_fc1), :136 (dense) and their autograd backward. */
+typedef struct {
+  int M, N, K;
+  const void* A; int lda; int a_mn_major;
+  const void* B; int ldb; int b_mn_major;
+  void* C; int ldc; int c_dtype;
+  const float* bias;
+  const void* residual; int ldr;
+  int act;
+  void* aux; int ldaux;
+  int split_k;
+  int accumulate;
+} tnr_gemm_args;
+int tnr_gemm_bf16(const tnr_gemm_args* args, void* stream);
+
+/* ------------------------------------------------- encoder row kernels (HBM-bound) */
+/* out[t,:] = LayerNorm_eps( word[ids[t]] + pos[t % L] + type0 )  ->  bf16 [n_rows*L, E].
+ * ids: int64, row r at ids + r*ids_ld (the reference packs ids|mask as x[n, 2L]).
+ * word_dtype: TNR_BF16 or TNR_F32 table [vocab, E]; pos fp32 [>=L, E]; type0 fp32 [E].
+ * Replaces BertEmbeddings.forward, tnlrv3/modeling.py:153-178 (dropout not applied here). */
+int tnr_embed_ln_fwd(const int64_t* ids, int ids_ld, int n_rows, int L, int vocab, const void* word,
+                     int word_dtype, const float* pos, const float* type0, const float* gamma,
+                     const float* beta, float eps, int E, void* out_bf16, void* stream);
+
+/* y = LayerNorm(x) over rows of a bf16 [rows, E] buffer (the "dense + bias + residual" sum the
+ * GEMM epilogue wrote).  Replaces the LayerNorm of transformers BertSelfOutput / BertOutput
+ * (imported at tnlrv3/modeling.py:12-14, used at :287 and :306). */
+int tnr_layernorm_fwd(const void* x_bf16, int rows, int E, const float* gamma, const float* beta,
+                      float eps, void* y_bf16, void* stream);
+/* dx = dLN(dy; x) ; dgamma += , dbeta += (fp32, caller zero-initialises).  autograd of the above. */
+int tnr_layernorm_bwd(const void* dy_bf16, const void* x_bf16, int rows, int E, const float* gamma,
+                      float eps, void* dx_bf16, float* dgamma, float* dbeta, void* stream);
+/* out[c] += sum_r x[r,c]  (bias gradients of nn.Linear). */
+int tnr_colsum_bf16(const void* x_bf16, int rows, int cols, int ld, float* out, void* stream);
+
+/* ------------------------------------------------------------ fused attention */
+/* ctx = softmax(Q K^T / 8 + (1-mask)*-10000 + relpos[h]) V for L <= 32, head dim 64.
+ * qkv bf16 [n*L, 3E] (Q | K | V), mask int64 (row r at mask + r*mask_ld, 1 = attend),
+ * relpos fp32 [A, L, L], ctx bf16 [n*L, E].
+ * Replaces BertSelfAttention.multi_head_attention, tnlrv3/modeling.py:205-231. */
+int tnr_attn_relpos_fwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relpos,
+                        void* ctx_bf16, int n_news, int L, int A, int E, void* stream);
+/* dqkv bf16 [n*L, 3E] from dctx (probabilities recomputed). */
+int tnr_attn_relpos_bwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relpos,
+                        const void* dctx_bf16, void* dqkv_bf16, int n_news, int L, int A, int E, void* stream);
+
+/* ------------------------------------------------------- additive attention pooling (words) */
+/* a = normalise(exp(e.w2 + b2) [* mask]);  out[n,:] = sum_s a[n,s] x[n,s,:]
+ * x bf16 [n,S,C]; e = tanh(fc1 x) bf16 [n*S, ldq] (from tnr_gemm_bf16 with TNR_ACT_TANH);
+ * mask fp32 [n,S] or NULL; out bf16 [n,C]; a_out fp32 [n,S] (saved for backward).
+ * Replaces AttentionPooling.forward, Tiny-NewsRec/model_bert.py:15-34 (word level, :133). */
+int tnr_attnpool_fwd(const void* x_bf16, const void* e_bf16, int ldq, int Q, const float* w2,
+                     const float* b2, const float* mask, void* out_bf16, float* a_out, int n, int S,
+                     int C, void* stream);
+/* dout fp32 [n,C] -> dx_direct bf16 [n,S,C] (= a*dout), du bf16 [n*S, ldq] (grad at fc1
+ * pre-activation), dw2 += [Q], db2 += [1]. */
+int tnr_attnpool_bwd(const void* x_bf16, const void* e_bf16, int ldq, int Q, const float* w2,
+                     const float* a_in, const float* dout, void* dx_bf16, void* du_bf16, float* dw2,
+                     float* db2, int n, int S, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TINYREC_H_ */

@@ -1,0 +1,243 @@
+"""GPU parity tests of the individual CUDA kernels (through the C ABI via tinyrec.ops)
+against plain PyTorch fp32 restatements of the same op.  Tolerances are the bf16 bar of
+BASELINE.json's north_star (1e-2 relative) unless stated."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def _ops():
+    import tinyrec.ops as ops
+    return ops
+
+
+def _rel_err(got, ref):
+    got, ref = got.float(), ref.float()
+    return float((got - ref).norm() / (ref.norm() + 1e-12)), float((got - ref).abs().max())
+
+
+def _randn(*shape, scale=1.0, dtype=BF, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(dtype)
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 256, 128), (1000, 768, 768), (257, 2304, 768),
+                                   (130, 200, 768), (4096, 3072, 768), (513, 768, 3072), (64, 128, 200)])
+def test_gemm_nt_plain(M, N, K):
+    ops = _ops()
+    a, b = _randn(M, K, seed=1), _randn(N, K, seed=2)
+    out = torch.empty(M, N, device="cuda", dtype=BF)
+    ops.gemm(a, b, out)
+    ref = a.float() @ b.float().t()
+    rel, mx = _rel_err(out, ref)
+    assert rel < 5e-3, (rel, mx)
+
+
+def test_gemm_fp32_out_bias_residual():
+    ops = _ops()
+    M, N, K = 777, 768, 768
+    a, b = _randn(M, K, seed=3), _randn(N, K, scale=0.05, seed=4)
+    bias = _randn(N, dtype=torch.float32, seed=5)
+    res = _randn(M, N, seed=6)
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out, bias=bias, residual=res)
+    ref = a.float() @ b.float().t() + bias + res.float()
+    rel, mx = _rel_err(out, ref)
+    assert rel < 1e-4, (rel, mx)       # fp32 accumulate + fp32 store: only summation order differs
+
+
+def test_gemm_gelu_with_preact_and_tanh():
+    ops = _ops()
+    M, N, K = 500, 3072, 768
+    a, b = _randn(M, K, seed=7), _randn(N, K, scale=0.03, seed=8)
+    bias = _randn(N, dtype=torch.float32, scale=0.1, seed=9)
+    out = torch.empty(M, N, device="cuda", dtype=BF)
+    pre = torch.empty(M, N, device="cuda", dtype=BF)
+    ops.gemm(a, b, out, bias=bias, act=ops.ACT_GELU, aux=pre)
+    z = a.float() @ b.float().t() + bias
+    assert _rel_err(pre, z)[0] < 5e-3
+    assert _rel_err(out, torch.nn.functional.gelu(z))[0] < 5e-3
+    N2 = 200
+    b2 = _randn(N2, K, scale=0.03, seed=10)
+    out2 = torch.empty(M, N2, device="cuda", dtype=BF)
+    ops.gemm(a, b2, out2, bias=bias[:N2].contiguous(), act=ops.ACT_TANH)
+    assert _rel_err(out2, torch.tanh(a.float() @ b2.float().t() + bias[:N2]))[0] < 5e-3
+
+
+def test_gemm_dgelu_epilogue():
+    ops = _ops()
+    M, N, K = 384, 3072, 768
+    dy, w = _randn(M, K, seed=11), _randn(K, N, scale=0.03, seed=12)      # dgrad through W [out=K, in=N]
+    z = _randn(M, N, seed=13)
+    out = torch.empty(M, N, device="cuda", dtype=BF)
+    ops.gemm(dy, w, out, b_t=True, act=ops.ACT_DGELU, aux=z)
+    zf = z.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).backward(dy.float() @ w.float())
+    assert _rel_err(out, zf.grad)[0] < 5e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 768, 768), (1000, 768, 3072), (300, 3072, 768), (100, 768, 200)])
+def test_gemm_b_mn_major(M, N, K):
+    """dgrad: dX[M, N] = dY[M, K] @ W[K, N] with W stored [K, N] row-major."""
+    ops = _ops()
+    a, w = _randn(M, K, seed=14), _randn(K, N, scale=0.05, seed=15)
+    out = torch.empty(M, N, device="cuda", dtype=BF)
+    ops.gemm(a, w, out, b_t=True)
+    rel, mx = _rel_err(out, a.float() @ w.float())
+    assert rel < 5e-3, (rel, mx)
+
+
+@pytest.mark.parametrize("M,N,K,split", [(768, 768, 512, 1), (768, 3072, 1000, 4), (3072, 768, 5280, 8),
+                                         (200, 768, 960, 3), (256, 256, 1760, 2)])
+def test_gemm_wgrad_mn_major_splitk(M, N, K, split):
+    """wgrad: dW[M, N] = dY[K, M]^T @ X[K, N], both operands MN-major, split-K fp32 atomics."""
+    ops = _ops()
+    dy, x = _randn(K, M, seed=16), _randn(K, N, seed=17)
+    out = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(dy, x, out, a_t=True, b_t=True, split_k=split, accumulate=True)
+    ref = dy.float().t() @ x.float()
+    rel, mx = _rel_err(out, ref)
+    assert rel < 1e-4, (rel, mx)
+    ops.gemm(dy, x, out, a_t=True, b_t=True, split_k=split, accumulate=True)     # accumulates
+    assert _rel_err(out, 2 * ref)[0] < 1e-4
+
+
+def test_gemm_rejects_bad_arguments():
+    import tinyrec._lib as L
+    ops = _ops()
+    a, b = _randn(64, 64), _randn(30, 64)
+    with pytest.raises(L.TinyRecError):
+        ops.gemm(a, b, torch.empty(64, 30, device="cuda", dtype=BF))      # N % 8 != 0
+
+
+# ------------------------------------------------------------------ row kernels
+def test_embed_ln():
+    ops = _ops()
+    n, L, E, V = 37, 30, 768, 30522
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ids = torch.randint(0, V, (n, L), generator=g, device="cuda")
+    x = torch.cat([ids, torch.ones_like(ids)], 1)
+    word = _randn(V, E, scale=0.02, dtype=torch.float32, seed=1)
+    pos, typ = _randn(512, E, scale=0.02, dtype=torch.float32, seed=2), _randn(2, E, scale=0.02, dtype=torch.float32, seed=3)
+    gamma, beta = 1 + _randn(E, scale=0.1, dtype=torch.float32, seed=4), _randn(E, scale=0.1, dtype=torch.float32, seed=5)
+    ref = torch.nn.functional.layer_norm(word[ids] + pos[:L] + typ[0], (E,), gamma, beta, 1e-12).reshape(n * L, E)
+    for table in (word, word.to(BF)):
+        out = torch.empty(n * L, E, device="cuda", dtype=BF)
+        ops.embed_ln(x, L, table, pos, typ[0].contiguous(), gamma, beta, 1e-12, out)
+        ref_t = ref if table.dtype == torch.float32 else torch.nn.functional.layer_norm(
+            table.float()[ids] + pos[:L] + typ[0], (E,), gamma, beta, 1e-12).reshape(n * L, E)
+        assert (out.float() - ref_t).abs().max() < 0.03      # bf16 output rounding of O(1..4) values
+        assert _rel_err(out, ref_t)[0] < 4e-3
+
+
+def test_layernorm_fwd_bwd():
+    ops = _ops()
+    rows, E = 1003, 768
+    x = _randn(rows, E, seed=1)
+    dy = _randn(rows, E, seed=2)
+    gamma, beta = 1 + _randn(E, scale=0.1, dtype=torch.float32, seed=3), _randn(E, scale=0.1, dtype=torch.float32, seed=4)
+    y = torch.empty_like(x)
+    ops.layernorm_fwd(x, gamma, beta, 1e-12, y)
+    xf = x.float().requires_grad_(True)
+    gf, bf = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xf, (E,), gf, bf, 1e-12)
+    assert _rel_err(y, ref)[0] < 4e-3
+    ref.backward(dy.float())
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(E, device="cuda"), torch.zeros(E, device="cuda")
+    ops.layernorm_bwd(dy, x, gamma, 1e-12, dx, dg, db)
+    assert _rel_err(dx, xf.grad)[0] < 5e-3
+    assert _rel_err(dg, gf.grad)[0] < 1e-4
+    assert _rel_err(db, bf.grad)[0] < 1e-4
+
+
+def test_colsum():
+    ops = _ops()
+    x = _randn(5281, 3072, seed=1)
+    out = torch.zeros(3072, device="cuda")
+    ops.colsum(x, out)
+    assert _rel_err(out, x.float().sum(0))[0] < 1e-5
+    x2 = _randn(77, 200, seed=2)
+    out2 = torch.zeros(200, device="cuda")
+    ops.colsum(x2, out2)
+    assert _rel_err(out2, x2.float().sum(0))[0] < 1e-5
+
+
+# ------------------------------------------------------------------ attention
+def _attn_ref(qkv, mask, relpos, n, L, A):
+    E = qkv.shape[1] // 3
+    q, k, v = [t.reshape(n, L, A, 64).permute(0, 2, 1, 3) for t in qkv.float().split(E, dim=1)]
+    s = q @ k.transpose(-1, -2) / 8.0 + (1.0 - mask.float())[:, None, None, :] * -10000.0 + relpos[None]
+    return (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(n * L, E)
+
+
+@pytest.mark.parametrize("L", [30, 32, 9, 1])
+def test_attention_fwd_bwd(L):
+    ops = _ops()
+    n, A, E = 11, 12, 768
+    qkv = _randn(n * L, 3 * E, seed=1)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    lens = torch.randint(1, L + 1, (n,), generator=g, device="cuda")
+    lens[0] = L
+    mask = (torch.arange(L, device="cuda")[None, :] < lens[:, None]).long()
+    if n > 2:
+        mask[2] = 0                                  # all-pad news
+    x = torch.cat([torch.zeros_like(mask), mask], 1)
+    relpos = _randn(A, L, L, dtype=torch.float32, seed=4)
+    ctx = torch.empty(n * L, E, device="cuda", dtype=BF)
+    ops.attn_fwd(qkv, x, L, relpos, ctx, A)
+    qf = qkv.float().requires_grad_(True)
+    ref = _attn_ref(qf, mask, relpos, n, L, A)
+    assert _rel_err(ctx, ref)[0] < 5e-3
+    dctx = _randn(n * L, E, seed=5)
+    ref.backward(dctx.float())
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(qkv, x, L, relpos, dctx, dqkv, A)
+    assert _rel_err(dqkv, qf.grad)[0] < 6e-3
+
+
+# ------------------------------------------------------------------ pooling
+@pytest.mark.parametrize("with_mask", [False, True])
+def test_attnpool_fwd_bwd(with_mask):
+    ops = _ops()
+    n, S, C, Q = 23, 30, 768, 200
+    x = _randn(n * S, C, seed=1)
+    e = torch.tanh(_randn(n * S, Q, seed=2).float()).to(BF)
+    w2, b2 = _randn(Q, dtype=torch.float32, scale=0.1, seed=3), _randn(1, dtype=torch.float32, seed=4)
+    mask = None
+    if with_mask:
+        mask = (torch.rand(n, S, device="cuda") > 0.3).float()
+        mask[1] = 0
+    out = torch.empty(n, C, device="cuda", dtype=BF)
+    a = torch.empty(n, S, device="cuda")
+    ops.attnpool_fwd(x, e, Q, w2, b2, mask, out, a, n, S)
+    xf = x.float().reshape(n, S, C).requires_grad_(True)
+    ef = e.float().reshape(n, S, Q).requires_grad_(True)
+    w2f, b2f = w2.clone().requires_grad_(True), b2.clone().requires_grad_(True)
+    alpha = torch.exp(ef @ w2f + b2f)
+    if mask is not None:
+        alpha = alpha * mask
+    aref = alpha / (alpha.sum(1, keepdim=True) + 1e-8)
+    ref = (aref.unsqueeze(-1) * xf).sum(1)
+    assert _rel_err(a, aref)[0] < 1e-4
+    assert _rel_err(out, ref)[0] < 4e-3
+    if with_mask:
+        assert float(out[1].float().abs().max()) == 0.0
+    dout = _randn(n, C, dtype=torch.float32, seed=6)
+    ref.backward(dout)
+    dx = torch.empty_like(x)
+    du = torch.empty_like(e)
+    dw2, db2 = torch.zeros(Q, device="cuda"), torch.zeros(1, device="cuda")
+    ops.attnpool_bwd(x, e, Q, w2, a, dout, dx, du, dw2, db2, n, S)
+    # dx_direct = a * dout (the part of dx not flowing through fc1)
+    assert _rel_err(dx, (aref.detach().unsqueeze(-1) * dout.unsqueeze(1)).reshape(n * S, C))[0] < 4e-3
+    du_ref = ef.grad * (1 - ef.detach() ** 2)
+    assert _rel_err(du, du_ref.reshape(n * S, Q))[0] < 6e-3
+    assert _rel_err(dw2, w2f.grad)[0] < 1e-3
+    assert _rel_err(db2, b2f.grad)[0] < 1e-3 or float(b2f.grad.abs()) < 1e-5

@@ -1,0 +1,47 @@
+// Error plumbing, device check.
+#include "common.cuh"
+#include <cstring>
+
+namespace tnr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return 2;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+}  // namespace tnr
+
+extern "C" __attribute__((visibility("default"))) const char* tnr_last_error(void) { return tnr::g_err; }
+extern "C" __attribute__((visibility("default"))) int tnr_abi_version(void) { return TNR_ABI_VERSION; }
+
+extern "C" __attribute__((visibility("default"))) int tnr_device_check(int* sms) {
+  int dev = 0, major = 0, minor = 0;
+  TNR_CHECK_CUDA(cudaGetDevice(&dev));
+  TNR_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  TNR_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  TNR_REQUIRE(major == 10, "libtinyrec is built for sm_100a only; device %d is sm_%d%d (no fallback path)", dev, major,
+              minor);
+  if (sms) *sms = tnr::num_sms();
+  return 0;
+}

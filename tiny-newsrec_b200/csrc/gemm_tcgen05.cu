@@ -1,0 +1,457 @@
+// bf16 GEMM on 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in TMEM), operands
+// staged by TMA into 128B-swizzled shared memory, warp-specialised persistent kernel:
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      MMA issuer   (one elected lane, tcgen05.mma cta_group::1, 128 x BN x 16)
+//   warp 2      TMEM allocator / deallocator
+//   warps 4-11  epilogue: tcgen05.ld -> bias / GELU / tanh / dGELU / residual -> global
+// Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile i overlap the
+// main loop of tile i+1.  Split-K work items accumulate with fp32 atomics (wgrad).
+//
+// Replaces every nn.Linear on the path (reference call sites listed in include/tinyrec.h).
+#include <cuda.h>
+#include "common.cuh"
+
+namespace tnr {
+namespace gemm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;          // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
+
+struct Params {
+  int M, N, K;
+  int m_tiles, n_tiles, k_blocks, k_per_split, splits;
+  void* C; int ldc; int c_f32;
+  const float* bias;
+  const __nv_bfloat16* residual; int ldr;
+  int act;
+  __nv_bfloat16* aux; int ldaux;
+  int atomic;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 24)) __trap();   // watchdog: turn a protocol bug into an error, not a hang
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (sm_100 format, version 1, SWIZZLE_128B).
+//   K-major : rows of 128 B; 8-row groups 1024 B apart (SBO); LBO unused.
+//   MN-major: atoms of (64 MN x 8 K) = 1024 B; next 8 K-rows +1024 B (SBO);
+//             next 64 MN elements = next TMA box, +8192 B (LBO).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, bool mn_major) {
+  const uint64_t sbo = 1024 >> 4;
+  const uint64_t lbo = mn_major ? (uint64_t)((BK * 128) >> 4) : 0;
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= lbo << 16;
+  d |= sbo << 32;
+  d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;     // SWIZZLE_128B
+  return d;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__host__ __device__ constexpr uint32_t make_idesc() {
+  return (1u << 4)                      // D format f32
+         | (1u << 7)                    // A bf16
+         | (1u << 10)                   // B bf16
+         | ((A_MN ? 1u : 0u) << 15)     // A major
+         | ((B_MN ? 1u : 0u) << 16)     // B major
+         | ((uint32_t)(BN >> 3) << 17)  // N
+         | ((uint32_t)(BM >> 4) << 24); // M
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;             // 2 accumulator stages (power of 2 >= 32)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------- epilogue math
+template <int ACT>
+__device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t* acc, int row, int col0) {
+  // 32 consecutive columns [col0, col0+32) of one output row
+  const bool row_ok = row < p.M;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = col0 + g * 8;
+    if (!row_ok || col >= p.N) continue;      // N % 8 == 0 is required by the host wrapper
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[g * 8 + i]);
+    if (p.bias != nullptr) {
+      const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+      const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (ACT == TNR_ACT_GELU) {
+      if (p.aux != nullptr)
+        *reinterpret_cast<bf16x8*>(p.aux + (size_t)row * p.ldaux + col) = pack8(v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    } else if (ACT == TNR_ACT_TANH) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = tanhf(v[i]);
+    } else if (ACT == TNR_ACT_DGELU) {
+      float z[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(p.aux + (size_t)row * p.ldaux + col), z);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(z[i]);
+    }
+    if (p.residual != nullptr) {
+      float r[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(p.residual + (size_t)row * p.ldr + col), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += r[i];
+    }
+    if (p.c_f32) {
+      float* c = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col;
+      if (p.atomic) {
+        atomicAdd(reinterpret_cast<float4*>(c), make_float4(v[0], v[1], v[2], v[3]));
+        atomicAdd(reinterpret_cast<float4*>(c + 4), make_float4(v[4], v[5], v[6], v[7]));
+      } else {
+        *reinterpret_cast<float4*>(c) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    } else {
+      __nv_bfloat16* c = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col;
+      *reinterpret_cast<bf16x8*>(c) = pack8(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- kernel
+template <int BN, bool A_MN, bool B_MN, int ACT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // barriers after the pipeline stages
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), NUM_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_blk = t % p.n_tiles;
+        const int m_blk = (t / p.n_tiles) % p.m_tiles;
+        const int ks = t / (p.n_tiles * p.m_tiles);
+        const int kb0 = ks * p.k_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.k_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_load_2d(sa + i * (BK * 128), &tmap_a, full_bar(stage), m_blk * BM + i * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(sb + i * (BK * 128), &tmap_b, full_bar(stage), n_blk * BN + i * 64, kb * BK);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int ks = t / (p.n_tiles * p.m_tiles);
+        const int kb0 = ks * p.k_per_split;
+        const int kb1 = min(p.k_blocks, kb0 + p.k_per_split);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t adesc = make_desc(sa, A_MN);
+          const uint64_t bdesc = make_desc(sb, B_MN);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance inside the swizzle atom: K-major +32 B per UMMA_K, MN-major +16 rows * 128 B
+            const uint64_t aoff = (uint64_t)((A_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
+            const uint64_t boff = (uint64_t)((B_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
+            tc_mma_bf16(tmem_d, adesc + aoff, bdesc + boff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));            // frees the smem stage when these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));                // accumulator ready for the epilogue
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int e = warp - 4;
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = e >> 2;                      // column half of the tile
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int n_blk = t % p.n_tiles;
+      const int m_blk = (t / p.n_tiles) % p.m_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + quarter * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        const int coff = half * (BN / 2) + c * 32;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + coff), r);
+        tmem_ld_wait();
+        epilogue_chunk<ACT>(p, r, row, n_blk * BN + coff);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: dim0 (contiguous) = inner, dim1 = outer with row stride ld elements.
+static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                    uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  TNR_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TNR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (CUresult %d) inner=%llu outer=%llu ld=%llu", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN, int ACT>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t st) {
+  auto kern = gemm_kernel<BN, A_MN, B_MN, ACT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TNR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int dispatch_act(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t st) {
+  switch (p.act) {
+    case TNR_ACT_NONE: return launch<BN, A_MN, B_MN, TNR_ACT_NONE>(ta, tb, p, grid, st);
+    case TNR_ACT_GELU: return launch<BN, A_MN, B_MN, TNR_ACT_GELU>(ta, tb, p, grid, st);
+    case TNR_ACT_TANH: return launch<BN, A_MN, B_MN, TNR_ACT_TANH>(ta, tb, p, grid, st);
+    case TNR_ACT_DGELU: return launch<BN, A_MN, B_MN, TNR_ACT_DGELU>(ta, tb, p, grid, st);
+  }
+  set_error("tnr_gemm_bf16: unknown act %d", p.act);
+  return 1;
+}
+
+template <int BN>
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid,
+                          cudaStream_t st) {
+  if (!a_mn && !b_mn) return dispatch_act<BN, false, false>(ta, tb, p, grid, st);
+  if (!a_mn && b_mn) return dispatch_act<BN, false, true>(ta, tb, p, grid, st);
+  if (a_mn && b_mn) {
+    // wgrad only ever uses the plain epilogue
+    TNR_REQUIRE(p.act == TNR_ACT_NONE, "tnr_gemm_bf16: A MN-major supports act=NONE only");
+    return launch<BN, true, true, TNR_ACT_NONE>(ta, tb, p, grid, st);
+  }
+  set_error("tnr_gemm_bf16: A MN-major with B K-major is not instantiated");
+  return 1;
+}
+
+}  // namespace gemm
+}  // namespace tnr
+
+extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_gemm_args* a, void* stream) {
+  using namespace tnr;
+  using namespace tnr::gemm;
+  TNR_REQUIRE(a != nullptr, "tnr_gemm_bf16: null args");
+  TNR_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "tnr_gemm_bf16: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
+  TNR_REQUIRE(a->N % 8 == 0, "tnr_gemm_bf16: N=%d must be a multiple of 8", a->N);
+  TNR_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0 && a->ldc % 8 == 0, "tnr_gemm_bf16: leading dims must be multiples of 8");
+  TNR_REQUIRE(((uintptr_t)a->A % 16 == 0) && ((uintptr_t)a->B % 16 == 0) && ((uintptr_t)a->C % 16 == 0),
+              "tnr_gemm_bf16: operands must be 16-byte aligned");
+  TNR_REQUIRE(a->residual == nullptr || (a->ldr % 8 == 0 && (uintptr_t)a->residual % 16 == 0),
+              "tnr_gemm_bf16: residual alignment");
+  TNR_REQUIRE(a->aux == nullptr || (a->ldaux % 8 == 0 && (uintptr_t)a->aux % 16 == 0), "tnr_gemm_bf16: aux alignment");
+  TNR_REQUIRE(a->act != TNR_ACT_DGELU || a->aux != nullptr, "tnr_gemm_bf16: DGELU needs aux (pre-activation)");
+  TNR_REQUIRE(a->bias == nullptr || (uintptr_t)a->bias % 16 == 0, "tnr_gemm_bf16: bias alignment");
+  const bool atomic = a->split_k > 1 || a->accumulate != 0;
+  TNR_REQUIRE(!atomic || a->c_dtype == TNR_F32, "tnr_gemm_bf16: split_k/accumulate require fp32 C");
+  TNR_REQUIRE(!atomic || (a->act == TNR_ACT_NONE && a->residual == nullptr),
+              "tnr_gemm_bf16: split_k/accumulate support the plain epilogue only");
+  const bool a_mn = a->a_mn_major != 0, b_mn = a->b_mn_major != 0;
+  if (a_mn) TNR_REQUIRE(a->M % 8 == 0, "tnr_gemm_bf16: MN-major A needs M %% 8 == 0");
+
+  const int BN = (a->N > 128) ? 256 : 128;
+  Params p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.m_tiles = (a->M + BM - 1) / BM;
+  p.n_tiles = (a->N + BN - 1) / BN;
+  p.k_blocks = (a->K + BK - 1) / BK;
+  int splits = a->split_k > 1 ? a->split_k : 1;
+  if (splits > p.k_blocks) splits = p.k_blocks;
+  p.k_per_split = (p.k_blocks + splits - 1) / splits;
+  p.splits = (p.k_blocks + p.k_per_split - 1) / p.k_per_split;
+  p.C = a->C; p.ldc = a->ldc; p.c_f32 = (a->c_dtype == TNR_F32);
+  p.bias = a->bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual); p.ldr = a->ldr;
+  p.act = a->act;
+  p.aux = reinterpret_cast<__nv_bfloat16*>(a->aux); p.ldaux = a->ldaux;
+  p.atomic = atomic ? 1 : 0;
+
+  CUtensorMap ta, tb;
+  if (!a_mn) { if (make_map(&ta, a->A, a->K, a->M, a->lda, BK, BM)) return 1; }
+  else       { if (make_map(&ta, a->A, a->M, a->K, a->lda, 64, BK)) return 1; }
+  if (!b_mn) { if (make_map(&tb, a->B, a->K, a->N, a->ldb, BK, BN)) return 1; }
+  else       { if (make_map(&tb, a->B, a->N, a->K, a->ldb, 64, BK)) return 1; }
+
+  const int tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int sms = num_sms();
+  TNR_REQUIRE(sms > 0, "tnr_gemm_bf16: no CUDA device");
+  const int grid = tiles < sms ? tiles : sms;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (BN == 256) return dispatch_major<256>(a_mn, b_mn, ta, tb, p, grid, st);
+  return dispatch_major<128>(a_mn, b_mn, ta, tb, p, grid, st);
+}

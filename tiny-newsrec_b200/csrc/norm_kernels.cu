@@ -1,0 +1,276 @@
+// HBM-bound row kernels of the encoder: embedding gather + LayerNorm, LayerNorm forward /
+// backward, column sums (bias gradients).  One warp per row, 16-byte vector loads, the row
+// lives in registers (E <= 1024), warp-shuffle reductions.
+#include "common.cuh"
+
+namespace tnr {
+
+constexpr int ROWS_PER_BLOCK = 8;   // 8 warps
+
+template <int VPL>   // 8-element vectors per lane: E = VPL * 256
+__device__ __forceinline__ void ln_row(float (&x)[VPL * 8], const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, int lane,
+                                       __nv_bfloat16* __restrict__ out) {
+  constexpr int E = VPL * 256;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL * 8; ++i) s += x[i];
+  const float mean = warp_sum(s) * (1.0f / E);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL * 8; ++i) { const float d = x[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / E) + eps);
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + col);
+    const float4 g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + col);
+    const float4 b1 = *reinterpret_cast<const float4*>(beta + col + 4);
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = (x[v * 8 + i] - mean) * rstd * g[i] + b[i];
+    *reinterpret_cast<bf16x8*>(out + col) = pack8(y);
+  }
+}
+
+// out[t, :] = LN(word[id[t]] + pos[t % L] + type[0])         (tnlrv3/modeling.py:168-177)
+// ids: int64, row n at ids + n * ids_ld, L tokens per row.  word table bf16 or fp32.
+template <int VPL, bool WORD_BF16>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+embed_ln_kernel(const int64_t* __restrict__ ids, int ids_ld, int L, int n_tokens, int vocab,
+                const void* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type0,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                __nv_bfloat16* __restrict__ out) {
+  constexpr int E = VPL * 256;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * ROWS_PER_BLOCK + warp;
+  if (t >= n_tokens) return;
+  const int n = t / L, l = t - n * L;
+  long long id = ids[(size_t)n * ids_ld + l];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);     // defensive clamp (torch would raise)
+  float x[VPL * 8];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    float w[8];
+    if (WORD_BF16) {
+      unpack8(*reinterpret_cast<const bf16x8*>(reinterpret_cast<const __nv_bfloat16*>(word) + (size_t)id * E + col), w);
+    } else {
+      const float* wp = reinterpret_cast<const float*>(word) + (size_t)id * E + col;
+      const float4 a = *reinterpret_cast<const float4*>(wp), b = *reinterpret_cast<const float4*>(wp + 4);
+      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    }
+    const float4 p0 = *reinterpret_cast<const float4*>(pos + (size_t)l * E + col);
+    const float4 p1 = *reinterpret_cast<const float4*>(pos + (size_t)l * E + col + 4);
+    const float4 t0 = *reinterpret_cast<const float4*>(type0 + col);
+    const float4 t1 = *reinterpret_cast<const float4*>(type0 + col + 4);
+    x[v * 8 + 0] = w[0] + p0.x + t0.x; x[v * 8 + 1] = w[1] + p0.y + t0.y;
+    x[v * 8 + 2] = w[2] + p0.z + t0.z; x[v * 8 + 3] = w[3] + p0.w + t0.w;
+    x[v * 8 + 4] = w[4] + p1.x + t1.x; x[v * 8 + 5] = w[5] + p1.y + t1.y;
+    x[v * 8 + 6] = w[6] + p1.z + t1.z; x[v * 8 + 7] = w[7] + p1.w + t1.w;
+  }
+  ln_row<VPL>(x, gamma, beta, eps, lane, out + (size_t)t * E);
+}
+
+// y = LN(x) for a bf16 "pre-LN" buffer (dense + bias + residual written by the GEMM epilogue)
+template <int VPL>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int rows, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y) {
+  constexpr int E = VPL * 256;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * ROWS_PER_BLOCK + warp;
+  if (r >= rows) return;
+  float v[VPL * 8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    unpack8(*reinterpret_cast<const bf16x8*>(x + (size_t)r * E + (i * 32 + lane) * 8), &v[i * 8]);
+  ln_row<VPL>(v, gamma, beta, eps, lane, y + (size_t)r * E);
+}
+
+// LayerNorm backward.  xhat recomputed from the saved pre-LN row.
+//   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+//   dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy      (fp32 atomics, one per column per block)
+// A persistent grid walks rows so each block flushes its partial sums once.
+template <int VPL>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, int rows,
+                     const float* __restrict__ gamma, float eps, __nv_bfloat16* __restrict__ dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int E = VPL * 256;
+  __shared__ float s_dg[E];
+  __shared__ float s_db[E];
+  for (int i = threadIdx.x; i < E; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float g_r[VPL * 8];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + col);
+    const float4 g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
+    g_r[v * 8 + 0] = g0.x; g_r[v * 8 + 1] = g0.y; g_r[v * 8 + 2] = g0.z; g_r[v * 8 + 3] = g0.w;
+    g_r[v * 8 + 4] = g1.x; g_r[v * 8 + 5] = g1.y; g_r[v * 8 + 6] = g1.z; g_r[v * 8 + 7] = g1.w;
+  }
+  float acc_dg[VPL * 8], acc_db[VPL * 8];
+#pragma unroll
+  for (int i = 0; i < VPL * 8; ++i) { acc_dg[i] = 0.f; acc_db[i] = 0.f; }
+
+  for (int r = blockIdx.x * ROWS_PER_BLOCK + warp; r < rows; r += gridDim.x * ROWS_PER_BLOCK) {
+    float xv[VPL * 8], dv[VPL * 8];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const size_t off = (size_t)r * E + (v * 32 + lane) * 8;
+      unpack8(*reinterpret_cast<const bf16x8*>(x + off), &xv[v * 8]);
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + off), &dv[v * 8]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL * 8; ++i) s += xv[i];
+    const float mean = warp_sum(s) * (1.0f / E);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL * 8; ++i) { xv[i] -= mean; q += xv[i] * xv[i]; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / E) + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL * 8; ++i) {
+      xv[i] *= rstd;                       // xhat
+      acc_dg[i] += dv[i] * xv[i];
+      acc_db[i] += dv[i];
+      dv[i] *= g_r[i];                     // g
+      sg += dv[i];
+      sgx += dv[i] * xv[i];
+    }
+    sg = warp_sum(sg) * (1.0f / E);
+    sgx = warp_sum(sgx) * (1.0f / E);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = rstd * (dv[v * 8 + i] - sg - xv[v * 8 + i] * sgx);
+      *reinterpret_cast<bf16x8*>(dx + (size_t)r * E + (v * 32 + lane) * 8) = pack8(o);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int col = (v * 32 + lane) * 8 + i;
+      atomicAdd(&s_dg[col], acc_dg[v * 8 + i]);
+      atomicAdd(&s_db[col], acc_db[v * 8 + i]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < E; i += blockDim.x) {
+    atomicAdd(dgamma + i, s_dg[i]);
+    atomicAdd(dbeta + i, s_db[i]);
+  }
+}
+
+// out[c] += sum_r x[r, c]   (bias gradients).  bf16 input, fp32 atomics; cols % 8 == 0.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols, int ld, float* __restrict__ out) {
+  // block handles a 64-column strip (8 lanes x 8 cols) and a row slab; 32 row-lanes per block
+  const int cgroup = threadIdx.x & 7;            // 8 column vectors of 8
+  const int rlane = threadIdx.x >> 3;            // 32 row lanes
+  const int col = (blockIdx.x * 8 + cgroup) * 8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (col < cols) {
+    for (int r = blockIdx.y * 32 + rlane; r < rows; r += gridDim.y * 32) {
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + (size_t)r * ld + col), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+  __shared__ float red[32][65];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[rlane][cgroup * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) s += red[r][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < cols) atomicAdd(out + c, s);
+  }
+}
+
+}  // namespace tnr
+
+using namespace tnr;
+
+#define DISPATCH_VPL(E, CALL)                                   \
+  switch ((E) / 256) {                                          \
+    case 1: { constexpr int VPL = 1; CALL; break; }             \
+    case 2: { constexpr int VPL = 2; CALL; break; }             \
+    case 3: { constexpr int VPL = 3; CALL; break; }             \
+    case 4: { constexpr int VPL = 4; CALL; break; }             \
+    default: set_error("hidden size %d not supported (need 256/512/768/1024)", (E)); return 1; \
+  }
+
+extern "C" __attribute__((visibility("default"))) int tnr_embed_ln_fwd(const int64_t* ids, int ids_ld, int n_rows, int L, int vocab, const void* word,
+                                int word_dtype, const float* pos, const float* type0, const float* gamma,
+                                const float* beta, float eps, int E, void* out_bf16, void* stream) {
+  TNR_REQUIRE(E % 256 == 0, "tnr_embed_ln_fwd: E=%d must be a multiple of 256", E);
+  TNR_REQUIRE(n_rows >= 0 && L > 0, "tnr_embed_ln_fwd: bad shape");
+  if (n_rows == 0) return 0;
+  const int n_tokens = n_rows * L;
+  const int grid = (n_tokens + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  if (word_dtype == TNR_BF16) {
+    DISPATCH_VPL(E, (embed_ln_kernel<VPL, true><<<grid, ROWS_PER_BLOCK * 32, 0, st>>>(
+                        ids, ids_ld, L, n_tokens, vocab, word, pos, type0, gamma, beta, eps, out)));
+  } else {
+    DISPATCH_VPL(E, (embed_ln_kernel<VPL, false><<<grid, ROWS_PER_BLOCK * 32, 0, st>>>(
+                        ids, ids_ld, L, n_tokens, vocab, word, pos, type0, gamma, beta, eps, out)));
+  }
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int tnr_layernorm_fwd(const void* x_bf16, int rows, int E, const float* gamma, const float* beta, float eps,
+                                 void* y_bf16, void* stream) {
+  if (rows == 0) return 0;
+  const int grid = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_VPL(E, (layernorm_fwd_kernel<VPL><<<grid, ROWS_PER_BLOCK * 32, 0, st>>>(
+                      reinterpret_cast<const __nv_bfloat16*>(x_bf16), rows, gamma, beta, eps,
+                      reinterpret_cast<__nv_bfloat16*>(y_bf16))));
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int tnr_layernorm_bwd(const void* dy_bf16, const void* x_bf16, int rows, int E, const float* gamma, float eps,
+                                 void* dx_bf16, float* dgamma, float* dbeta, void* stream) {
+  if (rows == 0) return 0;
+  int grid = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+  const int cap = num_sms() * 4;
+  if (grid > cap) grid = cap;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  DISPATCH_VPL(E, (layernorm_bwd_kernel<VPL><<<grid, ROWS_PER_BLOCK * 32, 0, st>>>(
+                      reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16),
+                      rows, gamma, eps, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta)));
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int tnr_colsum_bf16(const void* x_bf16, int rows, int cols, int ld, float* out, void* stream) {
+  TNR_REQUIRE(cols % 8 == 0 && ld % 8 == 0, "tnr_colsum_bf16: cols/ld must be multiples of 8");
+  if (rows == 0) return 0;
+  dim3 grid((cols + 63) / 64, 1);
+  int gy = (num_sms() * 8) / (int)grid.x;
+  if (gy < 1) gy = 1;
+  const int max_gy = (rows + 31) / 32;
+  grid.y = gy < max_gy ? gy : max_gy;
+  colsum_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x_bf16), rows, cols, ld, out);
+  TNR_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,158 @@
+"""Tensor-level wrappers over the C ABI (include/tinyrec.h).
+
+Every function takes CUDA torch tensors, checks dtype / layout, and enqueues the
+kernel on torch's current stream.  Torch is used only for device memory and
+streams.  No function here has a non-CUDA path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ACT_DGELU, ACT_GELU, ACT_NONE, ACT_TANH, BF16, F32, GemmArgs  # noqa: F401
+
+_bf16 = torch.bfloat16
+_f32 = torch.float32
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, dtype, name):
+    if t.dtype != dtype or not t.is_cuda:
+        raise _lib.TinyRecError(f"{name}: expected CUDA {dtype}, got {t.dtype} on {t.device}")
+    return t
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _ready(t):
+    _lib.require_device(t.device.index)
+    return _lib.load()
+
+
+def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, aux=None,
+         split_k=1, accumulate=False):
+    """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).
+
+    a: bf16 [M,K] (or [K,M] when ``a_t``); b: bf16 [N,K] (or [K,N] when ``b_t``); 2-D, unit
+    inner stride.  out: bf16 or fp32 [M,N].  See tnr_gemm_bf16 in include/tinyrec.h.
+    """
+    lib = _ready(a)
+    _chk(a, _bf16, "gemm.a"); _chk(b, _bf16, "gemm.b")
+    if a.stride(1) != 1 or b.stride(1) != 1 or out.stride(1) != 1:
+        raise _lib.TinyRecError("gemm: operands must have unit inner stride")
+    M, K = (a.shape[1], a.shape[0]) if a_t else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_t else (b.shape[0], b.shape[1])
+    if K != Kb or out.shape[0] != M or out.shape[1] != N:
+        raise _lib.TinyRecError(f"gemm: shape mismatch A{tuple(a.shape)} B{tuple(b.shape)} C{tuple(out.shape)} "
+                                f"a_t={a_t} b_t={b_t}")
+    g = GemmArgs()
+    g.M, g.N, g.K = M, N, K
+    g.A, g.lda, g.a_mn_major = a.data_ptr(), a.stride(0), int(a_t)
+    g.B, g.ldb, g.b_mn_major = b.data_ptr(), b.stride(0), int(b_t)
+    g.C, g.ldc = out.data_ptr(), out.stride(0)
+    if out.dtype == _bf16:
+        g.c_dtype = BF16
+    elif out.dtype == _f32:
+        g.c_dtype = F32
+    else:
+        raise _lib.TinyRecError("gemm: out must be bf16 or fp32")
+    g.bias = _chk(bias, _f32, "gemm.bias").data_ptr() if bias is not None else None
+    if residual is not None:
+        _chk(residual, _bf16, "gemm.residual")
+        g.residual, g.ldr = residual.data_ptr(), residual.stride(0)
+    g.act = act
+    if aux is not None:
+        _chk(aux, _bf16, "gemm.aux")
+        g.aux, g.ldaux = aux.data_ptr(), aux.stride(0)
+    g.split_k = split_k
+    g.accumulate = int(accumulate)
+    _lib.check(lib.tnr_gemm_bf16(ctypes.byref(g), _stream()), "tnr_gemm_bf16")
+    return out
+
+
+def embed_ln(x, L, word, pos, type0, gamma, beta, eps, out):
+    """x: int64 [n, 2L] (ids | mask) -> out bf16 [n*L, E]."""
+    lib = _ready(x)
+    _chk(x, torch.int64, "embed_ln.x")
+    n = x.shape[0]
+    E = word.shape[1]
+    wd = BF16 if word.dtype == _bf16 else F32
+    _lib.check(lib.tnr_embed_ln_fwd(_ptr(x), x.stride(0), n, L, word.shape[0], _ptr(word), wd,
+                                    _ptr(_chk(pos, _f32, "pos")), _ptr(_chk(type0, _f32, "type0")),
+                                    _ptr(_chk(gamma, _f32, "gamma")), _ptr(_chk(beta, _f32, "beta")),
+                                    eps, E, _ptr(_chk(out, _bf16, "out")), _stream()), "tnr_embed_ln_fwd")
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps, out):
+    lib = _ready(x)
+    rows, E = x.shape
+    _lib.check(lib.tnr_layernorm_fwd(_ptr(_chk(x, _bf16, "ln.x")), rows, E, _ptr(gamma), _ptr(beta), eps,
+                                     _ptr(_chk(out, _bf16, "ln.out")), _stream()), "tnr_layernorm_fwd")
+    return out
+
+
+def layernorm_bwd(dy, x, gamma, eps, dx, dgamma, dbeta):
+    lib = _ready(x)
+    rows, E = x.shape
+    _lib.check(lib.tnr_layernorm_bwd(_ptr(_chk(dy, _bf16, "ln.dy")), _ptr(_chk(x, _bf16, "ln.x")), rows, E,
+                                     _ptr(gamma), eps, _ptr(_chk(dx, _bf16, "ln.dx")),
+                                     _ptr(_chk(dgamma, _f32, "dgamma")), _ptr(_chk(dbeta, _f32, "dbeta")),
+                                     _stream()), "tnr_layernorm_bwd")
+    return dx
+
+
+def colsum(x, out):
+    lib = _ready(x)
+    _lib.check(lib.tnr_colsum_bf16(_ptr(_chk(x, _bf16, "colsum.x")), x.shape[0], x.shape[1], x.stride(0),
+                                   _ptr(_chk(out, _f32, "colsum.out")), _stream()), "tnr_colsum_bf16")
+    return out
+
+
+def attn_fwd(qkv, x, L, relpos, ctx, A):
+    """qkv bf16 [n*L, 3E]; x int64 [n, 2L] (mask = columns L..2L); relpos fp32 [A,L,L]."""
+    lib = _ready(qkv)
+    n = x.shape[0]
+    E = qkv.shape[1] // 3
+    mask_ptr = ctypes.c_void_p(x.data_ptr() + 8 * L)
+    _lib.check(lib.tnr_attn_relpos_fwd(_ptr(_chk(qkv, _bf16, "attn.qkv")), mask_ptr, x.stride(0),
+                                       _ptr(_chk(relpos, _f32, "relpos")), _ptr(_chk(ctx, _bf16, "ctx")),
+                                       n, L, A, E, _stream()), "tnr_attn_relpos_fwd")
+    return ctx
+
+
+def attn_bwd(qkv, x, L, relpos, dctx, dqkv, A):
+    lib = _ready(qkv)
+    n = x.shape[0]
+    E = qkv.shape[1] // 3
+    mask_ptr = ctypes.c_void_p(x.data_ptr() + 8 * L)
+    _lib.check(lib.tnr_attn_relpos_bwd(_ptr(_chk(qkv, _bf16, "attn.qkv")), mask_ptr, x.stride(0),
+                                       _ptr(relpos), _ptr(_chk(dctx, _bf16, "dctx")),
+                                       _ptr(_chk(dqkv, _bf16, "dqkv")), n, L, A, E, _stream()),
+               "tnr_attn_relpos_bwd")
+    return dqkv
+
+
+def attnpool_fwd(x, e, Q, w2, b2, mask, out, a_out, n, S):
+    """x bf16 [n*S, C]; e bf16 [n*S, ldq]; out bf16 [n, C]; a_out fp32 [n, S]."""
+    lib = _ready(x)
+    C = x.shape[1]
+    _lib.check(lib.tnr_attnpool_fwd(_ptr(_chk(x, _bf16, "pool.x")), _ptr(_chk(e, _bf16, "pool.e")), e.stride(0), Q,
+                                    _ptr(_chk(w2, _f32, "w2")), _ptr(_chk(b2, _f32, "b2")), _ptr(mask),
+                                    _ptr(_chk(out, _bf16, "pool.out")), _ptr(_chk(a_out, _f32, "a_out")),
+                                    n, S, C, _stream()), "tnr_attnpool_fwd")
+    return out
+
+
+def attnpool_bwd(x, e, Q, w2, a_in, dout, dx, du, dw2, db2, n, S):
+    lib = _ready(x)
+    C = x.shape[1]
+    _lib.check(lib.tnr_attnpool_bwd(_ptr(x), _ptr(e), e.stride(0), Q, _ptr(w2), _ptr(_chk(a_in, _f32, "a_in")),
+                                    _ptr(_chk(dout, _f32, "dout")), _ptr(_chk(dx, _bf16, "dx")),
+                                    _ptr(_chk(du, _bf16, "du")), _ptr(_chk(dw2, _f32, "dw2")),
+                                    _ptr(_chk(db2, _f32, "db2")), n, S, C, _stream()), "tnr_attnpool_bwd")
