@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the Tiny-NewsRec hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py --gpus N --steps K --warmup W [--workload kd4|kd2|table|eval] [--impl reference]
+
+Default workload ``kd4`` is BASELINE.json configs[1]: the 4-layer student, finetuning-stage
+multi-teacher KD step (forward 4 layers + backward layers {2,3} + fused Adam(amsgrad)), M=4
+teachers, per-GPU batch 32, history 50, npratio 4, title 30 tokens, bf16 compute, synthetic
+MIND-shaped data, random-init weights.  A "step" is one such train step on one batch.
+
+One JSON line is printed by rank 0.  ``value`` is device-timed whole-job impressions/s with
+inputs resident in HBM; ``e2e`` is the same metric through the public ``Model.forward`` API with
+pinned HOST inputs copied to the device every step and the loss read back.
+``--impl reference`` times the CPU oracle port of the reference (all host threads).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "kd4": dict(layers=4, trainable=[2, 3], name="Tiny-NewsRec 4-layer student finetuning-stage KD, M=4 teachers"),
+    "kd2": dict(layers=2, trainable=[0, 1], name="Tiny-NewsRec 2-layer student finetuning-stage KD, M=4 teachers"),
+}
+B, H, K, L, M, D, N_NEWS = 32, 50, 5, 30, 4, 256, 161013
+N_BATCHES = 8
+
+
+def flops_per_step(layers, n_train, tokens):
+    """per token per layer fwd 14 247 936 FLOP; bwd of a trainable layer 2x,
+    lowest trainable layer omits the QKV dgrad (3 538 944); heads 307 200 /token + 393 216 /news."""
+    fwd = 14247936 * layers
+    bwd = 28495872 * n_train - 3538944
+    return tokens * (fwd + bwd) + tokens * 307200 * 3 + (tokens // L) * 393216 * 3
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured"
+    except Exception:  # noqa: BLE001
+        return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- problem setup
+def make_inputs(rank, device):
+    """N_BATCHES distinct device-resident batches built with the device gather kernels, plus the
+    same tensors in pinned host memory for the e2e leg."""
+    import tinyrec.dataloader as dl
+    import tinyrec.synth as synth
+    news = synth.news_table(N_NEWS, L=L, seed=1234)
+    g = torch.Generator(device=device).manual_seed(4321)
+    teachers = [(torch.randn(N_NEWS + 1, D, generator=g, device=device) * 0.1) for _ in range(M)]
+    tables = dl.DeviceTables(news, [], device)
+    tables.teachers = teachers
+    hist_idx, hmask, cand_idx, label = synth.train_impressions(B * N_BATCHES, N_NEWS, H, K, seed=1234 + rank)
+    batcher = dl.TrainBatcher(tables, B, H, K)
+    dev_batches, host_batches = [], []
+    for i in range(N_BATCHES):
+        sl = slice(i * B, (i + 1) * B)
+        hi = torch.from_numpy(hist_idx[sl]).to(device)
+        ci = torch.from_numpy(cand_idx[sl]).to(device)
+        history, candidate, th, tc = batcher.assemble(hi, ci)
+        batch = (history.clone(), torch.from_numpy(hmask[sl]).to(device), candidate.clone(),
+                 torch.from_numpy(label[sl]).to(device), [t.clone() for t in th], [t.clone() for t in tc])
+        dev_batches.append(batch)
+        pin = lambda t: t.cpu().pin_memory()  # noqa: E731
+        host_batches.append((pin(batch[0]), pin(batch[1]), pin(batch[2]), pin(batch[3]), [pin(t) for t in batch[4]],
+                             [pin(t) for t in batch[5]]))
+    return dev_batches, host_batches
+
+
+def make_model(layers, trainable, device):
+    import tinyrec.model_bert as mb
+    import tinyrec.synth as synth
+    args = synth.demo_args(num_student_layers=layers, num_teachers=M, bert_trainable_layer=trainable)
+    torch.manual_seed(0)
+    model = mb.Model(args)
+    model.load_state_dict(synth.kd_model_state(layers, M, 0), strict=True)
+    model.to(device)
+    for p in model.teachers.parameters():                       # run.py:101-112
+        p.requires_grad = False
+    bm = model.student.news_encoder.bert_model
+    for p in bm.parameters():
+        p.requires_grad = False
+    for i, layer in enumerate(bm.bert.encoder.layer):
+        if i in trainable:
+            for p in layer.parameters():
+                p.requires_grad = True
+    return model, args
+
+
+def bytes_of(batch):
+    n = 0
+    for t in batch[:4]:
+        n += t.numel() * t.element_size()
+    for lst in batch[4:]:
+        for t in lst:
+            n += t.numel() * t.element_size()
+    return n
+
+
+# ----------------------------------------------------------------------------- CPU legs (oracle)
+def oracle_train_step_fn(layers, trainable, b_sample, seed=0):
+    """Reference algorithm on CPU (oracle port): forward + backward + Adam(amsgrad) for b_sample
+    impressions at the workload's shape.  Returns a callable running one step."""
+    import tinyrec.synth as synth
+    from oracle import model as om, optim as oopt
+    sd = synth.kd_model_state(layers, M, 0)
+    keys = om.trainable_keys(sd, trainable)
+    for k in keys:
+        sd[k].requires_grad_(True)
+    news = synth.news_table(5000, L=L, seed=1234)
+    tabs = synth.teacher_tables(5000, M, D, seed=1234)
+    hist_idx, hmask, cand_idx, label = synth.train_impressions(b_sample, 5000, H, K, seed=seed)
+    history = torch.from_numpy(news[hist_idx].astype(np.int64))
+    candidate = torch.from_numpy(news[cand_idx].astype(np.int64))
+    th = [torch.from_numpy(t[hist_idx]) for t in tabs]
+    tc = [torch.from_numpy(t[cand_idx]) for t in tabs]
+    state = {k: [torch.zeros_like(sd[k]) for _ in range(3)] for k in keys}
+    step = [0]
+
+    def run():
+        for k in keys:
+            sd[k].grad = None
+        total = om.kd_model_forward(sd, history, torch.from_numpy(hmask), candidate, torch.from_numpy(label), th, tc,
+                                    layers, False, 1.0, 0.2)[0]
+        total.backward()
+        step[0] += 1
+        with torch.no_grad():
+            for k in keys:
+                m_, v_, vm_ = state[k]
+                oopt.adam_amsgrad_step(sd[k], sd[k].grad, m_, v_, vm_, step[0], lr=1e-4)
+        return float(total)
+    return run
+
+
+def cpu_baseline(layers, trainable, budget_s=20.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    b_sample = 4
+    fn = oracle_train_step_fn(layers, trainable, b_sample)
+    t0 = time.perf_counter()
+    fn()
+    t1 = time.perf_counter() - t0
+    reps = max(1, min(3, int(budget_s / max(t1, 1e-3)) - 1))
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts)) if ts else t1
+    return {"value": b_sample / t, "unit": "impressions/s", "cores": cores, "kind": "port",
+            "sample": f"{1 + reps} train steps (fwd+bwd+Adam) of {b_sample} impressions at the workload shape, fp32 torch CPU oracle",
+            "seconds_per_step": t}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[a.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # size the per-step sample so that (steps + warmup) steps finish within a few minutes
+    probe = oracle_train_step_fn(wl["layers"], wl["trainable"], 2)
+    t0 = time.perf_counter(); probe(); per_imp = (time.perf_counter() - t0) / 2.0
+    budget = 150.0 / max(1, a.steps + a.warmup)
+    b_sample = int(max(1, min(B, budget / max(per_imp, 1e-4))))
+    fn = oracle_train_step_fn(wl["layers"], wl["trainable"], b_sample)
+    for _ in range(a.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    val = b_sample * a.steps / dt
+    line = {"impl": "reference", "metric": "kd_train_impressions_per_sec", "value": val, "unit": "impressions/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(a.workload, 1, b_sample),
+            "cpu_baseline": {"value": val, "unit": "impressions/s", "cores": cores, "kind": "port",
+                             "sample": f"{b_sample} impressions per step (of {B}) at the workload shape; oracle port of the "
+                                       "reference modules (the Python reference cannot travel to the GPU box)"},
+            "e2e": {"value": val, "unit": "impressions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(workload, n, batch=B):
+    wl = WORKLOADS[workload]
+    return {"workload": wl["name"], "student_layers": wl["layers"], "trainable_layers": wl["trainable"],
+            "per_gpu_batch": batch, "global_batch": batch * n, "history": H, "npratio": K - 1, "title_tokens": L,
+            "teachers": M, "news_dim": D, "vocab": 30522, "parallelism": f"dp{n}",
+            "l2": "per-step activation working set (~5 GB) >> 126 MB L2; 8 rotating input batches",
+            "dropout": "off (eval-mode parity; see DESIGN.md)"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_tinyrec(a):
+    import torch.distributed as dist
+    import tinyrec.ops as ops
+    import tinyrec.optim as topt
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus > 1 and world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} needs torchrun with {a.gpus} ranks (WORLD_SIZE={world})")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    wl = WORKLOADS[a.workload]
+    model, margs = make_model(wl["layers"], wl["trainable"], device)
+    opt = topt.Adam(model, lr=1e-4)
+    if world > 1:
+        topt.broadcast_parameters(model, 0)
+        opt = topt.DistributedOptimizer(opt)
+    dev_batches, host_batches = make_inputs(rank, device)
+
+    def step(batch):
+        opt.zero_grad()
+        out = model(*batch)
+        out[0].backward()
+        opt.step()
+        return out[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(a.warmup, 3)):
+        step(dev_batches[i % N_BATCHES])
+    barrier()
+    # ---- device-timed region (inputs resident in HBM)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.stats.gemm_events = []
+    launches0 = ops.stats.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(a.steps):
+        step(dev_batches[i % N_BATCHES])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.stats.launches - launches0
+    gemm_events, ops.stats.gemm_events = ops.stats.gemm_events, None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = B * world * a.steps / (ms / 1e3)
+
+    # ---- e2e: host (pinned) inputs -> H2D every step -> public API -> loss read back
+    def e2e_step(hb):
+        batch = (hb[0].to(device, non_blocking=True), hb[1].to(device, non_blocking=True),
+                 hb[2].to(device, non_blocking=True), hb[3].to(device, non_blocking=True),
+                 [t.to(device, non_blocking=True) for t in hb[4]], [t.to(device, non_blocking=True) for t in hb[5]])
+        return float(step(batch).item())
+    for i in range(3):
+        e2e_step(host_batches[i % N_BATCHES])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        e2e_step(host_batches[i % N_BATCHES])
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = B * world * a.steps / float(t.item())
+
+    if rank == 0:
+        peak_tf, peak_bw, how = peaks()
+        gflop = sum(f for f, _, _ in gemm_events)
+        gms = sum(s.elapsed_time(e) for _, s, e in gemm_events)
+        ach = gflop / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+        tokens = B * (H + K) * L
+        algo = flops_per_step(wl["layers"], len(wl["trainable"]), tokens)
+        line = {"metric": "kd_train_impressions_per_sec", "value": value, "unit": "impressions/s", "n_gpus": world,
+                "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": config_dict(a.workload, world), "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": "impressions/s", "h2d_bytes_per_step": bytes_of(host_batches[0]),
+                        "d2h_bytes_per_step": 4},
+                "gpu_launches": launches,
+                "roofline": {"bound": "tensor", "kernel": "tnr::gemm::gemm_kernel (tcgen05, all GEMM launches of the step)",
+                             "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                             "peak_source": f"{how} bf16_tflops_sustained", "traffic": None,
+                             "gemm_launches_per_step": len(gemm_events) / a.steps,
+                             "gemm_ms_per_step": gms / a.steps,
+                             "gemm_share_of_step": gms / ms if ms > 0 else None,
+                             "algorithmic_tflop_per_step": algo / 1e12,
+                             "step_frac_of_tensor_roofline": (algo / 1e12) / (ms / a.steps * 1e-3) / peak_tf}}
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl["layers"], wl["trainable"])
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="tinyrec", choices=["tinyrec", "reference"])
+    ap.add_argument("--workload", default="kd4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_tinyrec(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -111,6 +111,70 @@ int tnr_attnpool_bwd(const void* x_bf16, const void* e_bf16, int ldq, int Q, con
                      const float* a_in, const float* dout, void* dx_bf16, void* du_bf16, float* dw2,
                      float* db2, int n, int S, int C, void* stream);
 
+/* ------------------------------------------------- user encoder / scoring / KD loss (fp32) */
+/* Additive-attention user encoder, NAML branch.  vecs fp32 [B,H,D], mask fp32 [B,H].
+ *   use_mask = 0 (args.user_log_mask False): v = vec*m + pad_doc*(1-m), unmasked pooling
+ *   use_mask = 1: masked pooling (alpha *= m).  All-masked history -> exactly 0.
+ * user fp32 [B,D]; a_out [B,H] normalised weights; e_out [B,H,Q] tanh activations (or NULL).
+ * Replaces UserEncoder.forward, Tiny-NewsRec/model_bert.py:155-176 (+ AttentionPooling :15-34). */
+int tnr_user_encoder_fwd(const float* vecs, const float* mask, const float* pad_doc, const float* W1,
+                         const float* b1, const float* w2, const float* b2, int use_mask, float* user,
+                         float* a_out, float* e_out, int B, int H, int D, int Q, void* stream);
+/* d_user [B,D] -> d_vecs += [B*H, D]; dpad/dW1/db1/dw2/db2 += (fp32 atomics). */
+int tnr_user_encoder_bwd(const float* vecs, const float* mask, const float* pad_doc, const float* W1,
+                         const float* w2, int use_mask, const float* a_in, const float* e_in,
+                         const float* d_user, float* d_vecs, float* dpad, float* dW1, float* db1,
+                         float* dw2, float* db2, int B, int H, int D, int Q, void* stream);
+
+/* Click score + CE + multi-teacher KD loss and its gradients in one pass.
+ * Row layout of the [R, D] news matrices: history block (b,h) -> b*H+h, then candidate block
+ * (b,k) -> B*H + b*K + k; teacher matrices T_ext / TP_ext / G_ext are [M, B*(H+K)+B, D] with the
+ * B per-impression user rows appended (raw / projected by transform_matrix / gradient).
+ * losses[0..2] += {distill, emb, target} batch means; score_out [B,K];
+ * if want_grad: d_news [R,D] (assigned), d_user [B,D], G_ext (grad w.r.t. TP_ext).
+ * M == 0 gives the PLM-NR loss (CE only, coef scales it).
+ * Replaces Model.forward, Tiny-NewsRec/model_bert.py:262-306 (+ kd_ce_loss :208-219,
+ * hid_mse_loss :222-244, score :204) and its autograd backward. */
+int tnr_kd_loss_fwdbwd(const float* s_news, const float* s_user, const int64_t* label,
+                       const float* T_ext, const float* TP_ext, int M, int B, int H, int K, int D,
+                       float temperature, float coef, int want_grad, float* score_out, float* losses,
+                       float* d_news, float* d_user, float* G_ext, void* stream);
+
+/* Small batched fp32 GEMMs for transform_matrix (model_bert.py:277-278,283):
+ *   nt:     C[b][M,N]  = A[b][M,K] . B[b][N,K]^T + bias[b][N]
+ *   tn_acc: C[b][N1,N2] += A[b][R,N1]^T . B[b][R,N2];  cbias[b][N1] += colsum(A[b])   */
+int tnr_sgemm_nt(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
+                 int batch, long long sA, long long sB, long long sbias, long long sC, void* stream);
+int tnr_sgemm_tn_acc(const float* A, const float* B, float* C, float* cbias, int R, int N1, int N2,
+                     int batch, long long sA, long long sB, long long sC, long long sbias, void* stream);
+
+/* ------------------------------------------------------------------ optimiser */
+/* Adam(amsgrad=True) on a flat fp32 buffer (torch.optim.Adam semantics, run.py:134) fused with
+ * the bf16 shadow-weight refresh; grad_scale pre-multiplies g. */
+int tnr_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, void* shadow_bf16,
+                     long long n, float lr, float beta1, float beta2, float eps, int step,
+                     float grad_scale, void* stream);
+int tnr_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);
+
+/* ------------------------------------------------------------------ batch assembly */
+/* out[r,:] = (int64) table[idx[r], :]   (news_combined[idx] -> LongTensor, dataloader.py:131,138,152-156);
+ * idx outside [0, n_rows_table) maps to row 0 (dataloader.py:74).  Bit-exact. */
+int tnr_gather_rows_i32_i64(const int32_t* table, long long n_rows_table, const int32_t* idx,
+                            long long n, int W, int64_t* out, void* stream);
+/* out[r, :D] = table[idx[r], :]  fp32 (teacher_embs[i][idx], dataloader.py:142,144; news_scoring[idx] :295,301). */
+int tnr_gather_rows_f32(const float* table, long long n_rows_table, const int32_t* idx, long long n,
+                        int D, float* out, long long out_ld, void* stream);
+
+/* ------------------------------------------------------------------ impression scoring */
+/* Per impression b: score_c = table[cand[ptr[b]+c]] . user[b]; AUC / MRR / nDCG@5 / nDCG@10 with
+ * binary labels; impressions with constant labels are skipped (valid = 0).
+ * per_imp double [n_imp, 5] = {auc, mrr, ndcg5, ndcg10, valid}; sums double [5] += column sums
+ * (NULL to skip); score_out fp32 [nnz] or NULL.
+ * Replaces the Python loop at Tiny-NewsRec/run.py:346-361 + metrics.py:5-23 + sklearn roc_auc_score. */
+int tnr_eval_metrics(const float* table, const float* user, const long long* ptr, const int32_t* cand,
+                     const int8_t* label, long long n_imp, int D, int max_c, double* per_imp,
+                     double* sums, float* score_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,193 @@
+"""CPU-only tests: the C-ABI library builds, loads and exports every symbol the header
+declares; host-side logic (index parsing / padding, rel-pos buckets, synthetic init,
+state_dict keys, sharding + collectives over gloo with world_size 2)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    import __graft_entry__ as ge
+    import tinyrec._lib as L
+    if not os.path.exists(L.LIB_PATH):
+        ge.build()
+    return L.LIB_PATH
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "tinyrec.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(tnr_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_header_symbol(built_lib):
+    import tinyrec._lib as L
+    out = subprocess.run(["nm", "-D", "--defined-only", built_lib], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (tnr_[a-z0-9_]+)", out))
+    declared = _header_symbols()
+    assert declared, "no declarations parsed from include/tinyrec.h"
+    missing = [s for s in declared if s not in exported]
+    assert not missing, f"declared in tinyrec.h but not exported: {missing}"
+    assert sorted(L.exported_names()) == declared, "ctypes binding table and header disagree"
+    lib = L.load()
+    assert lib.tnr_abi_version() == 1
+
+
+def test_ops_fail_loudly_without_cuda(built_lib):
+    import tinyrec._lib as L
+    import tinyrec.ops as ops
+    a = torch.zeros(64, 64, dtype=torch.bfloat16)
+    with pytest.raises(L.TinyRecError):
+        ops.gemm(a, a, torch.zeros(64, 64, dtype=torch.bfloat16))
+    import tinyrec.model_bert as mb
+    import tinyrec.synth as synth
+    ne = mb.NewsEncoder(synth.demo_args(num_student_layers=1))
+    with pytest.raises(L.TinyRecError):
+        ne(torch.zeros(2, 60, dtype=torch.int64))       # CPU tensor -> no fallback
+
+
+def test_missing_library_is_an_error(monkeypatch, tmp_path):
+    import tinyrec._lib as L
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(L.TinyRecError):
+        L.load()
+
+
+def test_relpos_bucket_table_matches_reference(golden):
+    from tinyrec.engine import rel_pos_bucket_table
+    g = golden("relpos")
+    lut = dict(zip(g["rel"].tolist(), g["bucket"].tolist()))
+    for L in (1, 9, 30, 32, 180, 512):
+        t = rel_pos_bucket_table(L)
+        pos = np.arange(L)
+        rel = pos[None, :] - pos[:, None]
+        want = np.vectorize(lut.get)(rel)
+        assert np.array_equal(t.numpy(), want)
+
+
+def test_state_dict_keys_match_reference_layout():
+    import tinyrec.model_bert as mb
+    import tinyrec.model_bert_2 as mb2
+    import tinyrec.synth as synth
+    m = mb.Model(synth.demo_args(num_student_layers=4, num_teachers=4))
+    want = synth.kd_model_state(4, 4, 0)
+    got = m.state_dict()
+    assert list(got.keys()) == list(want.keys())           # names AND order (113 keys)
+    assert len(got) == 113
+    for k in want:
+        assert tuple(got[k].shape) == tuple(want[k].shape), k
+    t = mb2.ModelBert(synth.demo_args(num_hidden_layers=2))
+    assert list(t.state_dict().keys()) == list(synth.model_bert_state("", 2, 0).keys())
+    # attribute paths used by run.py:101-112,285,343,442
+    assert len(m.student.news_encoder.bert_model.bert.encoder.layer) == 4
+    assert hasattr(m.student, "user_encoder") and hasattr(m, "teachers") and hasattr(m, "transform_matrix")
+    n_train = 0
+    for p in m.teachers.parameters():
+        p.requires_grad = False
+    for p in m.student.news_encoder.bert_model.parameters():
+        p.requires_grad = False
+    for i in (2, 3):
+        for p in m.student.news_encoder.bert_model.bert.encoder.layer[i].parameters():
+            p.requires_grad = True
+    trainable = [p for p in m.parameters() if p.requires_grad]
+    assert len(trainable) == 51 and sum(p.numel() for p in trainable) == 14841634
+
+
+def test_loader_index_logic_bit_exact(golden):
+    import random
+    import tinyrec.dataloader as dl
+    g = golden("batching")
+    H, npratio = int(g["H"]), int(g["npratio"])
+    n_news = g["news_combined"].shape[0] - 1
+    news_index = {f"N{i}": i for i in range(1, n_news + 1)}
+    random.seed(123)
+    hist, masks, cands, labels = [], [], [], []
+    for clicks, pos, neg in zip(g["clicks"], g["pos"], g["neg"]):
+        line = "\t".join(["0", "U1", "t", str(clicks), str(pos), str(neg)]).encode()
+        h, m, c, lab = dl.parse_train_line(line, news_index, H, npratio)
+        hist.append(h); masks.append(m); cands.append(c); labels.append(lab)
+    assert np.array_equal(g["news_combined"][np.array(hist)].astype(np.int64), g["user_feature"])
+    assert np.array_equal(g["news_combined"][np.array(cands)].astype(np.int64), g["news_feature"])
+    assert np.array_equal(np.array(masks, dtype=np.float32), g["log_mask"])
+    assert np.array_equal(np.array(labels), g["label"])
+    assert dl.pad_to_fix_len([1, 2, 3], 2) == ([2, 3], [1, 1])
+    assert dl.pad_to_fix_len([], 3) == ([0, 0, 0], [0, 0, 0])
+    h, m, c, labs = dl.parse_eval_line("1\tU\tt\tN1 N2\tN3-1 N4-0 NX-0", news_index, 4)
+    assert h == [0, 0, 1, 2] and m == [0, 0, 1, 1] and c == [3, 4, 0] and labs == [1, 0, 0]
+
+
+def test_synth_shapes_and_determinism():
+    import tinyrec.synth as synth
+    t = synth.news_table(100, L=30, seed=1)
+    assert t.shape == (101, 60) and t.dtype == np.int32 and not t[0].any()
+    assert (t[1:, 0] == 101).all() and ((t[:, :30] > 0) == (t[:, 30:] == 1)).all()
+    h, m, c, y = synth.train_impressions(64, 100, 50, 5, seed=2)
+    assert h.shape == (64, 50) and ((h > 0) == (m > 0)).all() and (m[:, -1] == 1).all()
+    assert c.shape == (64, 5) and y.max() < 5
+    hh, mm, ptr, cand, lab = synth.eval_impressions(200, 100, seed=3)
+    for i in range(200):
+        seg = lab[ptr[i]:ptr[i + 1]]
+        assert 0 < seg.sum() < len(seg)
+    a = synth.kd_model_state(1, 1, 0)["student.news_encoder.dense.weight"]
+    b = synth.kd_model_state(1, 1, 0)["student.news_encoder.dense.weight"]
+    assert torch.equal(a, b)
+
+
+def test_shard_helpers():
+    import tinyrec.parallel as par
+    assert par.shard_files(list("abcdefg"), 1, 3) == ["b", "e"]
+    cover = []
+    for r in range(8):
+        lo, hi = par.shard_rows(161014, r, 8)
+        cover += list(range(lo, hi))[:1] + [hi]
+    assert par.shard_rows(161014, 0, 8)[0] == 0 and par.shard_rows(161014, 7, 8)[1] == 161014
+    assert sum(par.shard_rows(10, r, 4)[1] - par.shard_rows(10, r, 4)[0] for r in range(4)) == 10
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+import tinyrec.parallel as par
+from oracle import optim as oopt
+world, rank, local = par.init_distributed(backend="gloo")
+assert world == 2
+g = torch.Generator().manual_seed(7)
+grads = [torch.randn(1000, generator=g) for _ in range(2)]          # identical on both ranks
+mine = grads[rank].clone()
+par.allreduce_mean_(mine)
+assert torch.allclose(mine, oopt.allreduce_average(grads), atol=1e-7)
+# SUM all-reduce + grad_scale = 1/world (what DistributedOptimizer does) == average
+s = grads[rank].clone(); par.allreduce_sum_(s)
+assert torch.allclose(s * 0.5, oopt.allreduce_average(grads), atol=1e-7)
+# table build: shard rows, all-gather, equals the unsharded table
+table = torch.arange(11 * 4, dtype=torch.float32).reshape(11, 4)
+lo, hi = par.shard_rows(11, rank, world)
+full = par.allgather_rows(table[lo:hi].clone(), 11)
+assert torch.equal(full, table)
+# eval reduction (run.py:372-379): sums over ranks / total count
+mean, total = par.reduce_eval_sums(3 + rank, torch.tensor([1.0, 2.0, 3.0, 4.0]) * (rank + 1))
+assert total == 7 and torch.allclose(mean, torch.tensor([3.0, 6.0, 9.0, 12.0], dtype=torch.float64) / 7)
+assert par.shard_files(list(range(5)), rank, world) == list(range(rank, 5, 2))
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_collectives(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                       capture_output=True, text=True, timeout=240, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ok 0" in r.stdout and "ok 1" in r.stdout

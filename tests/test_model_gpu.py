@@ -1,0 +1,284 @@
+"""GPU parity tests of the module-level API (drop-in boundary) against
+(a) the golden vectors produced by the real reference code (tests/golden/*.npz) and
+(b) the CPU oracle on seeded synthetic inputs.
+
+Tolerances: bf16 compute path -> 1e-2 relative (BASELINE.json north_star) on logits /
+embeddings / losses; gradients 3e-2 relative in norm (bf16 activations and grads);
+bit-exact for gathers; 1e-3 absolute for ranking metrics (they are exact in practice)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(got, ref):
+    got = torch.as_tensor(got).float().cpu()
+    ref = torch.as_tensor(ref).float().cpu()
+    return float((got - ref).norm() / (ref.norm() + 1e-12))
+
+
+def _grad_err(name, got, ref, named):
+    """Relative gradient error.  d loss / d key.bias is identically zero (softmax is invariant to a
+    per-query constant q.b_k), so both sides hold rounding noise: measure it against the query-bias
+    gradient scale instead of against itself."""
+    got = torch.as_tensor(got).float().cpu()
+    ref = torch.as_tensor(ref).float().cpu()
+    if name.endswith("attention.self.key.bias"):
+        scale = named[name.replace("key.bias", "query.bias")].grad.float().norm().cpu()
+        return float((got - ref).norm() / (scale + 1e-12))
+    return float((got - ref).norm() / (ref.norm() + 1e-12))
+
+
+def _apply_freeze(model, trainable_layers, student=True):
+    """run.py:101-112"""
+    if student:
+        for p in model.teachers.parameters():
+            p.requires_grad = False
+        bm = model.student.news_encoder.bert_model
+    else:
+        bm = model.news_encoder.bert_model
+    for p in bm.parameters():
+        p.requires_grad = False
+    for i, layer in enumerate(bm.bert.encoder.layer):
+        if i in trainable_layers:
+            for p in layer.parameters():
+                p.requires_grad = True
+
+
+def test_news_encoder_vs_reference_golden(golden):
+    import tinyrec.model_bert as mb
+    import tinyrec.synth as synth
+    g = golden("encoder")
+    layers = int(g["layers"])
+    sd = synth.model_bert_state("", layers, int(g["seed"]), noisy=True)
+    sd = {k[len("news_encoder."):]: v for k, v in sd.items() if k.startswith("news_encoder.")}
+    ne = mb.NewsEncoder(synth.demo_args(num_student_layers=layers))
+    ne.load_state_dict(sd, strict=True)
+    ne.cuda().eval()
+    with torch.no_grad():
+        vec = ne(torch.from_numpy(g["x"]).cuda())
+    assert _rel(vec, g["news_vec"]) < 1e-2
+    assert torch.isfinite(vec).all()
+
+
+@pytest.mark.parametrize("tag,ulm", [("pad", False), ("mask", True)])
+def test_model_bert_vs_reference_golden(golden, tag, ulm):
+    import tinyrec.model_bert as mb
+    import tinyrec.synth as synth
+    g = golden("modelbert")
+    layers = int(g["layers"])
+    H = g["history"].shape[1]
+    m = mb.ModelBert(synth.demo_args(num_student_layers=layers, user_log_length=H, user_log_mask=ulm))
+    m.load_state_dict(synth.model_bert_state("", layers, int(g["seed"]), noisy=True), strict=True)
+    m.cuda().eval()
+    with torch.no_grad():
+        score, hv, cv, uv = m(torch.from_numpy(g["history"]).cuda(), torch.from_numpy(g["history_mask"]).cuda(),
+                              torch.from_numpy(g["candidate"]).cuda())
+    assert _rel(hv, g[f"hist_{tag}"]) < 1e-2
+    assert _rel(cv, g[f"cand_{tag}"]) < 1e-2
+    assert _rel(uv, g[f"user_{tag}"]) < 1e-2
+    assert _rel(score, g[f"score_{tag}"]) < 2e-2
+    if ulm:
+        assert float(uv[1].abs().max()) == 0.0          # fully masked history -> exact zeros
+
+
+def test_plmnr_loss_vs_reference_golden(golden):
+    import tinyrec.model_bert_2 as mb2
+    import tinyrec.synth as synth
+    g = golden("modelbert")
+    layers = int(g["layers"])
+    H = g["history"].shape[1]
+    m = mb2.ModelBert(synth.demo_args(num_hidden_layers=layers, user_log_length=H, user_log_mask=False))
+    m.load_state_dict(synth.model_bert_state("", layers, int(g["seed"]), noisy=True), strict=True)
+    m.cuda().eval()
+    _apply_freeze(m, [0], student=False)
+    with torch.no_grad():
+        loss, score = m(torch.from_numpy(g["history"]).cuda(), torch.from_numpy(g["history_mask"]).cuda(),
+                        torch.from_numpy(g["candidate"]).cuda(), torch.from_numpy(g["plmnr_label"]).cuda())
+    assert abs(float(loss) - float(g["plmnr_loss"])) < 1e-2 * abs(float(g["plmnr_loss"])) + 1e-3
+    assert _rel(score, g["plmnr_score"]) < 2e-2
+
+
+def _kd_model(g, ulm):
+    import tinyrec.model_bert as mb
+    import tinyrec.synth as synth
+    layers, M = int(g["layers"]), int(g["M"])
+    H = g["history"].shape[1]
+    m = mb.Model(synth.demo_args(num_student_layers=layers, user_log_length=H, user_log_mask=ulm, num_teachers=M,
+                                 temperature=float(g["temperature"]), coef=float(g["coef"])))
+    m.load_state_dict(synth.kd_model_state(layers, M, int(g["seed"]), noisy=True), strict=True)
+    m.cuda()
+    _apply_freeze(m, [int(i) for i in g["trainable"]])
+    inputs = (torch.from_numpy(g["history"]).cuda(), torch.from_numpy(g["history_mask"]).cuda(),
+              torch.from_numpy(g["candidate"]).cuda(), torch.from_numpy(g["label"]).cuda(),
+              [torch.from_numpy(g[f"th{i}"]).cuda() for i in range(M)], [torch.from_numpy(g[f"tc{i}"]).cuda() for i in range(M)])
+    return m, inputs
+
+
+@pytest.mark.parametrize("tag,ulm", [("pad", False), ("mask", True)])
+def test_kd_forward_vs_reference_golden(golden, tag, ulm):
+    g = golden("kd")
+    m, inputs = _kd_model(g, ulm)
+    with torch.no_grad():
+        res = m(*inputs)
+    for v, nm in zip(res[:4], ("total", "distill", "emb", "target")):
+        ref = float(g[f"{nm}_{tag}"])
+        assert abs(float(v) - ref) < 1e-2 * abs(ref) + 1e-4, (nm, float(v), ref)
+    assert _rel(res[4], g[f"score_{tag}"]) < 2e-2
+
+
+def test_kd_gradients_vs_reference_golden(golden):
+    g = golden("kd")
+    m, inputs = _kd_model(g, False)
+    total = m(*inputs)[0]
+    total.backward()
+    named = dict(m.named_parameters())
+    worst = 0.0
+    for k in [str(s) for s in g["trainable_names"]]:
+        gr = named[k].grad
+        assert gr is not None, k
+        if f"gfull/{k}" in g.files:
+            ref = torch.from_numpy(g[f"gfull/{k}"])
+            r = _grad_err(k, gr.reshape(ref.shape), ref, named)
+        else:
+            ref = torch.from_numpy(g[f"gslice/{k}"])
+            r = _grad_err(k, gr[:16, :16], ref, named)
+        worst = max(worst, r)
+        assert r < 5e-2, (k, r)
+        ref_abs = float(g[f"gabs/{k}"])
+        if not k.endswith("key.bias"):
+            assert abs(float(gr.double().abs().sum()) - ref_abs) < 3e-2 * ref_abs + 1e-7, k
+    # frozen parameters got no gradient
+    for k, p in named.items():
+        if not p.requires_grad:
+            assert p.grad is None
+    # a second backward accumulates (optimizer.zero_grad() semantics are the caller's)
+    g1 = named["transform_matrix.0.weight"].grad.clone()
+    m(*inputs)[0].backward()
+    assert _rel(named["transform_matrix.0.weight"].grad, 2 * g1) < 1e-3
+
+
+def test_kd_step_vs_oracle_at_demo_shape():
+    """B=4 impressions at the demo shape (H=50, K=5, L=30, M=4, 2 layers, layer 1 trainable):
+    CUDA path vs the CPU oracle on the same seeded inputs; losses, scores and gradients."""
+    import tinyrec.model_bert as mb
+    import tinyrec.synth as synth
+    from oracle import model as om
+    B, H, K, L, M, layers, D = 4, 50, 5, 30, 4, 2, 256
+    news = synth.news_table(500, L=L, seed=3)
+    hist_idx, hmask, cand_idx, label = synth.train_impressions(B, 500, H, K, seed=4)
+    tables = synth.teacher_tables(500, M, D, seed=5)
+    history = torch.from_numpy(news[hist_idx].astype(np.int64))
+    candidate = torch.from_numpy(news[cand_idx].astype(np.int64))
+    th = [torch.from_numpy(t[hist_idx]) for t in tables]
+    tc = [torch.from_numpy(t[cand_idx]) for t in tables]
+    sd = synth.kd_model_state(layers, M, 11, noisy=True)
+    args = synth.demo_args(num_student_layers=layers, num_teachers=M)
+    m = mb.Model(args)
+    m.load_state_dict(sd, strict=True)
+    m.cuda()
+    _apply_freeze(m, [1])
+    res = m(history.cuda(), torch.from_numpy(hmask).cuda(), candidate.cuda(), torch.from_numpy(label).cuda(),
+            [t.cuda() for t in th], [t.cuda() for t in tc])
+    res[0].backward()
+    keys = om.trainable_keys(sd, [1])
+    osd = {k: v.clone().requires_grad_(k in keys) for k, v in sd.items()}
+    ref = om.kd_model_forward(osd, history, torch.from_numpy(hmask), candidate, torch.from_numpy(label), th, tc, layers,
+                              False, args.temperature, args.coef)
+    ref[0].backward()
+    for v, r, nm in zip(res[:4], ref[:4], ("total", "distill", "emb", "target")):
+        assert abs(float(v) - float(r)) < 1e-2 * abs(float(r)) + 1e-4, (nm, float(v), float(r))
+    assert _rel(res[4], ref[4].detach()) < 2e-2
+    named = dict(m.named_parameters())
+    for k in keys:
+        r = _rel(named[k].grad, osd[k].grad)
+        assert r < 5e-2, (k, r)
+
+
+def test_train_state_survives_optimizer_step_and_matches_oracle_adam(golden):
+    """Fused Adam(amsgrad) kernel vs torch.optim.Adam golden trajectory."""
+    import tinyrec.ops as ops
+    g = golden("adam")
+    p = torch.from_numpy(g["p0"].copy()).cuda()
+    m, v, vmax = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    shadow = torch.zeros(p.numel(), device="cuda", dtype=torch.bfloat16)
+    for step in range(g["grads"].shape[0]):
+        ops.adam_amsgrad(p, torch.from_numpy(g["grads"][step]).cuda(), m, v, vmax, shadow, 1e-4, 0.9, 0.999, 1e-8, step + 1)
+        np.testing.assert_allclose(p.cpu().numpy(), g["params"][step], rtol=2e-6, atol=1e-7)
+    assert torch.equal(shadow, p.to(torch.bfloat16))
+
+
+def test_fused_adam_moves_model_and_refreshes_shadow(golden):
+    import tinyrec.optim as topt
+    g = golden("kd")
+    m, inputs = _kd_model(g, False)
+    opt = topt.Adam(m, lr=1e-3)
+    l0 = float(m(*inputs)[0])
+    for _ in range(5):
+        opt.zero_grad()
+        loss = m(*inputs)[0]
+        loss.backward()
+        opt.step()
+    l1 = float(m(*inputs)[0])
+    assert l1 < l0                                # same batch, loss must go down
+    st = m.train_state()
+    assert torch.equal(st.flat.shadow, st.flat.data.to(torch.bfloat16))
+
+
+def test_gathers_bit_exact(golden):
+    import tinyrec.ops as ops
+    g = golden("batching")
+    table = torch.from_numpy(g["news_combined"]).cuda()
+    H = int(g["H"])
+    uf = g["user_feature"]              # int64 [B, H, 2L] from the reference loader
+    # recover the indices the reference used by matching rows is unnecessary: re-derive them like the oracle
+    from oracle import batching as ob
+    n_news = table.shape[0] - 1
+    news_index = {f"N{i}": i for i in range(1, n_news + 1)}
+    idx = [ob.pad_history(ob.to_index(str(c).split(), news_index), H)[0] for c in g["clicks"]]
+    idx_t = torch.tensor(idx, dtype=torch.int32).cuda().reshape(-1)
+    out = torch.empty(idx_t.numel(), table.shape[1], dtype=torch.int64, device="cuda")
+    ops.gather_rows_i32_i64(table, idx_t, out)
+    assert np.array_equal(out.cpu().numpy().reshape(uf.shape), uf)
+    t0 = torch.from_numpy(g["t0"]).cuda()
+    outf = torch.empty(idx_t.numel(), t0.shape[1], device="cuda")
+    ops.gather_rows_f32(t0, idx_t, outf)
+    assert np.array_equal(outf.cpu().numpy().reshape(g["th0"].shape), g["th0"])
+    # out-of-range index -> row 0
+    bad = torch.tensor([-1, 10 ** 6], dtype=torch.int32).cuda()
+    o2 = torch.empty(2, t0.shape[1], device="cuda")
+    ops.gather_rows_f32(t0, bad, o2)
+    assert torch.equal(o2[0], t0[0]) and torch.equal(o2[1], t0[0])
+
+
+def test_eval_metrics_vs_reference_golden(golden):
+    """Scores are injected through a 1-D 'embedding' (D=4: table row = [score,0,0,0], user = e0)."""
+    import tinyrec.ops as ops
+    g = golden("metrics")
+    ptr = torch.from_numpy(g["ptr"].astype(np.int64)).cuda()
+    nnz = int(g["ptr"][-1])
+    table = torch.zeros(nnz, 4, device="cuda")
+    table[:, 0] = torch.from_numpy(g["score"]).cuda()
+    n_imp = len(g["ptr"]) - 1
+    user = torch.zeros(n_imp, 4, device="cuda")
+    user[:, 0] = 1.0
+    cand = torch.arange(nnz, dtype=torch.int32, device="cuda")
+    label = torch.from_numpy(g["label"].astype(np.int8)).cuda()
+    per = torch.zeros(n_imp, 5, dtype=torch.float64, device="cuda")
+    sums = torch.zeros(5, dtype=torch.float64, device="cuda")
+    ops.eval_metrics(table, user, ptr, cand, label, int(np.diff(g["ptr"]).max()), per, sums)
+    per = per.cpu().numpy()
+    vals = g["vals"]
+    valid = ~np.isnan(vals[:, 0])
+    assert np.array_equal(per[:, 4] == 1.0, valid)
+    # AUC is tie-aware and exact; MRR / nDCG depend on the tie order of np.argsort (unspecified for
+    # equal scores), so impressions whose scores contain ties among differently-labelled items get 1e-3.. skip
+    np.testing.assert_allclose(per[valid, 0], vals[valid, 0], atol=1e-12)
+    ptr_h = g["ptr"]
+    for i in np.nonzero(valid)[0]:
+        s = g["score"][ptr_h[i]:ptr_h[i + 1]]
+        if len(np.unique(s)) == len(s):
+            np.testing.assert_allclose(per[i, 1:4], vals[i, 1:4], atol=1e-12)
+    np.testing.assert_allclose(sums.cpu().numpy()[:4], per[:, :4].sum(0), rtol=1e-12)
+    assert int(sums[4]) == int(valid.sum())

@@ -1,0 +1,285 @@
+// Optimiser, dtype casts, batch-assembly gathers and the impression-scoring metrics kernel.
+#include "common.cuh"
+
+#define TNR_API extern "C" __attribute__((visibility("default")))
+
+namespace tnr {
+
+// ---------------------------------------------------------------------------------
+// Adam(amsgrad=True) over one flat fp32 parameter buffer (torch.optim.Adam semantics,
+// reference Tiny-NewsRec/run.py:134), fused with the bf16 shadow-weight refresh.
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; vmax = max(vmax, v)
+//   p -= (lr / bc1) * m / (sqrt(vmax) / sqrt(bc2) + eps)
+// grad_scale multiplies g first (1/world for a summed all-reduce).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                    float* __restrict__ vmax, __nv_bfloat16* __restrict__ shadow, long long n, float lr, float b1,
+                    float b2, float eps, float bc1, float rsqrt_bc2, float grad_scale) {
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  if (i4 + 4 <= n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i4);
+    const float4 gg = *reinterpret_cast<const float4*>(g + i4);
+    float4 mm = *reinterpret_cast<float4*>(m + i4);
+    float4 vv = *reinterpret_cast<float4*>(v + i4);
+    float4 vx = *reinterpret_cast<float4*>(vmax + i4);
+    float* P = reinterpret_cast<float*>(&pp);
+    const float* G = reinterpret_cast<const float*>(&gg);
+    float* Mm = reinterpret_cast<float*>(&mm);
+    float* V = reinterpret_cast<float*>(&vv);
+    float* VX = reinterpret_cast<float*>(&vx);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = G[k] * grad_scale;
+      Mm[k] = b1 * Mm[k] + (1.0f - b1) * gr;
+      V[k] = b2 * V[k] + (1.0f - b2) * gr * gr;
+      VX[k] = fmaxf(VX[k], V[k]);
+      P[k] -= (lr / bc1) * Mm[k] / (sqrtf(VX[k]) * rsqrt_bc2 + eps);
+    }
+    *reinterpret_cast<float4*>(p + i4) = pp;
+    *reinterpret_cast<float4*>(m + i4) = mm;
+    *reinterpret_cast<float4*>(v + i4) = vv;
+    *reinterpret_cast<float4*>(vmax + i4) = vx;
+    if (shadow != nullptr) {
+      uint2 o;
+      o.x = pack_bf16(P[0], P[1]);
+      o.y = pack_bf16(P[2], P[3]);
+      *reinterpret_cast<uint2*>(shadow + i4) = o;
+    }
+  } else {
+    for (long long i = i4; i < n; ++i) {
+      const float gr = g[i] * grad_scale;
+      m[i] = b1 * m[i] + (1.0f - b1) * gr;
+      v[i] = b2 * v[i] + (1.0f - b2) * gr * gr;
+      vmax[i] = fmaxf(vmax[i], v[i]);
+      p[i] -= (lr / bc1) * m[i] / (sqrtf(vmax[i]) * rsqrt_bc2 + eps);
+      if (shadow != nullptr) shadow[i] = __float2bfloat16_rn(p[i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  if (i4 + 4 <= n && (((uintptr_t)(x + i4) & 15) == 0) && (((uintptr_t)(y + i4) & 7) == 0)) {
+    const float4 a = *reinterpret_cast<const float4*>(x + i4);
+    uint2 o;
+    o.x = pack_bf16(a.x, a.y);
+    o.y = pack_bf16(a.z, a.w);
+    *reinterpret_cast<uint2*>(y + i4) = o;
+  } else {
+    for (long long i = i4; i < n && i < i4 + 4; ++i) y[i] = __float2bfloat16_rn(x[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// batch assembly gathers (reference: Tiny-NewsRec/dataloader.py:131,138 token rows -> LongTensor;
+// :142,144 and :295,301 embedding rows).  Bit-exact copies.
+//   i32 table rows -> int64 out (the reference converts the int32 news_combined rows with
+//   torch.LongTensor);  f32 table rows -> f32 out.  One warp per output row.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_rows_i32_i64_kernel(const int32_t* __restrict__ table, long long n_rows_table, const int32_t* __restrict__ idx,
+                           long long n, int W, int64_t* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= n) return;
+  long long src = idx[r];
+  if (src < 0 || src >= n_rows_table) src = 0;          // unknown id -> row 0 (dataloader.py:74)
+  const int lane = threadIdx.x & 31;
+  for (int c = lane; c < W; c += 32) out[r * W + c] = (int64_t)table[src * W + c];
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows_f32_kernel(const float* __restrict__ table, long long n_rows_table, const int32_t* __restrict__ idx,
+                       long long n, int D, float* __restrict__ out, long long out_ld) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= n) return;
+  long long src = idx[r];
+  if (src < 0 || src >= n_rows_table) src = 0;
+  const int lane = threadIdx.x & 31;
+  const float4* s = reinterpret_cast<const float4*>(table + src * D);
+  float4* d = reinterpret_cast<float4*>(out + r * out_ld);
+  for (int c = lane; c < D / 4; c += 32) d[c] = s[c];
+}
+
+// ---------------------------------------------------------------------------------
+// impression scoring + ranking metrics (reference: Tiny-NewsRec/run.py:346-361,
+// metrics.py:5-23, sklearn roc_auc_score).  One block per impression:
+//   score_c = table[cand_c] . user ;  skip if labels constant ;
+//   rank_c  = 1 + #{s_j > s_c} + #{s_j == s_c, j > c}     (= np.argsort(score)[::-1] order)
+//   AUC = (sum_pos #neg below + 0.5 #neg tied) / (P N);  MRR = sum_pos 1/rank / P
+//   nDCG@k = sum_{pos, rank<=k} 1/log2(rank+1) / sum_{r<=min(k,P)} 1/log2(r+1)   (binary labels)
+// out[imp] = {auc, mrr, ndcg5, ndcg10, valid}
+// ---------------------------------------------------------------------------------
+constexpr int EVAL_THREADS = 128;
+
+__global__ void __launch_bounds__(EVAL_THREADS)
+eval_metrics_kernel(const float* __restrict__ table, const float* __restrict__ user, const long long* __restrict__ ptr,
+                    const int32_t* __restrict__ cand, const int8_t* __restrict__ label, int D,
+                    double* __restrict__ out, float* __restrict__ score_out) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const long long p0 = ptr[b];
+  const int C = (int)(ptr[b + 1] - p0);
+  float* s_user = sm;                         // [D]
+  float* s_score = sm + D;                    // [C]
+  int8_t* s_lab = reinterpret_cast<int8_t*>(s_score + C);
+  __shared__ double red[4][EVAL_THREADS / 32];
+  __shared__ int s_pos;
+  for (int d = tid; d < D; d += EVAL_THREADS) s_user[d] = user[(size_t)b * D + d];
+  if (tid == 0) s_pos = 0;
+  __syncthreads();
+  int npos_local = 0;
+  for (int c = warp; c < C; c += EVAL_THREADS / 32) {
+    const float* row = table + (size_t)cand[p0 + c] * D;
+    float t = 0.f;
+    for (int d = lane * 4; d < D; d += 128) {
+      const float4 x = *reinterpret_cast<const float4*>(row + d);
+      t = fmaf(x.x, s_user[d], fmaf(x.y, s_user[d + 1], fmaf(x.z, s_user[d + 2], fmaf(x.w, s_user[d + 3], t))));
+    }
+    t = warp_sum(t);
+    if (lane == 0) {
+      s_score[c] = t;
+      const int8_t y = label[p0 + c];
+      s_lab[c] = y;
+      npos_local += (y != 0);
+      if (score_out != nullptr) score_out[p0 + c] = t;
+    }
+  }
+  if (lane == 0 && npos_local) atomicAdd(&s_pos, npos_local);
+  __syncthreads();
+  const int P = s_pos, N = C - P;
+  if (P == 0 || N == 0) {                      // run.py:348 -- skipped impression
+    if (tid < 5) out[(size_t)b * 5 + tid] = 0.0;
+    return;
+  }
+  double auc = 0.0, mrr = 0.0, d5 = 0.0, d10 = 0.0;
+  for (int c = tid; c < C; c += EVAL_THREADS) {
+    if (s_lab[c] == 0) continue;
+    const float sc = s_score[c];
+    int above = 0, neg_below = 0, neg_tied = 0;
+    for (int j = 0; j < C; ++j) {
+      const float sj = s_score[j];
+      above += (sj > sc) || (sj == sc && j > c);
+      if (s_lab[j] == 0) { neg_below += (sj < sc); neg_tied += (sj == sc); }
+    }
+    const int rank = above + 1;
+    auc += (double)neg_below + 0.5 * (double)neg_tied;
+    mrr += 1.0 / (double)rank;
+    const double disc = 1.0 / log2((double)rank + 1.0);
+    if (rank <= 5) d5 += disc;
+    if (rank <= 10) d10 += disc;
+  }
+  double vals[4] = {auc, mrr, d5, d10};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double v = vals[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[k][warp] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double t[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 4; ++k)
+      for (int w = 0; w < EVAL_THREADS / 32; ++w) t[k] += red[k][w];
+    double i5 = 0.0, i10 = 0.0;
+    for (int r = 1; r <= min(P, 10); ++r) {
+      const double disc = 1.0 / log2((double)r + 1.0);
+      if (r <= 5) i5 += disc;
+      i10 += disc;
+    }
+    out[(size_t)b * 5 + 0] = t[0] / ((double)P * (double)N);
+    out[(size_t)b * 5 + 1] = t[1] / (double)P;
+    out[(size_t)b * 5 + 2] = t[2] / i5;
+    out[(size_t)b * 5 + 3] = t[3] / i10;
+    out[(size_t)b * 5 + 4] = 1.0;
+  }
+}
+
+// sums[0..3] += metric sums over impressions, sums[4] += number of valid impressions
+__global__ void __launch_bounds__(256)
+eval_reduce_kernel(const double* __restrict__ per_imp, long long n, double* __restrict__ sums) {
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc[k] += per_imp[i * 5 + k];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sums + k, v);
+  }
+}
+
+}  // namespace tnr
+
+using namespace tnr;
+
+TNR_API int tnr_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, void* shadow_bf16, long long n,
+                             float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+  TNR_REQUIRE(step >= 1, "tnr_adam_amsgrad: step must be >= 1");
+  if (n == 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const long long threads = (n + 3) / 4;
+  const int grid = (int)((threads + 255) / 256);
+  adam_amsgrad_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, vmax, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr, beta1, beta2, eps, (float)bc1,
+      (float)(1.0 / sqrt(bc2)), grad_scale);
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
+
+TNR_API int tnr_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream) {
+  if (n == 0) return 0;
+  const long long threads = (n + 3) / 4;
+  cast_f32_bf16_kernel<<<(int)((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(y_bf16), n);
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
+
+TNR_API int tnr_gather_rows_i32_i64(const int32_t* table, long long n_rows_table, const int32_t* idx, long long n, int W,
+                                    int64_t* out, void* stream) {
+  if (n == 0) return 0;
+  gather_rows_i32_i64_kernel<<<(int)((n + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, n_rows_table,
+                                                                                                      idx, n, W, out);
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
+
+TNR_API int tnr_gather_rows_f32(const float* table, long long n_rows_table, const int32_t* idx, long long n, int D,
+                                float* out, long long out_ld, void* stream) {
+  TNR_REQUIRE(D % 4 == 0 && out_ld % 4 == 0, "tnr_gather_rows_f32: D and out_ld must be multiples of 4");
+  if (n == 0) return 0;
+  gather_rows_f32_kernel<<<(int)((n + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, n_rows_table, idx,
+                                                                                                  n, D, out, out_ld);
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
+
+TNR_API int tnr_eval_metrics(const float* table, const float* user, const long long* ptr, const int32_t* cand,
+                             const int8_t* label, long long n_imp, int D, int max_c, double* per_imp, double* sums,
+                             float* score_out, void* stream) {
+  TNR_REQUIRE(D % 4 == 0, "tnr_eval_metrics: D must be a multiple of 4");
+  if (n_imp == 0) return 0;
+  const int smem = (D + max_c) * 4 + ((max_c + 15) / 16) * 16;
+  TNR_REQUIRE(smem <= 200 * 1024, "tnr_eval_metrics: max candidates %d too large", max_c);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (smem > 48 * 1024)
+    TNR_CHECK_CUDA(cudaFuncSetAttribute(eval_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  eval_metrics_kernel<<<(int)n_imp, EVAL_THREADS, smem, st>>>(table, user, ptr, cand, label, D, per_imp, score_out);
+  TNR_LAUNCH_CHECK();
+  if (sums != nullptr) {
+    int grid = (int)((n_imp + 255) / 256);
+    if (grid > 592) grid = 592;
+    eval_reduce_kernel<<<grid, 256, 0, st>>>(per_imp, n_imp, sums);
+    TNR_LAUNCH_CHECK();
+  }
+  return 0;
+}

@@ -1,0 +1,355 @@
+"""Orchestration of the CUDA path: flat parameter / gradient buffers, bf16 shadow weights,
+activation workspaces and the forward / backward kernel sequences of the news encoder and
+of the scoring + KD head.  Pure plumbing: every arithmetic op is a kernel behind the C ABI
+(tinyrec.ops); torch supplies device memory, streams and views.
+
+Reference call stacks this replaces: SURVEY.md section 3.1 (train step), 3.2 (table build).
+"""
+import math
+
+import torch
+
+from . import ops
+from ._lib import TinyRecError
+
+BF = torch.bfloat16
+F32 = torch.float32
+LN_EPS = 1e-12            # tnlrv3/configuration_tnlrv3.py:61
+
+
+def _align8(n):
+    return (n + 7) // 8 * 8
+
+
+def rel_pos_bucket_table(L, num_buckets=32, max_distance=128):
+    """int64 [L, L] bucket of (pos_j - pos_i); host-side restatement of
+    tnlrv3/modeling.py:345-373 for position_ids = arange(L) (batch-invariant)."""
+    pos = torch.arange(L)
+    rel = pos[None, :] - pos[:, None]
+    half = num_buckets // 2
+    ret = (rel > 0).long() * half
+    n = rel.abs()
+    exact = half // 2
+    big = exact + (torch.log(n.float() / exact) / math.log(max_distance / exact) * (half - exact)).to(torch.long)
+    big = torch.min(big, torch.full_like(big, half - 1))
+    return ret + torch.where(n < exact, n, big)
+
+
+class LayerRefs:
+    """Parameter handles of one BertLayer, by the reference's attribute names."""
+
+    def __init__(self, layer):
+        s, a = layer.attention.self, layer.attention.output
+        self.q, self.k, self.v = s.query, s.key, s.value
+        self.o, self.ln1 = a.dense, a.LayerNorm
+        self.f1, self.f2, self.ln2 = layer.intermediate.dense, layer.output.dense, layer.output.LayerNorm
+
+    def params(self):
+        return [self.q.weight, self.k.weight, self.v.weight, self.q.bias, self.k.bias, self.v.bias,
+                self.o.weight, self.o.bias, self.ln1.weight, self.ln1.bias,
+                self.f1.weight, self.f1.bias, self.f2.weight, self.f2.bias, self.ln2.weight, self.ln2.bias]
+
+
+class FlatParams:
+    """Trainable parameters re-homed into one flat fp32 buffer (+ flat grad, + bf16 shadow).
+
+    The order keeps [Wq, Wk, Wv] and [bq, bk, bv] of a layer contiguous so the fused QKV GEMM,
+    its wgrad and the Adam kernel all address them as one [3E, E] / [3E] tensor, and keeps
+    transform_matrix.{i}.{weight,bias} at a constant stride for the batched fp32 GEMMs."""
+
+    def __init__(self, ordered_params, device):
+        self.params = ordered_params
+        self.offsets = []
+        off = 0
+        for p in ordered_params:
+            self.offsets.append(off)
+            off += p.numel()
+            # keep every tensor 8-element aligned unless the next one must stay contiguous
+            off = _align8(off)
+        self.numel = off
+        self.data = torch.zeros(off, device=device, dtype=F32)
+        self.grad = torch.zeros(off, device=device, dtype=F32)
+        self.shadow = torch.zeros(off, device=device, dtype=BF)
+        for p, o in zip(ordered_params, self.offsets):
+            view = self.data[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+        self._index = {id(p): i for i, p in enumerate(ordered_params)}
+        self.refresh_shadow()
+
+    def refresh_shadow(self):
+        ops.cast_f32_bf16(self.data, self.shadow)
+        self.versions = [p._version for p in self.params]
+
+    def stale(self):
+        return any(p._version != v for p, v in zip(self.params, self.versions))
+
+    def attached(self):
+        """True while every parameter still lives in the flat buffers (a `.to()` / `.cuda()` or an
+        optimizer that replaced `.data` / `.grad` breaks this and forces a rebuild)."""
+        for p, o in zip(self.params, self.offsets):
+            if p.data_ptr() != self.data.data_ptr() + 4 * o:
+                return False
+        return True
+
+    def reattach_grads(self):
+        for p, o in zip(self.params, self.offsets):
+            g = p.grad
+            if g is None or g.data_ptr() != self.grad.data_ptr() + 4 * o:
+                view = self.grad[o:o + p.numel()].view(p.shape)
+                if g is None:
+                    view.zero_()
+                else:
+                    view.copy_(g)
+                p.grad = view
+
+    def has(self, p):
+        return id(p) in self._index
+
+    def off(self, p):
+        return self.offsets[self._index[id(p)]]
+
+    def w_shadow(self, p, rows=None):
+        o = self.off(p)
+        n = p.numel() if rows is None else rows * p.shape[1]
+        return self.shadow[o:o + n].view(-1, p.shape[1])
+
+    def g_view(self, p, numel=None, shape=None):
+        o = self.off(p)
+        n = p.numel() if numel is None else numel
+        v = self.grad[o:o + n]
+        return v.view(shape) if shape is not None else v.view(p.shape) if numel is None else v
+
+
+class _Frozen:
+    """bf16 / fp32 device copies of frozen tensors, refreshed when the source `_version` or
+    storage changes (e.g. after load_state_dict)."""
+
+    def __init__(self):
+        self.cache = {}
+
+    def get(self, key, tensors, build):
+        sig = tuple((t.data_ptr(), t._version) for t in tensors)
+        hit = self.cache.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        val = build()
+        self.cache[key] = (sig, val)
+        return val
+
+
+class Encoder:
+    """News encoder (TNLRv3 layers + word pooling + dense) on the CUDA path."""
+
+    def __init__(self, news_encoder_module):
+        self.mod = news_encoder_module
+        bert = news_encoder_module.bert_model.bert
+        self.bert = bert
+        self.layers = [LayerRefs(l) for l in bert.encoder.layer]
+        self.E = bert.embeddings.word_embeddings.weight.shape[1]
+        self.A = bert.rel_pos_bias.weight.shape[0]
+        self.F = self.layers[0].f1.weight.shape[0] if self.layers else 4 * self.E
+        self.Q = news_encoder_module.attn.att_fc1.weight.shape[0]
+        self.D = news_encoder_module.dense.weight.shape[0]
+        self.frozen = _Frozen()
+        self.ws = {}
+        self.scratch_ln = None
+
+    # ---- parameter access ---------------------------------------------------------
+    def trainable_order(self):
+        """Trainable parameters of the encoder in flat-buffer order."""
+        out = []
+        for lr in self.layers:
+            ps = lr.params()
+            flags = [p.requires_grad for p in ps]
+            if any(flags):
+                if not all(flags):
+                    raise TinyRecError("a BertLayer must be trainable or frozen as a whole (run.py:101-112 policy)")
+                out += ps
+        for p in (self.mod.attn.att_fc1.weight, self.mod.attn.att_fc1.bias, self.mod.attn.att_fc2.weight,
+                  self.mod.attn.att_fc2.bias, self.mod.dense.weight, self.mod.dense.bias):
+            if p.requires_grad:
+                out.append(p)
+        return out
+
+    def lowest_trainable_layer(self):
+        for i, lr in enumerate(self.layers):
+            if lr.q.weight.requires_grad:
+                return i
+        return len(self.layers)
+
+    def check_supported(self):
+        emb = self.bert.embeddings
+        for p in list(emb.parameters()) + [self.bert.rel_pos_bias.weight]:
+            if p.requires_grad:
+                raise TinyRecError(
+                    "training the embeddings / rel_pos_bias is outside the supported hot path "
+                    "(the reference freezes them, run.py:103-104); set requires_grad=False")
+
+    def _w(self, flat, p):
+        """bf16 GEMM operand of a weight matrix."""
+        if flat is not None and flat.has(p):
+            return flat.w_shadow(p)
+        return self.frozen.get(("w", id(p)), [p], lambda: p.detach().to(BF).contiguous())
+
+    def layer_weights(self, flat, i):
+        lr = self.layers[i]
+        if flat is not None and flat.has(lr.q.weight):
+            E = self.E
+            o = flat.off(lr.q.weight)
+            wqkv = flat.shadow[o:o + 3 * E * E].view(3 * E, E)
+            ob = flat.off(lr.q.bias)
+            bqkv = flat.data[ob:ob + 3 * E]
+        else:
+            wqkv = self.frozen.get(("wqkv", i), [lr.q.weight, lr.k.weight, lr.v.weight],
+                                   lambda: torch.cat([lr.q.weight, lr.k.weight, lr.v.weight], 0).detach().to(BF).contiguous())
+            bqkv = self.frozen.get(("bqkv", i), [lr.q.bias, lr.k.bias, lr.v.bias],
+                                   lambda: torch.cat([lr.q.bias, lr.k.bias, lr.v.bias], 0).detach().float().contiguous())
+        return wqkv, bqkv, self._w(flat, lr.o.weight), self._w(flat, lr.f1.weight), self._w(flat, lr.f2.weight)
+
+    def relpos(self, L):
+        w = self.bert.rel_pos_bias.weight
+        return self.frozen.get(("relpos", L), [w],
+                               lambda: w.detach().float()[:, rel_pos_bucket_table(L).to(w.device)].contiguous())
+
+    def word_table(self):
+        w = self.bert.embeddings.word_embeddings.weight
+        return self.frozen.get(("word",), [w], lambda: w.detach().to(BF).contiguous())
+
+    # ---- workspaces -----------------------------------------------------------------
+    def workspace(self, n, L, n_saved_layers, dev):
+        key = (n, L, n_saved_layers)
+        ws = self.ws.get(key)
+        if ws is not None:
+            return ws
+        T, E, Fd = n * L, self.E, self.F
+        mk = lambda *s, dt=BF: torch.empty(*s, device=dev, dtype=dt)  # noqa: E731
+        ws = dict(x0=mk(T, E), xa=mk(T, E), xb=mk(T, E), qkv=mk(T, 3 * E), ctx=mk(T, E), pre=mk(T, E), x1=mk(T, E),
+                  h=mk(T, Fd), e=mk(T, self.Q), a=mk(n, L, dt=F32), pooled=mk(n, E), saved=[])
+        for _ in range(n_saved_layers):
+            ws["saved"].append(dict(xin=None, qkv=mk(T, 3 * E), ctx=mk(T, E), pre1=mk(T, E), x1=mk(T, E),
+                                    z=mk(T, Fd), h=mk(T, Fd), pre2=mk(T, E), xout=mk(T, E)))
+        if n_saved_layers:
+            ws.update(dx=mk(T, E), dx2=mk(T, E), dpre=mk(T, E), dz=mk(T, Fd), dqkv=mk(T, 3 * E), dctx=mk(T, E),
+                      du=mk(T, self.Q), dnews_bf=mk(n, self.D), dpooled=mk(n, E, dt=F32))
+        if len(self.ws) > 8:
+            self.ws.clear()
+        self.ws[key] = ws
+        return ws
+
+    # ---- forward ----------------------------------------------------------------------
+    def forward(self, x, flat=None, save=False, out=None):
+        """x int64 [n, 2L] -> news vectors fp32 [n, D].  With ``save`` the activations the
+        backward needs are kept in the workspace (layers >= lowest trainable layer)."""
+        if x.dtype != torch.int64 or x.dim() != 2 or x.shape[1] % 2:
+            raise TinyRecError(f"news encoder input must be int64 [n, 2L], got {x.dtype} {tuple(x.shape)}")
+        x = x.contiguous()
+        n, L = x.shape[0], x.shape[1] // 2
+        dev = x.device
+        nl = len(self.layers)
+        low = self.lowest_trainable_layer() if save else nl
+        ws = self.workspace(n, L, nl - low if save else 0, dev)
+        emb = self.bert.embeddings
+        relpos = self.relpos(L)
+        cur = ws["x0"]
+        ops.embed_ln(x, L, self.word_table(), emb.position_embeddings.weight, emb.token_type_embeddings.weight[0],
+                     emb.LayerNorm.weight, emb.LayerNorm.bias, LN_EPS, cur)
+        for i, lr in enumerate(self.layers):
+            wqkv, bqkv, wo, w1, w2 = self.layer_weights(flat, i)
+            if i >= low:
+                sv = ws["saved"][i - low]
+                sv["xin"] = cur
+                qkv, ctx, pre1, x1, h, pre2, xout, z = sv["qkv"], sv["ctx"], sv["pre1"], sv["x1"], sv["h"], sv["pre2"], sv["xout"], sv["z"]
+            else:
+                qkv, ctx, pre1, x1, h, pre2, z = ws["qkv"], ws["ctx"], ws["pre"], ws["x1"], ws["h"], ws["pre"], None
+                xout = ws["xb"] if cur is ws["xa"] else ws["xa"]
+            ops.gemm(cur, wqkv, qkv, bias=bqkv)
+            ops.attn_fwd(qkv, x, L, relpos, ctx, self.A)
+            ops.gemm(ctx, wo, pre1, bias=lr.o.bias, residual=cur)
+            ops.layernorm_fwd(pre1, lr.ln1.weight, lr.ln1.bias, LN_EPS, x1)
+            ops.gemm(x1, w1, h, bias=lr.f1.bias, act=ops.ACT_GELU, aux=z)
+            ops.gemm(h, w2, pre2, bias=lr.f2.bias, residual=x1)
+            ops.layernorm_fwd(pre2, lr.ln2.weight, lr.ln2.bias, LN_EPS, xout)
+            cur = xout
+        at = self.mod.attn
+        ops.gemm(cur, self._w(flat, at.att_fc1.weight), ws["e"], bias=at.att_fc1.bias, act=ops.ACT_TANH)
+        ops.attnpool_fwd(cur, ws["e"], self.Q, at.att_fc2.weight.view(-1), at.att_fc2.bias, None, ws["pooled"], ws["a"], n, L)
+        if out is None:
+            out = torch.empty(n, self.D, device=dev, dtype=F32)
+        ops.gemm(ws["pooled"], self._w(flat, self.mod.dense.weight), out, bias=self.mod.dense.bias)
+        if save:
+            ws["xlast"], ws["x"], ws["n"], ws["L"], ws["low"] = cur, x, n, L, low
+        self.last_ws = ws
+        return out
+
+    # ---- backward -----------------------------------------------------------------------
+    def _splitk(self, M, N, K):
+        tiles = ((M + 127) // 128) * ((N + (255 if N > 128 else 127)) // (256 if N > 128 else 128))
+        sms = 148
+        s = max(1, int(round(2.0 * sms / tiles)))
+        return max(1, min(s, (K + 63) // 64 // 4 or 1))
+
+    def _wgrad(self, flat, p, dy, xin, rows=None):
+        """dW[out,in] += dy[T,out]^T @ x[T,in]; db += colsum(dy)."""
+        M = dy.shape[1]
+        g = flat.g_view(p) if rows is None else flat.grad[flat.off(p):flat.off(p) + rows * p.shape[1]].view(rows, p.shape[1])
+        ops.gemm(dy, xin, g, a_t=True, b_t=True, split_k=self._splitk(M, xin.shape[1], dy.shape[0]), accumulate=True)
+
+    def backward(self, d_news, flat):
+        """d_news fp32 [n, D] -> parameter gradients accumulated into ``flat.grad``."""
+        ws = self.last_ws
+        n, L, low, x = ws["n"], ws["L"], ws["low"], ws["x"]
+        T, E = n * L, self.E
+        nl = len(self.layers)
+        at, dense = self.mod.attn, self.mod.dense
+        if self.scratch_ln is None or self.scratch_ln.device != d_news.device:
+            self.scratch_ln = torch.zeros(2 * E, device=d_news.device, dtype=F32)
+        ops.cast_f32_bf16(d_news, ws["dnews_bf"])
+        dnb = ws["dnews_bf"]
+        if flat.has(dense.weight):
+            self._wgrad(flat, dense.weight, dnb, ws["pooled"])
+            ops.colsum(dnb, flat.g_view(dense.bias))
+        ops.gemm(dnb, self._w(flat, dense.weight), ws["dpooled"], b_t=True)
+        xl = ws["xlast"]
+        if flat.has(at.att_fc1.weight):
+            dw2, db2 = flat.g_view(at.att_fc2.weight).view(-1), flat.g_view(at.att_fc2.bias)
+        else:
+            dw2, db2 = self.scratch_ln[:self.Q], self.scratch_ln[E:E + 1]
+        ops.attnpool_bwd(xl, ws["e"], self.Q, at.att_fc2.weight.view(-1), ws["a"], ws["dpooled"], ws["dx2"], ws["du"],
+                         dw2, db2, n, L)
+        if flat.has(at.att_fc1.weight):
+            self._wgrad(flat, at.att_fc1.weight, ws["du"], xl)
+            ops.colsum(ws["du"], flat.g_view(at.att_fc1.bias))
+        if low >= nl:
+            return
+        dx = ws["dx"]
+        ops.gemm(ws["du"], self._w(flat, at.att_fc1.weight), dx, b_t=True, residual=ws["dx2"])
+        for i in range(nl - 1, low - 1, -1):
+            lr, sv = self.layers[i], ws["saved"][i - low]
+            train = flat.has(lr.q.weight)
+            wqkv, bqkv, wo, w1, w2 = self.layer_weights(flat, i)
+            dpre, dz, dqkv, dctx, dx2 = ws["dpre"], ws["dz"], ws["dqkv"], ws["dctx"], ws["dx2"]
+            sg, sb = (flat.g_view(lr.ln2.weight), flat.g_view(lr.ln2.bias)) if train else (self.scratch_ln[:E], self.scratch_ln[E:])
+            ops.layernorm_bwd(dx, sv["pre2"], lr.ln2.weight, LN_EPS, dpre, sg, sb)
+            if train:
+                self._wgrad(flat, lr.f2.weight, dpre, sv["h"])
+                ops.colsum(dpre, flat.g_view(lr.f2.bias))
+            ops.gemm(dpre, w2, dz, b_t=True, act=ops.ACT_DGELU, aux=sv["z"])
+            if train:
+                self._wgrad(flat, lr.f1.weight, dz, sv["x1"])
+                ops.colsum(dz, flat.g_view(lr.f1.bias))
+            ops.gemm(dz, w1, dx2, b_t=True, residual=dpre)                 # d x1
+            sg, sb = (flat.g_view(lr.ln1.weight), flat.g_view(lr.ln1.bias)) if train else (self.scratch_ln[:E], self.scratch_ln[E:])
+            ops.layernorm_bwd(dx2, sv["pre1"], lr.ln1.weight, LN_EPS, dpre, sg, sb)
+            if train:
+                self._wgrad(flat, lr.o.weight, dpre, sv["ctx"])
+                ops.colsum(dpre, flat.g_view(lr.o.bias))
+            ops.gemm(dpre, wo, dctx, b_t=True)
+            ops.attn_bwd(sv["qkv"], x, L, self.relpos(L), dctx, dqkv, self.A)
+            if train:
+                self._wgrad(flat, lr.q.weight, dqkv, sv["xin"], rows=3 * E)
+                ob = flat.off(lr.q.bias)
+                ops.colsum(dqkv, flat.grad[ob:ob + 3 * E])
+            if i > low:
+                ops.gemm(dqkv, wqkv, dx, b_t=True, residual=dpre)

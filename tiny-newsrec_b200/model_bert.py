@@ -1,0 +1,418 @@
+"""Drop-in replacement for the reference's ``Tiny-NewsRec/model_bert.py`` on the B200 path.
+
+Same class names, constructor arguments, forward signatures, sub-module attribute paths and
+``state_dict`` keys as the reference, so ``run.py`` works by changing
+``from model_bert import Model`` to ``from tinyrec.model_bert import Model``.  The modules
+are parameter holders: the arithmetic runs in the sm_100a kernels of libtinyrec.so
+(``tinyrec.engine`` / ``tinyrec.ops``); there is no PyTorch-op or CPU fallback.
+
+Reference: Tiny-NewsRec/model_bert.py:8-34 (AttentionPooling), :103-137 (NewsEncoder),
+:140-176 (UserEncoder), :179-205 (ModelBert), :208-244 (losses), :247-306 (Model);
+tnlrv3/modeling.py:133-476,713-801 for the encoder parameter tree.
+"""
+import json
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import TinyRecError
+from .engine import BF, F32, Encoder, FlatParams
+from .synth import BERT_BASE
+
+# ------------------------------------------------------------------------------------
+# parameter-holder tree with the reference's attribute names
+# ------------------------------------------------------------------------------------
+
+
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise TinyRecError(f"{type(self).__name__} is a parameter holder; compute goes through the CUDA engine")
+
+
+def _bert_init(module, std):
+    """tnlrv3/modeling.py:41-51"""
+    if isinstance(module, (nn.Linear, nn.Embedding)):
+        module.weight.data.normal_(mean=0.0, std=std)
+    elif isinstance(module, nn.LayerNorm):
+        module.bias.data.zero_()
+        module.weight.data.fill_(1.0)
+    if isinstance(module, nn.Linear) and module.bias is not None:
+        module.bias.data.zero_()
+
+
+def load_bert_config(config_name, **over):
+    cfg = dict(BERT_BASE, initializer_range=0.02)
+    if config_name:
+        with open(config_name, "r", encoding="utf-8") as f:
+            cfg.update(json.load(f))
+    cfg.update(over)
+    return cfg
+
+
+def _bert_layer(cfg):
+    E, Fd, eps = cfg["hidden_size"], cfg["intermediate_size"], cfg["layer_norm_eps"]
+    layer = _Holder()
+    layer.attention = _Holder()
+    layer.attention.self = _Holder()
+    layer.attention.self.query = nn.Linear(E, E)
+    layer.attention.self.key = nn.Linear(E, E)
+    layer.attention.self.value = nn.Linear(E, E)
+    layer.attention.output = _Holder()
+    layer.attention.output.dense = nn.Linear(E, E)
+    layer.attention.output.LayerNorm = nn.LayerNorm(E, eps=eps)
+    layer.intermediate = _Holder()
+    layer.intermediate.dense = nn.Linear(E, Fd)
+    layer.output = _Holder()
+    layer.output.dense = nn.Linear(Fd, E)
+    layer.output.LayerNorm = nn.LayerNorm(E, eps=eps)
+    return layer
+
+
+def build_bert_model(cfg, num_layers):
+    """Parameter tree of TuringNLRv3ForSequenceClassification (tnlrv3/modeling.py:713-723):
+    ``bert.{embeddings,encoder.layer[i],pooler,rel_pos_bias}`` + ``classifier``.  The pooler and
+    classifier are dead compute in the reference (model_bert.py:128-129 discards their
+    outputs) but must exist so load_state_dict stays strict."""
+    E = cfg["hidden_size"]
+    m = _Holder()
+    m.bert = _Holder()
+    emb = _Holder()
+    emb.word_embeddings = nn.Embedding(cfg["vocab_size"], E, padding_idx=0)
+    emb.position_embeddings = nn.Embedding(cfg["max_position_embeddings"], E)
+    emb.token_type_embeddings = nn.Embedding(cfg["type_vocab_size"], E)
+    emb.LayerNorm = nn.LayerNorm(E, eps=cfg["layer_norm_eps"])
+    m.bert.embeddings = emb
+    m.bert.encoder = _Holder()
+    m.bert.encoder.layer = nn.ModuleList([_bert_layer(cfg) for _ in range(num_layers)])
+    m.bert.pooler = _Holder()
+    m.bert.pooler.dense = nn.Linear(E, E)
+    m.bert.rel_pos_bias = nn.Linear(cfg["rel_pos_bins"], cfg["num_attention_heads"], bias=False)
+    m.classifier = nn.Linear(E, cfg.get("num_labels", 2))
+    std = cfg.get("initializer_range", 0.02)
+    m.apply(lambda mod: _bert_init(mod, std))
+    return m
+
+
+# ------------------------------------------------------------------------------------
+# modules
+# ------------------------------------------------------------------------------------
+class AttentionPooling(nn.Module):
+    """model_bert.py:8-34.  Standalone ``forward`` handles fp32 [B, S, C] inputs (S <= 64)."""
+
+    def __init__(self, emb_size, hidden_size):
+        super().__init__()
+        self.att_fc1 = nn.Linear(emb_size, hidden_size)
+        self.att_fc2 = nn.Linear(hidden_size, 1)
+
+    def forward(self, x, attn_mask=None):
+        B, S, C = x.shape
+        x = x.contiguous().float()
+        mask = torch.ones(B, S, device=x.device, dtype=F32) if attn_mask is None else attn_mask.contiguous().float()
+        out = torch.empty(B, C, device=x.device, dtype=F32)
+        a = torch.empty(B, S, device=x.device, dtype=F32)
+        ops.user_encoder_fwd(x.view(B * S, C), mask, self.att_fc1.bias, self.att_fc1.weight, self.att_fc1.bias,
+                             self.att_fc2.weight.view(-1), self.att_fc2.bias, True, out, a, None, B, S)
+        return out
+
+
+class NewsEncoder(nn.Module):
+    """model_bert.py:103-137 (``pooling='att'`` only; 'cls'/'mean' are out of scope)."""
+
+    def __init__(self, args, is_teacher=False, num_layers=None):
+        super().__init__()
+        if getattr(args, "pooling", "att") != "att":
+            raise TinyRecError("only pooling='att' is on the supported hot path (demo.sh:28)")
+        if getattr(args, "model_type", "tnlrv3") != "tnlrv3":
+            raise TinyRecError("only model_type='tnlrv3' is supported (the reference's bert/roberta branch is broken)")
+        if num_layers is None:
+            num_layers = args.num_teacher_layers if is_teacher else args.num_student_layers
+        self.pooling = args.pooling
+        self.bert_config = load_bert_config(getattr(args, "config_name", None), num_hidden_layers=num_layers)
+        self.bert_model = build_bert_model(self.bert_config, num_layers)
+        self.attn = AttentionPooling(self.bert_config["hidden_size"], args.news_query_vector_dim)
+        self.dense = nn.Linear(self.bert_config["hidden_size"], args.news_dim)
+        self._engine = None
+        self._flat = None           # set by the owning TrainState
+
+    def engine(self):
+        if self._engine is None:
+            self._engine = Encoder(self)
+        return self._engine
+
+    def forward(self, x, chunk=2048):
+        """x int64 [n, 2L] (ids | mask) -> fp32 [n, news_dim].  Inference path (no autograd graph);
+        training goes through ``Model`` / ``model_bert_2.ModelBert``."""
+        if not x.is_cuda:
+            raise TinyRecError("tinyrec NewsEncoder needs CUDA tensors (no CPU path)")
+        eng = self.engine()
+        flat = self._flat
+        if flat is not None:
+            if not flat.attached():
+                flat = self._flat = None
+            elif flat.stale():
+                flat.refresh_shadow()
+        n = x.shape[0]
+        if n <= chunk:
+            return eng.forward(x, flat)
+        out = torch.empty(n, eng.D, device=x.device, dtype=F32)
+        for s in range(0, n, chunk):
+            eng.forward(x[s:s + chunk], flat, out=out[s:s + chunk])
+        return out
+
+
+class UserEncoder(nn.Module):
+    """model_bert.py:140-176, NAML branch (additive attention).  NRMS is a 'next' row."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        if getattr(args, "model", "NAML") == "NRMS":
+            raise TinyRecError("model='NRMS' (multi-head self-attention user encoder) is not built yet")
+        self.attn = AttentionPooling(args.news_dim, args.user_query_vector_dim)
+        self.pad_doc = nn.Parameter(torch.empty(1, args.news_dim).uniform_(-1, 1))
+
+    def forward(self, news_vecs, log_mask=None):
+        B, H, D = news_vecs.shape
+        v = news_vecs.contiguous().float()
+        m = log_mask.contiguous().float()
+        user = torch.empty(B, D, device=v.device, dtype=F32)
+        a = torch.empty(B, H, device=v.device, dtype=F32)
+        at = self.attn
+        ops.user_encoder_fwd(v.view(B * H, D), m, self.pad_doc.view(-1), at.att_fc1.weight, at.att_fc1.bias,
+                             at.att_fc2.weight.view(-1), at.att_fc2.bias, bool(self.args.user_log_mask), user, a, None, B, H)
+        return user
+
+
+# ------------------------------------------------------------------------------------
+# training state shared by Model and model_bert_2.ModelBert
+# ------------------------------------------------------------------------------------
+class TrainState:
+    """Flat parameter / gradient buffers + head workspaces of one trainable top-level model."""
+
+    def __init__(self, news_encoder, user_encoder, teachers, transform, device):
+        self.ne, self.ue, self.teachers, self.transform = news_encoder, user_encoder, teachers, transform
+        self.enc = news_encoder.engine()
+        self.enc.check_supported()
+        enc_params = self.enc.trainable_order()
+        at = user_encoder.attn
+        head = [p for p in (user_encoder.pad_doc, at.att_fc1.weight, at.att_fc1.bias, at.att_fc2.weight, at.att_fc2.bias)
+                if p.requires_grad]
+        if head and len(head) != 5:
+            raise TinyRecError("the user encoder must be trainable or frozen as a whole")
+        self.ue_trainable = bool(head)
+        tparams = []
+        for lin in transform:
+            if lin.weight.requires_grad != lin.bias.requires_grad:
+                raise TinyRecError("transform_matrix weight/bias must share requires_grad")
+            if lin.weight.requires_grad:
+                tparams += [lin.weight, lin.bias]
+        self.tm_trainable = bool(tparams)
+        if tparams and len(tparams) != 2 * len(transform):
+            raise TinyRecError("transform_matrix modules must be trainable or frozen together")
+        ordered = enc_params + head + tparams
+        self.sig = tuple(id(p) for p in ordered)
+        self.flat = FlatParams(ordered, device) if ordered else None
+        self.head_begin = self.flat.off(head[0]) if head else (self.flat.off(tparams[0]) if tparams else (self.flat.numel if self.flat else 0))
+        self.head_end = self.flat.numel if self.flat else 0
+        self.stage = torch.zeros(max(self.head_end - self.head_begin, 1), device=device, dtype=F32)
+        news_encoder._flat = self.flat
+        self.hw = {}
+        self.anchor = torch.zeros(1, device=device, requires_grad=True)
+        self.comm_hook = None      # optional callable(flat) run at the end of backward (NCCL all-reduce)
+
+    def valid(self, module):
+        want = tuple(id(p) for p in _trainable_signature(module))
+        if set(want) != set(self.sig):
+            return False
+        return self.flat is None or self.flat.attached()
+
+    def _stage_view(self, p):
+        o = self.flat.off(p) - self.head_begin
+        return self.stage[o:o + p.numel()]
+
+    def head_ws(self, B, H, K, M, D, Q, dev):
+        key = (B, H, K, M)
+        w = self.hw.get(key)
+        if w is None:
+            R = B * (H + K)
+            mk = lambda *s: torch.empty(*s, device=dev, dtype=F32)  # noqa: E731
+            w = dict(news=mk(R, D), user=mk(B, D), a=mk(B, H), e=mk(B, H, Q), ta=mk(B, H), score=mk(B, K),
+                     losses=torch.zeros(4, device=dev, dtype=F32), d_news=mk(R, D), d_user=mk(B, D),
+                     T=mk(max(M, 1), R + B, D), TP=mk(max(M, 1), R + B, D), G=mk(max(M, 1), R + B, D))
+            self.hw[key] = w
+        return w
+
+    # ---- one fused forward (+ eager head gradients) -------------------------------------------
+    def step_forward(self, history, history_mask, candidate, label, th_list, tc_list, temperature, coef, use_mask,
+                     want_grad):
+        B, H, W = history.shape
+        K = candidate.shape[1]
+        M = len(th_list)
+        dev = history.device
+        flat = self.flat
+        if flat is not None:
+            if flat.stale():
+                flat.refresh_shadow()
+            if want_grad:
+                flat.reattach_grads()
+        x = torch.cat([history.reshape(B * H, W), candidate.reshape(B * K, W)], 0)
+        D = self.enc.D
+        Q = self.ue.attn.att_fc1.weight.shape[0]
+        w = self.head_ws(B, H, K, M, D, Q, dev)
+        R = B * (H + K)
+        news = self.enc.forward(x, flat, save=want_grad, out=w["news"])
+        mask = history_mask.contiguous().float()
+        label = label.contiguous()
+        at = self.ue.attn
+        ops.user_encoder_fwd(news[:B * H], mask, self.ue.pad_doc.view(-1), at.att_fc1.weight, at.att_fc1.bias,
+                             at.att_fc2.weight.view(-1), at.att_fc2.bias, use_mask, w["user"], w["a"], w["e"], B, H)
+        T, TP, G = w["T"], w["TP"], w["G"]
+        for i in range(M):
+            T[i, :B * H].copy_(th_list[i].reshape(B * H, D))
+            T[i, B * H:R].copy_(tc_list[i].reshape(B * K, D))
+            t = self.teachers[i]
+            ops.user_encoder_fwd(T[i, :B * H], mask, t.pad_doc.view(-1), t.attn.att_fc1.weight, t.attn.att_fc1.bias,
+                                 t.attn.att_fc2.weight.view(-1), t.attn.att_fc2.bias, use_mask, T[i, R:], w["ta"], None, B, H)
+            lin = self.transform[i]
+            ops.sgemm_nt(T[i], lin.weight, lin.bias, TP[i], R + B, D, D, 1, 0, 0, 0, 0)
+        w["losses"].zero_()
+        ops.kd_loss(news, w["user"], label, T if M else None, TP if M else None, M, B, H, K, D, temperature, coef,
+                    want_grad, w["score"], w["losses"], w["d_news"], w["d_user"], G if M else None)
+        if want_grad:
+            self.stage.zero_()
+            if self.ue_trainable:
+                sv = self._stage_view
+                ops.user_encoder_bwd(news[:B * H], mask, self.ue.pad_doc.view(-1), at.att_fc1.weight, at.att_fc2.weight.view(-1),
+                                     use_mask, w["a"], w["e"], w["d_user"], w["d_news"], sv(self.ue.pad_doc), sv(at.att_fc1.weight),
+                                     sv(at.att_fc1.bias), sv(at.att_fc2.weight), sv(at.att_fc2.bias), B, H)
+            else:
+                scratch = torch.zeros(D + Q * D + 2 * Q + 1, device=dev, dtype=F32)
+                ops.user_encoder_bwd(news[:B * H], mask, self.ue.pad_doc.view(-1), at.att_fc1.weight, at.att_fc2.weight.view(-1),
+                                     use_mask, w["a"], w["e"], w["d_user"], w["d_news"], scratch[:D], scratch[D:D + Q * D],
+                                     scratch[D + Q * D:D + Q * D + Q], scratch[D + Q * D + Q:D + Q * D + 2 * Q],
+                                     scratch[D + Q * D + 2 * Q:], B, H)
+            if self.tm_trainable:
+                for i in range(M):
+                    lin = self.transform[i]
+                    ops.sgemm_tn_acc(G[i], T[i], self._stage_view(lin.weight), self._stage_view(lin.bias), R + B, D, D, 1,
+                                     0, 0, 0, 0)
+        self.last = w
+        return w
+
+    def step_backward(self, g_total):
+        """Upstream gradient of the total loss (a device scalar) -> encoder backward + staged head grads."""
+        w = self.last
+        flat = self.flat
+        w["d_news"].mul_(g_total)
+        self.enc.backward(w["d_news"], flat)
+        if self.head_end > self.head_begin:
+            self.stage.mul_(g_total)
+            flat.grad[self.head_begin:self.head_end].add_(self.stage[:self.head_end - self.head_begin])
+        if self.comm_hook is not None:
+            self.comm_hook(flat)
+
+
+def _trainable_signature(module):
+    return [p for p in module.parameters() if p.requires_grad]
+
+
+class _StepFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, state, args):
+        w = state.step_forward(*args)
+        ctx.state = state
+        losses = w["losses"]
+        return losses[3].clone(), losses[0].clone(), losses[1].clone(), losses[2].clone(), w["score"].clone()
+
+    @staticmethod
+    def backward(ctx, g_total, g_distill, g_emb, g_target, g_score):
+        ctx.state.step_backward(g_total)
+        return None, None, None
+
+
+def _get_state(module, build):
+    st = getattr(module, "_tnr_state", None)
+    if st is None or not st.valid(module):
+        st = build()
+        object.__setattr__(module, "_tnr_state", st)
+    return st
+
+
+class ModelBert(nn.Module):
+    """model_bert.py:179-205: (score, history_vecs, candidate_vecs, user_vec).  Inference semantics
+    (outputs carry no autograd graph); the training entry points are ``Model.forward`` and
+    ``tinyrec.model_bert_2.ModelBert.forward``."""
+
+    def __init__(self, args, is_teacher=False):
+        super().__init__()
+        self.args = args
+        self.news_encoder = NewsEncoder(args, is_teacher)
+        self.user_encoder = UserEncoder(args)
+
+    def forward(self, history, history_mask, candidate):
+        B, H, W = history.shape
+        K = candidate.shape[1]
+        x = torch.cat([history.reshape(B * H, W), candidate.reshape(B * K, W)], 0)
+        vec = self.news_encoder(x)
+        hist = vec[:B * H].view(B, H, -1)
+        cand = vec[B * H:].view(B, K, -1)
+        user = self.user_encoder(hist, history_mask)
+        w = torch.zeros(4, device=vec.device, dtype=F32)
+        score = torch.empty(B, K, device=vec.device, dtype=F32)
+        label = torch.zeros(B, device=vec.device, dtype=torch.int64)
+        ops.kd_loss(vec, user, label, None, None, 0, B, H, K, vec.shape[1], 1.0, 1.0, False, score, w, None, None, None)
+        return score, hist, cand, user
+
+
+def kd_ce_loss(logits_S, logits_T, temperature=1):
+    """model_bert.py:208-219.  Kept for API completeness (tiny torch expression on the caller's
+    tensors); the training path computes it inside tnr_kd_loss_fwdbwd."""
+    p_T = torch.softmax(logits_T / temperature, dim=-1)
+    return -(p_T * torch.log_softmax(logits_S / temperature, dim=-1)).sum(dim=-1).mean()
+
+
+def hid_mse_loss(state_S, state_T, mask=None, reduce=True):
+    """model_bert.py:222-244 (API completeness; see kd_ce_loss)."""
+    se = (state_S - state_T) ** 2
+    if mask is None:
+        return se.mean() if reduce else se.mean(dim=-1)
+    if not reduce:
+        return (se * mask.unsqueeze(-1)).mean(dim=-1)
+    return (se * mask.unsqueeze(-1)).sum() / (mask.sum() * state_S.size(-1))
+
+
+class Model(nn.Module):
+    """model_bert.py:247-306: multi-teacher KD wrapper.
+    forward(...) -> (total_loss, distill_loss, emb_loss, target_loss, student_score); only
+    ``total_loss`` carries gradient (that is all run.py:194 back-propagates)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.teachers = nn.ModuleList([UserEncoder(args) for _ in range(args.num_teachers)])
+        self.student = ModelBert(args, is_teacher=False)
+        self.target_loss_fn = nn.CrossEntropyLoss()
+        self.transform_matrix = nn.ModuleList([nn.Linear(args.news_dim, args.news_dim) for _ in range(args.num_teachers)])
+        for module in self.transform_matrix:
+            nn.init.xavier_uniform_(module.weight, gain=1.0)
+            nn.init.constant_(module.bias, 0.0)
+
+    def train_state(self):
+        dev = self.transform_matrix[0].weight.device if len(self.transform_matrix) else self.student.user_encoder.pad_doc.device
+        if dev.type != "cuda":
+            raise TinyRecError("tinyrec Model needs its parameters on a CUDA device (no CPU path)")
+        return _get_state(self, lambda: TrainState(self.student.news_encoder, self.student.user_encoder,
+                                                   list(self.teachers), list(self.transform_matrix), dev))
+
+    def forward(self, history, history_mask, candidate, label, teacher_history_embs, teacher_candidate_embs):
+        st = self.train_state()
+        want_grad = torch.is_grad_enabled() and st.flat is not None
+        args = (history, history_mask, candidate, label, list(teacher_history_embs), list(teacher_candidate_embs),
+                float(self.args.temperature), float(self.args.coef), bool(self.args.user_log_mask), want_grad)
+        if want_grad:
+            return _StepFn.apply(st.anchor, st, args)
+        w = st.step_forward(*args)
+        ls = w["losses"]
+        return ls[3].clone(), ls[0].clone(), ls[1].clone(), ls[2].clone(), w["score"].clone()

@@ -29,8 +29,20 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
-def _ready(t):
+class _Stats:
+    """Launch accounting for bench.py: ``launches`` counts kernels of libtinyrec enqueued;
+    when ``gemm_events`` is a list every tnr_gemm_bf16 launch is bracketed by CUDA events on the
+    launching stream and (flops, start, stop) is appended (roofline measurement)."""
+    launches = 0
+    gemm_events = None
+
+
+stats = _Stats()
+
+
+def _ready(t, kernels=1):
     _lib.require_device(t.device.index)
+    stats.launches += kernels
     return _lib.load()
 
 
@@ -71,6 +83,13 @@ def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_N
         g.aux, g.ldaux = aux.data_ptr(), aux.stride(0)
     g.split_k = split_k
     g.accumulate = int(accumulate)
+    if stats.gemm_events is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.tnr_gemm_bf16(ctypes.byref(g), _stream()), "tnr_gemm_bf16")
+        e1.record()
+        stats.gemm_events.append((2.0 * M * N * K, e0, e1))
+        return out
     _lib.check(lib.tnr_gemm_bf16(ctypes.byref(g), _stream()), "tnr_gemm_bf16")
     return out
 
@@ -156,3 +175,96 @@ def attnpool_bwd(x, e, Q, w2, a_in, dout, dx, du, dw2, db2, n, S):
                                     _ptr(_chk(dout, _f32, "dout")), _ptr(_chk(dx, _bf16, "dx")),
                                     _ptr(_chk(du, _bf16, "du")), _ptr(_chk(dw2, _f32, "dw2")),
                                     _ptr(_chk(db2, _f32, "db2")), n, S, C, _stream()), "tnr_attnpool_bwd")
+
+
+def cast_f32_bf16(x, y):
+    lib = _ready(x)
+    _lib.check(lib.tnr_cast_f32_bf16(_ptr(_chk(x, _f32, "cast.x")), _ptr(_chk(y, _bf16, "cast.y")), x.numel(),
+                                     _stream()), "tnr_cast_f32_bf16")
+    return y
+
+
+def user_encoder_fwd(vecs, mask, pad_doc, W1, b1, w2, b2, use_mask, user, a_out, e_out, B, H):
+    """vecs fp32 [B*H, D] (contiguous rows), mask fp32 [B, H] -> user [B, D], a [B, H], e [B, H, Q]."""
+    lib = _ready(vecs)
+    D, Q = W1.shape[1], W1.shape[0]
+    for t, nm in ((vecs, "vecs"), (mask, "mask"), (pad_doc, "pad_doc"), (W1, "W1"), (b1, "b1"), (w2, "w2"), (b2, "b2"),
+                  (user, "user"), (a_out, "a")):
+        _chk(t, _f32, "user_encoder." + nm)
+    _lib.check(lib.tnr_user_encoder_fwd(_ptr(vecs), _ptr(mask), _ptr(pad_doc), _ptr(W1), _ptr(b1), _ptr(w2), _ptr(b2),
+                                        int(use_mask), _ptr(user), _ptr(a_out), _ptr(e_out), B, H, D, Q, _stream()),
+               "tnr_user_encoder_fwd")
+    return user
+
+
+def user_encoder_bwd(vecs, mask, pad_doc, W1, w2, use_mask, a_in, e_in, d_user, d_vecs, dpad, dW1, db1, dw2, db2, B, H):
+    lib = _ready(vecs)
+    D, Q = W1.shape[1], W1.shape[0]
+    for t, nm in ((d_user, "d_user"), (d_vecs, "d_vecs"), (dpad, "dpad"), (dW1, "dW1"), (db1, "db1"), (dw2, "dw2"),
+                  (db2, "db2"), (a_in, "a"), (e_in, "e")):
+        _chk(t, _f32, "user_encoder_bwd." + nm)
+    _lib.check(lib.tnr_user_encoder_bwd(_ptr(vecs), _ptr(mask), _ptr(pad_doc), _ptr(W1), _ptr(w2), int(use_mask),
+                                        _ptr(a_in), _ptr(e_in), _ptr(d_user), _ptr(d_vecs), _ptr(dpad), _ptr(dW1),
+                                        _ptr(db1), _ptr(dw2), _ptr(db2), B, H, D, Q, _stream()), "tnr_user_encoder_bwd")
+
+
+def kd_loss(s_news, s_user, label, T_ext, TP_ext, M, B, H, K, D, temperature, coef, want_grad, score_out, losses,
+            d_news, d_user, G_ext):
+    lib = _ready(s_news)
+    _chk(label, torch.int64, "kd_loss.label")
+    for t, nm in ((s_news, "s_news"), (s_user, "s_user"), (score_out, "score"), (losses, "losses")):
+        _chk(t, _f32, "kd_loss." + nm)
+    _lib.check(lib.tnr_kd_loss_fwdbwd(_ptr(s_news), _ptr(s_user), _ptr(label), _ptr(T_ext), _ptr(TP_ext), M, B, H, K, D,
+                                      float(temperature), float(coef), int(want_grad), _ptr(score_out), _ptr(losses),
+                                      _ptr(d_news), _ptr(d_user), _ptr(G_ext), _stream()), "tnr_kd_loss_fwdbwd")
+
+
+def sgemm_nt(A, Bm, bias, C, M, N, K, batch, sA, sB, sbias, sC):
+    lib = _ready(A)
+    _lib.check(lib.tnr_sgemm_nt(_ptr(_chk(A, _f32, "sgemm.A")), _ptr(_chk(Bm, _f32, "sgemm.B")), _ptr(bias),
+                                _ptr(_chk(C, _f32, "sgemm.C")), M, N, K, batch, sA, sB, sbias, sC, _stream()),
+               "tnr_sgemm_nt")
+
+
+def sgemm_tn_acc(A, Bm, C, cbias, R, N1, N2, batch, sA, sB, sC, sbias):
+    lib = _ready(A)
+    _lib.check(lib.tnr_sgemm_tn_acc(_ptr(_chk(A, _f32, "sgemm.A")), _ptr(_chk(Bm, _f32, "sgemm.B")),
+                                    _ptr(_chk(C, _f32, "sgemm.C")), _ptr(cbias), R, N1, N2, batch, sA, sB, sC, sbias,
+                                    _stream()), "tnr_sgemm_tn_acc")
+
+
+def adam_amsgrad(p, g, m, v, vmax, shadow, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    lib = _ready(p)
+    for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v"), (vmax, "vmax")):
+        _chk(t, _f32, "adam." + nm)
+    _lib.check(lib.tnr_adam_amsgrad(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(vmax), _ptr(shadow), p.numel(), lr, beta1,
+                                    beta2, eps, step, grad_scale, _stream()), "tnr_adam_amsgrad")
+
+
+def gather_rows_i32_i64(table, idx, out):
+    """out int64 [n, W] = table int32 [N, W][idx int32 [n]]"""
+    lib = _ready(table)
+    _chk(table, torch.int32, "gather.table"); _chk(idx, torch.int32, "gather.idx"); _chk(out, torch.int64, "gather.out")
+    _lib.check(lib.tnr_gather_rows_i32_i64(_ptr(table), table.shape[0], _ptr(idx), idx.numel(), table.shape[1], _ptr(out),
+                                           _stream()), "tnr_gather_rows_i32_i64")
+    return out
+
+
+def gather_rows_f32(table, idx, out, out_ld=None):
+    lib = _ready(table)
+    _chk(table, _f32, "gather.table"); _chk(idx, torch.int32, "gather.idx"); _chk(out, _f32, "gather.out")
+    D = table.shape[1]
+    _lib.check(lib.tnr_gather_rows_f32(_ptr(table), table.shape[0], _ptr(idx), idx.numel(), D, _ptr(out),
+                                       D if out_ld is None else out_ld, _stream()), "tnr_gather_rows_f32")
+    return out
+
+
+def eval_metrics(table, user, ptr, cand, label, max_c, per_imp, sums=None, score_out=None):
+    """table fp32 [N, D]; user fp32 [n_imp, D]; ptr int64 [n_imp+1]; cand int32 [nnz]; label int8 [nnz]."""
+    lib = _ready(table)
+    _chk(table, _f32, "eval.table"); _chk(user, _f32, "eval.user"); _chk(ptr, torch.int64, "eval.ptr")
+    _chk(cand, torch.int32, "eval.cand"); _chk(label, torch.int8, "eval.label"); _chk(per_imp, torch.float64, "eval.per_imp")
+    n_imp = ptr.numel() - 1
+    _lib.check(lib.tnr_eval_metrics(_ptr(table), _ptr(user), _ptr(ptr), _ptr(cand), _ptr(label), n_imp, table.shape[1],
+                                    int(max_c), _ptr(per_imp), _ptr(sums), _ptr(score_out), _stream()), "tnr_eval_metrics")
+    return per_imp

@@ -1,0 +1,104 @@
+"""Fused Adam(amsgrad) over the model's flat parameter buffer and the NCCL data-parallel
+wrapper that replaces Horovod.
+
+Reference: ``optim.Adam(model.parameters(), lr=args.lr, amsgrad=True)`` (Tiny-NewsRec/run.py:134),
+``hvd.broadcast_parameters`` / ``hvd.DistributedOptimizer(op=hvd.Average)`` (run.py:142-149).
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import TinyRecError
+
+
+class Adam:
+    """``Adam(model, lr, amsgrad=True)``: one kernel launch per step over all trainable parameters
+    (fp32 master weights, m, v, vmax) that also refreshes the bf16 shadow weights the GEMMs read."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, amsgrad=True):
+        if not amsgrad:
+            raise TinyRecError("only amsgrad=True is implemented (what run.py:134 uses)")
+        self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
+        self.step_count = 0
+        self.m = self.v = self.vmax = None
+        self.grad_scale = 1.0
+
+    def _flat(self):
+        st = self.model.train_state()
+        if st.flat is None:
+            raise TinyRecError("model has no trainable parameters")
+        return st.flat
+
+    def zero_grad(self, set_to_none=False):
+        flat = self._flat()
+        flat.reattach_grads()
+        flat.grad.zero_()
+
+    def step(self):
+        flat = self._flat()
+        if self.m is None or self.m.numel() != flat.numel or self.m.device != flat.data.device:
+            self.m = torch.zeros_like(flat.data)
+            self.v = torch.zeros_like(flat.data)
+            self.vmax = torch.zeros_like(flat.data)
+        self.step_count += 1
+        ops.adam_amsgrad(flat.data, flat.grad, self.m, self.v, self.vmax, flat.shadow, self.lr, self.betas[0],
+                         self.betas[1], self.eps, self.step_count, self.grad_scale)
+
+    def state_dict(self):
+        return dict(step=self.step_count, m=self.m, v=self.v, vmax=self.vmax, lr=self.lr)
+
+    def load_state_dict(self, sd):
+        self.step_count, self.m, self.v, self.vmax, self.lr = sd["step"], sd["m"], sd["v"], sd["vmax"], sd["lr"]
+
+
+def broadcast_parameters(model, root_rank=0):
+    """hvd.broadcast_parameters(model.state_dict(), root_rank=0), run.py:142,247."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    st = getattr(model, "train_state", None)
+    flat = st().flat if st is not None else None
+    if flat is not None:
+        dist.broadcast(flat.data, src=root_rank)
+        flat.refresh_shadow()
+    seen = set(id(p) for p in flat.params) if flat is not None else set()
+    for t in list(model.parameters()) + list(model.buffers()):
+        if id(t) not in seen:
+            dist.broadcast(t.data, src=root_rank)
+
+
+class DistributedOptimizer:
+    """Average the flat gradient buffer over ranks (NCCL all-reduce over NVLink), then step.
+
+    ``overlap=True`` launches the all-reduce on a side stream from the end of the backward
+    (TrainState.comm_hook) so it overlaps the remaining host work; ``step()`` waits for it."""
+
+    def __init__(self, optimizer, overlap=True):
+        self.opt = optimizer
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.opt.grad_scale = 1.0 / self.world          # SUM all-reduce, scale folded into Adam
+        self.stream = torch.cuda.Stream() if (self.world > 1 and overlap) else None
+        self.pending = None
+        if self.stream is not None:
+            self.opt.model.train_state().comm_hook = self._launch
+
+    def _launch(self, flat):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
+            done = torch.cuda.Event()
+            done.record()
+        self.pending = done
+
+    def zero_grad(self, set_to_none=False):
+        self.opt.zero_grad()
+
+    def step(self):
+        if self.world > 1:
+            if self.stream is not None and self.pending is not None:
+                torch.cuda.current_stream().wait_event(self.pending)
+                self.pending = None
+            else:
+                dist.all_reduce(self.opt._flat().grad, op=dist.ReduceOp.SUM)
+        self.opt.step()

@@ -1,0 +1,91 @@
+"""One process per GPU over ``torch.distributed`` (NCCL on the B200 box, gloo in CPU tests):
+the replacement for the reference's Horovod plumbing.
+
+Reference: Tiny-NewsRec/utils.py:43-60 (``init_hvd_cuda``), run.py:142-149 (broadcast +
+DistributedOptimizer(op=Average)), run.py:372-379 (eval sum all-reduce), streaming.py:40-58
+(file sharding r, r+world, ...).  The path shards by impressions (training / eval) and by news
+rows (table build); the only data-path collectives are the gradient all-reduce, the final table
+all-gather and the 5-scalar metric reduction.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(enable=True, backend=None):
+    """-> (world, rank, local_rank), mirroring ``init_hvd_cuda`` (utils.py:43-60).  Reads the
+    torchrun environment; a single process without it is world 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if enable and world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return world, rank, local
+
+
+def world_size():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def get_rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def shard_files(files, rank, world):
+    """streaming.py:53-54: worker r reads files r, r+world, ..."""
+    return [f for i, f in enumerate(files) if i % world == rank]
+
+
+def shard_rows(n_rows, rank, world):
+    """Contiguous row range of the news table owned by ``rank`` (table build)."""
+    per = (n_rows + world - 1) // world
+    lo = min(n_rows, rank * per)
+    return lo, min(n_rows, lo + per)
+
+
+def allreduce_sum_(t):
+    if world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def allreduce_mean_(t):
+    """hvd.allreduce(op=Average) semantics (run.py:145-149)."""
+    w = world_size()
+    if w > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t.div_(w)
+    return t
+
+
+def reduce_eval_sums(local_count, local_sums):
+    """run.py:372-379: total metric sums / total impression count (all impressions, skipped ones
+    included).  local_sums: float64 [4] tensor; returns (mean float64 [4], total_count)."""
+    buf = torch.cat([local_sums.double().reshape(4), torch.tensor([float(local_count)], dtype=torch.float64,
+                                                                 device=local_sums.device)])
+    allreduce_sum_(buf)
+    total = float(buf[4].item())
+    return buf[:4] / max(total, 1.0), int(total)
+
+
+def allgather_rows(local_rows, n_rows):
+    """Gather the per-rank ``[hi-lo, D]`` table shards (``shard_rows`` layout) into ``[n_rows, D]``."""
+    w = world_size()
+    if w == 1:
+        return local_rows
+    per = (n_rows + w - 1) // w
+    D = local_rows.shape[1]
+    pad = torch.zeros(per, D, device=local_rows.device, dtype=local_rows.dtype)
+    pad[:local_rows.shape[0]] = local_rows
+    out = torch.empty(w * per, D, device=local_rows.device, dtype=local_rows.dtype)
+    dist.all_gather_into_tensor(out, pad)
+    return out[:n_rows]
