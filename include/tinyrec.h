@@ -29,12 +29,27 @@
 extern "C" {
 #endif
 
-#define TNR_ABI_VERSION 1
+#define TNR_ABI_VERSION 2
 
 const char* tnr_last_error(void);
 int tnr_abi_version(void);
 /* Fails unless the current device is compute capability 10.x. Returns SM count in *num_sms. */
 int tnr_device_check(int* num_sms);
+
+/* ------------------------------------------------------------------ dropout */
+/* Training-mode dropout (the reference trains with dropout 0.1 active: run.py never calls
+ * model.eval() in train()).  Masks are counter-based (Philox4x32-7 keyed by
+ * *seed, per-tensor `site`, element index) so the backward regenerates them instead of storing
+ * them; oracle/dropout.py restates the generator bit-for-bit.  `seed` is a DEVICE pointer so a
+ * captured CUDA graph replays with a fresh seed.  NULL struct, NULL seed or p <= 0 disables. */
+typedef struct {
+  const unsigned long long* seed;
+  unsigned int site;
+  float p;
+} tnr_dropout;
+
+/* keep[i] = 1/0 for the first n elements of dropout tensor `site` (linear element index; tests). */
+int tnr_dropout_mask(const tnr_dropout* drop, long long n, unsigned char* keep, void* stream);
 
 /* ------------------------------------------------------------------ GEMM */
 enum { TNR_ACT_NONE = 0, TNR_ACT_GELU = 1, TNR_ACT_TANH = 2, TNR_ACT_DGELU = 3 };
@@ -47,7 +62,7 @@ enum { TNR_BF16 = 0, TNR_F32 = 1 };
  *   b_mn_major = 0: B memory is [N,K] row-major (nn.Linear weight [out,in]).
  *   b_mn_major = 1: B memory is [K,N] row-major (dgrad through weight; wgrad activations).
  * epilogue:  v = acc (+ bias[n]);  GELU: (aux <- bf16(v) if aux) v = gelu_erf(v);
- *            TANH: v = tanh(v);  DGELU: v *= gelu_erf'(aux[m,n]);  v += residual[m,n];
+ *            TANH: v = tanh(v);  DGELU: v *= gelu_erf'(aux[m,n]);  v = dropout(v);  v += residual[m,n];
  *            c_dtype bf16 | f32;  split_k > 1 or accumulate: fp32 atomic add into C.
  * Replaces torch nn.Linear call sites: tnlrv3/modeling.py:236-248 (QKV), transformers
  * BertSelfOutput/BertIntermediate/BertOutput dense (used at modeling.py:287,305-306),
@@ -63,6 +78,7 @@ typedef struct {
   void* aux; int ldaux;
   int split_k;
   int accumulate;
+  const tnr_dropout* drop;   /* v = dropout(acc + bias) before the residual add; NULL = off (plain epilogue only) */
 } tnr_gemm_args;
 int tnr_gemm_bf16(const tnr_gemm_args* args, void* stream);
 
@@ -70,32 +86,39 @@ int tnr_gemm_bf16(const tnr_gemm_args* args, void* stream);
 /* out[t,:] = LayerNorm_eps( word[ids[t]] + pos[t % L] + type0 )  ->  bf16 [n_rows*L, E].
  * ids: int64, row r at ids + r*ids_ld (the reference packs ids|mask as x[n, 2L]).
  * word_dtype: TNR_BF16 or TNR_F32 table [vocab, E]; pos fp32 [>=L, E]; type0 fp32 [E].
- * Replaces BertEmbeddings.forward, tnlrv3/modeling.py:153-178 (dropout not applied here). */
+ * Replaces BertEmbeddings.forward, tnlrv3/modeling.py:153-178 (dropout :177 applied when `drop` is given). */
 int tnr_embed_ln_fwd(const int64_t* ids, int ids_ld, int n_rows, int L, int vocab, const void* word,
                      int word_dtype, const float* pos, const float* type0, const float* gamma,
-                     const float* beta, float eps, int E, void* out_bf16, void* stream);
+                     const float* beta, float eps, int E, void* out_bf16, const tnr_dropout* drop,
+                     void* stream);
 
 /* y = LayerNorm(x) over rows of a bf16 [rows, E] buffer (the "dense + bias + residual" sum the
  * GEMM epilogue wrote).  Replaces the LayerNorm of transformers BertSelfOutput / BertOutput
  * (imported at tnlrv3/modeling.py:12-14, used at :287 and :306). */
 int tnr_layernorm_fwd(const void* x_bf16, int rows, int E, const float* gamma, const float* beta,
                       float eps, void* y_bf16, void* stream);
-/* dx = dLN(dy; x) ; dgamma += , dbeta += (fp32, caller zero-initialises).  autograd of the above. */
+/* dx = dLN(dy; x) ; dgamma += , dbeta += (fp32, caller zero-initialises).  autograd of the above.
+ * If dx_drop_bf16 != NULL it receives dx * keep / (1-p) for dropout tensor `drop` -- the gradient
+ * w.r.t. the dense output that was dropped out before the residual add (dx itself is the residual
+ * branch); with drop disabled it is a plain copy of dx. */
 int tnr_layernorm_bwd(const void* dy_bf16, const void* x_bf16, int rows, int E, const float* gamma,
-                      float eps, void* dx_bf16, float* dgamma, float* dbeta, void* stream);
+                      float eps, void* dx_bf16, float* dgamma, float* dbeta, void* dx_drop_bf16,
+                      const tnr_dropout* drop, void* stream);
 /* out[c] += sum_r x[r,c]  (bias gradients of nn.Linear). */
 int tnr_colsum_bf16(const void* x_bf16, int rows, int cols, int ld, float* out, void* stream);
 
 /* ------------------------------------------------------------ fused attention */
 /* ctx = softmax(Q K^T / 8 + (1-mask)*-10000 + relpos[h]) V for L <= 32, head dim 64.
  * qkv bf16 [n*L, 3E] (Q | K | V), mask int64 (row r at mask + r*mask_ld, 1 = attend),
- * relpos fp32 [A, L, L], ctx bf16 [n*L, E].
+ * relpos fp32 [A, L, L], ctx bf16 [n*L, E].  `drop` applies dropout to the probabilities (:223).
  * Replaces BertSelfAttention.multi_head_attention, tnlrv3/modeling.py:205-231. */
 int tnr_attn_relpos_fwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relpos,
-                        void* ctx_bf16, int n_news, int L, int A, int E, void* stream);
-/* dqkv bf16 [n*L, 3E] from dctx (probabilities recomputed). */
+                        void* ctx_bf16, int n_news, int L, int A, int E, const tnr_dropout* drop,
+                        void* stream);
+/* dqkv bf16 [n*L, 3E] from dctx (probabilities recomputed, dropout mask regenerated). */
 int tnr_attn_relpos_bwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relpos,
-                        const void* dctx_bf16, void* dqkv_bf16, int n_news, int L, int A, int E, void* stream);
+                        const void* dctx_bf16, void* dqkv_bf16, int n_news, int L, int A, int E,
+                        const tnr_dropout* drop, void* stream);
 
 /* ------------------------------------------------------- additive attention pooling (words) */
 /* a = normalise(exp(e.w2 + b2) [* mask]);  out[n,:] = sum_s a[n,s] x[n,s,:]

@@ -202,6 +202,102 @@ def test_attention_fwd_bwd(L):
     assert _rel_err(dqkv, qf.grad)[0] < 6e-3
 
 
+# ------------------------------------------------------------------ dropout (counter-based masks)
+P_DROP = 0.1
+
+
+def _seed_tensor(seed):
+    return torch.tensor([seed], device="cuda", dtype=torch.int64)
+
+
+def _keep(seed, site, n):
+    from oracle.dropout import keep_mask
+    return torch.from_numpy(keep_mask(seed, site, n, P_DROP)).cuda()
+
+
+def test_dropout_mask_matches_oracle_generator():
+    ops = _ops()
+    for seed, site, n in ((12345, 3, 100003), (2 ** 40 + 17, 77, 4099), (0, 0, 8)):
+        st = _seed_tensor(seed)
+        got = ops.dropout_mask(ops.make_drop(st, site, P_DROP), n, "cuda").bool()
+        want = _keep(seed, site, n)
+        assert torch.equal(got, want)
+    big = ops.dropout_mask(ops.make_drop(_seed_tensor(99), 5, P_DROP), 1 << 22, "cuda").float()
+    assert abs(float(big.mean()) - (1 - P_DROP)) < 1e-3            # keep rate
+    a, b = big[:-1], big[1:]
+    assert abs(float(((a - a.mean()) * (b - b.mean())).mean())) < 1e-3   # neighbours uncorrelated
+    other = ops.dropout_mask(ops.make_drop(_seed_tensor(100), 5, P_DROP), 1 << 22, "cuda").float()
+    assert abs(float(((big - big.mean()) * (other - other.mean())).mean())) < 1e-3   # seeds independent
+
+
+def test_gemm_dropout_epilogue():
+    ops = _ops()
+    M, N, K = 333, 768, 256
+    a, b = _randn(M, K, seed=3), _randn(N, K, scale=0.05, seed=4)
+    bias = _randn(N, dtype=torch.float32, seed=5)
+    res = _randn(M, N, seed=6)
+    st = _seed_tensor(4242)
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out, bias=bias, residual=res, drop=ops.make_drop(st, 9, P_DROP))
+    keep = _keep(4242, 9, M * N).reshape(M, N).float()
+    ref = (a.float() @ b.float().t() + bias) * keep / (1 - P_DROP) + res.float()
+    assert _rel_err(out, ref)[0] < 1e-4
+
+
+def test_embed_ln_dropout_and_layernorm_bwd_drop_output():
+    ops = _ops()
+    n, L, E, V = 19, 30, 768, 1000
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ids = torch.randint(0, V, (n, L), generator=g, device="cuda")
+    x = torch.cat([ids, torch.ones_like(ids)], 1)
+    word = _randn(V, E, scale=0.02, dtype=torch.float32, seed=1)
+    pos, typ = _randn(512, E, scale=0.02, dtype=torch.float32, seed=2), _randn(2, E, scale=0.02, dtype=torch.float32, seed=3)
+    gamma, beta = 1 + _randn(E, scale=0.1, dtype=torch.float32, seed=4), _randn(E, scale=0.1, dtype=torch.float32, seed=5)
+    st = _seed_tensor(777)
+    out = torch.empty(n * L, E, device="cuda", dtype=BF)
+    ops.embed_ln(x, L, word, pos, typ[0].contiguous(), gamma, beta, 1e-12, out, drop=ops.make_drop(st, 1, P_DROP))
+    keep = _keep(777, 1, n * L * E).reshape(n * L, E).float()
+    ref = torch.nn.functional.layer_norm(word[ids] + pos[:L] + typ[0], (E,), gamma, beta, 1e-12).reshape(n * L, E)
+    assert _rel_err(out, ref * keep / (1 - P_DROP))[0] < 4e-3
+    assert torch.equal(out == 0, keep == 0) or float(((out == 0) != (keep == 0)).float().mean()) < 1e-4
+    # LayerNorm backward: second output = dx * keep / (1 - p)
+    rows = n * L
+    xin, dy = _randn(rows, E, seed=6), _randn(rows, E, seed=7)
+    dx, dxd = torch.empty_like(xin), torch.empty_like(xin)
+    dg, db = torch.zeros(E, device="cuda"), torch.zeros(E, device="cuda")
+    ops.layernorm_bwd(dy, xin, gamma, 1e-12, dx, dg, db, dx_drop=dxd, drop=ops.make_drop(st, 1, P_DROP))
+    assert _rel_err(dxd, dx.float() * keep / (1 - P_DROP))[0] < 4e-3
+    ops.layernorm_bwd(dy, xin, gamma, 1e-12, dx, dg, db, dx_drop=dxd, drop=None)
+    assert torch.equal(dxd, dx)
+
+
+@pytest.mark.parametrize("L", [30, 17])
+def test_attention_dropout_fwd_bwd(L):
+    from oracle.dropout import attention_keep
+    ops = _ops()
+    n, A, E = 9, 12, 768
+    qkv = _randn(n * L, 3 * E, seed=1)
+    mask = torch.ones(n, L, device="cuda", dtype=torch.long)
+    mask[1, L // 2:] = 0
+    x = torch.cat([torch.zeros_like(mask), mask], 1)
+    relpos = _randn(A, L, L, dtype=torch.float32, seed=4)
+    st = _seed_tensor(31337)
+    drop = ops.make_drop(st, 21, P_DROP)
+    ctx = torch.empty(n * L, E, device="cuda", dtype=BF)
+    ops.attn_fwd(qkv, x, L, relpos, ctx, A, drop=drop)
+    keep = torch.from_numpy(attention_keep(31337, 21, n * A, L, P_DROP)).cuda().float().reshape(n, A, L, L)
+    qf = qkv.float().requires_grad_(True)
+    q, k, v = [t.reshape(n, L, A, 64).permute(0, 2, 1, 3) for t in qf.split(E, dim=1)]
+    s = q @ k.transpose(-1, -2) / 8.0 + (1.0 - mask.float())[:, None, None, :] * -10000.0 + relpos[None]
+    ref = ((torch.softmax(s, -1) * keep / (1 - P_DROP)) @ v).permute(0, 2, 1, 3).reshape(n * L, E)
+    assert _rel_err(ctx, ref)[0] < 6e-3
+    dctx = _randn(n * L, E, seed=5)
+    ref.backward(dctx.float())
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(qkv, x, L, relpos, dctx, dqkv, A, drop=drop)
+    assert _rel_err(dqkv, qf.grad)[0] < 8e-3
+
+
 # ------------------------------------------------------------------ pooling
 @pytest.mark.parametrize("with_mask", [False, True])
 def test_attnpool_fwd_bwd(with_mask):

@@ -5,7 +5,7 @@ fails, a ``TinyRecError`` is raised.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint, c_void_p
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libtinyrec.so")
@@ -18,6 +18,11 @@ class TinyRecError(RuntimeError):
     pass
 
 
+class Dropout(Structure):
+    """tnr_dropout: DEVICE pointer to the uint64 seed, per-tensor site id, drop probability."""
+    _fields_ = [("seed", c_void_p), ("site", c_uint), ("p", c_float)]
+
+
 class GemmArgs(Structure):
     _fields_ = [("M", c_int), ("N", c_int), ("K", c_int),
                 ("A", c_void_p), ("lda", c_int), ("a_mn_major", c_int),
@@ -28,7 +33,8 @@ class GemmArgs(Structure):
                 ("act", c_int),
                 ("aux", c_void_p), ("ldaux", c_int),
                 ("split_k", c_int),
-                ("accumulate", c_int)]
+                ("accumulate", c_int),
+                ("drop", POINTER(Dropout))]
 
 
 P = c_void_p
@@ -36,12 +42,13 @@ _SIGNATURES = {
     "tnr_abi_version": ([], c_int),
     "tnr_device_check": ([POINTER(c_int)], c_int),
     "tnr_gemm_bf16": ([POINTER(GemmArgs), P], c_int),
-    "tnr_embed_ln_fwd": ([P, c_int, c_int, c_int, c_int, P, c_int, P, P, P, P, c_float, c_int, P, P], c_int),
+    "tnr_dropout_mask": ([POINTER(Dropout), c_int64, P, P], c_int),
+    "tnr_embed_ln_fwd": ([P, c_int, c_int, c_int, c_int, P, c_int, P, P, P, P, c_float, c_int, P, POINTER(Dropout), P], c_int),
     "tnr_layernorm_fwd": ([P, c_int, c_int, P, P, c_float, P, P], c_int),
-    "tnr_layernorm_bwd": ([P, P, c_int, c_int, P, c_float, P, P, P, P], c_int),
+    "tnr_layernorm_bwd": ([P, P, c_int, c_int, P, c_float, P, P, P, P, POINTER(Dropout), P], c_int),
     "tnr_colsum_bf16": ([P, c_int, c_int, c_int, P, P], c_int),
-    "tnr_attn_relpos_fwd": ([P, P, c_int, P, P, c_int, c_int, c_int, c_int, P], c_int),
-    "tnr_attn_relpos_bwd": ([P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
+    "tnr_attn_relpos_fwd": ([P, P, c_int, P, P, c_int, c_int, c_int, c_int, POINTER(Dropout), P], c_int),
+    "tnr_attn_relpos_bwd": ([P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, POINTER(Dropout), P], c_int),
     "tnr_attnpool_fwd": ([P, P, c_int, c_int, P, P, P, P, P, c_int, c_int, c_int, P], c_int),
     "tnr_attnpool_bwd": ([P, P, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_int, P], c_int),
     "tnr_user_encoder_fwd": ([P, P, P, P, P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
@@ -80,7 +87,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res
-    if lib.tnr_abi_version() != 1:
+    if lib.tnr_abi_version() != 2:
         raise TinyRecError("libtinyrec.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -1,10 +1,15 @@
 // Fused short-sequence self-attention with relative-position bias (L <= 32, head dim 64).
-//   P = softmax(Q K^T / sqrt(dh) + (1 - mask) * -10000 + relpos[h]);  ctx = P V
+//   P = softmax(Q K^T / sqrt(dh) + (1 - mask) * -10000 + relpos[h]);  ctx = dropout(P) V
 // Reference: Tiny-NewsRec/tnlrv3/modeling.py:205-231 (multi_head_attention), mask :446-454,
 // rel-pos bias :458-463 (batch-invariant [A, L, L] table).
-// One warp per (news, head): K/V (and Q/dO in backward) tiles staged in shared memory as
-// bf16, lane i owns query row i, scores / probabilities live in registers.  The backward
-// recomputes P from Q,K (nothing but QKV is saved by the forward).
+//
+// The op is HBM-bound (arithmetic intensity 4*L*E / (8*E) = 15 FLOP/B at L = 30): one warp per
+// (news, head) stages its 32x64 Q/K/V (and dO) tiles with cp.async into padded shared memory,
+// runs the two small contractions on the warp-level tensor path (ldmatrix + mma.sync m16n8k16,
+// bf16 in / fp32 accumulate; the 30x30x64 tiles are far below a tcgen05 128-row atom), keeps
+// scores / probabilities in registers and writes the result through shared memory as full
+// 128-byte rows.  The backward recomputes P from Q,K (nothing but QKV is saved) and regenerates
+// the dropout mask from the Philox counter.
 #include "common.cuh"
 
 namespace tnr {
@@ -12,186 +17,349 @@ namespace tnr {
 constexpr int DH = 64;
 constexpr int LMAX = 32;
 constexpr int ATT_WARPS = 4;
+constexpr int TS = 72;            // smem row stride (bf16) of a 32 x 64 tile: 144 B, ldmatrix conflict-free
+constexpr int PS = 40;            // smem row stride (bf16) of the 32 x 32 P / dS tiles: 80 B
+constexpr int TILE_BYTES = LMAX * TS * 2;
+constexpr int PT_BYTES = LMAX * PS * 2;
+constexpr int ATT_FWD_SMEM_PER_WARP = 3 * TILE_BYTES + LMAX * 4;
+constexpr int ATT_BWD_SMEM_PER_WARP = 4 * TILE_BYTES + 2 * PT_BYTES + LMAX * 4;
 
-__device__ __forceinline__ void load_tile_bf16(__nv_bfloat16* s, const __nv_bfloat16* g, int L, int ld, int lane) {
-  // L rows x 64 bf16 (128 B per row): 8 x 16 B chunks per row
-  for (int idx = lane; idx < L * 8; idx += 32) {
-    const int r = idx >> 3, c = idx & 7;
-    *reinterpret_cast<bf16x8*>(s + r * DH + c * 8) = *reinterpret_cast<const bf16x8*>(g + (size_t)r * ld + c * 8);
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// L rows x 64 bf16 from global (row stride ld) -> padded smem tile; rows >= L are zero-filled
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* s, const __nv_bfloat16* g, int L, int ld, int lane) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = lane + 32 * it, r = idx >> 3, c = idx & 7;
+    if (r < L) cp_async16(smem_addr(s + r * TS + c * 8), g + (size_t)r * ld + c * 8);
+    else *reinterpret_cast<uint4*>(s + r * TS + c * 8) = make_uint4(0, 0, 0, 0);
   }
 }
 
-__device__ __forceinline__ float dot_row(const float* a, const __nv_bfloat16* srow) {
-  float acc = 0.f;
+// padded smem tile -> global rows (full 128-byte rows, 16 B per lane)
+__device__ __forceinline__ void store_tile(__nv_bfloat16* g, const __nv_bfloat16* s, int L, int ld, int lane) {
 #pragma unroll
-  for (int c = 0; c < DH / 8; ++c) {
-    float f[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(srow + c * 8), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc = fmaf(a[c * 8 + i], f[i], acc);
-  }
-  return acc;
-}
-
-__device__ __forceinline__ void axpy_row(float* acc, float a, const __nv_bfloat16* srow) {
-#pragma unroll
-  for (int c = 0; c < DH / 8; ++c) {
-    float f[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(srow + c * 8), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[c * 8 + i] = fmaf(a, f[i], acc[c * 8 + i]);
+  for (int it = 0; it < 8; ++it) {
+    const int idx = lane + 32 * it, r = idx >> 3, c = idx & 7;
+    if (r < L) *reinterpret_cast<uint4*>(g + (size_t)r * ld + c * 8) = *reinterpret_cast<const uint4*>(s + r * TS + c * 8);
   }
 }
 
-__device__ __forceinline__ void load_row_regs(float* r, const __nv_bfloat16* g) {
+// C fragments (2 m-tiles x 8 n-tiles of a 32 x 64 fp32 result) -> bf16 smem tile
+__device__ __forceinline__ void stage_c64(__nv_bfloat16* s, const float (&o)[2][8][4], int lane) {
+  const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int c = 0; c < DH / 8; ++c) unpack8(*reinterpret_cast<const bf16x8*>(g + c * 8), r + c * 8);
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      *reinterpret_cast<uint32_t*>(s + (mt * 16 + g) * TS + nt * 8 + 2 * t) = pack_bf16(o[mt][nt][0], o[mt][nt][1]);
+      *reinterpret_cast<uint32_t*>(s + (mt * 16 + g + 8) * TS + nt * 8 + 2 * t) = pack_bf16(o[mt][nt][2], o[mt][nt][3]);
+    }
 }
 
-__device__ __forceinline__ void store_row_regs(__nv_bfloat16* g, const float* r) {
+// acc[2][4] (32 x 32) = X[32 x 64] . Y[32 x 64]^T, both row-major padded smem tiles
+__device__ __forceinline__ void mma_xyT(float (&acc)[2][4][4], const __nv_bfloat16* sX, const __nv_bfloat16* sY, int lane) {
+  uint32_t yb[4][2][4];
 #pragma unroll
-  for (int c = 0; c < DH / 8; ++c) *reinterpret_cast<bf16x8*>(g + c * 8) = pack8(r + c * 8);
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+      ldsm_x4(smem_addr(sY + (nt * 8 + (lane & 7)) * TS + half * 32 + (lane >> 3) * 8), yb[nt][half]);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a[4];
+      ldsm_x4(smem_addr(sX + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * TS + ks * 16 + (lane >> 4) * 8), a);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[mt][nt], a, yb[nt][ks >> 1][(ks & 1) * 2], yb[nt][ks >> 1][(ks & 1) * 2 + 1]);
+    }
 }
 
-// scores -> normalised probabilities of row `lane` (valid for lane < L); p[j] for j >= L is 0
-__device__ __forceinline__ void softmax_row(float (&p)[LMAX], const float* q, const __nv_bfloat16* sK,
-                                            const float* __restrict__ relrow, float my_mask_add, int L, int lane) {
-  float mx = -INFINITY;
+// out[2][8] (32 x 64) += P[32 x 32] . Y[32 x 64]; P given as A fragments pa[mt][ks], Y row-major smem tile
+__device__ __forceinline__ void mma_pY(float (&out)[2][8][4], const uint32_t (&pa)[2][2][4], const __nv_bfloat16* sY, int lane) {
 #pragma unroll
-  for (int j = 0; j < LMAX; ++j) {
-    const float madd = __shfl_sync(0xffffffffu, my_mask_add, j);
-    if (j < L) {
-      float s = dot_row(q, sK + j * DH) + madd;
-      if (lane < L) s += relrow[j];
-      p[j] = s;
-      mx = fmaxf(mx, s);
-    } else {
-      p[j] = 0.f;
+  for (int nt = 0; nt < 8; ++nt) {
+    uint32_t b[4];
+    ldsm_x4_t(smem_addr(sY + lane * TS + nt * 8), b);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      mma_bf16(out[mt][nt], pa[mt][0], b[0], b[1]);
+      mma_bf16(out[mt][nt], pa[mt][1], b[2], b[3]);
     }
   }
-  float sum = 0.f;
+}
+
+// A fragments of X^T where X is a 32 x 32 bf16 tile stored row-major (stride PS)
+__device__ __forceinline__ void load_xT_frags(uint32_t (&pa)[2][2][4], const __nv_bfloat16* sX, int lane) {
+  const int mi = lane >> 3;
 #pragma unroll
-  for (int j = 0; j < LMAX; ++j)
-    if (j < L) { p[j] = __expf(p[j] - mx); sum += p[j]; }
-  const float inv = 1.0f / sum;
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-  for (int j = 0; j < LMAX; ++j) p[j] *= inv;
+    for (int ks = 0; ks < 2; ++ks)
+      ldsm_x4_t(smem_addr(sX + (ks * 16 + (lane & 7) + (mi >> 1) * 8) * PS + mt * 16 + (mi & 1) * 8), pa[mt][ks]);
+}
+
+// C-layout fp32 32x32 -> bf16 A fragments
+__device__ __forceinline__ void c_to_a(uint32_t (&pa)[2][2][4], const float (&p)[2][4][4]) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      pa[mt][ks][0] = pack_bf16(p[mt][2 * ks][0], p[mt][2 * ks][1]);
+      pa[mt][ks][1] = pack_bf16(p[mt][2 * ks][2], p[mt][2 * ks][3]);
+      pa[mt][ks][2] = pack_bf16(p[mt][2 * ks + 1][0], p[mt][2 * ks + 1][1]);
+      pa[mt][ks][3] = pack_bf16(p[mt][2 * ks + 1][2], p[mt][2 * ks + 1][3]);
+    }
+}
+
+// raw QK^T accumulators -> normalised probabilities (C layout; columns >= L become 0)
+__device__ __forceinline__ void softmax_frag(float (&s)[2][4][4], const float* smadd, const float* __restrict__ relpos_h,
+                                             int L, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const int i = mt * 16 + g + hi * 8;
+      const float* relrow = relpos_h + (size_t)(i < L ? i : L - 1) * L;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = nt * 8 + 2 * t + e;
+          float v = -INFINITY;
+          if (j < L) v = s[mt][nt][hi * 2 + e] * 0.125f + smadd[j] + __ldg(relrow + j);
+          s[mt][nt][hi * 2 + e] = v;
+          mx = fmaxf(mx, v);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float p = __expf(s[mt][nt][hi * 2 + e] - mx);
+          s[mt][nt][hi * 2 + e] = p;
+          sum += p;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) s[mt][nt][hi * 2 + e] *= inv;
+    }
+}
+
+// Dropout keep bits of the probabilities this thread holds for row (mt, hi): bit (nt*2 + e).
+// Element (item, i, j) lives in Philox group (item*32 + i)*4 + ((j >> 1) & 3), lane (j >> 3)*2 + (j & 1),
+// i.e. linear dropout index ((item*32 + i)*4 + ((j>>1)&3))*8 + (j>>3)*2 + (j&1)  (oracle/dropout.py).
+__device__ __forceinline__ uint32_t attn_keep8(const DropCfg& dc, long long item, int i, int t) {
+  return dropout_keep8(dc, ((uint64_t)item * 32 + (uint64_t)i) * 4 + (uint64_t)t);
 }
 
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ mask, int mask_ld,
-                const float* __restrict__ relpos, __nv_bfloat16* __restrict__ ctx, int n_news, int L, int A, int E) {
+                const float* __restrict__ relpos, __nv_bfloat16* __restrict__ ctx, int n_news, int L, int A, int E,
+                const tnr_dropout drop) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem) + (size_t)warp * 2 * LMAX * DH;
-  __nv_bfloat16* sV = sK + LMAX * DH;
   const long long item = (long long)blockIdx.x * ATT_WARPS + warp;
   if (item >= (long long)n_news * A) return;
+  uint8_t* wbase = smem + (size_t)warp * ATT_FWD_SMEM_PER_WARP;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(wbase);
+  __nv_bfloat16* sK = sQ + LMAX * TS;
+  __nv_bfloat16* sV = sK + LMAX * TS;
+  float* smadd = reinterpret_cast<float*>(sV + LMAX * TS);
   const int n = (int)(item / A), h = (int)(item % A);
   const int ld = 3 * E;
   const __nv_bfloat16* base = qkv + (size_t)n * L * ld + h * DH;
-  load_tile_bf16(sK, base + E, L, ld, lane);
-  load_tile_bf16(sV, base + 2 * E, L, ld, lane);
-  float q[DH];
-  float my_mask_add = 0.f;
-  if (lane < L) {
-    load_row_regs(q, base + (size_t)lane * ld);
-#pragma unroll
-    for (int i = 0; i < DH; ++i) q[i] *= 0.125f;          // 1/sqrt(64), exact
-    my_mask_add = (1.0f - (float)mask[(size_t)n * mask_ld + lane]) * -10000.0f;
-  } else {
-#pragma unroll
-    for (int i = 0; i < DH; ++i) q[i] = 0.f;
-  }
+  load_tile_async(sQ, base, L, ld, lane);
+  load_tile_async(sK, base + E, L, ld, lane);
+  load_tile_async(sV, base + 2 * E, L, ld, lane);
+  smadd[lane] = lane < L ? (1.0f - (float)mask[(size_t)n * mask_ld + lane]) * -10000.0f : 0.f;
+  const DropCfg dc = load_drop(drop);
+  cp_async_wait_all();
   __syncwarp();
-  float p[LMAX];
-  softmax_row(p, q, sK, relpos + ((size_t)h * L + (lane < L ? lane : 0)) * L, my_mask_add, L, lane);
-  float acc[DH];
-#pragma unroll
-  for (int i = 0; i < DH; ++i) acc[i] = 0.f;
-#pragma unroll
-  for (int j = 0; j < LMAX; ++j)
-    if (j < L) axpy_row(acc, p[j], sV + j * DH);
-  if (lane < L) store_row_regs(ctx + ((size_t)n * L + lane) * E + h * DH, acc);
-}
 
-// backward: dQKV from dCtx (recompute P).  smem per warp: Q,K,V,dO tiles (bf16) + P, dS (fp32, padded)
-constexpr int ATT_BWD_SMEM_PER_WARP = 4 * LMAX * DH * 2 + 2 * LMAX * (LMAX + 1) * 4;
+  float s[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[mt][nt][c] = 0.f;
+  mma_xyT(s, sQ, sK, lane);
+  softmax_frag(s, smadd, relpos + (size_t)h * L * L, L, lane);
+  if (dc.thr16 != 0) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        const uint32_t keep = attn_keep8(dc, item, mt * 16 + g + hi * 8, t);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            s[mt][nt][hi * 2 + e] = ((keep >> (nt * 2 + e)) & 1u) ? s[mt][nt][hi * 2 + e] * dc.scale : 0.f;
+      }
+  }
+  uint32_t pa[2][2][4];
+  c_to_a(pa, s);
+  float o[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[mt][nt][c] = 0.f;
+  mma_pY(o, pa, sV, lane);
+  __syncwarp();
+  stage_c64(sQ, o, lane);
+  __syncwarp();
+  store_tile(ctx + (size_t)n * L * E + h * DH, sQ, L, E, lane);
+}
 
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ mask, int mask_ld,
                 const float* __restrict__ relpos, const __nv_bfloat16* __restrict__ dctx,
-                __nv_bfloat16* __restrict__ dqkv, int n_news, int L, int A, int E) {
+                __nv_bfloat16* __restrict__ dqkv, int n_news, int L, int A, int E, const tnr_dropout drop) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* wbase = smem + (size_t)warp * ATT_BWD_SMEM_PER_WARP;
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(wbase);
-  __nv_bfloat16* sK = sQ + LMAX * DH;
-  __nv_bfloat16* sV = sK + LMAX * DH;
-  __nv_bfloat16* sO = sV + LMAX * DH;
-  float* sP = reinterpret_cast<float*>(sO + LMAX * DH);
-  float* sS = sP + LMAX * (LMAX + 1);
   const long long item = (long long)blockIdx.x * ATT_WARPS + warp;
   if (item >= (long long)n_news * A) return;
+  uint8_t* wbase = smem + (size_t)warp * ATT_BWD_SMEM_PER_WARP;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(wbase);
+  __nv_bfloat16* sK = sQ + LMAX * TS;
+  __nv_bfloat16* sV = sK + LMAX * TS;
+  __nv_bfloat16* sO = sV + LMAX * TS;
+  __nv_bfloat16* sP = sO + LMAX * TS;
+  __nv_bfloat16* sS = sP + LMAX * PS;
+  float* smadd = reinterpret_cast<float*>(sS + LMAX * PS);
   const int n = (int)(item / A), h = (int)(item % A);
   const int ld = 3 * E;
+  const int g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* base = qkv + (size_t)n * L * ld + h * DH;
-  load_tile_bf16(sQ, base, L, ld, lane);
-  load_tile_bf16(sK, base + E, L, ld, lane);
-  load_tile_bf16(sV, base + 2 * E, L, ld, lane);
-  load_tile_bf16(sO, dctx + (size_t)n * L * E + h * DH, L, E, lane);
-  float my_mask_add = 0.f;
-  if (lane < L) my_mask_add = (1.0f - (float)mask[(size_t)n * mask_ld + lane]) * -10000.0f;
+  load_tile_async(sQ, base, L, ld, lane);
+  load_tile_async(sK, base + E, L, ld, lane);
+  load_tile_async(sV, base + 2 * E, L, ld, lane);
+  load_tile_async(sO, dctx + (size_t)n * L * E + h * DH, L, E, lane);
+  smadd[lane] = lane < L ? (1.0f - (float)mask[(size_t)n * mask_ld + lane]) * -10000.0f : 0.f;
+  const DropCfg dc = load_drop(drop);
+  cp_async_wait_all();
   __syncwarp();
-  const int li = lane < L ? lane : 0;
-  float p[LMAX];
-  {
-    float q[DH];
-    load_row_regs(q, sQ + li * DH);
+
+  float p[2][4][4], dp[2][4][4];
 #pragma unroll
-    for (int i = 0; i < DH; ++i) q[i] *= 0.125f;
-    softmax_row(p, q, sK, relpos + ((size_t)h * L + li) * L, my_mask_add, L, lane);
-  }
-  float ds[LMAX];
-  {
-    float dO[DH];
-    load_row_regs(dO, sO + li * DH);
-    float delta = 0.f;
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int j = 0; j < LMAX; ++j) {
-      ds[j] = (j < L) ? dot_row(dO, sV + j * DH) : 0.f;      // dP_ij
-      delta = fmaf(p[j], ds[j], delta);
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { p[mt][nt][c] = 0.f; dp[mt][nt][c] = 0.f; }
+  mma_xyT(p, sQ, sK, lane);
+  softmax_frag(p, smadd, relpos + (size_t)h * L * L, L, lane);
+  mma_xyT(dp, sO, sV, lane);                    // dP = dO V^T
+  // dS = P o (dP_eff - delta) / 8, P_drop = P o keep * scale; both to smem (bf16) for the transposed products
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const int i = mt * 16 + g + hi * 8;
+      uint32_t keep = 0xffu;
+      if (dc.thr16 != 0) keep = attn_keep8(dc, item, i, t);
+      float delta = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float k = ((keep >> (nt * 2 + e)) & 1u) ? dc.scale : 0.f;
+          const float de = dp[mt][nt][hi * 2 + e] * k;          // gradient w.r.t. the pre-dropout probability
+          dp[mt][nt][hi * 2 + e] = de;
+          delta = fmaf(p[mt][nt][hi * 2 + e], de, delta);
+        }
+      delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+      delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float pd[2], ds[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float pv = p[mt][nt][hi * 2 + e];
+          const float k = ((keep >> (nt * 2 + e)) & 1u) ? dc.scale : 0.f;
+          pd[e] = pv * k;
+          ds[e] = pv * (dp[mt][nt][hi * 2 + e] - delta) * 0.125f;
+          dp[mt][nt][hi * 2 + e] = ds[e];
+        }
+        *reinterpret_cast<uint32_t*>(sP + i * PS + nt * 8 + 2 * t) = pack_bf16(pd[0], pd[1]);
+        *reinterpret_cast<uint32_t*>(sS + i * PS + nt * 8 + 2 * t) = pack_bf16(ds[0], ds[1]);
+      }
     }
-#pragma unroll
-    for (int j = 0; j < LMAX; ++j) ds[j] = p[j] * (ds[j] - delta) * 0.125f;   // dS_ij / sqrt(dh)
-  }
-  if (lane < L) {
-#pragma unroll
-    for (int j = 0; j < LMAX; ++j) { sP[lane * (LMAX + 1) + j] = p[j]; sS[lane * (LMAX + 1) + j] = ds[j]; }
-  }
   __nv_bfloat16* dbase = dqkv + (size_t)n * L * ld + h * DH;
-  {
-    float acc[DH];
+  float acc[2][8][4];
+  uint32_t pa[2][2][4];
+  // dQ = dS K
+  c_to_a(pa, dp);
 #pragma unroll
-    for (int i = 0; i < DH; ++i) acc[i] = 0.f;
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int j = 0; j < LMAX; ++j)
-      if (j < L) axpy_row(acc, ds[j], sK + j * DH);           // dQ_i = sum_j dS_ij K_j
-    if (lane < L) store_row_regs(dbase + (size_t)lane * ld, acc);
-  }
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
+  mma_pY(acc, pa, sK, lane);
+  __syncwarp();                                   // all lanes done reading sK; sP / sS visible
+  stage_c64(sK, acc, lane);
   __syncwarp();
-  // phase B: lane j owns key/value row j
-  {
-    float acc[DH];
+  store_tile(dbase, sK, L, ld, lane);
+  // dV = P_drop^T dO
+  load_xT_frags(pa, sP, lane);
 #pragma unroll
-    for (int i = 0; i < DH; ++i) acc[i] = 0.f;
-    for (int i = 0; i < L; ++i) axpy_row(acc, sP[i * (LMAX + 1) + li], sO + i * DH);   // dV_j = sum_i P_ij dO_i
-    if (lane < L) store_row_regs(dbase + 2 * E + (size_t)lane * ld, acc);
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int i = 0; i < DH; ++i) acc[i] = 0.f;
-    for (int i = 0; i < L; ++i) axpy_row(acc, sS[i * (LMAX + 1) + li], sQ + i * DH);   // dK_j = sum_i dS_ij Q_i
-    if (lane < L) store_row_regs(dbase + E + (size_t)lane * ld, acc);
-  }
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
+  mma_pY(acc, pa, sO, lane);
+  stage_c64(sV, acc, lane);                       // V was last read by the dP product
+  __syncwarp();
+  store_tile(dbase + 2 * E, sV, L, ld, lane);
+  // dK = dS^T Q
+  load_xT_frags(pa, sS, lane);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
+  mma_pY(acc, pa, sQ, lane);
+  __syncwarp();
+  stage_c64(sQ, acc, lane);
+  __syncwarp();
+  store_tile(dbase + E, sQ, L, ld, lane);
 }
 
 }  // namespace tnr
@@ -205,21 +373,27 @@ static int check_attn(const char* who, int L, int A, int E) {
 }
 
 extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_fwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relpos,
-                                   void* ctx_bf16, int n_news, int L, int A, int E, void* stream) {
+                                   void* ctx_bf16, int n_news, int L, int A, int E, const tnr_dropout* drop, void* stream) {
   if (check_attn("tnr_attn_relpos_fwd", L, A, E)) return 1;
   if (n_news == 0) return 0;
   const long long items = (long long)n_news * A;
   const int grid = (int)((items + ATT_WARPS - 1) / ATT_WARPS);
-  const int smem = ATT_WARPS * 2 * LMAX * DH * 2;
+  const int smem = ATT_WARPS * ATT_FWD_SMEM_PER_WARP;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TNR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
   attn_fwd_kernel<<<grid, ATT_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relpos, reinterpret_cast<__nv_bfloat16*>(ctx_bf16),
-      n_news, L, A, E);
+      n_news, L, A, E, drop_or_none(drop));
   TNR_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_bwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relpos,
-                                   const void* dctx_bf16, void* dqkv_bf16, int n_news, int L, int A, int E, void* stream) {
+                                   const void* dctx_bf16, void* dqkv_bf16, int n_news, int L, int A, int E,
+                                   const tnr_dropout* drop, void* stream) {
   if (check_attn("tnr_attn_relpos_bwd", L, A, E)) return 1;
   if (n_news == 0) return 0;
   const long long items = (long long)n_news * A;
@@ -232,7 +406,8 @@ extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_bwd(const 
   }
   attn_bwd_kernel<<<grid, ATT_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relpos,
-      reinterpret_cast<const __nv_bfloat16*>(dctx_bf16), reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), n_news, L, A, E);
+      reinterpret_cast<const __nv_bfloat16*>(dctx_bf16), reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), n_news, L, A, E,
+      drop_or_none(drop));
   TNR_LAUNCH_CHECK();
   return 0;
 }

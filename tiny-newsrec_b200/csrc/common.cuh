@@ -76,4 +76,53 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
   return v;
 }
 
+
+// ---- counter-based dropout (Philox4x32-7) -----------------------------------------
+// One Philox call yields 8 x 16-bit lanes: element e of group g is KEPT iff lane_e >= thr16,
+// thr16 = round(p * 65536).  ctr = (g_lo, g_hi, site, 0), key = (seed_lo, seed_hi).
+// The numpy restatement used by the tests is oracle/dropout.py.
+__device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+struct DropCfg {            // device-side view of tnr_dropout
+  uint64_t seed; uint32_t site; uint32_t thr16; float scale;   // thr16 == 0: disabled
+};
+
+__device__ __forceinline__ DropCfg load_drop(const tnr_dropout& d) {
+  DropCfg c;
+  c.site = d.site;
+  if (d.seed == nullptr || !(d.p > 0.f)) { c.seed = 0; c.thr16 = 0; c.scale = 1.f; return c; }
+  c.seed = *d.seed;
+  c.thr16 = (uint32_t)(d.p * 65536.0f + 0.5f);
+  c.scale = 1.0f / (1.0f - d.p);
+  return c;
+}
+
+// bit e of the result = keep flag of element e (0..7) of group g
+__device__ __forceinline__ uint32_t dropout_keep8(const DropCfg& c, uint64_t g) {
+  const uint4 r = philox4x32_7(make_uint4((uint32_t)g, (uint32_t)(g >> 32), c.site, 0u),
+                               make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m |= ((w[i] & 0xffffu) >= c.thr16 ? 1u : 0u) << (2 * i);
+    m |= ((w[i] >> 16) >= c.thr16 ? 1u : 0u) << (2 * i + 1);
+  }
+  return m;
+}
+
+inline tnr_dropout drop_or_none(const tnr_dropout* d) {
+  tnr_dropout z; z.seed = nullptr; z.site = 0; z.p = 0.f;
+  return d ? *d : z;
+}
+
 }  // namespace tnr

@@ -29,6 +29,7 @@ struct Params {
   int act;
   __nv_bfloat16* aux; int ldaux;
   int atomic;
+  tnr_dropout drop;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -134,7 +135,7 @@ struct Cfg {
 
 // ---------------------------------------------------------------- epilogue math
 template <int ACT>
-__device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t* acc, int row, int col0) {
+__device__ __forceinline__ void epilogue_chunk(const Params& p, const DropCfg& dc, const uint32_t* acc, int row, int col0) {
   // 32 consecutive columns [col0, col0+32) of one output row
   const bool row_ok = row < p.M;
 #pragma unroll
@@ -163,6 +164,11 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t* 
       unpack8(*reinterpret_cast<const bf16x8*>(p.aux + (size_t)row * p.ldaux + col), z);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(z[i]);
+    }
+    if (dc.thr16 != 0) {       // dropout on (dense + bias), before the residual (BertSelfOutput / BertOutput)
+      const uint32_t keep = dropout_keep8(dc, ((uint64_t)row * (uint64_t)p.N + (uint64_t)col) >> 3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * dc.scale : 0.f;
     }
     if (p.residual != nullptr) {
       float r[8];
@@ -299,6 +305,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = e >> 2;                      // column half of the tile
     int acc = 0; uint32_t acc_phase = 0;
+    const DropCfg dc = load_drop(p.drop);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_blk = t % p.n_tiles;
       const int m_blk = (t / p.n_tiles) % p.m_tiles;
@@ -311,7 +318,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + coff), r);
         tmem_ld_wait();
-        epilogue_chunk<ACT>(p, r, row, n_blk * BN + coff);
+        epilogue_chunk<ACT>(p, dc, r, row, n_blk * BN + coff);
       }
       tc_fence_before();
       __syncwarp();
@@ -440,6 +447,9 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
   p.act = a->act;
   p.aux = reinterpret_cast<__nv_bfloat16*>(a->aux); p.ldaux = a->ldaux;
   p.atomic = atomic ? 1 : 0;
+  p.drop = drop_or_none(a->drop);
+  TNR_REQUIRE(p.drop.seed == nullptr || !(p.drop.p > 0.f) || (!atomic && a->act == TNR_ACT_NONE),
+              "tnr_gemm_bf16: dropout is supported with the plain (bias + residual) epilogue only");
 
   CUtensorMap ta, tb;
   if (!a_mn) { if (make_map(&ta, a->A, a->K, a->M, a->lda, BK, BM)) return 1; }

@@ -216,9 +216,26 @@ eval_reduce_kernel(const double* __restrict__ per_imp, long long n, double* __re
   }
 }
 
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(const tnr_dropout drop, long long n, unsigned char* __restrict__ keep) {
+  const DropCfg dc = load_drop(drop);
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g * 8 >= n) return;
+  const uint32_t m = dc.thr16 != 0 ? dropout_keep8(dc, (uint64_t)g) : 0xffu;
+  for (int e = 0; e < 8 && g * 8 + e < n; ++e) keep[g * 8 + e] = (m >> e) & 1u;
+}
+
 }  // namespace tnr
 
 using namespace tnr;
+
+TNR_API int tnr_dropout_mask(const tnr_dropout* drop, long long n, unsigned char* keep, void* stream) {
+  if (n == 0) return 0;
+  const long long groups = (n + 7) / 8;
+  dropout_mask_kernel<<<(int)((groups + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(drop_or_none(drop), n, keep);
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
 
 TNR_API int tnr_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, void* shadow_bf16, long long n,
                              float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {

@@ -10,7 +10,7 @@ constexpr int ROWS_PER_BLOCK = 8;   // 8 warps
 template <int VPL>   // 8-element vectors per lane: E = VPL * 256
 __device__ __forceinline__ void ln_row(float (&x)[VPL * 8], const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, int lane,
-                                       __nv_bfloat16* __restrict__ out) {
+                                       __nv_bfloat16* __restrict__ out, const DropCfg& dc, uint64_t row) {
   constexpr int E = VPL * 256;
   float s = 0.f;
 #pragma unroll
@@ -32,6 +32,11 @@ __device__ __forceinline__ void ln_row(float (&x)[VPL * 8], const float* __restr
     float y[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) y[i] = (x[v * 8 + i] - mean) * rstd * g[i] + b[i];
+    if (dc.thr16 != 0) {
+      const uint32_t keep = dropout_keep8(dc, (row * (uint64_t)E + (uint64_t)col) >> 3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = ((keep >> i) & 1u) ? y[i] * dc.scale : 0.f;
+    }
     *reinterpret_cast<bf16x8*>(out + col) = pack8(y);
   }
 }
@@ -43,11 +48,12 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 embed_ln_kernel(const int64_t* __restrict__ ids, int ids_ld, int L, int n_tokens, int vocab,
                 const void* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type0,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                __nv_bfloat16* __restrict__ out) {
+                __nv_bfloat16* __restrict__ out, const tnr_dropout drop) {
   constexpr int E = VPL * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * ROWS_PER_BLOCK + warp;
   if (t >= n_tokens) return;
+  const DropCfg dc = load_drop(drop);
   const int n = t / L, l = t - n * L;
   long long id = ids[(size_t)n * ids_ld + l];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);     // defensive clamp (torch would raise)
@@ -72,7 +78,7 @@ embed_ln_kernel(const int64_t* __restrict__ ids, int ids_ld, int L, int n_tokens
     x[v * 8 + 4] = w[4] + p1.x + t1.x; x[v * 8 + 5] = w[5] + p1.y + t1.y;
     x[v * 8 + 6] = w[6] + p1.z + t1.z; x[v * 8 + 7] = w[7] + p1.w + t1.w;
   }
-  ln_row<VPL>(x, gamma, beta, eps, lane, out + (size_t)t * E);
+  ln_row<VPL>(x, gamma, beta, eps, lane, out + (size_t)t * E, dc, (uint64_t)t);
 }
 
 // y = LN(x) for a bf16 "pre-LN" buffer (dense + bias + residual written by the GEMM epilogue)
@@ -88,7 +94,8 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int rows, const float*
 #pragma unroll
   for (int i = 0; i < VPL; ++i)
     unpack8(*reinterpret_cast<const bf16x8*>(x + (size_t)r * E + (i * 32 + lane) * 8), &v[i * 8]);
-  ln_row<VPL>(v, gamma, beta, eps, lane, y + (size_t)r * E);
+  DropCfg dc; dc.seed = 0; dc.site = 0; dc.thr16 = 0; dc.scale = 1.f;
+  ln_row<VPL>(v, gamma, beta, eps, lane, y + (size_t)r * E, dc, 0);
 }
 
 // LayerNorm backward.  xhat recomputed from the saved pre-LN row.
@@ -99,8 +106,10 @@ template <int VPL>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, int rows,
                      const float* __restrict__ gamma, float eps, __nv_bfloat16* __restrict__ dx,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_drop,
+                     const tnr_dropout drop) {
   constexpr int E = VPL * 256;
+  const DropCfg dc = load_drop(drop);
   __shared__ float s_dg[E];
   __shared__ float s_db[E];
   for (int i = threadIdx.x; i < E; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
@@ -153,6 +162,14 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = rstd * (dv[v * 8 + i] - sg - xv[v * 8 + i] * sgx);
       *reinterpret_cast<bf16x8*>(dx + (size_t)r * E + (v * 32 + lane) * 8) = pack8(o);
+      if (dx_drop != nullptr) {
+        if (dc.thr16 != 0) {
+          const uint32_t keep = dropout_keep8(dc, ((uint64_t)r * (uint64_t)E + (uint64_t)((v * 32 + lane) * 8)) >> 3);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * dc.scale : 0.f;
+        }
+        *reinterpret_cast<bf16x8*>(dx_drop + (size_t)r * E + (v * 32 + lane) * 8) = pack8(o);
+      }
     }
   }
 #pragma unroll
@@ -216,7 +233,7 @@ using namespace tnr;
 
 extern "C" __attribute__((visibility("default"))) int tnr_embed_ln_fwd(const int64_t* ids, int ids_ld, int n_rows, int L, int vocab, const void* word,
                                 int word_dtype, const float* pos, const float* type0, const float* gamma,
-                                const float* beta, float eps, int E, void* out_bf16, void* stream) {
+                                const float* beta, float eps, int E, void* out_bf16, const tnr_dropout* drop, void* stream) {
   TNR_REQUIRE(E % 256 == 0, "tnr_embed_ln_fwd: E=%d must be a multiple of 256", E);
   TNR_REQUIRE(n_rows >= 0 && L > 0, "tnr_embed_ln_fwd: bad shape");
   if (n_rows == 0) return 0;
@@ -226,10 +243,10 @@ extern "C" __attribute__((visibility("default"))) int tnr_embed_ln_fwd(const int
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   if (word_dtype == TNR_BF16) {
     DISPATCH_VPL(E, (embed_ln_kernel<VPL, true><<<grid, ROWS_PER_BLOCK * 32, 0, st>>>(
-                        ids, ids_ld, L, n_tokens, vocab, word, pos, type0, gamma, beta, eps, out)));
+                        ids, ids_ld, L, n_tokens, vocab, word, pos, type0, gamma, beta, eps, out, drop_or_none(drop))));
   } else {
     DISPATCH_VPL(E, (embed_ln_kernel<VPL, false><<<grid, ROWS_PER_BLOCK * 32, 0, st>>>(
-                        ids, ids_ld, L, n_tokens, vocab, word, pos, type0, gamma, beta, eps, out)));
+                        ids, ids_ld, L, n_tokens, vocab, word, pos, type0, gamma, beta, eps, out, drop_or_none(drop))));
   }
   TNR_LAUNCH_CHECK();
   return 0;
@@ -248,7 +265,8 @@ extern "C" __attribute__((visibility("default"))) int tnr_layernorm_fwd(const vo
 }
 
 extern "C" __attribute__((visibility("default"))) int tnr_layernorm_bwd(const void* dy_bf16, const void* x_bf16, int rows, int E, const float* gamma, float eps,
-                                 void* dx_bf16, float* dgamma, float* dbeta, void* stream) {
+                                 void* dx_bf16, float* dgamma, float* dbeta, void* dx_drop_bf16, const tnr_dropout* drop,
+                                 void* stream) {
   if (rows == 0) return 0;
   int grid = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
   const int cap = num_sms() * 4;
@@ -256,7 +274,8 @@ extern "C" __attribute__((visibility("default"))) int tnr_layernorm_bwd(const vo
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   DISPATCH_VPL(E, (layernorm_bwd_kernel<VPL><<<grid, ROWS_PER_BLOCK * 32, 0, st>>>(
                       reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16),
-                      rows, gamma, eps, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta)));
+                      rows, gamma, eps, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta,
+                      reinterpret_cast<__nv_bfloat16*>(dx_drop_bf16), drop_or_none(drop))));
   TNR_LAUNCH_CHECK();
   return 0;
 }

@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ACT_DGELU, ACT_GELU, ACT_NONE, ACT_TANH, BF16, F32, GemmArgs  # noqa: F401
+from ._lib import ACT_DGELU, ACT_GELU, ACT_NONE, ACT_TANH, BF16, F32, Dropout, GemmArgs  # noqa: F401
 
 _bf16 = torch.bfloat16
 _f32 = torch.float32
@@ -27,6 +27,28 @@ def _chk(t, dtype, name):
 
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def make_drop(seed_tensor, site, p):
+    """tnr_dropout for dropout tensor ``site``; ``seed_tensor`` is a 1-element CUDA int64 tensor
+    (the kernels read the seed from device memory).  Returns None when p == 0."""
+    if seed_tensor is None or not p > 0.0:
+        return None
+    d = Dropout()
+    d.seed, d.site, d.p = seed_tensor.data_ptr(), int(site), float(p)
+    return d
+
+
+def _dp(d):
+    return ctypes.byref(d) if d is not None else None
+
+
+def dropout_mask(drop, n, device):
+    """keep flags (uint8 [n]) of dropout tensor ``drop`` by linear element index (tests)."""
+    keep = torch.empty(n, device=device, dtype=torch.uint8)
+    lib = _ready(keep)
+    _lib.check(lib.tnr_dropout_mask(_dp(drop), n, _ptr(keep), _stream()), "tnr_dropout_mask")
+    return keep
 
 
 class _Stats:
@@ -47,7 +69,7 @@ def _ready(t, kernels=1):
 
 
 def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, aux=None,
-         split_k=1, accumulate=False):
+         split_k=1, accumulate=False, drop=None):
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).
 
     a: bf16 [M,K] (or [K,M] when ``a_t``); b: bf16 [N,K] (or [K,N] when ``b_t``); 2-D, unit
@@ -83,6 +105,8 @@ def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_N
         g.aux, g.ldaux = aux.data_ptr(), aux.stride(0)
     g.split_k = split_k
     g.accumulate = int(accumulate)
+    if drop is not None:
+        g.drop = ctypes.pointer(drop)
     if stats.gemm_events is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -94,7 +118,7 @@ def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_N
     return out
 
 
-def embed_ln(x, L, word, pos, type0, gamma, beta, eps, out):
+def embed_ln(x, L, word, pos, type0, gamma, beta, eps, out, drop=None):
     """x: int64 [n, 2L] (ids | mask) -> out bf16 [n*L, E]."""
     lib = _ready(x)
     _chk(x, torch.int64, "embed_ln.x")
@@ -104,7 +128,7 @@ def embed_ln(x, L, word, pos, type0, gamma, beta, eps, out):
     _lib.check(lib.tnr_embed_ln_fwd(_ptr(x), x.stride(0), n, L, word.shape[0], _ptr(word), wd,
                                     _ptr(_chk(pos, _f32, "pos")), _ptr(_chk(type0, _f32, "type0")),
                                     _ptr(_chk(gamma, _f32, "gamma")), _ptr(_chk(beta, _f32, "beta")),
-                                    eps, E, _ptr(_chk(out, _bf16, "out")), _stream()), "tnr_embed_ln_fwd")
+                                    eps, E, _ptr(_chk(out, _bf16, "out")), _dp(drop), _stream()), "tnr_embed_ln_fwd")
     return out
 
 
@@ -116,13 +140,13 @@ def layernorm_fwd(x, gamma, beta, eps, out):
     return out
 
 
-def layernorm_bwd(dy, x, gamma, eps, dx, dgamma, dbeta):
+def layernorm_bwd(dy, x, gamma, eps, dx, dgamma, dbeta, dx_drop=None, drop=None):
     lib = _ready(x)
     rows, E = x.shape
     _lib.check(lib.tnr_layernorm_bwd(_ptr(_chk(dy, _bf16, "ln.dy")), _ptr(_chk(x, _bf16, "ln.x")), rows, E,
                                      _ptr(gamma), eps, _ptr(_chk(dx, _bf16, "ln.dx")),
                                      _ptr(_chk(dgamma, _f32, "dgamma")), _ptr(_chk(dbeta, _f32, "dbeta")),
-                                     _stream()), "tnr_layernorm_bwd")
+                                     _ptr(dx_drop), _dp(drop), _stream()), "tnr_layernorm_bwd")
     return dx
 
 
@@ -133,7 +157,7 @@ def colsum(x, out):
     return out
 
 
-def attn_fwd(qkv, x, L, relpos, ctx, A):
+def attn_fwd(qkv, x, L, relpos, ctx, A, drop=None):
     """qkv bf16 [n*L, 3E]; x int64 [n, 2L] (mask = columns L..2L); relpos fp32 [A,L,L]."""
     lib = _ready(qkv)
     n = x.shape[0]
@@ -141,18 +165,18 @@ def attn_fwd(qkv, x, L, relpos, ctx, A):
     mask_ptr = ctypes.c_void_p(x.data_ptr() + 8 * L)
     _lib.check(lib.tnr_attn_relpos_fwd(_ptr(_chk(qkv, _bf16, "attn.qkv")), mask_ptr, x.stride(0),
                                        _ptr(_chk(relpos, _f32, "relpos")), _ptr(_chk(ctx, _bf16, "ctx")),
-                                       n, L, A, E, _stream()), "tnr_attn_relpos_fwd")
+                                       n, L, A, E, _dp(drop), _stream()), "tnr_attn_relpos_fwd")
     return ctx
 
 
-def attn_bwd(qkv, x, L, relpos, dctx, dqkv, A):
+def attn_bwd(qkv, x, L, relpos, dctx, dqkv, A, drop=None):
     lib = _ready(qkv)
     n = x.shape[0]
     E = qkv.shape[1] // 3
     mask_ptr = ctypes.c_void_p(x.data_ptr() + 8 * L)
     _lib.check(lib.tnr_attn_relpos_bwd(_ptr(_chk(qkv, _bf16, "attn.qkv")), mask_ptr, x.stride(0),
                                        _ptr(relpos), _ptr(_chk(dctx, _bf16, "dctx")),
-                                       _ptr(_chk(dqkv, _bf16, "dqkv")), n, L, A, E, _stream()),
+                                       _ptr(_chk(dqkv, _bf16, "dqkv")), n, L, A, E, _dp(drop), _stream()),
                "tnr_attn_relpos_bwd")
     return dqkv
 
