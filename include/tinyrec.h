@@ -143,11 +143,21 @@ int tnr_attnpool_bwd(const void* x_bf16, const void* e_bf16, int ldq, int Q, con
 int tnr_user_encoder_fwd(const float* vecs, const float* mask, const float* pad_doc, const float* W1,
                          const float* b1, const float* w2, const float* b2, int use_mask, float* user,
                          float* a_out, float* e_out, int B, int H, int D, int Q, void* stream);
-/* d_user [B,D] -> d_vecs += [B*H, D]; dpad/dW1/db1/dw2/db2 += (fp32 atomics). */
+/* The same for n_enc (<= 9) encoders sharing `mask` in ONE launch (grid B x n_enc): the student
+ * user encoder and the M teacher user encoders of Model.forward (model_bert.py:269,281). */
+typedef struct {
+  const float *vecs, *pad_doc, *W1, *b1, *w2, *b2;
+  float *user, *a_out, *e_out;
+} tnr_user_encoder_io;
+int tnr_user_encoder_fwd_multi(const tnr_user_encoder_io* enc, int n_enc, const float* mask, int use_mask,
+                               int B, int H, int D, int Q, void* stream);
+/* d_user [B,D] -> d_vecs += [B*H, D]; dpad/dW1/db1/dw2/db2 += (fp32 atomics).
+ * scratch: fp32 [B*H*(Q+D)] workspace (grad at the fc1 pre-activation + blended inputs; dW1 is then
+ * one TN GEMM over all impressions). */
 int tnr_user_encoder_bwd(const float* vecs, const float* mask, const float* pad_doc, const float* W1,
                          const float* w2, int use_mask, const float* a_in, const float* e_in,
                          const float* d_user, float* d_vecs, float* dpad, float* dW1, float* db1,
-                         float* dw2, float* db2, int B, int H, int D, int Q, void* stream);
+                         float* dw2, float* db2, float* scratch, int B, int H, int D, int Q, void* stream);
 
 /* Click score + CE + multi-teacher KD loss and its gradients in one pass.
  * Row layout of the [R, D] news matrices: history block (b,h) -> b*H+h, then candidate block
@@ -163,7 +173,7 @@ int tnr_kd_loss_fwdbwd(const float* s_news, const float* s_user, const int64_t* 
                        float temperature, float coef, int want_grad, float* score_out, float* losses,
                        float* d_news, float* d_user, float* G_ext, void* stream);
 
-/* Small batched fp32 GEMMs for transform_matrix (model_bert.py:277-278,283):
+/* Small batched fp32 GEMMs (TF32 mma.sync, fp32 accumulate) for transform_matrix (model_bert.py:277-278,283):
  *   nt:     C[b][M,N]  = A[b][M,K] . B[b][N,K]^T + bias[b][N]
  *   tn_acc: C[b][N1,N2] += A[b][R,N1]^T . B[b][R,N2];  cbias[b][N1] += colsum(A[b])   */
 int tnr_sgemm_nt(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,

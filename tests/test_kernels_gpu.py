@@ -337,3 +337,94 @@ def test_attnpool_fwd_bwd(with_mask):
     assert _rel_err(du, du_ref.reshape(n * S, Q))[0] < 6e-3
     assert _rel_err(dw2, w2f.grad)[0] < 1e-3
     assert _rel_err(db2, b2f.grad)[0] < 1e-3 or float(b2f.grad.abs()) < 1e-5
+
+
+# ------------------------------------------------------------------ fp32 head (TF32 mma path)
+def _ue_ref(vecs, mask, pad, W1, b1, w2, b2, use_mask):
+    """model_bert.py:155-176 (NAML) + :15-34 in torch fp32."""
+    if use_mask:
+        v = vecs
+    else:
+        v = vecs * mask.unsqueeze(-1) + pad.view(1, 1, -1) * (1 - mask.unsqueeze(-1))
+    e = torch.tanh(v @ W1.t() + b1)
+    alpha = torch.exp(e @ w2 + b2)
+    if use_mask:
+        alpha = alpha * mask
+    a = alpha / (alpha.sum(1, keepdim=True) + 1e-8)
+    return (a.unsqueeze(-1) * v).sum(1), a, e
+
+
+@pytest.mark.parametrize("use_mask", [False, True])
+@pytest.mark.parametrize("H,Q", [(50, 200), (13, 64), (64, 256)])
+def test_user_encoder_multi_fwd_bwd(use_mask, H, Q):
+    ops = _ops()
+    B, D, n_enc = 7, 256, 3
+    f32 = torch.float32
+    mask = (torch.rand(B, H, device="cuda") > 0.3).float()
+    mask[1] = 0                                   # all-masked history
+    mask[2] = 1
+    encs, refs, leaves = [], [], []
+    for i in range(n_enc):
+        vecs = _randn(B, H, D, dtype=f32, scale=0.5, seed=10 * i + 1)
+        pad = _randn(D, dtype=f32, scale=0.5, seed=10 * i + 2)
+        W1 = _randn(Q, D, dtype=f32, scale=0.06, seed=10 * i + 3)
+        b1, w2, b2 = _randn(Q, dtype=f32, scale=0.1, seed=10 * i + 4), _randn(Q, dtype=f32, scale=0.1, seed=10 * i + 5), _randn(1, dtype=f32, seed=10 * i + 6)
+        lv = [t.clone().requires_grad_(True) for t in (vecs, pad, W1, b1, w2, b2)]
+        leaves.append(lv)
+        refs.append(_ue_ref(lv[0], mask, *lv[1:], use_mask))
+        encs.append(dict(vecs=vecs.view(B * H, D), pad_doc=pad, W1=W1, b1=b1, w2=w2, b2=b2,
+                         user=torch.empty(B, D, device="cuda"), a=torch.empty(B, H, device="cuda"),
+                         e=torch.empty(B, H, Q, device="cuda") if i == 0 else None))
+    ops.user_encoder_fwd_multi(encs, mask, use_mask, B, H)
+    for enc, (u, a, e) in zip(encs, refs):
+        assert _rel_err(enc["user"], u)[0] < 2e-3
+        assert _rel_err(enc["a"], a)[0] < 2e-3
+        if use_mask:
+            assert float(enc["user"][1].abs().max()) == 0.0          # 0 / (0 + 1e-8) -> exact zero
+    assert _rel_err(encs[0]["e"], refs[0][2])[0] < 2e-3
+    # backward of encoder 0
+    d_user = _randn(B, D, dtype=f32, seed=99)
+    refs[0][0].backward(d_user)
+    v0, pad0, W10, b10, w20, b20 = leaves[0]
+    d_vecs = _randn(B * H, D, dtype=f32, seed=98)                   # accumulates into existing gradient
+    base = d_vecs.clone()
+    dpad, dW1 = torch.zeros(D, device="cuda"), torch.zeros(Q, D, device="cuda")
+    db1, dw2, db2 = torch.zeros(Q, device="cuda"), torch.zeros(Q, device="cuda"), torch.zeros(1, device="cuda")
+    scratch = torch.empty(B * H * (Q + D), device="cuda")
+    e_exact = refs[0][2].detach().contiguous()
+    a_exact = refs[0][1].detach().contiguous()
+    ops.user_encoder_bwd(encs[0]["vecs"], mask, encs[0]["pad_doc"], encs[0]["W1"], encs[0]["w2"], use_mask, a_exact, e_exact,
+                         d_user, d_vecs, dpad, dW1, db1, dw2, db2, scratch, B, H)
+    assert _rel_err(d_vecs - base, v0.grad.reshape(B * H, D))[0] < 3e-3
+    assert _rel_err(dW1, W10.grad)[0] < 3e-3
+    assert _rel_err(db1, b10.grad)[0] < 3e-3
+    assert _rel_err(dw2, w20.grad)[0] < 3e-3
+    assert _rel_err(db2, b20.grad)[0] < 3e-3 or float(b20.grad.abs().max()) < 1e-4
+    if not use_mask:
+        assert _rel_err(dpad, pad0.grad)[0] < 3e-3
+
+
+@pytest.mark.parametrize("M,N,K,batch", [(1792, 256, 256, 4), (100, 72, 40, 1), (65, 200, 256, 2)])
+def test_sgemm_nt_tf32(M, N, K, batch):
+    ops = _ops()
+    f32 = torch.float32
+    A, Bm = _randn(batch, M, K, dtype=f32, seed=1), _randn(batch, N, K, dtype=f32, seed=2)
+    bias = _randn(batch, N, dtype=f32, seed=3)
+    C = torch.empty(batch, M, N, device="cuda")
+    ops.sgemm_nt(A, Bm, bias, C, M, N, K, batch, M * K, N * K, N, M * N)
+    ref = torch.einsum("bmk,bnk->bmn", A.double(), Bm.double()).float() + bias[:, None, :]
+    assert _rel_err(C, ref)[0] < 1e-3                        # TF32 inputs (10-bit mantissa), fp32 accumulate
+
+
+@pytest.mark.parametrize("R,N1,N2,batch", [(1792, 256, 256, 4), (1600, 200, 256, 1), (37, 64, 72, 2)])
+def test_sgemm_tn_acc_tf32(R, N1, N2, batch):
+    ops = _ops()
+    f32 = torch.float32
+    A, Bm = _randn(batch, R, N1, dtype=f32, seed=1), _randn(batch, R, N2, dtype=f32, seed=2)
+    C = _randn(batch, N1, N2, dtype=f32, seed=3)
+    cb = _randn(batch, N1, dtype=f32, seed=4)
+    C0, cb0 = C.clone(), cb.clone()
+    ops.sgemm_tn_acc(A, Bm, C, cb, R, N1, N2, batch, R * N1, R * N2, N1 * N2, N1)
+    ref = torch.einsum("brm,brn->bmn", A.double(), Bm.double()).float()
+    assert _rel_err(C - C0, ref)[0] < 1e-3
+    assert _rel_err(cb - cb0, A.sum(1))[0] < 1e-4

@@ -23,6 +23,11 @@ class Dropout(Structure):
     _fields_ = [("seed", c_void_p), ("site", c_uint), ("p", c_float)]
 
 
+class UserEncoderIO(Structure):
+    """tnr_user_encoder_io"""
+    _fields_ = [(n, c_void_p) for n in ("vecs", "pad_doc", "W1", "b1", "w2", "b2", "user", "a_out", "e_out")]
+
+
 class GemmArgs(Structure):
     _fields_ = [("M", c_int), ("N", c_int), ("K", c_int),
                 ("A", c_void_p), ("lda", c_int), ("a_mn_major", c_int),
@@ -52,7 +57,8 @@ _SIGNATURES = {
     "tnr_attnpool_fwd": ([P, P, c_int, c_int, P, P, P, P, P, c_int, c_int, c_int, P], c_int),
     "tnr_attnpool_bwd": ([P, P, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_int, P], c_int),
     "tnr_user_encoder_fwd": ([P, P, P, P, P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
-    "tnr_user_encoder_bwd": ([P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
+    "tnr_user_encoder_fwd_multi": ([P, c_int, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "tnr_user_encoder_bwd": ([P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "tnr_kd_loss_fwdbwd": ([P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P, P],
                            c_int),
     "tnr_sgemm_nt": ([P, P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, P], c_int),

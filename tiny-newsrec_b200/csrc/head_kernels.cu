@@ -1,8 +1,6 @@
-// fp32 "head" of the model: additive-attention user encoder (forward / backward), click
-// scoring + cross-entropy + multi-teacher KD loss with its gradients, and the small fp32
-// GEMMs of the per-teacher projection (transform_matrix) forward / weight gradient.
-// All of this is latency / HBM bound (a few MB per step) -> warp-shuffle reductions,
-// shared-memory staging, one block per impression.
+// fp32 "head" of the model: click scoring + cross-entropy + multi-teacher KD loss with its
+// gradients (the user encoders and the transform_matrix GEMMs live in head_mma.cu).
+// Latency / HBM bound (a few MB per step) -> warp-shuffle reductions, one block per impression.
 //
 // Reference: Tiny-NewsRec/model_bert.py:155-176 (UserEncoder, NAML branches), :15-34
 // (AttentionPooling), :204 (score), :208-219 (kd_ce_loss), :222-244 (hid_mse_loss),
@@ -23,181 +21,6 @@ __device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
 #pragma unroll
   for (int i = 0; i < UE_THREADS / 32; ++i) t += red[i];
   return t;
-}
-
-// ----------------------------------------------------------------------------------
-// user encoder forward.  vecs: row (b, h) at vecs + (b*H + h) * D.
-//   blend (user_log_mask == 0): v = vec*m + pad_doc*(1-m); alpha unmasked
-//   mask  (user_log_mask == 1): v = vec;  alpha *= m
-// outputs user [B, D]; a [B, H] (normalised weights); e [B, H, Q] (tanh activations)
-// smem: v [H][D] + e [H][Qp] + z[H]
-// ----------------------------------------------------------------------------------
-template <int HMAX>
-__global__ void __launch_bounds__(UE_THREADS)
-user_encoder_fwd_kernel(const float* __restrict__ vecs, const float* __restrict__ mask, const float* __restrict__ pad_doc,
-                        const float* __restrict__ W1, const float* __restrict__ b1, const float* __restrict__ w2,
-                        const float* __restrict__ b2, int use_mask, float* __restrict__ user, float* __restrict__ a_out,
-                        float* __restrict__ e_out, int H, int D, int Q) {
-  extern __shared__ __align__(16) float sm[];
-  float* sv = sm;                       // [H][D]
-  float* se = sv + (size_t)H * D;       // [H][Q]
-  float* sz = se + (size_t)H * Q;       // [H]
-  __shared__ float s_inv;
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < H * D; i += UE_THREADS) {
-    const int h = i / D, d = i - h * D;
-    float v = vecs[((size_t)b * H + h) * D + d];
-    if (!use_mask) {
-      const float m = mask[(size_t)b * H + h];
-      v = v * m + pad_doc[d] * (1.0f - m);
-    }
-    sv[i] = v;
-  }
-  __syncthreads();
-  // e[h][q] = tanh(b1[q] + v[h] . W1[q])  -- thread q keeps acc[h] in registers
-  for (int q = tid; q < Q; q += UE_THREADS) {
-    float acc[HMAX];
-#pragma unroll
-    for (int h = 0; h < HMAX; ++h) acc[h] = 0.f;
-    const float* wrow = W1 + (size_t)q * D;
-    for (int d = 0; d < D; d += 4) {
-      const float4 w = *reinterpret_cast<const float4*>(wrow + d);
-#pragma unroll
-      for (int h = 0; h < HMAX; ++h) {
-        if (h < H) {
-          const float4 x = *reinterpret_cast<const float4*>(sv + (size_t)h * D + d);
-          acc[h] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[h]))));
-        }
-      }
-    }
-    const float bq = b1[q];
-#pragma unroll
-    for (int h = 0; h < HMAX; ++h)
-      if (h < H) se[(size_t)h * Q + q] = tanhf(acc[h] + bq);
-  }
-  __syncthreads();
-  for (int h = warp; h < H; h += UE_THREADS / 32) {
-    float t = 0.f;
-    for (int q = lane; q < Q; q += 32) t = fmaf(se[(size_t)h * Q + q], w2[q], t);
-    t = warp_sum(t);
-    if (lane == 0) {
-      float al = __expf(t + b2[0]);
-      if (use_mask) al *= mask[(size_t)b * H + h];
-      sz[h] = al;
-    }
-  }
-  __syncthreads();
-  if (warp == 0) {
-    float t = 0.f;
-    for (int h = lane; h < H; h += 32) t += sz[h];
-    t = warp_sum(t);
-    if (lane == 0) s_inv = 1.0f / (t + 1e-8f);
-  }
-  __syncthreads();
-  const float inv = s_inv;
-  for (int h = tid; h < H; h += UE_THREADS) a_out[(size_t)b * H + h] = sz[h] * inv;
-  for (int d = tid; d < D; d += UE_THREADS) {
-    float acc = 0.f;
-    for (int h = 0; h < H; ++h) acc = fmaf(sz[h] * inv, sv[(size_t)h * D + d], acc);
-    user[(size_t)b * D + d] = acc;
-  }
-  if (e_out != nullptr)
-    for (int i = tid; i < H * Q; i += UE_THREADS) e_out[(size_t)b * H * Q + i] = se[i];
-}
-
-// ----------------------------------------------------------------------------------
-// user encoder backward (student).  d_user [B, D] -> d_vecs (+=) [B*H, D] and parameter
-// gradients (fp32 atomics into dpad [D], dW1 [Q, D], db1 [Q], dw2 [Q], db2 [1]).
-// ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(UE_THREADS)
-user_encoder_bwd_kernel(const float* __restrict__ vecs, const float* __restrict__ mask, const float* __restrict__ pad_doc,
-                        const float* __restrict__ W1, const float* __restrict__ w2, int use_mask,
-                        const float* __restrict__ a_in, const float* __restrict__ e_in, const float* __restrict__ d_user,
-                        float* __restrict__ d_vecs, float* __restrict__ dpad, float* __restrict__ dW1,
-                        float* __restrict__ db1, float* __restrict__ dw2, float* __restrict__ db2, int H, int D, int Q) {
-  extern __shared__ __align__(16) float sm[];
-  float* sv = sm;                        // [H][D] blended inputs
-  float* sdu = sv + (size_t)H * D;       // [H][Q]  grad at fc1 pre-activation
-  float* sa = sdu + (size_t)H * Q;       // [H]
-  float* sdz = sa + H;                   // [H]
-  float* sdusr = sdz + H;                // [D]
-  __shared__ float s_dot;
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < H * D; i += UE_THREADS) {
-    const int h = i / D, d = i - h * D;
-    float v = vecs[((size_t)b * H + h) * D + d];
-    if (!use_mask) {
-      const float m = mask[(size_t)b * H + h];
-      v = v * m + pad_doc[d] * (1.0f - m);
-    }
-    sv[i] = v;
-  }
-  for (int h = tid; h < H; h += UE_THREADS) sa[h] = a_in[(size_t)b * H + h];
-  for (int d = tid; d < D; d += UE_THREADS) sdusr[d] = d_user[(size_t)b * D + d];
-  __syncthreads();
-  for (int h = warp; h < H; h += UE_THREADS / 32) {       // da_h = d_user . v_h
-    float t = 0.f;
-    for (int d = lane; d < D; d += 32) t = fmaf(sdusr[d], sv[(size_t)h * D + d], t);
-    t = warp_sum(t);
-    if (lane == 0) sdz[h] = t;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    float t = 0.f;
-    for (int h = lane; h < H; h += 32) t += sa[h] * sdz[h];
-    t = warp_sum(t);
-    if (lane == 0) s_dot = t;
-  }
-  __syncthreads();
-  const float dot = s_dot;
-  for (int h = tid; h < H; h += UE_THREADS) sdz[h] = sa[h] * (sdz[h] - dot);
-  __syncthreads();
-  // du[h][q] = dz_h * w2_q * (1 - e^2); dw2_q, db1_q
-  for (int q = tid; q < Q; q += UE_THREADS) {
-    const float w = w2[q];
-    float gw2 = 0.f, gb1 = 0.f;
-    for (int h = 0; h < H; ++h) {
-      const float ev = e_in[((size_t)b * H + h) * Q + q];
-      const float dz = sdz[h];
-      gw2 = fmaf(dz, ev, gw2);
-      const float du = dz * w * (1.0f - ev * ev);
-      sdu[(size_t)h * Q + q] = du;
-      gb1 += du;
-    }
-    atomicAdd(dw2 + q, gw2);
-    atomicAdd(db1 + q, gb1);
-  }
-  if (warp == 0) {
-    float t = 0.f;
-    for (int h = lane; h < H; h += 32) t += sdz[h];
-    t = warp_sum(t);
-    if (lane == 0) atomicAdd(db2, t);
-  }
-  __syncthreads();
-  // thread d: dW1[q][d] += sum_h du[h][q] v[h][d];   dv[h][d] = a_h dusr_d + sum_q du[h][q] W1[q][d]
-  for (int d = tid; d < D; d += UE_THREADS) {
-    for (int q = 0; q < Q; ++q) {
-      float t = 0.f;
-      for (int h = 0; h < H; ++h) t = fmaf(sdu[(size_t)h * Q + q], sv[(size_t)h * D + d], t);
-      atomicAdd(dW1 + (size_t)q * D + d, t);
-    }
-    float gpad = 0.f;
-    for (int h = 0; h < H; ++h) {
-      float t = sa[h] * sdusr[d];
-      for (int q = 0; q < Q; ++q) t = fmaf(sdu[(size_t)h * Q + q], W1[(size_t)q * D + d], t);
-      float* dst = d_vecs + ((size_t)b * H + h) * D + d;
-      if (use_mask) {
-        *dst += t;
-      } else {
-        const float m = mask[(size_t)b * H + h];
-        *dst += t * m;
-        gpad = fmaf(t, 1.0f - m, gpad);
-      }
-    }
-    if (!use_mask) atomicAdd(dpad + d, gpad);
-  }
 }
 
 // ----------------------------------------------------------------------------------
@@ -228,7 +51,6 @@ kd_loss_kernel(const float* __restrict__ s_news, const float* __restrict__ s_use
   const int R = B * (H + K);
   const size_t Rext = (size_t)R + B;
   const float* cand = s_news + ((size_t)B * H + (size_t)b * K) * D;
-  const float* hist = s_news + (size_t)b * H * D;
   const float* usr = s_user + (size_t)b * D;
   const int lab = (int)label[b];
   const float invB = 1.0f / (float)B;
@@ -353,139 +175,11 @@ kd_loss_kernel(const float* __restrict__ s_news, const float* __restrict__ s_use
   }
 }
 
-// ----------------------------------------------------------------------------------
-// small fp32 GEMMs (SIMT, 64x64 tiles, 4x4 per thread), batched over blockIdx.z
-//   NT: C[M,N] = A[M,K] . B[N,K]^T + bias[N]
-//   TN: C[N1,N2] += A[R,N1]^T . B[R,N2];  cbias[N1] += colsum(A)
-// ----------------------------------------------------------------------------------
-constexpr int SG_T = 64, SG_K = 16;
-
-__global__ void __launch_bounds__(256)
-sgemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ Bm, const float* __restrict__ bias,
-                float* __restrict__ C, int M, int N, int K, long long sA, long long sB, long long sbias, long long sC) {
-  __shared__ float As[SG_K][SG_T + 4];
-  __shared__ float Bs[SG_K][SG_T + 4];
-  A += blockIdx.z * sA; Bm += blockIdx.z * sB; C += blockIdx.z * sC;
-  if (bias) bias += blockIdx.z * sbias;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * SG_T, n0 = blockIdx.x * SG_T;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += SG_K) {
-    for (int i = tid; i < SG_T * SG_K; i += 256) {
-      const int r = i / SG_K, c = i - r * SG_K;
-      As[c][r] = (m0 + r < M && k0 + c < K) ? A[(size_t)(m0 + r) * K + k0 + c] : 0.f;
-      Bs[c][r] = (n0 + r < N && k0 + c < K) ? Bm[(size_t)(n0 + r) * K + k0 + c] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < SG_K; ++k) {
-      float a[4], bb[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; bb[i] = Bs[k][tx * 4 + i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n < N) C[(size_t)m * N + n] = acc[i][j] + (bias ? bias[n] : 0.f);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-sgemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C, float* __restrict__ cbias,
-                int R, int N1, int N2, long long sA, long long sB, long long sC, long long sbias) {
-  __shared__ float As[SG_K][SG_T + 4];
-  __shared__ float Bs[SG_K][SG_T + 4];
-  A += blockIdx.z * sA; Bm += blockIdx.z * sB; C += blockIdx.z * sC;
-  if (cbias) cbias += blockIdx.z * sbias;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int i0 = blockIdx.y * SG_T, j0 = blockIdx.x * SG_T;
-  float acc[4][4] = {};
-  float bsum[4] = {};
-  for (int r0 = 0; r0 < R; r0 += SG_K) {
-    for (int i = tid; i < SG_T * SG_K; i += 256) {
-      const int r = i / SG_T, c = i - r * SG_T;
-      As[r][c] = (r0 + r < R && i0 + c < N1) ? A[(size_t)(r0 + r) * N1 + i0 + c] : 0.f;
-      Bs[r][c] = (r0 + r < R && j0 + c < N2) ? Bm[(size_t)(r0 + r) * N2 + j0 + c] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < SG_K; ++k) {
-      float a[4], bb[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; bb[i] = Bs[k][tx * 4 + i]; bsum[i] += a[i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = i0 + ty * 4 + i;
-    if (m >= N1) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = j0 + tx * 4 + j;
-      if (n < N2) C[(size_t)m * N2 + n] += acc[i][j];
-    }
-    if (cbias != nullptr && blockIdx.x == 0 && tx == 0) cbias[m] += bsum[i];
-  }
-}
-
 }  // namespace tnr
 
 using namespace tnr;
 
 #define TNR_API extern "C" __attribute__((visibility("default")))
-
-static int ue_smem_fwd(int H, int D, int Q) { return (H * D + H * Q + H) * 4; }
-static int ue_smem_bwd(int H, int D, int Q) { return (H * D + H * Q + 2 * H + D) * 4; }
-
-TNR_API int tnr_user_encoder_fwd(const float* vecs, const float* mask, const float* pad_doc, const float* W1,
-                                 const float* b1, const float* w2, const float* b2, int use_mask, float* user,
-                                 float* a_out, float* e_out, int B, int H, int D, int Q, void* stream) {
-  TNR_REQUIRE(H >= 1 && H <= 64, "tnr_user_encoder_fwd: history length %d not supported (1..64)", H);
-  TNR_REQUIRE(D % 4 == 0, "tnr_user_encoder_fwd: D must be a multiple of 4");
-  if (B == 0) return 0;
-  const int smem = ue_smem_fwd(H, D, Q);
-  TNR_REQUIRE(smem <= 200 * 1024, "tnr_user_encoder_fwd: H*D too large for shared memory");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (H <= 16) {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(user_encoder_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    user_encoder_fwd_kernel<16><<<B, UE_THREADS, smem, st>>>(vecs, mask, pad_doc, W1, b1, w2, b2, use_mask, user, a_out, e_out, H, D, Q);
-  } else {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(user_encoder_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    user_encoder_fwd_kernel<64><<<B, UE_THREADS, smem, st>>>(vecs, mask, pad_doc, W1, b1, w2, b2, use_mask, user, a_out, e_out, H, D, Q);
-  }
-  TNR_LAUNCH_CHECK();
-  return 0;
-}
-
-TNR_API int tnr_user_encoder_bwd(const float* vecs, const float* mask, const float* pad_doc, const float* W1,
-                                 const float* w2, int use_mask, const float* a_in, const float* e_in,
-                                 const float* d_user, float* d_vecs, float* dpad, float* dW1, float* db1, float* dw2,
-                                 float* db2, int B, int H, int D, int Q, void* stream) {
-  if (B == 0) return 0;
-  const int smem = ue_smem_bwd(H, D, Q);
-  TNR_REQUIRE(smem <= 200 * 1024, "tnr_user_encoder_bwd: H*D too large for shared memory");
-  TNR_CHECK_CUDA(cudaFuncSetAttribute(user_encoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  user_encoder_bwd_kernel<<<B, UE_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      vecs, mask, pad_doc, W1, w2, use_mask, a_in, e_in, d_user, d_vecs, dpad, dW1, db1, dw2, db2, H, D, Q);
-  TNR_LAUNCH_CHECK();
-  return 0;
-}
 
 TNR_API int tnr_kd_loss_fwdbwd(const float* s_news, const float* s_user, const int64_t* label, const float* T_ext,
                                const float* TP_ext, int M, int B, int H, int K, int D, float temperature, float coef,
@@ -501,20 +195,3 @@ TNR_API int tnr_kd_loss_fwdbwd(const float* s_news, const float* s_user, const i
   return 0;
 }
 
-TNR_API int tnr_sgemm_nt(const float* A, const float* Bm, const float* bias, float* C, int M, int N, int K, int batch,
-                         long long sA, long long sB, long long sbias, long long sC, void* stream) {
-  if (M == 0 || N == 0 || batch == 0) return 0;
-  dim3 grid((N + SG_T - 1) / SG_T, (M + SG_T - 1) / SG_T, batch);
-  sgemm_nt_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(A, Bm, bias, C, M, N, K, sA, sB, sbias, sC);
-  TNR_LAUNCH_CHECK();
-  return 0;
-}
-
-TNR_API int tnr_sgemm_tn_acc(const float* A, const float* Bm, float* C, float* cbias, int R, int N1, int N2, int batch,
-                             long long sA, long long sB, long long sC, long long sbias, void* stream) {
-  if (N1 == 0 || N2 == 0 || batch == 0) return 0;
-  dim3 grid((N2 + SG_T - 1) / SG_T, (N1 + SG_T - 1) / SG_T, batch);
-  sgemm_tn_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(A, Bm, C, cbias, R, N1, N2, sA, sB, sC, sbias);
-  TNR_LAUNCH_CHECK();
-  return 0;
-}

@@ -238,7 +238,8 @@ class TrainState:
         if w is None:
             R = B * (H + K)
             mk = lambda *s: torch.empty(*s, device=dev, dtype=F32)  # noqa: E731
-            w = dict(news=mk(R, D), user=mk(B, D), a=mk(B, H), e=mk(B, H, Q), ta=mk(B, H), score=mk(B, K),
+            w = dict(news=mk(R, D), user=mk(B, D), a=mk(B, H), e=mk(B, H, Q), ta=mk(max(M, 1), B, H), score=mk(B, K),
+                     ue_scratch=mk(B * H * (Q + D)),
                      losses=torch.zeros(4, device=dev, dtype=F32), d_news=mk(R, D), d_user=mk(B, D),
                      T=mk(max(M, 1), R + B, D), TP=mk(max(M, 1), R + B, D), G=mk(max(M, 1), R + B, D))
             self.hw[key] = w
@@ -266,17 +267,24 @@ class TrainState:
         mask = history_mask.contiguous().float()
         label = label.contiguous()
         at = self.ue.attn
-        ops.user_encoder_fwd(news[:B * H], mask, self.ue.pad_doc.view(-1), at.att_fc1.weight, at.att_fc1.bias,
-                             at.att_fc2.weight.view(-1), at.att_fc2.bias, use_mask, w["user"], w["a"], w["e"], B, H)
         T, TP, G = w["T"], w["TP"], w["G"]
+        encs = [dict(vecs=news[:B * H], pad_doc=self.ue.pad_doc.view(-1), W1=at.att_fc1.weight, b1=at.att_fc1.bias,
+                     w2=at.att_fc2.weight.view(-1), b2=at.att_fc2.bias, user=w["user"], a=w["a"], e=w["e"])]
         for i in range(M):
             T[i, :B * H].copy_(th_list[i].reshape(B * H, D))
             T[i, B * H:R].copy_(tc_list[i].reshape(B * K, D))
             t = self.teachers[i]
-            ops.user_encoder_fwd(T[i, :B * H], mask, t.pad_doc.view(-1), t.attn.att_fc1.weight, t.attn.att_fc1.bias,
-                                 t.attn.att_fc2.weight.view(-1), t.attn.att_fc2.bias, use_mask, T[i, R:], w["ta"], None, B, H)
-            lin = self.transform[i]
-            ops.sgemm_nt(T[i], lin.weight, lin.bias, TP[i], R + B, D, D, 1, 0, 0, 0, 0)
+            encs.append(dict(vecs=T[i, :B * H], pad_doc=t.pad_doc.view(-1), W1=t.attn.att_fc1.weight, b1=t.attn.att_fc1.bias,
+                             w2=t.attn.att_fc2.weight.view(-1), b2=t.attn.att_fc2.bias, user=T[i, R:], a=w["ta"][i], e=None))
+        ops.user_encoder_fwd_multi(encs, mask, use_mask, B, H)
+        if M:
+            ws, bs = [lin.weight for lin in self.transform], [lin.bias for lin in self.transform]
+            sw, sb = _const_stride(ws), _const_stride(bs)
+            if sw is not None and sb is not None:
+                ops.sgemm_nt(T, ws[0], bs[0], TP, R + B, D, D, M, (R + B) * D, sw, sb, (R + B) * D)
+            else:
+                for i in range(M):
+                    ops.sgemm_nt(T[i], ws[i], bs[i], TP[i], R + B, D, D, 1, 0, 0, 0, 0)
         w["losses"].zero_()
         ops.kd_loss(news, w["user"], label, T if M else None, TP if M else None, M, B, H, K, D, temperature, coef,
                     want_grad, w["score"], w["losses"], w["d_news"], w["d_user"], G if M else None)
@@ -284,20 +292,24 @@ class TrainState:
             self.stage.zero_()
             if self.ue_trainable:
                 sv = self._stage_view
-                ops.user_encoder_bwd(news[:B * H], mask, self.ue.pad_doc.view(-1), at.att_fc1.weight, at.att_fc2.weight.view(-1),
-                                     use_mask, w["a"], w["e"], w["d_user"], w["d_news"], sv(self.ue.pad_doc), sv(at.att_fc1.weight),
-                                     sv(at.att_fc1.bias), sv(at.att_fc2.weight), sv(at.att_fc2.bias), B, H)
+                dpad, dW1, db1, dw2, db2 = (sv(self.ue.pad_doc), sv(at.att_fc1.weight), sv(at.att_fc1.bias),
+                                            sv(at.att_fc2.weight), sv(at.att_fc2.bias))
             else:
                 scratch = torch.zeros(D + Q * D + 2 * Q + 1, device=dev, dtype=F32)
-                ops.user_encoder_bwd(news[:B * H], mask, self.ue.pad_doc.view(-1), at.att_fc1.weight, at.att_fc2.weight.view(-1),
-                                     use_mask, w["a"], w["e"], w["d_user"], w["d_news"], scratch[:D], scratch[D:D + Q * D],
-                                     scratch[D + Q * D:D + Q * D + Q], scratch[D + Q * D + Q:D + Q * D + 2 * Q],
-                                     scratch[D + Q * D + 2 * Q:], B, H)
-            if self.tm_trainable:
-                for i in range(M):
-                    lin = self.transform[i]
-                    ops.sgemm_tn_acc(G[i], T[i], self._stage_view(lin.weight), self._stage_view(lin.bias), R + B, D, D, 1,
-                                     0, 0, 0, 0)
+                dpad, dW1, db1 = scratch[:D], scratch[D:D + Q * D], scratch[D + Q * D:D + Q * D + Q]
+                dw2, db2 = scratch[D + Q * D + Q:D + Q * D + 2 * Q], scratch[D + Q * D + 2 * Q:]
+            ops.user_encoder_bwd(news[:B * H], mask, self.ue.pad_doc.view(-1), at.att_fc1.weight, at.att_fc2.weight.view(-1),
+                                 use_mask, w["a"], w["e"], w["d_user"], w["d_news"], dpad, dW1, db1, dw2, db2, w["ue_scratch"],
+                                 B, H)
+            if self.tm_trainable and M:
+                gw = [self._stage_view(lin.weight) for lin in self.transform]
+                gb = [self._stage_view(lin.bias) for lin in self.transform]
+                sw, sb = _const_stride(gw), _const_stride(gb)
+                if sw is not None and sb is not None:
+                    ops.sgemm_tn_acc(G, T, gw[0], gb[0], R + B, D, D, M, (R + B) * D, (R + B) * D, sw, sb)
+                else:
+                    for i in range(M):
+                        ops.sgemm_tn_acc(G[i], T[i], gw[i], gb[i], R + B, D, D, 1, 0, 0, 0, 0)
         self.last = w
         return w
 
@@ -312,6 +324,21 @@ class TrainState:
             flat.grad[self.head_begin:self.head_end].add_(self.stage[:self.head_end - self.head_begin])
         if self.comm_hook is not None:
             self.comm_hook(flat)
+
+
+def _const_stride(tensors):
+    """Element stride between consecutive fp32 tensors of a list if it is constant and 16-byte
+    aligned (the flat buffer keeps transform_matrix.{i} that way), else None."""
+    if len(tensors) == 1:
+        return 0
+    base = tensors[0].data_ptr()
+    d = tensors[1].data_ptr() - base
+    if d <= 0 or d % 16:
+        return None
+    for i, t in enumerate(tensors):
+        if t.data_ptr() - base != i * d or not t.is_contiguous():
+            return None
+    return d // 4
 
 
 def _trainable_signature(module):

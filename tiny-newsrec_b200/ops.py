@@ -54,12 +54,39 @@ def dropout_mask(drop, n, device):
 class _Stats:
     """Launch accounting for bench.py: ``launches`` counts kernels of libtinyrec enqueued;
     when ``gemm_events`` is a list every tnr_gemm_bf16 launch is bracketed by CUDA events on the
-    launching stream and (flops, start, stop) is appended (roofline measurement)."""
+    launching stream and (flops, start, stop) is appended (roofline measurement); when
+    ``op_events`` is a list every op wrapper of this module is bracketed the same way and
+    (name, tag, start, stop) appended (tools/step_profile.py)."""
     launches = 0
     gemm_events = None
+    op_events = None
 
 
 stats = _Stats()
+
+
+def _timed(fn):
+    """Per-op CUDA-event bracketing, active only while ``stats.op_events`` is a list."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrap(*a, **k):
+        if stats.op_events is None:
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **k)
+        e1.record()
+        tag = ""
+        if fn.__name__ == "gemm":
+            A, Bm = a[0], a[1]
+            M, K = (A.shape[1], A.shape[0]) if k.get("a_t") else (A.shape[0], A.shape[1])
+            N = Bm.shape[1] if k.get("b_t") else Bm.shape[0]
+            tag = f"{M}x{N}x{K}" + ("/wgrad" if k.get("a_t") else "/dgrad" if k.get("b_t") else "") + \
+                  {ACT_NONE: "", ACT_GELU: "+gelu", ACT_TANH: "+tanh", ACT_DGELU: "+dgelu"}[k.get("act", ACT_NONE)]
+        stats.op_events.append((fn.__name__, tag, e0, e1))
+        return r
+    return wrap
 
 
 def _ready(t, kernels=1):
@@ -68,6 +95,7 @@ def _ready(t, kernels=1):
     return _lib.load()
 
 
+@_timed
 def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, aux=None,
          split_k=1, accumulate=False, drop=None):
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).
@@ -118,6 +146,7 @@ def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_N
     return out
 
 
+@_timed
 def embed_ln(x, L, word, pos, type0, gamma, beta, eps, out, drop=None):
     """x: int64 [n, 2L] (ids | mask) -> out bf16 [n*L, E]."""
     lib = _ready(x)
@@ -132,6 +161,7 @@ def embed_ln(x, L, word, pos, type0, gamma, beta, eps, out, drop=None):
     return out
 
 
+@_timed
 def layernorm_fwd(x, gamma, beta, eps, out):
     lib = _ready(x)
     rows, E = x.shape
@@ -140,6 +170,7 @@ def layernorm_fwd(x, gamma, beta, eps, out):
     return out
 
 
+@_timed
 def layernorm_bwd(dy, x, gamma, eps, dx, dgamma, dbeta, dx_drop=None, drop=None):
     lib = _ready(x)
     rows, E = x.shape
@@ -150,6 +181,7 @@ def layernorm_bwd(dy, x, gamma, eps, dx, dgamma, dbeta, dx_drop=None, drop=None)
     return dx
 
 
+@_timed
 def colsum(x, out):
     lib = _ready(x)
     _lib.check(lib.tnr_colsum_bf16(_ptr(_chk(x, _bf16, "colsum.x")), x.shape[0], x.shape[1], x.stride(0),
@@ -157,6 +189,7 @@ def colsum(x, out):
     return out
 
 
+@_timed
 def attn_fwd(qkv, x, L, relpos, ctx, A, drop=None):
     """qkv bf16 [n*L, 3E]; x int64 [n, 2L] (mask = columns L..2L); relpos fp32 [A,L,L]."""
     lib = _ready(qkv)
@@ -169,6 +202,7 @@ def attn_fwd(qkv, x, L, relpos, ctx, A, drop=None):
     return ctx
 
 
+@_timed
 def attn_bwd(qkv, x, L, relpos, dctx, dqkv, A, drop=None):
     lib = _ready(qkv)
     n = x.shape[0]
@@ -181,6 +215,7 @@ def attn_bwd(qkv, x, L, relpos, dctx, dqkv, A, drop=None):
     return dqkv
 
 
+@_timed
 def attnpool_fwd(x, e, Q, w2, b2, mask, out, a_out, n, S):
     """x bf16 [n*S, C]; e bf16 [n*S, ldq]; out bf16 [n, C]; a_out fp32 [n, S]."""
     lib = _ready(x)
@@ -192,6 +227,7 @@ def attnpool_fwd(x, e, Q, w2, b2, mask, out, a_out, n, S):
     return out
 
 
+@_timed
 def attnpool_bwd(x, e, Q, w2, a_in, dout, dx, du, dw2, db2, n, S):
     lib = _ready(x)
     C = x.shape[1]
@@ -201,6 +237,7 @@ def attnpool_bwd(x, e, Q, w2, a_in, dout, dx, du, dw2, db2, n, S):
                                     _ptr(_chk(db2, _f32, "db2")), n, S, C, _stream()), "tnr_attnpool_bwd")
 
 
+@_timed
 def cast_f32_bf16(x, y):
     lib = _ready(x)
     _lib.check(lib.tnr_cast_f32_bf16(_ptr(_chk(x, _f32, "cast.x")), _ptr(_chk(y, _bf16, "cast.y")), x.numel(),
@@ -208,6 +245,7 @@ def cast_f32_bf16(x, y):
     return y
 
 
+@_timed
 def user_encoder_fwd(vecs, mask, pad_doc, W1, b1, w2, b2, use_mask, user, a_out, e_out, B, H):
     """vecs fp32 [B*H, D] (contiguous rows), mask fp32 [B, H] -> user [B, D], a [B, H], e [B, H, Q]."""
     lib = _ready(vecs)
@@ -221,17 +259,42 @@ def user_encoder_fwd(vecs, mask, pad_doc, W1, b1, w2, b2, use_mask, user, a_out,
     return user
 
 
-def user_encoder_bwd(vecs, mask, pad_doc, W1, w2, use_mask, a_in, e_in, d_user, d_vecs, dpad, dW1, db1, dw2, db2, B, H):
-    lib = _ready(vecs)
+@_timed
+def user_encoder_fwd_multi(encoders, mask, use_mask, B, H):
+    """One launch for several user encoders sharing ``mask``.  ``encoders``: list of dicts with
+    vecs [B*H, D], pad_doc [D], W1 [Q, D], b1 [Q], w2 [Q], b2 [1], user [B, D], a [B, H], e [B, H, Q] | None."""
+    lib = _ready(mask, 1)
+    n = len(encoders)
+    arr = (_lib.UserEncoderIO * n)()
+    D, Q = encoders[0]["W1"].shape[1], encoders[0]["W1"].shape[0]
+    for io, enc in zip(arr, encoders):
+        for k in ("vecs", "pad_doc", "W1", "b1", "w2", "b2", "user", "a"):
+            _chk(enc[k], _f32, "user_encoder." + k)
+        if tuple(enc["W1"].shape) != (Q, D) or not enc["W1"].is_contiguous():
+            raise _lib.TinyRecError("user_encoder_fwd_multi: all encoders must share [Q, D] contiguous fc1 weights")
+        io.vecs, io.pad_doc, io.W1, io.b1 = enc["vecs"].data_ptr(), enc["pad_doc"].data_ptr(), enc["W1"].data_ptr(), enc["b1"].data_ptr()
+        io.w2, io.b2, io.user, io.a_out = enc["w2"].data_ptr(), enc["b2"].data_ptr(), enc["user"].data_ptr(), enc["a"].data_ptr()
+        io.e_out = enc["e"].data_ptr() if enc.get("e") is not None else None
+    _lib.check(lib.tnr_user_encoder_fwd_multi(arr, n, _ptr(_chk(mask, _f32, "user_encoder.mask")), int(use_mask), B, H, D, Q,
+                                              _stream()), "tnr_user_encoder_fwd_multi")
+
+
+@_timed
+def user_encoder_bwd(vecs, mask, pad_doc, W1, w2, use_mask, a_in, e_in, d_user, d_vecs, dpad, dW1, db1, dw2, db2, scratch, B, H):
+    lib = _ready(vecs, 2)
     D, Q = W1.shape[1], W1.shape[0]
     for t, nm in ((d_user, "d_user"), (d_vecs, "d_vecs"), (dpad, "dpad"), (dW1, "dW1"), (db1, "db1"), (dw2, "dw2"),
-                  (db2, "db2"), (a_in, "a"), (e_in, "e")):
+                  (db2, "db2"), (a_in, "a"), (e_in, "e"), (scratch, "scratch")):
         _chk(t, _f32, "user_encoder_bwd." + nm)
+    if scratch.numel() < B * H * (Q + D):
+        raise _lib.TinyRecError("user_encoder_bwd: scratch too small")
     _lib.check(lib.tnr_user_encoder_bwd(_ptr(vecs), _ptr(mask), _ptr(pad_doc), _ptr(W1), _ptr(w2), int(use_mask),
                                         _ptr(a_in), _ptr(e_in), _ptr(d_user), _ptr(d_vecs), _ptr(dpad), _ptr(dW1),
-                                        _ptr(db1), _ptr(dw2), _ptr(db2), B, H, D, Q, _stream()), "tnr_user_encoder_bwd")
+                                        _ptr(db1), _ptr(dw2), _ptr(db2), _ptr(scratch), B, H, D, Q, _stream()),
+               "tnr_user_encoder_bwd")
 
 
+@_timed
 def kd_loss(s_news, s_user, label, T_ext, TP_ext, M, B, H, K, D, temperature, coef, want_grad, score_out, losses,
             d_news, d_user, G_ext):
     lib = _ready(s_news)
@@ -243,6 +306,7 @@ def kd_loss(s_news, s_user, label, T_ext, TP_ext, M, B, H, K, D, temperature, co
                                       _ptr(d_news), _ptr(d_user), _ptr(G_ext), _stream()), "tnr_kd_loss_fwdbwd")
 
 
+@_timed
 def sgemm_nt(A, Bm, bias, C, M, N, K, batch, sA, sB, sbias, sC):
     lib = _ready(A)
     _lib.check(lib.tnr_sgemm_nt(_ptr(_chk(A, _f32, "sgemm.A")), _ptr(_chk(Bm, _f32, "sgemm.B")), _ptr(bias),
@@ -250,6 +314,7 @@ def sgemm_nt(A, Bm, bias, C, M, N, K, batch, sA, sB, sbias, sC):
                "tnr_sgemm_nt")
 
 
+@_timed
 def sgemm_tn_acc(A, Bm, C, cbias, R, N1, N2, batch, sA, sB, sC, sbias):
     lib = _ready(A)
     _lib.check(lib.tnr_sgemm_tn_acc(_ptr(_chk(A, _f32, "sgemm.A")), _ptr(_chk(Bm, _f32, "sgemm.B")),
@@ -257,6 +322,7 @@ def sgemm_tn_acc(A, Bm, C, cbias, R, N1, N2, batch, sA, sB, sC, sbias):
                                     _stream()), "tnr_sgemm_tn_acc")
 
 
+@_timed
 def adam_amsgrad(p, g, m, v, vmax, shadow, lr, beta1, beta2, eps, step, grad_scale=1.0):
     lib = _ready(p)
     for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v"), (vmax, "vmax")):
@@ -265,6 +331,7 @@ def adam_amsgrad(p, g, m, v, vmax, shadow, lr, beta1, beta2, eps, step, grad_sca
                                     beta2, eps, step, grad_scale, _stream()), "tnr_adam_amsgrad")
 
 
+@_timed
 def gather_rows_i32_i64(table, idx, out):
     """out int64 [n, W] = table int32 [N, W][idx int32 [n]]"""
     lib = _ready(table)
@@ -274,6 +341,7 @@ def gather_rows_i32_i64(table, idx, out):
     return out
 
 
+@_timed
 def gather_rows_f32(table, idx, out, out_ld=None):
     lib = _ready(table)
     _chk(table, _f32, "gather.table"); _chk(idx, torch.int32, "gather.idx"); _chk(out, _f32, "gather.out")
@@ -283,6 +351,7 @@ def gather_rows_f32(table, idx, out, out_ld=None):
     return out
 
 
+@_timed
 def eval_metrics(table, user, ptr, cand, label, max_c, per_imp, sums=None, score_out=None):
     """table fp32 [N, D]; user fp32 [n_imp, D]; ptr int64 [n_imp+1]; cand int32 [nnz]; label int8 [nnz]."""
     lib = _ready(table)
