@@ -52,14 +52,28 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// erf-GELU exactly as torch F.gelu (transformers ACT2FN['gelu'])
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-level for GELU): 5 FMA + one
+// MUFU.RCP + one MUFU.EX2 instead of erff()'s two divergent branches -- the GEMM epilogues are
+// issue-bound at K = 768 (24 instructions per element budget).  ex2 returns exp(-x^2).
+__device__ __forceinline__ float erf_as(float x, float& ex2) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  ex2 = __expf(-ax * ax);
+  return copysignf(fmaf(-poly * t, ex2, 1.0f), x);
+}
+// erf-GELU as torch F.gelu (transformers ACT2FN['gelu']) and its derivative
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  float e2;
+  return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f, e2));
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e2;                                          // = exp(-x^2 / 2)
+  const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752440f, e2));
+  return fmaf(x * 0.39894228040143267794f, e2, cdf);
 }
 
 // 16-byte vector of 8 bf16

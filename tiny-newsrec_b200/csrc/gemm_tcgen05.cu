@@ -3,7 +3,12 @@
 //   warp 0      TMA producer (one elected lane)
 //   warp 1      MMA issuer   (one elected lane, tcgen05.mma cta_group::1, 128 x BN x 16)
 //   warp 2      TMEM allocator / deallocator
-//   warps 4-11  epilogue: tcgen05.ld -> bias / GELU / tanh / dGELU / residual -> global
+//   warps 4-11  epilogue: tcgen05.ld -> bias / GELU / tanh / dGELU / dropout / residual
+//               bf16 outputs: each warp stages 32 x 64 boxes in 128B-swizzled shared memory and
+//               writes them with TMA stores; the residual (or the dGELU pre-activation) box is
+//               prefetched by TMA at tile start.  (Per-thread-row 16 B global accesses made the
+//               epilogue L1-tag bound: 32 lines per request, ncu l1tex 68 % / tensor 18 %.)
+//               fp32 / split-K outputs: direct stores / fp32 atomics.
 // Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile i overlap the
 // main loop of tile i+1.  Split-K work items accumulate with fp32 atomics (wgrad).
 //
@@ -30,6 +35,9 @@ struct Params {
   __nv_bfloat16* aux; int ldaux;
   int atomic;
   tnr_dropout drop;
+  int epi_tma;        // bf16 C through smem + TMA store
+  int in_mode;        // 0 none, 1 residual box prefetched by TMA, 2 dGELU pre-activation box
+  int aux_out;        // GELU pre-activation written through TMA
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -66,6 +74,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -128,9 +146,12 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? 3 : 4;
   static constexpr int TMEM_COLS = 2 * BN;             // 2 accumulator stages (power of 2 >= 32)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BOX_BYTES = 32 * 128;       // 32 rows x 64 bf16, SWIZZLE_128B
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * 2 * EPI_BOX_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NUM_EPI_WARPS;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 8 * NUM_BARS + 16;
 };
 
 // ---------------------------------------------------------------- epilogue math
@@ -192,21 +213,66 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const DropCfg& d
   }
 }
 
+// bf16 output path: 8 consecutive columns of one row, staged in 128B-swizzled shared memory
+// (box row = lane, 16-byte chunk index c) for the TMA store; `in` holds the residual / dGELU box.
+template <int ACT>
+__device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg& dc, const uint32_t* acc, int row, int col,
+                                                 uint8_t* out_box, uint8_t* in_box, uint8_t* aux_box, uint32_t swz) {
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[i]);
+  if (p.bias != nullptr && col < p.N) {
+    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (ACT == TNR_ACT_GELU) {
+    if (p.aux_out) *reinterpret_cast<bf16x8*>(aux_box + swz) = pack8(v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+  } else if (ACT == TNR_ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = tanhf(v[i]);
+  } else if (ACT == TNR_ACT_DGELU) {
+    float z[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(in_box + swz), z);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(z[i]);
+  }
+  if (dc.thr16 != 0) {
+    const uint32_t keep = dropout_keep8(dc, ((uint64_t)row * (uint64_t)p.N + (uint64_t)col) >> 3);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * dc.scale : 0.f;
+  }
+  if (ACT != TNR_ACT_DGELU && p.in_mode == 1) {
+    float r[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(in_box + swz), r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += r[i];
+  }
+  *reinterpret_cast<bf16x8*>(out_box + swz) = pack8(v);
+}
+
 // ---------------------------------------------------------------- kernel
 template <int BN, bool A_MN, bool B_MN, int ACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_in,
+            const __grid_constant__ CUtensorMap tmap_aux, const Params p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // barriers after the pipeline stages
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  // [pipeline stages][epilogue staging boxes][barriers]
+  const uint32_t epi_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = epi_base + C::EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+  auto ld_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::STAGES + 4 + 2 * w + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES + 8 * C::NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -214,10 +280,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.epi_tma) tma_prefetch_desc(&tmap_c);
+    if (p.in_mode) tma_prefetch_desc(&tmap_in);
+    if (p.aux_out) tma_prefetch_desc(&tmap_aux);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), NUM_EPI_WARPS); }
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) { mbar_init(ld_bar(w, 0), 1); mbar_init(ld_bar(w, 1), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -306,24 +376,91 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int half = e >> 2;                      // column half of the tile
     int acc = 0; uint32_t acc_phase = 0;
     const DropCfg dc = load_drop(p.drop);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int n_blk = t % p.n_tiles;
-      const int m_blk = (t / p.n_tiles) % p.m_tiles;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const int row = m_blk * BM + quarter * 32 + lane;
+    if (p.epi_tma) {
+      constexpr int NB = BN / 128;                // 64-column boxes per warp per tile
+      uint8_t* box0 = smem_gen + C::STAGES * C::STAGE_BYTES + e * (2 * C::EPI_BOX_BYTES);
+      const uint32_t box0_u32 = epi_base + e * (2 * C::EPI_BOX_BYTES);
+      const uint32_t swz_row = (uint32_t)lane * 128u;
+      uint32_t ld_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_blk = t % p.n_tiles;
+        const int m_blk = (t / p.n_tiles) % p.m_tiles;
+        const int row0 = m_blk * BM + quarter * 32;
+        const int colbase = n_blk * BN + half * (BN / 2);
+        if (p.in_mode) {
+          // both boxes are about to be overwritten by the prefetch: their previous stores must have been read
+          if (lane == 0) {
+            bulk_wait_read<0>();
+#pragma unroll
+            for (int hb = 0; hb < NB; ++hb) {
+              mbar_expect_tx(ld_bar(e, hb), C::EPI_BOX_BYTES);
+              tma_load_2d(box0_u32 + hb * C::EPI_BOX_BYTES, &tmap_in, ld_bar(e, hb), colbase + hb * 64, row0);
+            }
+          }
+          __syncwarp();
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        const int coff = half * (BN / 2) + c * 32;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + coff), r);
-        tmem_ld_wait();
-        epilogue_chunk<ACT>(p, dc, r, row, n_blk * BN + coff);
+        for (int hb = 0; hb < NB; ++hb) {
+          uint32_t r[64];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2) + hb * 64);
+          tmem_ld32(taddr, r);
+          tmem_ld32(taddr + 32, r + 32);
+          tmem_ld_wait();
+          if (hb == NB - 1) {                      // accumulator drained: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          uint8_t* out_box = box0 + ((p.aux_out || NB == 1) ? 0 : hb * C::EPI_BOX_BYTES);
+          uint8_t* in_box = box0 + hb * C::EPI_BOX_BYTES;
+          uint8_t* aux_box = box0 + C::EPI_BOX_BYTES;
+          if (p.in_mode) {
+            mbar_wait(ld_bar(e, hb), ld_phase);
+          } else {
+            if (lane == 0) { if (p.aux_out || NB == 1) bulk_wait_read<0>(); else bulk_wait_read<NB - 1>(); }
+            __syncwarp();
+          }
+          const int row = row0 + lane;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t swz = swz_row + (uint32_t)((c ^ (lane & 7)) << 4);
+            epilogue_staged8<ACT>(p, dc, r + c * 8, row, colbase + hb * 64 + c * 8, out_box, in_box, aux_box, swz);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && colbase + hb * 64 < p.N) {
+            const uint32_t out_u32 = box0_u32 + (uint32_t)(out_box - box0);
+            tma_store_2d(&tmap_c, out_u32, colbase + hb * 64, row0);
+            if (p.aux_out) tma_store_2d(&tmap_aux, box0_u32 + C::EPI_BOX_BYTES, colbase + hb * 64, row0);
+            bulk_commit();
+          }
+        }
+        if (p.in_mode) ld_phase ^= 1u;
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      if (lane == 0) bulk_wait_all();
+    } else {
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_blk = t % p.n_tiles;
+        const int m_blk = (t / p.n_tiles) % p.m_tiles;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const int row = m_blk * BM + quarter * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          const int coff = half * (BN / 2) + c * 32;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + coff), r);
+          tmem_ld_wait();
+          epilogue_chunk<ACT>(p, dc, r, row, n_blk * BN + coff);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      }
     }
   }
 
@@ -369,39 +506,38 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t 
 }
 
 template <int BN, bool A_MN, bool B_MN, int ACT>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t st) {
+static int launch(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
   auto kern = gemm_kernel<BN, A_MN, B_MN, ACT>;
   static bool attr_done = false;
   if (!attr_done) {
     TNR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     attr_done = true;
   }
-  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   TNR_LAUNCH_CHECK();
   return 0;
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int dispatch_act(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t st) {
+static int dispatch_act(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
   switch (p.act) {
-    case TNR_ACT_NONE: return launch<BN, A_MN, B_MN, TNR_ACT_NONE>(ta, tb, p, grid, st);
-    case TNR_ACT_GELU: return launch<BN, A_MN, B_MN, TNR_ACT_GELU>(ta, tb, p, grid, st);
-    case TNR_ACT_TANH: return launch<BN, A_MN, B_MN, TNR_ACT_TANH>(ta, tb, p, grid, st);
-    case TNR_ACT_DGELU: return launch<BN, A_MN, B_MN, TNR_ACT_DGELU>(ta, tb, p, grid, st);
+    case TNR_ACT_NONE: return launch<BN, A_MN, B_MN, TNR_ACT_NONE>(maps, p, grid, st);
+    case TNR_ACT_GELU: return launch<BN, A_MN, B_MN, TNR_ACT_GELU>(maps, p, grid, st);
+    case TNR_ACT_TANH: return launch<BN, A_MN, B_MN, TNR_ACT_TANH>(maps, p, grid, st);
+    case TNR_ACT_DGELU: return launch<BN, A_MN, B_MN, TNR_ACT_DGELU>(maps, p, grid, st);
   }
   set_error("tnr_gemm_bf16: unknown act %d", p.act);
   return 1;
 }
 
 template <int BN>
-static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid,
-                          cudaStream_t st) {
-  if (!a_mn && !b_mn) return dispatch_act<BN, false, false>(ta, tb, p, grid, st);
-  if (!a_mn && b_mn) return dispatch_act<BN, false, true>(ta, tb, p, grid, st);
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
+  if (!a_mn && !b_mn) return dispatch_act<BN, false, false>(maps, p, grid, st);
+  if (!a_mn && b_mn) return dispatch_act<BN, false, true>(maps, p, grid, st);
   if (a_mn && b_mn) {
     // wgrad only ever uses the plain epilogue
     TNR_REQUIRE(p.act == TNR_ACT_NONE, "tnr_gemm_bf16: A MN-major supports act=NONE only");
-    return launch<BN, true, true, TNR_ACT_NONE>(ta, tb, p, grid, st);
+    return launch<BN, true, true, TNR_ACT_NONE>(maps, p, grid, st);
   }
   set_error("tnr_gemm_bf16: A MN-major with B K-major is not instantiated");
   return 1;
@@ -451,17 +587,38 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
   TNR_REQUIRE(p.drop.seed == nullptr || !(p.drop.p > 0.f) || (!atomic && a->act == TNR_ACT_NONE),
               "tnr_gemm_bf16: dropout is supported with the plain (bias + residual) epilogue only");
 
-  CUtensorMap ta, tb;
+  CUtensorMap maps[5];
+  CUtensorMap &ta = maps[0], &tb = maps[1];
   if (!a_mn) { if (make_map(&ta, a->A, a->K, a->M, a->lda, BK, BM)) return 1; }
   else       { if (make_map(&ta, a->A, a->M, a->K, a->lda, 64, BK)) return 1; }
   if (!b_mn) { if (make_map(&tb, a->B, a->K, a->N, a->ldb, BK, BN)) return 1; }
   else       { if (make_map(&tb, a->B, a->N, a->K, a->ldb, 64, BK)) return 1; }
+  // bf16 outputs go through shared memory + TMA (32-row x 64-column boxes, 128B swizzle)
+  p.epi_tma = (!p.c_f32 && !atomic) ? 1 : 0;
+  p.in_mode = 0; p.aux_out = 0;
+  maps[2] = ta; maps[3] = ta; maps[4] = ta;        // placeholders when unused
+  if (p.epi_tma) {
+    TNR_REQUIRE(!(a->act == TNR_ACT_DGELU && a->residual != nullptr),
+                "tnr_gemm_bf16: DGELU with a residual is not supported for bf16 outputs");
+    if (make_map(&maps[2], a->C, a->N, a->M, a->ldc, 64, 32)) return 1;
+    if (a->act == TNR_ACT_DGELU) {
+      p.in_mode = 2;
+      if (make_map(&maps[3], a->aux, a->N, a->M, a->ldaux, 64, 32)) return 1;
+    } else if (a->residual != nullptr) {
+      p.in_mode = 1;
+      if (make_map(&maps[3], a->residual, a->N, a->M, a->ldr, 64, 32)) return 1;
+    }
+    if (a->act == TNR_ACT_GELU && a->aux != nullptr) {
+      p.aux_out = 1;
+      if (make_map(&maps[4], a->aux, a->N, a->M, a->ldaux, 64, 32)) return 1;
+    }
+  }
 
   const int tiles = p.m_tiles * p.n_tiles * p.splits;
   const int sms = num_sms();
   TNR_REQUIRE(sms > 0, "tnr_gemm_bf16: no CUDA device");
   const int grid = tiles < sms ? tiles : sms;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (BN == 256) return dispatch_major<256>(a_mn, b_mn, ta, tb, p, grid, st);
-  return dispatch_major<128>(a_mn, b_mn, ta, tb, p, grid, st);
+  if (BN == 256) return dispatch_major<256>(a_mn, b_mn, maps, p, grid, st);
+  return dispatch_major<128>(a_mn, b_mn, maps, p, grid, st);
 }
