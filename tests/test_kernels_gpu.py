@@ -70,6 +70,37 @@ def test_gemm_gelu_with_preact_and_tanh():
     assert _rel_err(out2, torch.tanh(a.float() @ b2.float().t() + bias[:N2]))[0] < 5e-3
 
 
+def test_gemm_gelu_epilogue_extreme_preactivations():
+    """The epilogue GELU is a fitted sigmoid form (common.cuh): check it against erf-GELU over the
+    whole range including |z| far outside the fitted interval."""
+    ops = _ops()
+    M, N, K = 256, 256, 64
+    z = torch.linspace(-40, 40, M * N, device="cuda").reshape(M, N)
+    a = torch.zeros(M, K, device="cuda", dtype=BF)
+    b = torch.zeros(N, K, device="cuda", dtype=BF)
+    a[:, 0] = 1.0
+    out = torch.empty(M, N, device="cuda", dtype=BF)
+    # pre-activation = 0 + bias is per-column only, so sweep through K=64 one-hot rows instead
+    zz = torch.linspace(-40, 40, M, device="cuda")
+    a[:, 0] = zz.to(BF)
+    b[:, 0] = 1.0
+    ops.gemm(a, b, out, act=ops.ACT_GELU)
+    ref = torch.nn.functional.gelu(a[:, 0].float())[:, None].expand(M, N)
+    assert float((out.float() - ref).abs().max()) <= 0.13              # bf16 rounding of values up to 40
+    assert _rel_err(out, ref)[0] < 4e-3
+    assert float(out[zz < -9].float().abs().max()) < 1e-6
+    dz = torch.empty(M, N, device="cuda", dtype=BF)
+    ones = torch.zeros(M, K, device="cuda", dtype=BF)
+    ones[:, 0] = 1.0
+    w = torch.zeros(K, N, device="cuda", dtype=BF)
+    w[0] = 1.0
+    aux = a[:, :1].expand(M, N).contiguous()
+    ops.gemm(ones, w, dz, b_t=True, act=ops.ACT_DGELU, aux=aux)
+    zf = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).sum().backward()
+    assert float((dz.float() - zf.grad).abs().max()) < 6e-3
+
+
 def test_gemm_dgelu_epilogue():
     ops = _ops()
     M, N, K = 384, 3072, 768

@@ -141,15 +141,15 @@ __host__ __device__ constexpr uint32_t make_idesc() {
          | ((uint32_t)(BM >> 4) << 24); // M
 }
 
-template <int BN>
+template <int BN, bool EPI_TMA>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 3 : 4;
+  static constexpr int STAGES = (BN == 256) ? (EPI_TMA ? 3 : 4) : (EPI_TMA ? 4 : 6);
   static constexpr int TMEM_COLS = 2 * BN;             // 2 accumulator stages (power of 2 >= 32)
   static constexpr int EPI_BOX_BYTES = 32 * 128;       // 32 rows x 64 bf16, SWIZZLE_128B
-  static constexpr int EPI_BYTES = NUM_EPI_WARPS * 2 * EPI_BOX_BYTES;
+  static constexpr int EPI_BYTES = EPI_TMA ? NUM_EPI_WARPS * 2 * EPI_BOX_BYTES : 0;
   static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NUM_EPI_WARPS;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 8 * NUM_BARS + 16;
 };
@@ -255,12 +255,12 @@ __device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg&
 }
 
 // ---------------------------------------------------------------- kernel
-template <int BN, bool A_MN, bool B_MN, int ACT>
+template <int BN, bool A_MN, bool B_MN, int ACT, bool EPI_TMA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_in,
             const __grid_constant__ CUtensorMap tmap_aux, const Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, EPI_TMA>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -280,7 +280,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    if (p.epi_tma) tma_prefetch_desc(&tmap_c);
+    if (EPI_TMA) tma_prefetch_desc(&tmap_c);
     if (p.in_mode) tma_prefetch_desc(&tmap_in);
     if (p.aux_out) tma_prefetch_desc(&tmap_aux);
   }
@@ -376,7 +376,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int half = e >> 2;                      // column half of the tile
     int acc = 0; uint32_t acc_phase = 0;
     const DropCfg dc = load_drop(p.drop);
-    if (p.epi_tma) {
+    if (EPI_TMA) {
       constexpr int NB = BN / 128;                // 64-column boxes per warp per tile
       uint8_t* box0 = smem_gen + C::STAGES * C::STAGE_BYTES + e * (2 * C::EPI_BOX_BYTES);
       const uint32_t box0_u32 = epi_base + e * (2 * C::EPI_BOX_BYTES);
@@ -505,15 +505,16 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t 
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, int ACT>
+template <int BN, bool A_MN, bool B_MN, int ACT, bool EPI_TMA>
 static int launch(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
-  auto kern = gemm_kernel<BN, A_MN, B_MN, ACT>;
+  using C = Cfg<BN, EPI_TMA>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, ACT, EPI_TMA>;
   static bool attr_done = false;
   if (!attr_done) {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    TNR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
-  kern<<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   TNR_LAUNCH_CHECK();
   return 0;
 }
@@ -521,10 +522,12 @@ static int launch(const CUtensorMap* maps, const Params& p, int grid, cudaStream
 template <int BN, bool A_MN, bool B_MN>
 static int dispatch_act(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
   switch (p.act) {
-    case TNR_ACT_NONE: return launch<BN, A_MN, B_MN, TNR_ACT_NONE>(maps, p, grid, st);
-    case TNR_ACT_GELU: return launch<BN, A_MN, B_MN, TNR_ACT_GELU>(maps, p, grid, st);
-    case TNR_ACT_TANH: return launch<BN, A_MN, B_MN, TNR_ACT_TANH>(maps, p, grid, st);
-    case TNR_ACT_DGELU: return launch<BN, A_MN, B_MN, TNR_ACT_DGELU>(maps, p, grid, st);
+    case TNR_ACT_NONE:
+      if (p.epi_tma) return launch<BN, A_MN, B_MN, TNR_ACT_NONE, true>(maps, p, grid, st);
+      return launch<BN, A_MN, B_MN, TNR_ACT_NONE, false>(maps, p, grid, st);
+    case TNR_ACT_GELU: return launch<BN, A_MN, B_MN, TNR_ACT_GELU, true>(maps, p, grid, st);
+    case TNR_ACT_TANH: return launch<BN, A_MN, B_MN, TNR_ACT_TANH, true>(maps, p, grid, st);
+    case TNR_ACT_DGELU: return launch<BN, A_MN, B_MN, TNR_ACT_DGELU, true>(maps, p, grid, st);
   }
   set_error("tnr_gemm_bf16: unknown act %d", p.act);
   return 1;
@@ -537,7 +540,8 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* maps, const P
   if (a_mn && b_mn) {
     // wgrad only ever uses the plain epilogue
     TNR_REQUIRE(p.act == TNR_ACT_NONE, "tnr_gemm_bf16: A MN-major supports act=NONE only");
-    return launch<BN, true, true, TNR_ACT_NONE>(maps, p, grid, st);
+    TNR_REQUIRE(!p.epi_tma, "tnr_gemm_bf16: A MN-major (wgrad) writes fp32 only");
+    return launch<BN, true, true, TNR_ACT_NONE, false>(maps, p, grid, st);
   }
   set_error("tnr_gemm_bf16: A MN-major with B K-major is not instantiated");
   return 1;
@@ -595,6 +599,7 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
   else       { if (make_map(&tb, a->B, a->N, a->K, a->ldb, 64, BK)) return 1; }
   // bf16 outputs go through shared memory + TMA (32-row x 64-column boxes, 128B swizzle)
   p.epi_tma = (!p.c_f32 && !atomic) ? 1 : 0;
+  TNR_REQUIRE(p.epi_tma || a->act == TNR_ACT_NONE, "tnr_gemm_bf16: activation epilogues need a bf16 output");
   p.in_mode = 0; p.aux_out = 0;
   maps[2] = ta; maps[3] = ta; maps[4] = ta;        // placeholders when unused
   if (p.epi_tma) {
