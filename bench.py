@@ -246,7 +246,7 @@ def config_dict(workload, n, batch=B):
             "per_gpu_batch": batch, "global_batch": batch * n, "history": H, "npratio": K - 1, "title_tokens": L,
             "teachers": M, "news_dim": D, "vocab": 30522, "parallelism": f"dp{n}",
             "l2": "per-step activation working set (~5 GB) >> 126 MB L2; 8 rotating input batches",
-            "dropout": "off (eval-mode parity; see DESIGN.md)"}
+            "dropout": "0.1 active (training mode, as the reference train(); counter-based masks regenerated in backward)"}
 
 
 # ----------------------------------------------------------------------------- GPU arm

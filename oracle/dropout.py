@@ -57,3 +57,37 @@ def attention_keep(seed, site, n_items, L, p):
     flat = keep_mask(seed, site, n_items * 32 * 32, p).reshape(n_items, 32, 4, 8)
     j = np.arange(L)
     return flat[:, :L][:, :, (j >> 1) & 3, (j >> 3) * 2 + (j & 1)]
+
+
+# dropout tensor ids of the CUDA path (tiny-newsrec_b200/engine.py: SITE_EMB, drop_site)
+SITE_EMB = 0
+KIND_ATTN, KIND_ATT_OUT, KIND_FFN_OUT = 0, 1, 2
+
+
+def drop_site(layer, kind):
+    return 8 * (layer + 1) + kind
+
+
+class Plan:
+    """Multipliers keep / (1 - p) for every dropout tensor of one encoder forward over the
+    concatenated news batch (rows = news; the CUDA path encodes [history rows | candidate rows] in one
+    pass, so callers pass the row offset of the slice they encode)."""
+
+    def __init__(self, seed, p_hidden=0.1, p_attn=0.1):
+        self.seed, self.p_hidden, self.p_attn = int(seed), float(p_hidden), float(p_attn)
+
+    def _rows(self, site, row0, n, L, E, p):
+        import torch
+        full = keep_mask(self.seed, site, (row0 + n) * L * E, p)[row0 * L * E:]
+        return torch.from_numpy(full.reshape(n, L, E).astype(np.float32)) / (1.0 - p)
+
+    def emb(self, row0, n, L, E):
+        return self._rows(SITE_EMB, row0, n, L, E, self.p_hidden)
+
+    def dense(self, layer, kind, row0, n, L, E):
+        return self._rows(drop_site(layer, kind), row0, n, L, E, self.p_hidden)
+
+    def attn(self, layer, row0, n, A, L):
+        import torch
+        k = attention_keep(self.seed, drop_site(layer, KIND_ATTN), (row0 + n) * A, L, self.p_attn)[row0 * A:]
+        return torch.from_numpy(k.reshape(n, A, L, L).astype(np.float32)) / (1.0 - self.p_attn)

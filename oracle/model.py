@@ -1,8 +1,10 @@
 """Oracle (test infrastructure): fp32 restatement of the reference model path.
 
 Functional style over a flat ``state_dict`` (the reference's own key names), so
-the same tensors can be handed to the CUDA path and to the oracle.  Dropout is
-not modelled: parity is defined in ``eval()`` mode ("dropout").
+the same tensors can be handed to the CUDA path and to the oracle.  Dropout
+(active in the reference's train(), which never leaves training mode) is modelled
+by INJECTED masks: ``drop=(plan, row0)`` with an ``oracle.dropout.Plan`` reproducing
+the CUDA path's counter-based generator; ``drop=None`` is ``eval()`` mode.
 
 Citations are relative to /root/reference.
 """
@@ -47,17 +49,20 @@ def rel_pos_bias_table(rel_pos_weight, L, num_buckets=32, max_distance=128):
 # --------------------------------------------------------------------------
 # encoder
 # --------------------------------------------------------------------------
-def embeddings(sd, pfx, ids):
-    """LN(word[id] + pos[arange L] + type[0])   (modeling.py:153-178)."""
+def embeddings(sd, pfx, ids, drop=None):
+    """dropout(LN(word[id] + pos[arange L] + type[0]))   (modeling.py:153-178)."""
     L = ids.shape[1]
     x = sd[pfx + "word_embeddings.weight"][ids]
     x = x + sd[pfx + "position_embeddings.weight"][:L].unsqueeze(0)
     x = x + sd[pfx + "token_type_embeddings.weight"][0]
-    return F.layer_norm(x, (x.shape[-1],), sd[pfx + "LayerNorm.weight"],
-                        sd[pfx + "LayerNorm.bias"], LN_EPS)
+    x = F.layer_norm(x, (x.shape[-1],), sd[pfx + "LayerNorm.weight"],
+                     sd[pfx + "LayerNorm.bias"], LN_EPS)
+    if drop is not None:
+        x = x * drop[0].emb(drop[1], x.shape[0], L, x.shape[-1])
+    return x
 
 
-def self_attention(sd, pfx, x, ext_mask, relpos, heads):
+def self_attention(sd, pfx, x, ext_mask, relpos, heads, drop=None, layer=0):
     """modeling.py:205-231, 233-272: QKV linears, scores/sqrt(dh) + mask + relpos,
     softmax, PV, merge heads."""
     n, L, E = x.shape
@@ -71,35 +76,42 @@ def self_attention(sd, pfx, x, ext_mask, relpos, heads):
     s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(dh)
     s = s + ext_mask + relpos
     p = torch.softmax(s, dim=-1)
+    if drop is not None:                                     # modeling.py:223
+        p = p * drop[0].attn(layer, drop[1], n, heads, L)
     ctx = torch.matmul(p, v).permute(0, 2, 1, 3).reshape(n, L, E)
     return ctx
 
 
-def encoder_layer(sd, pfx, x, ext_mask, relpos, heads):
+def encoder_layer(sd, pfx, x, ext_mask, relpos, heads, drop=None, layer=0):
     """modeling.py:275-308 plus transformers BertSelfOutput / BertIntermediate /
     BertOutput (third-party, imported at modeling.py:12-14): post-LN residual
     blocks with erf-GELU."""
     E = x.shape[-1]
-    ctx = self_attention(sd, pfx + "attention.self.", x, ext_mask, relpos, heads)
+    n, L = x.shape[0], x.shape[1]
+    ctx = self_attention(sd, pfx + "attention.self.", x, ext_mask, relpos, heads, drop, layer)
     a = F.linear(ctx, sd[pfx + "attention.output.dense.weight"], sd[pfx + "attention.output.dense.bias"])
+    if drop is not None:                                     # BertSelfOutput.dropout
+        a = a * drop[0].dense(layer, 1, drop[1], n, L, E)
     a = F.layer_norm(a + x, (E,), sd[pfx + "attention.output.LayerNorm.weight"],
                      sd[pfx + "attention.output.LayerNorm.bias"], LN_EPS)
     h = F.gelu(F.linear(a, sd[pfx + "intermediate.dense.weight"], sd[pfx + "intermediate.dense.bias"]))
     o = F.linear(h, sd[pfx + "output.dense.weight"], sd[pfx + "output.dense.bias"])
+    if drop is not None:                                     # BertOutput.dropout
+        o = o * drop[0].dense(layer, 2, drop[1], n, L, E)
     return F.layer_norm(o + a, (E,), sd[pfx + "output.LayerNorm.weight"],
                         sd[pfx + "output.LayerNorm.bias"], LN_EPS)
 
 
-def bert_last_hidden(sd, pfx, ids, mask, num_layers, heads=12, all_hidden=False):
+def bert_last_hidden(sd, pfx, ids, mask, num_layers, heads=12, all_hidden=False, drop=None):
     """TuringNLRv3Model.forward (modeling.py:421-476) up to the last hidden
     state; the pooler/classifier outputs are discarded by the caller
     (model_bert.py:128-129) and are not computed here."""
     ext_mask = (1.0 - mask.to(torch.float32))[:, None, None, :] * -10000.0   # modeling.py:446-454
-    x = embeddings(sd, pfx + "bert.embeddings.", ids)
+    x = embeddings(sd, pfx + "bert.embeddings.", ids, drop)
     relpos = rel_pos_bias_table(sd[pfx + "bert.rel_pos_bias.weight"], ids.shape[1]).unsqueeze(0)
     hs = [x]
     for l in range(num_layers):                                               # modeling.py:318-342
-        x = encoder_layer(sd, f"{pfx}bert.encoder.layer.{l}.", x, ext_mask, relpos, heads)
+        x = encoder_layer(sd, f"{pfx}bert.encoder.layer.{l}.", x, ext_mask, relpos, heads, drop, l)
         hs.append(x)
     return hs if all_hidden else x
 
@@ -114,12 +126,12 @@ def attention_pooling(sd, pfx, x, mask=None):
     return torch.bmm(x.permute(0, 2, 1), alpha).squeeze(-1)
 
 
-def news_encoder(sd, pfx, x, num_layers, heads=12):
+def news_encoder(sd, pfx, x, num_layers, heads=12, drop=None):
     """model_bert.py:119-137 (pooling='att'): split ids|mask, encoder, UNMASKED
     additive pooling over words, dense E->D."""
     L = x.shape[1] // 2
     ids, mask = x[:, :L], x[:, L:]
-    h = bert_last_hidden(sd, pfx + "bert_model.", ids, mask, num_layers, heads)
+    h = bert_last_hidden(sd, pfx + "bert_model.", ids, mask, num_layers, heads, drop=drop)
     pooled = attention_pooling(sd, pfx + "attn.", h)
     return F.linear(pooled, sd[pfx + "dense.weight"], sd[pfx + "dense.bias"])
 
@@ -135,13 +147,16 @@ def user_encoder(sd, pfx, vecs, log_mask, user_log_mask):
 
 
 def model_bert_forward(sd, pfx, history, history_mask, candidate, num_layers, user_log_mask,
-                       heads=12):
+                       heads=12, drop_plan=None):
     """ModelBert.forward, model_bert.py:187-205 ->
     (score[B,K], hist_vecs[B,H,D], cand_vecs[B,K,D], user_vec[B,D])."""
     B, H, W = history.shape
-    cand = news_encoder(sd, pfx + "news_encoder.", candidate.reshape(-1, W), num_layers, heads)
+    # the CUDA path encodes [history rows | candidate rows] as one batch: dropout rows are offset accordingly
+    dc = (drop_plan, B * H) if drop_plan is not None else None
+    dh = (drop_plan, 0) if drop_plan is not None else None
+    cand = news_encoder(sd, pfx + "news_encoder.", candidate.reshape(-1, W), num_layers, heads, dc)
     cand = cand.reshape(B, -1, cand.shape[-1])
-    hist = news_encoder(sd, pfx + "news_encoder.", history.reshape(-1, W), num_layers, heads)
+    hist = news_encoder(sd, pfx + "news_encoder.", history.reshape(-1, W), num_layers, heads, dh)
     hist = hist.reshape(B, H, -1)
     user = user_encoder(sd, pfx + "user_encoder.", hist, history_mask, user_log_mask)
     score = torch.bmm(cand, user.unsqueeze(-1)).squeeze(-1)
@@ -164,11 +179,11 @@ def kd_ce_loss(logits_s, logits_t, temperature=1.0):
 
 def kd_model_forward(sd, history, history_mask, candidate, label, teacher_history_embs,
                      teacher_candidate_embs, num_layers, user_log_mask, temperature=1.0,
-                     coef=1.0):
+                     coef=1.0, drop_plan=None):
     """Model.forward, model_bert.py:262-306 ->
     (total, distill, emb, target, student_score)."""
     s_score, s_hist, s_cand, s_user = model_bert_forward(
-        sd, "student.", history, history_mask, candidate, num_layers, user_log_mask)
+        sd, "student.", history, history_mask, candidate, num_layers, user_log_mask, drop_plan=drop_plan)
     s_news = torch.cat([s_hist, s_cand], dim=1)
     target = F.cross_entropy(s_score, label)                                   # :271
     t_scores, t_losses, ne, ue = [], [], [], []

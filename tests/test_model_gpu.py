@@ -112,7 +112,7 @@ def _kd_model(g, ulm):
     m = mb.Model(synth.demo_args(num_student_layers=layers, user_log_length=H, user_log_mask=ulm, num_teachers=M,
                                  temperature=float(g["temperature"]), coef=float(g["coef"])))
     m.load_state_dict(synth.kd_model_state(layers, M, int(g["seed"]), noisy=True), strict=True)
-    m.cuda()
+    m.cuda().eval()                      # golden vectors are eval()-mode outputs of the reference
     _apply_freeze(m, [int(i) for i in g["trainable"]])
     inputs = (torch.from_numpy(g["history"]).cuda(), torch.from_numpy(g["history_mask"]).cuda(),
               torch.from_numpy(g["candidate"]).cuda(), torch.from_numpy(g["label"]).cuda(),
@@ -181,7 +181,7 @@ def test_kd_step_vs_oracle_at_demo_shape():
     args = synth.demo_args(num_student_layers=layers, num_teachers=M)
     m = mb.Model(args)
     m.load_state_dict(sd, strict=True)
-    m.cuda()
+    m.cuda().eval()
     _apply_freeze(m, [1])
     res = m(history.cuda(), torch.from_numpy(hmask).cuda(), candidate.cuda(), torch.from_numpy(label).cuda(),
             [t.cuda() for t in th], [t.cuda() for t in tc])
@@ -198,6 +198,60 @@ def test_kd_step_vs_oracle_at_demo_shape():
     for k in keys:
         r = _grad_err(k, named[k].grad, osd[k].grad, named)
         assert r < 5e-2, (k, r)
+
+
+def test_kd_training_mode_step_with_dropout_vs_oracle_with_injected_masks():
+    """Training mode (the reference's train() never calls eval(): dropout 0.1 is active in the
+    embeddings, attention probabilities and both dense outputs of every layer).  The CUDA path draws
+    its masks from a counter-based generator; the oracle gets the SAME masks injected
+    (oracle/dropout.py), so losses, scores and all gradients must agree like in eval mode."""
+    import tinyrec.model_bert as mb
+    import tinyrec.synth as synth
+    from oracle import model as om
+    from oracle.dropout import Plan
+    B, H, K, L, M, layers, D = 3, 7, 3, 12, 2, 2, 256
+    news = synth.news_table(300, L=L, seed=3)
+    hist_idx, hmask, cand_idx, label = synth.train_impressions(B, 300, H, K, seed=4)
+    tables = synth.teacher_tables(300, M, D, seed=5)
+    history = torch.from_numpy(news[hist_idx].astype(np.int64))
+    candidate = torch.from_numpy(news[cand_idx].astype(np.int64))
+    th = [torch.from_numpy(t[hist_idx]) for t in tables]
+    tc = [torch.from_numpy(t[cand_idx]) for t in tables]
+    sd = synth.kd_model_state(layers, M, 11, noisy=True)
+    args = synth.demo_args(num_student_layers=layers, num_teachers=M, user_log_length=H)
+    m = mb.Model(args)
+    m.load_state_dict(sd, strict=True)
+    m.cuda()
+    assert m.training                                  # default nn.Module mode, as in the reference's train()
+    _apply_freeze(m, [0, 1])
+    drop = m.student.news_encoder.drop_state(torch.device("cuda", 0))
+    seed0 = int(drop.seed.item())
+    gpu_in = (history.cuda(), torch.from_numpy(hmask).cuda(), candidate.cuda(), torch.from_numpy(label).cuda(),
+              [t.cuda() for t in th], [t.cuda() for t in tc])
+    res = m(*gpu_in)
+    res[0].backward()
+    assert int(drop.seed.item()) == seed0 + 1          # one seed per step
+    keys = om.trainable_keys(sd, [0, 1])
+    osd = {k: v.clone().requires_grad_(k in keys) for k, v in sd.items()}
+    plan = Plan(seed0 + 1, drop.p_hidden, drop.p_attn)
+    ref = om.kd_model_forward(osd, history, torch.from_numpy(hmask), candidate, torch.from_numpy(label), th, tc, layers,
+                              False, args.temperature, args.coef, drop_plan=plan)
+    ref[0].backward()
+    for v, r, nm in zip(res[:4], ref[:4], ("total", "distill", "emb", "target")):
+        assert abs(float(v) - float(r)) < 1e-2 * abs(float(r)) + 1e-4, (nm, float(v), float(r))
+    assert _rel(res[4], ref[4].detach()) < 2e-2
+    named = dict(m.named_parameters())
+    for k in keys:
+        r = _grad_err(k, named[k].grad, osd[k].grad, named)
+        assert r < 5e-2, (k, r)
+    # eval() switches dropout off and a new step draws new masks
+    with torch.no_grad():
+        a1 = float(m(*gpu_in)[0])
+        a2 = float(m(*gpu_in)[0])
+        m.eval()
+        e1 = float(m(*gpu_in)[0])
+        e2 = float(m(*gpu_in)[0])
+    assert a1 != a2 and e1 == e2
 
 
 def test_train_state_survives_optimizer_step_and_matches_oracle_adam(golden):

@@ -16,6 +16,32 @@ BF = torch.bfloat16
 F32 = torch.float32
 LN_EPS = 1e-12            # tnlrv3/configuration_tnlrv3.py:61
 
+# dropout tensor ids ("sites", include/tinyrec.h tnr_dropout.site): one Philox stream per tensor
+SITE_EMB = 0              # embeddings output, tnlrv3/modeling.py:177
+KIND_ATTN, KIND_ATT_OUT, KIND_FFN_OUT = 0, 1, 2    # attention probs :223; BertSelfOutput / BertOutput dense
+
+
+def drop_site(layer, kind):
+    return 8 * (layer + 1) + kind
+
+
+class DropState:
+    """Training-mode dropout of the encoder: probabilities from the model config and a device-resident
+    64-bit seed that advances once per forward (the backward of the same step regenerates the masks
+    from it; a captured CUDA graph replays with a fresh seed)."""
+
+    def __init__(self, device, p_hidden=0.1, p_attn=0.1, seed=None):
+        self.p_hidden, self.p_attn = float(p_hidden), float(p_attn)
+        if seed is None:
+            seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        self.seed = torch.tensor([seed], device=device, dtype=torch.int64)
+
+    def advance(self):
+        self.seed.add_(1)
+
+    def make(self, site, p):
+        return ops.make_drop(self.seed, site, p)
+
 
 def _align8(n):
     return (n + 7) // 8 * 8
@@ -231,7 +257,7 @@ class Encoder:
             ws["saved"].append(dict(xin=None, qkv=mk(T, 3 * E), ctx=mk(T, E), pre1=mk(T, E), x1=mk(T, E),
                                     z=mk(T, Fd), h=mk(T, Fd), pre2=mk(T, E), xout=mk(T, E)))
         if n_saved_layers:
-            ws.update(dx=mk(T, E), dx2=mk(T, E), dpre=mk(T, E), dz=mk(T, Fd), dqkv=mk(T, 3 * E), dctx=mk(T, E),
+            ws.update(dx=mk(T, E), dx2=mk(T, E), dpre=mk(T, E), dpre_drop=mk(T, E), dz=mk(T, Fd), dqkv=mk(T, 3 * E), dctx=mk(T, E),
                       du=mk(T, self.Q), dnews_bf=mk(n, self.D), dpooled=mk(n, E, dt=F32))
         if len(self.ws) > 8:
             self.ws.clear()
@@ -239,9 +265,10 @@ class Encoder:
         return ws
 
     # ---- forward ----------------------------------------------------------------------
-    def forward(self, x, flat=None, save=False, out=None):
+    def forward(self, x, flat=None, save=False, out=None, drop=None):
         """x int64 [n, 2L] -> news vectors fp32 [n, D].  With ``save`` the activations the
-        backward needs are kept in the workspace (layers >= lowest trainable layer)."""
+        backward needs are kept in the workspace (layers >= lowest trainable layer).  ``drop`` is a
+        DropState (training mode, reference semantics) or None (eval)."""
         if x.dtype != torch.int64 or x.dim() != 2 or x.shape[1] % 2:
             raise TinyRecError(f"news encoder input must be int64 [n, 2L], got {x.dtype} {tuple(x.shape)}")
         x = x.contiguous()
@@ -253,8 +280,10 @@ class Encoder:
         emb = self.bert.embeddings
         relpos = self.relpos(L)
         cur = ws["x0"]
+        dmk = (lambda site, p: drop.make(site, p)) if drop is not None else (lambda site, p: None)
+        ph, pa = (drop.p_hidden, drop.p_attn) if drop is not None else (0.0, 0.0)
         ops.embed_ln(x, L, self.word_table(), emb.position_embeddings.weight, emb.token_type_embeddings.weight[0],
-                     emb.LayerNorm.weight, emb.LayerNorm.bias, LN_EPS, cur)
+                     emb.LayerNorm.weight, emb.LayerNorm.bias, LN_EPS, cur, drop=dmk(SITE_EMB, ph))
         for i, lr in enumerate(self.layers):
             wqkv, bqkv, wo, w1, w2 = self.layer_weights(flat, i)
             if i >= low:
@@ -265,11 +294,11 @@ class Encoder:
                 qkv, ctx, pre1, x1, h, pre2, z = ws["qkv"], ws["ctx"], ws["pre"], ws["x1"], ws["h"], ws["pre"], None
                 xout = ws["xb"] if cur is ws["xa"] else ws["xa"]
             ops.gemm(cur, wqkv, qkv, bias=bqkv)
-            ops.attn_fwd(qkv, x, L, relpos, ctx, self.A)
-            ops.gemm(ctx, wo, pre1, bias=lr.o.bias, residual=cur)
+            ops.attn_fwd(qkv, x, L, relpos, ctx, self.A, drop=dmk(drop_site(i, KIND_ATTN), pa))
+            ops.gemm(ctx, wo, pre1, bias=lr.o.bias, residual=cur, drop=dmk(drop_site(i, KIND_ATT_OUT), ph))
             ops.layernorm_fwd(pre1, lr.ln1.weight, lr.ln1.bias, LN_EPS, x1)
             ops.gemm(x1, w1, h, bias=lr.f1.bias, act=ops.ACT_GELU, aux=z)
-            ops.gemm(h, w2, pre2, bias=lr.f2.bias, residual=x1)
+            ops.gemm(h, w2, pre2, bias=lr.f2.bias, residual=x1, drop=dmk(drop_site(i, KIND_FFN_OUT), ph))
             ops.layernorm_fwd(pre2, lr.ln2.weight, lr.ln2.bias, LN_EPS, xout)
             cur = xout
         at = self.mod.attn
@@ -279,7 +308,7 @@ class Encoder:
             out = torch.empty(n, self.D, device=dev, dtype=F32)
         ops.gemm(ws["pooled"], self._w(flat, self.mod.dense.weight), out, bias=self.mod.dense.bias)
         if save:
-            ws["xlast"], ws["x"], ws["n"], ws["L"], ws["low"] = cur, x, n, L, low
+            ws["xlast"], ws["x"], ws["n"], ws["L"], ws["low"], ws["drop"] = cur, x, n, L, low, drop
         self.last_ws = ws
         return out
 
@@ -300,6 +329,9 @@ class Encoder:
         """d_news fp32 [n, D] -> parameter gradients accumulated into ``flat.grad``."""
         ws = self.last_ws
         n, L, low, x = ws["n"], ws["L"], ws["low"], ws["x"]
+        drop = ws.get("drop")
+        dmk = (lambda site, p: drop.make(site, p)) if drop is not None else (lambda site, p: None)
+        ph, pa = (drop.p_hidden, drop.p_attn) if drop is not None else (0.0, 0.0)
         T, E = n * L, self.E
         nl = len(self.layers)
         at, dense = self.mod.attn, self.mod.dense
@@ -331,22 +363,29 @@ class Encoder:
             wqkv, bqkv, wo, w1, w2 = self.layer_weights(flat, i)
             dpre, dz, dqkv, dctx, dx2 = ws["dpre"], ws["dz"], ws["dqkv"], ws["dctx"], ws["dx2"]
             sg, sb = (flat.g_view(lr.ln2.weight), flat.g_view(lr.ln2.bias)) if train else (self.scratch_ln[:E], self.scratch_ln[E:])
-            ops.layernorm_bwd(dx, sv["pre2"], lr.ln2.weight, LN_EPS, dpre, sg, sb)
+            # dpre = grad at (dropout(dense) + residual); dd = grad at the dense output (mask re-applied)
+            d2 = dmk(drop_site(i, KIND_FFN_OUT), ph)
+            dd = ws["dpre_drop"] if d2 is not None else dpre
+            ops.layernorm_bwd(dx, sv["pre2"], lr.ln2.weight, LN_EPS, dpre, sg, sb,
+                              dx_drop=dd if d2 is not None else None, drop=d2)
             if train:
-                self._wgrad(flat, lr.f2.weight, dpre, sv["h"])
-                ops.colsum(dpre, flat.g_view(lr.f2.bias))
-            ops.gemm(dpre, w2, dz, b_t=True, act=ops.ACT_DGELU, aux=sv["z"])
+                self._wgrad(flat, lr.f2.weight, dd, sv["h"])
+                ops.colsum(dd, flat.g_view(lr.f2.bias))
+            ops.gemm(dd, w2, dz, b_t=True, act=ops.ACT_DGELU, aux=sv["z"])
             if train:
                 self._wgrad(flat, lr.f1.weight, dz, sv["x1"])
                 ops.colsum(dz, flat.g_view(lr.f1.bias))
             ops.gemm(dz, w1, dx2, b_t=True, residual=dpre)                 # d x1
             sg, sb = (flat.g_view(lr.ln1.weight), flat.g_view(lr.ln1.bias)) if train else (self.scratch_ln[:E], self.scratch_ln[E:])
-            ops.layernorm_bwd(dx2, sv["pre1"], lr.ln1.weight, LN_EPS, dpre, sg, sb)
+            d1 = dmk(drop_site(i, KIND_ATT_OUT), ph)
+            dd = ws["dpre_drop"] if d1 is not None else dpre
+            ops.layernorm_bwd(dx2, sv["pre1"], lr.ln1.weight, LN_EPS, dpre, sg, sb,
+                              dx_drop=dd if d1 is not None else None, drop=d1)
             if train:
-                self._wgrad(flat, lr.o.weight, dpre, sv["ctx"])
-                ops.colsum(dpre, flat.g_view(lr.o.bias))
-            ops.gemm(dpre, wo, dctx, b_t=True)
-            ops.attn_bwd(sv["qkv"], x, L, self.relpos(L), dctx, dqkv, self.A)
+                self._wgrad(flat, lr.o.weight, dd, sv["ctx"])
+                ops.colsum(dd, flat.g_view(lr.o.bias))
+            ops.gemm(dd, wo, dctx, b_t=True)
+            ops.attn_bwd(sv["qkv"], x, L, self.relpos(L), dctx, dqkv, self.A, drop=dmk(drop_site(i, KIND_ATTN), pa))
             if train:
                 self._wgrad(flat, lr.q.weight, dqkv, sv["xin"], rows=3 * E)
                 ob = flat.off(lr.q.bias)

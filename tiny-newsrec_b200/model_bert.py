@@ -18,7 +18,7 @@ from torch import nn
 
 from . import ops
 from ._lib import TinyRecError
-from .engine import BF, F32, Encoder, FlatParams
+from .engine import BF, F32, DropState, Encoder, FlatParams
 from .synth import BERT_BASE
 
 # ------------------------------------------------------------------------------------
@@ -135,6 +135,15 @@ class NewsEncoder(nn.Module):
         self.dense = nn.Linear(self.bert_config["hidden_size"], args.news_dim)
         self._engine = None
         self._flat = None           # set by the owning TrainState
+        self._drop = None
+
+    def drop_state(self, device):
+        """Dropout state shared by every forward of this encoder (probabilities from the bert config;
+        the reference's nn.Dropout modules, tnlrv3/modeling.py:177,223 + BertSelfOutput / BertOutput)."""
+        if self._drop is None or self._drop.seed.device != device:
+            c = self.bert_config
+            self._drop = DropState(device, c.get("hidden_dropout_prob", 0.1), c.get("attention_probs_dropout_prob", 0.1))
+        return self._drop
 
     def engine(self):
         if self._engine is None:
@@ -154,11 +163,14 @@ class NewsEncoder(nn.Module):
             elif flat.stale():
                 flat.refresh_shadow()
         n = x.shape[0]
-        if n <= chunk:
-            return eng.forward(x, flat)
+        drop = None
+        if self.training:                      # nn.Module semantics: dropout is active unless .eval() was called
+            drop = self.drop_state(x.device)
         out = torch.empty(n, eng.D, device=x.device, dtype=F32)
         for s in range(0, n, chunk):
-            eng.forward(x[s:s + chunk], flat, out=out[s:s + chunk])
+            if drop is not None:
+                drop.advance()
+            eng.forward(x[s:s + chunk], flat, out=out[s:s + chunk], drop=drop)
         return out
 
 
@@ -247,7 +259,7 @@ class TrainState:
 
     # ---- one fused forward (+ eager head gradients) -------------------------------------------
     def step_forward(self, history, history_mask, candidate, label, th_list, tc_list, temperature, coef, use_mask,
-                     want_grad):
+                     want_grad, training=False):
         B, H, W = history.shape
         K = candidate.shape[1]
         M = len(th_list)
@@ -263,7 +275,11 @@ class TrainState:
         Q = self.ue.attn.att_fc1.weight.shape[0]
         w = self.head_ws(B, H, K, M, D, Q, dev)
         R = B * (H + K)
-        news = self.enc.forward(x, flat, save=want_grad, out=w["news"])
+        drop = None
+        if training:
+            drop = self.ne.drop_state(dev)
+            drop.advance()
+        news = self.enc.forward(x, flat, save=want_grad, out=w["news"], drop=drop)
         mask = history_mask.contiguous().float()
         label = label.contiguous()
         at = self.ue.attn
@@ -437,7 +453,8 @@ class Model(nn.Module):
         st = self.train_state()
         want_grad = torch.is_grad_enabled() and st.flat is not None
         args = (history, history_mask, candidate, label, list(teacher_history_embs), list(teacher_candidate_embs),
-                float(self.args.temperature), float(self.args.coef), bool(self.args.user_log_mask), want_grad)
+                float(self.args.temperature), float(self.args.coef), bool(self.args.user_log_mask), want_grad,
+                bool(self.training))
         if want_grad:
             return _StepFn.apply(st.anchor, st, args)
         w = st.step_forward(*args)

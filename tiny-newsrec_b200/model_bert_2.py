@@ -37,7 +37,8 @@ class ModelBert(nn.Module):
         st = self.train_state()
         want_grad = torch.is_grad_enabled() and st.flat is not None
         # CE only: M = 0 teachers, coef = 1 -> total == target loss (model_bert_2.py:212)
-        args = (history, history_mask, candidate, label, [], [], 1.0, 1.0, bool(self.args.user_log_mask), want_grad)
+        args = (history, history_mask, candidate, label, [], [], 1.0, 1.0, bool(self.args.user_log_mask), want_grad,
+                bool(self.training))
         if want_grad:
             total, _, _, _, score = _StepFn.apply(st.anchor, st, args)
             return total, score

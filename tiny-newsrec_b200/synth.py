@@ -24,7 +24,8 @@ import torch
 
 BERT_BASE = dict(vocab_size=30522, hidden_size=768, num_attention_heads=12,
                  intermediate_size=3072, max_position_embeddings=512, type_vocab_size=2,
-                 rel_pos_bins=32, max_rel_pos=128, layer_norm_eps=1e-12, num_labels=2)
+                 rel_pos_bins=32, max_rel_pos=128, layer_norm_eps=1e-12, num_labels=2,
+                 hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
 
 
 def _gen(seed, key):
