@@ -100,10 +100,11 @@ int tnr_layernorm_fwd(const void* x_bf16, int rows, int E, const float* gamma, c
 /* dx = dLN(dy; x) ; dgamma += , dbeta += (fp32, caller zero-initialises).  autograd of the above.
  * If dx_drop_bf16 != NULL it receives dx * keep / (1-p) for dropout tensor `drop` -- the gradient
  * w.r.t. the dense output that was dropped out before the residual add (dx itself is the residual
- * branch); with drop disabled it is a plain copy of dx. */
+ * branch); with drop disabled it is a plain copy of dx.  If dsum != NULL, dsum[c] += sum_r
+ * (dropout-masked) dx[r,c]: the bias gradient of that dense layer, fused here. */
 int tnr_layernorm_bwd(const void* dy_bf16, const void* x_bf16, int rows, int E, const float* gamma,
                       float eps, void* dx_bf16, float* dgamma, float* dbeta, void* dx_drop_bf16,
-                      const tnr_dropout* drop, void* stream);
+                      float* dsum, const tnr_dropout* drop, void* stream);
 /* out[c] += sum_r x[r,c]  (bias gradients of nn.Linear). */
 int tnr_colsum_bf16(const void* x_bf16, int rows, int cols, int ld, float* out, void* stream);
 

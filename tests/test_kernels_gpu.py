@@ -296,8 +296,10 @@ def test_embed_ln_dropout_and_layernorm_bwd_drop_output():
     xin, dy = _randn(rows, E, seed=6), _randn(rows, E, seed=7)
     dx, dxd = torch.empty_like(xin), torch.empty_like(xin)
     dg, db = torch.zeros(E, device="cuda"), torch.zeros(E, device="cuda")
-    ops.layernorm_bwd(dy, xin, gamma, 1e-12, dx, dg, db, dx_drop=dxd, drop=ops.make_drop(st, 1, P_DROP))
+    dsum = torch.zeros(E, device="cuda")
+    ops.layernorm_bwd(dy, xin, gamma, 1e-12, dx, dg, db, dx_drop=dxd, drop=ops.make_drop(st, 1, P_DROP), dsum=dsum)
     assert _rel_err(dxd, dx.float() * keep / (1 - P_DROP))[0] < 4e-3
+    assert _rel_err(dsum, (dx.float() * keep / (1 - P_DROP)).sum(0))[0] < 2e-3     # fused bias gradient
     ops.layernorm_bwd(dy, xin, gamma, 1e-12, dx, dg, db, dx_drop=dxd, drop=None)
     assert torch.equal(dxd, dx)
 

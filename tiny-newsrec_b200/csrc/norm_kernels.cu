@@ -81,109 +81,211 @@ embed_ln_kernel(const int64_t* __restrict__ ids, int ids_ld, int L, int n_tokens
   ln_row<VPL>(x, gamma, beta, eps, lane, out + (size_t)t * E, dc, (uint64_t)t);
 }
 
-// y = LN(x) for a bf16 "pre-LN" buffer (dense + bias + residual written by the GEMM epilogue)
+// y = LN(x) for a bf16 "pre-LN" buffer (dense + bias + residual written by the GEMM epilogue).
+// Persistent warps: gamma / beta stay in registers (re-loading them per row made the kernel
+// L1-bound: ncu l1tex 85 %, dram 36 %), two rows in flight per warp.
 template <int VPL>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int rows, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y) {
   constexpr int E = VPL * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * ROWS_PER_BLOCK + warp;
-  if (r >= rows) return;
-  float v[VPL * 8];
+  float g[VPL * 8], bt[VPL * 8];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i)
-    unpack8(*reinterpret_cast<const bf16x8*>(x + (size_t)r * E + (i * 32 + lane) * 8), &v[i * 8]);
-  DropCfg dc; dc.seed = 0; dc.site = 0; dc.thr16 = 0; dc.scale = 1.f;
-  ln_row<VPL>(v, gamma, beta, eps, lane, y + (size_t)r * E, dc, 0);
+  for (int v = 0; v < VPL; ++v) {
+    const int col = (v * 32 + lane) * 8;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 gg = *reinterpret_cast<const float4*>(gamma + col + 4 * h);
+      const float4 bb = *reinterpret_cast<const float4*>(beta + col + 4 * h);
+      g[v * 8 + 4 * h + 0] = gg.x; g[v * 8 + 4 * h + 1] = gg.y; g[v * 8 + 4 * h + 2] = gg.z; g[v * 8 + 4 * h + 3] = gg.w;
+      bt[v * 8 + 4 * h + 0] = bb.x; bt[v * 8 + 4 * h + 1] = bb.y; bt[v * 8 + 4 * h + 2] = bb.z; bt[v * 8 + 4 * h + 3] = bb.w;
+    }
+  }
+  const int stride = gridDim.x * ROWS_PER_BLOCK;
+  for (int r0 = blockIdx.x * ROWS_PER_BLOCK + warp; r0 < rows; r0 += 2 * stride) {
+    const int r1 = r0 + stride;
+    bf16x8 raw0[VPL], raw1[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) raw0[v] = *reinterpret_cast<const bf16x8*>(x + (size_t)r0 * E + (v * 32 + lane) * 8);
+    if (r1 < rows) {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) raw1[v] = *reinterpret_cast<const bf16x8*>(x + (size_t)r1 * E + (v * 32 + lane) * 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int r = k ? r1 : r0;
+      if (r >= rows) break;
+      float xv[VPL * 8];
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) unpack8(k ? raw1[v] : raw0[v], &xv[v * 8]);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL * 8; ++i) s += xv[i];
+      const float mean = warp_sum(s) * (1.0f / E);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL * 8; ++i) { const float d = xv[i] - mean; q += d * d; }
+      const float rstd = rsqrtf(warp_sum(q) * (1.0f / E) + eps);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (xv[v * 8 + i] - mean) * rstd * g[v * 8 + i] + bt[v * 8 + i];
+        *reinterpret_cast<bf16x8*>(y + (size_t)r * E + (v * 32 + lane) * 8) = pack8(o);
+      }
+    }
+  }
 }
 
 // LayerNorm backward.  xhat recomputed from the saved pre-LN row.
 //   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
-//   dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy      (fp32 atomics, one per column per block)
-// A persistent grid walks rows so each block flushes its partial sums once.
+//   dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; dsum += sum_rows dx_drop (the bias gradient of
+//   the dense layer in front of this LayerNorm -- saves a separate column-sum pass over dx)
+// Persistent grid, one 14-warp block per SM.  The three per-column accumulators live in registers; each warp
+// streams its rows through a private double-buffered shared-memory stage filled by cp.async, so the
+// next row's loads are in flight while the current row is reduced (the first version held the row in
+// registers: 171 registers, 1 block / SM, 29 % of HBM peak).
+__device__ __forceinline__ void ln_cp_async16(void* smem_dst, const void* src) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+constexpr int LNB_WARPS = 12;      // 384 threads x 144 registers (3 warps per SM sub-partition): one block per SM, no spills
+
 template <int VPL>
-__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+__global__ void __maxnreg__(144)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, int rows,
                      const float* __restrict__ gamma, float eps, __nv_bfloat16* __restrict__ dx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_drop,
-                     const tnr_dropout drop) {
+                     float* __restrict__ dsum, const tnr_dropout drop) {
   constexpr int E = VPL * 256;
+  extern __shared__ __align__(16) uint8_t ln_smem[];
   const DropCfg dc = load_drop(drop);
-  __shared__ float s_dg[E];
-  __shared__ float s_db[E];
-  for (int i = threadIdx.x; i < E; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float g_r[VPL * 8];
+  float* s_acc = reinterpret_cast<float*>(ln_smem);                       // [2][E] block totals of dgamma, dsum
+  float* s_db = s_acc + 2 * E + (size_t)warp * E;                          // per-warp dbeta accumulator [E]
+  // per warp: 2 stages x {x row, dy row} bf16
+  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(ln_smem + (2 + LNB_WARPS) * E * 4) + (size_t)warp * 4 * E;
+  for (int i = threadIdx.x; i < (2 + LNB_WARPS) * E; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float acc_dg[VPL * 8], acc_ds[VPL * 8];
 #pragma unroll
-  for (int v = 0; v < VPL; ++v) {
-    const int col = (v * 32 + lane) * 8;
-    const float4 g0 = *reinterpret_cast<const float4*>(gamma + col);
-    const float4 g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
-    g_r[v * 8 + 0] = g0.x; g_r[v * 8 + 1] = g0.y; g_r[v * 8 + 2] = g0.z; g_r[v * 8 + 3] = g0.w;
-    g_r[v * 8 + 4] = g1.x; g_r[v * 8 + 5] = g1.y; g_r[v * 8 + 6] = g1.z; g_r[v * 8 + 7] = g1.w;
-  }
-  float acc_dg[VPL * 8], acc_db[VPL * 8];
-#pragma unroll
-  for (int i = 0; i < VPL * 8; ++i) { acc_dg[i] = 0.f; acc_db[i] = 0.f; }
-
-  for (int r = blockIdx.x * ROWS_PER_BLOCK + warp; r < rows; r += gridDim.x * ROWS_PER_BLOCK) {
-    float xv[VPL * 8], dv[VPL * 8];
+  for (int i = 0; i < VPL * 8; ++i) { acc_dg[i] = 0.f; acc_ds[i] = 0.f; }
+  const int stride = gridDim.x * LNB_WARPS;
+  auto prefetch = [&](int st, int r) {
+    __nv_bfloat16* sx = stage + st * 2 * E;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-      const size_t off = (size_t)r * E + (v * 32 + lane) * 8;
-      unpack8(*reinterpret_cast<const bf16x8*>(x + off), &xv[v * 8]);
-      unpack8(*reinterpret_cast<const bf16x8*>(dy + off), &dv[v * 8]);
+      const int col = (v * 32 + lane) * 8;
+      ln_cp_async16(sx + col, x + (size_t)r * E + col);
+      ln_cp_async16(sx + E + col, dy + (size_t)r * E + col);
     }
+  };
+  int r = blockIdx.x * LNB_WARPS + warp;
+  if (r < rows) prefetch(0, r);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int st = 0;
+  for (; r < rows; r += stride, st ^= 1) {
+    if (r + stride < rows) prefetch(st ^ 1, r + stride);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    bf16x8 rx[VPL], rd[VPL];
+    {
+      const __nv_bfloat16* sx = stage + st * 2 * E;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        rx[v] = *reinterpret_cast<const bf16x8*>(sx + (v * 32 + lane) * 8);
+        rd[v] = *reinterpret_cast<const bf16x8*>(sx + E + (v * 32 + lane) * 8);
+      }
+    }
+    __syncwarp();                      // stage consumed: the next-next prefetch may overwrite it
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL * 8; ++i) s += xv[i];
+    for (int v = 0; v < VPL; ++v) {
+      float t[8];
+      unpack8(rx[v], t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += t[i];
+    }
     const float mean = warp_sum(s) * (1.0f / E);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL * 8; ++i) { xv[i] -= mean; q += xv[i] * xv[i]; }
+    for (int v = 0; v < VPL; ++v) {
+      float t[8];
+      unpack8(rx[v], t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = t[i] - mean; q += d * d; }
+    }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / E) + eps);
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL * 8; ++i) {
-      xv[i] *= rstd;                       // xhat
-      acc_dg[i] += dv[i] * xv[i];
-      acc_db[i] += dv[i];
-      dv[i] *= g_r[i];                     // g
-      sg += dv[i];
-      sgx += dv[i] * xv[i];
+    for (int v = 0; v < VPL; ++v) {
+      float t[8], d[8];
+      const int col = (v * 32 + lane) * 8;
+      unpack8(rx[v], t);
+      unpack8(rd[v], d);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float4 b0 = *reinterpret_cast<float4*>(s_db + col), b1 = *reinterpret_cast<float4*>(s_db + col + 4);
+      b0.x += d[0]; b0.y += d[1]; b0.z += d[2]; b0.w += d[3];
+      b1.x += d[4]; b1.y += d[5]; b1.z += d[6]; b1.w += d[7];
+      *reinterpret_cast<float4*>(s_db + col) = b0;
+      *reinterpret_cast<float4*>(s_db + col + 4) = b1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = (t[i] - mean) * rstd;
+        acc_dg[v * 8 + i] = fmaf(d[i], xh, acc_dg[v * 8 + i]);
+        const float gg = d[i] * gm[i];
+        sg += gg;
+        sgx = fmaf(gg, xh, sgx);
+      }
     }
     sg = warp_sum(sg) * (1.0f / E);
     sgx = warp_sum(sgx) * (1.0f / E);
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-      float o[8];
+      float t[8], d[8], o[8];
+      const int col = (v * 32 + lane) * 8;
+      unpack8(rx[v], t);
+      unpack8(rd[v], d);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = rstd * (dv[v * 8 + i] - sg - xv[v * 8 + i] * sgx);
-      *reinterpret_cast<bf16x8*>(dx + (size_t)r * E + (v * 32 + lane) * 8) = pack8(o);
-      if (dx_drop != nullptr) {
-        if (dc.thr16 != 0) {
-          const uint32_t keep = dropout_keep8(dc, ((uint64_t)r * (uint64_t)E + (uint64_t)((v * 32 + lane) * 8)) >> 3);
+      for (int i = 0; i < 8; ++i) o[i] = rstd * (d[i] * gm[i] - sg - (t[i] - mean) * rstd * sgx);
+      *reinterpret_cast<bf16x8*>(dx + (size_t)r * E + col) = pack8(o);
+      if (dc.thr16 != 0) {
+        const uint32_t keep = dropout_keep8(dc, ((uint64_t)r * (uint64_t)E + (uint64_t)col) >> 3);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * dc.scale : 0.f;
-        }
-        *reinterpret_cast<bf16x8*>(dx_drop + (size_t)r * E + (v * 32 + lane) * 8) = pack8(o);
+        for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * dc.scale : 0.f;
+      }
+      if (dx_drop != nullptr) *reinterpret_cast<bf16x8*>(dx_drop + (size_t)r * E + col) = pack8(o);
+      if (dsum != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc_ds[v * 8 + i] += o[i];
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int v = 0; v < VPL; ++v)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int col = (v * 32 + lane) * 8 + i;
-      atomicAdd(&s_dg[col], acc_dg[v * 8 + i]);
-      atomicAdd(&s_db[col], acc_db[v * 8 + i]);
+      atomicAdd(&s_acc[col], acc_dg[v * 8 + i]);
+      if (dsum != nullptr) atomicAdd(&s_acc[E + col], acc_ds[v * 8 + i]);
     }
   __syncthreads();
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
-    atomicAdd(dgamma + i, s_dg[i]);
-    atomicAdd(dbeta + i, s_db[i]);
+    atomicAdd(dgamma + i, s_acc[i]);
+    if (dsum != nullptr) atomicAdd(dsum + i, s_acc[E + i]);
+    float b = 0.f;
+#pragma unroll
+    for (int w = 0; w < LNB_WARPS; ++w) b += s_acc[(2 + w) * E + i];
+    atomicAdd(dbeta + i, b);
   }
 }
 
@@ -255,7 +357,9 @@ extern "C" __attribute__((visibility("default"))) int tnr_embed_ln_fwd(const int
 extern "C" __attribute__((visibility("default"))) int tnr_layernorm_fwd(const void* x_bf16, int rows, int E, const float* gamma, const float* beta, float eps,
                                  void* y_bf16, void* stream) {
   if (rows == 0) return 0;
-  const int grid = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+  int grid = (rows + 2 * ROWS_PER_BLOCK - 1) / (2 * ROWS_PER_BLOCK);
+  const int cap_f = num_sms() * 2;
+  if (grid > cap_f) grid = cap_f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   DISPATCH_VPL(E, (layernorm_fwd_kernel<VPL><<<grid, ROWS_PER_BLOCK * 32, 0, st>>>(
                       reinterpret_cast<const __nv_bfloat16*>(x_bf16), rows, gamma, beta, eps,
@@ -265,17 +369,19 @@ extern "C" __attribute__((visibility("default"))) int tnr_layernorm_fwd(const vo
 }
 
 extern "C" __attribute__((visibility("default"))) int tnr_layernorm_bwd(const void* dy_bf16, const void* x_bf16, int rows, int E, const float* gamma, float eps,
-                                 void* dx_bf16, float* dgamma, float* dbeta, void* dx_drop_bf16, const tnr_dropout* drop,
-                                 void* stream) {
+                                 void* dx_bf16, float* dgamma, float* dbeta, void* dx_drop_bf16, float* dsum,
+                                 const tnr_dropout* drop, void* stream) {
   if (rows == 0) return 0;
-  int grid = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
-  const int cap = num_sms() * 4;
+  int grid = (rows + LNB_WARPS - 1) / LNB_WARPS;
+  const int cap = num_sms();
   if (grid > cap) grid = cap;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  DISPATCH_VPL(E, (layernorm_bwd_kernel<VPL><<<grid, ROWS_PER_BLOCK * 32, 0, st>>>(
+  const int smem = (2 + LNB_WARPS) * E * 4 + LNB_WARPS * 4 * E * 2;
+  DISPATCH_VPL(E, (cudaFuncSetAttribute(layernorm_bwd_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
+  DISPATCH_VPL(E, (layernorm_bwd_kernel<VPL><<<grid, LNB_WARPS * 32, smem, st>>>(
                       reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16),
                       rows, gamma, eps, reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta,
-                      reinterpret_cast<__nv_bfloat16*>(dx_drop_bf16), drop_or_none(drop))));
+                      reinterpret_cast<__nv_bfloat16*>(dx_drop_bf16), dsum, drop_or_none(drop))));
   TNR_LAUNCH_CHECK();
   return 0;
 }

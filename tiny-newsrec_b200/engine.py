@@ -367,10 +367,10 @@ class Encoder:
             d2 = dmk(drop_site(i, KIND_FFN_OUT), ph)
             dd = ws["dpre_drop"] if d2 is not None else dpre
             ops.layernorm_bwd(dx, sv["pre2"], lr.ln2.weight, LN_EPS, dpre, sg, sb,
-                              dx_drop=dd if d2 is not None else None, drop=d2)
+                              dx_drop=dd if d2 is not None else None, drop=d2,
+                              dsum=flat.g_view(lr.f2.bias) if train else None)       # + f2.bias gradient
             if train:
                 self._wgrad(flat, lr.f2.weight, dd, sv["h"])
-                ops.colsum(dd, flat.g_view(lr.f2.bias))
             ops.gemm(dd, w2, dz, b_t=True, act=ops.ACT_DGELU, aux=sv["z"])
             if train:
                 self._wgrad(flat, lr.f1.weight, dz, sv["x1"])
@@ -380,10 +380,10 @@ class Encoder:
             d1 = dmk(drop_site(i, KIND_ATT_OUT), ph)
             dd = ws["dpre_drop"] if d1 is not None else dpre
             ops.layernorm_bwd(dx2, sv["pre1"], lr.ln1.weight, LN_EPS, dpre, sg, sb,
-                              dx_drop=dd if d1 is not None else None, drop=d1)
+                              dx_drop=dd if d1 is not None else None, drop=d1,
+                              dsum=flat.g_view(lr.o.bias) if train else None)        # + attention.output.dense.bias gradient
             if train:
                 self._wgrad(flat, lr.o.weight, dd, sv["ctx"])
-                ops.colsum(dd, flat.g_view(lr.o.bias))
             ops.gemm(dd, wo, dctx, b_t=True)
             ops.attn_bwd(sv["qkv"], x, L, self.relpos(L), dctx, dqkv, self.A, drop=dmk(drop_site(i, KIND_ATTN), pa))
             if train:

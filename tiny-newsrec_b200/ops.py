@@ -173,13 +173,13 @@ def layernorm_fwd(x, gamma, beta, eps, out):
 
 
 @_timed
-def layernorm_bwd(dy, x, gamma, eps, dx, dgamma, dbeta, dx_drop=None, drop=None):
+def layernorm_bwd(dy, x, gamma, eps, dx, dgamma, dbeta, dx_drop=None, drop=None, dsum=None):
     lib = _ready(x)
     rows, E = x.shape
     _lib.check(lib.tnr_layernorm_bwd(_ptr(_chk(dy, _bf16, "ln.dy")), _ptr(_chk(x, _bf16, "ln.x")), rows, E,
                                      _ptr(gamma), eps, _ptr(_chk(dx, _bf16, "ln.dx")),
                                      _ptr(_chk(dgamma, _f32, "dgamma")), _ptr(_chk(dbeta, _f32, "dbeta")),
-                                     _ptr(dx_drop), _dp(drop), _stream()), "tnr_layernorm_bwd")
+                                     _ptr(dx_drop), _ptr(dsum), _dp(drop), _stream()), "tnr_layernorm_bwd")
     return dx
 
 
