@@ -325,8 +325,10 @@ class Encoder:
         g = flat.g_view(p) if rows is None else flat.grad[flat.off(p):flat.off(p) + rows * p.shape[1]].view(rows, p.shape[1])
         ops.gemm(dy, xin, g, a_t=True, b_t=True, split_k=self._splitk(M, xin.shape[1], dy.shape[0]), accumulate=True)
 
-    def backward(self, d_news, flat):
-        """d_news fp32 [n, D] -> parameter gradients accumulated into ``flat.grad``."""
+    def backward(self, d_news, flat, on_layer_done=None):
+        """d_news fp32 [n, D] -> parameter gradients accumulated into ``flat.grad``.
+        ``on_layer_done(i)`` is called after the last gradient kernel of encoder layer ``i`` was
+        enqueued (bucketed gradient all-reduce overlapping the rest of the backward)."""
         ws = self.last_ws
         n, L, low, x = ws["n"], ws["L"], ws["low"], ws["x"]
         drop = ws.get("drop")
@@ -392,3 +394,5 @@ class Encoder:
                 ops.colsum(dqkv, flat.grad[ob:ob + 3 * E])
             if i > low:
                 ops.gemm(dqkv, wqkv, dx, b_t=True, residual=dpre)
+            if on_layer_done is not None and train:
+                on_layer_done(i)

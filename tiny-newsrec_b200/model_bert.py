@@ -334,12 +334,26 @@ class TrainState:
         w = self.last
         flat = self.flat
         w["d_news"].mul_(g_total)
-        self.enc.backward(w["d_news"], flat)
         if self.head_end > self.head_begin:
             self.stage.mul_(g_total)
             flat.grad[self.head_begin:self.head_end].add_(self.stage[:self.head_end - self.head_begin])
-        if self.comm_hook is not None:
-            self.comm_hook(flat)
+        if self.comm_hook is None:
+            self.enc.backward(w["d_news"], flat)
+            return
+        # Bucketed exchange: the flat buffer is laid out [layer low | ... | layer top | pooling head | user
+        # encoder | transform_matrix] and the backward finishes it from the END: once layer i is done,
+        # everything from its first parameter up to the previous bucket start is final.
+        done_to = [flat.numel]
+
+        def layer_done(i):
+            lo = flat.off(self.enc.layers[i].q.weight)
+            if lo < done_to[0]:
+                self.comm_hook(flat, lo, done_to[0])
+                done_to[0] = lo
+
+        self.enc.backward(w["d_news"], flat, on_layer_done=layer_done)
+        if done_to[0] > 0:
+            self.comm_hook(flat, 0, done_to[0])
 
 
 def _const_stride(tensors):

@@ -69,36 +69,40 @@ def broadcast_parameters(model, root_rank=0):
 class DistributedOptimizer:
     """Average the flat gradient buffer over ranks (NCCL all-reduce over NVLink), then step.
 
-    ``overlap=True`` launches the all-reduce on a side stream from the end of the backward
-    (TrainState.comm_hook) so it overlaps the remaining host work; ``step()`` waits for it."""
+    ``overlap=True`` launches one all-reduce per gradient bucket on a side stream as soon as the
+    backward has finished that bucket (TrainState.comm_hook: top encoder layer + heads first, lower
+    layers as they complete), so the exchange of layer i overlaps the backward of layer i-1 like
+    Horovod's per-tensor hooks did; ``step()`` waits for all of them."""
 
     def __init__(self, optimizer, overlap=True):
         self.opt = optimizer
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.opt.grad_scale = 1.0 / self.world          # SUM all-reduce, scale folded into Adam
         self.stream = torch.cuda.Stream() if (self.world > 1 and overlap) else None
-        self.pending = None
+        self.pending = []
         if self.stream is not None:
             self.opt.model.train_state().comm_hook = self._launch
 
-    def _launch(self, flat):
+    def _launch(self, flat, lo=0, hi=None):
+        hi = flat.numel if hi is None else hi
         ev = torch.cuda.Event()
         ev.record()
         self.stream.wait_event(ev)
         with torch.cuda.stream(self.stream):
-            dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
+            dist.all_reduce(flat.grad[lo:hi], op=dist.ReduceOp.SUM)
             done = torch.cuda.Event()
             done.record()
-        self.pending = done
+        self.pending.append(done)
 
     def zero_grad(self, set_to_none=False):
         self.opt.zero_grad()
 
     def step(self):
         if self.world > 1:
-            if self.stream is not None and self.pending is not None:
-                torch.cuda.current_stream().wait_event(self.pending)
-                self.pending = None
+            if self.stream is not None and self.pending:
+                for ev in self.pending:
+                    torch.cuda.current_stream().wait_event(ev)
+                self.pending = []
             else:
                 dist.all_reduce(self.opt._flat().grad, op=dist.ReduceOp.SUM)
         self.opt.step()
