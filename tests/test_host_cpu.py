@@ -179,15 +179,19 @@ mean, total = par.reduce_eval_sums(3 + rank, torch.tensor([1.0, 2.0, 3.0, 4.0]) 
 assert total == 7 and torch.allclose(mean, torch.tensor([3.0, 6.0, 9.0, 12.0], dtype=torch.float64) / 7)
 assert par.shard_files(list(range(5)), rank, world) == list(range(rank, 5, 2))
 dist.destroy_process_group()
-print("ok", rank)
+sys.stdout.write("ok%d\n" % rank); sys.stdout.flush()
 """
 
 
 def test_two_rank_gloo_collectives(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER.format(root=ROOT))
+    import socket
+    with socket.socket() as sk:                       # a free port: a fixed one can still be in TIME_WAIT
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        capture_output=True, text=True, timeout=240, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "ok 0" in r.stdout and "ok 1" in r.stdout
+    assert "ok0" in r.stdout and "ok1" in r.stdout
