@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TNR_ABI_VERSION 2
+#define TNR_ABI_VERSION 3
 
 const char* tnr_last_error(void);
 int tnr_abi_version(void);
@@ -109,15 +109,19 @@ int tnr_layernorm_bwd(const void* dy_bf16, const void* x_bf16, int rows, int E, 
 int tnr_colsum_bf16(const void* x_bf16, int rows, int cols, int ld, float* out, void* stream);
 
 /* ------------------------------------------------------------ fused attention */
-/* ctx = softmax(Q K^T / 8 + (1-mask)*-10000 + relpos[h]) V for L <= 32, head dim 64.
- * qkv bf16 [n*L, 3E] (Q | K | V), mask int64 (row r at mask + r*mask_ld, 1 = attend),
- * relpos fp32 [A, L, L], ctx bf16 [n*L, E].  `drop` applies dropout to the probabilities (:223).
+/* ctx = dropout(softmax(Q K^T / 8 + (1-mask)*-10000 + relbias[h][j-i])) V, head dim 64, 1 <= L <= 512.
+ * qkv bf16 [n*L, 3E] (Q | K | V), mask int64 (row r at mask + r*mask_ld, 1 = attend), ctx bf16 [n*L, E].
+ * relbias fp32 [A, 2L-1]: bias of key j for query i at index (j - i) + L - 1.  The reference builds a
+ * [n, A, L, L] bias per forward from one-hot buckets (tnlrv3/modeling.py:458-463); position_ids are always
+ * arange(L) (:162-163), so it is batch-invariant and a function of j - i only.
+ * L <= 32: one warp per (news, head); L > 32: streamed-KV online-softmax kernel (attention_long.cu).
+ * `drop` applies dropout to the probabilities (:223).
  * Replaces BertSelfAttention.multi_head_attention, tnlrv3/modeling.py:205-231. */
-int tnr_attn_relpos_fwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relpos,
+int tnr_attn_relpos_fwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias,
                         void* ctx_bf16, int n_news, int L, int A, int E, const tnr_dropout* drop,
                         void* stream);
-/* dqkv bf16 [n*L, 3E] from dctx (probabilities recomputed, dropout mask regenerated). */
-int tnr_attn_relpos_bwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relpos,
+/* dqkv bf16 [n*L, 3E] from dctx (probabilities recomputed, dropout mask regenerated).  L <= 32. */
+int tnr_attn_relpos_bwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias,
                         const void* dctx_bf16, void* dqkv_bf16, int n_news, int L, int A, int E,
                         const tnr_dropout* drop, void* stream);
 
@@ -164,7 +168,9 @@ int tnr_user_encoder_bwd(const float* vecs, const float* mask, const float* pad_
  * Row layout of the [R, D] news matrices: history block (b,h) -> b*H+h, then candidate block
  * (b,k) -> B*H + b*K + k; teacher matrices T_ext / TP_ext / G_ext are [M, B*(H+K)+B, D] with the
  * B per-impression user rows appended (raw / projected by transform_matrix / gradient).
- * losses[0..2] += {distill, emb, target} batch means; score_out [B,K];
+ * losses: fp32 [4 + 4B + 1], zero-initialised ONCE by the caller: [0..3] = {distill, emb, target, total}
+ * batch means (assigned; summed in impression order, so bit-reproducible), [4 + 4b ..] per-impression
+ * terms, last word a ticket counter the kernel resets.  score_out [B,K];
  * if want_grad: d_news [R,D] (assigned), d_user [B,D], G_ext (grad w.r.t. TP_ext).
  * M == 0 gives the PLM-NR loss (CE only, coef scales it).
  * Replaces Model.forward, Tiny-NewsRec/model_bert.py:262-306 (+ kd_ce_loss :208-219,

@@ -125,7 +125,7 @@ def test_gemm_b_mn_major(M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K,split", [(768, 768, 512, 1), (768, 3072, 1000, 4), (3072, 768, 5280, 8),
-                                         (200, 768, 960, 3), (256, 256, 1760, 2)])
+                                         (200, 768, 960, 3), (256, 256, 1760, 2), (640, 768, 2000, 5)])
 def test_gemm_wgrad_mn_major_splitk(M, N, K, split):
     """wgrad: dW[M, N] = dY[K, M]^T @ X[K, N], both operands MN-major, split-K fp32 atomics."""
     ops = _ops()
@@ -137,6 +137,64 @@ def test_gemm_wgrad_mn_major_splitk(M, N, K, split):
     assert rel < 1e-4, (rel, mx)
     ops.gemm(dy, x, out, a_t=True, b_t=True, split_k=split, accumulate=True)     # accumulates
     assert _rel_err(out, 2 * ref)[0] < 1e-4
+
+
+# CTA-pair (tcgen05 cta_group::2) kernels take over for M >= 4096, N > 128, bf16 output (gemm_tcgen05.cu).
+@pytest.mark.parametrize("M,N,K,b_t", [(4096, 768, 768, False), (4200, 2304, 768, False), (4232, 768, 3072, False),
+                                       (4096, 256, 64, False), (5000, 3072, 768, True), (4200, 768, 2304, True),
+                                       (4100, 200, 768, False)])
+def test_gemm_cta_pair_plain(M, N, K, b_t):
+    """Odd numbers of 128-row tiles (the second CTA of the last pair is all padding), ragged M and N,
+    K-major and MN-major B."""
+    ops = _ops()
+    a = _randn(M, K, seed=21)
+    blog = _randn(N, K, scale=0.05, seed=22)
+    b = blog.t().contiguous() if b_t else blog
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=BF)
+    ops.gemm(a, b, out, b_t=b_t)
+    ref = a.float() @ blog.float().t()
+    rel, mx = _rel_err(out, ref)
+    assert rel < 5e-3, (rel, mx)
+    # every row block matches on its own (a swapped / dropped half tile would hide in a global norm)
+    blk = (out.float() - ref).reshape(-1)[: (M // 8) * 8 * N].reshape(M // 8, -1).norm(dim=1)
+    refn = ref.reshape(-1)[: (M // 8) * 8 * N].reshape(M // 8, -1).norm(dim=1)
+    assert float((blk / (refn + 1e-6)).max()) < 2e-2
+
+
+def test_gemm_cta_pair_epilogues():
+    ops = _ops()
+    M, N, K = 4200, 3072, 768
+    a, b = _randn(M, K, seed=23), _randn(N, K, scale=0.03, seed=24)
+    bias = _randn(N, dtype=torch.float32, scale=0.1, seed=25)
+    out = torch.empty(M, N, device="cuda", dtype=BF)
+    pre = torch.empty(M, N, device="cuda", dtype=BF)
+    ops.gemm(a, b, out, bias=bias, act=ops.ACT_GELU, aux=pre)
+    z = a.float() @ b.float().t() + bias
+    assert _rel_err(pre, z)[0] < 5e-3
+    assert _rel_err(out, torch.nn.functional.gelu(z))[0] < 5e-3
+    ops.gemm(a, b, out, bias=bias, act=ops.ACT_GELU)                       # no pre-activation output
+    assert _rel_err(out, torch.nn.functional.gelu(z))[0] < 5e-3
+    # bias + residual (BertSelfOutput / BertOutput dense)
+    N2, K2 = 768, 3072
+    a2, b2 = _randn(M, K2, seed=26), _randn(N2, K2, scale=0.03, seed=27)
+    res = _randn(M, N2, seed=28)
+    out2 = torch.empty(M, N2, device="cuda", dtype=BF)
+    ops.gemm(a2, b2, out2, bias=bias[:N2].contiguous(), residual=res)
+    assert _rel_err(out2, a2.float() @ b2.float().t() + bias[:N2] + res.float())[0] < 5e-3
+    # dgrad + dGELU (MN-major B, pre-activation box prefetched by TMA)
+    dy, w = _randn(M, K, seed=29), _randn(K, N, scale=0.03, seed=30)
+    zz = _randn(M, N, seed=31)
+    dz = torch.empty(M, N, device="cuda", dtype=BF)
+    ops.gemm(dy, w, dz, b_t=True, act=ops.ACT_DGELU, aux=zz)
+    zf = zz.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).backward(dy.float() @ w.float())
+    assert _rel_err(dz, zf.grad)[0] < 5e-3
+    # dgrad + residual
+    dx = torch.empty(M, K, device="cuda", dtype=BF)
+    w1 = _randn(N, K, scale=0.03, seed=32)
+    r2 = _randn(M, K, seed=33)
+    ops.gemm(dz, w1, dx, b_t=True, residual=r2)
+    assert _rel_err(dx, dz.float() @ w1.float() + r2.float())[0] < 5e-3
 
 
 def test_gemm_rejects_bad_arguments():
@@ -201,7 +259,14 @@ def test_colsum():
 
 
 # ------------------------------------------------------------------ attention
-def _attn_ref(qkv, mask, relpos, n, L, A):
+def _rel_matrix(relvec, L):
+    """[A, 2L-1] bias vector -> the [A, L, L] matrix the reference adds (entry [i, j] = vec[(j - i) + L - 1])."""
+    idx = torch.arange(L, device=relvec.device)
+    return relvec[:, (idx[None, :] - idx[:, None]) + L - 1]
+
+
+def _attn_ref(qkv, mask, relvec, n, L, A):
+    relpos = _rel_matrix(relvec, L)
     E = qkv.shape[1] // 3
     q, k, v = [t.reshape(n, L, A, 64).permute(0, 2, 1, 3) for t in qkv.float().split(E, dim=1)]
     s = q @ k.transpose(-1, -2) / 8.0 + (1.0 - mask.float())[:, None, None, :] * -10000.0 + relpos[None]
@@ -220,7 +285,7 @@ def test_attention_fwd_bwd(L):
     if n > 2:
         mask[2] = 0                                  # all-pad news
     x = torch.cat([torch.zeros_like(mask), mask], 1)
-    relpos = _randn(A, L, L, dtype=torch.float32, seed=4)
+    relpos = _randn(A, 2 * L - 1, dtype=torch.float32, seed=4)
     ctx = torch.empty(n * L, E, device="cuda", dtype=BF)
     ops.attn_fwd(qkv, x, L, relpos, ctx, A)
     qf = qkv.float().requires_grad_(True)
@@ -231,6 +296,29 @@ def test_attention_fwd_bwd(L):
     dqkv = torch.empty_like(qkv)
     ops.attn_bwd(qkv, x, L, relpos, dctx, dqkv, A)
     assert _rel_err(dqkv, qf.grad)[0] < 6e-3
+
+
+@pytest.mark.parametrize("L", [33, 64, 100, 180, 512])
+def test_attention_long_fwd(L):
+    """Streamed-KV kernel for body / abstract lengths (32 < L <= 512): ragged lengths, an all-pad row,
+    tail query block and tail key chunk."""
+    ops = _ops()
+    n, A, E = (5, 12, 768) if L <= 180 else (2, 12, 768)
+    qkv = _randn(n * L, 3 * E, seed=1)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    lens = torch.randint(1, L + 1, (n,), generator=g, device="cuda")
+    lens[0] = L
+    mask = (torch.arange(L, device="cuda")[None, :] < lens[:, None]).long()
+    mask[n - 1] = 0                                  # all-pad news
+    x = torch.cat([torch.zeros_like(mask), mask], 1)
+    relpos = _randn(A, 2 * L - 1, dtype=torch.float32, seed=4)
+    ctx = torch.full((n * L, E), float("nan"), device="cuda", dtype=BF)
+    ops.attn_fwd(qkv, x, L, relpos, ctx, A)
+    ref = _attn_ref(qkv, mask, relpos, n, L, A)
+    assert torch.isfinite(ctx.float()).all()
+    assert _rel_err(ctx, ref)[0] < 5e-3
+    per_row = (ctx.float() - ref).norm(dim=1) / (ref.norm(dim=1) + 1e-3)
+    assert float(per_row.max()) < 3e-2
 
 
 # ------------------------------------------------------------------ dropout (counter-based masks)
@@ -313,7 +401,7 @@ def test_attention_dropout_fwd_bwd(L):
     mask = torch.ones(n, L, device="cuda", dtype=torch.long)
     mask[1, L // 2:] = 0
     x = torch.cat([torch.zeros_like(mask), mask], 1)
-    relpos = _randn(A, L, L, dtype=torch.float32, seed=4)
+    relpos = _randn(A, 2 * L - 1, dtype=torch.float32, seed=4)
     st = _seed_tensor(31337)
     drop = ops.make_drop(st, 21, P_DROP)
     ctx = torch.empty(n * L, E, device="cuda", dtype=BF)
@@ -321,7 +409,7 @@ def test_attention_dropout_fwd_bwd(L):
     keep = torch.from_numpy(attention_keep(31337, 21, n * A, L, P_DROP)).cuda().float().reshape(n, A, L, L)
     qf = qkv.float().requires_grad_(True)
     q, k, v = [t.reshape(n, L, A, 64).permute(0, 2, 1, 3) for t in qf.split(E, dim=1)]
-    s = q @ k.transpose(-1, -2) / 8.0 + (1.0 - mask.float())[:, None, None, :] * -10000.0 + relpos[None]
+    s = q @ k.transpose(-1, -2) / 8.0 + (1.0 - mask.float())[:, None, None, :] * -10000.0 + _rel_matrix(relpos, L)[None]
     ref = ((torch.softmax(s, -1) * keep / (1 - P_DROP)) @ v).permute(0, 2, 1, 3).reshape(n * L, E)
     assert _rel_err(ctx, ref)[0] < 6e-3
     dctx = _randn(n * L, E, seed=5)

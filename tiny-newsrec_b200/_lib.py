@@ -93,7 +93,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res
-    if lib.tnr_abi_version() != 2:
+    if lib.tnr_abi_version() != 3:
         raise TinyRecError("libtinyrec.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -1,7 +1,9 @@
 // Fused short-sequence self-attention with relative-position bias (L <= 32, head dim 64).
-//   P = softmax(Q K^T / sqrt(dh) + (1 - mask) * -10000 + relpos[h]);  ctx = dropout(P) V
+//   P = softmax(Q K^T / sqrt(dh) + (1 - mask) * -10000 + relbias[h][j - i]);  ctx = dropout(P) V
 // Reference: Tiny-NewsRec/tnlrv3/modeling.py:205-231 (multi_head_attention), mask :446-454,
-// rel-pos bias :458-463 (batch-invariant [A, L, L] table).
+// rel-pos bias :458-463.  position_ids are always arange(L) (:162-163), so the reference's per-forward
+// [n, A, L, L] bias is batch-invariant and Toeplitz: a [A, 2L-1] vector indexed by (j - i) + L - 1, which
+// each warp keeps in shared memory.  L > 32 is handled by attention_long.cu (forward).
 //
 // The op is HBM-bound (arithmetic intensity 4*L*E / (8*E) = 15 FLOP/B at L = 30): one warp per
 // (news, head) stages its 32x64 Q/K/V (and dO) tiles with cp.async into padded shared memory,
@@ -11,6 +13,7 @@
 // 128-byte rows.  The backward recomputes P from Q,K (nothing but QKV is saved) and regenerates
 // the dropout mask from the Philox counter.
 #include "common.cuh"
+#include "mma_sync.cuh"
 
 namespace tnr {
 
@@ -21,30 +24,11 @@ constexpr int TS = 72;            // smem row stride (bf16) of a 32 x 64 tile: 1
 constexpr int PS = 40;            // smem row stride (bf16) of the 32 x 32 P / dS tiles: 80 B
 constexpr int TILE_BYTES = LMAX * TS * 2;
 constexpr int PT_BYTES = LMAX * PS * 2;
-constexpr int ATT_FWD_SMEM_PER_WARP = 3 * TILE_BYTES + LMAX * 4;
-constexpr int ATT_BWD_SMEM_PER_WARP = 4 * TILE_BYTES + 2 * PT_BYTES + LMAX * 4;
+constexpr int ATT_FWD_SMEM_PER_WARP = 3 * TILE_BYTES + LMAX * 4 + 2 * LMAX * 4;        // tiles, key mask, rel-pos vector
+constexpr int ATT_BWD_SMEM_PER_WARP = 4 * TILE_BYTES + 2 * PT_BYTES + LMAX * 4 + 2 * LMAX * 4;
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
+int attn_long_fwd_launch(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias, void* ctx_bf16,
+                         int n_news, int L, int A, int E, const tnr_dropout* drop, cudaStream_t st);
 
 // L rows x 64 bf16 from global (row stride ld) -> padded smem tile; rows >= L are zero-filled
 __device__ __forceinline__ void load_tile_async(__nv_bfloat16* s, const __nv_bfloat16* g, int L, int ld, int lane) {
@@ -133,16 +117,22 @@ __device__ __forceinline__ void c_to_a(uint32_t (&pa)[2][2][4], const float (&p)
     }
 }
 
+// per-head rel-pos bias vector [2L-1] (index (j - i) + L - 1) -> this warp's shared-memory copy
+__device__ __forceinline__ void load_relbias(float* srel, const float* __restrict__ relbias, int h, int L, int lane) {
+  const float* src = relbias + (size_t)h * (2 * L - 1);
+  if (lane < 2 * L - 1) srel[lane] = __ldg(src + lane);
+  if (lane + 32 < 2 * L - 1) srel[lane + 32] = __ldg(src + lane + 32);
+}
+
 // raw QK^T accumulators -> normalised probabilities (C layout; columns >= L become 0)
-__device__ __forceinline__ void softmax_frag(float (&s)[2][4][4], const float* smadd, const float* __restrict__ relpos_h,
-                                             int L, int lane) {
+__device__ __forceinline__ void softmax_frag(float (&s)[2][4][4], const float* smadd, const float* srel, int L, int lane) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int hi = 0; hi < 2; ++hi) {
       const int i = mt * 16 + g + hi * 8;
-      const float* relrow = relpos_h + (size_t)(i < L ? i : L - 1) * L;
+      const float* relrow = srel + (L - 1 - (i < L ? i : L - 1));      // relrow[j] = bias of key j for query i
       float mx = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
@@ -150,7 +140,7 @@ __device__ __forceinline__ void softmax_frag(float (&s)[2][4][4], const float* s
         for (int e = 0; e < 2; ++e) {
           const int j = nt * 8 + 2 * t + e;
           float v = -INFINITY;
-          if (j < L) v = s[mt][nt][hi * 2 + e] * 0.125f + smadd[j] + __ldg(relrow + j);
+          if (j < L) v = s[mt][nt][hi * 2 + e] * 0.125f + smadd[j] + relrow[j];
           s[mt][nt][hi * 2 + e] = v;
           mx = fmaxf(mx, v);
         }
@@ -184,7 +174,7 @@ __device__ __forceinline__ uint32_t attn_keep8(const DropCfg& dc, long long item
 
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ mask, int mask_ld,
-                const float* __restrict__ relpos, __nv_bfloat16* __restrict__ ctx, int n_news, int L, int A, int E,
+                const float* __restrict__ relbias, __nv_bfloat16* __restrict__ ctx, int n_news, int L, int A, int E,
                 const tnr_dropout drop) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,6 +185,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
   __nv_bfloat16* sK = sQ + LMAX * TS;
   __nv_bfloat16* sV = sK + LMAX * TS;
   float* smadd = reinterpret_cast<float*>(sV + LMAX * TS);
+  float* srel = smadd + LMAX;
   const int n = (int)(item / A), h = (int)(item % A);
   const int ld = 3 * E;
   const __nv_bfloat16* base = qkv + (size_t)n * L * ld + h * DH;
@@ -202,6 +193,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
   load_tile_async(sK, base + E, L, ld, lane);
   load_tile_async(sV, base + 2 * E, L, ld, lane);
   smadd[lane] = lane < L ? (1.0f - (float)mask[(size_t)n * mask_ld + lane]) * -10000.0f : 0.f;
+  load_relbias(srel, relbias, h, L, lane);
   const DropCfg dc = load_drop(drop);
   cp_async_wait_all();
   __syncwarp();
@@ -214,7 +206,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
 #pragma unroll
       for (int c = 0; c < 4; ++c) s[mt][nt][c] = 0.f;
   mma_xyT(s, sQ, sK, lane);
-  softmax_frag(s, smadd, relpos + (size_t)h * L * L, L, lane);
+  softmax_frag(s, smadd, srel, L, lane);
   if (dc.thr16 != 0) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
@@ -247,7 +239,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
 
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ mask, int mask_ld,
-                const float* __restrict__ relpos, const __nv_bfloat16* __restrict__ dctx,
+                const float* __restrict__ relbias, const __nv_bfloat16* __restrict__ dctx,
                 __nv_bfloat16* __restrict__ dqkv, int n_news, int L, int A, int E, const tnr_dropout drop) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -261,6 +253,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
   __nv_bfloat16* sP = sO + LMAX * TS;
   __nv_bfloat16* sS = sP + LMAX * PS;
   float* smadd = reinterpret_cast<float*>(sS + LMAX * PS);
+  float* srel = smadd + LMAX;
   const int n = (int)(item / A), h = (int)(item % A);
   const int ld = 3 * E;
   const int g = lane >> 2, t = lane & 3;
@@ -270,6 +263,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
   load_tile_async(sV, base + 2 * E, L, ld, lane);
   load_tile_async(sO, dctx + (size_t)n * L * E + h * DH, L, E, lane);
   smadd[lane] = lane < L ? (1.0f - (float)mask[(size_t)n * mask_ld + lane]) * -10000.0f : 0.f;
+  load_relbias(srel, relbias, h, L, lane);
   const DropCfg dc = load_drop(drop);
   cp_async_wait_all();
   __syncwarp();
@@ -282,7 +276,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
 #pragma unroll
       for (int c = 0; c < 4; ++c) { p[mt][nt][c] = 0.f; dp[mt][nt][c] = 0.f; }
   mma_xyT(p, sQ, sK, lane);
-  softmax_frag(p, smadd, relpos + (size_t)h * L * L, L, lane);
+  softmax_frag(p, smadd, srel, L, lane);
   mma_xyT(dp, sO, sV, lane);                    // dP = dO V^T
   // dS = P o (dP_eff - delta) / 8, P_drop = P o keep * scale; both to smem (bf16) for the transposed products
 #pragma unroll
@@ -366,16 +360,19 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
 
 using namespace tnr;
 
-static int check_attn(const char* who, int L, int A, int E) {
-  TNR_REQUIRE(L >= 1 && L <= LMAX, "%s: L=%d not supported by the short-sequence kernel (1..%d)", who, L, LMAX);
+static int check_attn(const char* who, int L, int A, int E, int lmax) {
+  TNR_REQUIRE(L >= 1 && L <= lmax, "%s: L=%d not supported (1..%d)", who, L, lmax);
   TNR_REQUIRE(A * DH == E, "%s: needs head dim 64 (A=%d, E=%d)", who, A, E);
   return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_fwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relpos,
+extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_fwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias,
                                    void* ctx_bf16, int n_news, int L, int A, int E, const tnr_dropout* drop, void* stream) {
-  if (check_attn("tnr_attn_relpos_fwd", L, A, E)) return 1;
+  if (check_attn("tnr_attn_relpos_fwd", L, A, E, 512)) return 1;
   if (n_news == 0) return 0;
+  if (L > LMAX)
+    return attn_long_fwd_launch(qkv_bf16, mask, mask_ld, relbias, ctx_bf16, n_news, L, A, E, drop,
+                                reinterpret_cast<cudaStream_t>(stream));
   const long long items = (long long)n_news * A;
   const int grid = (int)((items + ATT_WARPS - 1) / ATT_WARPS);
   const int smem = ATT_WARPS * ATT_FWD_SMEM_PER_WARP;
@@ -385,16 +382,16 @@ extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_fwd(const 
     attr_done = true;
   }
   attn_fwd_kernel<<<grid, ATT_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relpos, reinterpret_cast<__nv_bfloat16*>(ctx_bf16),
+      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relbias, reinterpret_cast<__nv_bfloat16*>(ctx_bf16),
       n_news, L, A, E, drop_or_none(drop));
   TNR_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_bwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relpos,
+extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_bwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias,
                                    const void* dctx_bf16, void* dqkv_bf16, int n_news, int L, int A, int E,
                                    const tnr_dropout* drop, void* stream) {
-  if (check_attn("tnr_attn_relpos_bwd", L, A, E)) return 1;
+  if (check_attn("tnr_attn_relpos_bwd", L, A, E, LMAX)) return 1;      // L > 32: forward only so far
   if (n_news == 0) return 0;
   const long long items = (long long)n_news * A;
   const int grid = (int)((items + ATT_WARPS - 1) / ATT_WARPS);
@@ -405,7 +402,7 @@ extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_bwd(const 
     attr_done = true;
   }
   attn_bwd_kernel<<<grid, ATT_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relpos,
+      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relbias,
       reinterpret_cast<const __nv_bfloat16*>(dctx_bf16), reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), n_news, L, A, E,
       drop_or_none(drop));
   TNR_LAUNCH_CHECK();

@@ -1,0 +1,211 @@
+// Self-attention with relative-position bias for 32 < L <= 512 (body / abstract text, table build of
+// title+abstract+body rows), head dim 64, forward.
+//   P = softmax(Q K^T / 8 + (1 - mask) * -10000 + relbias[h][j - i]);  ctx = dropout(P) V
+// Reference: Tiny-NewsRec/tnlrv3/modeling.py:205-231, mask :446-454, rel-pos bias :458-463.
+//
+// One block (4 warps) per (news, head, 64-query block); each warp owns 16 query rows.  K / V are streamed
+// through shared memory in 64-key chunks (cp.async), the two contractions run on ldmatrix + mma.sync
+// m16n8k16 (bf16 in, fp32 accumulate) with the usual online softmax (running max / sum per row, the output
+// accumulator rescaled when the max moves), so nothing of size L x L is ever materialised.  The bias is a
+// function of j - i only: the per-head [2L-1] vector and the additive key mask live in shared memory.
+// Arithmetic intensity is 4 L E / (8 E) = L / 2 FLOP/B: HBM-bound below L ~ 400 on B200.
+#include "common.cuh"
+#include "mma_sync.cuh"
+
+namespace tnr {
+
+constexpr int LDH = 64;            // head dim
+constexpr int LQB = 64;            // query rows per block
+constexpr int LKB = 64;            // keys per chunk
+constexpr int LTS = 72;            // smem row stride (bf16): 144 B, ldmatrix conflict-free
+constexpr int LONG_LMAX = 512;
+
+// rows [r0, r0 + 64) x 64 bf16 of a [L, ld] matrix -> padded smem tile; rows >= L zero-filled. 128 threads.
+__device__ __forceinline__ void long_load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, int r0, int L, int ld, int tid) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = tid + 128 * it, r = idx >> 3, c = idx & 7;
+    if (r0 + r < L) cp_async16(smem_addr(s + r * LTS + c * 8), g + (size_t)(r0 + r) * ld + c * 8);
+    else *reinterpret_cast<uint4*>(s + r * LTS + c * 8) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+attn_long_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ mask, int mask_ld,
+                     const float* __restrict__ relbias, __nv_bfloat16* __restrict__ ctx, int n_news, int L, int A, int E,
+                     int q_blocks, const tnr_dropout drop) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sK = sQ + LQB * LTS;
+  __nv_bfloat16* sV = sK + LKB * LTS;
+  float* s_madd = reinterpret_cast<float*>(sV + LKB * LTS);       // [k_chunks * 64]
+  const int k_chunks = (L + LKB - 1) / LKB;
+  float* s_rel = s_madd + k_chunks * LKB;                         // [2L - 1]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const long long item = blockIdx.x / q_blocks;
+  const int qb = blockIdx.x % q_blocks;
+  const int n = (int)(item / A), h = (int)(item % A);
+  const int q0 = qb * LQB;
+  const int ld = 3 * E;
+  const __nv_bfloat16* base = qkv + (size_t)n * L * ld + h * LDH;
+  const DropCfg dc = load_drop(drop);
+
+  long_load_tile(sQ, base, q0, L, ld, tid);
+  for (int j = tid; j < k_chunks * LKB; j += 128)
+    s_madd[j] = j < L ? (1.0f - (float)mask[(size_t)n * mask_ld + j]) * -10000.0f : -INFINITY;
+  for (int d = tid; d < 2 * L - 1; d += 128) s_rel[d] = relbias[(size_t)h * (2 * L - 1) + d];
+  cp_async_wait_all();
+  __syncthreads();
+
+  // Q fragments of this warp's 16 rows stay in registers for the whole key loop
+  uint32_t qa[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    ldsm_x4(smem_addr(sQ + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LTS + ks * 16 + (lane >> 4) * 8), qa[ks]);
+
+  float o[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[nt][c] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int i0 = q0 + warp * 16 + g;                 // this thread's rows: i0 and i0 + 8
+  const bool warp_live = q0 + warp * 16 < L;         // warp-uniform: rows beyond L produce nothing
+
+  for (int kc = 0; kc < k_chunks; ++kc) {
+    const int c0 = kc * LKB;
+    __syncthreads();                                 // previous chunk fully consumed
+    long_load_tile(sK, base + E, c0, L, ld, tid);
+    long_load_tile(sV, base + 2 * E, c0, L, ld, tid);
+    cp_async_wait_all();
+    __syncthreads();
+    if (!warp_live) continue;
+
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[nt][c] = 0.f;
+      uint32_t kb[2][4];
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+        ldsm_x4(smem_addr(sK + (nt * 8 + (lane & 7)) * LTS + half * 32 + (lane >> 3) * 8), kb[half]);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) mma_bf16(s[nt], qa[ks], kb[ks >> 1][(ks & 1) * 2], kb[ks >> 1][(ks & 1) * 2 + 1]);
+    }
+    // scores -> probabilities of this chunk under the running maximum
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const int i = min(i0 + hi * 8, L - 1);
+      const float* rel = s_rel + (L - 1 - i);        // rel[j] = bias of key j for query i
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = c0 + nt * 8 + 2 * t + e;
+          float v = -INFINITY;
+          if (j < L) v = s[nt][hi * 2 + e] * 0.125f + s_madd[j] + rel[j];
+          s[nt][hi * 2 + e] = v;
+          mx = fmaxf(mx, v);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(m_run[hi], mx);      // finite: every chunk holds at least one key j < L
+      const float corr = __expf(m_run[hi] - m_new);  // exp(-inf) = 0 on the first chunk
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float pv = __expf(s[nt][hi * 2 + e] - m_new);
+          s[nt][hi * 2 + e] = pv;
+          sum += pv;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      l_run[hi] = l_run[hi] * corr + sum;
+      m_run[hi] = m_new;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) { o[nt][hi * 2] *= corr; o[nt][hi * 2 + 1] *= corr; }
+    }
+    if (dc.thr16 != 0) {
+      // dropout on the (unnormalised) probabilities; the 1/(1-p) scale commutes with the final 1/l.
+      // Philox group of (item, i, chunk kc, quad lane t, half of the chunk): 8 elements, bit (nt & 3) * 2 + e.
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        const uint64_t row = (uint64_t)item * (uint64_t)L + (uint64_t)min(i0 + hi * 8, L - 1);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const uint32_t keep = dropout_keep8(dc, ((row * (uint64_t)k_chunks + (uint64_t)kc) * 4 + (uint64_t)t) * 2 + hf);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              s[hf * 4 + q][hi * 2 + e] = ((keep >> (q * 2 + e)) & 1u) ? s[hf * 4 + q][hi * 2 + e] * dc.scale : 0.f;
+        }
+      }
+    }
+    // P (16 x 64, C layout) -> A fragments; O += P V
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      pa[ks][0] = pack_bf16(s[2 * ks][0], s[2 * ks][1]);
+      pa[ks][1] = pack_bf16(s[2 * ks][2], s[2 * ks][3]);
+      pa[ks][2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+      pa[ks][3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int kh = 0; kh < 2; ++kh) {               // keys 0-31, 32-63 of the chunk
+        uint32_t vb[4];
+        ldsm_x4_t(smem_addr(sV + (kh * 32 + lane) * LTS + nt * 8), vb);
+        mma_bf16(o[nt], pa[kh * 2], vb[0], vb[1]);
+        mma_bf16(o[nt], pa[kh * 2 + 1], vb[2], vb[3]);
+      }
+    }
+  }
+  if (!warp_live) return;
+  // normalise, stage this warp's 16 x 64 rows in its own (already consumed) part of sQ, store full 128 B rows
+  const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
+  __nv_bfloat16* sO = sQ + warp * 16 * LTS;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<uint32_t*>(sO + g * LTS + nt * 8 + 2 * t) = pack_bf16(o[nt][0] * inv0, o[nt][1] * inv0);
+    *reinterpret_cast<uint32_t*>(sO + (g + 8) * LTS + nt * 8 + 2 * t) = pack_bf16(o[nt][2] * inv1, o[nt][3] * inv1);
+  }
+  __syncwarp();
+  __nv_bfloat16* obase = ctx + (size_t)n * L * E + h * LDH;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = lane + 32 * it, r = idx >> 3, c = idx & 7;
+    const int row = q0 + warp * 16 + r;
+    if (row < L) *reinterpret_cast<uint4*>(obase + (size_t)row * E + c * 8) = *reinterpret_cast<const uint4*>(sO + r * LTS + c * 8);
+  }
+}
+
+// host launcher used by tnr_attn_relpos_fwd (attention.cu) for L > 32
+int attn_long_fwd_launch(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias, void* ctx_bf16,
+                         int n_news, int L, int A, int E, const tnr_dropout* drop, cudaStream_t st) {
+  TNR_REQUIRE(L <= LONG_LMAX, "tnr_attn_relpos_fwd: L=%d exceeds %d (the position table of the encoder)", L, LONG_LMAX);
+  const int q_blocks = (L + LQB - 1) / LQB;
+  const int k_chunks = (L + LKB - 1) / LKB;
+  const long long blocks = (long long)n_news * A * q_blocks;
+  TNR_REQUIRE(blocks < (1ll << 31), "tnr_attn_relpos_fwd: too many blocks");
+  const int smem = 3 * LQB * LTS * 2 + (k_chunks * LKB + 2 * L - 1) * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TNR_CHECK_CUDA(cudaFuncSetAttribute(attn_long_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        3 * LQB * LTS * 2 + (LONG_LMAX + 2 * LONG_LMAX) * 4));
+    attr_done = true;
+  }
+  attn_long_fwd_kernel<<<(unsigned)blocks, 128, smem, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relbias, reinterpret_cast<__nv_bfloat16*>(ctx_bf16),
+      n_news, L, A, E, q_blocks, drop_or_none(drop));
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tnr

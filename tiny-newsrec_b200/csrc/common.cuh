@@ -82,6 +82,71 @@ __device__ __forceinline__ float gelu_erf_grad(float z) {
   return fmaf(s * s * e * qp2, zc, s);
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) ----------------
+// The K = 768 GEMM epilogues have ~45 issue slots per output element and thread; the scalar GELU alone took
+// ~10 of the ~24 they used, which made the FFN1 / dGELU GEMMs epilogue-bound (1050 vs 1250 TFLOP/s).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid(2 q(z)) for a pair: s = 1 / (1 + 2^(w(u) z)), u = min(z^2, 64).  Clamping u (not z) keeps the
+// fitted range of the polynomial and still saturates: |z| > 8 gives 2^(-4.98 |z|) -> 0 or inf -> s = 1 or 0.
+__device__ __forceinline__ void gelu_sig2(f32x2 z, float& s0, float& s1) {
+  float u0, u1;
+  upk2(mul2(z, z), u0, u1);
+  const f32x2 u = pk2(fminf(u0, 64.0f), fminf(u1, 64.0f));
+  const f32x2 w = fma2(fma2(pk2(0.001014264184050262f, 0.001014264184050262f), u,
+                            pk2(-0.10677573084831238f, -0.10677573084831238f)), u,
+                       pk2(-2.301121234893799f, -2.301121234893799f));
+  float a0, a1;
+  upk2(mul2(w, z), a0, a1);
+  float d0, d1;
+  upk2(add2(pk2(ex2_approx(a0), ex2_approx(a1)), pk2(1.0f, 1.0f)), d0, d1);
+  s0 = rcp_approx(d0);
+  s1 = rcp_approx(d1);
+}
+// same function as gelu_erf() / gelu_erf_grad(), two elements per call
+__device__ __forceinline__ f32x2 gelu_erf2(f32x2 z) {
+  float s0, s1;
+  gelu_sig2(z, s0, s1);
+  return mul2(z, pk2(s0, s1));
+}
+__device__ __forceinline__ f32x2 gelu_erf_grad2(f32x2 z) {
+  float s0, s1;
+  gelu_sig2(z, s0, s1);
+  const f32x2 s = pk2(s0, s1);
+  float u0, u1;
+  upk2(mul2(z, z), u0, u1);
+  const f32x2 u = pk2(fminf(u0, 64.0f), fminf(u1, 64.0f));
+  const f32x2 qp2 = fma2(fma2(pk2(-0.003515171750f, -0.003515171750f), u, pk2(0.2220338916f, 0.2220338916f)), u,
+                         pk2(1.595015762f, 1.595015762f));                       // 2 q'(z)
+  const f32x2 ss = fma2(mul2(s, pk2(-1.0f, -1.0f)), s, s);                       // s (1 - s) = s - s^2 (no inf * 0)
+  return fma2(mul2(ss, qp2), z, s);
+}
+
 // 16-byte vector of 8 bf16
 struct __align__(16) bf16x8 { uint32_t u[4]; };
 

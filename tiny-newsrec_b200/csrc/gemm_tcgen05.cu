@@ -12,8 +12,16 @@
 // Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile i overlap the
 // main loop of tile i+1.  Split-K work items accumulate with fp32 atomics (wgrad).
 //
+// CTA2 variant (large-M forward / dgrad GEMMs): the two CTAs of a cluster (one TPC) work on one
+// 256 x BN tile with tcgen05.mma.cta_group::2.  Each CTA TMA-loads its own 128 rows of A and HALF of the
+// B tile (BN/2 rows) -- 32 KB instead of 48 KB of L2->SM operand traffic per CTA and k-block -- and both
+// loads signal the LEADER's "full" barrier; the leader's elected thread issues the 256-row MMAs and
+// multicasts the "stage free" / "accumulator ready" commits to both CTAs; each CTA's epilogue warps
+// drain their own 128 TMEM lanes and release the accumulator on the leader's barrier.
+//
 // Replaces every nn.Linear on the path (reference call sites listed in include/tinyrec.h).
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace tnr {
@@ -101,6 +109,47 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on a barrier given by its shared::cluster address (possibly in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are accounted on `cluster_bar` (the leader's barrier)
+__device__ __forceinline__ void tma_load_2d_cta2(uint32_t smem_dst, const CUtensorMap* map, uint32_t cluster_bar, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive (when all prior MMAs of this thread retire) on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc2(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_cta2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -130,7 +179,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, bool mn_major)
   return d;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool CTA2 = false>
 __host__ __device__ constexpr uint32_t make_idesc() {
   return (1u << 4)                      // D format f32
          | (1u << 7)                    // A bf16
@@ -138,15 +187,17 @@ __host__ __device__ constexpr uint32_t make_idesc() {
          | ((A_MN ? 1u : 0u) << 15)     // A major
          | ((B_MN ? 1u : 0u) << 16)     // B major
          | ((uint32_t)(BN >> 3) << 17)  // N
-         | ((uint32_t)(BM >> 4) << 24); // M
+         | ((uint32_t)((CTA2 ? 2 * BM : BM) >> 4) << 24); // M (256 across the CTA pair)
 }
 
-template <int BN, bool EPI_TMA>
+template <int BN, bool EPI_TMA, bool CTA2 = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;    // B rows (of N) staged by one CTA
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? (EPI_TMA ? 3 : 4) : (EPI_TMA ? 4 : 6);
+  static constexpr int STAGES = CTA2 ? ((BN == 256) ? (EPI_TMA ? 5 : 6) : (EPI_TMA ? 6 : 8))
+                                     : ((BN == 256) ? (EPI_TMA ? 3 : 4) : (EPI_TMA ? 4 : 6));
   static constexpr int TMEM_COLS = 2 * BN;             // 2 accumulator stages (power of 2 >= 32)
   static constexpr int EPI_BOX_BYTES = 32 * 128;       // 32 rows x 64 bf16, SWIZZLE_128B
   static constexpr int EPI_BYTES = EPI_TMA ? NUM_EPI_WARPS * 2 * EPI_BOX_BYTES : 0;
@@ -218,49 +269,55 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const DropCfg& d
 template <int ACT>
 __device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg& dc, const uint32_t* acc, int row, int col,
                                                  uint8_t* out_box, uint8_t* in_box, uint8_t* aux_box, uint32_t swz) {
-  float v[8];
+  // four packed fp32 pairs (FFMA2 path, common.cuh)
+  f32x2 v[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[i]);
+  for (int i = 0; i < 4; ++i) v[i] = pk2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
   if (p.bias != nullptr && col < p.N) {
     const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
     const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    v[0] = add2(v[0], pk2(b0.x, b0.y)); v[1] = add2(v[1], pk2(b0.z, b0.w));
+    v[2] = add2(v[2], pk2(b1.x, b1.y)); v[3] = add2(v[3], pk2(b1.z, b1.w));
   }
-  if (ACT == TNR_ACT_GELU) {
-    if (p.aux_out) *reinterpret_cast<bf16x8*>(aux_box + swz) = pack8(v);
+  auto pack_out = [&](uint8_t* box) {
+    bf16x8 o;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 4; ++i) { float lo, hi; upk2(v[i], lo, hi); o.u[i] = pack_bf16(lo, hi); }
+    *reinterpret_cast<bf16x8*>(box + swz) = o;
+  };
+  if (ACT == TNR_ACT_GELU) {
+    if (p.aux_out) pack_out(aux_box);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = gelu_erf2(v[i]);
   } else if (ACT == TNR_ACT_TANH) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = tanhf(v[i]);
+    for (int i = 0; i < 4; ++i) { float lo, hi; upk2(v[i], lo, hi); v[i] = pk2(tanhf(lo), tanhf(hi)); }
   } else if (ACT == TNR_ACT_DGELU) {
-    float z[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(in_box + swz), z);
+    const bf16x8 zr = *reinterpret_cast<const bf16x8*>(in_box + swz);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(z[i]);
+    for (int i = 0; i < 4; ++i) v[i] = mul2(v[i], gelu_erf_grad2(pk2(bf16_lo(zr.u[i]), bf16_hi(zr.u[i]))));
   }
   if (dc.thr16 != 0) {
     const uint32_t keep = dropout_keep8(dc, ((uint64_t)row * (uint64_t)p.N + (uint64_t)col) >> 3);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * dc.scale : 0.f;
+    for (int i = 0; i < 4; ++i)
+      v[i] = mul2(v[i], pk2(((keep >> (2 * i)) & 1u) ? dc.scale : 0.f, ((keep >> (2 * i + 1)) & 1u) ? dc.scale : 0.f));
   }
   if (ACT != TNR_ACT_DGELU && p.in_mode == 1) {
-    float r[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(in_box + swz), r);
+    const bf16x8 rr = *reinterpret_cast<const bf16x8*>(in_box + swz);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += r[i];
+    for (int i = 0; i < 4; ++i) v[i] = add2(v[i], pk2(bf16_lo(rr.u[i]), bf16_hi(rr.u[i])));
   }
-  *reinterpret_cast<bf16x8*>(out_box + swz) = pack8(v);
+  pack_out(out_box);
 }
 
 // ---------------------------------------------------------------- kernel
-template <int BN, bool A_MN, bool B_MN, int ACT, bool EPI_TMA>
+template <int BN, bool A_MN, bool B_MN, int ACT, bool EPI_TMA, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_in,
             const __grid_constant__ CUtensorMap tmap_aux, const Params p) {
-  using C = Cfg<BN, EPI_TMA>;
+  using C = Cfg<BN, EPI_TMA, CTA2>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -276,6 +333,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;     // 0 = leader of the CTA pair
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -286,50 +344,82 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), NUM_EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), (CTA2 ? 2 : 1) * NUM_EPI_WARPS); }
     for (int w = 0; w < NUM_EPI_WARPS; ++w) { mbar_init(ld_bar(w, 0), 1); mbar_init(ld_bar(w, 1), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTA2) {   // pair allocation: the same warp of both CTAs, same columns in both SMs
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();     // the peer's barriers must be initialised before remote arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  // work items: (n_blk fastest, m_unit, k split); an m_unit is one 128-row tile, or a 256-row pair tile (CTA2)
+  const int m_units = CTA2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int total_tiles = m_units * p.n_tiles * p.splits;
+  const int t_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_stride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < total_tiles; t += t_stride) {
         const int n_blk = t % p.n_tiles;
-        const int m_blk = (t / p.n_tiles) % p.m_tiles;
-        const int ks = t / (p.n_tiles * p.m_tiles);
+        const int m_unit = (t / p.n_tiles) % m_units;
+        const int m_blk = CTA2 ? 2 * m_unit + (int)cta_rank : m_unit;
+        const int ks = t / (p.n_tiles * m_units);
         const int kb0 = ks * p.k_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.k_per_split);
+        const int n0 = n_blk * BN + (CTA2 ? (int)cta_rank * (BN / 2) : 0);   // this CTA's rows of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
-          if (!A_MN) {
-            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
-          } else {
+          if (CTA2) {
+            // both CTAs' bytes land on the leader's barrier; only the leader arrives on it
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+            const uint32_t fb = mapa_cluster(full_bar(stage), 0);
+            if (!A_MN) {
+              tma_load_2d_cta2(sa, &tmap_a, fb, kb * BK, m_blk * BM);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i)
-              tma_load_2d(sa + i * (BK * 128), &tmap_a, full_bar(stage), m_blk * BM + i * 64, kb * BK);
-          }
-          if (!B_MN) {
-            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
-          } else {
+              for (int i = 0; i < BM / 64; ++i)
+                tma_load_2d_cta2(sa + i * (BK * 128), &tmap_a, fb, m_blk * BM + i * 64, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d_cta2(sb, &tmap_b, fb, kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(sb + i * (BK * 128), &tmap_b, full_bar(stage), n_blk * BN + i * 64, kb * BK);
+              for (int i = 0; i < C::B_ROWS / 64; ++i)
+                tma_load_2d_cta2(sb + i * (BK * 128), &tmap_b, fb, n0 + i * 64, kb * BK);
+            }
+          } else {
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m_blk * BM);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i)
+                tma_load_2d(sa + i * (BK * 128), &tmap_a, full_bar(stage), m_blk * BM + i * 64, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_2d(sb + i * (BK * 128), &tmap_b, full_bar(stage), n0 + i * 64, kb * BK);
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -337,12 +427,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
+    if (lane == 0 && cta_rank == 0) {             // CTA2: the leader issues for the pair
+      constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN, CTA2>();
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int ks = t / (p.n_tiles * p.m_tiles);
+      for (int t = t_first; t < total_tiles; t += t_stride) {
+        const int ks = t / (p.n_tiles * m_units);
         const int kb0 = ks * p.k_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.k_per_split);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -360,12 +450,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             // advance inside the swizzle atom: K-major +32 B per UMMA_K, MN-major +16 rows * 128 B
             const uint64_t aoff = (uint64_t)((A_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
             const uint64_t boff = (uint64_t)((B_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
-            tc_mma_bf16(tmem_d, adesc + aoff, bdesc + boff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CTA2) tc_mma_bf16_cta2(tmem_d, adesc + aoff, bdesc + boff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else tc_mma_bf16(tmem_d, adesc + aoff, bdesc + boff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(empty_bar(stage));            // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          if (CTA2) tc_commit_mc2(empty_bar(stage), 3); else tc_commit(empty_bar(stage));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(tfull_bar(acc));                // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if (CTA2) tc_commit_mc2(tfull_bar(acc), 3); else tc_commit(tfull_bar(acc));
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       }
     }
@@ -376,15 +469,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int half = e >> 2;                      // column half of the tile
     int acc = 0; uint32_t acc_phase = 0;
     const DropCfg dc = load_drop(p.drop);
+    // accumulator release goes to the leader's barrier (the MMA issuer waits there for both CTAs)
+    auto release_acc = [&](int a) {
+      if (CTA2) mbar_arrive_cluster(mapa_cluster(tempty_bar(a), 0));
+      else mbar_arrive(tempty_bar(a));
+    };
     if (EPI_TMA) {
       constexpr int NB = BN / 128;                // 64-column boxes per warp per tile
       uint8_t* box0 = smem_gen + C::STAGES * C::STAGE_BYTES + e * (2 * C::EPI_BOX_BYTES);
       const uint32_t box0_u32 = epi_base + e * (2 * C::EPI_BOX_BYTES);
       const uint32_t swz_row = (uint32_t)lane * 128u;
       uint32_t ld_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < total_tiles; t += t_stride) {
         const int n_blk = t % p.n_tiles;
-        const int m_blk = (t / p.n_tiles) % p.m_tiles;
+        const int m_unit = (t / p.n_tiles) % m_units;
+        const int m_blk = CTA2 ? 2 * m_unit + (int)cta_rank : m_unit;
         const int row0 = m_blk * BM + quarter * 32;
         const int colbase = n_blk * BN + half * (BN / 2);
         if (p.in_mode) {
@@ -411,7 +510,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (hb == NB - 1) {                      // accumulator drained: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) release_acc(acc);
           }
           uint8_t* out_box = box0 + ((p.aux_out || NB == 1) ? 0 : hb * C::EPI_BOX_BYTES);
           uint8_t* in_box = box0 + hb * C::EPI_BOX_BYTES;
@@ -442,9 +541,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
       if (lane == 0) bulk_wait_all();
     } else {
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < total_tiles; t += t_stride) {
         const int n_blk = t % p.n_tiles;
-        const int m_blk = (t / p.n_tiles) % p.m_tiles;
+        const int m_unit = (t / p.n_tiles) % m_units;
+        const int m_blk = CTA2 ? 2 * m_unit + (int)cta_rank : m_unit;
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const int row = m_blk * BM + quarter * 32 + lane;
@@ -458,16 +558,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) release_acc(acc);
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();   // pair: the leader's MMAs also write the peer's TMEM
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    if (CTA2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
   }
 }
 
@@ -505,18 +608,45 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t 
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, int ACT, bool EPI_TMA>
+template <int BN, bool A_MN, bool B_MN, int ACT, bool EPI_TMA, bool CTA2 = false>
 static int launch(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
-  using C = Cfg<BN, EPI_TMA>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, ACT, EPI_TMA>;
+  using C = Cfg<BN, EPI_TMA, CTA2>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, ACT, EPI_TMA, CTA2>;
   static bool attr_done = false;
   if (!attr_done) {
     TNR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
+  if (CTA2) {
+    // `grid` counts CTA pairs: launch them as clusters of 2 (the two SMs of one TPC)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    TNR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], p));
+    return 0;
+  }
   kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   TNR_LAUNCH_CHECK();
   return 0;
+}
+
+// CTA-pair kernels: bf16 outputs, BN = 256, A K-major (forward and dgrad GEMMs of the encoder)
+template <bool B_MN>
+static int dispatch_act_cta2(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
+  switch (p.act) {
+    case TNR_ACT_NONE: return launch<256, false, B_MN, TNR_ACT_NONE, true, true>(maps, p, grid, st);
+    case TNR_ACT_GELU: return launch<256, false, B_MN, TNR_ACT_GELU, true, true>(maps, p, grid, st);
+    case TNR_ACT_TANH: return launch<256, false, B_MN, TNR_ACT_TANH, true, true>(maps, p, grid, st);
+    case TNR_ACT_DGELU: return launch<256, false, B_MN, TNR_ACT_DGELU, true, true>(maps, p, grid, st);
+  }
+  set_error("tnr_gemm_bf16: unknown act %d", p.act);
+  return 1;
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -572,6 +702,14 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
   if (a_mn) TNR_REQUIRE(a->M % 8 == 0, "tnr_gemm_bf16: MN-major A needs M %% 8 == 0");
 
   const int BN = (a->N > 128) ? 256 : 128;
+  const bool atomic_out = a->split_k > 1 || a->accumulate != 0;
+  // CTA-pair (cta_group::2) path: large-M GEMMs with a bf16 TMA-stored output.  TNR_GEMM_CTA2=0 disables it.
+  static const int cta2_env = [] { const char* e = getenv("TNR_GEMM_CTA2"); return e ? atoi(e) : 1; }();
+  //   forward / dgrad: bf16 output, A K-major, M >= 4096;  wgrad: both operands MN-major, fp32 (atomic) output.
+  const bool cta2_fwd = BN == 256 && !a_mn && !atomic_out && a->c_dtype == TNR_BF16 && a->M >= 4096;
+  const bool cta2_wgrad = BN == 256 && a_mn && b_mn && a->c_dtype == TNR_F32 && a->act == TNR_ACT_NONE && a->M >= 512 &&
+                          a->residual == nullptr;
+  const bool cta2 = cta2_env != 0 && (cta2_fwd || (cta2_wgrad && cta2_env != 2));
   Params p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.m_tiles = (a->M + BM - 1) / BM;
@@ -595,7 +733,7 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
   CUtensorMap &ta = maps[0], &tb = maps[1];
   if (!a_mn) { if (make_map(&ta, a->A, a->K, a->M, a->lda, BK, BM)) return 1; }
   else       { if (make_map(&ta, a->A, a->M, a->K, a->lda, 64, BK)) return 1; }
-  if (!b_mn) { if (make_map(&tb, a->B, a->K, a->N, a->ldb, BK, BN)) return 1; }
+  if (!b_mn) { if (make_map(&tb, a->B, a->K, a->N, a->ldb, BK, cta2 ? BN / 2 : BN)) return 1; }
   else       { if (make_map(&tb, a->B, a->N, a->K, a->ldb, 64, BK)) return 1; }
   // bf16 outputs go through shared memory + TMA (32-row x 64-column boxes, 128B swizzle)
   p.epi_tma = (!p.c_f32 && !atomic) ? 1 : 0;
@@ -619,11 +757,17 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
     }
   }
 
-  const int tiles = p.m_tiles * p.n_tiles * p.splits;
   const int sms = num_sms();
   TNR_REQUIRE(sms > 0, "tnr_gemm_bf16: no CUDA device");
-  const int grid = tiles < sms ? tiles : sms;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cta2) {
+    const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles * p.splits;
+    const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+    if (a_mn) return launch<256, true, true, TNR_ACT_NONE, false, true>(maps, p, pairs, st);
+    return b_mn ? dispatch_act_cta2<true>(maps, p, pairs, st) : dispatch_act_cta2<false>(maps, p, pairs, st);
+  }
+  const int tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = tiles < sms ? tiles : sms;
   if (BN == 256) return dispatch_major<256>(a_mn, b_mn, maps, p, grid, st);
   return dispatch_major<128>(a_mn, b_mn, maps, p, grid, st);
 }

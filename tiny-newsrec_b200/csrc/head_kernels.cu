@@ -139,10 +139,22 @@ kd_loss_kernel(const float* __restrict__ s_news, const float* __restrict__ s_use
     }
     for (int k = 0; k < K; ++k)
       s_ds[k] = (s_ds[k] + coef * (expf(s_sc[k] - lse) - (k == lab ? 1.0f : 0.0f))) * invB;
-    atomicAdd(losses + 0, distill * invB);
-    atomicAdd(losses + 1, emb * invB);
-    atomicAdd(losses + 2, target * invB);
-    atomicAdd(losses + 3, (distill + coef * target + emb) * invB);     // model_bert.py:305
+    // deterministic batch means: per-impression terms go to losses[4 + 4b ..]; the block that finishes last
+    // (ticket counter behind them) adds them up in impression order -- fp32 atomics would make the loss
+    // depend on block scheduling in its last bits.
+    float* part = losses + 4 + 4 * (size_t)b;
+    part[0] = distill; part[1] = emb; part[2] = target; part[3] = distill + coef * target + emb;   // model_bert.py:305
+    __threadfence();
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(losses + 4 + 4 * (size_t)B);
+    if (atomicAdd(ticket, 1u) == (unsigned int)B - 1) {
+      __threadfence();
+      float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+      const volatile float* all = losses + 4;
+      for (int i = 0; i < B; ++i)
+        for (int c = 0; c < 4; ++c) acc4[c] += all[4 * (size_t)i + c];
+      for (int c = 0; c < 4; ++c) losses[c] = acc4[c] * invB;
+      *ticket = 0u;                                   // ready for the next launch
+    }
   }
   __syncthreads();
   for (int k = tid; k < K; k += UE_THREADS) score_out[(size_t)b * K + k] = s_sc[k];

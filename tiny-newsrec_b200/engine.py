@@ -235,9 +235,15 @@ class Encoder:
         return wqkv, bqkv, self._w(flat, lr.o.weight), self._w(flat, lr.f1.weight), self._w(flat, lr.f2.weight)
 
     def relpos(self, L):
+        """fp32 [A, 2L-1] rel-pos bias vector, entry (j - i) + L - 1 (position_ids are arange(L), so the
+        reference's [n, A, L, L] bias, modeling.py:458-463, is batch-invariant and Toeplitz)."""
         w = self.bert.rel_pos_bias.weight
-        return self.frozen.get(("relpos", L), [w],
-                               lambda: w.detach().float()[:, rel_pos_bucket_table(L).to(w.device)].contiguous())
+
+        def build():
+            tab = rel_pos_bucket_table(L)                                   # [i, j] -> bucket(j - i)
+            vec = torch.cat([tab[1:, 0].flip(0), tab[0, :]])                # d = -(L-1) .. L-1
+            return w.detach().float()[:, vec.to(w.device)].contiguous()
+        return self.frozen.get(("relpos", L), [w], build)
 
     def word_table(self):
         w = self.bert.embeddings.word_embeddings.weight

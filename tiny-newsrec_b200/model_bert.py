@@ -252,7 +252,7 @@ class TrainState:
             mk = lambda *s: torch.empty(*s, device=dev, dtype=F32)  # noqa: E731
             w = dict(news=mk(R, D), user=mk(B, D), a=mk(B, H), e=mk(B, H, Q), ta=mk(max(M, 1), B, H), score=mk(B, K),
                      ue_scratch=mk(B * H * (Q + D)),
-                     losses=torch.zeros(4, device=dev, dtype=F32), d_news=mk(R, D), d_user=mk(B, D),
+                     losses=torch.zeros(4 + 4 * B + 1, device=dev, dtype=F32), d_news=mk(R, D), d_user=mk(B, D),
                      T=mk(max(M, 1), R + B, D), TP=mk(max(M, 1), R + B, D), G=mk(max(M, 1), R + B, D))
             self.hw[key] = w
         return w
@@ -301,7 +301,6 @@ class TrainState:
             else:
                 for i in range(M):
                     ops.sgemm_nt(T[i], ws[i], bs[i], TP[i], R + B, D, D, 1, 0, 0, 0, 0)
-        w["losses"].zero_()
         ops.kd_loss(news, w["user"], label, T if M else None, TP if M else None, M, B, H, K, D, temperature, coef,
                     want_grad, w["score"], w["losses"], w["d_news"], w["d_user"], G if M else None)
         if want_grad:
@@ -416,7 +415,7 @@ class ModelBert(nn.Module):
         hist = vec[:B * H].view(B, H, -1)
         cand = vec[B * H:].view(B, K, -1)
         user = self.user_encoder(hist, history_mask)
-        w = torch.zeros(4, device=vec.device, dtype=F32)
+        w = torch.zeros(4 + 4 * B + 1, device=vec.device, dtype=F32)
         score = torch.empty(B, K, device=vec.device, dtype=F32)
         label = torch.zeros(B, device=vec.device, dtype=torch.int64)
         ops.kd_loss(vec, user, label, None, None, 0, B, H, K, vec.shape[1], 1.0, 1.0, False, score, w, None, None, None)

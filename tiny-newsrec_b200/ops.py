@@ -191,13 +191,22 @@ def colsum(x, out):
     return out
 
 
+def _chk_relbias(relpos, A, L):
+    _chk(relpos, _f32, "relpos")
+    if tuple(relpos.shape) != (A, 2 * L - 1) or not relpos.is_contiguous():
+        raise _lib.TinyRecError(f"attention: rel-pos bias must be contiguous fp32 [A, 2L-1] = [{A}, {2 * L - 1}], "
+                                f"got {tuple(relpos.shape)}")
+
+
 @_timed
 def attn_fwd(qkv, x, L, relpos, ctx, A, drop=None):
-    """qkv bf16 [n*L, 3E]; x int64 [n, 2L] (mask = columns L..2L); relpos fp32 [A,L,L]."""
+    """qkv bf16 [n*L, 3E]; x int64 [n, 2L] (mask = columns L..2L); relpos fp32 [A, 2L-1] (bias of key j for
+    query i at index (j - i) + L - 1).  L <= 32: one warp per (news, head); 32 < L <= 512: streamed-KV kernel."""
     lib = _ready(qkv)
     n = x.shape[0]
     E = qkv.shape[1] // 3
     mask_ptr = ctypes.c_void_p(x.data_ptr() + 8 * L)
+    _chk_relbias(relpos, A, L)
     _lib.check(lib.tnr_attn_relpos_fwd(_ptr(_chk(qkv, _bf16, "attn.qkv")), mask_ptr, x.stride(0),
                                        _ptr(_chk(relpos, _f32, "relpos")), _ptr(_chk(ctx, _bf16, "ctx")),
                                        n, L, A, E, _dp(drop), _stream()), "tnr_attn_relpos_fwd")
@@ -210,6 +219,7 @@ def attn_bwd(qkv, x, L, relpos, dctx, dqkv, A, drop=None):
     n = x.shape[0]
     E = qkv.shape[1] // 3
     mask_ptr = ctypes.c_void_p(x.data_ptr() + 8 * L)
+    _chk_relbias(relpos, A, L)
     _lib.check(lib.tnr_attn_relpos_bwd(_ptr(_chk(qkv, _bf16, "attn.qkv")), mask_ptr, x.stride(0),
                                        _ptr(relpos), _ptr(_chk(dctx, _bf16, "dctx")),
                                        _ptr(_chk(dqkv, _bf16, "dqkv")), n, L, A, E, _dp(drop), _stream()),
@@ -303,6 +313,8 @@ def kd_loss(s_news, s_user, label, T_ext, TP_ext, M, B, H, K, D, temperature, co
     _chk(label, torch.int64, "kd_loss.label")
     for t, nm in ((s_news, "s_news"), (s_user, "s_user"), (score_out, "score"), (losses, "losses")):
         _chk(t, _f32, "kd_loss." + nm)
+    if losses.numel() < 4 + 4 * B + 1:
+        raise _lib.TinyRecError("kd_loss: losses must hold 4 + 4B + 1 floats (zero-initialised once)")
     _lib.check(lib.tnr_kd_loss_fwdbwd(_ptr(s_news), _ptr(s_user), _ptr(label), _ptr(T_ext), _ptr(TP_ext), M, B, H, K, D,
                                       float(temperature), float(coef), int(want_grad), _ptr(score_out), _ptr(losses),
                                       _ptr(d_news), _ptr(d_user), _ptr(G_ext), _stream()), "tnr_kd_loss_fwdbwd")

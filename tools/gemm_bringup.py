@@ -55,7 +55,7 @@ def check(name, M, N, K, a_t=False, b_t=False, **kw):
     a = alog.t().contiguous() if a_t else alog
     b = blog.t().contiguous() if b_t else blog
     split = kw.pop("split_k", 1)
-    out = torch.zeros(M, N, device=dev, dtype=torch.float32 if split > 1 else BF)
+    out = torch.zeros(M, N, device=dev, dtype=torch.float32 if (split > 1 or a_t) else BF)
     try:
         ops.gemm(a, b, out, a_t=a_t, b_t=b_t, split_k=split, accumulate=split > 1, **kw)
         torch.cuda.synchronize()
@@ -119,6 +119,9 @@ if __name__ == "__main__":
     ok &= check("nt_tails", 300, 200, 200)
     ok &= check("nt_bn128", 256, 128, 128)
     ok &= check("nt_big", 4096, 2304, 768)
+    ok &= check("pair_small", 4096, 256, 64)             # CTA-pair kernels (M >= 4096, N > 128)
+    ok &= check("pair_odd", 4200, 768, 768)
+    ok &= check("pair_bmn", 4200, 768, 2304, b_t=True)
     ok &= check("bmn_small", 128, 256, 64, b_t=True)
     ok &= check("bmn", 1000, 768, 3072, b_t=True)
     ok &= check("wgrad_small", 128, 256, 64, a_t=True, b_t=True)
@@ -130,10 +133,11 @@ if __name__ == "__main__":
         bench("ffn1_gelu", T, 3072, 768, act=ops.ACT_GELU)
         bench("ffn2", T, 768, 3072)
         bench("dgrad_ffn2", T, 3072, 768, b_t=True)
+        bench("dgrad_ffn1", T, 768, 3072, b_t=True)
         bench("wgrad_ffn1", 3072, 768, T, a_t=True, b_t=True, split_k=8)
         bench("wgrad_qkv", 2304, 768, T, a_t=True, b_t=True, split_k=8)
         bench("wgrad_o", 768, 768, T, a_t=True, b_t=True, split_k=16)
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/gemm_bringup.json", "w") as f:
+    with open(os.environ.get("TNR_BRINGUP_OUT", "gpurun_out/gemm_bringup.json"), "w") as f:
         json.dump(results, f, indent=1)
     print("ALL OK" if ok else "SOME FAILED")
