@@ -46,6 +46,7 @@ kd_loss_kernel(const float* __restrict__ s_news, const float* __restrict__ s_use
   __shared__ float s_ds[KD_MAXK];                 // d loss / d student score
   __shared__ float s_mse[KD_MAXM];                // NE_i + UE_i
   __shared__ float red[8];
+  __shared__ int s_last;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int R = B * (H + K);
@@ -139,21 +140,29 @@ kd_loss_kernel(const float* __restrict__ s_news, const float* __restrict__ s_use
     }
     for (int k = 0; k < K; ++k)
       s_ds[k] = (s_ds[k] + coef * (expf(s_sc[k] - lse) - (k == lab ? 1.0f : 0.0f))) * invB;
-    // deterministic batch means: per-impression terms go to losses[4 + 4b ..]; the block that finishes last
-    // (ticket counter behind them) adds them up in impression order -- fp32 atomics would make the loss
-    // depend on block scheduling in its last bits.
+    // deterministic batch means: per-impression terms go to losses[4 + 4b ..]; the block that takes the last
+    // ticket adds them up in a fixed order (below) -- fp32 atomics would make the loss depend on block
+    // scheduling in its last bits.
     float* part = losses + 4 + 4 * (size_t)b;
     part[0] = distill; part[1] = emb; part[2] = target; part[3] = distill + coef * target + emb;   // model_bert.py:305
     __threadfence();
     unsigned int* ticket = reinterpret_cast<unsigned int*>(losses + 4 + 4 * (size_t)B);
-    if (atomicAdd(ticket, 1u) == (unsigned int)B - 1) {
-      __threadfence();
-      float acc4[4] = {0.f, 0.f, 0.f, 0.f};
-      const volatile float* all = losses + 4;
-      for (int i = 0; i < B; ++i)
-        for (int c = 0; c < 4; ++c) acc4[c] += all[4 * (size_t)i + c];
+    s_last = (atomicAdd(ticket, 1u) == (unsigned int)B - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last && warp == 0) {
+    // lane i sums impressions i, i + 32, ... in order, then a fixed butterfly over the 32 lanes
+    __threadfence();
+    float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = lane; i < B; i += 32) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(losses + 4) + i);
+      acc4[0] += v.x; acc4[1] += v.y; acc4[2] += v.z; acc4[3] += v.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc4[c] = warp_sum(acc4[c]);
+    if (lane == 0) {
       for (int c = 0; c < 4; ++c) losses[c] = acc4[c] * invB;
-      *ticket = 0u;                                   // ready for the next launch
+      *reinterpret_cast<unsigned int*>(losses + 4 + 4 * (size_t)B) = 0u;     // ready for the next launch
     }
   }
   __syncthreads();

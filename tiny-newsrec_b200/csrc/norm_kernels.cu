@@ -208,19 +208,21 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int rows, const float*
 //   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
 //   dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; dsum += sum_rows dx_drop (the bias gradient of
 //   the dense layer in front of this LayerNorm -- saves a separate column-sum pass over dx)
-// Persistent grid, one 14-warp block per SM.  The three per-column accumulators live in registers; each warp
-// streams its rows through a private double-buffered shared-memory stage filled by cp.async, so the
-// next row's loads are in flight while the current row is reduced (the first version held the row in
-// registers: 171 registers, 1 block / SM, 29 % of HBM peak).
+// Persistent grid, one 12-warp block per SM.  gamma and the three per-column accumulators (dgamma, dbeta,
+// dsum) live in registers; each warp streams its rows through a private 3-stage shared-memory ring filled by
+// cp.async, so two further rows are in flight while the current one is reduced.  History: rows held in
+// registers (171 registers, 29 % of HBM peak) -> double-buffered stage with gamma re-read from L1 and dbeta
+// accumulated in shared memory (~20 KB of LSU traffic per 6 KB row pair, 55 %) -> this version.
 __device__ __forceinline__ void ln_cp_async16(void* smem_dst, const void* src) {
   const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-constexpr int LNB_WARPS = 12;      // 384 threads x 144 registers (3 warps per SM sub-partition): one block per SM, no spills
+constexpr int LNB_WARPS = 12;      // 384 threads, <= 168 registers: one block per SM
+constexpr int LNB_STAGES = 3;
 
 template <int VPL>
-__global__ void __maxnreg__(144)
+__global__ void __launch_bounds__(LNB_WARPS * 32, 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, int rows,
                      const float* __restrict__ gamma, float eps, __nv_bfloat16* __restrict__ dx,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dx_drop,
@@ -229,33 +231,43 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   extern __shared__ __align__(16) uint8_t ln_smem[];
   const DropCfg dc = load_drop(drop);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* s_acc = reinterpret_cast<float*>(ln_smem);                       // [2][E] block totals of dgamma, dsum
-  float* s_db = s_acc + 2 * E + (size_t)warp * E;                          // per-warp dbeta accumulator [E]
-  // per warp: 2 stages x {x row, dy row} bf16
-  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(ln_smem + (2 + LNB_WARPS) * E * 4) + (size_t)warp * 4 * E;
-  for (int i = threadIdx.x; i < (2 + LNB_WARPS) * E; i += blockDim.x) s_acc[i] = 0.f;
+  float* s_acc = reinterpret_cast<float*>(ln_smem);                       // [3][E] block totals of dgamma, dbeta, dsum
+  // per warp: LNB_STAGES x {x row, dy row} bf16
+  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(ln_smem + 3 * E * 4) + (size_t)warp * LNB_STAGES * 2 * E;
+  for (int i = threadIdx.x; i < 3 * E; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
-  float acc_dg[VPL * 8], acc_ds[VPL * 8];
+  float gm[VPL * 8], acc_dg[VPL * 8], acc_db[VPL * 8], acc_ds[VPL * 8];
 #pragma unroll
-  for (int i = 0; i < VPL * 8; ++i) { acc_dg[i] = 0.f; acc_ds[i] = 0.f; }
+  for (int v = 0; v < VPL; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    gm[v * 8 + 0] = g0.x; gm[v * 8 + 1] = g0.y; gm[v * 8 + 2] = g0.z; gm[v * 8 + 3] = g0.w;
+    gm[v * 8 + 4] = g1.x; gm[v * 8 + 5] = g1.y; gm[v * 8 + 6] = g1.z; gm[v * 8 + 7] = g1.w;
+  }
+#pragma unroll
+  for (int i = 0; i < VPL * 8; ++i) { acc_dg[i] = 0.f; acc_db[i] = 0.f; acc_ds[i] = 0.f; }
   const int stride = gridDim.x * LNB_WARPS;
   auto prefetch = [&](int st, int r) {
-    __nv_bfloat16* sx = stage + st * 2 * E;
+    if (r < rows) {
+      __nv_bfloat16* sx = stage + st * 2 * E;
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int col = (v * 32 + lane) * 8;
-      ln_cp_async16(sx + col, x + (size_t)r * E + col);
-      ln_cp_async16(sx + E + col, dy + (size_t)r * E + col);
+      for (int v = 0; v < VPL; ++v) {
+        const int col = (v * 32 + lane) * 8;
+        ln_cp_async16(sx + col, x + (size_t)r * E + col);
+        ln_cp_async16(sx + E + col, dy + (size_t)r * E + col);
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");       // one group per slot, empty past the end
   };
   int r = blockIdx.x * LNB_WARPS + warp;
-  if (r < rows) prefetch(0, r);
-  asm volatile("cp.async.commit_group;" ::: "memory");
+  prefetch(0, r);
+  prefetch(1, r + stride);
   int st = 0;
-  for (; r < rows; r += stride, st ^= 1) {
-    if (r + stride < rows) prefetch(st ^ 1, r + stride);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
+  for (; r < rows; r += stride) {
+    int st2 = st + 2; if (st2 >= LNB_STAGES) st2 -= LNB_STAGES;
+    prefetch(st2, r + 2 * stride);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
     __syncwarp();
     bf16x8 rx[VPL], rd[VPL];
     {
@@ -266,7 +278,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         rd[v] = *reinterpret_cast<const bf16x8*>(sx + E + (v * 32 + lane) * 8);
       }
     }
-    __syncwarp();                      // stage consumed: the next-next prefetch may overwrite it
+    __syncwarp();                      // stage consumed: a later prefetch may overwrite it
+    if (++st == LNB_STAGES) st = 0;
     float s = 0.f;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
@@ -289,22 +302,14 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
       float t[8], d[8];
-      const int col = (v * 32 + lane) * 8;
       unpack8(rx[v], t);
       unpack8(rd[v], d);
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
-      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      float4 b0 = *reinterpret_cast<float4*>(s_db + col), b1 = *reinterpret_cast<float4*>(s_db + col + 4);
-      b0.x += d[0]; b0.y += d[1]; b0.z += d[2]; b0.w += d[3];
-      b1.x += d[4]; b1.y += d[5]; b1.z += d[6]; b1.w += d[7];
-      *reinterpret_cast<float4*>(s_db + col) = b0;
-      *reinterpret_cast<float4*>(s_db + col + 4) = b1;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float xh = (t[i] - mean) * rstd;
         acc_dg[v * 8 + i] = fmaf(d[i], xh, acc_dg[v * 8 + i]);
-        const float gg = d[i] * gm[i];
+        acc_db[v * 8 + i] += d[i];
+        const float gg = d[i] * gm[v * 8 + i];
         sg += gg;
         sgx = fmaf(gg, xh, sgx);
       }
@@ -317,11 +322,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       const int col = (v * 32 + lane) * 8;
       unpack8(rx[v], t);
       unpack8(rd[v], d);
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
-      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = rstd * (d[i] * gm[i] - sg - (t[i] - mean) * rstd * sgx);
+      for (int i = 0; i < 8; ++i) o[i] = rstd * (d[i] * gm[v * 8 + i] - sg - (t[i] - mean) * rstd * sgx);
       *reinterpret_cast<bf16x8*>(dx + (size_t)r * E + col) = pack8(o);
       if (dc.thr16 != 0) {
         const uint32_t keep = dropout_keep8(dc, ((uint64_t)r * (uint64_t)E + (uint64_t)col) >> 3);
@@ -329,10 +331,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * dc.scale : 0.f;
       }
       if (dx_drop != nullptr) *reinterpret_cast<bf16x8*>(dx_drop + (size_t)r * E + col) = pack8(o);
-      if (dsum != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc_ds[v * 8 + i] += o[i];
-      }
+      for (int i = 0; i < 8; ++i) acc_ds[v * 8 + i] += o[i];
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -342,16 +342,14 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     for (int i = 0; i < 8; ++i) {
       const int col = (v * 32 + lane) * 8 + i;
       atomicAdd(&s_acc[col], acc_dg[v * 8 + i]);
-      if (dsum != nullptr) atomicAdd(&s_acc[E + col], acc_ds[v * 8 + i]);
+      atomicAdd(&s_acc[E + col], acc_db[v * 8 + i]);
+      if (dsum != nullptr) atomicAdd(&s_acc[2 * E + col], acc_ds[v * 8 + i]);
     }
   __syncthreads();
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
     atomicAdd(dgamma + i, s_acc[i]);
-    if (dsum != nullptr) atomicAdd(dsum + i, s_acc[E + i]);
-    float b = 0.f;
-#pragma unroll
-    for (int w = 0; w < LNB_WARPS; ++w) b += s_acc[(2 + w) * E + i];
-    atomicAdd(dbeta + i, b);
+    atomicAdd(dbeta + i, s_acc[E + i]);
+    if (dsum != nullptr) atomicAdd(dsum + i, s_acc[2 * E + i]);
   }
 }
 
@@ -446,7 +444,7 @@ extern "C" __attribute__((visibility("default"))) int tnr_layernorm_bwd(const vo
   const int cap = num_sms();
   if (grid > cap) grid = cap;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int smem = (2 + LNB_WARPS) * E * 4 + LNB_WARPS * 4 * E * 2;
+  const int smem = 3 * E * 4 + LNB_WARPS * LNB_STAGES * 2 * E * 2;
   DISPATCH_VPL(E, (cudaFuncSetAttribute(layernorm_bwd_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
   DISPATCH_VPL(E, (layernorm_bwd_kernel<VPL><<<grid, LNB_WARPS * 32, smem, st>>>(
                       reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16),
