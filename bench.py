@@ -33,6 +33,15 @@ WORKLOADS = {
 }
 B, H, K, L, M, D, N_NEWS = 32, 50, 5, 30, 4, 256, 161013
 N_BATCHES = 8
+# secondary workloads (BASELINE.json configs[3], configs[4]); one "step" = one batch of rows / impressions
+TABLE_WORKLOADS = {
+    "table": dict(layers=12, L=30, rows=4096, mean_len=14.0, std_len=4.0, min_len=4,
+                  name="get_teacher_emb: 12-layer teacher news-table build, title rows (30 tokens)"),
+    "table_long": dict(layers=12, L=180, rows=1024, mean_len=140.0, std_len=40.0, min_len=10,
+                       name="get_teacher_emb: 12-layer teacher news-table build, title+abstract+body rows (180 tokens)"),
+}
+EVAL_WORKLOAD = dict(imps=4096, name="Impression scoring eval from a precomputed news table: gather + user attention "
+                                     "+ dot scoring + AUC/MRR/nDCG@5/10")
 
 
 def flops_per_step(layers, n_train, tokens):
@@ -371,17 +380,293 @@ def run_tinyrec(a):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- shared timing helpers
+def _dist_setup(a):
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus > 1 and world != a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} needs torchrun with {a.gpus} ranks (WORLD_SIZE={world})")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    return rank, world, local, device
+
+
+def _timed_steps(step, a, rank, world, local, device):
+    """W warm-up steps, then K steps bracketed by barrier + synchronize, CUDA events, max over ranks.
+    Returns (ms total, launches, gemm_events, op_events, clocks)."""
+    import torch.distributed as dist
+    import tinyrec.ops as ops
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for i in range(max(a.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.stats.gemm_events = []
+    launches0 = ops.stats.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(a.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.stats.launches - launches0
+    gemm_events, ops.stats.gemm_events = ops.stats.gemm_events, None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), launches, gemm_events, clocks, barrier
+
+
+def _wall_steps(step, a, world, device, barrier):
+    import torch.distributed as dist
+    for i in range(3):
+        step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        step(i)
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ----------------------------------------------------------------------------- table build (configs[3])
+def table_flops_per_news(layers, Lw):
+    """per token per layer 14 155 776 (GEMMs) + 4 L E (attention); heads 307 200 / token
+    + 393 216 / news."""
+    return layers * (14155776 + 4 * Lw * 768) * Lw + 307200 * Lw + 393216
+
+
+def run_table(a):
+    import torch.distributed as dist
+    import tinyrec.model_bert_2 as mb2
+    import tinyrec.parallel as par
+    import tinyrec.synth as synth
+    wl = TABLE_WORKLOADS[a.workload]
+    rank, world, local, device = _dist_setup(a)
+    Lw, rows, layers = wl["L"], wl["rows"], wl["layers"]
+    margs = synth.demo_args(num_hidden_layers=layers)
+    model = mb2.ModelBert(margs)
+    model.load_state_dict(synth.model_bert_state("", layers, 0), strict=True)
+    model.to(device).eval()
+    enc = model.news_encoder
+    news = synth.news_table(N_NEWS, L=Lw, seed=1234, mean_len=wl["mean_len"], std_len=wl["std_len"], min_len=wl["min_len"])
+    lo, hi = par.shard_rows(news.shape[0], rank, world)                 # contiguous row ranges per rank (run.py:438-447)
+    nb = min(N_BATCHES, (hi - lo) // rows)
+    shard = torch.from_numpy(news[lo:lo + nb * rows])
+    dev_tab = shard.to(device)                                          # int32 rows resident in HBM
+    host_tab = shard.pin_memory()
+    out = torch.empty(rows, D, device=device, dtype=torch.float32)
+    host_out = torch.empty(rows, D, dtype=torch.float32).pin_memory()
+
+    @torch.no_grad()
+    def step(i):
+        b = i % nb
+        x = dev_tab[b * rows:(b + 1) * rows].to(torch.int64)            # torch.LongTensor(arr), run.py:276-277
+        out.copy_(enc(x))
+
+    @torch.no_grad()
+    def e2e_step(i):
+        b = i % nb
+        x = host_tab[b * rows:(b + 1) * rows].to(device, non_blocking=True).to(torch.int64)
+        host_out.copy_(enc(x), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms, launches, gemm_events, clocks, barrier = _timed_steps(step, a, rank, world, local, device)
+    value = rows * world * a.steps / (ms / 1e3)
+    e2e_val = rows * world * a.steps / _wall_steps(e2e_step, a, world, device, barrier)
+    if rank == 0:
+        peak_tf, peak_bw, how = peaks()
+        gflop = sum(f for f, _, _ in gemm_events)
+        gms = sum(s_.elapsed_time(e_) for _, s_, e_ in gemm_events)
+        ach = gflop / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+        algo = table_flops_per_news(layers, Lw) * rows
+        line = {"metric": "news_embeddings_per_sec", "value": value, "unit": "news/s", "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": wl["name"], "teacher_layers": layers, "tokens_per_news": Lw, "rows_per_step": rows,
+                           "table_rows": N_NEWS + 1, "news_dim": D, "vocab": 30522, "parallelism": f"rows sharded x{world}",
+                           "l2": f"{nb} rotating row batches; per-step activations >> 126 MB L2",
+                           "note": "eval-mode forward (no dropout), random-init weights"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": "news/s", "h2d_bytes_per_step": rows * 2 * Lw * 4,
+                        "d2h_bytes_per_step": rows * D * 4},
+                "gpu_launches": launches,
+                "roofline": {"bound": "tensor", "kernel": "tnr::gemm::gemm_kernel (tcgen05, all GEMM launches of the step)",
+                             "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                             "peak_source": f"{how} bf16_tflops_sustained", "traffic": None,
+                             "gemm_ms_per_step": gms / a.steps, "gemm_share_of_step": gms / ms if ms > 0 else None,
+                             "algorithmic_tflop_per_step": algo / 1e12,
+                             "step_frac_of_tensor_roofline": (algo / 1e12) / (ms / a.steps * 1e-3) / peak_tf}}
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = table_cpu_baseline(layers, Lw, news)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def table_cpu_baseline(layers, Lw, news, budget_s=20.0):
+    import tinyrec.synth as synth
+    from oracle import model as om
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.model_bert_state("", layers, 0)
+    n = 16 if Lw <= 32 else 4
+    x = torch.from_numpy(news[1:1 + n].astype(np.int64))
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        om.news_encoder(sd, "news_encoder.", x, layers)
+        t1 = time.perf_counter() - t0
+        reps = max(1, min(4, int(budget_s / max(t1, 1e-3)) - 1))
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            om.news_encoder(sd, "news_encoder.", x, layers)
+            ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts))
+    return {"value": n / t, "unit": "news/s", "cores": cores, "kind": "port",
+            "sample": f"{1 + reps} forward passes of {n} news rows ({Lw} tokens, {layers} layers), fp32 torch CPU oracle"}
+
+
+# ----------------------------------------------------------------------------- eval scoring (configs[4])
+def run_eval(a):
+    import torch.distributed as dist
+    import tinyrec.dataloader as dl
+    import tinyrec.model_bert as mb
+    import tinyrec.ops as ops
+    import tinyrec.synth as synth
+    rank, world, local, device = _dist_setup(a)
+    n_imp = EVAL_WORKLOAD["imps"]
+    margs = synth.demo_args()
+    ue = mb.UserEncoder(margs)
+    ue.load_state_dict(synth.user_encoder_state("", D, margs.user_query_vector_dim, 0), strict=True)
+    ue.to(device).eval()
+    g = torch.Generator(device=device).manual_seed(4321)
+    table = torch.randn(N_NEWS + 1, D, generator=g, device=device) * 0.1           # precomputed news vectors (165 MB)
+    hist, hmask, ptr, cand, lab = synth.eval_impressions(n_imp * N_BATCHES, N_NEWS, H, seed=1234 + rank)
+    batches, host_batches = [], []
+    for b in range(N_BATCHES):
+        s0, s1 = b * n_imp, (b + 1) * n_imp
+        p0, p1 = int(ptr[s0]), int(ptr[s1])
+        hb = (torch.from_numpy(hist[s0:s1]), torch.from_numpy(hmask[s0:s1]), torch.from_numpy(ptr[s0:s1 + 1] - p0),
+              torch.from_numpy(cand[p0:p1]), torch.from_numpy(lab[p0:p1]))
+        host_batches.append(tuple(t.pin_memory() for t in hb) + (int(np.diff(ptr[s0:s1 + 1]).max()),))
+        batches.append(tuple(t.to(device) for t in hb) + (int(np.diff(ptr[s0:s1 + 1]).max()),))
+    log_vecs = torch.empty(n_imp, H, D, device=device, dtype=torch.float32)
+    per = torch.zeros(n_imp, 5, device=device, dtype=torch.float64)
+    sums = torch.zeros(5, device=device, dtype=torch.float64)
+
+    @torch.no_grad()
+    def score(bt):
+        hi_t, hm_t, ptr_t, cand_t, lab_t, max_c = bt
+        dl.gather_history_vecs(table, hi_t, out=log_vecs)
+        user = ue(log_vecs, hm_t)
+        ops.eval_metrics(table, user, ptr_t, cand_t, lab_t, max_c, per, sums)
+
+    def step(i):
+        score(batches[i % N_BATCHES])
+
+    def e2e_step(i):
+        hb = host_batches[i % N_BATCHES]
+        score(tuple(t.to(device, non_blocking=True) for t in hb[:5]) + (hb[5],))
+        return sums.cpu()                                                       # the 5 running sums read back
+
+    ms, launches, _, clocks, barrier = _timed_steps(step, a, rank, world, local, device)
+    value = n_imp * world * a.steps / (ms / 1e3)
+    e2e_val = n_imp * world * a.steps / _wall_steps(e2e_step, a, world, device, barrier)
+    # per-kernel device times for the roofline of the dominant kernel
+    ops.stats.op_events = []
+    for i in range(N_BATCHES):
+        step(i)
+    torch.cuda.synchronize()
+    ev, ops.stats.op_events = ops.stats.op_events, None
+    per_op = {}
+    for name, _, s_, e_ in ev:
+        per_op[name] = per_op.get(name, 0.0) + s_.elapsed_time(e_) / N_BATCHES
+    nnz = float(np.mean([bt[3].numel() for bt in batches]))
+    algo_bytes = {"gather_rows_f32": n_imp * H * D * 4 * 2, "user_encoder_fwd": n_imp * H * (D + 1) * 4,
+                  "eval_metrics": nnz * (D * 4 + 5) + n_imp * D * 4}
+    if rank == 0:
+        _, peak_bw, how = peaks()
+        top = max(per_op, key=per_op.get)
+        ach = algo_bytes.get(top, 0.0) / (per_op[top] * 1e-3) / 1e9
+        h2d = sum(t.numel() * t.element_size() for t in host_batches[0][:5])
+        line = {"metric": "eval_impressions_per_sec", "value": value, "unit": "impressions/s", "n_gpus": world,
+                "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (scores), f64 (metrics)", "data": "synthetic",
+                "config": {"workload": EVAL_WORKLOAD["name"], "impressions_per_step": n_imp, "history": H,
+                           "mean_candidates": nnz / n_imp, "table_rows": N_NEWS + 1, "news_dim": D,
+                           "parallelism": f"impressions sharded x{world}",
+                           "l2": f"{N_BATCHES} rotating batches; 165 MB table + 210 MB gathered history per step > 126 MB L2"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": "impressions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 40},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": "tnr_" + top, "achieved": ach, "peak": peak_bw, "unit": "GB/s",
+                             "frac": ach / peak_bw, "peak_source": f"{how} hbm_gbs", "traffic": None,
+                             "kernel_ms_per_step": per_op, "algorithmic_bytes_per_step": algo_bytes}}
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = eval_cpu_baseline(hist, hmask, ptr, cand, lab)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def eval_cpu_baseline(hist, hmask, ptr, cand, lab, n=1500):
+    """The reference's per-impression Python loop (run.py:335-361) restated with the oracle: user vector,
+    dot scores, AUC / MRR / nDCG@5/10."""
+    import tinyrec.synth as synth
+    from oracle import metrics as omet, model as om
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(0)
+    table = (rng.standard_normal((N_NEWS + 1, D)) * 0.1).astype(np.float32)
+    sd = synth.user_encoder_state("user_encoder.", D, 200, 0)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for s0 in range(0, n, 128):                                            # batches of 128 like the eval loader
+            s1 = min(n, s0 + 128)
+            vecs = torch.from_numpy(table[hist[s0:s1]])
+            user = om.user_encoder(sd, "user_encoder.", vecs, torch.from_numpy(hmask[s0:s1]), False).numpy()
+            for i in range(s0, s1):
+                c = table[cand[ptr[i]:ptr[i + 1]]]
+                omet.impression_metrics(lab[ptr[i]:ptr[i + 1]], c @ user[i - s0])
+    t = time.perf_counter() - t0
+    return {"value": n / t, "unit": "impressions/s", "cores": cores, "kind": "port",
+            "sample": f"{n} impressions, per-impression Python loop as the reference's test()"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="tinyrec", choices=["tinyrec", "reference"])
-    ap.add_argument("--workload", default="kd4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="kd4", choices=sorted(WORKLOADS) + sorted(TABLE_WORKLOADS) + ["eval"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
+        if a.workload not in WORKLOADS:
+            raise SystemExit("--impl reference is defined for the train workloads (kd4 / kd2)")
         run_reference(a)
+    elif a.workload in TABLE_WORKLOADS:
+        run_table(a)
+    elif a.workload == "eval":
+        run_eval(a)
     else:
         run_tinyrec(a)
 

@@ -30,7 +30,7 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;     // 4 per SM sub-partition: 4 TMEM lane quarters x 4 column slices of the tile
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 
 struct Params {
@@ -200,8 +200,8 @@ struct Cfg {
                                      : ((BN == 256) ? (EPI_TMA ? 3 : 4) : (EPI_TMA ? 4 : 6));
   static constexpr int TMEM_COLS = 2 * BN;             // 2 accumulator stages (power of 2 >= 32)
   static constexpr int EPI_BOX_BYTES = 32 * 128;       // 32 rows x 64 bf16, SWIZZLE_128B
-  static constexpr int EPI_BYTES = EPI_TMA ? NUM_EPI_WARPS * 2 * EPI_BOX_BYTES : 0;
-  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NUM_EPI_WARPS;
+  static constexpr int EPI_BYTES = EPI_TMA ? NUM_EPI_WARPS * EPI_BOX_BYTES : 0;      // one staging box per epilogue warp
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + NUM_EPI_WARPS;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 8 * NUM_BARS + 16;
 };
 
@@ -266,9 +266,26 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const DropCfg& d
 
 // bf16 output path: 8 consecutive columns of one row, staged in 128B-swizzled shared memory
 // (box row = lane, 16-byte chunk index c) for the TMA store; `in` holds the residual / dGELU box.
+// z = acc + bias as bf16 into the staging box (GELU pre-activation kept for the backward)
+__device__ __forceinline__ void epilogue_preact8(const Params& p, const uint32_t* acc, int col, uint8_t* box, uint32_t swz) {
+  f32x2 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = pk2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+  if (p.bias != nullptr && col < p.N) {
+    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+    v[0] = add2(v[0], pk2(b0.x, b0.y)); v[1] = add2(v[1], pk2(b0.z, b0.w));
+    v[2] = add2(v[2], pk2(b1.x, b1.y)); v[3] = add2(v[3], pk2(b1.z, b1.w));
+  }
+  bf16x8 o;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float lo, hi; upk2(v[i], lo, hi); o.u[i] = pack_bf16(lo, hi); }
+  *reinterpret_cast<bf16x8*>(box + swz) = o;
+}
+
 template <int ACT>
 __device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg& dc, const uint32_t* acc, int row, int col,
-                                                 uint8_t* out_box, uint8_t* in_box, uint8_t* aux_box, uint32_t swz) {
+                                                 uint8_t* out_box, uint8_t* in_box, uint32_t swz) {
   // four packed fp32 pairs (FFMA2 path, common.cuh)
   f32x2 v[4];
 #pragma unroll
@@ -279,14 +296,7 @@ __device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg&
     v[0] = add2(v[0], pk2(b0.x, b0.y)); v[1] = add2(v[1], pk2(b0.z, b0.w));
     v[2] = add2(v[2], pk2(b1.x, b1.y)); v[3] = add2(v[3], pk2(b1.z, b1.w));
   }
-  auto pack_out = [&](uint8_t* box) {
-    bf16x8 o;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float lo, hi; upk2(v[i], lo, hi); o.u[i] = pack_bf16(lo, hi); }
-    *reinterpret_cast<bf16x8*>(box + swz) = o;
-  };
   if (ACT == TNR_ACT_GELU) {
-    if (p.aux_out) pack_out(aux_box);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = gelu_erf2(v[i]);
   } else if (ACT == TNR_ACT_TANH) {
@@ -308,7 +318,10 @@ __device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg&
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = add2(v[i], pk2(bf16_lo(rr.u[i]), bf16_hi(rr.u[i])));
   }
-  pack_out(out_box);
+  bf16x8 o;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float lo, hi; upk2(v[i], lo, hi); o.u[i] = pack_bf16(lo, hi); }
+  *reinterpret_cast<bf16x8*>(out_box + swz) = o;
 }
 
 // ---------------------------------------------------------------- kernel
@@ -328,7 +341,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
-  auto ld_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::STAGES + 4 + 2 * w + b); };
+  auto ld_bar = [&](int w) { return bar_base + 8u * (2 * C::STAGES + 4 + w); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES + 8 * C::NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
@@ -345,7 +358,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), (CTA2 ? 2 : 1) * NUM_EPI_WARPS); }
-    for (int w = 0; w < NUM_EPI_WARPS; ++w) { mbar_init(ld_bar(w, 0), 1); mbar_init(ld_bar(w, 1), 1); }
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(ld_bar(w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -464,9 +477,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
+    // 16 warps: TMEM lane quarter (warp & 3) x 64-column slice of the tile.  Each warp drains its 32 x 64
+    // accumulator block into registers as soon as the tile is complete and hands the TMEM stage back right
+    // away; the math, the shared-memory staging and the TMA store then overlap the next tile's MMAs, with
+    // four warps per scheduler to hide the tcgen05.ld / MUFU / TMA latencies (8 warps were latency-bound:
+    // issue slots 40 % busy, K = 768 GEMMs with GELU / dropout epilogues at 700-1050 TFLOP/s).
     const int e = warp - 4;
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = e >> 2;                      // column half of the tile
+    const int slice = e >> 2;                     // 64-column slice of the tile
     int acc = 0; uint32_t acc_phase = 0;
     const DropCfg dc = load_drop(p.drop);
     // accumulator release goes to the leader's barrier (the MMA issuer waits there for both CTAs)
@@ -474,10 +492,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (CTA2) mbar_arrive_cluster(mapa_cluster(tempty_bar(a), 0));
       else mbar_arrive(tempty_bar(a));
     };
+    const bool slice_live = slice * 64 < BN;       // BN = 128: half of the warps only keep the barrier counts
     if (EPI_TMA) {
-      constexpr int NB = BN / 128;                // 64-column boxes per warp per tile
-      uint8_t* box0 = smem_gen + C::STAGES * C::STAGE_BYTES + e * (2 * C::EPI_BOX_BYTES);
-      const uint32_t box0_u32 = epi_base + e * (2 * C::EPI_BOX_BYTES);
+      uint8_t* box = smem_gen + C::STAGES * C::STAGE_BYTES + e * C::EPI_BOX_BYTES;
+      const uint32_t box_u32 = epi_base + e * C::EPI_BOX_BYTES;
       const uint32_t swz_row = (uint32_t)lane * 128u;
       uint32_t ld_phase = 0;
       for (int t = t_first; t < total_tiles; t += t_stride) {
@@ -485,59 +503,66 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int m_unit = (t / p.n_tiles) % m_units;
         const int m_blk = CTA2 ? 2 * m_unit + (int)cta_rank : m_unit;
         const int row0 = m_blk * BM + quarter * 32;
-        const int colbase = n_blk * BN + half * (BN / 2);
-        if (p.in_mode) {
-          // both boxes are about to be overwritten by the prefetch: their previous stores must have been read
+        const int col0 = n_blk * BN + slice * 64;
+        const bool live = slice_live && row0 < p.M && col0 < p.N;      // warp-uniform
+        if (p.in_mode && live) {
+          // the box is about to be overwritten by the prefetch: its previous store must have been read
           if (lane == 0) {
             bulk_wait_read<0>();
-#pragma unroll
-            for (int hb = 0; hb < NB; ++hb) {
-              mbar_expect_tx(ld_bar(e, hb), C::EPI_BOX_BYTES);
-              tma_load_2d(box0_u32 + hb * C::EPI_BOX_BYTES, &tmap_in, ld_bar(e, hb), colbase + hb * 64, row0);
-            }
+            mbar_expect_tx(ld_bar(e), C::EPI_BOX_BYTES);
+            tma_load_2d(box_u32, &tmap_in, ld_bar(e), col0, row0);
           }
           __syncwarp();
         }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-#pragma unroll 1
-        for (int hb = 0; hb < NB; ++hb) {
-          uint32_t r[64];
-          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2) + hb * 64);
+        uint32_t r[64];
+        if (slice_live) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + slice * 64);
           tmem_ld32(taddr, r);
           tmem_ld32(taddr + 32, r + 32);
           tmem_ld_wait();
-          if (hb == NB - 1) {                      // accumulator drained: hand the TMEM stage back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) release_acc(acc);
-          }
-          uint8_t* out_box = box0 + ((p.aux_out || NB == 1) ? 0 : hb * C::EPI_BOX_BYTES);
-          uint8_t* in_box = box0 + hb * C::EPI_BOX_BYTES;
-          uint8_t* aux_box = box0 + C::EPI_BOX_BYTES;
-          if (p.in_mode) {
-            mbar_wait(ld_bar(e, hb), ld_phase);
-          } else {
-            if (lane == 0) { if (p.aux_out || NB == 1) bulk_wait_read<0>(); else bulk_wait_read<NB - 1>(); }
-            __syncwarp();
-          }
-          const int row = row0 + lane;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release_acc(acc);             // accumulator block is in registers
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        if (!live) continue;
+        if (p.in_mode) {
+          mbar_wait(ld_bar(e), ld_phase);
+          ld_phase ^= 1u;
+        } else {
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+        }
+        const int row = row0 + lane;
+        if (ACT == TNR_ACT_GELU && p.aux_out) {
+          // pre-activation z = acc + bias goes out first through the same box
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint32_t swz = swz_row + (uint32_t)((c ^ (lane & 7)) << 4);
-            epilogue_staged8<ACT>(p, dc, r + c * 8, row, colbase + hb * 64 + c * 8, out_box, in_box, aux_box, swz);
+            epilogue_preact8(p, r + c * 8, col0 + c * 8, box, swz);
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < p.M && colbase + hb * 64 < p.N) {
-            const uint32_t out_u32 = box0_u32 + (uint32_t)(out_box - box0);
-            tma_store_2d(&tmap_c, out_u32, colbase + hb * 64, row0);
-            if (p.aux_out) tma_store_2d(&tmap_aux, box0_u32 + C::EPI_BOX_BYTES, colbase + hb * 64, row0);
+          if (lane == 0) {
+            tma_store_2d(&tmap_aux, box_u32, col0, row0);
             bulk_commit();
+            bulk_wait_read<0>();
           }
+          __syncwarp();
         }
-        if (p.in_mode) ld_phase ^= 1u;
-        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t swz = swz_row + (uint32_t)((c ^ (lane & 7)) << 4);
+          epilogue_staged8<ACT>(p, dc, r + c * 8, row, col0 + c * 8, box, box, swz);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmap_c, box_u32, col0, row0);
+          bulk_commit();
+        }
       }
       if (lane == 0) bulk_wait_all();
     } else {
@@ -548,18 +573,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const int row = m_blk * BM + quarter * 32 + lane;
-#pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
-          const int coff = half * (BN / 2) + c * 32;
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + coff), r);
+        uint32_t r[64];
+        if (slice_live) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + slice * 64);
+          tmem_ld32(taddr, r);
+          tmem_ld32(taddr + 32, r + 32);
           tmem_ld_wait();
-          epilogue_chunk<ACT>(p, dc, r, row, n_blk * BN + coff);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) release_acc(acc);
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+        if (!slice_live) continue;
+        epilogue_chunk<ACT>(p, dc, r, row, n_blk * BN + slice * 64);
+        epilogue_chunk<ACT>(p, dc, r + 32, row, n_blk * BN + slice * 64 + 32);
       }
     }
   }
