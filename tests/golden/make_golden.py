@@ -252,6 +252,29 @@ def gen_batching():
         th0=thb[0].numpy(), th1=thb[1].numpy(), tc0=tcb[0].numpy(), tc1=tcb[1].numpy())
 
 
+def gen_unilm_convert():
+    """A UniLM-format state dict (fused qkv_linear, q_bias / v_bias, encoder.rel_pos_bias) through the
+    reference's converter and position-table resize logic (tnlrv3/convert_state_dict.py:39-71,
+    tnlrv3/modeling.py:88-118 restated inline there; here the converter is called directly)."""
+    import tnlrv3.convert_state_dict as ref_conv
+    g = torch.Generator().manual_seed(11)
+    E, A, layers = 16, 2, 2
+    sd = {"bert.embeddings.word_embeddings.weight": torch.randn(50, E, generator=g),
+          "bert.embeddings.position_embeddings.weight": torch.randn(12, E, generator=g),
+          "bert.encoder.rel_pos_bias.weight": torch.randn(A, 32, generator=g)}
+    for l in range(layers):
+        pfx = f"bert.encoder.layer.{l}.attention.self."
+        sd[pfx + "qkv_linear.weight"] = torch.randn(3 * E, E, generator=g)
+        sd[pfx + "q_bias"] = torch.randn(1, 1, E, generator=g)
+        sd[pfx + "v_bias"] = torch.randn(1, 1, E, generator=g)
+        sd[f"bert.encoder.layer.{l}.output.dense.weight"] = torch.randn(E, 4 * E, generator=g)
+    out = ref_conv.state_dict_convert["tnlrv3"]({k: v.clone() for k, v in sd.items()})
+    fix = {"in/" + k: v.numpy() for k, v in sd.items()}
+    fix.update({"out/" + k: v.numpy() for k, v in out.items()})
+    fix["out_keys"] = np.array(list(out.keys()))
+    np.savez_compressed(os.path.join(HERE, "unilm_convert.npz"), **fix)
+
+
 if __name__ == "__main__":
     gen_relpos()
     gen_encoder()
@@ -263,3 +286,4 @@ if __name__ == "__main__":
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
+    gen_unilm_convert()

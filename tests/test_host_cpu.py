@@ -195,3 +195,70 @@ def test_two_rank_gloo_collectives(tmp_path):
                        capture_output=True, text=True, timeout=240, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok0" in r.stdout and "ok1" in r.stdout
+
+
+# ------------------------------------------------------------------ on-disk formats
+def test_unilm_state_dict_conversion_matches_reference(golden):
+    """tinyrec.checkpoint.convert_unilm_state_dict vs the reference's converter run on the same
+    UniLM-format dict (fixture made by tests/golden/make_golden.py:gen_unilm_convert)."""
+    import tinyrec.checkpoint as ck
+    g = golden("unilm_convert")
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("in/")}
+    want = {k[4:]: g[k] for k in g.files if k.startswith("out/")}
+    got = ck.convert_unilm_state_dict(sd)
+    assert list(got.keys()) == [str(k) for k in g["out_keys"]]            # same keys, same order
+    for k, v in want.items():
+        assert got[k].shape == v.shape and np.array_equal(got[k].numpy(), v), k
+    assert float(got["bert.encoder.layer.0.attention.self.key.bias"].abs().sum()) == 0.0
+
+
+def test_position_resize_and_nonstrict_bin_load(tmp_path):
+    """tnlrv3/modeling.py:88-118 semantics + loading a deeper .bin into a shallower encoder."""
+    import tinyrec.checkpoint as ck
+    old = torch.arange(12 * 4, dtype=torch.float32).reshape(12, 4)
+    k = "bert.embeddings.position_embeddings.weight"
+    grown = ck.resize_position_embeddings({k: old.clone()}, 30, reuse_position_embedding=True)[k]
+    assert grown.shape == (30, 4) and torch.equal(grown[:12], old) and torch.equal(grown[12:24], old) \
+        and torch.equal(grown[24:], old[:6])
+    once = ck.resize_position_embeddings({k: old.clone()}, 30)[k]
+    assert torch.equal(once[:12], old) and not torch.equal(once[12:24], old) and float(once[12:].abs().max()) < 0.2
+    cut = ck.resize_position_embeddings({k: old.clone()}, 5)[k]
+    assert torch.equal(cut, old[:5])
+    assert ck.strip_prefix({"unilm.a": 1, "b": 2}, "unilm.") == {"a": 1, "b": 2}
+
+    class Tiny(torch.nn.Module):                        # stands in for TuringNLRv3ForSequenceClassification
+        def __init__(self):
+            super().__init__()
+            self.bert = torch.nn.Module()
+            self.bert.embeddings = torch.nn.Module()
+            self.bert.embeddings.position_embeddings = torch.nn.Embedding(20, 4)
+            self.bert.rel_pos_bias = torch.nn.Linear(32, 2, bias=False)
+            self.classifier = torch.nn.Linear(4, 2)
+    m = Tiny()
+    unilm = {k: old.clone(), "bert.encoder.rel_pos_bias.weight": torch.ones(2, 32),
+             "bert.encoder.layer.11.output.dense.weight": torch.zeros(4, 16)}
+    path = tmp_path / "unilm.bin"
+    torch.save(unilm, path)
+    missing, unexpected = ck.load_unilm_bin(m, str(path))
+    assert torch.equal(m.bert.rel_pos_bias.weight.data, torch.ones(2, 32))
+    assert torch.equal(m.bert.embeddings.position_embeddings.weight.data[:12], old)
+    assert "classifier.weight" in missing and "bert.encoder.layer.11.output.dense.weight" in unexpected
+
+
+def test_checkpoint_and_teacher_table_roundtrip(tmp_path):
+    import tinyrec.checkpoint as ck
+    m = torch.nn.Linear(3, 2)
+    p = tmp_path / "epoch-1.pt"
+    ck.save_checkpoint(str(p), m, category_dict={"a": 1}, word_dict=None, subcategory_dict={"b": 2})
+    raw = torch.load(str(p), map_location="cpu")
+    assert sorted(raw) == ["category_dict", "model_state_dict", "subcategory_dict", "word_dict"]     # run.py:205-214
+    m2 = torch.nn.Linear(3, 2)
+    ck.load_checkpoint(str(p), m2)
+    assert torch.equal(m2.weight, m.weight) and raw["category_dict"] == {"a": 1}
+    tab = np.random.default_rng(0).standard_normal((7, 4)).astype(np.float32)
+    tp = tmp_path / "teacher_emb-0.pkl"
+    ck.save_teacher_table(str(tp), torch.from_numpy(tab))
+    import pickle
+    with open(tp, "rb") as f:
+        assert np.array_equal(pickle.load(f), tab)                                                   # run.py:458-459
+    assert np.array_equal(ck.load_teacher_table(str(tp)), tab)

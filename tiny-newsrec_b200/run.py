@@ -21,6 +21,7 @@ import random
 import numpy as np
 import torch
 
+from . import checkpoint as ckpt
 from . import dataloader as dl
 from . import ops
 from . import parallel as par
@@ -145,9 +146,7 @@ def train(args, news_combined, teacher_embs, batches, model=None, category_dict=
         if rank == 0 and getattr(args, "model_dir", None):
             os.makedirs(args.model_dir, exist_ok=True)
             ckpt_path = os.path.join(args.model_dir, f"epoch-{ep + 1}.pt")
-            torch.save({"model_state_dict": {k: v.detach().cpu().clone() for k, v in model.state_dict().items()},
-                        "category_dict": category_dict, "word_dict": word_dict,
-                        "subcategory_dict": subcategory_dict}, ckpt_path)
+            ckpt.save_checkpoint(ckpt_path, model, category_dict, word_dict, subcategory_dict)       # run.py:205-214
             logging.info(f"Model saved to {ckpt_path}")
     return model
 
@@ -232,8 +231,7 @@ def get_teacher_emb(args, teacher_state_dicts, news_combined, out_paths=None):
         arr = table.cpu().numpy()
         logging.info("news scoring num: {}".format(arr.shape[0]))
         if out_paths is not None and rank == 0:
-            with open(out_paths[i], "wb") as f:
-                pickle.dump(arr, f)
+            ckpt.save_teacher_table(out_paths[i], arr)                                          # run.py:458-459
             logging.info(f"teacher embedding saved at {out_paths[i]}")
         tables.append(arr)
         del model
