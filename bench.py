@@ -52,6 +52,16 @@ def flops_per_step(layers, n_train, tokens):
     return tokens * (fwd + bwd) + tokens * 307200 * 3 + (tokens // L) * 393216 * 3
 
 
+def ncu_traffic():
+    """DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the 37 GEMM launches
+    of one kd4 step) from the committed `ncu --set full` capture; None when the summary is absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_ncu_full_v7.json")) as f:
+            return float(json.load(f)["traffic_bytes_per_launch"])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -367,7 +377,11 @@ def run_tinyrec(a):
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "kernel": "tnr::gemm::gemm_kernel (tcgen05, all GEMM launches of the step)",
                              "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                             "peak_source": f"{how} bf16_tflops_sustained", "traffic": None,
+                             "peak_source": f"{how} bf16_tflops_sustained",
+                             "traffic": ncu_traffic() if a.workload == "kd4" else None,
+                             "traffic_note": "DRAM bytes per GEMM launch, ncu --set full over one step "
+                                             "(profiles/r01_gemm_ncu_full_v7.json); algorithmic operand+output bytes "
+                                             "average 345 MB per launch (operands are read from HBM once: no re-reads)",
                              "gemm_launches_per_step": len(gemm_events) / a.steps,
                              "gemm_ms_per_step": gms / a.steps,
                              "gemm_share_of_step": gms / ms if ms > 0 else None,
