@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TNR_ABI_VERSION 3
+#define TNR_ABI_VERSION 4
 
 const char* tnr_last_error(void);
 int tnr_abi_version(void);
@@ -79,6 +79,8 @@ typedef struct {
   int split_k;
   int accumulate;
   const tnr_dropout* drop;   /* v = dropout(acc + bias) before the residual add; NULL = off (plain epilogue only) */
+  float* colsum;             /* if != NULL (bf16 output only): colsum[n] += sum_m C[m,n] of the rounded bf16 output --
+                                the bias gradient of the layer in front (fp32 atomics), fused into the dgrad epilogue */
 } tnr_gemm_args;
 int tnr_gemm_bf16(const tnr_gemm_args* args, void* stream);
 
@@ -120,9 +122,10 @@ int tnr_colsum_bf16(const void* x_bf16, int rows, int cols, int ld, float* out, 
 int tnr_attn_relpos_fwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias,
                         void* ctx_bf16, int n_news, int L, int A, int E, const tnr_dropout* drop,
                         void* stream);
-/* dqkv bf16 [n*L, 3E] from dctx (probabilities recomputed, dropout mask regenerated).  L <= 32. */
+/* dqkv bf16 [n*L, 3E] from dctx (probabilities recomputed, dropout mask regenerated).  L <= 32.
+ * If dbias_qkv != NULL: dbias_qkv[3E] += column sums of dqkv (the fused [bq|bk|bv] gradient, fp32 atomics). */
 int tnr_attn_relpos_bwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias,
-                        const void* dctx_bf16, void* dqkv_bf16, int n_news, int L, int A, int E,
+                        const void* dctx_bf16, void* dqkv_bf16, float* dbias_qkv, int n_news, int L, int A, int E,
                         const tnr_dropout* drop, void* stream);
 
 /* ------------------------------------------------------- additive attention pooling (words) */

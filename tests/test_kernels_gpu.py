@@ -107,7 +107,9 @@ def test_gemm_dgelu_epilogue():
     dy, w = _randn(M, K, seed=11), _randn(K, N, scale=0.03, seed=12)      # dgrad through W [out=K, in=N]
     z = _randn(M, N, seed=13)
     out = torch.empty(M, N, device="cuda", dtype=BF)
-    ops.gemm(dy, w, out, b_t=True, act=ops.ACT_DGELU, aux=z)
+    cs = torch.zeros(N, device="cuda")
+    ops.gemm(dy, w, out, b_t=True, act=ops.ACT_DGELU, aux=z, colsum=cs)       # M = 384: single-CTA kernels
+    assert _rel_err(cs, out.float().sum(0))[0] < 1e-5
     zf = z.float().requires_grad_(True)
     torch.nn.functional.gelu(zf).backward(dy.float() @ w.float())
     assert _rel_err(out, zf.grad)[0] < 5e-3
@@ -185,10 +187,12 @@ def test_gemm_cta_pair_epilogues():
     dy, w = _randn(M, K, seed=29), _randn(K, N, scale=0.03, seed=30)
     zz = _randn(M, N, seed=31)
     dz = torch.empty(M, N, device="cuda", dtype=BF)
-    ops.gemm(dy, w, dz, b_t=True, act=ops.ACT_DGELU, aux=zz)
+    cs = torch.zeros(N, device="cuda")
+    ops.gemm(dy, w, dz, b_t=True, act=ops.ACT_DGELU, aux=zz, colsum=cs)
     zf = zz.float().requires_grad_(True)
     torch.nn.functional.gelu(zf).backward(dy.float() @ w.float())
     assert _rel_err(dz, zf.grad)[0] < 5e-3
+    assert _rel_err(cs, dz.float().sum(0))[0] < 1e-5                # fused bias gradient = colsum of the bf16 output
     # dgrad + residual
     dx = torch.empty(M, K, device="cuda", dtype=BF)
     w1 = _randn(N, K, scale=0.03, seed=32)
@@ -294,8 +298,10 @@ def test_attention_fwd_bwd(L):
     dctx = _randn(n * L, E, seed=5)
     ref.backward(dctx.float())
     dqkv = torch.empty_like(qkv)
-    ops.attn_bwd(qkv, x, L, relpos, dctx, dqkv, A)
+    dbias = torch.zeros(3 * E, device="cuda")
+    ops.attn_bwd(qkv, x, L, relpos, dctx, dqkv, A, dbias=dbias)
     assert _rel_err(dqkv, qf.grad)[0] < 6e-3
+    assert _rel_err(dbias, dqkv.float().sum(0))[0] < 1e-5           # fused [bq|bk|bv] gradient = colsum(dqkv)
 
 
 @pytest.mark.parametrize("L", [33, 64, 100, 180, 512])

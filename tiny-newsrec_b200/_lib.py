@@ -39,7 +39,8 @@ class GemmArgs(Structure):
                 ("aux", c_void_p), ("ldaux", c_int),
                 ("split_k", c_int),
                 ("accumulate", c_int),
-                ("drop", POINTER(Dropout))]
+                ("drop", POINTER(Dropout)),
+                ("colsum", c_void_p)]
 
 
 P = c_void_p
@@ -53,7 +54,7 @@ _SIGNATURES = {
     "tnr_layernorm_bwd": ([P, P, c_int, c_int, P, c_float, P, P, P, P, P, POINTER(Dropout), P], c_int),
     "tnr_colsum_bf16": ([P, c_int, c_int, c_int, P, P], c_int),
     "tnr_attn_relpos_fwd": ([P, P, c_int, P, P, c_int, c_int, c_int, c_int, POINTER(Dropout), P], c_int),
-    "tnr_attn_relpos_bwd": ([P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, POINTER(Dropout), P], c_int),
+    "tnr_attn_relpos_bwd": ([P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, POINTER(Dropout), P], c_int),
     "tnr_attnpool_fwd": ([P, P, c_int, c_int, P, P, P, P, P, c_int, c_int, c_int, P], c_int),
     "tnr_attnpool_bwd": ([P, P, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_int, P], c_int),
     "tnr_user_encoder_fwd": ([P, P, P, P, P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
@@ -93,7 +94,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res
-    if lib.tnr_abi_version() != 3:
+    if lib.tnr_abi_version() != 4:
         raise TinyRecError("libtinyrec.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -49,6 +49,19 @@ __device__ __forceinline__ void store_tile(__nv_bfloat16* g, const __nv_bfloat16
   }
 }
 
+// out[c] += sum over the first L rows of the staged bf16 tile (columns 2*lane, 2*lane+1): the bias gradient
+// contribution of this (news, head) block, from the same rounded values that go to dqkv
+__device__ __forceinline__ void tile_colsum(float* __restrict__ out, const __nv_bfloat16* s, int L, int lane) {
+  float a0 = 0.f, a1 = 0.f;
+  for (int r = 0; r < L; ++r) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(s + r * TS + 2 * lane);
+    a0 += bf16_lo(u);
+    a1 += bf16_hi(u);
+  }
+  atomicAdd(out + 2 * lane, a0);
+  atomicAdd(out + 2 * lane + 1, a1);
+}
+
 // C fragments (2 m-tiles x 8 n-tiles of a 32 x 64 fp32 result) -> bf16 smem tile
 __device__ __forceinline__ void stage_c64(__nv_bfloat16* s, const float (&o)[2][8][4], int lane) {
   const int g = lane >> 2, t = lane & 3;
@@ -240,7 +253,8 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
 __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ mask, int mask_ld,
                 const float* __restrict__ relbias, const __nv_bfloat16* __restrict__ dctx,
-                __nv_bfloat16* __restrict__ dqkv, int n_news, int L, int A, int E, const tnr_dropout drop) {
+                __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int n_news, int L, int A, int E,
+                const tnr_dropout drop) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * ATT_WARPS + warp;
@@ -329,6 +343,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
   stage_c64(sK, acc, lane);
   __syncwarp();
   store_tile(dbase, sK, L, ld, lane);
+  if (dbias != nullptr) tile_colsum(dbias + h * DH, sK, L, lane);
   // dV = P_drop^T dO
   load_xT_frags(pa, sP, lane);
 #pragma unroll
@@ -341,6 +356,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
   stage_c64(sV, acc, lane);                       // V was last read by the dP product
   __syncwarp();
   store_tile(dbase + 2 * E, sV, L, ld, lane);
+  if (dbias != nullptr) tile_colsum(dbias + 2 * E + h * DH, sV, L, lane);
   // dK = dS^T Q
   load_xT_frags(pa, sS, lane);
 #pragma unroll
@@ -354,6 +370,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
   stage_c64(sQ, acc, lane);
   __syncwarp();
   store_tile(dbase + E, sQ, L, ld, lane);
+  if (dbias != nullptr) tile_colsum(dbias + E + h * DH, sQ, L, lane);
 }
 
 }  // namespace tnr
@@ -389,7 +406,7 @@ extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_fwd(const 
 }
 
 extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_bwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias,
-                                   const void* dctx_bf16, void* dqkv_bf16, int n_news, int L, int A, int E,
+                                   const void* dctx_bf16, void* dqkv_bf16, float* dbias_qkv, int n_news, int L, int A, int E,
                                    const tnr_dropout* drop, void* stream) {
   if (check_attn("tnr_attn_relpos_bwd", L, A, E, LMAX)) return 1;      // L > 32: forward only so far
   if (n_news == 0) return 0;
@@ -403,8 +420,8 @@ extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_bwd(const 
   }
   attn_bwd_kernel<<<grid, ATT_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relbias,
-      reinterpret_cast<const __nv_bfloat16*>(dctx_bf16), reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), n_news, L, A, E,
-      drop_or_none(drop));
+      reinterpret_cast<const __nv_bfloat16*>(dctx_bf16), reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias_qkv, n_news, L,
+      A, E, drop_or_none(drop));
   TNR_LAUNCH_CHECK();
   return 0;
 }

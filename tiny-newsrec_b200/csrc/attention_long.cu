@@ -3,8 +3,9 @@
 //   P = softmax(Q K^T / 8 + (1 - mask) * -10000 + relbias[h][j - i]);  ctx = dropout(P) V
 // Reference: Tiny-NewsRec/tnlrv3/modeling.py:205-231, mask :446-454, rel-pos bias :458-463.
 //
-// One block (4 warps) per (news, head, 64-query block); each warp owns 16 query rows.  K / V are streamed
-// through shared memory in 64-key chunks (cp.async), the two contractions run on ldmatrix + mma.sync
+// One block (4 warps, 4 blocks per SM) per (news, head, 64-query block); each warp owns 16 query rows.  K / V
+// are streamed through a double-buffered shared-memory stage in 64-key chunks (cp.async, the next chunk in
+// flight while the current one is used), the two contractions run on ldmatrix + mma.sync
 // m16n8k16 (bf16 in, fp32 accumulate) with the usual online softmax (running max / sum per row, the output
 // accumulator rescaled when the max moves), so nothing of size L x L is ever materialised.  The bias is a
 // function of j - i only: the per-head [2L-1] vector and the additive key mask live in shared memory.
@@ -30,17 +31,24 @@ __device__ __forceinline__ void long_load_tile(__nv_bfloat16* s, const __nv_bflo
   }
 }
 
-__global__ void __launch_bounds__(128)
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(128, 4)
 attn_long_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ mask, int mask_ld,
                      const float* __restrict__ relbias, __nv_bfloat16* __restrict__ ctx, int n_news, int L, int A, int E,
                      int q_blocks, const tnr_dropout drop) {
   extern __shared__ __align__(16) uint8_t smem[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem);
-  __nv_bfloat16* sK = sQ + LQB * LTS;
-  __nv_bfloat16* sV = sK + LKB * LTS;
-  float* s_madd = reinterpret_cast<float*>(sV + LKB * LTS);       // [k_chunks * 64]
+  __nv_bfloat16* sKV = sQ + LQB * LTS;                           // [2 buffers][K tile | V tile]
   const int k_chunks = (L + LKB - 1) / LKB;
-  float* s_rel = s_madd + k_chunks * LKB;                         // [2L - 1]
+  float* s_madd = reinterpret_cast<float*>(sKV + 4 * LKB * LTS);  // [k_chunks * 64], pre-multiplied by log2(e)
+  float* s_rel = s_madd + k_chunks * LKB;                         // [2L - 1 (+ 64 zeros)], pre-multiplied by log2(e)
+  __shared__ int s_live[LONG_LMAX / LKB];                         // chunk holds at least one unmasked key
+  __shared__ int s_any;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const long long item = blockIdx.x / q_blocks;
@@ -52,10 +60,24 @@ attn_long_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __res
   const DropCfg dc = load_drop(drop);
 
   long_load_tile(sQ, base, q0, L, ld, tid);
-  for (int j = tid; j < k_chunks * LKB; j += 128)
-    s_madd[j] = j < L ? (1.0f - (float)mask[(size_t)n * mask_ld + j]) * -10000.0f : -INFINITY;
-  for (int d = tid; d < 2 * L - 1; d += 128) s_rel[d] = relbias[(size_t)h * (2 * L - 1) + d];
-  cp_async_wait_all();
+  long_load_tile(sKV, base + E, 0, L, ld, tid);
+  long_load_tile(sKV + LKB * LTS, base + 2 * E, 0, L, ld, tid);
+  cp_async_commit_group();
+  if (tid < LONG_LMAX / LKB) s_live[tid] = 0;
+  if (tid == 0) s_any = 0;
+  __syncthreads();
+  for (int j = tid; j < k_chunks * LKB; j += 128) {
+    float v = -INFINITY;
+    if (j < L) {
+      const bool keep = mask[(size_t)n * mask_ld + j] != 0;
+      v = keep ? 0.f : -10000.0f * LOG2E;
+      if (keep) { s_live[j / LKB] = 1; s_any = 1; }             // benign race: every writer stores 1
+    }
+    s_madd[j] = v;
+  }
+  for (int d = tid; d < 2 * L - 1 + LKB; d += 128)              // zero tail: keys j >= L index past the vector
+    s_rel[d] = d < 2 * L - 1 ? relbias[(size_t)h * (2 * L - 1) + d] * LOG2E : 0.f;
+  cp_async_wait_group<0>();
   __syncthreads();
 
   // Q fragments of this warp's 16 rows stay in registers for the whole key loop
@@ -72,100 +94,132 @@ attn_long_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __res
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const int i0 = q0 + warp * 16 + g;                 // this thread's rows: i0 and i0 + 8
   const bool warp_live = q0 + warp * 16 < L;         // warp-uniform: rows beyond L produce nothing
+  // A chunk whose keys are all masked (additive -10000) contributes exactly 0 to every row as soon as the
+  // news has one unmasked key anywhere (exp underflows in fp32), so it is skipped; an all-pad news keeps
+  // every chunk (uniform shift, the reference's result).
+  const bool any_key = s_any != 0;
 
   for (int kc = 0; kc < k_chunks; ++kc) {
     const int c0 = kc * LKB;
-    __syncthreads();                                 // previous chunk fully consumed
-    long_load_tile(sK, base + E, c0, L, ld, tid);
-    long_load_tile(sV, base + 2 * E, c0, L, ld, tid);
-    cp_async_wait_all();
-    __syncthreads();
-    if (!warp_live) continue;
-
-    float s[8][4];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) s[nt][c] = 0.f;
-      uint32_t kb[2][4];
-#pragma unroll
-      for (int half = 0; half < 2; ++half)
-        ldsm_x4(smem_addr(sK + (nt * 8 + (lane & 7)) * LTS + half * 32 + (lane >> 3) * 8), kb[half]);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) mma_bf16(s[nt], qa[ks], kb[ks >> 1][(ks & 1) * 2], kb[ks >> 1][(ks & 1) * 2 + 1]);
+    const __nv_bfloat16* sK = sKV + (kc & 1) * 2 * LKB * LTS;
+    const __nv_bfloat16* sV = sK + LKB * LTS;
+    if (kc + 1 < k_chunks) {                         // prefetch the next chunk into the other buffer
+      __nv_bfloat16* nK = sKV + ((kc + 1) & 1) * 2 * LKB * LTS;
+      long_load_tile(nK, base + E, c0 + LKB, L, ld, tid);
+      long_load_tile(nK + LKB * LTS, base + 2 * E, c0 + LKB, L, ld, tid);
+      cp_async_commit_group();
+      cp_async_wait_group<1>();
+    } else {
+      cp_async_wait_group<0>();
     }
-    // scores -> probabilities of this chunk under the running maximum
+    __syncthreads();                                 // chunk kc visible to all warps
+    if (warp_live && (s_live[kc] || !any_key)) {
+      float s[8][4];
 #pragma unroll
-    for (int hi = 0; hi < 2; ++hi) {
-      const int i = min(i0 + hi * 8, L - 1);
-      const float* rel = s_rel + (L - 1 - i);        // rel[j] = bias of key j for query i
-      float mx = -INFINITY;
+      for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+        for (int c = 0; c < 4; ++c) s[nt][c] = 0.f;
+        uint32_t kb[2][4];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = c0 + nt * 8 + 2 * t + e;
-          float v = -INFINITY;
-          if (j < L) v = s[nt][hi * 2 + e] * 0.125f + s_madd[j] + rel[j];
-          s[nt][hi * 2 + e] = v;
-          mx = fmaxf(mx, v);
+        for (int half = 0; half < 2; ++half)
+          ldsm_x4(smem_addr(sK + (nt * 8 + (lane & 7)) * LTS + half * 32 + (lane >> 3) * 8), kb[half]);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_bf16(s[nt], qa[ks], kb[ks >> 1][(ks & 1) * 2], kb[ks >> 1][(ks & 1) * 2 + 1]);
+      }
+      // scores (in log2 units) -> probabilities of this chunk under the running maximum.  Keys j >= L carry
+      // s_madd = -inf (no bound check).  The additive terms of this thread's 16 columns are fetched once: the
+      // key mask is shared by both rows, and row i0 + 8 sees the rel-pos values of row i0 eight keys earlier.
+      {
+        const int ib = min(i0, L - 1);
+        const float* relp = s_rel + (L - 1 - ib) + c0 + 2 * t;         // rel of (row i0, key c0 + 2t + ...)
+        float rel[9][2];
+#pragma unroll
+        for (int nt = 0; nt < 9; ++nt) {
+          const int off = (nt - 1) * 8;                                   // nt = 0: the eight keys before the chunk
+          const bool ok = (L - 1 - ib) + c0 + 2 * t + off >= 0;
+          rel[nt][0] = ok ? relp[off] : 0.f;
+          rel[nt][1] = ok ? relp[off + 1] : 0.f;
         }
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      const float m_new = fmaxf(m_run[hi], mx);      // finite: every chunk holds at least one key j < L
-      const float corr = __expf(m_run[hi] - m_new);  // exp(-inf) = 0 on the first chunk
-      float sum = 0.f;
+        const bool row1_clamped = i0 + 8 > L - 1;                        // tail rows reuse row L-1 (never stored)
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float pv = __expf(s[nt][hi * 2 + e] - m_new);
-          s[nt][hi * 2 + e] = pv;
-          sum += pv;
+        for (int nt = 0; nt < 8; ++nt) {
+          const float2 md = *reinterpret_cast<const float2*>(s_madd + c0 + nt * 8 + 2 * t);
+          const f32x2 mdp = pk2(md.x, md.y);
+          const f32x2 a0 = add2(mdp, pk2(rel[nt + 1][0], rel[nt + 1][1]));
+          const f32x2 a1 = add2(mdp, row1_clamped ? pk2(rel[nt + 1][0], rel[nt + 1][1]) : pk2(rel[nt][0], rel[nt][1]));
+          const f32x2 sc = pk2(0.125f * LOG2E, 0.125f * LOG2E);
+          upk2(fma2(pk2(s[nt][0], s[nt][1]), sc, a0), s[nt][0], s[nt][1]);
+          upk2(fma2(pk2(s[nt][2], s[nt][3]), sc, a1), s[nt][2], s[nt][3]);
         }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      l_run[hi] = l_run[hi] * corr + sum;
-      m_run[hi] = m_new;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) { o[nt][hi * 2] *= corr; o[nt][hi * 2 + 1] *= corr; }
-    }
-    if (dc.thr16 != 0) {
-      // dropout on the (unnormalised) probabilities; the 1/(1-p) scale commutes with the final 1/l.
-      // Philox group of (item, i, chunk kc, quad lane t, half of the chunk): 8 elements, bit (nt & 3) * 2 + e.
+      }
 #pragma unroll
       for (int hi = 0; hi < 2; ++hi) {
-        const uint64_t row = (uint64_t)item * (uint64_t)L + (uint64_t)min(i0 + hi * 8, L - 1);
+        float mx = -INFINITY;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const uint32_t keep = dropout_keep8(dc, ((row * (uint64_t)k_chunks + (uint64_t)kc) * 4 + (uint64_t)t) * 2 + hf);
+        for (int nt = 0; nt < 8; ++nt) mx = fmaxf(mx, fmaxf(s[nt][hi * 2], s[nt][hi * 2 + 1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float m_new = fmaxf(m_run[hi], mx);    // finite: a processed chunk holds at least one key j < L
+        const float corr = ex2_approx(m_run[hi] - m_new);   // 2^-inf = 0 on the first chunk
+        const f32x2 mneg = pk2(-m_new, -m_new);
+        f32x2 sum2 = pk2(0.f, 0.f);
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
+        for (int nt = 0; nt < 8; ++nt) {
+          float x0, x1;
+          upk2(add2(pk2(s[nt][hi * 2], s[nt][hi * 2 + 1]), mneg), x0, x1);
+          s[nt][hi * 2] = ex2_approx(x0);
+          s[nt][hi * 2 + 1] = ex2_approx(x1);
+          sum2 = add2(sum2, pk2(s[nt][hi * 2], s[nt][hi * 2 + 1]));
+        }
+        float sa, sb;
+        upk2(sum2, sa, sb);
+        float sum = sa + sb;
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        l_run[hi] = l_run[hi] * corr + sum;
+        m_run[hi] = m_new;
+        const f32x2 c2 = pk2(corr, corr);
 #pragma unroll
-            for (int e = 0; e < 2; ++e)
-              s[hf * 4 + q][hi * 2 + e] = ((keep >> (q * 2 + e)) & 1u) ? s[hf * 4 + q][hi * 2 + e] * dc.scale : 0.f;
+        for (int nt = 0; nt < 8; ++nt) upk2(mul2(pk2(o[nt][hi * 2], o[nt][hi * 2 + 1]), c2), o[nt][hi * 2], o[nt][hi * 2 + 1]);
+      }
+      if (dc.thr16 != 0) {
+        // dropout on the (unnormalised) probabilities; the 1/(1-p) scale commutes with the final 1/l.
+        // Philox group of (item, i, chunk kc, quad lane t, half of the chunk): 8 elements, bit (nt & 3) * 2 + e.
+#pragma unroll
+        for (int hi = 0; hi < 2; ++hi) {
+          const uint64_t row = (uint64_t)item * (uint64_t)L + (uint64_t)min(i0 + hi * 8, L - 1);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const uint32_t keep = dropout_keep8(dc, ((row * (uint64_t)k_chunks + (uint64_t)kc) * 4 + (uint64_t)t) * 2 + hf);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+                s[hf * 4 + q][hi * 2 + e] = ((keep >> (q * 2 + e)) & 1u) ? s[hf * 4 + q][hi * 2 + e] * dc.scale : 0.f;
+          }
+        }
+      }
+      // P (16 x 64, C layout) -> A fragments; O += P V
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        pa[ks][0] = pack_bf16(s[2 * ks][0], s[2 * ks][1]);
+        pa[ks][1] = pack_bf16(s[2 * ks][2], s[2 * ks][3]);
+        pa[ks][2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+        pa[ks][3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {             // keys 0-31, 32-63 of the chunk
+          uint32_t vb[4];
+          ldsm_x4_t(smem_addr(sV + (kh * 32 + lane) * LTS + nt * 8), vb);
+          mma_bf16(o[nt], pa[kh * 2], vb[0], vb[1]);
+          mma_bf16(o[nt], pa[kh * 2 + 1], vb[2], vb[3]);
         }
       }
     }
-    // P (16 x 64, C layout) -> A fragments; O += P V
-    uint32_t pa[4][4];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      pa[ks][0] = pack_bf16(s[2 * ks][0], s[2 * ks][1]);
-      pa[ks][1] = pack_bf16(s[2 * ks][2], s[2 * ks][3]);
-      pa[ks][2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
-      pa[ks][3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
-    }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int kh = 0; kh < 2; ++kh) {               // keys 0-31, 32-63 of the chunk
-        uint32_t vb[4];
-        ldsm_x4_t(smem_addr(sV + (kh * 32 + lane) * LTS + nt * 8), vb);
-        mma_bf16(o[nt], pa[kh * 2], vb[0], vb[1]);
-        mma_bf16(o[nt], pa[kh * 2 + 1], vb[2], vb[3]);
-      }
-    }
+    __syncthreads();                                 // chunk kc consumed: its buffer may be refilled
   }
   if (!warp_live) return;
   // normalise, stage this warp's 16 x 64 rows in its own (already consumed) part of sQ, store full 128 B rows
@@ -194,11 +248,11 @@ int attn_long_fwd_launch(const void* qkv_bf16, const int64_t* mask, int mask_ld,
   const int k_chunks = (L + LKB - 1) / LKB;
   const long long blocks = (long long)n_news * A * q_blocks;
   TNR_REQUIRE(blocks < (1ll << 31), "tnr_attn_relpos_fwd: too many blocks");
-  const int smem = 3 * LQB * LTS * 2 + (k_chunks * LKB + 2 * L - 1) * 4;
+  const int smem = 5 * LQB * LTS * 2 + (k_chunks * LKB + 2 * L - 1 + LKB) * 4;
   static bool attr_done = false;
   if (!attr_done) {
     TNR_CHECK_CUDA(cudaFuncSetAttribute(attn_long_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        3 * LQB * LTS * 2 + (LONG_LMAX + 2 * LONG_LMAX) * 4));
+                                        5 * LQB * LTS * 2 + (LONG_LMAX + 2 * LONG_LMAX + LKB) * 4));
     attr_done = true;
   }
   attn_long_fwd_kernel<<<(unsigned)blocks, 128, smem, st>>>(

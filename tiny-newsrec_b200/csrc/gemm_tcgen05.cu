@@ -46,6 +46,7 @@ struct Params {
   int epi_tma;        // bf16 C through smem + TMA store
   int in_mode;        // 0 none, 1 residual box prefetched by TMA, 2 dGELU pre-activation box
   int aux_out;        // GELU pre-activation written through TMA
+  float* colsum;      // column sums of the bf16 output (bias gradient), fp32 atomics; NULL = off
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -569,6 +570,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tma_store_2d(&tmap_c, box_u32, col0, row0);
           bulk_commit();
         }
+        if (p.colsum != nullptr) {
+          // columns 2*lane, 2*lane+1 of the staged 32 x 64 box (128B-swizzled rows); rows past M are skipped
+          const int rows_ok = min(32, p.M - row0);
+          const uint32_t cw = (uint32_t)(lane & 3) * 4u;
+          float a0 = 0.f, a1 = 0.f;
+          for (int r = 0; r < rows_ok; ++r) {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(box + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + cw);
+            a0 += bf16_lo(u);
+            a1 += bf16_hi(u);
+          }
+          const int c = col0 + 2 * lane;
+          if (c < p.N) { atomicAdd(p.colsum + c, a0); atomicAdd(p.colsum + c + 1, a1); }
+        }
       }
       if (lane == 0) bulk_wait_all();
     } else {
@@ -759,6 +773,9 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
   p.aux = reinterpret_cast<__nv_bfloat16*>(a->aux); p.ldaux = a->ldaux;
   p.atomic = atomic ? 1 : 0;
   p.drop = drop_or_none(a->drop);
+  p.colsum = a->colsum;
+  TNR_REQUIRE(a->colsum == nullptr || (a->c_dtype == TNR_BF16 && !atomic),
+              "tnr_gemm_bf16: colsum needs a bf16 (TMA-staged) output");
   TNR_REQUIRE(p.drop.seed == nullptr || !(p.drop.p > 0.f) || (!atomic && a->act == TNR_ACT_NONE),
               "tnr_gemm_bf16: dropout is supported with the plain (bias + residual) epilogue only");
 

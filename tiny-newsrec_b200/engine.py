@@ -379,10 +379,12 @@ class Encoder:
                               dsum=flat.g_view(lr.f2.bias) if train else None)       # + f2.bias gradient
             if train:
                 self._wgrad(flat, lr.f2.weight, dd, sv["h"])
-            ops.gemm(dd, w2, dz, b_t=True, act=ops.ACT_DGELU, aux=sv["z"])
+            # dz = (dd @ W2) * gelu'(z); its column sums (the intermediate.dense bias gradient) come out of the
+            # same epilogue
+            ops.gemm(dd, w2, dz, b_t=True, act=ops.ACT_DGELU, aux=sv["z"],
+                     colsum=flat.g_view(lr.f1.bias) if train else None)
             if train:
                 self._wgrad(flat, lr.f1.weight, dz, sv["x1"])
-                ops.colsum(dz, flat.g_view(lr.f1.bias))
             ops.gemm(dz, w1, dx2, b_t=True, residual=dpre)                 # d x1
             sg, sb = (flat.g_view(lr.ln1.weight), flat.g_view(lr.ln1.bias)) if train else (self.scratch_ln[:E], self.scratch_ln[E:])
             d1 = dmk(drop_site(i, KIND_ATT_OUT), ph)
@@ -393,11 +395,14 @@ class Encoder:
             if train:
                 self._wgrad(flat, lr.o.weight, dd, sv["ctx"])
             ops.gemm(dd, wo, dctx, b_t=True)
-            ops.attn_bwd(sv["qkv"], x, L, self.relpos(L), dctx, dqkv, self.A, drop=dmk(drop_site(i, KIND_ATTN), pa))
+            dbq = None
+            if train:
+                ob = flat.off(lr.q.bias)
+                dbq = flat.grad[ob:ob + 3 * E]                             # [bq | bk | bv] gradient, fused
+            ops.attn_bwd(sv["qkv"], x, L, self.relpos(L), dctx, dqkv, self.A, drop=dmk(drop_site(i, KIND_ATTN), pa),
+                         dbias=dbq)
             if train:
                 self._wgrad(flat, lr.q.weight, dqkv, sv["xin"], rows=3 * E)
-                ob = flat.off(lr.q.bias)
-                ops.colsum(dqkv, flat.grad[ob:ob + 3 * E])
             if i > low:
                 ops.gemm(dqkv, wqkv, dx, b_t=True, residual=dpre)
             if on_layer_done is not None and train:

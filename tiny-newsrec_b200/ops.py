@@ -99,7 +99,7 @@ def _ready(t, kernels=1):
 
 @_timed
 def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, aux=None,
-         split_k=1, accumulate=False, drop=None):
+         split_k=1, accumulate=False, drop=None, colsum=None):
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).
 
     a: bf16 [M,K] (or [K,M] when ``a_t``); b: bf16 [N,K] (or [K,N] when ``b_t``); 2-D, unit
@@ -137,6 +137,8 @@ def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_N
     g.accumulate = int(accumulate)
     if drop is not None:
         g.drop = ctypes.pointer(drop)
+    if colsum is not None:
+        g.colsum = _chk(colsum, _f32, "gemm.colsum").data_ptr()
     if stats.gemm_events is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -214,7 +216,8 @@ def attn_fwd(qkv, x, L, relpos, ctx, A, drop=None):
 
 
 @_timed
-def attn_bwd(qkv, x, L, relpos, dctx, dqkv, A, drop=None):
+def attn_bwd(qkv, x, L, relpos, dctx, dqkv, A, drop=None, dbias=None):
+    """dqkv from dctx; ``dbias`` fp32 [3E] (optional) += column sums of dqkv (the [bq|bk|bv] gradient)."""
     lib = _ready(qkv)
     n = x.shape[0]
     E = qkv.shape[1] // 3
@@ -222,7 +225,7 @@ def attn_bwd(qkv, x, L, relpos, dctx, dqkv, A, drop=None):
     _chk_relbias(relpos, A, L)
     _lib.check(lib.tnr_attn_relpos_bwd(_ptr(_chk(qkv, _bf16, "attn.qkv")), mask_ptr, x.stride(0),
                                        _ptr(relpos), _ptr(_chk(dctx, _bf16, "dctx")),
-                                       _ptr(_chk(dqkv, _bf16, "dqkv")), n, L, A, E, _dp(drop), _stream()),
+                                       _ptr(_chk(dqkv, _bf16, "dqkv")), _ptr(dbias), n, L, A, E, _dp(drop), _stream()),
                "tnr_attn_relpos_bwd")
     return dqkv
 
