@@ -136,13 +136,36 @@ def news_encoder(sd, pfx, x, num_layers, heads=12, drop=None):
     return F.linear(pooled, sd[pfx + "dense.weight"], sd[pfx + "dense.bias"])
 
 
+def multi_head_self_attn(sd, pfx, x, mask=None, d_k=16, d_v=16):
+    """NRMS user encoder, model_bert.py:37-100: Q/K/V projections, per-head
+    ``exp(QK^T / sqrt(d_k))`` (NOT a softmax: no max subtraction) [* key mask],
+    normalised by ``sum + 1e-8``, times V; heads concatenated."""
+    B, H, _ = x.shape
+    n_heads = sd[pfx + "W_Q.weight"].shape[0] // d_k
+    q = F.linear(x, sd[pfx + "W_Q.weight"], sd[pfx + "W_Q.bias"]).view(B, H, n_heads, d_k).transpose(1, 2)
+    k = F.linear(x, sd[pfx + "W_K.weight"], sd[pfx + "W_K.bias"]).view(B, H, n_heads, d_k).transpose(1, 2)
+    v = F.linear(x, sd[pfx + "W_V.weight"], sd[pfx + "W_V.bias"]).view(B, H, n_heads, d_v).transpose(1, 2)
+    scores = torch.exp(torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d_k))            # :53-54
+    if mask is not None:
+        scores = scores * mask[:, None, None, :]                                          # :56-57
+    attn = scores / (scores.sum(dim=-1, keepdim=True) + 1e-8)                             # :59
+    ctx = torch.matmul(attn, v)
+    return ctx.transpose(1, 2).contiguous().view(B, H, n_heads * d_v)
+
+
 def user_encoder(sd, pfx, vecs, log_mask, user_log_mask):
-    """model_bert.py:155-176, NAML branches: masked pool (:166) or pad_doc blend
-    then unmasked pool (:168-175)."""
+    """model_bert.py:155-176.  NAML branches: masked pool (:166) or pad_doc blend then unmasked pool
+    (:168-175).  NRMS branches (a state dict with ``multi_head_self_attn.*``): the same with the
+    multi-head self-attention in front of the pooling (:162-164, :171-173)."""
+    nrms = (pfx + "multi_head_self_attn.W_Q.weight") in sd
     if user_log_mask:
+        if nrms:
+            vecs = multi_head_self_attn(sd, pfx + "multi_head_self_attn.", vecs, log_mask)
         return attention_pooling(sd, pfx + "attn.", vecs, log_mask)
     m = log_mask.unsqueeze(-1)
     blended = vecs * m + sd[pfx + "pad_doc"].unsqueeze(0) * (1 - m)
+    if nrms:
+        blended = multi_head_self_attn(sd, pfx + "multi_head_self_attn.", blended)
     return attention_pooling(sd, pfx + "attn.", blended)
 
 

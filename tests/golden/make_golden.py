@@ -275,6 +275,55 @@ def gen_unilm_convert():
     np.savez_compressed(os.path.join(HERE, "unilm_convert.npz"), **fix)
 
 
+def gen_nrms():
+    """KD ``Model`` with the NRMS user encoders (args.model = 'NRMS': 16-head exp-normalised self-attention
+    over the history in front of the additive pooling, model_bert.py:37-100,145-148,162-164,171-173), both
+    ``user_log_mask`` branches, losses + scores + gradients of every trainable tensor."""
+    seed, layers, M, B, H, K, L, D = 13, 1, 2, 3, 5, 3, 8, 256
+    rng = np.random.default_rng(31)
+    hist = rand_news(rng, B * H, L).reshape(B, H, 2 * L)
+    cand = rand_news(rng, B * K, L).reshape(B, K, 2 * L)
+    hmask = np.array([[0, 0, 1, 1, 1], [0, 0, 0, 0, 1], [1, 1, 1, 1, 1]], dtype=np.float32)
+    hist[0, :2] = 0
+    hist[1, :4] = 0
+    label = np.array([1, 2, 0], dtype=np.int64)
+    th = [rng.standard_normal((B, H, D)).astype(np.float32) * 0.3 for _ in range(M)]
+    tc = [rng.standard_normal((B, K, D)).astype(np.float32) * 0.3 for _ in range(M)]
+    out = dict(seed=seed, layers=layers, M=M, history=hist, candidate=cand, history_mask=hmask, label=label,
+               temperature=1.5, coef=0.3,
+               **{f"th{i}": th[i] for i in range(M)}, **{f"tc{i}": tc[i] for i in range(M)})
+    sd = synth.kd_model_state(layers, M, seed, noisy=True, model="NRMS", n_heads=16)
+    for ulm in (False, True):
+        args = ref_shim.make_args(num_student_layers=layers, user_log_length=H, user_log_mask=ulm, num_teachers=M,
+                                  temperature=1.5, coef=0.3, model="NRMS", num_attention_heads=16)
+        m = ref_mb.Model(args).eval()
+        assert list(m.state_dict().keys()) == list(sd.keys())
+        m.load_state_dict(sd, strict=True)
+        for p in m.teachers.parameters():
+            p.requires_grad = False
+        for p in m.student.news_encoder.bert_model.parameters():
+            p.requires_grad = False
+        for p in m.student.news_encoder.bert_model.bert.encoder.layer[0].parameters():
+            p.requires_grad = True
+        res = m(torch.from_numpy(hist), torch.from_numpy(hmask), torch.from_numpy(cand),
+                torch.from_numpy(label), [torch.from_numpy(t) for t in th], [torch.from_numpy(t) for t in tc])
+        tag = "mask" if ulm else "pad"
+        for nm, v in zip(("total", "distill", "emb", "target"), res[:4]):
+            out[f"{nm}_{tag}"] = np.float64(v.detach())
+        out[f"score_{tag}"] = res[4].detach().numpy()
+        m.zero_grad()
+        res[0].backward()
+        names = []
+        for nm, p in m.named_parameters():
+            if p.requires_grad and p.grad is not None:       # pad_doc has no gradient in the user_log_mask branch
+                names.append(nm)
+                out.update({f"{tag}/{k}": v for k, v in grad_summary(nm, p.grad).items()})
+        out[f"trainable_names_{tag}"] = np.array(names)
+    out["wsum"] = checksum(sd)
+    out["state_keys"] = np.array(list(sd.keys()))
+    np.savez_compressed(os.path.join(HERE, "nrms.npz"), **out)
+
+
 if __name__ == "__main__":
     gen_relpos()
     gen_encoder()
@@ -287,3 +336,4 @@ if __name__ == "__main__":
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
     gen_unilm_convert()
+    gen_nrms()

@@ -177,3 +177,27 @@ def test_batching_bit_exact(golden):
 
 def test_shard_round_robin():
     assert ob.shard_round_robin(7, 1, 3) == [1, 4]
+
+
+# ------------------------------------------------------------------ NRMS user encoder
+@pytest.mark.parametrize("tag,ulm", [("pad", False), ("mask", True)])
+def test_nrms_kd_forward_and_gradients(golden, tag, ulm):
+    """Oracle vs the reference ``Model`` with args.model = 'NRMS' (fixture: make_golden.py:gen_nrms)."""
+    g = golden("nrms")
+    layers, M = int(g["layers"]), int(g["M"])
+    sd = synth.kd_model_state(layers, M, int(g["seed"]), noisy=True, model="NRMS", n_heads=16)
+    assert list(sd.keys()) == [str(k) for k in g["state_keys"]]                 # reference state_dict order
+    _check_weights(sd, g)
+    keys = [str(s) for s in g[f"trainable_names_{tag}"]]
+    for k in keys:
+        sd[k].requires_grad_(True)
+    res = om.kd_model_forward(sd, *_kd_inputs(g), layers, ulm, float(g["temperature"]), float(g["coef"]))
+    for v, nm in zip(res[:4], ("total", "distill", "emb", "target")):
+        np.testing.assert_allclose(float(v), float(g[f"{nm}_{tag}"]), rtol=2e-5)
+    np.testing.assert_allclose(res[4].detach().numpy(), g[f"score_{tag}"], rtol=1e-4, atol=2e-5)
+    res[0].backward()
+    for k in keys:
+        gr = sd[k].grad
+        np.testing.assert_allclose(float(gr.double().abs().sum()), float(g[f"{tag}/gabs/{k}"]), rtol=2e-4, atol=1e-9)
+        if f"{tag}/gfull/{k}" in g.files:
+            np.testing.assert_allclose(gr.numpy(), g[f"{tag}/gfull/{k}"], rtol=2e-3, atol=2e-7)

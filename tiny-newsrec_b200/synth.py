@@ -96,31 +96,41 @@ def attention_pooling_state(pfx, emb, hidden, seed):
     return sd
 
 
-def user_encoder_state(pfx, news_dim, qdim, seed):
+def user_encoder_state(pfx, news_dim, qdim, seed, model="NAML", n_heads=16):
+    """``UserEncoder`` (model_bert.py:140-153).  model='NRMS' adds the multi-head self-attention
+    (W_Q / W_K / W_V: xavier-uniform weights :73-76, default nn.Linear biases) and pools over
+    n_heads * 16 features; key order = the reference's state_dict order."""
     sd = {pfx + "pad_doc": _uniform(seed, pfx + "pad_doc", (1, news_dim), 1.0)}
-    sd.update(attention_pooling_state(pfx + "attn.", news_dim, qdim, seed))
+    pool_dim = news_dim
+    if model == "NRMS":
+        pool_dim = n_heads * 16
+        for nm in ("W_Q", "W_K", "W_V"):
+            k = pfx + "multi_head_self_attn." + nm
+            sd[k + ".weight"] = _uniform(seed, k + ".weight", (pool_dim, news_dim), math.sqrt(6.0 / (news_dim + pool_dim)))
+            sd[k + ".bias"] = _uniform(seed, k + ".bias", (pool_dim,), 1.0 / math.sqrt(news_dim))
+    sd.update(attention_pooling_state(pfx + "attn.", pool_dim, qdim, seed))
     return sd
 
 
 def model_bert_state(pfx, num_layers, seed, news_dim=256, news_q=200, user_q=200, cfg=None,
-                     noisy=False):
+                     noisy=False, model="NAML", n_heads=16):
     """``ModelBert`` = news_encoder (bert_model + attn + dense) + user_encoder."""
     E = (cfg or {}).get("hidden_size", BERT_BASE["hidden_size"])
     sd = bert_model_state(pfx + "news_encoder.bert_model.", num_layers, seed, cfg, noisy)
     sd.update(attention_pooling_state(pfx + "news_encoder.attn.", E, news_q, seed))
     _default_linear(sd, seed, pfx + "news_encoder.dense", news_dim, E)
-    sd.update(user_encoder_state(pfx + "user_encoder.", news_dim, user_q, seed))
+    sd.update(user_encoder_state(pfx + "user_encoder.", news_dim, user_q, seed, model, n_heads))
     return sd
 
 
 def kd_model_state(num_layers, num_teachers, seed, news_dim=256, news_q=200, user_q=200,
-                   cfg=None, noisy=False):
+                   cfg=None, noisy=False, model="NAML", n_heads=16):
     """``Model`` (KD wrapper): teachers.{i} user encoders, student ModelBert,
     transform_matrix.{i}.  Key order follows the reference module order."""
     sd = {}
     for i in range(num_teachers):
-        sd.update(user_encoder_state(f"teachers.{i}.", news_dim, user_q, seed))
-    sd.update(model_bert_state("student.", num_layers, seed, news_dim, news_q, user_q, cfg, noisy))
+        sd.update(user_encoder_state(f"teachers.{i}.", news_dim, user_q, seed, model, n_heads))
+    sd.update(model_bert_state("student.", num_layers, seed, news_dim, news_q, user_q, cfg, noisy, model, n_heads))
     for i in range(num_teachers):
         b = math.sqrt(6.0 / (news_dim + news_dim))
         sd[f"transform_matrix.{i}.weight"] = _uniform(seed, f"tm{i}.w", (news_dim, news_dim), b)
