@@ -581,15 +581,13 @@ def run_eval(a):
               torch.from_numpy(cand[p0:p1]), torch.from_numpy(lab[p0:p1]))
         host_batches.append(tuple(t.pin_memory() for t in hb) + (int(np.diff(ptr[s0:s1 + 1]).max()),))
         batches.append(tuple(t.to(device) for t in hb) + (int(np.diff(ptr[s0:s1 + 1]).max()),))
-    log_vecs = torch.empty(n_imp, H, D, device=device, dtype=torch.float32)
     per = torch.zeros(n_imp, 5, device=device, dtype=torch.float64)
     sums = torch.zeros(5, device=device, dtype=torch.float64)
 
     @torch.no_grad()
     def score(bt):
         hi_t, hm_t, ptr_t, cand_t, lab_t, max_c = bt
-        dl.gather_history_vecs(table, hi_t, out=log_vecs)
-        user = ue(log_vecs, hm_t)
+        user = ue.forward_gather(table, hi_t, hm_t)      # news_scoring[log_ids] fused into the user-encoder kernel
         ops.eval_metrics(table, user, ptr_t, cand_t, lab_t, max_c, per, sums)
 
     def step(i):
@@ -613,7 +611,7 @@ def run_eval(a):
     for name, _, s_, e_ in ev:
         per_op[name] = per_op.get(name, 0.0) + s_.elapsed_time(e_) / N_BATCHES
     nnz = float(np.mean([bt[3].numel() for bt in batches]))
-    algo_bytes = {"gather_rows_f32": n_imp * H * D * 4 * 2, "user_encoder_fwd": n_imp * H * (D + 1) * 4,
+    algo_bytes = {"user_encoder_score": n_imp * H * (D + 1 + 1) * 4 + n_imp * D * 4,
                   "eval_metrics": nnz * (D * 4 + 5) + n_imp * D * 4}
     if rank == 0:
         _, peak_bw, how = peaks()
@@ -626,7 +624,7 @@ def run_eval(a):
                 "config": {"workload": EVAL_WORKLOAD["name"], "impressions_per_step": n_imp, "history": H,
                            "mean_candidates": nnz / n_imp, "table_rows": N_NEWS + 1, "news_dim": D,
                            "parallelism": f"impressions sharded x{world}",
-                           "l2": f"{N_BATCHES} rotating batches; 165 MB table + 210 MB gathered history per step > 126 MB L2"},
+                           "l2": f"{N_BATCHES} rotating batches; 165 MB table, 210 MB of history rows gathered from it per step > 126 MB L2"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "impressions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 40},
                 "gpu_launches": launches,

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TNR_ABI_VERSION 4
+#define TNR_ABI_VERSION 5
 
 const char* tnr_last_error(void);
 int tnr_abi_version(void);
@@ -159,6 +159,27 @@ typedef struct {
 } tnr_user_encoder_io;
 int tnr_user_encoder_fwd_multi(const tnr_user_encoder_io* enc, int n_enc, const float* mask, int use_mask,
                                int B, int H, int D, int Q, void* stream);
+/* One encoder with the history rows gathered inside the kernel: vecs[b,h] = table[idx[b,h]] (idx int32 [B,H];
+ * ids outside [0, n_rows) read row 0 like the loader, dataloader.py:74).  Fuses news_scoring[log_ids] with
+ * the user encoder of the scoring loop (Tiny-NewsRec/run.py:340-343, dataloader.py:292-301): the
+ * [B,H,D] gathered copy is never written.  a_out may be NULL. */
+int tnr_user_encoder_fwd_gather(const float* table, long long n_rows, const int32_t* idx, const float* mask,
+                                const float* pad_doc, const float* W1, const float* b1, const float* w2,
+                                const float* b2, int use_mask, float* user, float* a_out, int B, int H, int D,
+                                int Q, void* stream);
+/* Scoring path of the same encoder for thousands of impressions per launch (the eval loop, run.py:335-361):
+ * the fc1 contraction runs as ONE flat TF32 GEMM over all B*H history rows (persistent CTAs, each keeping one
+ * column half of W1 resident in shared memory, 256-row tiles) that emits the logits, then a warp per impression
+ * normalises and pools.  `w1_packed`: tnr_user_encoder_packed_w1_floats(D) floats filled by
+ * tnr_user_encoder_pack_w1 (re-pack when att_fc1.weight changes).  idx NULL: vecs is [B*H, D]; else vecs is the
+ * [n_rows, D] table and idx int32 [B,H] (unknown ids read row 0).  a_out [B,H] is required (it holds the logits
+ * between the two kernels).  D % 32 == 0, D <= 256, Q <= 208, H <= 64. */
+long long tnr_user_encoder_packed_w1_floats(int D);
+int tnr_user_encoder_pack_w1(const float* W1, float* packed, int D, int Q, void* stream);
+int tnr_user_encoder_score(const float* vecs, long long n_rows, const int32_t* idx, const float* mask,
+                           const float* pad_doc, const float* w1_packed, const float* b1, const float* w2,
+                           const float* b2, int use_mask, float* user, float* a_out, int B, int H, int D, int Q,
+                           void* stream);
 /* d_user [B,D] -> d_vecs += [B*H, D]; dpad/dW1/db1/dw2/db2 += (fp32 atomics).
  * scratch: fp32 [B*H*(Q+D)] workspace (grad at the fc1 pre-activation + blended inputs; dW1 is then
  * one TN GEMM over all impressions). */
@@ -190,6 +211,27 @@ int tnr_sgemm_nt(const float* A, const float* B, const float* bias, float* C, in
                  int batch, long long sA, long long sB, long long sbias, long long sC, void* stream);
 int tnr_sgemm_tn_acc(const float* A, const float* B, float* C, float* cbias, int R, int N1, int N2,
                      int batch, long long sA, long long sB, long long sC, long long sbias, void* stream);
+
+/* ------------------------------------------------- NRMS user encoder (multi-head self-attention) */
+/* The self-attention in front of the additive pooling when args.model == 'NRMS'
+ * (Tiny-NewsRec/model_bert.py:37-100; wired in at :145-148,:162-164,:171-173).  d_k = d_v = 16 (:146).
+ *   blend_fwd:  out = vecs * m + pad_doc * (1 - m)            (user_log_mask False, model_bert.py:169-170)
+ *   blend_bwd:  d_vecs += d_blend * m, dpad += sum_r d_blend (1 - m)   (mask NULL: d_vecs += d_blend)
+ *   attn_fwd:   q, k, v, ctx fp32 [B*H, n_heads*16]; s_ij = exp(q_i.k_j / 4) [* mask_j] (NO max subtraction),
+ *               ctx_i = sum_j s_ij v_j / (sum_j s_ij + 1e-8); mask fp32 [B,H] or NULL (unmasked branch)
+ *   attn_bwd:   d_ctx -> dq, dk, dv (assigned; scores recomputed)
+ * The Q/K/V projections are tnr_sgemm_nt (batch 3), their weight gradients tnr_sgemm_tn_acc, and the input
+ * gradient dX = dQ W_Q + dK W_K + dV W_V is tnr_sgemm_nn:  C[M,N] = sum_p A[p][M,K] . B[p][K,N]. */
+int tnr_nrms_blend_fwd(const float* vecs, const float* mask, const float* pad_doc, float* out, int rows, int D,
+                       void* stream);
+int tnr_nrms_blend_bwd(const float* d_blend, const float* mask, float* d_vecs, float* dpad, int rows, int D,
+                       void* stream);
+int tnr_nrms_attn_fwd(const float* q, const float* k, const float* v, const float* mask, float* ctx, int B, int H,
+                      int n_heads, void* stream);
+int tnr_nrms_attn_bwd(const float* q, const float* k, const float* v, const float* mask, const float* d_ctx,
+                      float* dq, float* dk, float* dv, int B, int H, int n_heads, void* stream);
+int tnr_sgemm_nn(const float* A, const float* B, float* C, int M, int N, int K, int parts, long long sA,
+                 long long sB, void* stream);
 
 /* ------------------------------------------------------------------ optimiser */
 /* Adam(amsgrad=True) on a flat fp32 buffer (torch.optim.Adam semantics, run.py:134) fused with

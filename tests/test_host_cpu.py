@@ -38,7 +38,7 @@ def test_library_exports_every_header_symbol(built_lib):
     assert not missing, f"declared in tinyrec.h but not exported: {missing}"
     assert sorted(L.exported_names()) == declared, "ctypes binding table and header disagree"
     lib = L.load()
-    assert lib.tnr_abi_version() == 4
+    assert lib.tnr_abi_version() == 5
 
 
 def test_ops_fail_loudly_without_cuda(built_lib):
@@ -85,6 +85,9 @@ def test_state_dict_keys_match_reference_layout():
     assert len(got) == 113
     for k in want:
         assert tuple(got[k].shape) == tuple(want[k].shape), k
+    # NRMS variant (model_bert.py:145-148): W_Q / W_K / W_V in front of the pooling, same key order as the reference
+    n = mb.Model(synth.demo_args(num_student_layers=1, num_teachers=2, model="NRMS", num_attention_heads=16))
+    assert list(n.state_dict().keys()) == list(synth.kd_model_state(1, 2, 0, model="NRMS", n_heads=16).keys())
     t = mb2.ModelBert(synth.demo_args(num_hidden_layers=2))
     assert list(t.state_dict().keys()) == list(synth.model_bert_state("", 2, 0).keys())
     # attribute paths used by run.py:101-112,285,343,442

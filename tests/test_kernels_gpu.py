@@ -555,3 +555,127 @@ def test_sgemm_tn_acc_tf32(R, N1, N2, batch):
     ref = torch.einsum("brm,brn->bmn", A.double(), Bm.double()).float()
     assert _rel_err(C - C0, ref)[0] < 1e-3
     assert _rel_err(cb - cb0, A.sum(1))[0] < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K,parts", [(1600, 256, 256, 3), (100, 72, 40, 1), (65, 200, 36, 2)])
+def test_sgemm_nn_tf32(M, N, K, parts):
+    ops = _ops()
+    f32 = torch.float32
+    A, Bm = _randn(parts, M, K, dtype=f32, seed=1), _randn(parts, K, N, dtype=f32, seed=2)
+    C = torch.full((M, N), 7.0, device="cuda")
+    ops.sgemm_nn(A, Bm, C, M, N, K, parts, M * K, K * N)
+    ref = torch.einsum("pmk,pkn->mn", A.double(), Bm.double()).float()
+    assert _rel_err(C, ref)[0] < 1e-3
+
+
+# ------------------------------------------------------------------ NRMS self-attention (model_bert.py:37-100)
+def _nrms_ref(q, k, v, mask, B, H, heads):
+    """ScaledDotProductAttention.forward restated: exp (no max subtraction), mask, / (sum + 1e-8)."""
+    sp = lambda t: t.view(B, H, heads, 16).transpose(1, 2)     # noqa: E731
+    s = torch.exp(sp(q) @ sp(k).transpose(-1, -2) / 4.0)
+    if mask is not None:
+        s = s * mask[:, None, None, :]
+    a = s / (s.sum(-1, keepdim=True) + 1e-8)
+    return (a @ sp(v)).transpose(1, 2).reshape(B * H, heads * 16)
+
+
+@pytest.mark.parametrize("with_mask", [False, True])
+@pytest.mark.parametrize("B,H,heads", [(32, 50, 16), (3, 5, 16), (2, 64, 20), (5, 33, 3)])
+def test_nrms_attention_fwd_bwd(with_mask, B, H, heads):
+    ops = _ops()
+    f32 = torch.float32
+    Dh = heads * 16
+    qkv = _randn(3, B * H, Dh, dtype=f32, seed=1, scale=0.7)
+    mask = None
+    if with_mask:
+        mask = (torch.rand(B, H, generator=torch.Generator().manual_seed(3)) > 0.4).float().cuda()
+        mask[0] = 0.0                                            # an all-masked history: ctx exactly 0
+    ctx = torch.empty(B * H, Dh, device="cuda")
+    ops.nrms_attn_fwd(qkv, mask, ctx, B, H)
+    leaf = qkv.clone().requires_grad_(True)
+    ref = _nrms_ref(leaf[0], leaf[1], leaf[2], mask, B, H, heads)
+    assert _rel_err(ctx, ref.detach())[0] < 1e-5
+    if with_mask:
+        assert float(ctx[:H].abs().max()) == 0.0
+    d_ctx = _randn(B * H, Dh, dtype=f32, seed=5)
+    ref.backward(d_ctx)
+    dqkv = torch.full_like(qkv, 9.0)
+    ops.nrms_attn_bwd(qkv, mask, d_ctx, dqkv, B, H)
+    for p, nm in enumerate("qkv"):
+        assert _rel_err(dqkv[p], leaf.grad[p])[0] < 2e-5, nm
+
+
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_nrms_blend_fwd_bwd(use_mask):
+    ops = _ops()
+    f32 = torch.float32
+    R, D = 1600, 256
+    v, pad = _randn(R, D, dtype=f32, seed=1), _randn(D, dtype=f32, seed=2)
+    m = (torch.rand(R, generator=torch.Generator().manual_seed(3)) > 0.3).float().cuda()
+    out = torch.empty(R, D, device="cuda")
+    ops.nrms_blend_fwd(v, m, pad, out)
+    assert torch.equal(out, v * m[:, None] + pad[None, :] * (1 - m[:, None]))
+    g = _randn(R, D, dtype=f32, seed=4)
+    d_v = _randn(R, D, dtype=f32, seed=5)
+    d_v0 = d_v.clone()
+    dpad = torch.zeros(D, device="cuda")
+    ops.nrms_blend_bwd(g, None if use_mask else m, d_v, dpad)
+    if use_mask:
+        assert torch.equal(d_v, d_v0 + g) and float(dpad.abs().max()) == 0.0
+    else:
+        assert torch.equal(d_v, d_v0 + g * m[:, None])
+        assert _rel_err(dpad, (g * (1 - m[:, None])).sum(0))[0] < 1e-5
+
+
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_user_encoder_gather_equals_gather_then_encode(use_mask):
+    """tnr_user_encoder_fwd_gather == tnr_gather_rows_f32 + tnr_user_encoder_fwd (same arithmetic, rows read from
+    the table instead of a gathered copy; the logit partial sums meet in shared-memory atomics, so equality is to
+    fp32 rounding, not bit for bit); unknown ids read row 0 (dataloader.py:74)."""
+    ops = _ops()
+    f32 = torch.float32
+    B, H, D, Q, N = 37, 50, 256, 200, 1000
+    table = _randn(N, D, dtype=f32, scale=0.5, seed=1)
+    idx = torch.randint(0, N, (B, H), generator=torch.Generator().manual_seed(2)).int().cuda()
+    idx[0, :3] = torch.tensor([-1, N, N + 5], dtype=torch.int32)
+    mask = (torch.rand(B, H, generator=torch.Generator().manual_seed(3)) > 0.3).float().cuda()
+    pad, W1 = _randn(D, dtype=f32, scale=0.5, seed=4), _randn(Q, D, dtype=f32, scale=0.06, seed=5)
+    b1, w2, b2 = _randn(Q, dtype=f32, scale=0.1, seed=6), _randn(Q, dtype=f32, scale=0.1, seed=7), _randn(1, dtype=f32, seed=8)
+    vecs = torch.empty(B * H, D, device="cuda")
+    ops.gather_rows_f32(table, idx.reshape(-1), vecs)
+    assert torch.equal(vecs[:3], table[0].expand(3, D))
+    u0, a0 = torch.empty(B, D, device="cuda"), torch.empty(B, H, device="cuda")
+    ops.user_encoder_fwd(vecs, mask, pad, W1, b1, w2, b2, use_mask, u0, a0, None, B, H)
+    u1, a1 = torch.empty(B, D, device="cuda"), torch.empty(B, H, device="cuda")
+    ops.user_encoder_fwd_gather(table, idx, mask, pad, W1, b1, w2, b2, use_mask, u1, a1)
+    assert _rel_err(a1, a0)[0] < 1e-5 and _rel_err(u1, u0)[0] < 1e-5
+    u2, a2 = torch.empty(B, D, device="cuda"), torch.empty(B, H, device="cuda")        # the flat scoring path
+    ops.user_encoder_score(table, idx, mask, pad, ops.user_encoder_pack_w1(W1), Q, b1, w2, b2, use_mask, u2, a2, B, H)
+    assert _rel_err(a2, a0)[0] < 1e-5 and _rel_err(u2, u0)[0] < 1e-5
+    ref_u, _, _ = _ue_ref(vecs.view(B, H, D), mask, pad, W1, b1, w2, b2, use_mask)
+    assert _rel_err(u1, ref_u)[0] < 2e-3
+
+
+@pytest.mark.parametrize("use_mask", [False, True])
+@pytest.mark.parametrize("B,H,Q", [(300, 50, 200), (65, 7, 64), (64, 64, 208)])
+def test_user_encoder_scoring_path_vs_torch(use_mask, B, H, Q):
+    """Scoring-sized batches (B >= 64) take the flat logits GEMM + pooling kernels (tnr_user_encoder_score): same result as the
+    torch fp32 restatement, incl. an all-masked history and a ragged last 64-row tile."""
+    ops = _ops()
+    f32 = torch.float32
+    D = 256
+    vecs = _randn(B, H, D, dtype=f32, scale=0.5, seed=1)
+    mask = (torch.rand(B, H, generator=torch.Generator().manual_seed(2)) > 0.3).float().cuda()
+    mask[1] = 0
+    mask[2] = 1
+    pad, W1 = _randn(D, dtype=f32, scale=0.5, seed=4), _randn(Q, D, dtype=f32, scale=0.06, seed=5)
+    b1, w2, b2 = _randn(Q, dtype=f32, scale=0.1, seed=6), _randn(Q, dtype=f32, scale=0.1, seed=7), _randn(1, dtype=f32, seed=8)
+    user, a = torch.empty(B, D, device="cuda"), torch.empty(B, H, device="cuda")
+    assert ops.user_encoder_score_supported(B, H, D, Q)
+    ops.user_encoder_score(vecs.view(B * H, D), None, mask, pad, ops.user_encoder_pack_w1(W1), Q, b1, w2, b2, use_mask,
+                           user, a, B, H)
+    ref_u, ref_a, _ = _ue_ref(vecs, mask, pad, W1, b1, w2, b2, use_mask)
+    assert _rel_err(a, ref_a)[0] < 2e-3
+    assert _rel_err(user, ref_u)[0] < 2e-3
+    if use_mask:
+        assert float(user[1].abs().max()) == 0.0

@@ -27,6 +27,16 @@ def _grad_err(name, got, ref, named):
     if name.endswith("attention.self.key.bias"):
         scale = named[name.replace("key.bias", "query.bias")].grad.float().norm().cpu()
         return float((got - ref).norm() / (scale + 1e-12))
+    if name.endswith("multi_head_self_attn.W_K.bias"):
+        # NRMS: exp(q.(k + b_K)) / sum is invariant to b_K as well (up to the 1e-8 in the denominator)
+        scale = named[name.replace("W_K.bias", "W_Q.bias")].grad.float().norm().cpu()
+        return float((got - ref).norm() / (scale + 1e-12))
+    if ".user_encoder.attn." in name and name.replace("attn." + name.split("attn.")[1], "multi_head_self_attn.W_V.weight") in named:
+        # NRMS: the self-attention averages the history, so the rows the pooling sees are nearly equal and the true
+        # gradient of the pooling parameters is ~0 (1e-10 against 1e-3 for the W_V next to it): both sides hold the
+        # bf16 noise of the news vectors.  Measure against the W_V gradient of the same encoder.
+        wv = named[name.replace("attn." + name.split("attn.")[1], "multi_head_self_attn.W_V.weight")].grad
+        return float((got - ref).norm() / (max(float(ref.norm()), float(wv.float().norm().cpu())) + 1e-12))
     if name.endswith("attn.att_fc2.bias"):
         # additive-attention weights are shift invariant too (up to the 1e-8 in the denominator)
         scale = named[name.replace("att_fc2.bias", "att_fc2.weight")].grad.float().norm().cpu()
@@ -161,6 +171,96 @@ def test_kd_gradients_vs_reference_golden(golden):
     g1 = named["transform_matrix.0.weight"].grad.clone()
     m(*inputs)[0].backward()
     assert _rel(named["transform_matrix.0.weight"].grad, 2 * g1) < 1e-3
+
+
+# ------------------------------------------------------------------ NRMS user encoder
+def _nrms_model(g, ulm):
+    import tinyrec.model_bert as mb
+    import tinyrec.synth as synth
+    layers, M = int(g["layers"]), int(g["M"])
+    H = g["history"].shape[1]
+    m = mb.Model(synth.demo_args(num_student_layers=layers, user_log_length=H, user_log_mask=ulm, num_teachers=M,
+                                 temperature=float(g["temperature"]), coef=float(g["coef"]), model="NRMS",
+                                 num_attention_heads=16))
+    m.load_state_dict(synth.kd_model_state(layers, M, int(g["seed"]), noisy=True, model="NRMS", n_heads=16), strict=True)
+    m.cuda().eval()
+    _apply_freeze(m, [0])
+    inputs = (torch.from_numpy(g["history"]).cuda(), torch.from_numpy(g["history_mask"]).cuda(),
+              torch.from_numpy(g["candidate"]).cuda(), torch.from_numpy(g["label"]).cuda(),
+              [torch.from_numpy(g[f"th{i}"]).cuda() for i in range(M)], [torch.from_numpy(g[f"tc{i}"]).cuda() for i in range(M)])
+    return m, inputs
+
+
+@pytest.mark.parametrize("tag,ulm", [("pad", False), ("mask", True)])
+def test_nrms_kd_vs_reference_golden(golden, tag, ulm):
+    """KD ``Model`` with args.model = 'NRMS' against the reference's own outputs and gradients
+    (tests/golden/nrms.npz, make_golden.py:gen_nrms): losses, scores, every trainable tensor's gradient."""
+    g = golden("nrms")
+    m, inputs = _nrms_model(g, ulm)
+    res = m(*inputs)
+    for v, nm in zip(res[:4], ("total", "distill", "emb", "target")):
+        ref = float(g[f"{nm}_{tag}"])
+        assert abs(float(v) - ref) < 1e-2 * abs(ref) + 1e-4, (nm, float(v), ref)
+    assert _rel(res[4], g[f"score_{tag}"]) < 2e-2
+    res[0].backward()
+    named = dict(m.named_parameters())
+    for k in [str(s) for s in g[f"trainable_names_{tag}"]]:
+        gr = named[k].grad
+        assert gr is not None, k
+        if f"{tag}/gfull/{k}" in g.files:
+            ref = torch.from_numpy(g[f"{tag}/gfull/{k}"])
+            r = _grad_err(k, gr.reshape(ref.shape), ref, named)
+        else:
+            ref = torch.from_numpy(g[f"{tag}/gslice/{k}"])
+            r = _grad_err(k, gr[:16, :16], ref, named)
+        assert r < 5e-2, (k, r)
+    # the stand-alone user encoder (run.py:343) gives the same user vector as the training path
+    st = m.train_state()
+    hist = st.last["news"][:inputs[0].shape[0] * inputs[0].shape[1]].view(inputs[0].shape[0], inputs[0].shape[1], -1)
+    with torch.no_grad():
+        user = m.student.user_encoder(hist, inputs[1])
+    assert _rel(user, st.last["user"]) < 1e-5
+
+
+def test_nrms_step_vs_oracle_at_demo_shape():
+    """B=8 impressions at the demo history length (H=50, 16 heads) against the CPU oracle (itself pinned on the
+    reference by tests/test_oracle_golden.py::test_nrms_kd_forward_and_gradients)."""
+    import tinyrec.model_bert as mb
+    import tinyrec.synth as synth
+    from oracle import model as om
+    B, H, K, L, M, layers, N = 8, 50, 5, 12, 2, 1, 500
+    news = synth.news_table(N, L=L, seed=1)
+    hist_idx, hmask, cand_idx, label = synth.train_impressions(B, N, H, K, seed=2)
+    tables = synth.teacher_tables(N, M, 256, seed=3)
+    history = torch.from_numpy(news[hist_idx].astype(np.int64))
+    candidate = torch.from_numpy(news[cand_idx].astype(np.int64))
+    th = [torch.from_numpy(t[hist_idx]) for t in tables]
+    tc = [torch.from_numpy(t[cand_idx]) for t in tables]
+    sd = synth.kd_model_state(layers, M, 5, noisy=True, model="NRMS", n_heads=16)
+    for ulm in (False, True):
+        args = synth.demo_args(num_student_layers=layers, num_teachers=M, user_log_length=H, model="NRMS", user_log_mask=ulm)
+        m = mb.Model(args)
+        m.load_state_dict(sd, strict=True)
+        m.cuda().eval()
+        _apply_freeze(m, [0])
+        res = m(history.cuda(), torch.from_numpy(hmask).cuda(), candidate.cuda(), torch.from_numpy(label).cuda(),
+                [t.cuda() for t in th], [t.cuda() for t in tc])
+        res[0].backward()
+        osd = {k: v.clone() for k, v in sd.items()}
+        names = [k for k, p in m.named_parameters() if p.requires_grad]
+        for k in names:
+            osd[k].requires_grad_(True)
+        ref = om.kd_model_forward(osd, history, torch.from_numpy(hmask), candidate, torch.from_numpy(label), th, tc,
+                                  layers, ulm, args.temperature, args.coef)
+        ref[0].backward()
+        assert abs(float(res[0]) - float(ref[0])) < 1e-2 * abs(float(ref[0])) + 1e-4
+        assert _rel(res[4], ref[4].detach()) < 2e-2
+        named = dict(m.named_parameters())
+        for k in names:
+            if osd[k].grad is None:                 # pad_doc in the user_log_mask branch
+                assert float(named[k].grad.abs().max()) == 0.0, k
+                continue
+            assert _grad_err(k, named[k].grad, osd[k].grad, named) < 5e-2, k
 
 
 def test_kd_step_vs_oracle_at_demo_shape():

@@ -59,11 +59,20 @@ _SIGNATURES = {
     "tnr_attnpool_bwd": ([P, P, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_int, P], c_int),
     "tnr_user_encoder_fwd": ([P, P, P, P, P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "tnr_user_encoder_fwd_multi": ([P, c_int, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "tnr_user_encoder_fwd_gather": ([P, c_int64, P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, P], c_int),
+    "tnr_user_encoder_packed_w1_floats": ([c_int], c_int64),
+    "tnr_user_encoder_pack_w1": ([P, P, c_int, c_int, P], c_int),
+    "tnr_user_encoder_score": ([P, c_int64, P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "tnr_user_encoder_bwd": ([P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "tnr_kd_loss_fwdbwd": ([P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P, P],
                            c_int),
     "tnr_sgemm_nt": ([P, P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, P], c_int),
     "tnr_sgemm_tn_acc": ([P, P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int64, c_int64, P], c_int),
+    "tnr_nrms_blend_fwd": ([P, P, P, P, c_int, c_int, P], c_int),
+    "tnr_nrms_blend_bwd": ([P, P, P, P, c_int, c_int, P], c_int),
+    "tnr_nrms_attn_fwd": ([P, P, P, P, P, c_int, c_int, c_int, P], c_int),
+    "tnr_nrms_attn_bwd": ([P, P, P, P, P, P, P, P, c_int, c_int, c_int, P], c_int),
+    "tnr_sgemm_nn": ([P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, P], c_int),
     "tnr_adam_amsgrad": ([P, P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, c_float, P], c_int),
     "tnr_cast_f32_bf16": ([P, P, c_int64, P], c_int),
     "tnr_gather_rows_i32_i64": ([P, c_int64, P, c_int64, c_int, P, P], c_int),
@@ -94,7 +103,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res
-    if lib.tnr_abi_version() != 4:
+    if lib.tnr_abi_version() != 5:
         raise TinyRecError("libtinyrec.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

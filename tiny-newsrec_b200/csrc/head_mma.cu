@@ -12,10 +12,15 @@
 
 namespace tnr {
 
-__device__ __forceinline__ uint32_t f2tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
+// fp32 -> TF32, round to nearest (ties away), as cvt.rna.tf32.f32 -- which ptxas expands to ~8 instructions on
+// sm_100 (FSETP |x| < inf, three PLOP3, a predicated IADD, LOP3).  Adding half a TF32 ulp to the magnitude bits is
+// the same rounding for every finite input (inf stays inf, NaN stays NaN) and the tensor core ignores the low 13
+// bits of a .tf32 operand, so one IADD does it.
+__device__ __forceinline__ uint32_t f2tf32(float x) { return __float_as_uint(x) + 0x1000u; }
+// tanh(x) = 1 - 2 / (1 + e^{2x}): 5 instructions against ~25 for tanhf (64 evaluations per thread made the
+// epilogue a third of the kernel); absolute error < 3e-7, saturates to +-1 exactly for large |x|.
+__device__ __forceinline__ float tanh_exp(float x) {
+  return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -186,16 +191,25 @@ sgemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float
 // user encoders, forward.  grid (B, n_enc): block (b, i) handles impression b of encoder i.
 //   blend (use_mask == 0): v = vec*m + pad_doc*(1-m); alpha unmasked
 //   mask  (use_mask == 1): v = vec;  alpha *= m
-//   e = tanh(v W1^T + b1) [H, Q] (TF32 mma, W1 fragments straight from L2); alpha = exp(e.w2 + b2)
+//   e = tanh(v W1^T + b1) [H, Q] (TF32 mma); alpha = exp(e.w2 + b2)
 //   a = alpha / (sum + 1e-8); user = sum_h a_h v_h   (fp32)
+// W1 is streamed through shared memory in 16-column chunks (cp.async, double buffered; ~100 KB per block so two
+// blocks share an SM and one computes while the other waits).  v1 pulled the W1 fragments straight from L2 into
+// registers one k-step ahead: a dependent ~700-cycle load per k-step made the eval-scoring launch (4 096
+// impressions) latency-bound at 519 us.  With `idx` the history rows are gathered from the news table inside the
+// kernel (run.py:340-343 reads news_scoring[idx] and feeds the user encoder): no [B,H,D] intermediate.
 // ----------------------------------------------------------------------------------
 constexpr int UE_THREADS = 256;
 constexpr int UE_HMAX = 64;
 constexpr int UE_MAX_ENC = 9;
+constexpr int UE_KC = 16;             // W1 chunk width (k)
+constexpr int UE_WS = UE_KC + 4;      // padded chunk row: conflict-free fragment reads
 
 struct UeFwdParams {
   tnr_user_encoder_io enc[UE_MAX_ENC];
   const float* mask;
+  const int32_t* idx;                 // optional [B,H] row ids into enc[*].vecs (then a [n_rows, D] table)
+  long long n_rows;
   int use_mask, H, D, Q;
 };
 
@@ -209,22 +223,58 @@ user_encoder_fwd_kernel(const __grid_constant__ UeFwdParams p) {
   __shared__ float s_inv;
   const tnr_user_encoder_io io = p.enc[blockIdx.y];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  for (int i = tid; i < UE_HMAX * (D / 4); i += UE_THREADS) {
-    const int h = i / (D / 4), d = (i - h * (D / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (h < H) {
-      v = *reinterpret_cast<const float4*>(io.vecs + ((size_t)b * H + h) * D + d);
-      if (!p.use_mask) {
-        const float m = p.mask[(size_t)b * H + h];
-        const float4 pd = *reinterpret_cast<const float4*>(io.pad_doc + d);
-        v.x = v.x * m + pd.x * (1.0f - m); v.y = v.y * m + pd.y * (1.0f - m);
-        v.z = v.z * m + pd.z * (1.0f - m); v.w = v.w * m + pd.w * (1.0f - m);
+  constexpr int QT = 256;                      // all 32 n-tiles staged (rows >= Q zero-filled): no predicates in the k loop
+  float* sW = sz + UE_HMAX;                    // [2][QT][UE_WS]
+  auto load_w = [&](int st, int kc) {
+    float* dst = sW + st * QT * UE_WS;
+    for (int i = tid; i < QT * (UE_KC / 4); i += UE_THREADS) {
+      const int q = i >> 2, c = (i & 3) * 4;
+      const bool ok = q < Q;
+      cp_async16_zfill(dst + q * UE_WS + c, io.W1 + (size_t)(ok ? q : 0) * D + kc * UE_KC + c, ok);
+    }
+    cp_async_commit();
+  };
+  load_w(0, 0);
+  // input tile: warp w stages rows w, w + 8, ... (all eight rows of a warp in flight at once), blended if
+  // !use_mask and ROUNDED TO TF32 ONCE here (every warp reads every A fragment: converting in the k loop
+  // cost 8x the cvt work, and cvt.rna.tf32 is a 3-instruction emulation on sm_100).  The fp32 rows are
+  // read again (from L2) for the final weighted sum, so the user vector keeps full fp32 inputs.
+  size_t* srow = reinterpret_cast<size_t*>(sW + 2 * QT * UE_WS);     // [64] row offsets into io.vecs
+  {
+    const int D4 = D >> 2;
+    size_t rows[UE_HMAX / 8];
+#pragma unroll
+    for (int j = 0; j < UE_HMAX / 8; ++j) {
+      const int h = warp + 8 * j;
+      size_t row = (size_t)b * H + (h < H ? h : 0);
+      if (p.idx != nullptr) {
+        const long long r = p.idx[row];
+        row = (r >= 0 && r < p.n_rows) ? (size_t)r : 0;         // unknown id -> row 0 (dataloader.py:74)
+      }
+      rows[j] = row * D;
+      if (lane == 0) srow[h] = rows[j];
+    }
+    for (int d4 = lane; d4 < D4; d4 += 32) {
+      float4 v[UE_HMAX / 8];
+#pragma unroll
+      for (int j = 0; j < UE_HMAX / 8; ++j)
+        v[j] = (warp + 8 * j < H) ? *reinterpret_cast<const float4*>(io.vecs + rows[j] + d4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 pd = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!p.use_mask) pd = *reinterpret_cast<const float4*>(io.pad_doc + d4 * 4);
+#pragma unroll
+      for (int j = 0; j < UE_HMAX / 8; ++j) {
+        const int h = warp + 8 * j;
+        float4 x = v[j];
+        if (!p.use_mask && h < H) {
+          const float m = p.mask[(size_t)b * H + h], om = 1.0f - m;
+          x.x = x.x * m + pd.x * om; x.y = x.y * m + pd.y * om; x.z = x.z * m + pd.z * om; x.w = x.w * m + pd.w * om;
+        }
+        uint4 tq = make_uint4(f2tf32(x.x), f2tf32(x.y), f2tf32(x.z), f2tf32(x.w));
+        *reinterpret_cast<uint4*>(sv + h * DS + d4 * 4) = tq;
       }
     }
-    *reinterpret_cast<float4*>(sv + h * DS + d) = v;
   }
   if (tid < UE_HMAX) slog[tid] = 0.f;
-  __syncthreads();
   const int MT = (H + 15) >> 4;
   float acc[4][4][4];
 #pragma unroll
@@ -234,38 +284,32 @@ user_encoder_fwd_kernel(const __grid_constant__ UeFwdParams p) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[mt][i][c] = 0.f;
   // warp w owns n-tiles w, w+8, w+16, w+24 (Q <= 256)
-  const float* wrow[4];
-  bool wv[4];
+  const int NK = D / UE_KC;
+  for (int kc = 0; kc < NK; ++kc) {
+    if (kc + 1 < NK) { load_w((kc + 1) & 1, kc + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();                           // chunk kc landed for everyone (first pass: the input tile too)
+    const float* w = sW + (kc & 1) * QT * UE_WS;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int q = (warp + 8 * i) * 8 + g;
-    wv[i] = q < Q;
-    wrow[i] = io.W1 + (size_t)(wv[i] ? q : 0) * D + t;
-  }
-  float bn[4][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { bn[i][0] = wv[i] ? __ldg(wrow[i]) : 0.f; bn[i][1] = wv[i] ? __ldg(wrow[i] + 4) : 0.f; }
-  for (int ks = 0; ks < D / 8; ++ks) {
-    uint32_t bf[4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { bf[i][0] = f2tf32(bn[i][0]); bf[i][1] = f2tf32(bn[i][1]); }
-    if (ks + 1 < D / 8) {
+    for (int k8 = 0; k8 < UE_KC / 8; ++k8) {
+      uint32_t bf[4][2];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        bn[i][0] = wv[i] ? __ldg(wrow[i] + (ks + 1) * 8) : 0.f;
-        bn[i][1] = wv[i] ? __ldg(wrow[i] + (ks + 1) * 8 + 4) : 0.f;
+        const float* wr = w + ((warp + 8 * i) * 8 + g) * UE_WS + k8 * 8 + t;
+        bf[i][0] = f2tf32(wr[0]);
+        bf[i][1] = f2tf32(wr[4]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        if (mt < MT) {                           // block-uniform
+          uint32_t a[4];
+          const uint32_t* r0 = reinterpret_cast<const uint32_t*>(sv) + (mt * 16 + g) * DS + kc * UE_KC + k8 * 8 + t;
+          a[0] = r0[0]; a[1] = r0[8 * DS]; a[2] = r0[4]; a[3] = r0[8 * DS + 4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mma_tf32(acc[mt][i], a, bf[i][0], bf[i][1]);    // n-tiles past Q multiply zeros
+        }
       }
     }
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-      if (mt < MT) {
-        uint32_t a[4];
-        const float* r0 = sv + (mt * 16 + g) * DS + ks * 8 + t;
-        a[0] = f2tf32(r0[0]); a[1] = f2tf32(r0[8 * DS]); a[2] = f2tf32(r0[4]); a[3] = f2tf32(r0[8 * DS + 4]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) mma_tf32(acc[mt][i], a, bf[i][0], bf[i][1]);
-      }
-    }
+    __syncthreads();                           // everyone is done with this stage before it is refilled
   }
   // epilogue: e = tanh(acc + b1); partial logits
   float lp[4][2];
@@ -284,7 +328,7 @@ user_encoder_fwd_kernel(const __grid_constant__ UeFwdParams p) {
 #pragma unroll
         for (int hi = 0; hi < 2; ++hi) {
           const int h = mt * 16 + g + hi * 8;
-          const float ev = tanhf(acc[mt][i][hi * 2 + e] + bq);
+          const float ev = tanh_exp(acc[mt][i][hi * 2 + e] + bq);
           lp[mt][hi] = fmaf(ev, wq, lp[mt][hi]);
           if (io.e_out != nullptr && h < H) io.e_out[((size_t)b * H + h) * Q + q] = ev;
         }
@@ -317,12 +361,296 @@ user_encoder_fwd_kernel(const __grid_constant__ UeFwdParams p) {
   }
   __syncthreads();
   const float inv = s_inv;
-  if (tid < H) io.a_out[(size_t)b * H + tid] = sz[tid] * inv;
-  for (int d = tid; d < D; d += UE_THREADS) {
+  if (tid < H && io.a_out != nullptr) io.a_out[(size_t)b * H + tid] = sz[tid] * inv;
+  for (int d = tid; d < D; d += UE_THREADS) {     // fp32 rows again (L2-hot): sv holds their TF32 roundings
     float u = 0.f;
-    for (int h = 0; h < H; ++h) u = fmaf(sz[h] * inv, sv[h * DS + d], u);
+    const float pd = p.use_mask ? 0.f : io.pad_doc[d];
+#pragma unroll 10
+    for (int h = 0; h < H; ++h) {
+      float x = io.vecs[srow[h] + d];
+      if (!p.use_mask) {
+        const float m = p.mask[(size_t)b * H + h];
+        x = x * m + pd * (1.0f - m);
+      }
+      u = fmaf(sz[h] * inv, x, u);
+    }
     io.user[(size_t)b * D + d] = u;
   }
+}
+
+// ----------------------------------------------------------------------------------
+// user encoder forward for SCORING (one encoder, thousands of impressions, no e_out): two kernels.
+//   (1) ue_logits_kernel: logit[r] = w2 . tanh(W1 x_r + b1) as ONE flat GEMM over all R = B * H history rows.
+//       Persistent, one CTA per SM, W1 RESIDENT in shared memory: CTA c keeps column half (c & 1) of W1 (104 of
+//       the 208 padded columns, TF32-rounded, 108 KB, one cp.async.bulk) and walks the 256-row tiles
+//       (c >> 1), (c >> 1) + 74, ...; the two halves of a row's logit meet in a global fp32 atomicAdd (two
+//       addends: order-free).  The history rows are gathered from the news table by index inside the kernel
+//       (cp.async, 128-byte pieces, 3-stage ring that runs on across tile boundaries) and blended with pad_doc
+//       at fragment-load time.  What this replaced, measured on the 4 096-impression eval step:
+//         v1 per-impression kernel, W1 fragments from L2 per k-step ......................... 519 us
+//         v2 the same with W1 chunks staged by cp.async, TF32 rounding by IADD .............. 463 us
+//         v3 flat GEMM, 64-row tiles, W1 chunks re-streamed per tile (852 MB of L2 reads) ... 545 us
+//       -- every one of them waits on W1 traffic (40 % of the stall samples at the chunk wait): the cure is not a
+//       better pipeline but not moving W1 at all.
+//   (2) ue_pool_kernel: warp per impression, alpha = exp(logit + b2) [* mask], a = alpha / (sum + 1e-8),
+//       user = sum_h a_h x_h over the fp32 rows (gathered again; HBM / L2 bound).
+// ----------------------------------------------------------------------------------
+constexpr int UL_ROWS = 256, UL_THREADS = 256, UL_NT = 13, UL_HALF = UL_NT * 8, UL_QT = 2 * UL_HALF, UL_STAGES = 3;
+constexpr int UL_KC = 32, UL_XS = UL_KC + 4;        // X chunk: 32 columns (one 128-byte line per row), padded rows
+constexpr int UL_DMAX = 256;
+
+struct UlParams {
+  const float* vecs;          // [R, D] rows, or the [n_rows, D] table when idx != nullptr
+  const int32_t* idx;         // [R] or nullptr
+  long long n_rows;
+  const float *mask, *pad, *W1, *b1, *w2;     // W1: the PACKED copy (ue_pack_w1_kernel)
+  float* logits;              // [R], zero-initialised
+  int R, D, Q;
+};
+
+// Wp[half][q][D + 4] = tf32(W1[half * 104 + q][d]) for d < D and half * 104 + q < Q, else 0: each half is one
+// contiguous block already in the padded shared-memory layout (conflict-free B-fragment reads) and already rounded.
+__global__ void ue_pack_w1_kernel(const float* __restrict__ W1, float* __restrict__ Wp, int D, int Q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int DS = D + 4;
+  if (i >= UL_QT * DS) return;
+  const int d = i % DS, q = i / DS;
+  float v = 0.f;
+  if (d < D && q < Q) v = __uint_as_float(f2tf32(W1[(size_t)q * D + d]) & 0xffffe000u);
+  Wp[i] = v;
+}
+
+__device__ __forceinline__ void hm_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void hm_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hm_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "HM_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra HM_DONE;\n\t"
+      "bra HM_WAIT;\n\t"
+      "HM_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void hm_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <bool BLEND>
+__global__ void __launch_bounds__(UL_THREADS, 1)
+ue_logits_kernel(const __grid_constant__ UlParams p) {
+  extern __shared__ __align__(128) float sm[];
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int D = p.D, Q = p.Q, DS = D + 4;
+  float* sW = sm;                                        // [104][D + 4]   resident half of W1 (bulk-copy destination)
+  float* sX = sW + UL_HALF * DS;                         // [STAGES][256][UL_XS]
+  float* sB1 = sX + UL_STAGES * UL_ROWS * UL_XS;         // [104]
+  float* sW2 = sB1 + UL_HALF;                            // [104]
+  float* sPad = sW2 + UL_HALF;                           // [D]    (BLEND)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int half = blockIdx.x & 1;
+  const int n_tiles = (p.R + UL_ROWS - 1) / UL_ROWS;
+  const int tile0 = blockIdx.x >> 1, tstride = gridDim.x >> 1;
+  const int my_tiles = tile0 < n_tiles ? (n_tiles - tile0 + tstride - 1) / tstride : 0;
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+  if (tid == 0) {
+    hm_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)(UL_HALF * DS * 4);
+    hm_mbar_expect_tx(bar, bytes);
+    hm_bulk_g2s((uint32_t)__cvta_generic_to_shared(sW), p.W1 + (size_t)half * UL_HALF * DS, bytes, bar);
+  }
+  for (int q = tid; q < UL_HALF; q += UL_THREADS) {
+    const int col = half * UL_HALF + q;
+    sB1[q] = col < Q ? p.b1[col] : 0.f;
+    sW2[q] = col < Q ? p.w2[col] : 0.f;
+  }
+  if (BLEND)
+    for (int d = tid; d < D; d += UL_THREADS) sPad[d] = p.pad[d];
+  const int NK = D / UL_KC;
+  const int n_items = my_tiles * NK;                     // (tile, k chunk) pairs of this CTA, in order
+  // loader state: thread copies piece (tid & 7) of rows (tid >> 3) + 32 i of the tile being LOADED
+  const float* xsrc[8];
+  unsigned xok = 0;
+  auto set_tile = [&](int tl) {
+    const int r0 = (tile0 + tl * tstride) * UL_ROWS;
+    xok = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + (tid >> 3) + 32 * i;
+      // Rows with mask == 0 are not read at all: they pool with weight 0 (use_mask) or blend to pad_doc exactly
+      // (v * 0 + pad * 1), and they are the front padding of short histories -- index 0 for half of all (b, h) at
+      // MIND's history lengths, i.e. one 1 KB table row hammered by every SM through L2 (cp.async.cg bypasses L1):
+      // that hot line, not the GEMM, set the time of every version of this kernel (~500 us -> 190 us without it).
+      const bool ok = r < p.R && p.mask[r] != 0.f;
+      size_t src = ok ? (size_t)r : 0;
+      if (p.idx != nullptr && ok) {
+        const long long v = p.idx[r];
+        src = (v >= 0 && v < p.n_rows) ? (size_t)v : 0;  // unknown id -> row 0 (dataloader.py:74)
+      }
+      xsrc[i] = p.vecs + src * D + (tid & 7) * 4;
+      xok |= (ok ? 1u : 0u) << i;
+    }
+  };
+  auto load = [&](int item) {
+    if (item < n_items) {
+      const int tl = item / NK, kc = item - tl * NK;
+      if (kc == 0) set_tile(tl);
+      float* dx = sX + (item % UL_STAGES) * UL_ROWS * UL_XS;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        cp_async16_zfill(dx + ((tid >> 3) + 32 * i) * UL_XS + (tid & 7) * 4, xsrc[i] + kc * UL_KC, (xok >> i) & 1u);
+    }
+    cp_async_commit();
+  };
+  load(0);
+  load(1);
+  float acc[2][UL_NT][4];
+  float rm[2][2], rom[2][2];                             // row mask and 1 - mask of this thread's 4 rows (BLEND)
+  hm_mbar_wait(bar, 0);                                  // W1 half resident
+  for (int item = 0; item < n_items; ++item) {
+    const int tl = item / NK, kc = item - tl * NK;
+    const int r0 = (tile0 + tl * tstride) * UL_ROWS;
+    cp_async_wait<1>();                                  // this thread's X pieces of this item
+    __syncthreads();                                     // everyone's pieces; everyone is done with item - 1
+    load(item + 2);
+    if (kc == 0) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < UL_NT; ++nt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
+      if (BLEND) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int hi = 0; hi < 2; ++hi) {
+            const int r = r0 + warp * 32 + mt * 16 + g + hi * 8;
+            rm[mt][hi] = r < p.R ? p.mask[r] : 0.f;
+            rom[mt][hi] = 1.0f - rm[mt][hi];
+          }
+      }
+    }
+    const float* xs = sX + (item % UL_STAGES) * UL_ROWS * UL_XS;
+    const uint32_t* ws = reinterpret_cast<const uint32_t*>(sW) + kc * UL_KC;
+#pragma unroll
+    for (int k8 = 0; k8 < UL_KC / 8; ++k8) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float* r = xs + (warp * 32 + mt * 16 + g) * UL_XS + k8 * 8 + t;
+        float x0 = r[0], x1 = r[8 * UL_XS], x2 = r[4], x3 = r[8 * UL_XS + 4];
+        if (BLEND) {
+          const float p0 = sPad[kc * UL_KC + k8 * 8 + t], p1 = sPad[kc * UL_KC + k8 * 8 + t + 4];
+          x0 = x0 * rm[mt][0] + p0 * rom[mt][0]; x1 = x1 * rm[mt][1] + p0 * rom[mt][1];
+          x2 = x2 * rm[mt][0] + p1 * rom[mt][0]; x3 = x3 * rm[mt][1] + p1 * rom[mt][1];
+        }
+        a[mt][0] = f2tf32(x0); a[mt][1] = f2tf32(x1); a[mt][2] = f2tf32(x2); a[mt][3] = f2tf32(x3);
+      }
+#pragma unroll
+      for (int nt = 0; nt < UL_NT; ++nt) {
+        const uint32_t* wr = ws + (nt * 8 + g) * DS + k8 * 8 + t;
+        const uint32_t b0 = wr[0], b1 = wr[4];
+        mma_tf32(acc[0][nt], a[0], b0, b1);
+        mma_tf32(acc[1][nt], a[1], b0, b1);
+      }
+    }
+    if (kc == NK - 1) {
+      // tile epilogue: this thread's 4 rows over its 26 columns, then the t-quad, then the other column half (atomic)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hi = 0; hi < 2; ++hi) {
+          float part = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < UL_NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = nt * 8 + 2 * t + e;
+              part = fmaf(tanh_exp(acc[mt][nt][hi * 2 + e] + sB1[col]), sW2[col], part);
+            }
+          part += __shfl_xor_sync(0xffffffffu, part, 1);
+          part += __shfl_xor_sync(0xffffffffu, part, 2);
+          const int r = r0 + warp * 32 + mt * 16 + g + hi * 8;
+          if (t == 0 && r < p.R) atomicAdd(p.logits + r, part);
+        }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+constexpr int UP_WARPS = 4;
+template <bool BLEND>
+__global__ void __launch_bounds__(UP_WARPS * 32)
+ue_pool_kernel(const float* __restrict__ vecs, const int32_t* __restrict__ idx, long long n_rows,
+               const float* __restrict__ mask, const float* __restrict__ pad, const float* __restrict__ b2,
+               int use_mask, float* __restrict__ logits_a, float* __restrict__ user, int B, int H, int D) {
+  __shared__ float s_al[UP_WARPS][UE_HMAX];
+  __shared__ float s_m[UP_WARPS][UE_HMAX];
+  __shared__ size_t s_row[UP_WARPS][UE_HMAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * UP_WARPS + warp;
+  if (b >= B) return;
+  const float bias2 = b2[0];
+  float part = 0.f;
+  for (int h = lane; h < H; h += 32) {
+    const size_t r = (size_t)b * H + h;
+    float al = __expf(logits_a[r] + bias2);
+    const float m = mask[r];
+    if (use_mask) al *= m;
+    part += al;
+    s_al[warp][h] = al;
+    s_m[warp][h] = m;
+    size_t src = r;
+    if (idx != nullptr) {
+      const long long v = idx[r];
+      src = (v >= 0 && v < n_rows) ? (size_t)v : 0;
+    }
+    s_row[warp][h] = src * D;
+  }
+  part = warp_sum(part);
+  const float inv = 1.0f / (part + 1e-8f);
+  __syncwarp();
+  for (int h = lane; h < H; h += 32) logits_a[(size_t)b * H + h] = s_al[warp][h] * inv;      // a_out
+  const int NV = (D + 127) >> 7;                          // float4 per lane and row (D % 4 == 0, D <= 1024)
+  const int D4 = D >> 2;
+  float4 acc[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 pd[8];
+  if (BLEND) {
+#pragma unroll
+    for (int v = 0; v < 8; ++v)
+      if (v < NV && v * 32 + lane < D4) pd[v] = *reinterpret_cast<const float4*>(pad + (v * 32 + lane) * 4);
+  }
+#pragma unroll 5
+  for (int h = 0; h < H; ++h) {
+    const float a = s_al[warp][h] * inv;
+    const float* row = vecs + s_row[warp][h];
+    const float m = s_m[warp][h], om = 1.0f - m;
+    if (!BLEND && m == 0.f) continue;                     // weight exactly 0 (padding rows: index 0, a hot line)
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      if (v < NV && v * 32 + lane < D4) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m != 0.f) x = *reinterpret_cast<const float4*>(row + (v * 32 + lane) * 4);
+        if (BLEND) {
+          x.x = x.x * m + pd[v].x * om; x.y = x.y * m + pd[v].y * om;
+          x.z = x.z * m + pd[v].z * om; x.w = x.w * m + pd[v].w * om;
+        }
+        acc[v].x = fmaf(a, x.x, acc[v].x); acc[v].y = fmaf(a, x.y, acc[v].y);
+        acc[v].z = fmaf(a, x.z, acc[v].z); acc[v].w = fmaf(a, x.w, acc[v].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 8; ++v)
+    if (v < NV && v * 32 + lane < D4) *reinterpret_cast<float4*>(user + (size_t)b * D + (v * 32 + lane) * 4) = acc[v];
 }
 
 // ----------------------------------------------------------------------------------
@@ -527,24 +855,41 @@ static int ue_check(const char* who, int H, int D, int Q) {
   return 0;
 }
 
-TNR_API int tnr_user_encoder_fwd_multi(const tnr_user_encoder_io* enc, int n_enc, const float* mask, int use_mask, int B,
-                                       int H, int D, int Q, void* stream) {
+static int ue_fwd_launch(const tnr_user_encoder_io* enc, int n_enc, const float* mask, const int32_t* idx, long long n_rows,
+                         int use_mask, int B, int H, int D, int Q, cudaStream_t st) {
   if (ue_check("tnr_user_encoder_fwd", H, D, Q)) return 1;
+  TNR_REQUIRE(D % UE_KC == 0, "tnr_user_encoder_fwd: D=%d must be a multiple of %d", D, UE_KC);
   TNR_REQUIRE(n_enc >= 1 && n_enc <= UE_MAX_ENC, "tnr_user_encoder_fwd_multi: n_enc=%d out of range (1..%d)", n_enc, UE_MAX_ENC);
   if (B == 0) return 0;
   UeFwdParams p;
   for (int i = 0; i < n_enc; ++i) p.enc[i] = enc[i];
   for (int i = n_enc; i < UE_MAX_ENC; ++i) p.enc[i] = enc[0];
-  p.mask = mask; p.use_mask = use_mask; p.H = H; p.D = D; p.Q = Q;
-  const int smem = (UE_HMAX * (D + 4) + 2 * UE_HMAX) * 4;
+  p.mask = mask; p.idx = idx; p.n_rows = n_rows; p.use_mask = use_mask; p.H = H; p.D = D; p.Q = Q;
+  const int smem = (UE_HMAX * (D + 4) + 2 * UE_HMAX + 2 * 256 * UE_WS) * 4 + UE_HMAX * 8;
   static int attr_smem = 0;
   if (smem > attr_smem) {
     TNR_CHECK_CUDA(cudaFuncSetAttribute(user_encoder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  user_encoder_fwd_kernel<<<dim3(B, n_enc), UE_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  user_encoder_fwd_kernel<<<dim3(B, n_enc), UE_THREADS, smem, st>>>(p);
   TNR_LAUNCH_CHECK();
   return 0;
+}
+
+TNR_API int tnr_user_encoder_fwd_multi(const tnr_user_encoder_io* enc, int n_enc, const float* mask, int use_mask, int B,
+                                       int H, int D, int Q, void* stream) {
+  return ue_fwd_launch(enc, n_enc, mask, nullptr, 0, use_mask, B, H, D, Q, reinterpret_cast<cudaStream_t>(stream));
+}
+
+TNR_API int tnr_user_encoder_fwd_gather(const float* table, long long n_rows, const int32_t* idx, const float* mask,
+                                        const float* pad_doc, const float* W1, const float* b1, const float* w2,
+                                        const float* b2, int use_mask, float* user, float* a_out, int B, int H, int D,
+                                        int Q, void* stream) {
+  TNR_REQUIRE(idx != nullptr && n_rows >= 1, "tnr_user_encoder_fwd_gather: idx and a non-empty table are required");
+  tnr_user_encoder_io io;
+  io.vecs = table; io.pad_doc = pad_doc; io.W1 = W1; io.b1 = b1; io.w2 = w2; io.b2 = b2;
+  io.user = user; io.a_out = a_out; io.e_out = nullptr;
+  return ue_fwd_launch(&io, 1, mask, idx, n_rows, use_mask, B, H, D, Q, reinterpret_cast<cudaStream_t>(stream));
 }
 
 TNR_API int tnr_user_encoder_fwd(const float* vecs, const float* mask, const float* pad_doc, const float* W1,
@@ -554,6 +899,64 @@ TNR_API int tnr_user_encoder_fwd(const float* vecs, const float* mask, const flo
   io.vecs = vecs; io.pad_doc = pad_doc; io.W1 = W1; io.b1 = b1; io.w2 = w2; io.b2 = b2;
   io.user = user; io.a_out = a_out; io.e_out = e_out;
   return tnr_user_encoder_fwd_multi(&io, 1, mask, use_mask, B, H, D, Q, stream);
+}
+
+// ---- scoring path: flat logits GEMM + per-impression pooling (see ue_logits_kernel) -------------------
+static int ue_score_check(const char* who, int H, int D, int Q) {
+  TNR_REQUIRE(H >= 1 && H <= UE_HMAX, "%s: history length %d not supported (1..%d)", who, H, UE_HMAX);
+  TNR_REQUIRE(D % UL_KC == 0 && D >= UL_KC && D <= UL_DMAX, "%s: D=%d must be a multiple of %d in %d..%d", who, D, UL_KC, UL_KC, UL_DMAX);
+  TNR_REQUIRE(Q >= 1 && Q <= UL_QT, "%s: query dim %d not supported (1..%d)", who, Q, UL_QT);
+  return 0;
+}
+
+TNR_API long long tnr_user_encoder_packed_w1_floats(int D) { return (long long)UL_QT * (D + 4); }
+
+TNR_API int tnr_user_encoder_pack_w1(const float* W1, float* packed, int D, int Q, void* stream) {
+  if (ue_score_check("tnr_user_encoder_pack_w1", 1, D, Q)) return 1;
+  TNR_REQUIRE((uintptr_t)packed % 16 == 0, "tnr_user_encoder_pack_w1: packed must be 16-byte aligned");
+  const int total = UL_QT * (D + 4);
+  ue_pack_w1_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(W1, packed, D, Q);
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
+
+TNR_API int tnr_user_encoder_score(const float* vecs, long long n_rows, const int32_t* idx, const float* mask,
+                                   const float* pad_doc, const float* w1_packed, const float* b1, const float* w2,
+                                   const float* b2, int use_mask, float* user, float* a_out, int B, int H, int D, int Q,
+                                   void* stream) {
+  if (ue_score_check("tnr_user_encoder_score", H, D, Q)) return 1;
+  TNR_REQUIRE(a_out != nullptr && user != nullptr && w1_packed != nullptr && (uintptr_t)w1_packed % 16 == 0,
+              "tnr_user_encoder_score: a_out [B,H] (logits workspace), user and a 16-byte aligned packed W1 are required");
+  TNR_REQUIRE(idx == nullptr || n_rows >= 1, "tnr_user_encoder_score: empty table");
+  if (B == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  UlParams p;
+  p.vecs = vecs; p.idx = idx; p.n_rows = n_rows; p.mask = mask; p.pad = pad_doc; p.W1 = w1_packed; p.b1 = b1; p.w2 = w2;
+  p.logits = a_out; p.R = B * H; p.D = D; p.Q = Q;
+  const int smem = (UL_HALF * (D + 4) + UL_STAGES * UL_ROWS * UL_XS + 2 * UL_HALF + D) * 4;
+  static bool attr = false;
+  if (!attr) {
+    const int max_smem = (UL_HALF * (UL_DMAX + 4) + UL_STAGES * UL_ROWS * UL_XS + 2 * UL_HALF + UL_DMAX) * 4;
+    TNR_CHECK_CUDA(cudaFuncSetAttribute(ue_logits_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    TNR_CHECK_CUDA(cudaFuncSetAttribute(ue_logits_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    attr = true;
+  }
+  TNR_CHECK_CUDA(cudaMemsetAsync(a_out, 0, (size_t)B * H * sizeof(float), st));     // the two column halves add into it
+  const int n_tiles = (p.R + UL_ROWS - 1) / UL_ROWS;
+  const int pairs = n_tiles < num_sms() / 2 ? n_tiles : num_sms() / 2;
+  const int grid = 2 * pairs;
+  const int pgrid = (B + UP_WARPS - 1) / UP_WARPS;
+  if (use_mask) {
+    ue_logits_kernel<false><<<grid, UL_THREADS, smem, st>>>(p);
+    TNR_LAUNCH_CHECK();
+    ue_pool_kernel<false><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad_doc, b2, 1, a_out, user, B, H, D);
+  } else {
+    ue_logits_kernel<true><<<grid, UL_THREADS, smem, st>>>(p);
+    TNR_LAUNCH_CHECK();
+    ue_pool_kernel<true><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad_doc, b2, 0, a_out, user, B, H, D);
+  }
+  TNR_LAUNCH_CHECK();
+  return 0;
 }
 
 TNR_API int tnr_user_encoder_bwd(const float* vecs, const float* mask, const float* pad_doc, const float* W1,

@@ -174,27 +174,123 @@ class NewsEncoder(nn.Module):
         return out
 
 
+class MultiHeadSelfAttention(_Holder):
+    """model_bert.py:63-100: parameter holder for W_Q / W_K / W_V (xavier-uniform weights, :73-76).
+    The arithmetic is ``nrms_self_attention`` below (tnr_sgemm_nt + tnr_nrms_attn_fwd)."""
+
+    def __init__(self, d_model, n_heads, d_k, d_v):
+        super().__init__()
+        if d_k != 16 or d_v != 16:
+            raise TinyRecError("NRMS self-attention: d_k = d_v = 16 (as the reference hard-wires, model_bert.py:146)")
+        self.d_model, self.n_heads, self.d_k, self.d_v = d_model, n_heads, d_k, d_v
+        self.W_Q = nn.Linear(d_model, d_k * n_heads)
+        self.W_K = nn.Linear(d_model, d_k * n_heads)
+        self.W_V = nn.Linear(d_model, d_v * n_heads)
+        for m in (self.W_Q, self.W_K, self.W_V):
+            nn.init.xavier_uniform_(m.weight, gain=1)
+
+    def stacked(self):
+        """(W, b, stride_W, stride_b) for the batched (x3) projection GEMMs: the W_Q tensors themselves plus the
+        element strides to W_K / W_V when the three parameters sit at a constant stride in memory (the flat training
+        buffer keeps them contiguous), else a stacked [3, Dh, D] / [3, Dh] copy."""
+        ws = [self.W_Q.weight, self.W_K.weight, self.W_V.weight]
+        bs = [self.W_Q.bias, self.W_K.bias, self.W_V.bias]
+        sw, sb = _const_stride(ws), _const_stride(bs)
+        if sw is not None and sb is not None:
+            return ws[0].detach(), bs[0].detach(), sw, sb
+        Dh, D = ws[0].shape
+        return (torch.stack([w.detach() for w in ws]).contiguous(), torch.stack([b.detach() for b in bs]).contiguous(),
+                Dh * D, Dh)
+
+
+def nrms_self_attention(mh, pad_doc, vecs, mask, use_mask, B, H, buf=None):
+    """The NRMS front of ``UserEncoder.forward`` (model_bert.py:162-164, :169-173):
+    vecs fp32 [B*H, D], mask fp32 [B, H] -> dict(xb = attention input, qkv [3, B*H, Dh], ctx [B*H, Dh],
+    pool_mask = the mask the additive pooling applies: the log mask, or ones in the pad_doc branch)."""
+    R, D = vecs.shape
+    Dh = mh.W_Q.weight.shape[0]
+    dev = vecs.device
+    buf = {} if buf is None else buf
+
+    def get(name, *shape):
+        t = buf.get(name)
+        if t is None or tuple(t.shape) != shape:
+            t = buf[name] = torch.empty(*shape, device=dev, dtype=F32)
+        return t
+
+    if use_mask:
+        xb, pool_mask = vecs, mask
+    else:
+        xb = ops.nrms_blend_fwd(vecs, mask.reshape(-1), pad_doc.reshape(-1), get("xb", R, D))
+        pool_mask = buf.get("ones")
+        if pool_mask is None or tuple(pool_mask.shape) != (B, H):
+            pool_mask = buf["ones"] = torch.ones(B, H, device=dev, dtype=F32)
+    Wc, bc, sw, sb = mh.stacked()
+    qkv = get("qkv", 3, R, Dh)
+    ops.sgemm_nt(xb, Wc, bc, qkv, R, Dh, D, 3, 0, sw, sb, R * Dh)
+    ctx = ops.nrms_attn_fwd(qkv, mask if use_mask else None, get("ctx", R, Dh), B, H)
+    return dict(xb=xb, qkv=qkv, ctx=ctx, pool_mask=pool_mask, Wc=Wc, sw=sw)
+
+
 class UserEncoder(nn.Module):
-    """model_bert.py:140-176, NAML branch (additive attention).  NRMS is a 'next' row."""
+    """model_bert.py:140-176: additive attention over the clicked-news vectors (NAML), optionally behind
+    the 16-dim-per-head self-attention (args.model == 'NRMS', :145-148)."""
 
     def __init__(self, args):
         super().__init__()
         self.args = args
-        if getattr(args, "model", "NAML") == "NRMS":
-            raise TinyRecError("model='NRMS' (multi-head self-attention user encoder) is not built yet")
-        self.attn = AttentionPooling(args.news_dim, args.user_query_vector_dim)
+        self.nrms = getattr(args, "model", "NAML") == "NRMS"
+        if self.nrms:
+            self.multi_head_self_attn = MultiHeadSelfAttention(args.news_dim, args.num_attention_heads, 16, 16)
+            self.attn = AttentionPooling(args.num_attention_heads * 16, args.user_query_vector_dim)
+        else:
+            self.attn = AttentionPooling(args.news_dim, args.user_query_vector_dim)
         self.pad_doc = nn.Parameter(torch.empty(1, args.news_dim).uniform_(-1, 1))
+
+    def _packed_w1(self):
+        """Packed TF32 copy of att_fc1.weight for the scoring kernels, re-packed when the parameter changes."""
+        w = self.attn.att_fc1.weight
+        key = (w.data_ptr(), w._version, w.device)
+        c = getattr(self, "_w1_pack", None)
+        if c is None or c[0] != key:
+            c = (key, ops.user_encoder_pack_w1(w.detach()))
+            object.__setattr__(self, "_w1_pack", c)
+        return c[1]
+
+    def _pool(self, v, idx, m, use_mask, B, H):
+        """Additive pooling of v fp32 [B*H, D] (or table rows v[idx]) -> user fp32 [B, D]."""
+        at = self.attn
+        Q, D = at.att_fc1.weight.shape
+        user = torch.empty(B, D, device=v.device, dtype=F32)
+        a = torch.empty(B, H, device=v.device, dtype=F32)
+        if ops.user_encoder_score_supported(B, H, D, Q):          # scoring-sized batch: flat GEMM + pooling kernels
+            return ops.user_encoder_score(v, idx, m, self.pad_doc.view(-1), self._packed_w1(), Q, at.att_fc1.bias,
+                                          at.att_fc2.weight.view(-1), at.att_fc2.bias, use_mask, user, a, B, H)
+        if idx is not None:
+            return ops.user_encoder_fwd_gather(v, idx, m, self.pad_doc.view(-1), at.att_fc1.weight, at.att_fc1.bias,
+                                               at.att_fc2.weight.view(-1), at.att_fc2.bias, use_mask, user, a)
+        return ops.user_encoder_fwd(v, m, self.pad_doc.view(-1), at.att_fc1.weight, at.att_fc1.bias,
+                                    at.att_fc2.weight.view(-1), at.att_fc2.bias, use_mask, user, a, None, B, H)
 
     def forward(self, news_vecs, log_mask=None):
         B, H, D = news_vecs.shape
-        v = news_vecs.contiguous().float()
+        v = news_vecs.contiguous().float().view(B * H, D)
         m = log_mask.contiguous().float()
-        user = torch.empty(B, D, device=v.device, dtype=F32)
-        a = torch.empty(B, H, device=v.device, dtype=F32)
-        at = self.attn
-        ops.user_encoder_fwd(v.view(B * H, D), m, self.pad_doc.view(-1), at.att_fc1.weight, at.att_fc1.bias,
-                             at.att_fc2.weight.view(-1), at.att_fc2.bias, bool(self.args.user_log_mask), user, a, None, B, H)
-        return user
+        use_mask = bool(self.args.user_log_mask)
+        if self.nrms:
+            fr = nrms_self_attention(self.multi_head_self_attn, self.pad_doc, v, m, use_mask, B, H)
+            v, m, use_mask = fr["ctx"], fr["pool_mask"], True
+        return self._pool(v, None, m, use_mask, B, H)
+
+    def forward_gather(self, table, idx, log_mask):
+        """``self(table[idx], log_mask)`` for the scoring loop (run.py:340-343, dataloader.py:292-301) with the
+        gather fused into the user-encoder kernels: table fp32 [N+1, D], idx int32 [B, H] -> user fp32 [B, D]."""
+        B, H = idx.shape
+        if self.nrms:
+            vecs = torch.empty(B * H, table.shape[1], device=table.device, dtype=F32)
+            ops.gather_rows_f32(table, idx.reshape(-1), vecs)
+            return self.forward(vecs.view(B, H, -1), log_mask)
+        return self._pool(table, idx.contiguous(), log_mask.contiguous().float(), bool(self.args.user_log_mask), B, H)
 
 
 # ------------------------------------------------------------------------------------
@@ -209,9 +305,13 @@ class TrainState:
         self.enc.check_supported()
         enc_params = self.enc.trainable_order()
         at = user_encoder.attn
-        head = [p for p in (user_encoder.pad_doc, at.att_fc1.weight, at.att_fc1.bias, at.att_fc2.weight, at.att_fc2.bias)
-                if p.requires_grad]
-        if head and len(head) != 5:
+        head_all = [user_encoder.pad_doc, at.att_fc1.weight, at.att_fc1.bias, at.att_fc2.weight, at.att_fc2.bias]
+        self.nrms = bool(getattr(user_encoder, "nrms", False))
+        if self.nrms:      # [W_Q | W_K | W_V] and [b_Q | b_K | b_V] contiguous: one batched GEMM each way
+            mh = user_encoder.multi_head_self_attn
+            head_all += [mh.W_Q.weight, mh.W_K.weight, mh.W_V.weight, mh.W_Q.bias, mh.W_K.bias, mh.W_V.bias]
+        head = [p for p in head_all if p.requires_grad]
+        if head and len(head) != len(head_all):
             raise TinyRecError("the user encoder must be trainable or frozen as a whole")
         self.ue_trainable = bool(head)
         tparams = []
@@ -284,15 +384,26 @@ class TrainState:
         label = label.contiguous()
         at = self.ue.attn
         T, TP, G = w["T"], w["TP"], w["G"]
-        encs = [dict(vecs=news[:B * H], pad_doc=self.ue.pad_doc.view(-1), W1=at.att_fc1.weight, b1=at.att_fc1.bias,
+        pool_vecs, pool_mask, pool_use_mask = news[:B * H], mask, use_mask
+        if self.nrms:       # self-attention in front of every pooling (model_bert.py:162-164, :171-173)
+            nb = w.setdefault("nrms", [dict() for _ in range(1 + M)])
+            fr = w["fr"] = nrms_self_attention(self.ue.multi_head_self_attn, self.ue.pad_doc, news[:B * H], mask, use_mask,
+                                               B, H, nb[0])
+            if fr["ctx"].shape[1] != D:
+                raise TinyRecError("NRMS: num_attention_heads * 16 must equal news_dim (the click score is a dot product)")
+            pool_vecs, pool_mask, pool_use_mask = fr["ctx"], fr["pool_mask"], True
+        encs = [dict(vecs=pool_vecs, pad_doc=self.ue.pad_doc.view(-1), W1=at.att_fc1.weight, b1=at.att_fc1.bias,
                      w2=at.att_fc2.weight.view(-1), b2=at.att_fc2.bias, user=w["user"], a=w["a"], e=w["e"])]
         for i in range(M):
             T[i, :B * H].copy_(th_list[i].reshape(B * H, D))
             T[i, B * H:R].copy_(tc_list[i].reshape(B * K, D))
             t = self.teachers[i]
-            encs.append(dict(vecs=T[i, :B * H], pad_doc=t.pad_doc.view(-1), W1=t.attn.att_fc1.weight, b1=t.attn.att_fc1.bias,
+            tv = T[i, :B * H]
+            if self.nrms:
+                tv = nrms_self_attention(t.multi_head_self_attn, t.pad_doc, tv, mask, use_mask, B, H, nb[1 + i])["ctx"]
+            encs.append(dict(vecs=tv, pad_doc=t.pad_doc.view(-1), W1=t.attn.att_fc1.weight, b1=t.attn.att_fc1.bias,
                              w2=t.attn.att_fc2.weight.view(-1), b2=t.attn.att_fc2.bias, user=T[i, R:], a=w["ta"][i], e=None))
-        ops.user_encoder_fwd_multi(encs, mask, use_mask, B, H)
+        ops.user_encoder_fwd_multi(encs, pool_mask, pool_use_mask, B, H)
         if M:
             ws, bs = [lin.weight for lin in self.transform], [lin.bias for lin in self.transform]
             sw, sb = _const_stride(ws), _const_stride(bs)
@@ -313,9 +424,12 @@ class TrainState:
                 scratch = torch.zeros(D + Q * D + 2 * Q + 1, device=dev, dtype=F32)
                 dpad, dW1, db1 = scratch[:D], scratch[D:D + Q * D], scratch[D + Q * D:D + Q * D + Q]
                 dw2, db2 = scratch[D + Q * D + Q:D + Q * D + 2 * Q], scratch[D + Q * D + 2 * Q:]
-            ops.user_encoder_bwd(news[:B * H], mask, self.ue.pad_doc.view(-1), at.att_fc1.weight, at.att_fc2.weight.view(-1),
-                                 use_mask, w["a"], w["e"], w["d_user"], w["d_news"], dpad, dW1, db1, dw2, db2, w["ue_scratch"],
-                                 B, H)
+            if not self.nrms:
+                ops.user_encoder_bwd(news[:B * H], mask, self.ue.pad_doc.view(-1), at.att_fc1.weight, at.att_fc2.weight.view(-1),
+                                     use_mask, w["a"], w["e"], w["d_user"], w["d_news"], dpad, dW1, db1, dw2, db2, w["ue_scratch"],
+                                     B, H)
+            else:
+                self._nrms_backward(w, mask, use_mask, dpad, dW1, db1, dw2, db2, B, H, D)
             if self.tm_trainable and M:
                 gw = [self._stage_view(lin.weight) for lin in self.transform]
                 gb = [self._stage_view(lin.bias) for lin in self.transform]
@@ -327,6 +441,30 @@ class TrainState:
                         ops.sgemm_tn_acc(G[i], T[i], gw[i], gb[i], R + B, D, D, 1, 0, 0, 0, 0)
         self.last = w
         return w
+
+    def _nrms_backward(self, w, mask, use_mask, dpad, dW1, db1, dw2, db2, B, H, D):
+        """d_user -> pooling bwd -> self-attention bwd -> W_Q/K/V gradients, input gradient, pad_doc blend bwd."""
+        fr, at, mh = w["fr"], self.ue.attn, self.ue.multi_head_self_attn
+        Rh, Dh, dev = B * H, fr["ctx"].shape[1], mask.device
+        nb = w["nrms"][0]
+        for name, shape in (("d_ctx", (Rh, Dh)), ("dqkv", (3, Rh, Dh)), ("dxb", (Rh, D))):
+            if name not in nb:
+                nb[name] = torch.empty(*shape, device=dev, dtype=F32)
+        d_ctx = nb["d_ctx"].zero_()
+        ops.user_encoder_bwd(fr["ctx"], fr["pool_mask"], self.ue.pad_doc.view(-1), at.att_fc1.weight, at.att_fc2.weight.view(-1),
+                             True, w["a"], w["e"], w["d_user"], d_ctx, dpad, dW1, db1, dw2, db2, w["ue_scratch"], B, H)
+        ops.nrms_attn_bwd(fr["qkv"], mask if use_mask else None, d_ctx, nb["dqkv"], B, H)
+        if self.ue_trainable:      # stage views keep the flat buffer's [W_Q | W_K | W_V] / [b_Q | b_K | b_V] layout
+            o = self.flat.off(mh.W_Q.weight) - self.head_begin
+            gW = self.stage[o:o + 3 * Dh * D]
+            o = self.flat.off(mh.W_Q.bias) - self.head_begin
+            gb = self.stage[o:o + 3 * Dh]
+            if self.flat.off(mh.W_V.weight) - self.flat.off(mh.W_Q.weight) != 2 * Dh * D or \
+                    self.flat.off(mh.W_V.bias) - self.flat.off(mh.W_Q.bias) != 2 * Dh:
+                raise TinyRecError("NRMS: W_Q / W_K / W_V are not contiguous in the flat buffer")
+            ops.sgemm_tn_acc(nb["dqkv"], fr["xb"], gW, gb, Rh, Dh, D, 3, Rh * Dh, 0, Dh * D, Dh)
+        ops.sgemm_nn(nb["dqkv"], fr["Wc"], nb["dxb"], Rh, D, Dh, 3, Rh * Dh, fr["sw"])
+        ops.nrms_blend_bwd(nb["dxb"], None if use_mask else mask.reshape(-1), w["d_news"][:Rh], dpad)
 
     def step_backward(self, g_total):
         """Upstream gradient of the total loss (a device scalar) -> encoder backward + staged head grads."""

@@ -275,6 +275,65 @@ def user_encoder_fwd(vecs, mask, pad_doc, W1, b1, w2, b2, use_mask, user, a_out,
 
 
 @_timed
+def user_encoder_fwd_gather(table, idx, mask, pad_doc, W1, b1, w2, b2, use_mask, user, a_out=None):
+    """user[b] = user_encoder(table[idx[b, :]], mask[b]) with the row gather fused into the kernel.
+    table fp32 [n_rows, D], idx int32 [B, H], mask fp32 [B, H] -> user fp32 [B, D]."""
+    lib = _ready(table)
+    B, H = idx.shape
+    D, Q = W1.shape[1], W1.shape[0]
+    for t, nm in ((table, "table"), (mask, "mask"), (pad_doc, "pad_doc"), (W1, "W1"), (b1, "b1"), (w2, "w2"), (b2, "b2"),
+                  (user, "user")):
+        _chk(t, _f32, "user_encoder_gather." + nm)
+    _chk(idx, torch.int32, "user_encoder_gather.idx")
+    if table.shape[1] != D or not table.is_contiguous() or not idx.is_contiguous() or tuple(mask.shape) != (B, H):
+        raise _lib.TinyRecError("user_encoder_fwd_gather: shape / layout mismatch")
+    _lib.check(lib.tnr_user_encoder_fwd_gather(_ptr(table), table.shape[0], _ptr(idx), _ptr(mask), _ptr(pad_doc), _ptr(W1),
+                                               _ptr(b1), _ptr(w2), _ptr(b2), int(use_mask), _ptr(user), _ptr(a_out), B, H, D, Q,
+                                               _stream()), "tnr_user_encoder_fwd_gather")
+    return user
+
+
+def user_encoder_score_supported(B, H, D, Q):
+    """Shapes the flat scoring path takes (tnr_user_encoder_score); small batches stay on the per-impression kernel."""
+    return B >= 64 and H <= 64 and D % 32 == 0 and D <= 256 and Q <= 208
+
+
+def user_encoder_pack_w1(W1, packed=None):
+    """att_fc1.weight fp32 [Q, D] -> the packed, TF32-rounded, chunk-major copy tnr_user_encoder_score reads."""
+    lib = _ready(W1)
+    Q, D = W1.shape
+    n = int(lib.tnr_user_encoder_packed_w1_floats(D))
+    if packed is None or packed.numel() != n:
+        packed = torch.empty(n, device=W1.device, dtype=_f32)
+    _lib.check(lib.tnr_user_encoder_pack_w1(_ptr(_chk(W1.contiguous(), _f32, "pack_w1.W1")), _ptr(packed), D, Q, _stream()),
+               "tnr_user_encoder_pack_w1")
+    return packed
+
+
+@_timed
+def user_encoder_score(vecs, idx, mask, pad_doc, w1_packed, Q, b1, w2, b2, use_mask, user, a_out, B, H):
+    """Scoring path: vecs fp32 [B*H, D] (idx None) or the [N, D] table with idx int32 [B, H]; mask fp32 [B, H]
+    -> user fp32 [B, D], a_out fp32 [B, H]."""
+    lib = _ready(vecs, 2)
+    D = vecs.shape[1]
+    for t, nm in ((vecs, "vecs"), (mask, "mask"), (pad_doc, "pad_doc"), (w1_packed, "w1_packed"), (b1, "b1"), (w2, "w2"),
+                  (b2, "b2"), (user, "user"), (a_out, "a")):
+        _chk(t, _f32, "user_encoder_score." + nm)
+    if idx is not None:
+        _chk(idx, torch.int32, "user_encoder_score.idx")
+        if tuple(idx.shape) != (B, H) or not idx.is_contiguous():
+            raise _lib.TinyRecError("user_encoder_score: idx must be contiguous int32 [B, H]")
+    elif vecs.shape[0] != B * H:
+        raise _lib.TinyRecError("user_encoder_score: vecs must be [B*H, D]")
+    if not vecs.is_contiguous() or tuple(mask.shape) != (B, H) or a_out.numel() != B * H or user.numel() != B * D:
+        raise _lib.TinyRecError("user_encoder_score: shape / layout mismatch")
+    _lib.check(lib.tnr_user_encoder_score(_ptr(vecs), vecs.shape[0], _ptr(idx), _ptr(mask), _ptr(pad_doc), _ptr(w1_packed),
+                                          _ptr(b1), _ptr(w2), _ptr(b2), int(use_mask), _ptr(user), _ptr(a_out), B, H, D, Q,
+                                          _stream()), "tnr_user_encoder_score")
+    return user
+
+
+@_timed
 def user_encoder_fwd_multi(encoders, mask, use_mask, B, H):
     """One launch for several user encoders sharing ``mask``.  ``encoders``: list of dicts with
     vecs [B*H, D], pad_doc [D], W1 [Q, D], b1 [Q], w2 [Q], b2 [1], user [B, D], a [B, H], e [B, H, Q] | None."""
@@ -337,6 +396,68 @@ def sgemm_tn_acc(A, Bm, C, cbias, R, N1, N2, batch, sA, sB, sC, sbias):
     _lib.check(lib.tnr_sgemm_tn_acc(_ptr(_chk(A, _f32, "sgemm.A")), _ptr(_chk(Bm, _f32, "sgemm.B")),
                                     _ptr(_chk(C, _f32, "sgemm.C")), _ptr(cbias), R, N1, N2, batch, sA, sB, sC, sbias,
                                     _stream()), "tnr_sgemm_tn_acc")
+
+
+@_timed
+def sgemm_nn(A, Bm, C, M, N, K, parts=1, sA=0, sB=0):
+    """C[M,N] = sum_p A[p][M,K] . B[p][K,N]   (fp32, TF32 tensor path)."""
+    lib = _ready(A)
+    _lib.check(lib.tnr_sgemm_nn(_ptr(_chk(A, _f32, "sgemm_nn.A")), _ptr(_chk(Bm, _f32, "sgemm_nn.B")),
+                                _ptr(_chk(C, _f32, "sgemm_nn.C")), M, N, K, parts, sA, sB, _stream()), "tnr_sgemm_nn")
+
+
+# ---- NRMS user encoder (model_bert.py:37-100) ------------------------------------------------------
+@_timed
+def nrms_blend_fwd(vecs, mask, pad_doc, out):
+    """out = vecs * m + pad_doc * (1 - m);  vecs / out fp32 [R, D], mask fp32 [R]."""
+    lib = _ready(vecs)
+    R, D = vecs.shape
+    for t, nm in ((vecs, "vecs"), (mask, "mask"), (pad_doc, "pad_doc"), (out, "out")):
+        _chk(t, _f32, "nrms_blend_fwd." + nm)
+    if mask.numel() != R or pad_doc.numel() != D or not vecs.is_contiguous() or not out.is_contiguous():
+        raise _lib.TinyRecError("nrms_blend_fwd: shape / layout mismatch")
+    _lib.check(lib.tnr_nrms_blend_fwd(_ptr(vecs), _ptr(mask), _ptr(pad_doc), _ptr(out), R, D, _stream()), "tnr_nrms_blend_fwd")
+    return out
+
+
+@_timed
+def nrms_blend_bwd(d_blend, mask, d_vecs, dpad):
+    """d_vecs += d_blend * m, dpad += sum_r d_blend (1 - m);  mask None: d_vecs += d_blend."""
+    lib = _ready(d_blend)
+    R, D = d_blend.shape
+    for t, nm in ((d_blend, "d_blend"), (d_vecs, "d_vecs")):
+        _chk(t, _f32, "nrms_blend_bwd." + nm)
+    if not d_blend.is_contiguous() or not d_vecs.is_contiguous() or d_vecs.numel() != R * D:
+        raise _lib.TinyRecError("nrms_blend_bwd: shape / layout mismatch")
+    _lib.check(lib.tnr_nrms_blend_bwd(_ptr(d_blend), _ptr(mask), _ptr(d_vecs), _ptr(dpad), R, D, _stream()), "tnr_nrms_blend_bwd")
+
+
+def _nrms_planes(qkv, B, H):
+    _chk(qkv, _f32, "nrms.qkv")
+    if qkv.dim() != 3 or qkv.shape[0] != 3 or qkv.shape[1] != B * H or qkv.shape[2] % 16 or not qkv.is_contiguous():
+        raise _lib.TinyRecError(f"nrms: qkv must be contiguous fp32 [3, B*H, n_heads*16], got {tuple(qkv.shape)}")
+    return qkv.shape[2] // 16
+
+
+@_timed
+def nrms_attn_fwd(qkv, mask, ctx, B, H):
+    """qkv fp32 [3, B*H, Dh] planes, mask fp32 [B, H] or None -> ctx fp32 [B*H, Dh]."""
+    lib = _ready(qkv)
+    heads = _nrms_planes(qkv, B, H)
+    _chk(ctx, _f32, "nrms.ctx")
+    _lib.check(lib.tnr_nrms_attn_fwd(_ptr(qkv[0]), _ptr(qkv[1]), _ptr(qkv[2]), _ptr(mask), _ptr(ctx), B, H, heads, _stream()),
+               "tnr_nrms_attn_fwd")
+    return ctx
+
+
+@_timed
+def nrms_attn_bwd(qkv, mask, d_ctx, dqkv, B, H):
+    lib = _ready(qkv)
+    heads = _nrms_planes(qkv, B, H)
+    _nrms_planes(dqkv, B, H)
+    _chk(d_ctx, _f32, "nrms.d_ctx")
+    _lib.check(lib.tnr_nrms_attn_bwd(_ptr(qkv[0]), _ptr(qkv[1]), _ptr(qkv[2]), _ptr(mask), _ptr(d_ctx), _ptr(dqkv[0]),
+                                     _ptr(dqkv[1]), _ptr(dqkv[2]), B, H, heads, _stream()), "tnr_nrms_attn_bwd")
 
 
 @_timed

@@ -191,8 +191,10 @@ def evaluate(user_encoder, news_scoring, hist_idx, hist_mask, cand_ptr, cand_idx
         ptr_t = torch.from_numpy(np.ascontiguousarray(ptr_h[s:e + 1] - p0)).to(device)
         cand_t = torch.from_numpy(np.ascontiguousarray(cand_idx[p0:p1])).to(device)
         lab_t = torch.from_numpy(np.ascontiguousarray(labels[p0:p1])).to(device)
-        log_vecs = dl.gather_history_vecs(news_scoring, hi_t)
-        user = user_encoder(log_vecs, hm_t)
+        if hasattr(user_encoder, "forward_gather"):      # news_scoring[log_ids] (dataloader.py:295) fused into the kernel
+            user = user_encoder.forward_gather(news_scoring, hi_t, hm_t)
+        else:
+            user = user_encoder(dl.gather_history_vecs(news_scoring, hi_t), hm_t)
         per = torch.zeros(e - s, 5, device=device, dtype=torch.float64)
         max_c = int(np.diff(ptr_h[s:e + 1]).max())
         ops.eval_metrics(news_scoring, user, ptr_t, cand_t, lab_t, max_c, per, sums)
