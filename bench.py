@@ -316,25 +316,45 @@ def run_tinyrec(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The train step as the public API runs it at speed: tinyrec.run.GraphedTrainStep captures zero_grad + forward +
+    # backward (+ bucketed NCCL all-reduce) + Adam once and replays it per batch.  --no-graph keeps the eager loop.
+    gstep, graph_note = None, "eager (--no-graph)"
+    if not a.no_graph:
+        try:
+            import tinyrec.run as trun
+            gstep = trun.GraphedTrainStep(model, opt, dev_batches[0], warmup=max(a.warmup, 3))
+            graph_note = "CUDA graph replay of the whole step (tinyrec.run.GraphedTrainStep)"
+        except Exception as exc:                                  # noqa: BLE001  (reported, not hidden)
+            gstep, graph_note = None, f"eager: graph capture failed ({type(exc).__name__}: {exc})"
+            torch.cuda.synchronize()
+    if world > 1:                                                 # all ranks must take the same path
+        flag = torch.tensor([1 if gstep is not None else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and gstep is not None:
+            gstep, graph_note = None, "eager: graph capture failed on another rank"
+
+    def run_step(batch):
+        if gstep is not None:
+            return gstep(*batch)[0]
+        return step(batch)
+
     for i in range(max(a.warmup, 3)):
-        step(dev_batches[i % N_BATCHES])
+        run_step(dev_batches[i % N_BATCHES])
     barrier()
     # ---- device-timed region (inputs resident in HBM)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ops.stats.gemm_events = []
     launches0 = ops.stats.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for i in range(a.steps):
-        step(dev_batches[i % N_BATCHES])
+        run_step(dev_batches[i % N_BATCHES])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = ops.stats.launches - launches0
-    gemm_events, ops.stats.gemm_events = ops.stats.gemm_events, None
+    launches = (gstep.launches_per_step * a.steps) if gstep is not None else (ops.stats.launches - launches0)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
@@ -344,6 +364,8 @@ def run_tinyrec(a):
 
     # ---- e2e: host (pinned) inputs -> H2D every step -> public API -> loss read back
     def e2e_step(hb):
+        if gstep is not None:                                     # H2D straight into the graph's static inputs
+            return float(gstep(*hb)[0].item())
         batch = (hb[0].to(device, non_blocking=True), hb[1].to(device, non_blocking=True),
                  hb[2].to(device, non_blocking=True), hb[3].to(device, non_blocking=True),
                  [t.to(device, non_blocking=True) for t in hb[4]], [t.to(device, non_blocking=True) for t in hb[5]])
@@ -361,6 +383,21 @@ def run_tinyrec(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = B * world * a.steps / float(t.item())
 
+    # ---- roofline leg: the same steps launched eagerly with CUDA events around every tnr_gemm_bf16 launch (events
+    # cannot be recorded inside a graph replay, so the per-kernel durations come from this pass, run right after the
+    # timed region in the same process and clock state; without --no-graph it is a separate pass, with it the same)
+    n_roof = min(a.steps, 20)
+    barrier()
+    ops.stats.gemm_events = []
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for i in range(n_roof):
+        step(dev_batches[i % N_BATCHES])
+    r1.record()
+    barrier()
+    eager_ms = r0.elapsed_time(r1) / n_roof
+    gemm_events, ops.stats.gemm_events = ops.stats.gemm_events, None
+
     if rank == 0:
         peak_tf, peak_bw, how = peaks()
         gflop = sum(f for f, _, _ in gemm_events)
@@ -371,7 +408,7 @@ def run_tinyrec(a):
         line = {"metric": "kd_train_impressions_per_sec", "value": value, "unit": "impressions/s", "n_gpus": world,
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": config_dict(a.workload, world), "clocks": clocks,
+                "config": dict(config_dict(a.workload, world), launch=graph_note), "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "impressions/s", "h2d_bytes_per_step": bytes_of(host_batches[0]),
                         "d2h_bytes_per_step": 4},
                 "gpu_launches": launches,
@@ -382,9 +419,12 @@ def run_tinyrec(a):
                              "traffic_note": "DRAM bytes per GEMM launch, ncu --set full over one step "
                                              "(profiles/r01_gemm_ncu_full_v7.json); algorithmic operand+output bytes "
                                              "average 345 MB per launch (operands are read from HBM once: no re-reads)",
-                             "gemm_launches_per_step": len(gemm_events) / a.steps,
-                             "gemm_ms_per_step": gms / a.steps,
-                             "gemm_share_of_step": gms / ms if ms > 0 else None,
+                             "measured": f"CUDA events around every GEMM launch over {n_roof} eagerly launched steps right "
+                                         "after the timed region (per-kernel events cannot be recorded inside a graph replay)",
+                             "gemm_launches_per_step": len(gemm_events) / n_roof,
+                             "gemm_ms_per_step": gms / n_roof,
+                             "gemm_share_of_step": (gms / n_roof) / (ms / a.steps) if ms > 0 else None,
+                             "eager_ms_per_step_with_events": eager_ms,
                              "algorithmic_tflop_per_step": algo / 1e12,
                              "step_frac_of_tensor_roofline": (algo / 1e12) / (ms / a.steps * 1e-3) / peak_tf}}
         if world == 1 and not a.no_cpu_baseline:
@@ -670,6 +710,8 @@ def main():
     ap.add_argument("--impl", default="tinyrec", choices=["tinyrec", "reference"])
     ap.add_argument("--workload", default="kd4", choices=sorted(WORKLOADS) + sorted(TABLE_WORKLOADS) + ["eval"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true",
+                    help="kd workloads: launch every step eagerly instead of replaying the captured CUDA graph")
     a = ap.parse_args()
     if a.impl == "reference":
         if a.workload not in WORKLOADS:

@@ -239,6 +239,11 @@ int tnr_sgemm_nn(const float* A, const float* B, float* C, int M, int N, int K, 
 int tnr_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, void* shadow_bf16,
                      long long n, float lr, float beta1, float beta2, float eps, int step,
                      float grad_scale, void* stream);
+/* The same with the step counter ON THE DEVICE (int32, incremented by the call; bc_ws: 2 floats of workspace for
+ * the bias corrections): a captured CUDA graph of the train step replays with the right step number. */
+int tnr_adam_amsgrad_devstep(float* p, const float* g, float* m, float* v, float* vmax, void* shadow_bf16,
+                             long long n, float lr, float beta1, float beta2, float eps, int* step_dev,
+                             float* bc_ws, float grad_scale, void* stream);
 int tnr_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);
 
 /* ------------------------------------------------------------------ batch assembly */

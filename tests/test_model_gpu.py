@@ -440,3 +440,55 @@ def test_eval_metrics_vs_reference_golden(golden):
             np.testing.assert_allclose(per[i, 1:4], vals[i, 1:4], atol=1e-12)
     np.testing.assert_allclose(sums.cpu().numpy()[:4], per[:, :4].sum(0), rtol=1e-12)
     assert int(sums[4]) == int(valid.sum())
+
+
+def test_graphed_train_step_matches_eager_loop():
+    """tinyrec.run.GraphedTrainStep (one CUDA graph per step) against the eager loop of run.py:178-197 on the same
+    batches: same losses step by step, same parameters afterwards (split-K wgrads use fp32 atomics: not bitwise),
+    the Adam step counter advances inside the graph, and constructing the object does not train the model."""
+    import tinyrec.model_bert as mb
+    import tinyrec.optim as topt
+    import tinyrec.run as trun
+    import tinyrec.synth as synth
+    B, H, K, L, M, layers, N = 4, 10, 3, 12, 2, 2, 300
+    news = synth.news_table(N, L=L, seed=1)
+    tables = synth.teacher_tables(N, M, 256, seed=3)
+    batches = []
+    for s in range(3):
+        hist_idx, hmask, cand_idx, label = synth.train_impressions(B, N, H, K, seed=10 + s)
+        batches.append((torch.from_numpy(news[hist_idx].astype(np.int64)).cuda(), torch.from_numpy(hmask).cuda(),
+                        torch.from_numpy(news[cand_idx].astype(np.int64)).cuda(), torch.from_numpy(label).cuda(),
+                        [torch.from_numpy(t[hist_idx]).cuda() for t in tables], [torch.from_numpy(t[cand_idx]).cuda() for t in tables]))
+    sd = synth.kd_model_state(layers, M, 5, noisy=True)
+    runs = []
+    for graphed in (False, True):
+        m = mb.Model(synth.demo_args(num_student_layers=layers, num_teachers=M, user_log_length=H))
+        m.load_state_dict(sd, strict=True)
+        m.cuda().eval()                                   # dropout off: the two runs must see the same arithmetic
+        _apply_freeze(m, [1])
+        opt = topt.Adam(m, lr=1e-3)
+        losses = []
+        if graphed:
+            before = m.student.news_encoder.dense.weight.detach().clone()
+            step = trun.GraphedTrainStep(m, opt, batches[0])
+            assert torch.equal(m.student.news_encoder.dense.weight.detach(), before)      # no side effect
+            assert opt.steps_done() == 0
+            for b in batches:
+                losses.append(float(step(*b)[0]))
+            assert opt.steps_done() == len(batches)
+        else:
+            for b in batches:
+                opt.zero_grad()
+                out = m(*b)
+                out[0].backward()
+                opt.step()
+                losses.append(float(out[0]))
+        runs.append((losses, {k: v.detach().clone() for k, v in m.named_parameters() if v.requires_grad}))
+    (l0, p0), (l1, p1) = runs
+    assert l0[0] != l0[1]
+    for a, b in zip(l0, l1):
+        assert abs(a - b) < 2e-3 * abs(a) + 1e-5, (l0, l1)
+    for k in p0:
+        if k.endswith(("key.bias", "att_fc2.bias")):     # gradient identically 0 up to rounding noise: Adam turns the
+            continue                                     # noise into +-lr steps, different in any two runs
+        assert _rel(p1[k], p0[k]) < 2e-3, k

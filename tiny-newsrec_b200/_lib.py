@@ -74,6 +74,7 @@ _SIGNATURES = {
     "tnr_nrms_attn_bwd": ([P, P, P, P, P, P, P, P, c_int, c_int, c_int, P], c_int),
     "tnr_sgemm_nn": ([P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, P], c_int),
     "tnr_adam_amsgrad": ([P, P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, c_float, P], c_int),
+    "tnr_adam_amsgrad_devstep": ([P, P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P, c_float, P], c_int),
     "tnr_cast_f32_bf16": ([P, P, c_int64, P], c_int),
     "tnr_gather_rows_i32_i64": ([P, c_int64, P, c_int64, c_int, P, P], c_int),
     "tnr_gather_rows_f32": ([P, c_int64, P, c_int64, c_int, P, c_int64, P], c_int),

@@ -15,9 +15,10 @@ namespace tnr {
 __global__ void __launch_bounds__(256)
 adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                     float* __restrict__ vmax, __nv_bfloat16* __restrict__ shadow, long long n, float lr, float b1,
-                    float b2, float eps, float bc1, float rsqrt_bc2, float grad_scale) {
+                    float b2, float eps, float bc1, float rsqrt_bc2, float grad_scale, const float* __restrict__ bc_dev) {
   const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= n) return;
+  if (bc_dev != nullptr) { bc1 = bc_dev[0]; rsqrt_bc2 = bc_dev[1]; }      // device-resident step (CUDA-graph replay)
   if (i4 + 4 <= n) {
     float4 pp = *reinterpret_cast<float4*>(p + i4);
     const float4 gg = *reinterpret_cast<const float4*>(g + i4);
@@ -247,7 +248,30 @@ TNR_API int tnr_adam_amsgrad(float* p, const float* g, float* m, float* v, float
   const int grid = (int)((threads + 255) / 256);
   adam_amsgrad_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, vmax, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr, beta1, beta2, eps, (float)bc1,
-      (float)(1.0 / sqrt(bc2)), grad_scale);
+      (float)(1.0 / sqrt(bc2)), grad_scale, nullptr);
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
+
+// step counter on the device: ++step, then the two bias corrections (double precision, one thread)
+__global__ void adam_step_prep_kernel(int* __restrict__ step_dev, float* __restrict__ bc, float b1, float b2) {
+  const int step = ++(*step_dev);
+  bc[0] = (float)(1.0 - pow((double)b1, (double)step));
+  bc[1] = (float)(1.0 / sqrt(1.0 - pow((double)b2, (double)step)));
+}
+
+TNR_API int tnr_adam_amsgrad_devstep(float* p, const float* g, float* m, float* v, float* vmax, void* shadow_bf16,
+                                     long long n, float lr, float beta1, float beta2, float eps, int* step_dev,
+                                     float* bc_ws, float grad_scale, void* stream) {
+  TNR_REQUIRE(step_dev != nullptr && bc_ws != nullptr, "tnr_adam_amsgrad_devstep: step_dev (int32) and bc_ws (2 floats) are required");
+  if (n == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  adam_step_prep_kernel<<<1, 1, 0, st>>>(step_dev, bc_ws, beta1, beta2);
+  TNR_LAUNCH_CHECK();
+  const long long threads = (n + 3) / 4;
+  const int grid = (int)((threads + 255) / 256);
+  adam_amsgrad_kernel<<<grid, 256, 0, st>>>(p, g, m, v, vmax, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr, beta1,
+                                            beta2, eps, 1.0f, 1.0f, grad_scale, bc_ws);
   TNR_LAUNCH_CHECK();
   return 0;
 }

@@ -470,6 +470,18 @@ def adam_amsgrad(p, g, m, v, vmax, shadow, lr, beta1, beta2, eps, step, grad_sca
 
 
 @_timed
+def adam_amsgrad_devstep(p, g, m, v, vmax, shadow, lr, beta1, beta2, eps, step_dev, bc_ws, grad_scale=1.0):
+    """Adam(amsgrad) with the step counter on the device (int32 [1], incremented by the call): graph-capturable."""
+    lib = _ready(p, 2)
+    for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v"), (vmax, "vmax"), (bc_ws, "bc_ws")):
+        _chk(t, _f32, "adam." + nm)
+    _chk(step_dev, torch.int32, "adam.step_dev")
+    _lib.check(lib.tnr_adam_amsgrad_devstep(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(vmax), _ptr(shadow), p.numel(), lr, beta1,
+                                            beta2, eps, _ptr(step_dev), _ptr(bc_ws), grad_scale, _stream()),
+               "tnr_adam_amsgrad_devstep")
+
+
+@_timed
 def gather_rows_i32_i64(table, idx, out):
     """out int64 [n, W] = table int32 [N, W][idx int32 [n]]"""
     lib = _ready(table)

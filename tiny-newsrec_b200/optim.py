@@ -15,13 +15,17 @@ class Adam:
     """``Adam(model, lr, amsgrad=True)``: one kernel launch per step over all trainable parameters
     (fp32 master weights, m, v, vmax) that also refreshes the bf16 shadow weights the GEMMs read."""
 
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, amsgrad=True):
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, amsgrad=True, capturable=False):
         if not amsgrad:
             raise TinyRecError("only amsgrad=True is implemented (what run.py:134 uses)")
         self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
         self.step_count = 0
         self.m = self.v = self.vmax = None
         self.grad_scale = 1.0
+        # capturable: the step counter lives on the device so that a captured CUDA graph of the train step
+        # (tinyrec.run.GraphedTrainStep) replays with the right bias corrections
+        self.capturable = bool(capturable)
+        self.step_dev = self.bc_ws = None
 
     def _flat(self):
         st = self.model.train_state()
@@ -34,21 +38,42 @@ class Adam:
         flat.reattach_grads()
         flat.grad.zero_()
 
-    def step(self):
+    def make_capturable(self):
+        if not self.capturable:
+            self.capturable = True
+            self.step_dev = None
+
+    def ensure_state(self):
+        """Allocate m / v / vmax (and the device step counter when capturable) without stepping."""
         flat = self._flat()
         if self.m is None or self.m.numel() != flat.numel or self.m.device != flat.data.device:
             self.m = torch.zeros_like(flat.data)
             self.v = torch.zeros_like(flat.data)
             self.vmax = torch.zeros_like(flat.data)
+        if self.capturable and self.step_dev is None:
+            self.step_dev = torch.tensor([self.step_count], device=flat.data.device, dtype=torch.int32)
+            self.bc_ws = torch.zeros(2, device=flat.data.device, dtype=torch.float32)
+        return flat
+
+    def step(self):
+        flat = self.ensure_state()
+        if self.capturable:
+            ops.adam_amsgrad_devstep(flat.data, flat.grad, self.m, self.v, self.vmax, flat.shadow, self.lr, self.betas[0],
+                                     self.betas[1], self.eps, self.step_dev, self.bc_ws, self.grad_scale)
+            return
         self.step_count += 1
         ops.adam_amsgrad(flat.data, flat.grad, self.m, self.v, self.vmax, flat.shadow, self.lr, self.betas[0],
                          self.betas[1], self.eps, self.step_count, self.grad_scale)
 
+    def steps_done(self):
+        return int(self.step_dev) if self.capturable and self.step_dev is not None else self.step_count
+
     def state_dict(self):
-        return dict(step=self.step_count, m=self.m, v=self.v, vmax=self.vmax, lr=self.lr)
+        return dict(step=self.steps_done(), m=self.m, v=self.v, vmax=self.vmax, lr=self.lr)
 
     def load_state_dict(self, sd):
         self.step_count, self.m, self.v, self.vmax, self.lr = sd["step"], sd["m"], sd["v"], sd["vmax"], sd["lr"]
+        self.step_dev = None
 
 
 def broadcast_parameters(model, root_rank=0):
