@@ -122,11 +122,14 @@ int tnr_colsum_bf16(const void* x_bf16, int rows, int cols, int ld, float* out, 
 int tnr_attn_relpos_fwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias,
                         void* ctx_bf16, int n_news, int L, int A, int E, const tnr_dropout* drop,
                         void* stream);
-/* dqkv bf16 [n*L, 3E] from dctx (probabilities recomputed, dropout mask regenerated).  L <= 32.
+/* dqkv bf16 [n*L, 3E] from dctx (probabilities recomputed, dropout mask regenerated).
+ * L <= 32: one warp per (news, head), workspace unused (may be NULL).  32 < L <= 512: two streamed kernels
+ * (dQ with its own online softmax statistics, then dK / dV per key block) that need `workspace`:
+ * 2 * n_news * A * L floats (row log-sum-exp and delta_i = sum_j P_ij dP_ij).
  * If dbias_qkv != NULL: dbias_qkv[3E] += column sums of dqkv (the fused [bq|bk|bv] gradient, fp32 atomics). */
 int tnr_attn_relpos_bwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias,
-                        const void* dctx_bf16, void* dqkv_bf16, float* dbias_qkv, int n_news, int L, int A, int E,
-                        const tnr_dropout* drop, void* stream);
+                        const void* dctx_bf16, void* dqkv_bf16, float* dbias_qkv, float* workspace, int n_news,
+                        int L, int A, int E, const tnr_dropout* drop, void* stream);
 
 /* ------------------------------------------------------- additive attention pooling (words) */
 /* a = normalise(exp(e.w2 + b2) [* mask]);  out[n,:] = sum_s a[n,s] x[n,s,:]

@@ -679,3 +679,83 @@ def test_user_encoder_scoring_path_vs_torch(use_mask, B, H, Q):
     assert _rel_err(user, ref_u)[0] < 2e-3
     if use_mask:
         assert float(user[1].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("L", [33, 64, 100, 180, 512])
+def test_attention_long_bwd(L):
+    """Backward of the streamed-KV attention (32 < L <= 512) against torch autograd on the fp32 restatement: ragged
+    lengths (fully masked key chunks are skipped), an all-pad row, tail query / key blocks, fused bias gradient."""
+    ops = _ops()
+    n, A, E = (5, 12, 768) if L <= 180 else (2, 12, 768)
+    qkv = _randn(n * L, 3 * E, seed=1)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    lens = torch.randint(1, L + 1, (n,), generator=g, device="cuda")
+    lens[0] = L
+    mask = (torch.arange(L, device="cuda")[None, :] < lens[:, None]).long()
+    mask[n - 1] = 0                                  # all-pad news
+    x = torch.cat([torch.zeros_like(mask), mask], 1)
+    relpos = _randn(A, 2 * L - 1, dtype=torch.float32, seed=4)
+    qf = qkv.float().requires_grad_(True)
+    ref = _attn_ref(qf, mask, relpos, n, L, A)
+    dctx = _randn(n * L, E, seed=5)
+    ref.backward(dctx.float())
+    dqkv = torch.full_like(qkv, float("nan"))
+    dbias = torch.zeros(3 * E, device="cuda")
+    ops.attn_bwd(qkv, x, L, relpos, dctx, dqkv, A, dbias=dbias)
+    assert torch.isfinite(dqkv.float()).all()
+    for part, nm in enumerate("qkv"):
+        sl = slice(part * E, (part + 1) * E)
+        assert _rel_err(dqkv[:, sl], qf.grad[:, sl])[0] < 8e-3, nm
+    assert _rel_err(dbias, dqkv.float().sum(0))[0] < 1e-4
+
+
+@pytest.mark.parametrize("L", [48, 200])
+def test_attention_long_dropout_adjoint(L):
+    """With dropout the forward is still linear in V for a fixed seed, and the backward regenerates the same mask:
+    <dO, ctx(V)> == <dV, V> (adjoint identity).  For L <= 64 the keep mask is read out of the forward and injected
+    into the torch restatement, which pins dQ, dK and dV under dropout."""
+    ops = _ops()
+    n, A, E = 3, 12, 768
+    qkv = _randn(n * L, 3 * E, seed=1, scale=0.5)
+    mask = torch.ones(n, L, device="cuda", dtype=torch.long)
+    mask[1, L // 2:] = 0
+    x = torch.cat([torch.zeros_like(mask), mask], 1)
+    relpos = _randn(A, 2 * L - 1, dtype=torch.float32, seed=4, scale=0.3)
+    seed = _seed_tensor(77)                                         # must outlive `drop`: the kernels read it from HBM
+    drop = ops.make_drop(seed, 5, P_DROP)
+    ctx = torch.empty(n * L, E, device="cuda", dtype=BF)
+    ops.attn_fwd(qkv, x, L, relpos, ctx, A, drop=drop)
+    ctx2 = torch.empty_like(ctx)
+    ops.attn_fwd(qkv, x, L, relpos, ctx2, A, drop=drop)
+    assert torch.equal(ctx, ctx2)                                   # counter-based: same seed, same mask
+    nodrop = torch.empty_like(ctx)
+    ops.attn_fwd(qkv, x, L, relpos, nodrop, A)
+    assert _rel_err(ctx, nodrop)[0] > 0.05                          # the mask is really applied
+    dctx = _randn(n * L, E, seed=5)
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(qkv, x, L, relpos, dctx, dqkv, A, drop=drop)
+    lhs = float((dctx.float() * ctx.float()).sum())
+    rhs = float((dqkv[:, 2 * E:].float() * qkv[:, 2 * E:].float()).sum())
+    assert abs(lhs - rhs) < 1e-2 * abs(lhs) + 1e-2, (lhs, rhs)
+    if L > 64:
+        return
+    # L <= 64: read the keep mask out of the forward (V = one-hot rows make ctx[i, j] = dropout(P)_ij), inject it
+    # into the torch restatement and compare ALL of dQ, dK, dV with autograd
+    eye = torch.zeros(L, A, 64, device="cuda")
+    eye[torch.arange(L), :, torch.arange(L)] = 1.0
+    probe = qkv.clone()
+    probe[:, 2 * E:] = eye.reshape(1, L, E).expand(n, L, E).reshape(n * L, E).to(BF)
+    pm = torch.empty_like(ctx)
+    ops.attn_fwd(probe, x, L, relpos, pm, A, drop=drop)
+    keep = (pm.float().reshape(n, L, A, 64)[..., :L] != 0).permute(0, 2, 1, 3)          # [n, A, i, j]
+    qf = qkv.float().requires_grad_(True)
+    q, k, v = [t.reshape(n, L, A, 64).permute(0, 2, 1, 3) for t in qf.split(E, dim=1)]
+    sc = q @ k.transpose(-1, -2) / 8.0 + (1.0 - mask.float())[:, None, None, :] * -10000.0 + _rel_matrix(relpos, L)[None]
+    pr = torch.softmax(sc, -1)
+    keep = keep | (pr < 1e-30)                                     # an exactly-zero probability reads as "dropped"
+    ref = ((pr * keep / (1.0 - P_DROP)) @ v).permute(0, 2, 1, 3).reshape(n * L, E)
+    assert _rel_err(ctx, ref.detach())[0] < 6e-3
+    ref.backward(dctx.float())
+    for part, nm in enumerate("qkv"):
+        sl = slice(part * E, (part + 1) * E)
+        assert _rel_err(dqkv[:, sl], qf.grad[:, sl])[0] < 8e-3, nm

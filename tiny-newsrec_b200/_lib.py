@@ -54,7 +54,7 @@ _SIGNATURES = {
     "tnr_layernorm_bwd": ([P, P, c_int, c_int, P, c_float, P, P, P, P, P, POINTER(Dropout), P], c_int),
     "tnr_colsum_bf16": ([P, c_int, c_int, c_int, P, P], c_int),
     "tnr_attn_relpos_fwd": ([P, P, c_int, P, P, c_int, c_int, c_int, c_int, POINTER(Dropout), P], c_int),
-    "tnr_attn_relpos_bwd": ([P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, POINTER(Dropout), P], c_int),
+    "tnr_attn_relpos_bwd": ([P, P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, POINTER(Dropout), P], c_int),
     "tnr_attnpool_fwd": ([P, P, c_int, c_int, P, P, P, P, P, c_int, c_int, c_int, P], c_int),
     "tnr_attnpool_bwd": ([P, P, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_int, P], c_int),
     "tnr_user_encoder_fwd": ([P, P, P, P, P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P], c_int),

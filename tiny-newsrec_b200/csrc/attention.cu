@@ -27,6 +27,9 @@ constexpr int PT_BYTES = LMAX * PS * 2;
 constexpr int ATT_FWD_SMEM_PER_WARP = 3 * TILE_BYTES + LMAX * 4 + 2 * LMAX * 4;        // tiles, key mask, rel-pos vector
 constexpr int ATT_BWD_SMEM_PER_WARP = 4 * TILE_BYTES + 2 * PT_BYTES + LMAX * 4 + 2 * LMAX * 4;
 
+int attn_long_bwd_launch(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias, const void* dctx_bf16,
+                         void* dqkv_bf16, float* dbias, float* ws, int n_news, int L, int A, int E, const tnr_dropout* drop,
+                         cudaStream_t st);
 int attn_long_fwd_launch(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias, void* ctx_bf16,
                          int n_news, int L, int A, int E, const tnr_dropout* drop, cudaStream_t st);
 
@@ -406,10 +409,13 @@ extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_fwd(const 
 }
 
 extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_bwd(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias,
-                                   const void* dctx_bf16, void* dqkv_bf16, float* dbias_qkv, int n_news, int L, int A, int E,
-                                   const tnr_dropout* drop, void* stream) {
-  if (check_attn("tnr_attn_relpos_bwd", L, A, E, LMAX)) return 1;      // L > 32: forward only so far
+                                   const void* dctx_bf16, void* dqkv_bf16, float* dbias_qkv, float* workspace, int n_news, int L,
+                                   int A, int E, const tnr_dropout* drop, void* stream) {
+  if (check_attn("tnr_attn_relpos_bwd", L, A, E, 512)) return 1;
   if (n_news == 0) return 0;
+  if (L > LMAX)
+    return attn_long_bwd_launch(qkv_bf16, mask, mask_ld, relbias, dctx_bf16, dqkv_bf16, dbias_qkv, workspace, n_news, L, A, E,
+                                drop, reinterpret_cast<cudaStream_t>(stream));
   const long long items = (long long)n_news * A;
   const int grid = (int)((items + ATT_WARPS - 1) / ATT_WARPS);
   const int smem = ATT_WARPS * ATT_BWD_SMEM_PER_WARP;

@@ -240,6 +240,484 @@ attn_long_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Backward for 32 < L <= 512, two kernels, no atomics on the gradients (deterministic):
+//   dq kernel : block per (news, head, 64-query block), K / V streamed TWICE.  Sweep 1 recomputes the scores and
+//               dP = dO V^T and keeps, online (as the forward keeps m and l), the row maximum, the row sum and
+//               delta_i = sum_j P_ij dP_ij -- so neither the forward's statistics nor its output are needed.
+//               Sweep 2 forms dS = P o (dP - delta) / 8 chunk by chunk and accumulates dQ = dS K.  It also
+//               writes lse_i (log2 units) and delta_i for the second kernel.
+//   dkv kernel: block per (news, head, 64-key block), K / V tiles resident, Q / dO streamed in 64-query chunks.
+//               Phase 1 (warp = 16 queries, the forward's layout, so the dropout bits are the forward's):
+//               P~ = dropout(P) and dS into shared memory; phase 2 (warp = 16 keys): dV += P~^T dO,
+//               dK += dS^T Q with the transposed fragments read by ldmatrix.trans.
+// dP_eff = dP o keep / (1 - p) throughout (gradient w.r.t. the pre-dropout probability).
+// Reference: the autograd backward of tnlrv3/modeling.py:205-231.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lb_load_a(uint32_t (&a)[4][4], const __nv_bfloat16* sA, int row0, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    ldsm_x4(smem_addr(sA + (row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LTS + ks * 16 + (lane >> 4) * 8), a[ks]);
+}
+// A fragments of T^T for the 16 columns [m0, m0 + 16) of a 64 x 64 tile T (rows = the contraction index)
+__device__ __forceinline__ void lb_load_aT(uint32_t (&a)[4][4], const __nv_bfloat16* sT, int m0, int lane) {
+  const int mi = lane >> 3;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    ldsm_x4_t(smem_addr(sT + (ks * 16 + (lane & 7) + (mi >> 1) * 8) * LTS + m0 + (mi & 1) * 8), a[ks]);
+}
+// s[nt] = A (16 x 64) . B^T, B tile = 64 rows (n) x 64 (k)
+__device__ __forceinline__ void lb_mma_abT(float (&s)[8][4], const uint32_t (&a)[4][4], const __nv_bfloat16* sB, int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s[nt][c] = 0.f;
+    uint32_t kb[2][4];
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+      ldsm_x4(smem_addr(sB + (nt * 8 + (lane & 7)) * LTS + half * 32 + (lane >> 3) * 8), kb[half]);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) mma_bf16(s[nt], a[ks], kb[ks >> 1][(ks & 1) * 2], kb[ks >> 1][(ks & 1) * 2 + 1]);
+  }
+}
+// o[nt] += P (16 x 64, A fragments) . B, B tile = 64 rows (k) x 64 (n)
+__device__ __forceinline__ void lb_mma_pb(float (&o)[8][4], const uint32_t (&pa)[4][4], const __nv_bfloat16* sB, int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int kh = 0; kh < 2; ++kh) {
+      uint32_t vb[4];
+      ldsm_x4_t(smem_addr(sB + (kh * 32 + lane) * LTS + nt * 8), vb);
+      mma_bf16(o[nt], pa[kh * 2], vb[0], vb[1]);
+      mma_bf16(o[nt], pa[kh * 2 + 1], vb[2], vb[3]);
+    }
+}
+__device__ __forceinline__ void lb_c_to_a(uint32_t (&pa)[4][4], const float (&s)[8][4]) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    pa[ks][0] = pack_bf16(s[2 * ks][0], s[2 * ks][1]);
+    pa[ks][1] = pack_bf16(s[2 * ks][2], s[2 * ks][3]);
+    pa[ks][2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+    pa[ks][3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+  }
+}
+// raw QK^T accumulators -> scores in log2 units with the key mask and the rel-pos bias added (the forward's code):
+// rows i0 (c = 0, 1) and i0 + 8 (c = 2, 3), keys c0 + nt * 8 + 2 t + {0, 1}.  s_madd is indexed from key c0.
+__device__ __forceinline__ void lb_add_bias(float (&s)[8][4], const float* s_madd_c0, const float* s_rel, int i0, int c0, int L,
+                                            int t) {
+  const int ib = min(i0, L - 1);
+  const float* relp = s_rel + (L - 1 - ib) + c0 + 2 * t;
+  float rel[9][2];
+#pragma unroll
+  for (int nt = 0; nt < 9; ++nt) {
+    const int off = (nt - 1) * 8;
+    const bool ok = (L - 1 - ib) + c0 + 2 * t + off >= 0;
+    rel[nt][0] = ok ? relp[off] : 0.f;
+    rel[nt][1] = ok ? relp[off + 1] : 0.f;
+  }
+  const bool row1_clamped = i0 + 8 > L - 1;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const float2 md = *reinterpret_cast<const float2*>(s_madd_c0 + nt * 8 + 2 * t);
+    const float sc = 0.125f * LOG2E;
+    s[nt][0] = fmaf(s[nt][0], sc, md.x + rel[nt + 1][0]);
+    s[nt][1] = fmaf(s[nt][1], sc, md.y + rel[nt + 1][1]);
+    s[nt][2] = fmaf(s[nt][2], sc, md.x + (row1_clamped ? rel[nt + 1][0] : rel[nt][0]));
+    s[nt][3] = fmaf(s[nt][3], sc, md.y + (row1_clamped ? rel[nt + 1][1] : rel[nt][1]));
+  }
+}
+// keep * scale factors of this thread's 2 x 16 elements of (rows i0 / i0 + 8, key chunk kc): the forward's Philox groups
+__device__ __forceinline__ void lb_keep(float (&kf)[8][4], const DropCfg& dc, long long item, int L, int i0, int k_chunks, int kc,
+                                        int t) {
+#pragma unroll
+  for (int hi = 0; hi < 2; ++hi) {
+    const uint64_t row = (uint64_t)item * (uint64_t)L + (uint64_t)min(i0 + hi * 8, L - 1);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const uint32_t keep = dropout_keep8(dc, ((row * (uint64_t)k_chunks + (uint64_t)kc) * 4 + (uint64_t)t) * 2 + hf);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) kf[hf * 4 + q][hi * 2 + e] = ((keep >> (q * 2 + e)) & 1u) ? dc.scale : 0.f;
+    }
+  }
+}
+
+// the same, multiplied into dp in place (dP_eff)
+__device__ __forceinline__ void lb_apply_keep(float (&dp)[8][4], const DropCfg& dc, long long item, int L, int i0, int k_chunks,
+                                              int kc, int t) {
+#pragma unroll
+  for (int hi = 0; hi < 2; ++hi) {
+    const uint64_t row = (uint64_t)item * (uint64_t)L + (uint64_t)min(i0 + hi * 8, L - 1);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const uint32_t keep = dropout_keep8(dc, ((row * (uint64_t)k_chunks + (uint64_t)kc) * 4 + (uint64_t)t) * 2 + hf);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) dp[hf * 4 + q][hi * 2 + e] *= ((keep >> (q * 2 + e)) & 1u) ? dc.scale : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128, 2)
+attn_long_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ mask, int mask_ld,
+                        const float* __restrict__ relbias, const __nv_bfloat16* __restrict__ dctx,
+                        __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, float* __restrict__ ws_lse,
+                        float* __restrict__ ws_delta, int n_news, int L, int A, int E, int q_blocks, const tnr_dropout drop) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sdO = sQ + LQB * LTS;
+  __nv_bfloat16* sKV = sdO + LQB * LTS;                           // [2 buffers][K tile | V tile]
+  const int k_chunks = (L + LKB - 1) / LKB;
+  float* s_madd = reinterpret_cast<float*>(sKV + 4 * LKB * LTS);  // [k_chunks * 64]
+  float* s_rel = s_madd + k_chunks * LKB;                         // [2L - 1 (+ 64 zeros)]
+  __shared__ int s_live[LONG_LMAX / LKB];
+  __shared__ int s_any;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const long long item = blockIdx.x / q_blocks;
+  const int qb = blockIdx.x % q_blocks;
+  const int n = (int)(item / A), h = (int)(item % A);
+  const int q0 = qb * LQB;
+  const int ld = 3 * E;
+  const __nv_bfloat16* base = qkv + (size_t)n * L * ld + h * LDH;
+  const DropCfg dc = load_drop(drop);
+
+  long_load_tile(sQ, base, q0, L, ld, tid);
+  long_load_tile(sdO, dctx + (size_t)n * L * E + h * LDH, q0, L, E, tid);
+  long_load_tile(sKV, base + E, 0, L, ld, tid);
+  long_load_tile(sKV + LKB * LTS, base + 2 * E, 0, L, ld, tid);
+  cp_async_commit_group();
+  if (tid < LONG_LMAX / LKB) s_live[tid] = 0;
+  if (tid == 0) s_any = 0;
+  __syncthreads();
+  for (int j = tid; j < k_chunks * LKB; j += 128) {
+    float v = -INFINITY;
+    if (j < L) {
+      const bool keep = mask[(size_t)n * mask_ld + j] != 0;
+      v = keep ? 0.f : -10000.0f * LOG2E;
+      if (keep) { s_live[j / LKB] = 1; s_any = 1; }
+    }
+    s_madd[j] = v;
+  }
+  for (int d = tid; d < 2 * L - 1 + LKB; d += 128)
+    s_rel[d] = d < 2 * L - 1 ? relbias[(size_t)h * (2 * L - 1) + d] * LOG2E : 0.f;
+  cp_async_wait_group<0>();
+  __syncthreads();
+
+  uint32_t qa[4][4], da[4][4];
+  lb_load_a(qa, sQ, warp * 16, lane);
+  lb_load_a(da, sdO, warp * 16, lane);
+  const int i0 = q0 + warp * 16 + g;
+  const bool warp_live = q0 + warp * 16 < L;
+  const bool any_key = s_any != 0;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f}, d_run[2] = {0.f, 0.f};
+  float lse[2] = {0.f, 0.f}, delta[2] = {0.f, 0.f};
+  float dq[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dq[nt][c] = 0.f;
+
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    for (int kc = 0; kc < k_chunks; ++kc) {
+      const int c0 = kc * LKB;
+      const int it = sweep * k_chunks + kc;          // the two sweeps share one double-buffered stream of 2 k_chunks items
+      const __nv_bfloat16* sK = sKV + (it & 1) * 2 * LKB * LTS;
+      const __nv_bfloat16* sV = sK + LKB * LTS;
+      if (it + 1 < 2 * k_chunks) {                   // prefetch the next item (chunk 0 again after the first sweep)
+        const int nc = kc + 1 < k_chunks ? kc + 1 : 0;
+        __nv_bfloat16* nK = sKV + ((it + 1) & 1) * 2 * LKB * LTS;
+        long_load_tile(nK, base + E, nc * LKB, L, ld, tid);
+        long_load_tile(nK + LKB * LTS, base + 2 * E, nc * LKB, L, ld, tid);
+        cp_async_commit_group();
+        cp_async_wait_group<1>();
+      } else {
+        cp_async_wait_group<0>();
+      }
+      __syncthreads();
+      if (warp_live && (s_live[kc] || !any_key)) {
+        float s[8][4], dp[8][4];
+        lb_mma_abT(s, qa, sK, lane);
+        lb_add_bias(s, s_madd + c0, s_rel, i0, c0, L, t);
+        lb_mma_abT(dp, da, sV, lane);
+        if (dc.thr16 != 0) lb_apply_keep(dp, dc, item, L, i0, k_chunks, kc, t);
+        if (sweep == 0) {
+#pragma unroll
+          for (int hi = 0; hi < 2; ++hi) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) mx = fmaxf(mx, fmaxf(s[nt][hi * 2], s[nt][hi * 2 + 1]));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            const float m_new = fmaxf(m_run[hi], mx);
+            const float corr = ex2_approx(m_run[hi] - m_new);
+            float sum = 0.f, dsum = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float pv = ex2_approx(s[nt][hi * 2 + e] - m_new);
+                sum += pv;
+                dsum = fmaf(pv, dp[nt][hi * 2 + e], dsum);
+              }
+            l_run[hi] = l_run[hi] * corr + sum;           // per-thread partials: the quad is reduced after the sweep
+            d_run[hi] = d_run[hi] * corr + dsum;
+            m_run[hi] = m_new;
+          }
+        } else {
+          float ds[8][4];
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int hi = c >> 1;
+              const float pv = ex2_approx(s[nt][c] - lse[hi]);
+              ds[nt][c] = pv * (dp[nt][c] - delta[hi]) * 0.125f;
+            }
+          uint32_t pa[4][4];
+          lb_c_to_a(pa, ds);
+          lb_mma_pb(dq, pa, sK, lane);
+        }
+      }
+      __syncthreads();
+    }
+    if (sweep == 0) {
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        float l = l_run[hi], d = d_run[hi];
+        l += __shfl_xor_sync(0xffffffffu, l, 1); l += __shfl_xor_sync(0xffffffffu, l, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 1); d += __shfl_xor_sync(0xffffffffu, d, 2);
+        lse[hi] = m_run[hi] + log2f(l);
+        delta[hi] = d / l;
+        const int i = i0 + hi * 8;
+        if (warp_live && t == 0 && i < L) {
+          ws_lse[(size_t)item * L + i] = lse[hi];
+          ws_delta[(size_t)item * L + i] = delta[hi];
+        }
+      }
+    }
+  }
+  if (!warp_live) return;
+  __nv_bfloat16* sO = sQ + warp * 16 * LTS;       // this warp's (consumed) rows of sQ
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<uint32_t*>(sO + g * LTS + nt * 8 + 2 * t) = pack_bf16(dq[nt][0], dq[nt][1]);
+    *reinterpret_cast<uint32_t*>(sO + (g + 8) * LTS + nt * 8 + 2 * t) = pack_bf16(dq[nt][2], dq[nt][3]);
+  }
+  __syncwarp();
+  __nv_bfloat16* obase = dqkv + (size_t)n * L * ld + h * LDH;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = lane + 32 * it, r = idx >> 3, c = idx & 7;
+    const int row = q0 + warp * 16 + r;
+    if (row < L) *reinterpret_cast<uint4*>(obase + (size_t)row * ld + c * 8) = *reinterpret_cast<const uint4*>(sO + r * LTS + c * 8);
+  }
+  if (dbias != nullptr) {                          // bq gradient: column sums of the bf16 rows just stored
+    float a0 = 0.f, a1 = 0.f;
+    for (int r = 0; r < 16 && q0 + warp * 16 + r < L; ++r) {
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(sO + r * LTS + 2 * lane);
+      a0 += bf16_lo(u); a1 += bf16_hi(u);
+    }
+    atomicAdd(dbias + h * LDH + 2 * lane, a0);
+    atomicAdd(dbias + h * LDH + 2 * lane + 1, a1);
+  }
+}
+
+__global__ void __launch_bounds__(128, 2)
+attn_long_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ mask, int mask_ld,
+                         const float* __restrict__ relbias, const __nv_bfloat16* __restrict__ dctx,
+                         __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, const float* __restrict__ ws_lse,
+                         const float* __restrict__ ws_delta, int n_news, int L, int A, int E, int k_blocks,
+                         const tnr_dropout drop) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sV = sK + LKB * LTS;
+  __nv_bfloat16* sQd = sV + LKB * LTS;                            // [2 buffers][Q tile | dO tile]
+  __nv_bfloat16* sP = sQd + 4 * LQB * LTS;                        // [64 queries][64 keys]  dropout(P)
+  __nv_bfloat16* sS = sP + LQB * LTS;                             // [64 queries][64 keys]  dS
+  float* s_madd = reinterpret_cast<float*>(sS + LQB * LTS);       // [64] this key block
+  float* s_rel = s_madd + LKB;                                    // [2L - 1 (+ 64 zeros)]
+  __shared__ int s_any, s_live;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const long long item = blockIdx.x / k_blocks;
+  const int kb = blockIdx.x % k_blocks;
+  const int n = (int)(item / A), h = (int)(item % A);
+  const int c0 = kb * LKB;
+  const int ld = 3 * E;
+  const int q_chunks = (L + LQB - 1) / LQB;
+  const __nv_bfloat16* base = qkv + (size_t)n * L * ld + h * LDH;
+  const __nv_bfloat16* dobase = dctx + (size_t)n * L * E + h * LDH;
+  const DropCfg dc = load_drop(drop);
+
+  long_load_tile(sK, base + E, c0, L, ld, tid);
+  long_load_tile(sV, base + 2 * E, c0, L, ld, tid);
+  long_load_tile(sQd, base, 0, L, ld, tid);
+  long_load_tile(sQd + LQB * LTS, dobase, 0, L, E, tid);
+  cp_async_commit_group();
+  if (tid == 0) { s_any = 0; s_live = 0; }
+  __syncthreads();
+  for (int j = tid; j < L; j += 128) {
+    if (mask[(size_t)n * mask_ld + j] != 0) {
+      s_any = 1;
+      if (j >= c0 && j < c0 + LKB) s_live = 1;
+    }
+  }
+  if (tid < LKB) {
+    const int j = c0 + tid;
+    s_madd[tid] = j < L ? (mask[(size_t)n * mask_ld + j] != 0 ? 0.f : -10000.0f * LOG2E) : -INFINITY;
+  }
+  for (int d = tid; d < 2 * L - 1 + LKB; d += 128)
+    s_rel[d] = d < 2 * L - 1 ? relbias[(size_t)h * (2 * L - 1) + d] * LOG2E : 0.f;
+  __syncthreads();
+  const bool live = s_live != 0 || s_any == 0;     // a fully masked key block gets exactly zero probability
+
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { dk[nt][c] = 0.f; dv[nt][c] = 0.f; }
+
+  for (int qc = 0; qc < q_chunks && live; ++qc) {
+    const __nv_bfloat16* sQ = sQd + (qc & 1) * 2 * LQB * LTS;
+    const __nv_bfloat16* sdO = sQ + LQB * LTS;
+    if (qc + 1 < q_chunks) {
+      __nv_bfloat16* nQ = sQd + ((qc + 1) & 1) * 2 * LQB * LTS;
+      long_load_tile(nQ, base, (qc + 1) * LQB, L, ld, tid);
+      long_load_tile(nQ + LQB * LTS, dobase, (qc + 1) * LQB, L, E, tid);
+      cp_async_commit_group();
+      cp_async_wait_group<1>();
+    } else {
+      cp_async_wait_group<0>();
+    }
+    __syncthreads();
+    // ---- phase 1: this warp's 16 queries of the chunk against the 64 keys of the block
+    {
+      const int i0 = qc * LQB + warp * 16 + g;
+      uint32_t qa[4][4], da[4][4];
+      lb_load_a(qa, sQ, warp * 16, lane);
+      lb_load_a(da, sdO, warp * 16, lane);
+      float s[8][4], dp[8][4];
+      lb_mma_abT(s, qa, sK, lane);
+      lb_add_bias(s, s_madd, s_rel, i0, c0, L, t);
+      lb_mma_abT(dp, da, sV, lane);
+      float kf[8][4];
+      if (dc.thr16 != 0) {
+        lb_keep(kf, dc, item, L, i0, k_blocks, kb, t);
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) kf[nt][c] = 1.f;
+      }
+      float lse[2], delta[2];
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        const int i = i0 + hi * 8;
+        lse[hi] = i < L ? ws_lse[(size_t)item * L + i] : INFINITY;      // rows past L: probability 0
+        delta[hi] = i < L ? ws_delta[(size_t)item * L + i] : 0.f;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int hi = 0; hi < 2; ++hi) {
+          float pd[2], dsv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float pv = ex2_approx(s[nt][hi * 2 + e] - lse[hi]);
+            pd[e] = pv * kf[nt][hi * 2 + e];
+            dsv[e] = pv * (dp[nt][hi * 2 + e] * kf[nt][hi * 2 + e] - delta[hi]) * 0.125f;
+          }
+          const int r = warp * 16 + g + hi * 8;
+          *reinterpret_cast<uint32_t*>(sP + r * LTS + nt * 8 + 2 * t) = pack_bf16(pd[0], pd[1]);
+          *reinterpret_cast<uint32_t*>(sS + r * LTS + nt * 8 + 2 * t) = pack_bf16(dsv[0], dsv[1]);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: this warp's 16 keys: dV += P~^T dO, dK += dS^T Q
+    {
+      uint32_t pt[4][4];
+      lb_load_aT(pt, sP, warp * 16, lane);
+      lb_mma_pb(dv, pt, sdO, lane);
+      lb_load_aT(pt, sS, warp * 16, lane);
+      lb_mma_pb(dk, pt, sQ, lane);
+    }
+    __syncthreads();
+  }
+  if (!live) cp_async_wait_group<0>();
+  __syncthreads();
+  // dK -> sP, dV -> sS (this warp's 16 rows), then full 128-byte rows to global + bias column sums
+  if (c0 + warp * 16 < L) {
+    __nv_bfloat16* oK = sP + warp * 16 * LTS;
+    __nv_bfloat16* oV = sS + warp * 16 * LTS;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      *reinterpret_cast<uint32_t*>(oK + g * LTS + nt * 8 + 2 * t) = pack_bf16(dk[nt][0], dk[nt][1]);
+      *reinterpret_cast<uint32_t*>(oK + (g + 8) * LTS + nt * 8 + 2 * t) = pack_bf16(dk[nt][2], dk[nt][3]);
+      *reinterpret_cast<uint32_t*>(oV + g * LTS + nt * 8 + 2 * t) = pack_bf16(dv[nt][0], dv[nt][1]);
+      *reinterpret_cast<uint32_t*>(oV + (g + 8) * LTS + nt * 8 + 2 * t) = pack_bf16(dv[nt][2], dv[nt][3]);
+    }
+    __syncwarp();
+    __nv_bfloat16* obase = dqkv + (size_t)n * L * ld + h * LDH;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = lane + 32 * it, r = idx >> 3, c = idx & 7;
+      const int row = c0 + warp * 16 + r;
+      if (row < L) {
+        *reinterpret_cast<uint4*>(obase + (size_t)row * ld + E + c * 8) = *reinterpret_cast<const uint4*>(oK + r * LTS + c * 8);
+        *reinterpret_cast<uint4*>(obase + (size_t)row * ld + 2 * E + c * 8) = *reinterpret_cast<const uint4*>(oV + r * LTS + c * 8);
+      }
+    }
+    if (dbias != nullptr) {
+      float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+      for (int r = 0; r < 16 && c0 + warp * 16 + r < L; ++r) {
+        const uint32_t uk = *reinterpret_cast<const uint32_t*>(oK + r * LTS + 2 * lane);
+        const uint32_t uv = *reinterpret_cast<const uint32_t*>(oV + r * LTS + 2 * lane);
+        k0 += bf16_lo(uk); k1 += bf16_hi(uk); v0 += bf16_lo(uv); v1 += bf16_hi(uv);
+      }
+      atomicAdd(dbias + E + h * LDH + 2 * lane, k0);
+      atomicAdd(dbias + E + h * LDH + 2 * lane + 1, k1);
+      atomicAdd(dbias + 2 * E + h * LDH + 2 * lane, v0);
+      atomicAdd(dbias + 2 * E + h * LDH + 2 * lane + 1, v1);
+    }
+  }
+}
+
+// host launcher used by tnr_attn_relpos_bwd (attention.cu) for L > 32.  ws: 2 * n_news * A * L floats.
+int attn_long_bwd_launch(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias, const void* dctx_bf16,
+                         void* dqkv_bf16, float* dbias, float* ws, int n_news, int L, int A, int E, const tnr_dropout* drop,
+                         cudaStream_t st) {
+  TNR_REQUIRE(L <= LONG_LMAX, "tnr_attn_relpos_bwd: L=%d exceeds %d (the position table of the encoder)", L, LONG_LMAX);
+  TNR_REQUIRE(ws != nullptr, "tnr_attn_relpos_bwd: L=%d > 32 needs a workspace of 2 * n_news * A * L floats", L);
+  const int q_blocks = (L + LQB - 1) / LQB;
+  const int k_chunks = (L + LKB - 1) / LKB;
+  const long long blocks = (long long)n_news * A * q_blocks;
+  TNR_REQUIRE(blocks < (1ll << 31), "tnr_attn_relpos_bwd: too many blocks");
+  float* ws_lse = ws;
+  float* ws_delta = ws + (size_t)n_news * A * L;
+  const int smem_dq = 6 * LQB * LTS * 2 + (k_chunks * LKB + 2 * L - 1 + LKB) * 4;
+  const int smem_dkv = 8 * LQB * LTS * 2 + (LKB + 2 * L - 1 + LKB) * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TNR_CHECK_CUDA(cudaFuncSetAttribute(attn_long_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        6 * LQB * LTS * 2 + (LONG_LMAX + 2 * LONG_LMAX + LKB) * 4));
+    TNR_CHECK_CUDA(cudaFuncSetAttribute(attn_long_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        8 * LQB * LTS * 2 + (LKB + 2 * LONG_LMAX + LKB) * 4));
+    attr_done = true;
+  }
+  attn_long_bwd_dq_kernel<<<(unsigned)blocks, 128, smem_dq, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relbias, reinterpret_cast<const __nv_bfloat16*>(dctx_bf16),
+      reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias, ws_lse, ws_delta, n_news, L, A, E, q_blocks, drop_or_none(drop));
+  TNR_LAUNCH_CHECK();
+  attn_long_bwd_dkv_kernel<<<(unsigned)blocks, 128, smem_dkv, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relbias, reinterpret_cast<const __nv_bfloat16*>(dctx_bf16),
+      reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias, ws_lse, ws_delta, n_news, L, A, E, k_chunks, drop_or_none(drop));
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
+
 // host launcher used by tnr_attn_relpos_fwd (attention.cu) for L > 32
 int attn_long_fwd_launch(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias, void* ctx_bf16,
                          int n_news, int L, int A, int E, const tnr_dropout* drop, cudaStream_t st) {

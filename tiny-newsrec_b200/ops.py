@@ -215,17 +215,33 @@ def attn_fwd(qkv, x, L, relpos, ctx, A, drop=None):
     return ctx
 
 
+_attn_ws = {}
+
+
 @_timed
-def attn_bwd(qkv, x, L, relpos, dctx, dqkv, A, drop=None, dbias=None):
-    """dqkv from dctx; ``dbias`` fp32 [3E] (optional) += column sums of dqkv (the [bq|bk|bv] gradient)."""
-    lib = _ready(qkv)
+def attn_bwd(qkv, x, L, relpos, dctx, dqkv, A, drop=None, dbias=None, workspace=None):
+    """dqkv from dctx; ``dbias`` fp32 [3E] (optional) += column sums of dqkv (the [bq|bk|bv] gradient).
+    L > 32 needs ``workspace`` fp32 [2 * n * A * L] (row statistics between the two kernels); one cached per
+    (device, size) is used when none is passed."""
     n = x.shape[0]
+    lib = _ready(qkv, 1 if L <= 32 else 2)
     E = qkv.shape[1] // 3
     mask_ptr = ctypes.c_void_p(x.data_ptr() + 8 * L)
     _chk_relbias(relpos, A, L)
+    if L > 32 and workspace is None:
+        key = (qkv.device, 2 * n * A * L)
+        workspace = _attn_ws.get(key)
+        if workspace is None:
+            _attn_ws.clear()
+            workspace = _attn_ws[key] = torch.empty(2 * n * A * L, device=qkv.device, dtype=_f32)
+    if workspace is not None:
+        _chk(workspace, _f32, "attn.workspace")
+        if workspace.numel() < 2 * n * A * L:
+            raise _lib.TinyRecError("attn_bwd: workspace too small")
     _lib.check(lib.tnr_attn_relpos_bwd(_ptr(_chk(qkv, _bf16, "attn.qkv")), mask_ptr, x.stride(0),
                                        _ptr(relpos), _ptr(_chk(dctx, _bf16, "dctx")),
-                                       _ptr(_chk(dqkv, _bf16, "dqkv")), _ptr(dbias), n, L, A, E, _dp(drop), _stream()),
+                                       _ptr(_chk(dqkv, _bf16, "dqkv")), _ptr(dbias), _ptr(workspace), n, L, A, E, _dp(drop),
+                                       _stream()),
                "tnr_attn_relpos_bwd")
     return dqkv
 
