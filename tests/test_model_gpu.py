@@ -492,3 +492,41 @@ def test_graphed_train_step_matches_eager_loop():
         if k.endswith(("key.bias", "att_fc2.bias")):     # gradient identically 0 up to rounding noise: Adam turns the
             continue                                     # noise into +-lr steps, different in any two runs
         assert _rel(p1[k], p0[k]) < 2e-3, k
+
+
+def test_kd_step_long_sequence_vs_oracle():
+    """KD train step on long news rows (100 tokens: body-length text): forward through the
+    streamed-KV attention, backward through its dQ / dK-dV kernels; losses, scores and every trainable gradient
+    against the CPU oracle."""
+    import tinyrec.model_bert as mb
+    import tinyrec.synth as synth
+    from oracle import model as om
+    B, H, K, L, M, layers, N = 2, 4, 3, 100, 2, 2, 120
+    news = synth.news_table(N, L=L, seed=1)
+    hist_idx, hmask, cand_idx, label = synth.train_impressions(B, N, H, K, seed=2)
+    tables = synth.teacher_tables(N, M, 256, seed=3)
+    history = torch.from_numpy(news[hist_idx].astype(np.int64))
+    candidate = torch.from_numpy(news[cand_idx].astype(np.int64))
+    th = [torch.from_numpy(t[hist_idx]) for t in tables]
+    tc = [torch.from_numpy(t[cand_idx]) for t in tables]
+    sd = synth.kd_model_state(layers, M, 5, noisy=True)
+    args = synth.demo_args(num_student_layers=layers, num_teachers=M, user_log_length=H)
+    m = mb.Model(args)
+    m.load_state_dict(sd, strict=True)
+    m.cuda().eval()
+    _apply_freeze(m, [0, 1])
+    res = m(history.cuda(), torch.from_numpy(hmask).cuda(), candidate.cuda(), torch.from_numpy(label).cuda(),
+            [t.cuda() for t in th], [t.cuda() for t in tc])
+    res[0].backward()
+    osd = {k: v.clone() for k, v in sd.items()}
+    names = [k for k, p in m.named_parameters() if p.requires_grad]
+    for k in names:
+        osd[k].requires_grad_(True)
+    ref = om.kd_model_forward(osd, history, torch.from_numpy(hmask), candidate, torch.from_numpy(label), th, tc,
+                              layers, False, args.temperature, args.coef)
+    ref[0].backward()
+    assert abs(float(res[0]) - float(ref[0])) < 1e-2 * abs(float(ref[0])) + 1e-4
+    assert _rel(res[4], ref[4].detach()) < 2e-2
+    named = dict(m.named_parameters())
+    for k in names:
+        assert _grad_err(k, named[k].grad, osd[k].grad, named) < 5e-2, k
