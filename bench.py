@@ -431,7 +431,15 @@ def run_tinyrec(a):
             line["cpu_baseline"] = cpu_baseline(wl["layers"], wl["trainable"])
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # A captured graph holds NCCL kernels: tearing the communicator down while it is alive hung the ranks after
+        # the JSON line was out (observed at N=2).  Drop the graph, drain, and leave without the collective teardown.
+        gstep = None
+        import gc
+        gc.collect()
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ----------------------------------------------------------------------------- shared timing helpers

@@ -81,25 +81,33 @@ cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
 //   i32 table rows -> int64 out (the reference converts the int32 news_combined rows with
 //   torch.LongTensor);  f32 table rows -> f32 out.  One warp per output row.
 // ---------------------------------------------------------------------------------
+constexpr int GI_ROWS = 4;          // rows per warp: four index loads, then four row loads, then four stores in flight
 __global__ void __launch_bounds__(256)
 gather_rows_i32_i64_kernel(const int32_t* __restrict__ table, long long n_rows_table, const int32_t* __restrict__ idx,
                            long long n, int W, int64_t* __restrict__ out) {
-  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (r >= n) return;
-  long long src = idx[r];
-  if (src < 0 || src >= n_rows_table) src = 0;          // unknown id -> row 0 (dataloader.py:74)
+  const long long r0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * GI_ROWS;
+  if (r0 >= n) return;
   const int lane = threadIdx.x & 31;
+  long long src[GI_ROWS];
+#pragma unroll
+  for (int k = 0; k < GI_ROWS; ++k) {
+    src[k] = r0 + k < n ? idx[r0 + k] : 0;
+    if (src[k] < 0 || src[k] >= n_rows_table) src[k] = 0;      // unknown id -> row 0 (dataloader.py:74)
+  }
   if ((W & 1) == 0) {
-    // two tokens per lane: one 8-byte load, one 16-byte store (the scalar version moved 4 + 8 bytes per request and
-    // reached 41 % of HBM peak; rows are 2L int32 = 240 B in, 480 B out)
-    const int2* s2 = reinterpret_cast<const int2*>(table + src * W);
-    longlong2* d2 = reinterpret_cast<longlong2*>(out + r * W);
+    // two tokens per lane: one 8-byte load, one 16-byte store (the scalar one-row-per-warp version moved 4 + 8 bytes
+    // per request and reached 41 % of HBM peak; rows are 2L int32 = 240 B in, 480 B out)
     for (int c = lane; c < (W >> 1); c += 32) {
-      const int2 v = s2[c];
-      d2[c] = make_longlong2((long long)v.x, (long long)v.y);
+      int2 v[GI_ROWS];
+#pragma unroll
+      for (int k = 0; k < GI_ROWS; ++k) v[k] = reinterpret_cast<const int2*>(table + src[k] * W)[c];
+#pragma unroll
+      for (int k = 0; k < GI_ROWS; ++k)
+        if (r0 + k < n) reinterpret_cast<longlong2*>(out + (r0 + k) * W)[c] = make_longlong2((long long)v[k].x, (long long)v[k].y);
     }
   } else {
-    for (int c = lane; c < W; c += 32) out[r * W + c] = (int64_t)table[src * W + c];
+    for (int k = 0; k < GI_ROWS && r0 + k < n; ++k)
+      for (int c = lane; c < W; c += 32) out[(r0 + k) * W + c] = (int64_t)table[src[k] * W + c];
   }
 }
 
@@ -299,8 +307,8 @@ TNR_API int tnr_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* s
 TNR_API int tnr_gather_rows_i32_i64(const int32_t* table, long long n_rows_table, const int32_t* idx, long long n, int W,
                                     int64_t* out, void* stream) {
   if (n == 0) return 0;
-  gather_rows_i32_i64_kernel<<<(int)((n + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, n_rows_table,
-                                                                                                      idx, n, W, out);
+  gather_rows_i32_i64_kernel<<<(int)((n + 8 * GI_ROWS - 1) / (8 * GI_ROWS)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      table, n_rows_table, idx, n, W, out);
   TNR_LAUNCH_CHECK();
   return 0;
 }

@@ -156,6 +156,13 @@ class GraphedTrainStep:
         drop.seed.copy_(snap["seed"])
         torch.cuda.synchronize()
 
+    def close(self):
+        """Release the captured graph.  Call this before ``torch.distributed.destroy_process_group()``: the graph
+        holds the NCCL all-reduce kernels of the step, and tearing the communicator down under a live graph hangs."""
+        self.graph = None
+        self.out = None
+        torch.cuda.synchronize()
+
     @staticmethod
     def _clone(batch):
         h, m, c, l, th, tc = batch
