@@ -268,6 +268,12 @@ int tnr_eval_metrics(const float* table, const float* user, const long long* ptr
                      const int8_t* label, long long n_imp, int D, int max_c, double* per_imp,
                      double* sums, float* score_out, void* stream);
 
+/* doc-sim diagnostic: *sum_out += sum over pairs (i, j) int32 [n_pairs, 2] with i != j of the fp32 cosine of
+ * table rows i and j (pairs with i == j or out of range add 0, as the reference skips them).
+ * Replaces the 1 000 000-iteration numpy loop at Tiny-NewsRec/run.py:292-299. */
+int tnr_doc_sim(const float* table, long long n_rows, const int32_t* pairs, long long n_pairs, int D,
+                double* sum_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

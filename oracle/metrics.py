@@ -59,3 +59,16 @@ def eval_reduce(per_impression, total_count):
         if m is not None:
             sums += np.asarray(m, dtype=np.float64)
     return sums / float(total_count), sums
+
+
+def doc_sim(news_scoring, n_pairs, rng):
+    """Tiny-NewsRec/run.py:292-299, verbatim semantics: ``rng`` is a ``random.Random`` (the reference uses the
+    module-level generator)."""
+    total = 0
+    for _ in range(n_pairs):
+        i = rng.randrange(1, len(news_scoring))
+        j = rng.randrange(1, len(news_scoring))
+        if i != j:
+            total += np.dot(news_scoring[i], news_scoring[j]) / (
+                np.linalg.norm(news_scoring[i]) * np.linalg.norm(news_scoring[j]))
+    return total / n_pairs

@@ -530,3 +530,16 @@ def test_kd_step_long_sequence_vs_oracle():
     named = dict(m.named_parameters())
     for k in names:
         assert _grad_err(k, named[k].grad, osd[k].grad, named) < 5e-2, k
+
+
+def test_doc_sim_matches_reference_loop():
+    """run.py:292-299 (mean cosine of random row pairs) on the device against the oracle's verbatim loop, same
+    ``random`` stream; i == j pairs are skipped but counted in the mean."""
+    import random
+    import tinyrec.run as trun
+    from oracle import metrics as omet
+    g = torch.Generator().manual_seed(3)
+    table = torch.randn(40, 256, generator=g) * 0.3 + 0.05
+    got = trun.doc_sim(table.cuda(), n_pairs=5000, rng=random.Random(11))
+    want = omet.doc_sim(table.numpy(), 5000, random.Random(11))
+    assert abs(got - want) < 1e-6, (got, want)

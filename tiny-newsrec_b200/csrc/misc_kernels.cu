@@ -125,6 +125,44 @@ gather_rows_f32_kernel(const float* __restrict__ table, long long n_rows_table, 
 }
 
 // ---------------------------------------------------------------------------------
+// doc-sim diagnostic (reference: Tiny-NewsRec/run.py:292-299): sum over sampled pairs (i, j), i != j, of
+// cos(table[i], table[j]) = dot / (|a| |b|) in fp32 (np.dot / np.linalg.norm on float32 rows), summed in fp64.
+// One warp per pair, eight pairs per block, one fp64 atomic per block.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+doc_sim_kernel(const float* __restrict__ table, long long n_rows, const int32_t* __restrict__ pairs, long long n_pairs,
+               int D, double* __restrict__ sum_out) {
+  __shared__ double s_part[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pidx = (long long)blockIdx.x * 8 + warp;
+  double c = 0.0;
+  if (pidx < n_pairs) {
+    const long long i = pairs[2 * pidx], j = pairs[2 * pidx + 1];
+    if (i != j && i >= 0 && j >= 0 && i < n_rows && j < n_rows) {
+      const float4* a = reinterpret_cast<const float4*>(table + i * D);
+      const float4* b = reinterpret_cast<const float4*>(table + j * D);
+      float dot = 0.f, na = 0.f, nb = 0.f;
+      for (int k = lane; k < D / 4; k += 32) {
+        const float4 x = a[k], y = b[k];
+        dot = fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, fmaf(x.w, y.w, dot))));
+        na = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, na))));
+        nb = fmaf(y.x, y.x, fmaf(y.y, y.y, fmaf(y.z, y.z, fmaf(y.w, y.w, nb))));
+      }
+      dot = warp_sum(dot); na = warp_sum(na); nb = warp_sum(nb);
+      c = (double)(dot / (sqrtf(na) * sqrtf(nb)));
+    }
+  }
+  if (lane == 0) s_part[warp] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    atomicAdd(sum_out, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // impression scoring + ranking metrics (reference: Tiny-NewsRec/run.py:346-361,
 // metrics.py:5-23, sklearn roc_auc_score).  One block per impression:
 //   score_c = table[cand_c] . user ;  skip if labels constant ;
@@ -319,6 +357,17 @@ TNR_API int tnr_gather_rows_f32(const float* table, long long n_rows_table, cons
   if (n == 0) return 0;
   gather_rows_f32_kernel<<<(int)((n + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, n_rows_table, idx,
                                                                                                   n, D, out, out_ld);
+  TNR_LAUNCH_CHECK();
+  return 0;
+}
+
+TNR_API int tnr_doc_sim(const float* table, long long n_rows, const int32_t* pairs, long long n_pairs, int D,
+                        double* sum_out, void* stream) {
+  TNR_REQUIRE(D % 4 == 0 && D > 0, "tnr_doc_sim: D=%d must be a positive multiple of 4", D);
+  TNR_REQUIRE(sum_out != nullptr, "tnr_doc_sim: sum_out (one double, caller-initialised) is required");
+  if (n_pairs == 0) return 0;
+  doc_sim_kernel<<<(int)((n_pairs + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, n_rows, pairs, n_pairs, D,
+                                                                                             sum_out);
   TNR_LAUNCH_CHECK();
   return 0;
 }

@@ -527,3 +527,17 @@ def eval_metrics(table, user, ptr, cand, label, max_c, per_imp, sums=None, score
     _lib.check(lib.tnr_eval_metrics(_ptr(table), _ptr(user), _ptr(ptr), _ptr(cand), _ptr(label), n_imp, table.shape[1],
                                     int(max_c), _ptr(per_imp), _ptr(sums), _ptr(score_out), _stream()), "tnr_eval_metrics")
     return per_imp
+
+
+@_timed
+def doc_sim(table, pairs, sum_out):
+    """sum_out (fp64 [1]) += sum of cos(table[i], table[j]) over the int32 [P, 2] pairs with i != j."""
+    lib = _ready(table)
+    _chk(table, _f32, "doc_sim.table")
+    _chk(pairs, torch.int32, "doc_sim.pairs")
+    _chk(sum_out, torch.float64, "doc_sim.sum")
+    if pairs.dim() != 2 or pairs.shape[1] != 2 or not pairs.is_contiguous() or not table.is_contiguous():
+        raise _lib.TinyRecError("doc_sim: pairs must be contiguous int32 [P, 2]")
+    _lib.check(lib.tnr_doc_sim(_ptr(table), table.shape[0], _ptr(pairs), pairs.shape[0], table.shape[1], _ptr(sum_out),
+                               _stream()), "tnr_doc_sim")
+    return sum_out

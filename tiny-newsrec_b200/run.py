@@ -288,12 +288,28 @@ def evaluate(user_encoder, news_scoring, hist_idx, hist_mask, cand_ptr, cand_idx
     return mean, total
 
 
+def doc_sim(news_scoring, n_pairs=1000000, rng=random):
+    """run.py:292-299: mean cosine similarity of ``n_pairs`` random row pairs drawn from rows 1..N with
+    ``random.randrange`` exactly as the reference draws them (pairs with i == j add nothing but still count in the
+    mean).  The pair list is drawn on the host, the 2 x n_pairs row reads and cosines run in one kernel."""
+    n = news_scoring.shape[0]
+    pairs = np.empty((n_pairs, 2), dtype=np.int32)
+    for k in range(n_pairs):
+        pairs[k, 0] = rng.randrange(1, n)
+        pairs[k, 1] = rng.randrange(1, n)
+    total = torch.zeros(1, device=news_scoring.device, dtype=torch.float64)
+    ops.doc_sim(news_scoring, torch.from_numpy(pairs).to(news_scoring.device), total)
+    return float(total.item()) / n_pairs
+
+
 def test(args, model, news_combined, hist_idx, hist_mask, cand_ptr, cand_idx, labels):
     """run.py:219-379: student news table, then impression scoring with user_log_mask as in args."""
     world, rank, local = par.init_distributed(getattr(args, "enable_hvd", True))
     model.eval()
     news_scoring = build_news_table(model.student.news_encoder, news_combined, batch_size=args.batch_size * 16)
     logging.info("news scoring num: {}".format(news_scoring.shape[0]))
+    if rank == 0 and getattr(args, "doc_sim", True):
+        print(f"=== doc-sim: {doc_sim(news_scoring, getattr(args, 'doc_sim_pairs', 1000000))} ===")      # run.py:292-299
     mean, total = evaluate(model.student.user_encoder, news_scoring, hist_idx, hist_mask, cand_ptr, cand_idx, labels)
     if rank == 0:
         logging.info("[{}] Ed: {}: {}".format(rank, total, "\t".join("{:0.2f}".format(float(x) * 100) for x in mean)))
