@@ -52,7 +52,9 @@ typedef struct {
 int tnr_dropout_mask(const tnr_dropout* drop, long long n, unsigned char* keep, void* stream);
 
 /* ------------------------------------------------------------------ GEMM */
-enum { TNR_ACT_NONE = 0, TNR_ACT_GELU = 1, TNR_ACT_TANH = 2, TNR_ACT_DGELU = 3 };
+enum { TNR_ACT_NONE = 0, TNR_ACT_GELU = 1, TNR_ACT_TANH = 2, TNR_ACT_DGELU = 3,
+       TNR_ACT_GELU_DAUX = 4,   /* C = gelu(z), aux <- gelu'(z) (instead of z): what the FFN1 forward of a trained layer uses */
+       TNR_ACT_MULAUX = 5 };    /* C = acc * aux: the matching dgrad epilogue (dz = (dy W2) * gelu'(z)) */
 enum { TNR_BF16 = 0, TNR_F32 = 1 };
 
 /* C[M,N] = epilogue( A[M,K] . B[N,K]^T )       bf16 operands, fp32 accumulate in TMEM

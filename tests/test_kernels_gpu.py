@@ -759,3 +759,31 @@ def test_attention_long_dropout_adjoint(L):
     for part, nm in enumerate("qkv"):
         sl = slice(part * E, (part + 1) * E)
         assert _rel_err(dqkv[:, sl], qf.grad[:, sl])[0] < 8e-3, nm
+
+
+@pytest.mark.parametrize("M", [500, 4200])
+def test_gemm_gelu_daux_and_mulaux(M):
+    """FFN1 of a trained layer: C = gelu(z), aux = gelu'(z) (ACT_GELU_DAUX); its backward: dz = (dy W2) * aux
+    (ACT_MULAUX) with the fused bias column sums.  M = 500: single-CTA kernels, M = 4 200: CTA-pair kernels."""
+    ops = _ops()
+    N, K = 3072, 768
+    a, b = _randn(M, K, seed=7), _randn(N, K, scale=0.03, seed=8)
+    bias = _randn(N, dtype=torch.float32, scale=0.1, seed=9)
+    out = torch.empty(M, N, device="cuda", dtype=BF)
+    dax = torch.empty(M, N, device="cuda", dtype=BF)
+    ops.gemm(a, b, out, bias=bias, act=ops.ACT_GELU_DAUX, aux=dax)
+    z = (a.float() @ b.float().t() + bias).requires_grad_(True)
+    ref = torch.nn.functional.gelu(z)
+    ref.sum().backward()
+    assert _rel_err(out, ref.detach())[0] < 5e-3
+    assert _rel_err(dax, z.grad)[0] < 5e-3
+    assert float((dax.float() - z.grad).abs().max()) < 8e-3
+    out2 = torch.empty_like(out)
+    ops.gemm(a, b, out2, bias=bias, act=ops.ACT_GELU_DAUX)                 # no aux output: plain GELU
+    assert _rel_err(out2, ref.detach())[0] < 5e-3
+    dy, w = _randn(M, K, seed=29), _randn(K, N, scale=0.03, seed=30)
+    dz = torch.empty(M, N, device="cuda", dtype=BF)
+    cs = torch.zeros(N, device="cuda")
+    ops.gemm(dy, w, dz, b_t=True, act=ops.ACT_MULAUX, aux=dax, colsum=cs)
+    assert _rel_err(dz, (dy.float() @ w.float()) * dax.float())[0] < 5e-3
+    assert _rel_err(cs, dz.float().sum(0))[0] < 1e-5

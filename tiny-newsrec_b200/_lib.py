@@ -10,7 +10,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libtinyrec.so")
 
-ACT_NONE, ACT_GELU, ACT_TANH, ACT_DGELU = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_TANH, ACT_DGELU, ACT_GELU_DAUX, ACT_MULAUX = 0, 1, 2, 3, 4, 5
 BF16, F32 = 0, 1
 
 

@@ -243,6 +243,20 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const DropCfg& d
       unpack8(*reinterpret_cast<const bf16x8*>(p.aux + (size_t)row * p.ldaux + col), z);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] *= gelu_erf_grad(z[i]);
+    } else if (ACT == TNR_ACT_GELU_DAUX) {
+      if (p.aux != nullptr) {
+        float d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = gelu_erf_grad(v[i]);
+        *reinterpret_cast<bf16x8*>(p.aux + (size_t)row * p.ldaux + col) = pack8(d);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    } else if (ACT == TNR_ACT_MULAUX) {
+      float z[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(p.aux + (size_t)row * p.ldaux + col), z);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= z[i];
     }
     if (dc.thr16 != 0) {       // dropout on (dense + bias), before the residual (BertSelfOutput / BertOutput)
       const uint32_t keep = dropout_keep8(dc, ((uint64_t)row * (uint64_t)p.N + (uint64_t)col) >> 3);
@@ -290,6 +304,40 @@ __device__ __forceinline__ void epilogue_preact8(const Params& p, const uint32_t
   *reinterpret_cast<bf16x8*>(box + swz) = o;
 }
 
+// GELU_DAUX, first pass: z = acc + bias; gelu'(z) as bf16 into the staging box (the backward only ever needs the
+// derivative: storing it instead of z turns the dGELU dgrad epilogue into one multiply), gelu(z) as bf16 back into
+// acc[0..3] for the second pass.  Both come from ONE sigmoid evaluation.
+__device__ __forceinline__ void epilogue_gelu_both8(const Params& p, uint32_t* acc, int col, uint8_t* box, uint32_t swz) {
+  f32x2 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = pk2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+  if (p.bias != nullptr && col < p.N) {
+    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
+    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+    v[0] = add2(v[0], pk2(b0.x, b0.y)); v[1] = add2(v[1], pk2(b0.z, b0.w));
+    v[2] = add2(v[2], pk2(b1.x, b1.y)); v[3] = add2(v[3], pk2(b1.z, b1.w));
+  }
+  bf16x8 d;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float s0, s1;
+    gelu_sig2(v[i], s0, s1);
+    const f32x2 sg = pk2(s0, s1);
+    float u0, u1;
+    upk2(mul2(v[i], v[i]), u0, u1);
+    const f32x2 u = pk2(fminf(u0, 64.0f), fminf(u1, 64.0f));
+    const f32x2 qp2 = fma2(fma2(pk2(-0.003515171750f, -0.003515171750f), u, pk2(0.2220338916f, 0.2220338916f)), u,
+                           pk2(1.595015762f, 1.595015762f));
+    const f32x2 ss = fma2(mul2(sg, pk2(-1.0f, -1.0f)), sg, sg);
+    float lo, hi;
+    upk2(fma2(mul2(ss, qp2), v[i], sg), lo, hi);            // gelu'(z), same form as gelu_erf_grad2()
+    d.u[i] = pack_bf16(lo, hi);
+    upk2(mul2(v[i], sg), lo, hi);                          // gelu(z)
+    acc[i] = pack_bf16(lo, hi);
+  }
+  *reinterpret_cast<bf16x8*>(box + swz) = d;
+}
+
 template <int ACT>
 __device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg& dc, const uint32_t* acc, int row, int col,
                                                  uint8_t* out_box, uint8_t* in_box, uint32_t swz) {
@@ -313,6 +361,13 @@ __device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg&
     const bf16x8 zr = *reinterpret_cast<const bf16x8*>(in_box + swz);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = mul2(v[i], gelu_erf_grad2(pk2(bf16_lo(zr.u[i]), bf16_hi(zr.u[i]))));
+  } else if (ACT == TNR_ACT_MULAUX) {
+    const bf16x8 zr = *reinterpret_cast<const bf16x8*>(in_box + swz);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = mul2(v[i], pk2(bf16_lo(zr.u[i]), bf16_hi(zr.u[i])));
+  } else if (ACT == TNR_ACT_GELU_DAUX) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = gelu_erf2(v[i]);       // only reached without an aux output
   }
   if (dc.thr16 != 0) {
     const uint32_t keep = dropout_keep8(dc, ((uint64_t)row * (uint64_t)p.N + (uint64_t)col) >> 3);
@@ -320,7 +375,7 @@ __device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg&
     for (int i = 0; i < 4; ++i)
       v[i] = mul2(v[i], pk2(((keep >> (2 * i)) & 1u) ? dc.scale : 0.f, ((keep >> (2 * i + 1)) & 1u) ? dc.scale : 0.f));
   }
-  if (ACT != TNR_ACT_DGELU && p.in_mode == 1) {
+  if (ACT != TNR_ACT_DGELU && ACT != TNR_ACT_MULAUX && p.in_mode == 1) {
     const bf16x8 rr = *reinterpret_cast<const bf16x8*>(in_box + swz);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = add2(v[i], pk2(bf16_lo(rr.u[i]), bf16_hi(rr.u[i])));
@@ -543,12 +598,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           __syncwarp();
         }
         const int row = row0 + lane;
-        if (ACT == TNR_ACT_GELU && p.aux_out) {
-          // pre-activation z = acc + bias goes out first through the same box
+        if ((ACT == TNR_ACT_GELU || ACT == TNR_ACT_GELU_DAUX) && p.aux_out) {
+          // pre-activation z = acc + bias (GELU) or gelu'(z) (GELU_DAUX) goes out first through the same box
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const uint32_t swz = swz_row + (uint32_t)((c ^ (lane & 7)) << 4);
-            epilogue_preact8(p, r + c * 8, col0 + c * 8, box, swz);
+            if (ACT == TNR_ACT_GELU_DAUX) epilogue_gelu_both8(p, r + c * 8, col0 + c * 8, box, swz);
+            else epilogue_preact8(p, r + c * 8, col0 + c * 8, box, swz);
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -562,7 +618,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint32_t swz = swz_row + (uint32_t)((c ^ (lane & 7)) << 4);
-          epilogue_staged8<ACT>(p, dc, r + c * 8, row, col0 + c * 8, box, box, swz);
+          if (ACT == TNR_ACT_GELU_DAUX && p.aux_out) {          // gelu(z) was packed into r[c*8 .. +3] by the first pass
+            bf16x8 o;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o.u[i] = r[c * 8 + i];
+            *reinterpret_cast<bf16x8*>(box + swz) = o;
+          } else {
+            epilogue_staged8<ACT>(p, dc, r + c * 8, row, col0 + c * 8, box, box, swz);
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -691,6 +754,8 @@ static int dispatch_act_cta2(const CUtensorMap* maps, const Params& p, int grid,
     case TNR_ACT_GELU: return launch<256, false, B_MN, TNR_ACT_GELU, true, true>(maps, p, grid, st);
     case TNR_ACT_TANH: return launch<256, false, B_MN, TNR_ACT_TANH, true, true>(maps, p, grid, st);
     case TNR_ACT_DGELU: return launch<256, false, B_MN, TNR_ACT_DGELU, true, true>(maps, p, grid, st);
+    case TNR_ACT_GELU_DAUX: return launch<256, false, B_MN, TNR_ACT_GELU_DAUX, true, true>(maps, p, grid, st);
+    case TNR_ACT_MULAUX: return launch<256, false, B_MN, TNR_ACT_MULAUX, true, true>(maps, p, grid, st);
   }
   set_error("tnr_gemm_bf16: unknown act %d", p.act);
   return 1;
@@ -705,6 +770,8 @@ static int dispatch_act(const CUtensorMap* maps, const Params& p, int grid, cuda
     case TNR_ACT_GELU: return launch<BN, A_MN, B_MN, TNR_ACT_GELU, true>(maps, p, grid, st);
     case TNR_ACT_TANH: return launch<BN, A_MN, B_MN, TNR_ACT_TANH, true>(maps, p, grid, st);
     case TNR_ACT_DGELU: return launch<BN, A_MN, B_MN, TNR_ACT_DGELU, true>(maps, p, grid, st);
+    case TNR_ACT_GELU_DAUX: return launch<BN, A_MN, B_MN, TNR_ACT_GELU_DAUX, true>(maps, p, grid, st);
+    case TNR_ACT_MULAUX: return launch<BN, A_MN, B_MN, TNR_ACT_MULAUX, true>(maps, p, grid, st);
   }
   set_error("tnr_gemm_bf16: unknown act %d", p.act);
   return 1;
@@ -739,7 +806,8 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
   TNR_REQUIRE(a->residual == nullptr || (a->ldr % 8 == 0 && (uintptr_t)a->residual % 16 == 0),
               "tnr_gemm_bf16: residual alignment");
   TNR_REQUIRE(a->aux == nullptr || (a->ldaux % 8 == 0 && (uintptr_t)a->aux % 16 == 0), "tnr_gemm_bf16: aux alignment");
-  TNR_REQUIRE(a->act != TNR_ACT_DGELU || a->aux != nullptr, "tnr_gemm_bf16: DGELU needs aux (pre-activation)");
+  TNR_REQUIRE((a->act != TNR_ACT_DGELU && a->act != TNR_ACT_MULAUX) || a->aux != nullptr,
+              "tnr_gemm_bf16: DGELU / MULAUX need aux (pre-activation / multiplier)");
   TNR_REQUIRE(a->bias == nullptr || (uintptr_t)a->bias % 16 == 0, "tnr_gemm_bf16: bias alignment");
   const bool atomic = a->split_k > 1 || a->accumulate != 0;
   TNR_REQUIRE(!atomic || a->c_dtype == TNR_F32, "tnr_gemm_bf16: split_k/accumulate require fp32 C");
@@ -791,17 +859,17 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
   p.in_mode = 0; p.aux_out = 0;
   maps[2] = ta; maps[3] = ta; maps[4] = ta;        // placeholders when unused
   if (p.epi_tma) {
-    TNR_REQUIRE(!(a->act == TNR_ACT_DGELU && a->residual != nullptr),
-                "tnr_gemm_bf16: DGELU with a residual is not supported for bf16 outputs");
+    TNR_REQUIRE(!((a->act == TNR_ACT_DGELU || a->act == TNR_ACT_MULAUX) && a->residual != nullptr),
+                "tnr_gemm_bf16: DGELU / MULAUX with a residual is not supported for bf16 outputs");
     if (make_map(&maps[2], a->C, a->N, a->M, a->ldc, 64, 32)) return 1;
-    if (a->act == TNR_ACT_DGELU) {
+    if (a->act == TNR_ACT_DGELU || a->act == TNR_ACT_MULAUX) {
       p.in_mode = 2;
       if (make_map(&maps[3], a->aux, a->N, a->M, a->ldaux, 64, 32)) return 1;
     } else if (a->residual != nullptr) {
       p.in_mode = 1;
       if (make_map(&maps[3], a->residual, a->N, a->M, a->ldr, 64, 32)) return 1;
     }
-    if (a->act == TNR_ACT_GELU && a->aux != nullptr) {
+    if ((a->act == TNR_ACT_GELU || a->act == TNR_ACT_GELU_DAUX) && a->aux != nullptr) {
       p.aux_out = 1;
       if (make_map(&maps[4], a->aux, a->N, a->M, a->ldaux, 64, 32)) return 1;
     }

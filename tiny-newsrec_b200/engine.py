@@ -303,7 +303,8 @@ class Encoder:
             ops.attn_fwd(qkv, x, L, relpos, ctx, self.A, drop=dmk(drop_site(i, KIND_ATTN), pa))
             ops.gemm(ctx, wo, pre1, bias=lr.o.bias, residual=cur, drop=dmk(drop_site(i, KIND_ATT_OUT), ph))
             ops.layernorm_fwd(pre1, lr.ln1.weight, lr.ln1.bias, LN_EPS, x1)
-            ops.gemm(x1, w1, h, bias=lr.f1.bias, act=ops.ACT_GELU, aux=z)
+            # trained layers keep gelu'(z) (not z) for the backward: its dgrad epilogue is then a single multiply
+            ops.gemm(x1, w1, h, bias=lr.f1.bias, act=ops.ACT_GELU_DAUX if z is not None else ops.ACT_GELU, aux=z)
             ops.gemm(h, w2, pre2, bias=lr.f2.bias, residual=x1, drop=dmk(drop_site(i, KIND_FFN_OUT), ph))
             ops.layernorm_fwd(pre2, lr.ln2.weight, lr.ln2.bias, LN_EPS, xout)
             cur = xout
@@ -381,7 +382,7 @@ class Encoder:
                 self._wgrad(flat, lr.f2.weight, dd, sv["h"])
             # dz = (dd @ W2) * gelu'(z); its column sums (the intermediate.dense bias gradient) come out of the
             # same epilogue
-            ops.gemm(dd, w2, dz, b_t=True, act=ops.ACT_DGELU, aux=sv["z"],
+            ops.gemm(dd, w2, dz, b_t=True, act=ops.ACT_MULAUX, aux=sv["z"],
                      colsum=flat.g_view(lr.f1.bias) if train else None)
             if train:
                 self._wgrad(flat, lr.f1.weight, dz, sv["x1"])

@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ACT_DGELU, ACT_GELU, ACT_NONE, ACT_TANH, BF16, F32, Dropout, GemmArgs  # noqa: F401
+from ._lib import ACT_DGELU, ACT_GELU, ACT_GELU_DAUX, ACT_MULAUX, ACT_NONE, ACT_TANH, BF16, F32, Dropout, GemmArgs  # noqa: F401
 
 _bf16 = torch.bfloat16
 _f32 = torch.float32
@@ -83,8 +83,9 @@ def _timed(fn):
             M, K = (A.shape[1], A.shape[0]) if k.get("a_t") else (A.shape[0], A.shape[1])
             N = Bm.shape[1] if k.get("b_t") else Bm.shape[0]
             tag = f"{M}x{N}x{K}" + ("/wgrad" if k.get("a_t") else "/dgrad" if k.get("b_t") else "") + \
-                  {ACT_NONE: "", ACT_GELU: "+gelu", ACT_TANH: "+tanh", ACT_DGELU: "+dgelu"}[k.get("act", ACT_NONE)] + \
-                  ("+aux" if k.get("aux") is not None and k.get("act") == ACT_GELU else "") + \
+                  {ACT_NONE: "", ACT_GELU: "+gelu", ACT_TANH: "+tanh", ACT_DGELU: "+dgelu", ACT_GELU_DAUX: "+gelu",
+                   ACT_MULAUX: "+mulaux"}[k.get("act", ACT_NONE)] + \
+                  ("+aux" if k.get("aux") is not None and k.get("act") in (ACT_GELU, ACT_GELU_DAUX) else "") + \
                   ("+res" if k.get("residual") is not None else "") + ("+bias" if k.get("bias") is not None else "")
         stats.op_events.append((fn.__name__, tag, e0, e1))
         return r
