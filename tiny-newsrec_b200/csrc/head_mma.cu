@@ -585,60 +585,79 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
 }
 
 constexpr int UP_WARPS = 4;
-template <bool BLEND>
+// NVT = float4 per lane and row the kernel is compiled for (D <= 128 NVT): D = 256 -> 2, no predicated-off slots.
+// The rows with mask != 0 are compacted first (front-padded histories: about half of the H rows), so the streaming
+// loop runs over live rows only, eight rows of loads in flight per warp; in the pad_doc branch the masked rows are
+// all pad_doc and enter as (sum of their weights) * pad_doc at the end.
+template <bool BLEND, int NVT>
 __global__ void __launch_bounds__(UP_WARPS * 32)
 ue_pool_kernel(const float* __restrict__ vecs, const int32_t* __restrict__ idx, long long n_rows,
                const float* __restrict__ mask, const float* __restrict__ pad, const float* __restrict__ b2,
                int use_mask, float* __restrict__ logits_a, float* __restrict__ user, int B, int H, int D) {
-  __shared__ float s_al[UP_WARPS][UE_HMAX];
-  __shared__ float s_m[UP_WARPS][UE_HMAX];
-  __shared__ size_t s_row[UP_WARPS][UE_HMAX];
+  __shared__ float s_al[UP_WARPS][UE_HMAX];              // compacted: weight of live row k
+  __shared__ float s_m[UP_WARPS][UE_HMAX];               // compacted: its mask value
+  __shared__ size_t s_row[UP_WARPS][UE_HMAX];            // compacted: its row offset
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * UP_WARPS + warp;
   if (b >= B) return;
   const float bias2 = b2[0];
-  float part = 0.f;
-  for (int h = lane; h < H; h += 32) {
-    const size_t r = (size_t)b * H + h;
-    float al = __expf(logits_a[r] + bias2);
-    const float m = mask[r];
-    if (use_mask) al *= m;
-    part += al;
-    s_al[warp][h] = al;
-    s_m[warp][h] = m;
-    size_t src = r;
-    if (idx != nullptr) {
-      const long long v = idx[r];
-      src = (v >= 0 && v < n_rows) ? (size_t)v : 0;
+  float part = 0.f, padw = 0.f;
+  float al_own[2] = {0.f, 0.f};                          // this lane's rows h = lane, lane + 32 (H <= 64)
+  int n_live = 0;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int h = lane + 32 * j;
+    float al = 0.f, m = 0.f;
+    size_t src = 0;
+    const bool in = h < H;
+    if (in) {
+      const size_t r = (size_t)b * H + h;
+      al = __expf(logits_a[r] + bias2);
+      m = mask[r];
+      if (use_mask) al *= m;
+      src = r;
+      if (idx != nullptr) {
+        const long long v = idx[r];
+        src = (v >= 0 && v < n_rows) ? (size_t)v : 0;
+      }
     }
-    s_row[warp][h] = src * D;
+    al_own[j] = al;
+    part += al;
+    const bool live = in && m != 0.f;
+    if (BLEND && in && !live) padw += al;
+    const unsigned bal = __ballot_sync(0xffffffffu, live);
+    if (live) {
+      const int pos = n_live + __popc(bal & ((1u << lane) - 1u));
+      s_al[warp][pos] = al;
+      s_m[warp][pos] = m;
+      s_row[warp][pos] = src * D;
+    }
+    n_live += __popc(bal);
   }
   part = warp_sum(part);
+  padw = warp_sum(padw);
   const float inv = 1.0f / (part + 1e-8f);
   __syncwarp();
-  for (int h = lane; h < H; h += 32) logits_a[(size_t)b * H + h] = s_al[warp][h] * inv;      // a_out
-  const int NV = (D + 127) >> 7;                          // float4 per lane and row (D % 4 == 0, D <= 1024)
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    if (lane + 32 * j < H) logits_a[(size_t)b * H + lane + 32 * j] = al_own[j] * inv;       // a_out
   const int D4 = D >> 2;
-  float4 acc[8];
+  float4 acc[NVT], pd[NVT];
 #pragma unroll
-  for (int v = 0; v < 8; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 pd[8];
-  if (BLEND) {
-#pragma unroll
-    for (int v = 0; v < 8; ++v)
-      if (v < NV && v * 32 + lane < D4) pd[v] = *reinterpret_cast<const float4*>(pad + (v * 32 + lane) * 4);
+  for (int v = 0; v < NVT; ++v) {
+    acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pd[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (BLEND && v * 32 + lane < D4) pd[v] = *reinterpret_cast<const float4*>(pad + (v * 32 + lane) * 4);
   }
-#pragma unroll 5
-  for (int h = 0; h < H; ++h) {
-    const float a = s_al[warp][h] * inv;
-    const float* row = vecs + s_row[warp][h];
-    const float m = s_m[warp][h], om = 1.0f - m;
-    if (!BLEND && m == 0.f) continue;                     // weight exactly 0 (padding rows: index 0, a hot line)
+#pragma unroll 8
+  for (int k = 0; k < n_live; ++k) {
+    const float a = s_al[warp][k] * inv;
+    const float* row = vecs + s_row[warp][k];
+    const float m = s_m[warp][k], om = 1.0f - m;
 #pragma unroll
-    for (int v = 0; v < 8; ++v) {
-      if (v < NV && v * 32 + lane < D4) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m != 0.f) x = *reinterpret_cast<const float4*>(row + (v * 32 + lane) * 4);
+    for (int v = 0; v < NVT; ++v) {
+      if (v * 32 + lane < D4) {
+        float4 x = *reinterpret_cast<const float4*>(row + (v * 32 + lane) * 4);
         if (BLEND) {
           x.x = x.x * m + pd[v].x * om; x.y = x.y * m + pd[v].y * om;
           x.z = x.z * m + pd[v].z * om; x.w = x.w * m + pd[v].w * om;
@@ -648,9 +667,25 @@ ue_pool_kernel(const float* __restrict__ vecs, const int32_t* __restrict__ idx, 
       }
     }
   }
+  const float pw = padw * inv;
 #pragma unroll
-  for (int v = 0; v < 8; ++v)
-    if (v < NV && v * 32 + lane < D4) *reinterpret_cast<float4*>(user + (size_t)b * D + (v * 32 + lane) * 4) = acc[v];
+  for (int v = 0; v < NVT; ++v)
+    if (v * 32 + lane < D4) {
+      if (BLEND) {
+        acc[v].x = fmaf(pw, pd[v].x, acc[v].x); acc[v].y = fmaf(pw, pd[v].y, acc[v].y);
+        acc[v].z = fmaf(pw, pd[v].z, acc[v].z); acc[v].w = fmaf(pw, pd[v].w, acc[v].w);
+      }
+      *reinterpret_cast<float4*>(user + (size_t)b * D + (v * 32 + lane) * 4) = acc[v];
+    }
+}
+
+template <bool BLEND>
+static void ue_pool_launch(int pgrid, cudaStream_t st, const float* vecs, const int32_t* idx, long long n_rows, const float* mask,
+                           const float* pad, const float* b2, int use_mask, float* a_out, float* user, int B, int H, int D) {
+  if (D <= 128) ue_pool_kernel<BLEND, 1><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad, b2, use_mask, a_out, user, B, H, D);
+  else if (D <= 256) ue_pool_kernel<BLEND, 2><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad, b2, use_mask, a_out, user, B, H, D);
+  else if (D <= 512) ue_pool_kernel<BLEND, 4><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad, b2, use_mask, a_out, user, B, H, D);
+  else ue_pool_kernel<BLEND, 8><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad, b2, use_mask, a_out, user, B, H, D);
 }
 
 // ----------------------------------------------------------------------------------
@@ -949,11 +984,11 @@ TNR_API int tnr_user_encoder_score(const float* vecs, long long n_rows, const in
   if (use_mask) {
     ue_logits_kernel<false><<<grid, UL_THREADS, smem, st>>>(p);
     TNR_LAUNCH_CHECK();
-    ue_pool_kernel<false><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad_doc, b2, 1, a_out, user, B, H, D);
+    ue_pool_launch<false>(pgrid, st, vecs, idx, n_rows, mask, pad_doc, b2, 1, a_out, user, B, H, D);
   } else {
     ue_logits_kernel<true><<<grid, UL_THREADS, smem, st>>>(p);
     TNR_LAUNCH_CHECK();
-    ue_pool_kernel<true><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad_doc, b2, 0, a_out, user, B, H, D);
+    ue_pool_launch<true>(pgrid, st, vecs, idx, n_rows, mask, pad_doc, b2, 0, a_out, user, B, H, D);
   }
   TNR_LAUNCH_CHECK();
   return 0;

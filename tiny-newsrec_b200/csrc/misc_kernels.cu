@@ -191,20 +191,38 @@ eval_metrics_kernel(const float* __restrict__ table, const float* __restrict__ u
   if (tid == 0) s_pos = 0;
   __syncthreads();
   int npos_local = 0;
-  for (int c = warp; c < C; c += EVAL_THREADS / 32) {
-    const float* row = table + (size_t)cand[p0 + c] * D;
-    float t = 0.f;
+  // four candidates per warp and pass: their index loads, then their row loads, are all issued before the first
+  // reduction (one row in flight per warp left the kernel latency-bound: 1.4 TB/s of candidate rows)
+  constexpr int CPW = 4;
+  for (int c0 = warp * CPW; c0 < C; c0 += (EVAL_THREADS / 32) * CPW) {
+    const float* row[CPW];
+#pragma unroll
+    for (int k = 0; k < CPW; ++k) row[k] = table + (size_t)(c0 + k < C ? cand[p0 + c0 + k] : 0) * D;
+    float t[CPW];
+#pragma unroll
+    for (int k = 0; k < CPW; ++k) t[k] = 0.f;
     for (int d = lane * 4; d < D; d += 128) {
-      const float4 x = *reinterpret_cast<const float4*>(row + d);
-      t = fmaf(x.x, s_user[d], fmaf(x.y, s_user[d + 1], fmaf(x.z, s_user[d + 2], fmaf(x.w, s_user[d + 3], t))));
+      float4 x[CPW];
+#pragma unroll
+      for (int k = 0; k < CPW; ++k) x[k] = *reinterpret_cast<const float4*>(row[k] + d);
+      const float4 u = *reinterpret_cast<const float4*>(s_user + d);
+#pragma unroll
+      for (int k = 0; k < CPW; ++k) t[k] = fmaf(x[k].x, u.x, fmaf(x[k].y, u.y, fmaf(x[k].z, u.z, fmaf(x[k].w, u.w, t[k]))));
     }
-    t = warp_sum(t);
+#pragma unroll
+    for (int k = 0; k < CPW; ++k) t[k] = warp_sum(t[k]);
     if (lane == 0) {
-      s_score[c] = t;
-      const int8_t y = label[p0 + c];
-      s_lab[c] = y;
-      npos_local += (y != 0);
-      if (score_out != nullptr) score_out[p0 + c] = t;
+#pragma unroll
+      for (int k = 0; k < CPW; ++k) {
+        const int c = c0 + k;
+        if (c < C) {
+          s_score[c] = t[k];
+          const int8_t y = label[p0 + c];
+          s_lab[c] = y;
+          npos_local += (y != 0);
+          if (score_out != nullptr) score_out[p0 + c] = t[k];
+        }
+      }
     }
   }
   if (lane == 0 && npos_local) atomicAdd(&s_pos, npos_local);
