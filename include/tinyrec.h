@@ -181,10 +181,11 @@ int tnr_user_encoder_fwd_gather(const float* table, long long n_rows, const int3
  * between the two kernels).  D % 32 == 0, D <= 256, Q <= 208, H <= 64. */
 long long tnr_user_encoder_packed_w1_floats(int D);
 int tnr_user_encoder_pack_w1(const float* W1, float* packed, int D, int Q, void* stream);
+long long tnr_user_encoder_score_ws_bytes(int B, int H);
 int tnr_user_encoder_score(const float* vecs, long long n_rows, const int32_t* idx, const float* mask,
                            const float* pad_doc, const float* w1_packed, const float* b1, const float* w2,
-                           const float* b2, int use_mask, float* user, float* a_out, int B, int H, int D, int Q,
-                           void* stream);
+                           const float* b2, int use_mask, float* user, float* a_out, void* workspace, int B,
+                           int H, int D, int Q, void* stream);
 /* d_user [B,D] -> d_vecs += [B*H, D]; dpad/dW1/db1/dw2/db2 += (fp32 atomics).
  * scratch: fp32 [B*H*(Q+D)] workspace (grad at the fc1 pre-activation + blended inputs; dW1 is then
  * one TN GEMM over all impressions). */

@@ -405,8 +405,25 @@ struct UlParams {
   long long n_rows;
   const float *mask, *pad, *W1, *b1, *w2;     // W1: the PACKED copy (ue_pack_w1_kernel)
   float* logits;              // [R], zero-initialised
+  const int32_t* live;        // [n_live] ids of the rows with mask != 0 (ue_compact_kernel; any order)
+  const int32_t* n_live;      // device scalar
+  float* c_pad;               // device scalar, zero-initialised: logit of a pad_doc row (BLEND), two halves add into it
   int R, D, Q;
 };
+
+// live[] <- the rows r < R with mask[r] != 0, in any order (warp-aggregated atomic append).  Only these go through
+// the logits GEMM: at MIND history lengths about half of all (b, h) are front padding.
+__global__ void __launch_bounds__(256)
+ue_compact_kernel(const float* __restrict__ mask, int R, int32_t* __restrict__ live, int32_t* __restrict__ n_live) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool is_live = r < R && mask[r] != 0.f;
+  const unsigned bal = __ballot_sync(0xffffffffu, is_live);
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0 && bal) base = atomicAdd(n_live, __popc(bal));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (is_live) live[base + __popc(bal & ((1u << lane) - 1u))] = r;
+}
 
 // Wp[half][q][D + 4] = tf32(W1[half * 104 + q][d]) for d < D and half * 104 + q < Q, else 0: each half is one
 // contiguous block already in the padded shared-memory layout (conflict-free B-fragment reads) and already rounded.
@@ -453,7 +470,8 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
   float* sPad = sW2 + UL_HALF;                           // [D]    (BLEND)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int half = blockIdx.x & 1;
-  const int n_tiles = (p.R + UL_ROWS - 1) / UL_ROWS;
+  const int n_live = *p.n_live;
+  const int n_tiles = (n_live + UL_ROWS - 1) / UL_ROWS;
   const int tile0 = blockIdx.x >> 1, tstride = gridDim.x >> 1;
   const int my_tiles = tile0 < n_tiles ? (n_tiles - tile0 + tstride - 1) / tstride : 0;
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
@@ -481,15 +499,16 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
     xok = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int r = r0 + (tid >> 3) + 32 * i;
-      // Rows with mask == 0 are not read at all: they pool with weight 0 (use_mask) or blend to pad_doc exactly
-      // (v * 0 + pad * 1), and they are the front padding of short histories -- index 0 for half of all (b, h) at
-      // MIND's history lengths, i.e. one 1 KB table row hammered by every SM through L2 (cp.async.cg bypasses L1):
-      // that hot line, not the GEMM, set the time of every version of this kernel (~500 us -> 190 us without it).
-      const bool ok = r < p.R && p.mask[r] != 0.f;
-      size_t src = ok ? (size_t)r : 0;
+      const int li = r0 + (tid >> 3) + 32 * i;
+      // Rows with mask == 0 never get here (the tiles walk the compacted live list): they pool with weight 0
+      // (use_mask) or blend to pad_doc exactly (v * 0 + pad * 1), and they are the front padding of short histories --
+      // index 0 for half of all (b, h) at MIND's history lengths, i.e. one 1 KB table row hammered by every SM
+      // through L2 (cp.async.cg bypasses L1): that hot line, not the GEMM, set the time of the first four versions
+      // of this kernel (~500 us -> 190 us without it).
+      const bool ok = li < n_live;
+      size_t src = ok ? (size_t)p.live[li] : 0;
       if (p.idx != nullptr && ok) {
-        const long long v = p.idx[r];
+        const long long v = p.idx[src];
         src = (v >= 0 && v < p.n_rows) ? (size_t)v : 0;  // unknown id -> row 0 (dataloader.py:74)
       }
       xsrc[i] = p.vecs + src * D + (tid & 7) * 4;
@@ -511,7 +530,38 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
   load(1);
   float acc[2][UL_NT][4];
   float rm[2][2], rom[2][2];                             // row mask and 1 - mask of this thread's 4 rows (BLEND)
+  int rid[2][2];                                         // their row ids (-1: past the live list)
   hm_mbar_wait(bar, 0);                                  // W1 half resident
+  if (BLEND && blockIdx.x < 2 && warp == 0) {
+    // logit of a row that IS pad_doc (every masked row in this branch), this CTA's column half: one 16-row MMA tile
+    __syncwarp();
+    float pacc[UL_NT][4];
+#pragma unroll
+    for (int nt = 0; nt < UL_NT; ++nt)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) pacc[nt][c] = 0.f;
+    const uint32_t* wsp = reinterpret_cast<const uint32_t*>(sW);
+    for (int k8 = 0; k8 < D / 8; ++k8) {
+      const uint32_t p0 = f2tf32(p.pad[k8 * 8 + t]), p1 = f2tf32(p.pad[k8 * 8 + t + 4]);
+      const uint32_t a[4] = {p0, p0, p1, p1};
+#pragma unroll
+      for (int nt = 0; nt < UL_NT; ++nt) {
+        const uint32_t* wr = wsp + (nt * 8 + g) * DS + k8 * 8 + t;
+        mma_tf32(pacc[nt], a, wr[0], wr[4]);
+      }
+    }
+    float cp = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < UL_NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = half * UL_HALF + nt * 8 + 2 * t + e;
+        if (col < Q) cp = fmaf(tanh_exp(pacc[nt][e] + p.b1[col]), p.w2[col], cp);
+      }
+    cp += __shfl_xor_sync(0xffffffffu, cp, 1);
+    cp += __shfl_xor_sync(0xffffffffu, cp, 2);
+    if (lane == 0) atomicAdd(p.c_pad, cp);
+  }
   for (int item = 0; item < n_items; ++item) {
     const int tl = item / NK, kc = item - tl * NK;
     const int r0 = (tile0 + tl * tstride) * UL_ROWS;
@@ -525,16 +575,17 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
         for (int nt = 0; nt < UL_NT; ++nt)
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
-      if (BLEND) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int hi = 0; hi < 2; ++hi) {
-            const int r = r0 + warp * 32 + mt * 16 + g + hi * 8;
-            rm[mt][hi] = r < p.R ? p.mask[r] : 0.f;
+        for (int hi = 0; hi < 2; ++hi) {
+          const int li = r0 + warp * 32 + mt * 16 + g + hi * 8;
+          rid[mt][hi] = li < n_live ? p.live[li] : -1;
+          if (BLEND) {
+            rm[mt][hi] = rid[mt][hi] >= 0 ? p.mask[rid[mt][hi]] : 0.f;
             rom[mt][hi] = 1.0f - rm[mt][hi];
           }
-      }
+        }
     }
     const float* xs = sX + (item % UL_STAGES) * UL_ROWS * UL_XS;
     const uint32_t* ws = reinterpret_cast<const uint32_t*>(sW) + kc * UL_KC;
@@ -576,8 +627,7 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
             }
           part += __shfl_xor_sync(0xffffffffu, part, 1);
           part += __shfl_xor_sync(0xffffffffu, part, 2);
-          const int r = r0 + warp * 32 + mt * 16 + g + hi * 8;
-          if (t == 0 && r < p.R) atomicAdd(p.logits + r, part);
+          if (t == 0 && rid[mt][hi] >= 0) atomicAdd(p.logits + rid[mt][hi], part);
         }
     }
   }
@@ -593,7 +643,8 @@ template <bool BLEND, int NVT>
 __global__ void __launch_bounds__(UP_WARPS * 32)
 ue_pool_kernel(const float* __restrict__ vecs, const int32_t* __restrict__ idx, long long n_rows,
                const float* __restrict__ mask, const float* __restrict__ pad, const float* __restrict__ b2,
-               int use_mask, float* __restrict__ logits_a, float* __restrict__ user, int B, int H, int D) {
+               const float* __restrict__ c_pad, int use_mask, float* __restrict__ logits_a, float* __restrict__ user, int B,
+               int H, int D) {
   __shared__ float s_al[UP_WARPS][UE_HMAX];              // compacted: weight of live row k
   __shared__ float s_m[UP_WARPS][UE_HMAX];               // compacted: its mask value
   __shared__ size_t s_row[UP_WARPS][UE_HMAX];            // compacted: its row offset
@@ -612,8 +663,9 @@ ue_pool_kernel(const float* __restrict__ vecs, const int32_t* __restrict__ idx, 
     const bool in = h < H;
     if (in) {
       const size_t r = (size_t)b * H + h;
-      al = __expf(logits_a[r] + bias2);
       m = mask[r];
+      // masked rows never went through the logits GEMM: weight 0 (use_mask) or the pad_doc logit (pad_doc branch)
+      al = m != 0.f ? __expf(logits_a[r] + bias2) : (BLEND ? __expf(c_pad[0] + bias2) : 0.f);
       if (use_mask) al *= m;
       src = r;
       if (idx != nullptr) {
@@ -681,11 +733,12 @@ ue_pool_kernel(const float* __restrict__ vecs, const int32_t* __restrict__ idx, 
 
 template <bool BLEND>
 static void ue_pool_launch(int pgrid, cudaStream_t st, const float* vecs, const int32_t* idx, long long n_rows, const float* mask,
-                           const float* pad, const float* b2, int use_mask, float* a_out, float* user, int B, int H, int D) {
-  if (D <= 128) ue_pool_kernel<BLEND, 1><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad, b2, use_mask, a_out, user, B, H, D);
-  else if (D <= 256) ue_pool_kernel<BLEND, 2><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad, b2, use_mask, a_out, user, B, H, D);
-  else if (D <= 512) ue_pool_kernel<BLEND, 4><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad, b2, use_mask, a_out, user, B, H, D);
-  else ue_pool_kernel<BLEND, 8><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad, b2, use_mask, a_out, user, B, H, D);
+                           const float* pad, const float* b2, const float* c_pad, int use_mask, float* a_out, float* user, int B,
+                           int H, int D) {
+  if (D <= 128) ue_pool_kernel<BLEND, 1><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad, b2, c_pad, use_mask, a_out, user, B, H, D);
+  else if (D <= 256) ue_pool_kernel<BLEND, 2><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad, b2, c_pad, use_mask, a_out, user, B, H, D);
+  else if (D <= 512) ue_pool_kernel<BLEND, 4><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad, b2, c_pad, use_mask, a_out, user, B, H, D);
+  else ue_pool_kernel<BLEND, 8><<<pgrid, UP_WARPS * 32, 0, st>>>(vecs, idx, n_rows, mask, pad, b2, c_pad, use_mask, a_out, user, B, H, D);
 }
 
 // ----------------------------------------------------------------------------------
@@ -955,19 +1008,31 @@ TNR_API int tnr_user_encoder_pack_w1(const float* W1, float* packed, int D, int 
   return 0;
 }
 
+TNR_API long long tnr_user_encoder_score_ws_bytes(int B, int H) { return ((long long)B * H + 4) * 4; }
+
 TNR_API int tnr_user_encoder_score(const float* vecs, long long n_rows, const int32_t* idx, const float* mask,
                                    const float* pad_doc, const float* w1_packed, const float* b1, const float* w2,
-                                   const float* b2, int use_mask, float* user, float* a_out, int B, int H, int D, int Q,
-                                   void* stream) {
+                                   const float* b2, int use_mask, float* user, float* a_out, void* workspace, int B, int H,
+                                   int D, int Q, void* stream) {
   if (ue_score_check("tnr_user_encoder_score", H, D, Q)) return 1;
   TNR_REQUIRE(a_out != nullptr && user != nullptr && w1_packed != nullptr && (uintptr_t)w1_packed % 16 == 0,
               "tnr_user_encoder_score: a_out [B,H] (logits workspace), user and a 16-byte aligned packed W1 are required");
+  TNR_REQUIRE(workspace != nullptr && (uintptr_t)workspace % 16 == 0,
+              "tnr_user_encoder_score: workspace of tnr_user_encoder_score_ws_bytes(B, H) bytes required");
   TNR_REQUIRE(idx == nullptr || n_rows >= 1, "tnr_user_encoder_score: empty table");
   if (B == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int R = B * H;
+  // workspace: [0] n_live (int32), [1] c_pad (float), [4 ..] the live row list
+  int32_t* wsi = reinterpret_cast<int32_t*>(workspace);
+  TNR_CHECK_CUDA(cudaMemsetAsync(wsi, 0, 16, st));
+  TNR_CHECK_CUDA(cudaMemsetAsync(a_out, 0, (size_t)R * sizeof(float), st));       // the two column halves add into it
+  ue_compact_kernel<<<(R + 255) / 256, 256, 0, st>>>(mask, R, wsi + 4, wsi);
+  TNR_LAUNCH_CHECK();
   UlParams p;
   p.vecs = vecs; p.idx = idx; p.n_rows = n_rows; p.mask = mask; p.pad = pad_doc; p.W1 = w1_packed; p.b1 = b1; p.w2 = w2;
-  p.logits = a_out; p.R = B * H; p.D = D; p.Q = Q;
+  p.logits = a_out; p.live = wsi + 4; p.n_live = wsi; p.c_pad = reinterpret_cast<float*>(wsi + 1);
+  p.R = R; p.D = D; p.Q = Q;
   const int smem = (UL_HALF * (D + 4) + UL_STAGES * UL_ROWS * UL_XS + 2 * UL_HALF + D) * 4;
   static bool attr = false;
   if (!attr) {
@@ -976,19 +1041,19 @@ TNR_API int tnr_user_encoder_score(const float* vecs, long long n_rows, const in
     TNR_CHECK_CUDA(cudaFuncSetAttribute(ue_logits_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr = true;
   }
-  TNR_CHECK_CUDA(cudaMemsetAsync(a_out, 0, (size_t)B * H * sizeof(float), st));     // the two column halves add into it
-  const int n_tiles = (p.R + UL_ROWS - 1) / UL_ROWS;
+  const int n_tiles = (R + UL_ROWS - 1) / UL_ROWS;        // upper bound: the live count is only known on the device
   const int pairs = n_tiles < num_sms() / 2 ? n_tiles : num_sms() / 2;
   const int grid = 2 * pairs;
   const int pgrid = (B + UP_WARPS - 1) / UP_WARPS;
+  const float* c_pad = reinterpret_cast<const float*>(wsi + 1);
   if (use_mask) {
     ue_logits_kernel<false><<<grid, UL_THREADS, smem, st>>>(p);
     TNR_LAUNCH_CHECK();
-    ue_pool_launch<false>(pgrid, st, vecs, idx, n_rows, mask, pad_doc, b2, 1, a_out, user, B, H, D);
+    ue_pool_launch<false>(pgrid, st, vecs, idx, n_rows, mask, pad_doc, b2, c_pad, 1, a_out, user, B, H, D);
   } else {
     ue_logits_kernel<true><<<grid, UL_THREADS, smem, st>>>(p);
     TNR_LAUNCH_CHECK();
-    ue_pool_launch<true>(pgrid, st, vecs, idx, n_rows, mask, pad_doc, b2, 0, a_out, user, B, H, D);
+    ue_pool_launch<true>(pgrid, st, vecs, idx, n_rows, mask, pad_doc, b2, c_pad, 0, a_out, user, B, H, D);
   }
   TNR_LAUNCH_CHECK();
   return 0;

@@ -327,11 +327,14 @@ def user_encoder_pack_w1(W1, packed=None):
     return packed
 
 
+_score_ws = {}
+
+
 @_timed
 def user_encoder_score(vecs, idx, mask, pad_doc, w1_packed, Q, b1, w2, b2, use_mask, user, a_out, B, H):
     """Scoring path: vecs fp32 [B*H, D] (idx None) or the [N, D] table with idx int32 [B, H]; mask fp32 [B, H]
     -> user fp32 [B, D], a_out fp32 [B, H]."""
-    lib = _ready(vecs, 2)
+    lib = _ready(vecs, 3)
     D = vecs.shape[1]
     for t, nm in ((vecs, "vecs"), (mask, "mask"), (pad_doc, "pad_doc"), (w1_packed, "w1_packed"), (b1, "b1"), (w2, "w2"),
                   (b2, "b2"), (user, "user"), (a_out, "a")):
@@ -344,9 +347,15 @@ def user_encoder_score(vecs, idx, mask, pad_doc, w1_packed, Q, b1, w2, b2, use_m
         raise _lib.TinyRecError("user_encoder_score: vecs must be [B*H, D]")
     if not vecs.is_contiguous() or tuple(mask.shape) != (B, H) or a_out.numel() != B * H or user.numel() != B * D:
         raise _lib.TinyRecError("user_encoder_score: shape / layout mismatch")
+    nbytes = int(lib.tnr_user_encoder_score_ws_bytes(B, H))
+    key = (vecs.device, nbytes)
+    ws = _score_ws.get(key)
+    if ws is None:
+        _score_ws.clear()
+        ws = _score_ws[key] = torch.empty(nbytes, device=vecs.device, dtype=torch.uint8)
     _lib.check(lib.tnr_user_encoder_score(_ptr(vecs), vecs.shape[0], _ptr(idx), _ptr(mask), _ptr(pad_doc), _ptr(w1_packed),
-                                          _ptr(b1), _ptr(w2), _ptr(b2), int(use_mask), _ptr(user), _ptr(a_out), B, H, D, Q,
-                                          _stream()), "tnr_user_encoder_score")
+                                          _ptr(b1), _ptr(w2), _ptr(b2), int(use_mask), _ptr(user), _ptr(a_out), _ptr(ws),
+                                          B, H, D, Q, _stream()), "tnr_user_encoder_score")
     return user
 
 
