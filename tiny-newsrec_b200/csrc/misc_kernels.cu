@@ -172,6 +172,11 @@ doc_sim_kernel(const float* __restrict__ table, long long n_rows, const int32_t*
 // out[imp] = {auc, mrr, ndcg5, ndcg10, valid}
 // ---------------------------------------------------------------------------------
 constexpr int EVAL_THREADS = 128;
+// 1 / log2(r + 1), r = 1..10: the only discounts nDCG@5 / nDCG@10 ever use (metrics.py:7-9); fp64 log2() on the device
+// is a long software routine and sat on the serial tail of every block
+__constant__ double c_disc[10] = {1.0, 0.6309297535714575, 0.5, 0.43067655807339306, 0.38685280723454163,
+                                  0.3562071871080222, 0.3333333333333333, 0.31546487678572877, 0.3010299956639812,
+                                  0.2890648263178879};
 
 __global__ void __launch_bounds__(EVAL_THREADS)
 eval_metrics_kernel(const float* __restrict__ table, const float* __restrict__ user, const long long* __restrict__ ptr,
@@ -245,9 +250,11 @@ eval_metrics_kernel(const float* __restrict__ table, const float* __restrict__ u
     const int rank = above + 1;
     auc += (double)neg_below + 0.5 * (double)neg_tied;
     mrr += 1.0 / (double)rank;
-    const double disc = 1.0 / log2((double)rank + 1.0);
-    if (rank <= 5) d5 += disc;
-    if (rank <= 10) d10 += disc;
+    if (rank <= 10) {
+      const double disc = c_disc[rank - 1];
+      if (rank <= 5) d5 += disc;
+      d10 += disc;
+    }
   }
   double vals[4] = {auc, mrr, d5, d10};
 #pragma unroll
@@ -264,7 +271,7 @@ eval_metrics_kernel(const float* __restrict__ table, const float* __restrict__ u
       for (int w = 0; w < EVAL_THREADS / 32; ++w) t[k] += red[k][w];
     double i5 = 0.0, i10 = 0.0;
     for (int r = 1; r <= min(P, 10); ++r) {
-      const double disc = 1.0 / log2((double)r + 1.0);
+      const double disc = c_disc[r - 1];
       if (r <= 5) i5 += disc;
       i10 += disc;
     }
