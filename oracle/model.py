@@ -227,6 +227,41 @@ def kd_model_forward(sd, history, history_mask, candidate, label, teacher_histor
     return total, distill, emb, target, s_score
 
 
+def post_train_distill_forward(sd, title, body, labels, teacher_titles, teacher_bodies, num_layers):
+    """First-stage KD, Post-train_KD.ipynb cells 12 and 14 (TitleBodySimModel / DistillModel.forward) ->
+    (loss, target_loss, distill_loss, emb_loss, student_score).  PARITY UNPINNED: cell 14 as published multiplies the
+    Python list ``teacher_MSEs`` by a tensor (TypeError); this restates the evident intent,
+    ``torch.stack(teacher_MSEs, dim=-1) * teacher_weights``, and cannot be checked against a run of the notebook."""
+    bz, k1, w = title.shape
+    body_emb = news_encoder(sd, "student.news_encoder.", body, num_layers)                         # cell 12
+    title_emb = news_encoder(sd, "student.news_encoder.", title.reshape(-1, w), num_layers).reshape(bz, k1, -1)
+    s_score = torch.bmm(title_emb, body_emb.unsqueeze(-1)).squeeze(-1)
+    target = F.cross_entropy(s_score, labels)
+    t_scores, t_losses, mses = [], [], []
+    for i, (tt, tb) in enumerate(zip(teacher_titles, teacher_bodies)):
+        W, b = sd[f"transform_matrix.{i}.weight"], sd[f"transform_matrix.{i}.bias"]
+        sc = torch.bmm(tt, tb.unsqueeze(-1)).squeeze(-1)
+        t_scores.append(sc)
+        t_losses.append(F.cross_entropy(sc, labels, reduction="none"))
+        tt_p, tb_p = F.linear(tt, W, b), F.linear(tb, W, b)
+        mses.append(((title_emb - tt_p) ** 2).mean(-1).mean(-1) + ((body_emb - tb_p) ** 2).mean(-1))
+    wts = torch.softmax(-torch.stack(t_losses, -1), dim=-1)
+    t_score = torch.bmm(torch.stack(t_scores, -1), wts.unsqueeze(-1)).squeeze(-1)
+    distill = kd_ce_loss(s_score, t_score)
+    emb = (torch.stack(mses, -1) * wts).sum(-1).mean()
+    return target + distill + emb, target, distill, emb, s_score
+
+
+def domain_post_train_forward(sd, title, body, labels, num_layers):
+    """Domian-specific_Post-train.ipynb cell 11 (TitleBodySimModel.forward) -> (scores, loss); pinned on the
+    notebook's own code by tests/golden/post_train.npz."""
+    bz, k1, w = title.shape
+    body_emb = news_encoder(sd, "news_encoder.", body, num_layers)
+    title_emb = news_encoder(sd, "news_encoder.", title.reshape(-1, w), num_layers).reshape(bz, k1, -1)
+    scores = torch.bmm(title_emb, body_emb.unsqueeze(-1)).squeeze(-1)
+    return scores, F.cross_entropy(scores, labels)
+
+
 def accuracy(y_true, y_hat):
     """utils.py:79-83."""
     return (y_true == y_hat.argmax(-1)).sum().float() / y_true.shape[0]

@@ -324,6 +324,56 @@ def gen_nrms():
     np.savez_compressed(os.path.join(HERE, "nrms.npz"), **out)
 
 
+def gen_post_train():
+    """``TitleBodySimModel`` of Domian-specific_Post-train.ipynb, built by EXECUTING the notebook's own cells 10-11
+    (AttentionPooling / NewsEncoder / TitleBodySimModel) through the shim: 12-layer encoder as the cell hard-codes,
+    1+K titles and one body per sample through the same encoder, CE over the title scores.  Pins the two-pass
+    title / body path that ``tinyrec.post_train`` runs (the first-stage KD wrapper of Post-train_KD.ipynb shares it;
+    its cell 14 is not runnable as published)."""
+    import json
+    import shutil
+    import tempfile
+    import torch.nn.functional as F_
+    from torch import nn as nn_
+    from utils import MODEL_CLASSES
+    nb = json.load(open(os.path.join(ref_shim.REF_ROOT, "Domian-specific_Post-train.ipynb")))
+    tmp = tempfile.mkdtemp()
+    shutil.copy(os.path.join(ref_shim.REF_ROOT, "Tiny-NewsRec/tnlrv3/config/tnlrv3-base-uncased-config.json"),
+                os.path.join(tmp, "unilm2-base-uncased-config.json"))
+    ns = dict(nn=nn_, torch=torch, F=F_, os=os, np=np, MODEL_CLASSES=MODEL_CLASSES, path_turing=tmp)
+    for c in (10, 11):
+        exec("".join(nb["cells"][c]["source"]), ns)
+    seed, layers, B, K1, Lt, Lb = 17, 12, 2, 3, 8, 40
+    rng = np.random.default_rng(41)
+    title = rand_news(rng, B * K1, Lt).reshape(B, K1, 2 * Lt)
+    body = rand_news(rng, B, Lb, full_row=0)
+    labels = np.array([2, 0], dtype=np.int64)
+    args = types.SimpleNamespace(news_query_vector_dim=200, news_dim=256)
+    m = ns["TitleBodySimModel"](args).eval()
+    full = synth.model_bert_state("", layers, seed, noisy=True)
+    sd = {k: v for k, v in full.items() if k.startswith("news_encoder.")}
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    for p in m.news_encoder.bert_model.parameters():
+        p.requires_grad = False
+    for i in (10, 11):
+        for p in m.news_encoder.bert_model.bert.encoder.layer[i].parameters():
+            p.requires_grad = True
+    scores, loss = m(torch.from_numpy(title), torch.from_numpy(body), torch.from_numpy(labels))
+    loss.backward()
+    out = dict(seed=seed, layers=layers, title=title, body=body, labels=labels, scores=scores.detach().numpy(),
+               loss=np.float64(loss.detach()), trainable=np.array([10, 11]))
+    names = []
+    for nm, p in m.named_parameters():
+        if p.requires_grad and p.grad is not None:
+            names.append(nm)
+            out.update(grad_summary(nm, p.grad))
+    out["trainable_names"] = np.array(names)
+    out["wsum_head"] = checksum({k: v for k, v in sd.items() if ".attn." in k or ".dense." in k})
+    np.savez_compressed(os.path.join(HERE, "post_train.npz"), **out)
+    shutil.rmtree(tmp)
+
+
 if __name__ == "__main__":
     gen_relpos()
     gen_encoder()
@@ -337,3 +387,4 @@ if __name__ == "__main__":
             print(f, os.path.getsize(os.path.join(HERE, f)))
     gen_unilm_convert()
     gen_nrms()
+    gen_post_train()

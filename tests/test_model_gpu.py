@@ -543,3 +543,101 @@ def test_doc_sim_matches_reference_loop():
     got = trun.doc_sim(table.cuda(), n_pairs=5000, rng=random.Random(11))
     want = omet.doc_sim(table.numpy(), 5000, random.Random(11))
     assert abs(got - want) < 1e-6, (got, want)
+
+
+def test_post_train_distill_model_vs_oracle():
+    """First-stage KD wrappers (Post-train_KD.ipynb cells 12, 14): 1+K titles of 12 tokens and a 72-token body per
+    sample through the same encoder (two saved passes, the body through the streamed-KV attention), losses, scores and
+    every trainable gradient against the oracle restatement; then the two learning-rate groups of cell 18."""
+    from types import SimpleNamespace
+    import tinyrec.optim as topt
+    import tinyrec.post_train as pt
+    import tinyrec.synth as synth
+    from oracle import model as om
+    B, K1, Lt, Lb, M, layers, D = 3, 4, 12, 72, 2, 2, 256
+    rng = np.random.default_rng(5)
+    title = torch.from_numpy(synth.news_table(B * K1 - 1, L=Lt, seed=1).astype(np.int64)).reshape(B, K1, 2 * Lt)
+    body = torch.from_numpy(synth.news_table(B - 1, L=Lb, seed=2).astype(np.int64))
+    labels = torch.tensor([0, 2, 1])
+    tt = [torch.from_numpy(rng.standard_normal((B, K1, D)).astype(np.float32) * 0.3) for _ in range(M)]
+    tb = [torch.from_numpy(rng.standard_normal((B, D)).astype(np.float32) * 0.3) for _ in range(M)]
+    args = SimpleNamespace(news_query_vector_dim=200, news_dim=D, num_hidden_layers=layers, num_teachers=M)
+    m = pt.DistillModel(args)
+    full = synth.kd_model_state(layers, M, 7, noisy=True)
+    sd = {k: v for k, v in full.items() if k.startswith(("student.news_encoder.", "transform_matrix."))}
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    m.cuda().eval()
+    for p in m.student.news_encoder.bert_model.parameters():                # cell 17
+        p.requires_grad = False
+    for p in m.student.news_encoder.bert_model.bert.encoder.layer[1].parameters():
+        p.requires_grad = True
+    res = m(title.cuda(), body.cuda(), labels.cuda(), [t.cuda() for t in tt], [t.cuda() for t in tb])
+    res[0].backward()
+    osd = {k: v.clone() for k, v in sd.items()}
+    names = [k for k, p in m.named_parameters() if p.requires_grad]
+    for k in names:
+        osd[k].requires_grad_(True)
+    ref = om.post_train_distill_forward(osd, title, body, labels, tt, tb, layers)
+    ref[0].backward()
+    for got, want in zip(res[:4], ref[:4]):
+        assert abs(float(got) - float(want)) < 1e-2 * abs(float(want)) + 1e-4, (float(got), float(want))
+    assert _rel(res[4], ref[4].detach()) < 2e-2
+    named = dict(m.named_parameters())
+    for k in names:
+        assert _grad_err(k, named[k].grad, osd[k].grad, named) < 5e-2, k
+    # inference form of cell 12
+    with torch.no_grad():
+        sc, te, be = m.student(title.cuda(), body.cuda())
+    assert _rel(sc, ref[4].detach()) < 2e-2 and tuple(te.shape) == (B, K1, D) and tuple(be.shape) == (B, D)
+    # cell 18: bert_model at 1e-6, the rest at 1e-5
+    opt = topt.Adam(m, lr=1e-5)
+    ranges = m.lr_ranges(1e-6, 1e-5)
+    opt.set_lr_ranges(ranges)
+    st = m.train_state()
+    before = st.flat.data.clone()
+    opt.step()
+    step = (st.flat.data - before).abs()
+    cut = ranges[0][1]
+    assert 0 < cut < st.flat.numel
+    assert float(step[:cut].max()) <= 1.05e-6 and float(step[cut:].max()) <= 1.05e-5      # + fp32 rounding of p - p0
+    assert float(step[:cut].max()) > 5e-7 and float(step[cut:].max()) > 5e-6      # first Adam step = lr * sign(g)
+
+
+def test_domain_post_train_model_vs_reference_golden(golden):
+    """``tinyrec.post_train.DomainTitleBodySimModel`` against the notebook's own ``TitleBodySimModel`` (fixture generated
+    by executing cells 10-11 of Domian-specific_Post-train.ipynb): 12 layers, 1+K titles and a 40-token body per sample
+    through the same encoder -- the two-saved-passes path the first-stage KD wrapper shares."""
+    from types import SimpleNamespace
+    import tinyrec.post_train as pt
+    import tinyrec.synth as synth
+    g = golden("post_train")
+    layers = int(g["layers"])
+    m = pt.DomainTitleBodySimModel(SimpleNamespace(news_query_vector_dim=200, news_dim=256, num_hidden_layers=layers))
+    full = synth.model_bert_state("", layers, int(g["seed"]), noisy=True)
+    sd = {k: v for k, v in full.items() if k.startswith("news_encoder.")}
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    m.cuda().eval()
+    for p in m.news_encoder.bert_model.parameters():
+        p.requires_grad = False
+    for i in [int(t) for t in g["trainable"]]:
+        for p in m.news_encoder.bert_model.bert.encoder.layer[i].parameters():
+            p.requires_grad = True
+    scores, loss = m(torch.from_numpy(g["title"]).cuda(), torch.from_numpy(g["body"]).cuda(), torch.from_numpy(g["labels"]).cuda())
+    ref = torch.from_numpy(g["scores"])
+    assert _rel(scores, ref) < 1e-2
+    serr = float((scores.detach().cpu() - ref).abs().max())
+    assert abs(float(loss) - float(g["loss"])) < 2 * serr + 1e-3            # |d CE| <= 2 max |d score|
+    loss.backward()
+    named = dict(m.named_parameters())
+    for k in [str(s) for s in g["trainable_names"]]:
+        gr = named[k].grad
+        assert gr is not None, k
+        if f"gfull/{k}" in g.files:
+            refg = torch.from_numpy(g[f"gfull/{k}"])
+            r = _grad_err(k, gr.reshape(refg.shape), refg, named)
+        else:
+            refg = torch.from_numpy(g[f"gslice/{k}"])
+            r = _grad_err(k, gr[:16, :16], refg, named)
+        assert r < 8e-2, (k, r)             # 12 bf16 layers in front of the loss; the scores are ~60 with gaps of ~1

@@ -201,3 +201,26 @@ def test_nrms_kd_forward_and_gradients(golden, tag, ulm):
         np.testing.assert_allclose(float(gr.double().abs().sum()), float(g[f"{tag}/gabs/{k}"]), rtol=2e-4, atol=1e-9)
         if f"{tag}/gfull/{k}" in g.files:
             np.testing.assert_allclose(gr.numpy(), g[f"{tag}/gfull/{k}"], rtol=2e-3, atol=2e-7)
+
+
+# ------------------------------------------------------------------ post-training title / body model
+def test_domain_post_train_forward_and_gradients(golden):
+    """Oracle vs ``TitleBodySimModel`` of Domian-specific_Post-train.ipynb, executed from the notebook's own cells
+    (fixture: make_golden.py:gen_post_train): 12-layer encoder, titles and body through the same encoder, CE."""
+    g = golden("post_train")
+    layers = int(g["layers"])
+    full = synth.model_bert_state("", layers, int(g["seed"]), noisy=True)
+    sd = {k: v for k, v in full.items() if k.startswith("news_encoder.")}
+    keys = [str(s) for s in g["trainable_names"]]
+    for k in keys:
+        sd[k].requires_grad_(True)
+    scores, loss = om.domain_post_train_forward(sd, torch.from_numpy(g["title"]), torch.from_numpy(g["body"]),
+                                                torch.from_numpy(g["labels"]), layers)
+    np.testing.assert_allclose(scores.detach().numpy(), g["scores"], rtol=2e-5, atol=2e-4)
+    np.testing.assert_allclose(float(loss.detach()), float(g["loss"]), rtol=1e-4, atol=1e-5)
+    loss.backward()
+    for k in keys:
+        gr = sd[k].grad
+        np.testing.assert_allclose(float(gr.double().abs().sum()), float(g[f"gabs/{k}"]), rtol=5e-4, atol=1e-9)
+        if f"gfull/{k}" in g.files:
+            np.testing.assert_allclose(gr.numpy(), g[f"gfull/{k}"], rtol=5e-3, atol=1e-6)

@@ -250,8 +250,8 @@ class Encoder:
         return self.frozen.get(("word",), [w], lambda: w.detach().to(BF).contiguous())
 
     # ---- workspaces -----------------------------------------------------------------
-    def workspace(self, n, L, n_saved_layers, dev):
-        key = (n, L, n_saved_layers)
+    def workspace(self, n, L, n_saved_layers, dev, tag=None):
+        key = (n, L, n_saved_layers, tag)
         ws = self.ws.get(key)
         if ws is not None:
             return ws
@@ -271,7 +271,7 @@ class Encoder:
         return ws
 
     # ---- forward ----------------------------------------------------------------------
-    def forward(self, x, flat=None, save=False, out=None, drop=None):
+    def forward(self, x, flat=None, save=False, out=None, drop=None, tag=None):
         """x int64 [n, 2L] -> news vectors fp32 [n, D].  With ``save`` the activations the
         backward needs are kept in the workspace (layers >= lowest trainable layer).  ``drop`` is a
         DropState (training mode, reference semantics) or None (eval)."""
@@ -282,7 +282,7 @@ class Encoder:
         dev = x.device
         nl = len(self.layers)
         low = self.lowest_trainable_layer() if save else nl
-        ws = self.workspace(n, L, nl - low if save else 0, dev)
+        ws = self.workspace(n, L, nl - low if save else 0, dev, tag)      # tag: several saved passes per step
         emb = self.bert.embeddings
         relpos = self.relpos(L)
         cur = ws["x0"]
@@ -332,11 +332,11 @@ class Encoder:
         g = flat.g_view(p) if rows is None else flat.grad[flat.off(p):flat.off(p) + rows * p.shape[1]].view(rows, p.shape[1])
         ops.gemm(dy, xin, g, a_t=True, b_t=True, split_k=self._splitk(M, xin.shape[1], dy.shape[0]), accumulate=True)
 
-    def backward(self, d_news, flat, on_layer_done=None):
+    def backward(self, d_news, flat, on_layer_done=None, ws=None):
         """d_news fp32 [n, D] -> parameter gradients accumulated into ``flat.grad``.
         ``on_layer_done(i)`` is called after the last gradient kernel of encoder layer ``i`` was
         enqueued (bucketed gradient all-reduce overlapping the rest of the backward)."""
-        ws = self.last_ws
+        ws = self.last_ws if ws is None else ws      # ws: the workspace of the forward pass this backward belongs to
         n, L, low, x = ws["n"], ws["L"], ws["low"], ws["x"]
         drop = ws.get("drop")
         dmk = (lambda site, p: drop.make(site, p)) if drop is not None else (lambda site, p: None)

@@ -55,8 +55,25 @@ class Adam:
             self.bc_ws = torch.zeros(2, device=flat.data.device, dtype=torch.float32)
         return flat
 
+    def set_lr_ranges(self, ranges):
+        """Per-range learning rates over the flat buffer: ``[(lo, hi, lr), ...]`` in elements, contiguous and
+        covering it (the post-training notebook's two groups: 1e-6 for ``bert_model``, 1e-5 for the rest,
+        Post-train_KD.ipynb cell 18).  One kernel launch per range."""
+        self.lr_ranges = [(int(lo), int(hi), float(lr)) for lo, hi, lr in ranges]
+
     def step(self):
         flat = self.ensure_state()
+        ranges = getattr(self, "lr_ranges", None)
+        if ranges:
+            if self.capturable:
+                raise TinyRecError("lr ranges are not supported together with the device step counter")
+            self.step_count += 1
+            for lo, hi, lr in ranges:
+                if hi > lo:
+                    ops.adam_amsgrad(flat.data[lo:hi], flat.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], self.vmax[lo:hi],
+                                     flat.shadow[lo:hi], lr, self.betas[0], self.betas[1], self.eps, self.step_count,
+                                     self.grad_scale)
+            return
         if self.capturable:
             ops.adam_amsgrad_devstep(flat.data, flat.grad, self.m, self.v, self.vmax, flat.shadow, self.lr, self.betas[0],
                                      self.betas[1], self.eps, self.step_dev, self.bc_ws, self.grad_scale)
