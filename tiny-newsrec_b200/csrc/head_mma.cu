@@ -763,20 +763,36 @@ user_encoder_bwd_kernel(const float* __restrict__ vecs, const float* __restrict_
   float* sdusr = smk + UE_HMAX;           // [D]
   __shared__ float s_dot;
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  for (int i = tid; i < UE_HMAX * (D / 4); i += UE_THREADS) {
-    const int h = i / (D / 4), d = (i - h * (D / 4)) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (h < H) {
-      v = *reinterpret_cast<const float4*>(vecs + ((size_t)b * H + h) * D + d);
-      if (!use_mask) {
-        const float m = mask[(size_t)b * H + h];
-        const float4 pd = *reinterpret_cast<const float4*>(pad_doc + d);
-        v.x = v.x * m + pd.x * (1.0f - m); v.y = v.y * m + pd.y * (1.0f - m);
-        v.z = v.z * m + pd.z * (1.0f - m); v.w = v.w * m + pd.w * (1.0f - m);
+  // grid.y column slices: the batch is the grid (32 blocks at the demo shape on 148 SMs), so each impression is cut
+  // into S blocks that repeat the cheap part (dz, du) and split the n-tiles of the dv product; slice 0 alone
+  // writes dU / Vb and adds the parameter gradients.
+  const int slice = blockIdx.y, S = gridDim.y;
+  {
+    // input tile: warp w stages rows w, w + 8, ... with all eight rows of loads in flight (no div / mod per element)
+    const int D4 = D >> 2;
+    for (int d4 = lane; d4 < D4; d4 += 32) {
+      float4 v[UE_HMAX / 8];
+#pragma unroll
+      for (int j = 0; j < UE_HMAX / 8; ++j) {
+        const int h = warp + 8 * j;
+        v[j] = h < H ? *reinterpret_cast<const float4*>(vecs + ((size_t)b * H + h) * D + d4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      *reinterpret_cast<float4*>(Vb + ((size_t)b * H + h) * D + d) = v;
+      float4 pd = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!use_mask) pd = *reinterpret_cast<const float4*>(pad_doc + d4 * 4);
+#pragma unroll
+      for (int j = 0; j < UE_HMAX / 8; ++j) {
+        const int h = warp + 8 * j;
+        float4 x = v[j];
+        if (h < H) {
+          if (!use_mask) {
+            const float m = mask[(size_t)b * H + h], om = 1.0f - m;
+            x.x = x.x * m + pd.x * om; x.y = x.y * m + pd.y * om; x.z = x.z * m + pd.z * om; x.w = x.w * m + pd.w * om;
+          }
+          if (slice == 0) *reinterpret_cast<float4*>(Vb + ((size_t)b * H + h) * D + d4 * 4) = x;
+        }
+        *reinterpret_cast<float4*>(sv + h * DS + d4 * 4) = x;
+      }
     }
-    *reinterpret_cast<float4*>(sv + h * DS + d) = v;
   }
   for (int i = tid; i < UE_HMAX * QS; i += UE_THREADS) sdu[i] = 0.f;
   if (tid < UE_HMAX) {
@@ -811,13 +827,15 @@ user_encoder_bwd_kernel(const float* __restrict__ vecs, const float* __restrict_
       gw2 = fmaf(dz, ev, gw2);
       const float du = dz * w * (1.0f - ev * ev);
       sdu[h * QS + q] = du;
-      dU[((size_t)b * H + h) * Q + q] = du;
+      if (slice == 0) dU[((size_t)b * H + h) * Q + q] = du;
       gb1 += du;
     }
-    atomicAdd(dw2 + q, gw2);
-    atomicAdd(db1 + q, gb1);
+    if (slice == 0) {
+      atomicAdd(dw2 + q, gw2);
+      atomicAdd(db1 + q, gb1);
+    }
   }
-  if (warp == 0) {
+  if (warp == 0 && slice == 0) {
     float s = 0.f;
     for (int h = lane; h < H; h += 32) s += sdz[h];
     s = warp_sum(s);
@@ -837,7 +855,12 @@ user_encoder_bwd_kernel(const float* __restrict__ vecs, const float* __restrict_
     int ncol[4];
     bool nv[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { ncol[i] = (pass * 32 + warp + 8 * i) * 8; nv[i] = ncol[i] < D; }
+    for (int i = 0; i < 4; ++i) {
+      const int tile = pass * 32 + warp + 8 * i;
+      ncol[i] = tile * 8;
+      nv[i] = ncol[i] < D && ((tile >> 3) % S) == slice;      // groups of 8 n-tiles go round the slices (warp-uniform)
+    }
+    if (!(nv[0] || nv[1] || nv[2] || nv[3])) continue;
     for (int ks = 0; ks < Qp / 8; ++ks) {
       uint32_t bf[4][2];
       const int q0 = ks * 8 + t;
@@ -853,7 +876,8 @@ user_encoder_bwd_kernel(const float* __restrict__ vecs, const float* __restrict_
           const float* r0 = sdu + (mt * 16 + g) * QS + ks * 8 + t;
           a[0] = f2tf32(r0[0]); a[1] = f2tf32(r0[8 * QS]); a[2] = f2tf32(r0[4]); a[3] = f2tf32(r0[8 * QS + 4]);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) mma_tf32(acc[mt][i], a, bf[i][0], bf[i][1]);
+          for (int i = 0; i < 4; ++i)
+            if (nv[i]) mma_tf32(acc[mt][i], a, bf[i][0], bf[i][1]);
         }
       }
     }
@@ -1078,7 +1102,9 @@ TNR_API int tnr_user_encoder_bwd(const float* vecs, const float* mask, const flo
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* dU = scratch;
   float* Vb = scratch + (size_t)B * H * Q;
-  user_encoder_bwd_kernel<<<B, UE_THREADS, smem, st>>>(vecs, mask, pad_doc, W1, w2, use_mask, a_in, e_in, d_user, d_vecs,
+  int slices = (2 * num_sms()) / (B > 0 ? B : 1);              // fill the machine: 4 column slices at batch 32
+  slices = slices < 1 ? 1 : (slices > 4 ? 4 : slices);
+  user_encoder_bwd_kernel<<<dim3(B, slices), UE_THREADS, smem, st>>>(vecs, mask, pad_doc, W1, w2, use_mask, a_in, e_in, d_user, d_vecs,
                                                       dpad, db1, dw2, db2, dU, Vb, H, D, Q);
   TNR_LAUNCH_CHECK();
   return launch_sgemm_tn(dU, Vb, dW1, nullptr, B * H, Q, D, 1, 0, 0, 0, 0, st);
