@@ -657,17 +657,18 @@ def test_user_encoder_gather_equals_gather_then_encode(use_mask):
 
 
 @pytest.mark.parametrize("use_mask", [False, True])
-@pytest.mark.parametrize("B,H,Q", [(300, 50, 200), (65, 7, 64), (64, 64, 208)])
-def test_user_encoder_scoring_path_vs_torch(use_mask, B, H, Q):
+@pytest.mark.parametrize("B,H,Q,D", [(300, 50, 200, 256), (65, 7, 64, 256), (64, 64, 208, 256), (200, 50, 200, 64), (70, 20, 100, 128)])
+def test_user_encoder_scoring_path_vs_torch(use_mask, B, H, Q, D):
     """Scoring-sized batches (B >= 64) take the flat logits GEMM + pooling kernels (tnr_user_encoder_score): same result as the
     torch fp32 restatement, incl. an all-masked history and a ragged last 64-row tile."""
     ops = _ops()
     f32 = torch.float32
-    D = 256
     vecs = _randn(B, H, D, dtype=f32, scale=0.5, seed=1)
     mask = (torch.rand(B, H, generator=torch.Generator().manual_seed(2)) > 0.3).float().cuda()
     mask[1] = 0
     mask[2] = 1
+    mask[3, : H // 2] = 0                                  # front-padded history, as the loader builds them
+    mask[3, H // 2:] = 1
     pad, W1 = _randn(D, dtype=f32, scale=0.5, seed=4), _randn(Q, D, dtype=f32, scale=0.06, seed=5)
     b1, w2, b2 = _randn(Q, dtype=f32, scale=0.1, seed=6), _randn(Q, dtype=f32, scale=0.1, seed=7), _randn(1, dtype=f32, seed=8)
     user, a = torch.empty(B, D, device="cuda"), torch.empty(B, H, device="cuda")
