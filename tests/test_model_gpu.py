@@ -641,3 +641,34 @@ def test_domain_post_train_model_vs_reference_golden(golden):
             refg = torch.from_numpy(g[f"gslice/{k}"])
             r = _grad_err(k, gr[:16, :16], refg, named)
         assert r < 8e-2, (k, r)             # 12 bf16 layers in front of the loss; the scores are ~60 with gaps of ~1
+
+
+def test_scoring_path_sees_parameters_updated_by_the_fused_adam(golden):
+    """The scoring kernels read a packed copy of att_fc1.weight that is cached per parameter; the fused Adam rewrites
+    parameters through raw pointers (torch's version counters do not move), so the cache must key on the library's own
+    parameter generation: user vectors computed after a training step must match the per-impression kernel that
+    reads the live weights."""
+    import tinyrec.ops as ops
+    import tinyrec.optim as topt
+    g = golden("kd")
+    m, inputs = _kd_model(g, False)
+    for p in m.student.user_encoder.parameters():
+        p.requires_grad = True
+    opt = topt.Adam(m, lr=1e-2)
+    ue = m.student.user_encoder
+    B, H, D = 96, inputs[0].shape[1], 256
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    vecs = torch.randn(B, H, D, device="cuda", generator=gen) * 0.3
+    mask = torch.ones(B, H, device="cuda")
+    u_before = ue(vecs, mask).clone()                 # B >= 64: scoring path, packs W1
+    opt.zero_grad()
+    m(*inputs)[0].backward()
+    opt.step()
+    u_after = ue(vecs, mask)
+    assert _rel(u_after, u_before) > 1e-4             # the weights moved
+    at = ue.attn
+    ref = torch.empty(B, D, device="cuda")
+    a = torch.empty(B, H, device="cuda")
+    ops.user_encoder_fwd(vecs.view(B * H, D), mask, ue.pad_doc.view(-1), at.att_fc1.weight, at.att_fc1.bias,
+                         at.att_fc2.weight.view(-1), at.att_fc2.bias, False, ref, a, None, B, H)
+    assert _rel(u_after, ref) < 1e-5

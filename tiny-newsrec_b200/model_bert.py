@@ -250,7 +250,7 @@ class UserEncoder(nn.Module):
     def _packed_w1(self):
         """Packed TF32 copy of att_fc1.weight for the scoring kernels, re-packed when the parameter changes."""
         w = self.attn.att_fc1.weight
-        key = (w.data_ptr(), w._version, w.device)
+        key = (w.data_ptr(), w._version, w.device, ops.param_generation)
         c = getattr(self, "_w1_pack", None)
         if c is None or c[0] != key:
             c = (key, ops.user_encoder_pack_w1(w.detach()))

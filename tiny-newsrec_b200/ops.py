@@ -64,6 +64,16 @@ class _Stats:
 
 stats = _Stats()
 
+# Bumped whenever a kernel of this library rewrites parameters in place through raw pointers (the fused Adam, eager
+# or inside a replayed graph): torch's ``_version`` counters do not see those writes, so derived copies that are
+# cached per parameter (the packed TF32 W1 of the scoring kernels) key on this as well.
+param_generation = 0
+
+
+def bump_param_generation():
+    global param_generation
+    param_generation += 1
+
 
 def _timed(fn):
     """Per-op CUDA-event bracketing, active only while ``stats.op_events`` is a list."""

@@ -63,6 +63,7 @@ class Adam:
 
     def step(self):
         flat = self.ensure_state()
+        ops.bump_param_generation()
         ranges = getattr(self, "lr_ranges", None)
         if ranges:
             if self.capturable:

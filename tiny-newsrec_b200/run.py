@@ -187,6 +187,7 @@ class GraphedTrainStep:
         for d, t in zip(s[5], teacher_candidate_embs):
             d.copy_(t, non_blocking=True)
         self.graph.replay()
+        ops.bump_param_generation()          # the replay stepped the optimizer: cached parameter copies are stale
         return self.out
 
 
