@@ -266,23 +266,45 @@ def evaluate(user_encoder, news_scoring, hist_idx, hist_mask, cand_ptr, cand_idx
     sums = torch.zeros(5, device=device, dtype=torch.float64)
     per_all = []
     ptr_h = np.asarray(cand_ptr)
-    for s in range(lo, hi, batch_size):
+    # Index batches go host -> pinned staging -> device on a copy stream, one batch ahead of the scoring kernels
+    # (the reference's loader thread did the same job with blocking copies, dataloader.py:303-314); nothing is read
+    # back until the final reduction.
+    copy_stream = torch.cuda.Stream(device=device)
+    main = torch.cuda.current_stream(device)
+
+    def stage(s):
         e = min(hi, s + batch_size)
-        hi_t = torch.from_numpy(np.ascontiguousarray(hist_idx[s:e])).to(device)
-        hm_t = torch.from_numpy(np.ascontiguousarray(hist_mask[s:e])).to(device)
         p0, p1 = int(ptr_h[s]), int(ptr_h[e])
-        ptr_t = torch.from_numpy(np.ascontiguousarray(ptr_h[s:e + 1] - p0)).to(device)
-        cand_t = torch.from_numpy(np.ascontiguousarray(cand_idx[p0:p1])).to(device)
-        lab_t = torch.from_numpy(np.ascontiguousarray(labels[p0:p1])).to(device)
+        host = (np.ascontiguousarray(hist_idx[s:e]), np.ascontiguousarray(hist_mask[s:e]),
+                np.ascontiguousarray(ptr_h[s:e + 1] - p0), np.ascontiguousarray(cand_idx[p0:p1]),
+                np.ascontiguousarray(labels[p0:p1]))
+        max_c = int(np.diff(host[2]).max()) if e > s else 0
+        with torch.cuda.stream(copy_stream):
+            pinned = [torch.from_numpy(a).pin_memory() for a in host]
+            dev = [t.to(device, non_blocking=True) for t in pinned]
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        return dict(e=e, dev=dev, pinned=pinned, max_c=max_c, ready=ready)
+
+    nxt = stage(lo) if hi > lo else None
+    s = lo
+    while nxt is not None:
+        cur = nxt
+        e = cur["e"]
+        nxt = stage(e) if e < hi else None                       # next batch's copies overlap this batch's kernels
+        main.wait_event(cur["ready"])
+        hi_t, hm_t, ptr_t, cand_t, lab_t = cur["dev"]
+        for t in cur["dev"]:
+            t.record_stream(main)
         if hasattr(user_encoder, "forward_gather"):      # news_scoring[log_ids] (dataloader.py:295) fused into the kernel
             user = user_encoder.forward_gather(news_scoring, hi_t, hm_t)
         else:
             user = user_encoder(dl.gather_history_vecs(news_scoring, hi_t), hm_t)
         per = torch.zeros(e - s, 5, device=device, dtype=torch.float64)
-        max_c = int(np.diff(ptr_h[s:e + 1]).max())
-        ops.eval_metrics(news_scoring, user, ptr_t, cand_t, lab_t, max_c, per, sums)
+        ops.eval_metrics(news_scoring, user, ptr_t, cand_t, lab_t, cur["max_c"], per, sums)
         if return_per_impression:
             per_all.append(per)
+        s = e
     mean, total = par.reduce_eval_sums(hi - lo, sums[:4])
     if return_per_impression:
         return mean, total, torch.cat(per_all) if per_all else torch.zeros(0, 5, dtype=torch.float64)
