@@ -552,6 +552,18 @@ def run_table(a):
     ms, launches, gemm_events, clocks, barrier = _timed_steps(step, a, rank, world, local, device)
     value = rows * world * a.steps / (ms / 1e3)
     e2e_val = rows * world * a.steps / _wall_steps(e2e_step, a, world, device, barrier)
+    # ---- the whole 161k-news table (BASELINE.json configs[3]) through the public driver tinyrec.run.build_news_table:
+    # host int32 rows in, rows sharded over the ranks, all-gathered fp32 [N+1, D] table out; wall clock, max over ranks
+    import tinyrec.run as trun
+    barrier()
+    t0 = time.perf_counter()
+    full = trun.build_news_table(enc, news, batch_size=rows)
+    barrier()
+    tt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    full_s, full_rows = float(tt.item()), int(full.shape[0])
+    del full
     if rank == 0:
         peak_tf, peak_bw, how = peaks()
         gflop = sum(f for f, _, _ in gemm_events)
@@ -569,6 +581,8 @@ def run_table(a):
                 "e2e": {"value": e2e_val, "unit": "news/s", "h2d_bytes_per_step": rows * 2 * Lw * 4,
                         "d2h_bytes_per_step": rows * D * 4},
                 "gpu_launches": launches,
+                "full_table": {"api": "tinyrec.run.build_news_table (host int32 rows in, all-gathered fp32 table out)",
+                               "rows": full_rows, "seconds": full_s, "news_per_sec": full_rows / full_s},
                 "roofline": {"bound": "tensor", "kernel": "tnr::gemm::gemm_kernel (tcgen05, all GEMM launches of the step)",
                              "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                              "peak_source": f"{how} bf16_tflops_sustained", "traffic": None,
