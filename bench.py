@@ -16,7 +16,6 @@ pinned HOST inputs copied to the device every step and the loss read back.
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

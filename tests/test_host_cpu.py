@@ -105,6 +105,30 @@ def test_state_dict_keys_match_reference_layout():
     assert len(trainable) == 51 and sum(p.numel() for p in trainable) == 14841634
 
 
+def test_post_train_wrappers_keep_the_notebook_names():
+    """Post-train_KD.ipynb cells 12 / 14 and Domian-specific_Post-train.ipynb cell 11: attribute paths and state_dict
+    keys (``student.news_encoder.*`` + ``transform_matrix.{i}.*``; ``news_encoder.*``) and the freeze policy of cell 17."""
+    from types import SimpleNamespace
+    import tinyrec.post_train as pt
+    import tinyrec.synth as synth
+    args = SimpleNamespace(news_query_vector_dim=200, news_dim=256, num_hidden_layers=2, num_teachers=3)
+    m = pt.DistillModel(args)
+    full = synth.kd_model_state(2, 3, 0)
+    want = [k for k in full if k.startswith(("student.news_encoder.", "transform_matrix."))]
+    assert list(m.state_dict().keys()) == want
+    for p in m.student.news_encoder.bert_model.parameters():
+        p.requires_grad = False
+    for index, layer in enumerate(m.student.news_encoder.bert_model.bert.encoder.layer):
+        if index in [1]:
+            for p in layer.parameters():
+                p.requires_grad = True
+    d = pt.DomainTitleBodySimModel(args)
+    assert list(d.state_dict().keys()) == [k for k in synth.model_bert_state("", 2, 0) if k.startswith("news_encoder.")]
+    with pytest.raises(Exception):
+        m(torch.zeros(1, 2, 8, dtype=torch.int64), torch.zeros(1, 8, dtype=torch.int64), torch.zeros(1, dtype=torch.int64),
+          [torch.zeros(1, 2, 256)] * 3, [torch.zeros(1, 256)] * 3)            # CPU tensors: no fallback path
+
+
 def test_loader_index_logic_bit_exact(golden):
     import random
     import tinyrec.dataloader as dl

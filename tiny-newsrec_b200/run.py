@@ -15,7 +15,6 @@ of behaviour lines or pre-parsed index arrays.
 """
 import logging
 import os
-import pickle
 import random
 
 import numpy as np
