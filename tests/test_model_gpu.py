@@ -5,6 +5,8 @@
 Tolerances: bf16 compute path -> 1e-2 relative (BASELINE.json north_star) on logits /
 embeddings / losses; gradients 3e-2 relative in norm (bf16 activations and grads);
 bit-exact for gathers; 1e-3 absolute for ranking metrics (they are exact in practice)."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -672,3 +674,38 @@ def test_scoring_path_sees_parameters_updated_by_the_fused_adam(golden):
     ops.user_encoder_fwd(vecs.view(B * H, D), mask, ue.pad_doc.view(-1), at.att_fc1.weight, at.att_fc1.bias,
                          at.att_fc2.weight.view(-1), at.att_fc2.bias, False, ref, a, None, B, H)
     assert _rel(u_after, ref) < 1e-5
+
+
+def test_graphed_train_step_advances_dropout_seed_and_trains():
+    """Training mode (dropout active) under graph replay: the device-resident seed advances inside the graph, so
+    replays of the same batch draw different masks (different losses), the Adam step counter advances, and the
+    parameters move by about lr per replay (first Adam steps are lr * sign(g)); equality with the eager loop is
+    test_graphed_train_step_matches_eager_loop."""
+    import tinyrec.model_bert as mb
+    import tinyrec.optim as topt
+    import tinyrec.run as trun
+    import tinyrec.synth as synth
+    B, H, K, L, M, layers, N = 4, 10, 3, 12, 2, 2, 300
+    news = synth.news_table(N, L=L, seed=1)
+    tables = synth.teacher_tables(N, M, 256, seed=3)
+    hist_idx, hmask, cand_idx, label = synth.train_impressions(B, N, H, K, seed=10)
+    batch = (torch.from_numpy(news[hist_idx].astype(np.int64)).cuda(), torch.from_numpy(hmask).cuda(),
+             torch.from_numpy(news[cand_idx].astype(np.int64)).cuda(), torch.from_numpy(label).cuda(),
+             [torch.from_numpy(t[hist_idx]).cuda() for t in tables], [torch.from_numpy(t[cand_idx]).cuda() for t in tables])
+    m = mb.Model(synth.demo_args(num_student_layers=layers, num_teachers=M, user_log_length=H))
+    m.load_state_dict(synth.kd_model_state(layers, M, 5, noisy=True), strict=True)
+    m.cuda().train()
+    _apply_freeze(m, [1])
+    w0 = m.student.news_encoder.dense.weight.detach().clone()
+    opt = topt.Adam(m, lr=1e-4)
+    step = trun.GraphedTrainStep(m, opt, batch)
+    l1 = float(step(*batch)[0])
+    l2 = float(step(*batch)[0])
+    assert l1 != l2                                           # new dropout masks (and new weights) every replay
+    for _ in range(6):
+        step(*batch)
+    assert opt.steps_done() == 8
+    step.close()
+    moved = (m.student.news_encoder.dense.weight.detach() - w0).abs()
+    assert 1e-4 < float(moved.max()) <= 8.5e-4 and float(moved.mean()) > 5e-5
+    assert math.isfinite(l1) and math.isfinite(l2)
