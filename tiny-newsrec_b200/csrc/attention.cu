@@ -25,7 +25,10 @@ constexpr int PS = 40;            // smem row stride (bf16) of the 32 x 32 P / d
 constexpr int TILE_BYTES = LMAX * TS * 2;
 constexpr int PT_BYTES = LMAX * PS * 2;
 constexpr int ATT_FWD_SMEM_PER_WARP = 3 * TILE_BYTES + LMAX * 4 + 2 * LMAX * 4;        // tiles, key mask, rel-pos vector
-constexpr int ATT_BWD_SMEM_PER_WARP = 4 * TILE_BYTES + 2 * PT_BYTES + LMAX * 4 + 2 * LMAX * 4;
+// backward: Q, K, V, dO tiles + the dS tile; the dropout(P) tile ALIASES the V tile (V is dead once dP = dO V^T is in
+// registers), which brings a warp to 21.4 KB and five warps per block to two blocks = 10 warps per SM (was 8)
+constexpr int ATT_BWD_WARPS = 5;
+constexpr int ATT_BWD_SMEM_PER_WARP = 4 * TILE_BYTES + PT_BYTES + LMAX * 4 + 2 * LMAX * 4;
 
 int attn_long_bwd_launch(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias, const void* dctx_bf16,
                          void* dqkv_bf16, float* dbias, float* ws, int n_news, int L, int A, int E, const tnr_dropout* drop,
@@ -253,22 +256,22 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
   store_tile(ctx + (size_t)n * L * E + h * DH, sQ, L, E, lane);
 }
 
-__global__ void __launch_bounds__(ATT_WARPS * 32)
+__global__ void __launch_bounds__(ATT_BWD_WARPS * 32)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ mask, int mask_ld,
                 const float* __restrict__ relbias, const __nv_bfloat16* __restrict__ dctx,
                 __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int n_news, int L, int A, int E,
                 const tnr_dropout drop) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long item = (long long)blockIdx.x * ATT_WARPS + warp;
+  const long long item = (long long)blockIdx.x * ATT_BWD_WARPS + warp;
   if (item >= (long long)n_news * A) return;
   uint8_t* wbase = smem + (size_t)warp * ATT_BWD_SMEM_PER_WARP;
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(wbase);
   __nv_bfloat16* sK = sQ + LMAX * TS;
   __nv_bfloat16* sV = sK + LMAX * TS;
   __nv_bfloat16* sO = sV + LMAX * TS;
-  __nv_bfloat16* sP = sO + LMAX * TS;
-  __nv_bfloat16* sS = sP + LMAX * PS;
+  __nv_bfloat16* sS = sO + LMAX * TS;
+  __nv_bfloat16* sP = sV;                         // aliases V: written only after the dP product has consumed it
   float* smadd = reinterpret_cast<float*>(sS + LMAX * PS);
   float* srel = smadd + LMAX;
   const int n = (int)(item / A), h = (int)(item % A);
@@ -295,6 +298,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
   mma_xyT(p, sQ, sK, lane);
   softmax_frag(p, smadd, srel, L, lane);
   mma_xyT(dp, sO, sV, lane);                    // dP = dO V^T
+  __syncwarp();                                 // every lane is done reading V before dropout(P) goes into its tile
   // dS = P o (dP_eff - delta) / 8, P_drop = P o keep * scale; both to smem (bf16) for the transposed products
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -417,14 +421,14 @@ extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_bwd(const 
     return attn_long_bwd_launch(qkv_bf16, mask, mask_ld, relbias, dctx_bf16, dqkv_bf16, dbias_qkv, workspace, n_news, L, A, E,
                                 drop, reinterpret_cast<cudaStream_t>(stream));
   const long long items = (long long)n_news * A;
-  const int grid = (int)((items + ATT_WARPS - 1) / ATT_WARPS);
-  const int smem = ATT_WARPS * ATT_BWD_SMEM_PER_WARP;
+  const int grid = (int)((items + ATT_BWD_WARPS - 1) / ATT_BWD_WARPS);
+  const int smem = ATT_BWD_WARPS * ATT_BWD_SMEM_PER_WARP;
   static bool attr_done = false;
   if (!attr_done) {
     TNR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
-  attn_bwd_kernel<<<grid, ATT_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  attn_bwd_kernel<<<grid, ATT_BWD_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relbias,
       reinterpret_cast<const __nv_bfloat16*>(dctx_bf16), reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias_qkv, n_news, L,
       A, E, drop_or_none(drop));
