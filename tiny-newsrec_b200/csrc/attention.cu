@@ -3,7 +3,7 @@
 // Reference: Tiny-NewsRec/tnlrv3/modeling.py:205-231 (multi_head_attention), mask :446-454,
 // rel-pos bias :458-463.  position_ids are always arange(L) (:162-163), so the reference's per-forward
 // [n, A, L, L] bias is batch-invariant and Toeplitz: a [A, 2L-1] vector indexed by (j - i) + L - 1, which
-// each warp keeps in shared memory.  L > 32 is handled by attention_long.cu (forward).
+// each warp keeps in shared memory.  L > 32 is handled by attention_long.cu (forward and backward).
 //
 // The op is HBM-bound (arithmetic intensity 4*L*E / (8*E) = 15 FLOP/B at L = 30): one warp per
 // (news, head) stages its 32x64 Q/K/V (and dO) tiles with cp.async into padded shared memory,

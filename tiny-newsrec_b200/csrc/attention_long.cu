@@ -1,5 +1,5 @@
 // Self-attention with relative-position bias for 32 < L <= 512 (body / abstract text, table build of
-// title+abstract+body rows), head dim 64, forward.
+// title+abstract+body rows), head dim 64: forward (below) and backward (second half of the file).
 //   P = softmax(Q K^T / 8 + (1 - mask) * -10000 + relbias[h][j - i]);  ctx = dropout(P) V
 // Reference: Tiny-NewsRec/tnlrv3/modeling.py:205-231, mask :446-454, rel-pos bias :458-463.
 //
