@@ -41,6 +41,33 @@ def test_library_exports_every_header_symbol(built_lib):
     assert lib.tnr_abi_version() == 5
 
 
+def test_ctypes_signatures_match_header_declarations():
+    """Every C-ABI entry point: the ctypes binding (tinyrec/_lib.py) declares as many arguments, of pointer / integer /
+    float kind, as include/tinyrec.h does -- a mismatch would corrupt the call frame silently."""
+    import ctypes
+    import tinyrec._lib as L
+    txt = open(os.path.join(ROOT, "include", "tinyrec.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    decls = re.findall(r"\b(?:int|long long|const char\*)\s+(tnr_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", txt, flags=re.S)
+    assert len(decls) >= 30
+    for name, args in decls:
+        if name == "tnr_last_error":
+            continue
+        args = args.strip()
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        sig = L._SIGNATURES[name][0]
+        assert len(sig) == len(params), (name, len(sig), len(params))
+        for ct, decl in zip(sig, params):
+            if "*" in decl:
+                assert ct is ctypes.c_void_p or hasattr(ct, "contents") or ct is ctypes.c_char_p, (name, decl, ct)
+            elif decl.startswith("float"):
+                assert ct is ctypes.c_float, (name, decl, ct)
+            elif decl.startswith("long long"):
+                assert ct is ctypes.c_int64, (name, decl, ct)
+            elif decl.startswith("int"):
+                assert ct is ctypes.c_int, (name, decl, ct)
+
+
 def test_ops_fail_loudly_without_cuda(built_lib):
     import tinyrec._lib as L
     import tinyrec.ops as ops
