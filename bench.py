@@ -54,11 +54,13 @@ def flops_per_step(layers, n_train, tokens):
 def ncu_traffic():
     """DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the 37 GEMM launches
     of one kd4 step) from the committed `ncu --set full` capture; None when the summary is absent."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_ncu_full_v7.json")) as f:
-            return float(json.load(f)["traffic_bytes_per_launch"])
-    except Exception:  # noqa: BLE001
-        return None
+    for name in ("r01_s5_gemm_ncu_full.json", "r01_gemm_ncu_full_v7.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["traffic_bytes_per_launch"])
+        except Exception:  # noqa: BLE001
+            continue
+    return None
 
 
 def peaks():
@@ -416,7 +418,7 @@ def run_tinyrec(a):
                              "peak_source": f"{how} bf16_tflops_sustained",
                              "traffic": ncu_traffic() if a.workload == "kd4" else None,
                              "traffic_note": "DRAM bytes per GEMM launch, ncu --set full over one step "
-                                             "(profiles/r01_gemm_ncu_full_v7.json); algorithmic operand+output bytes "
+                                             "(profiles/r01_s5_gemm_ncu_full.json); algorithmic operand+output bytes "
                                              "average 345 MB per launch (operands are read from HBM once: no re-reads)",
                              "measured": f"CUDA events around every GEMM launch over {n_roof} eagerly launched steps right "
                                          "after the timed region (per-kernel events cannot be recorded inside a graph replay)",
