@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the Tiny-NewsRec hot path on B200 (contract: see the task statement / DESIGN.md).
 
-    python bench.py --gpus N --steps K --warmup W [--workload kd4|kd2|table|eval] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload kd4|kd2|table|table_long|eval] [--no-graph] [--impl reference]
 
 Default workload ``kd4`` is BASELINE.json configs[1]: the 4-layer student, finetuning-stage
 multi-teacher KD step (forward 4 layers + backward layers {2,3} + fused Adam(amsgrad)), M=4
@@ -9,8 +9,15 @@ teachers, per-GPU batch 32, history 50, npratio 4, title 30 tokens, bf16 compute
 MIND-shaped data, random-init weights.  A "step" is one such train step on one batch.
 
 One JSON line is printed by rank 0.  ``value`` is device-timed whole-job impressions/s with
-inputs resident in HBM; ``e2e`` is the same metric through the public ``Model.forward`` API with
-pinned HOST inputs copied to the device every step and the loss read back.
+inputs resident in HBM; ``e2e`` is the same metric through the public API with pinned HOST inputs
+copied to the device every step and the loss read back.  The train step runs the way the public
+API runs it at speed: ``tinyrec.run.GraphedTrainStep`` (zero_grad + Model.forward + backward +
+bucketed NCCL all-reduce + fused Adam captured once into a CUDA graph, replayed per batch;
+``--no-graph`` launches every step eagerly; ``config.launch`` says which ran).  ``roofline`` comes
+from CUDA events around every GEMM launch over eagerly launched steps right after the timed region
+(events cannot be recorded inside a replay).  The secondary workloads add one more leg through the
+public drivers on the whole BASELINE-sized input: ``full_table`` (``tinyrec.run.build_news_table`` over
+the 161k-row table) and ``full_dev_set`` (``tinyrec.run.evaluate`` over 376 471 impressions).
 ``--impl reference`` times the CPU oracle port of the reference (all host threads).
 """
 import argparse
