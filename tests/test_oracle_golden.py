@@ -224,3 +224,27 @@ def test_domain_post_train_forward_and_gradients(golden):
         np.testing.assert_allclose(float(gr.double().abs().sum()), float(g[f"gabs/{k}"]), rtol=5e-4, atol=1e-9)
         if f"gfull/{k}" in g.files:
             np.testing.assert_allclose(gr.numpy(), g[f"gfull/{k}"], rtol=5e-3, atol=1e-6)
+
+
+def test_oracle_auc_matches_installed_sklearn_on_random_ties():
+    """The tie-aware Mann-Whitney restatement of ``roc_auc_score`` (metrics.py:1 -- third-party, unpinned) against the
+    installed scikit-learn on random scores with many ties, and the doc-sim loop against a vectorised formula."""
+    import random
+    sk = pytest.importorskip("sklearn.metrics")
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        n = int(rng.integers(2, 60))
+        y = (rng.random(n) < 0.3).astype(np.int64)
+        if y.min() == y.max():
+            y[0], y[1] = 0, 1
+        s = np.round(rng.standard_normal(n), 1).astype(np.float32)       # rounding makes ties common
+        np.testing.assert_allclose(omet.auc(y, s), sk.roc_auc_score(y, s), atol=1e-12)
+    table = rng.standard_normal((30, 16)).astype(np.float32)
+    got = omet.doc_sim(table, 400, random.Random(5))
+    r = random.Random(5)
+    tot = 0.0
+    for _ in range(400):
+        i, j = r.randrange(1, 30), r.randrange(1, 30)
+        if i != j:
+            tot += float(table[i] @ table[j]) / (float(np.linalg.norm(table[i])) * float(np.linalg.norm(table[j])))
+    assert abs(got - tot / 400) < 1e-6
