@@ -59,15 +59,15 @@ def flops_per_step(layers, n_train, tokens):
 
 
 def ncu_traffic():
-    """DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the 37 GEMM launches
-    of one kd4 step) from the committed `ncu --set full` capture; None when the summary is absent."""
-    for name in ("r01_s5_gemm_ncu_full.json", "r01_gemm_ncu_full_v7.json"):
+    """DRAM bytes per GEMM launch (dram__bytes_read.sum + dram__bytes_write.sum averaged over the GEMM launches
+    of one kd4 step) from the newest committed `ncu --set full` capture -> (bytes, file) or (None, None)."""
+    for name in ("r02_gemm_ncu_full.json", "r01_s5_gemm_ncu_full.json", "r01_gemm_ncu_full_v7.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
-                return float(json.load(f)["traffic_bytes_per_launch"])
+                return float(json.load(f)["traffic_bytes_per_launch"]), "profiles/" + name
         except Exception:  # noqa: BLE001
             continue
-    return None
+    return None, None
 
 
 def peaks():
@@ -138,8 +138,9 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- problem setup
 def make_inputs(rank, device):
-    """N_BATCHES distinct device-resident batches built with the device gather kernels, plus the
-    same tensors in pinned host memory for the e2e leg."""
+    """The device-resident tables (news tokens int32 [N+1, 2L], M teacher tables fp32 [N+1, D]) with their batcher,
+    N_BATCHES distinct INDEX batches (hist_idx, hist_mask, cand_idx, label) on the device and the same in pinned host
+    memory -- what the training loader ships per step (dataloader.py:118-172 after id -> row mapping)."""
     import tinyrec.dataloader as dl
     import tinyrec.synth as synth
     news = synth.news_table(N_NEWS, L=L, seed=1234)
@@ -152,16 +153,19 @@ def make_inputs(rank, device):
     dev_batches, host_batches = [], []
     for i in range(N_BATCHES):
         sl = slice(i * B, (i + 1) * B)
-        hi = torch.from_numpy(hist_idx[sl]).to(device)
-        ci = torch.from_numpy(cand_idx[sl]).to(device)
-        history, candidate, th, tc = batcher.assemble(hi, ci)
-        batch = (history.clone(), torch.from_numpy(hmask[sl]).to(device), candidate.clone(),
-                 torch.from_numpy(label[sl]).to(device), [t.clone() for t in th], [t.clone() for t in tc])
-        dev_batches.append(batch)
-        pin = lambda t: t.cpu().pin_memory()  # noqa: E731
-        host_batches.append((pin(batch[0]), pin(batch[1]), pin(batch[2]), pin(batch[3]), [pin(t) for t in batch[4]],
-                             [pin(t) for t in batch[5]]))
-    return dev_batches, host_batches
+        hb = tuple(torch.from_numpy(np.ascontiguousarray(a[sl])).pin_memory() for a in (hist_idx, hmask, cand_idx, label))
+        host_batches.append(hb)
+        dev_batches.append(tuple(t.to(device) for t in hb))
+    return batcher, dev_batches, host_batches
+
+
+def assembled(batcher, idx_batch, clone=False):
+    """index batch -> the six tensors Model.forward takes (row gathers on the device)."""
+    hist_idx, hmask, cand_idx, label = idx_batch
+    history, candidate, th, tc = batcher.assemble(hist_idx, cand_idx)
+    if clone:
+        return (history.clone(), hmask, candidate.clone(), label, [t.clone() for t in th], [t.clone() for t in tc])
+    return (history, hmask, candidate, label, th, tc)
 
 
 def make_model(layers, trainable, device):
@@ -186,11 +190,9 @@ def make_model(layers, trainable, device):
 
 def bytes_of(batch):
     n = 0
-    for t in batch[:4]:
-        n += t.numel() * t.element_size()
-    for lst in batch[4:]:
-        for t in lst:
-            n += t.numel() * t.element_size()
+    for t in batch:
+        for u in (t if isinstance(t, (list, tuple)) else [t]):
+            n += u.numel() * u.element_size()
     return n
 
 
@@ -250,16 +252,20 @@ def cpu_baseline(layers, trainable, budget_s=20.0):
 
 
 def run_reference(a):
+    """Reference arm: the CPU oracle port of the reference's train step (fwd + bwd + Adam(amsgrad), fp32 torch, all host
+    threads) at the workload's shape and -- host time permitting -- its full per-GPU batch.  The port omits the
+    reference's dead BertPooler / classifier compute and its per-forward one-hot rel-pos bias, so it is FASTER than the
+    reference would be: the GPU / reference ratio the driver computes from it is a lower bound."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = WORKLOADS[a.workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    # size the per-step sample so that (steps + warmup) steps finish within a few minutes
+    # the full batch of 32 impressions per step unless (steps + warmup) such steps would not finish in ~6 minutes
     probe = oracle_train_step_fn(wl["layers"], wl["trainable"], 2)
     t0 = time.perf_counter(); probe(); per_imp = (time.perf_counter() - t0) / 2.0
-    budget = 150.0 / max(1, a.steps + a.warmup)
+    budget = 360.0 / max(1, a.steps + a.warmup)
     b_sample = int(max(1, min(B, budget / max(per_imp, 1e-4))))
     fn = oracle_train_step_fn(wl["layers"], wl["trainable"], b_sample)
     for _ in range(a.warmup):
@@ -274,8 +280,10 @@ def run_reference(a):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(a.workload, 1, b_sample),
             "cpu_baseline": {"value": val, "unit": "impressions/s", "cores": cores, "kind": "port",
-                             "sample": f"{b_sample} impressions per step (of {B}) at the workload shape; oracle port of the "
-                                       "reference modules (the Python reference cannot travel to the GPU box)"},
+                             "sample": f"{b_sample} impressions per step (of {B}) at the workload shape, eval-mode fwd + bwd + "
+                                       "Adam; oracle port of the reference modules (the Python reference cannot travel to "
+                                       "the GPU box); omits the reference's dead pooler/classifier and one-hot rel-pos "
+                                       "work, i.e. a lower bound on the speed-up"},
             "e2e": {"value": val, "unit": "impressions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -295,6 +303,7 @@ def run_tinyrec(a):
     import torch.distributed as dist
     import tinyrec.ops as ops
     import tinyrec.optim as topt
+    import tinyrec.run as trun
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -310,9 +319,11 @@ def run_tinyrec(a):
     if world > 1:
         topt.broadcast_parameters(model, 0)
         opt = topt.DistributedOptimizer(opt)
-    dev_batches, host_batches = make_inputs(rank, device)
+    batcher, dev_batches, host_batches = make_inputs(rank, device)
 
-    def step(batch):
+    def step(idx_batch):
+        """one eager step from an index batch: device row gathers (loader) + forward + backward + optimizer"""
+        batch = assembled(batcher, idx_batch)
         opt.zero_grad()
         out = model(*batch)
         out[0].backward()
@@ -324,14 +335,14 @@ def run_tinyrec(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # The train step as the public API runs it at speed: tinyrec.run.GraphedTrainStep captures zero_grad + forward +
-    # backward (+ bucketed NCCL all-reduce) + Adam once and replays it per batch.  --no-graph keeps the eager loop.
+    # The train step as the public API (tinyrec.run.train) runs it: tinyrec.run.GraphedTrainStep captures the loader's
+    # row gathers + zero_grad + forward + backward (+ bucketed NCCL all-reduce) + Adam once and replays it per batch;
+    # only the index arrays are inputs.  --no-graph keeps the eager loop.
     gstep, graph_note = None, "eager (--no-graph)"
     if not a.no_graph:
         try:
-            import tinyrec.run as trun
-            gstep = trun.GraphedTrainStep(model, opt, dev_batches[0], warmup=max(a.warmup, 3))
-            graph_note = "CUDA graph replay of the whole step (tinyrec.run.GraphedTrainStep)"
+            gstep = trun.GraphedTrainStep(model, opt, dev_batches[0], warmup=max(a.warmup, 3), batcher=batcher)
+            graph_note = "CUDA graph replay of the whole step incl. the loader's row gathers (tinyrec.run.GraphedTrainStep)"
         except Exception as exc:                                  # noqa: BLE001  (reported, not hidden)
             gstep, graph_note = None, f"eager: graph capture failed ({type(exc).__name__}: {exc})"
             torch.cuda.synchronize()
@@ -346,6 +357,20 @@ def run_tinyrec(a):
             return gstep(*batch)[0]
         return step(batch)
 
+    def timed(n_steps):
+        """n_steps device-timed steps over the rotating device-resident batches -> ms (max over ranks)"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(n_steps):
+            run_step(dev_batches[i % N_BATCHES])
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for i in range(max(a.warmup, 3)):
         run_step(dev_batches[i % N_BATCHES])
     barrier()
@@ -354,42 +379,56 @@ def run_tinyrec(a):
     if rank == 0:
         sampler.start()
     launches0 = ops.stats.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(a.steps):
-        run_step(dev_batches[i % N_BATCHES])
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed(a.steps)
     launches = (gstep.launches_per_step * a.steps) if gstep is not None else (ops.stats.launches - launches0)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     value = B * world * a.steps / (ms / 1e3)
+    # ---- the same loop for >= 2.5 s: the step runs at the board power cap, so a 0.15 s region (20 steps) is measured
+    # before the clocks settle; this is the number to quote for long runs
+    n_sus = max(a.steps, int(2500.0 / max(ms / a.steps, 1e-3)) + 1)
+    sampler2 = ClockSampler(local)
+    if rank == 0:
+        sampler2.start()
+    ms_sus = timed(n_sus)
+    clocks_sus = sampler2.stop() if rank == 0 else None
+    sustained = {"value": B * world * n_sus / (ms_sus / 1e3), "unit": "impressions/s", "steps": n_sus,
+                 "seconds": ms_sus / 1e3, "ms_per_step": ms_sus / n_sus, "clocks": clocks_sus}
 
-    # ---- e2e: host (pinned) inputs -> H2D every step -> public API -> loss read back
+    # ---- e2e: pinned host INDEX arrays -> H2D every step -> public API (row gathers + step) -> loss read back
     def e2e_step(hb):
         if gstep is not None:                                     # H2D straight into the graph's static inputs
             return float(gstep(*hb)[0].item())
-        batch = (hb[0].to(device, non_blocking=True), hb[1].to(device, non_blocking=True),
-                 hb[2].to(device, non_blocking=True), hb[3].to(device, non_blocking=True),
-                 [t.to(device, non_blocking=True) for t in hb[4]], [t.to(device, non_blocking=True) for t in hb[5]])
-        return float(step(batch).item())
-    for i in range(3):
-        e2e_step(host_batches[i % N_BATCHES])
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(a.steps):
-        e2e_step(host_batches[i % N_BATCHES])
-    barrier()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = B * world * a.steps / float(t.item())
+        return float(step(tuple(t.to(device, non_blocking=True) for t in hb)).item())
+
+    def wall(fn, batches):
+        for i in range(3):
+            fn(batches[i % N_BATCHES])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(a.steps):
+            fn(batches[i % N_BATCHES])
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return B * world * a.steps / float(t.item())
+    e2e_val = wall(e2e_step, host_batches)
+
+    # ---- the round-1 form of the same leg for comparison: the six ASSEMBLED model inputs (8 MB) shipped from pinned
+    # host memory every step, no loader work on the device (single GPU only: it needs a second captured graph)
+    e2e_pre = None
+    if world == 1 and gstep is not None and not a.no_preassembled:
+        pre_dev = assembled(batcher, dev_batches[0], clone=True)
+        pre_host = []
+        for i in range(N_BATCHES):
+            bt = assembled(batcher, dev_batches[i], clone=True)
+            pin = lambda t: t.cpu().pin_memory()  # noqa: E731
+            pre_host.append((pin(bt[0]), pin(bt[1]), pin(bt[2]), pin(bt[3]), [pin(t) for t in bt[4]], [pin(t) for t in bt[5]]))
+        g2 = trun.GraphedTrainStep(model, opt, pre_dev, warmup=3)
+        e2e_pre = {"value": wall(lambda hb: float(g2(*hb)[0].item()), pre_host), "unit": "impressions/s",
+                   "h2d_bytes_per_step": bytes_of(pre_host[0]), "d2h_bytes_per_step": 4,
+                   "what": "six pre-assembled Model.forward inputs per step from pinned host memory (round-1 e2e)"}
+        g2.close()
 
     # ---- roofline leg: the same steps launched eagerly with CUDA events around every tnr_gemm_bf16 launch (events
     # cannot be recorded inside a graph replay, so the per-kernel durations come from this pass, run right after the
@@ -413,20 +452,25 @@ def run_tinyrec(a):
         ach = gflop / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
         tokens = B * (H + K) * L
         algo = flops_per_step(wl["layers"], len(wl["trainable"]), tokens)
+        traffic, traffic_src = ncu_traffic() if a.workload == "kd4" else (None, None)
         line = {"metric": "kd_train_impressions_per_sec", "value": value, "unit": "impressions/s", "n_gpus": world,
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": dict(config_dict(a.workload, world), launch=graph_note), "clocks": clocks,
+                "config": config_dict(a.workload, world), "launch": graph_note, "clocks": clocks,
+                "sustained": sustained,
                 "e2e": {"value": e2e_val, "unit": "impressions/s", "h2d_bytes_per_step": bytes_of(host_batches[0]),
-                        "d2h_bytes_per_step": 4},
+                        "d2h_bytes_per_step": 4,
+                        "what": "pinned host index arrays (hist_idx, hist_mask, cand_idx, label) in, loader row gathers + "
+                                "train step on the device, loss read back"},
+                "e2e_preassembled": e2e_pre,
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "kernel": "tnr::gemm::gemm_kernel (tcgen05, all GEMM launches of the step)",
                              "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                              "peak_source": f"{how} bf16_tflops_sustained",
-                             "traffic": ncu_traffic() if a.workload == "kd4" else None,
-                             "traffic_note": "DRAM bytes per GEMM launch, ncu --set full over one step "
-                                             "(profiles/r01_s5_gemm_ncu_full.json); algorithmic operand+output bytes "
-                                             "average 345 MB per launch (operands are read from HBM once: no re-reads)",
+                             "traffic": traffic,
+                             "traffic_note": f"DRAM bytes per GEMM launch, ncu --set full over one step ({traffic_src}); "
+                                             "algorithmic operand+output bytes average 345 MB per launch (operands are "
+                                             "read from HBM once: no re-reads)",
                              "measured": f"CUDA events around every GEMM launch over {n_roof} eagerly launched steps right "
                                          "after the timed region (per-kernel events cannot be recorded inside a graph replay)",
                              "gemm_launches_per_step": len(gemm_events) / n_roof,
@@ -434,7 +478,8 @@ def run_tinyrec(a):
                              "gemm_share_of_step": (gms / n_roof) / (ms / a.steps) if ms > 0 else None,
                              "eager_ms_per_step_with_events": eager_ms,
                              "algorithmic_tflop_per_step": algo / 1e12,
-                             "step_frac_of_tensor_roofline": (algo / 1e12) / (ms / a.steps * 1e-3) / peak_tf}}
+                             "step_frac_of_tensor_roofline": (algo / 1e12) / (ms / a.steps * 1e-3) / peak_tf,
+                             "sustained_step_frac_of_tensor_roofline": (algo / 1e12) / (ms_sus / n_sus * 1e-3) / peak_tf}}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl["layers"], wl["trainable"])
         print(json.dumps(line), flush=True)
@@ -758,6 +803,8 @@ def main():
     ap.add_argument("--impl", default="tinyrec", choices=["tinyrec", "reference"])
     ap.add_argument("--workload", default="kd4", choices=sorted(WORKLOADS) + sorted(TABLE_WORKLOADS) + ["eval"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-preassembled", dest="no_preassembled", action="store_true",
+                    help="kd workloads: skip the extra e2e leg that ships pre-assembled model inputs (round-1 form)")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true",
                     help="kd workloads: launch every step eagerly instead of replaying the captured CUDA graph")
     a = ap.parse_args()

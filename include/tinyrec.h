@@ -241,7 +241,8 @@ int tnr_sgemm_nn(const float* A, const float* B, float* C, int M, int N, int K, 
 
 /* ------------------------------------------------------------------ optimiser */
 /* Adam(amsgrad=True) on a flat fp32 buffer (torch.optim.Adam semantics, run.py:134) fused with
- * the bf16 shadow-weight refresh; grad_scale pre-multiplies g. */
+ * the bf16 shadow-weight refresh; grad_scale pre-multiplies g.  vmax == NULL: plain Adam (amsgrad=False, the
+ * optimiser of Post-train_KD.ipynb cell 18): the denominator uses v. */
 int tnr_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, void* shadow_bf16,
                      long long n, float lr, float beta1, float beta2, float eps, int step,
                      float grad_scale, void* stream);

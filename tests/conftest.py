@@ -31,3 +31,18 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
     return load
+
+
+_REPORT = os.path.join(ROOT, "gpurun_out", "test_report.jsonl")
+
+
+def report(label, value, bound=None):
+    """Append one measured test quantity (error, tolerance) to gpurun_out/test_report.jsonl (scratch; summarised
+    into profiles/ by tools/test_report_summary.py)."""
+    import json
+    try:
+        os.makedirs(os.path.dirname(_REPORT), exist_ok=True)
+        with open(_REPORT, "a") as f:
+            f.write(json.dumps({"label": label, "value": value, "bound": bound}) + "\n")
+    except OSError:
+        pass

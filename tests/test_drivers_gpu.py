@@ -1,0 +1,397 @@
+"""GPU parity tests of the public DRIVERS (tinyrec.run) -- the calls bench.py times -- against the CPU oracle:
+
+  * ``run.evaluate``          vs the reference's per-impression loop (run.py:335-379, metrics.py:5-23)
+  * ``run.build_news_table``  vs the per-row news encoder (run.py:432-447, :281-289), row 0 and a ragged last batch
+  * ``run.train``             vs the oracle train loop incl. ``utils.acc`` (run.py:173-200, utils.py:79-83), eager and
+                              CUDA-graph replay, from ``IndexBatches`` and from ``LineBatches``
+  * one KD step at the EXACT benchmark configuration (4 layers, layers {2,3} trainable, B=32, H=50, K=5, L=30, M=4)
+    vs the oracle: losses, scores and all 51 gradient tensors (model_bert.py:262-306)
+  * ``run.test`` / ``run.get_teacher_emb`` mode drivers end to end through the on-disk formats.
+
+Tolerances: bf16 path 1e-2 relative on vectors / scores / losses; ranking metrics exact (1e-12) on the kernel's own
+scores and within 1e-3 on the means end to end (north_star); row gathers bit-exact.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import report
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(got, ref):
+    got = torch.as_tensor(got).double().cpu()
+    ref = torch.as_tensor(ref).double().cpu()
+    return float((got - ref).norm() / (ref.norm() + 1e-30))
+
+
+def _chk(label, value, bound):
+    report(label, float(value), float(bound))
+    assert value < bound, (label, value, bound)
+
+
+# ------------------------------------------------------------------------------------------------ evaluate
+def _eval_problem(n_imp=700, n_news=3000, H=50, D=256, seed=5):
+    """Dev-shaped impressions with the edge cases of run.py:346-361: candidate counts 2..300, constant-label
+    impressions (skipped, run.py:348), duplicate candidates with equal labels (tied scores whose order cannot
+    change MRR / nDCG), a candidate that is both clicked and not clicked (pos/neg tie: AUC only), all-pad and full
+    histories."""
+    import tinyrec.synth as synth
+    rng = np.random.default_rng(seed)
+    hist, hmask, ptr, cand, lab = synth.eval_impressions(n_imp, n_news, H, seed=seed)
+    hist, hmask, cand, lab = hist.copy(), hmask.copy(), cand.copy(), lab.copy()
+    C = np.diff(ptr)
+    C_forced = {0: 2, 1: 300, 2: 299, 3: 3}
+    # rebuild the CSR with a few forced sizes
+    sizes = C.copy()
+    for i, c in C_forced.items():
+        sizes[i] = c
+    ptr2 = np.zeros(n_imp + 1, dtype=np.int64)
+    np.cumsum(sizes, out=ptr2[1:])
+    cand2 = np.empty(int(ptr2[-1]), dtype=np.int32)
+    for i in range(n_imp):                               # distinct candidates per impression: ties only where planted below
+        cand2[int(ptr2[i]):int(ptr2[i + 1])] = rng.choice(n_news, size=int(sizes[i]), replace=False) + 1
+    lab2 = (rng.random(int(ptr2[-1])) < 0.15).astype(np.int8)
+    for i in range(n_imp):
+        seg = slice(int(ptr2[i]), int(ptr2[i + 1]))
+        if lab2[seg].sum() == 0:
+            lab2[ptr2[i]] = 1
+        if lab2[seg].sum() == sizes[i]:
+            lab2[ptr2[i] + 1] = 0
+    kinds = np.zeros(n_imp, dtype=np.int64)              # 0 plain, 1 constant labels, 2 same-label duplicates, 3 pos/neg tie
+    for i in range(10, 30):                              # constant labels: all 0 or all 1
+        lab2[int(ptr2[i]):int(ptr2[i + 1])] = i % 2
+        kinds[i] = 1
+    for i in range(30, 60):                              # duplicates with the same label
+        p0, c = int(ptr2[i]), int(sizes[i])
+        if c >= 4:
+            cand2[p0 + 1] = cand2[p0]
+            lab2[p0 + 1] = lab2[p0]
+            cand2[p0 + c - 1] = cand2[p0 + c - 2]
+            lab2[p0 + c - 1] = lab2[p0 + c - 2]
+            if lab2[p0:p0 + c].sum() in (0, c):
+                lab2[p0 + 2] = 1 - lab2[p0]
+            kinds[i] = 2
+    for i in range(60, 80):                              # the same news once clicked, once not
+        p0, c = int(ptr2[i]), int(sizes[i])
+        if c >= 3:
+            cand2[p0 + 1] = cand2[p0]
+            lab2[p0], lab2[p0 + 1] = 1, 0
+            kinds[i] = 3
+    hist[5], hmask[5] = 0, 0.0                           # empty history (all pad): a zero user vector under the log mask,
+    kinds[5] = 3                                         # i.e. every score ties -- AUC only
+    hist[6] = rng.integers(1, n_news + 1, size=H)
+    hmask[6] = 1.0                                       # full history
+    g = torch.Generator().manual_seed(seed)
+    table = (torch.randn(n_news + 1, D, generator=g) * 0.1)
+    table[0] = 0.0
+    return hist, hmask, ptr2, cand2, lab2, kinds, table
+
+
+@pytest.mark.parametrize("ulm", [False, True])
+def test_evaluate_vs_oracle_loop(ulm):
+    import tinyrec.model_bert as mb
+    import tinyrec.ops as ops
+    import tinyrec.run as trun
+    import tinyrec.synth as synth
+    from oracle import metrics as omet, model as om
+    H, D = 50, 256
+    hist, hmask, ptr, cand, lab, kinds, table = _eval_problem(H=H, D=D)
+    n = hist.shape[0]
+    args = synth.demo_args(user_log_mask=ulm)
+    sd = synth.user_encoder_state("", D, args.user_query_vector_dim, 3)
+    ue = mb.UserEncoder(args)
+    ue.load_state_dict(sd, strict=True)
+    ue.cuda().eval()
+    tab_d = table.cuda()
+    # ---- the driver, in three ragged batches
+    mean, total, per = trun.evaluate(ue, tab_d, hist, hmask, ptr, cand, lab, batch_size=256, return_per_impression=True)
+    mean2, total2 = trun.evaluate(ue, tab_d, hist, hmask, ptr, cand, lab, batch_size=4096)
+    assert total == n and total2 == n
+    assert torch.allclose(mean, mean2, rtol=0, atol=1e-12)            # batching does not change the result
+    per = per.cpu().numpy()
+    # ---- the same kernels once more with the scores exposed: metrics must be EXACT for those scores
+    with torch.no_grad():
+        user = ue.forward_gather(tab_d, torch.from_numpy(hist).cuda(), torch.from_numpy(hmask).cuda())
+        per2 = torch.zeros(n, 5, device="cuda", dtype=torch.float64)
+        scores = torch.zeros(len(cand), device="cuda", dtype=torch.float32)
+        ops.eval_metrics(tab_d, user, torch.from_numpy(ptr).cuda(), torch.from_numpy(cand).cuda(), torch.from_numpy(lab).cuda(),
+                         int(np.diff(ptr).max()), per2, None, scores)
+    scores = scores.cpu().numpy()
+    assert np.array_equal(per2.cpu().numpy()[:, :4], per[:, :4])
+    # ---- oracle: user vectors (fp32 torch), np.dot scores, sklearn-equivalent AUC, metrics.py MRR / nDCG
+    osd = {"user_encoder." + k: v for k, v in sd.items()}
+    with torch.no_grad():
+        o_user = om.user_encoder(osd, "user_encoder.", table[torch.from_numpy(hist.astype(np.int64))], torch.from_numpy(hmask),
+                                 ulm).numpy()
+    _chk(f"evaluate.user_vec.ulm{int(ulm)}", _rel(user, o_user), 1e-2)
+    if ulm:
+        assert float(user[5].abs().max()) == 0.0                       # empty history under the mask -> exact zero vector
+    tab_np = table.numpy()
+    o_per, exact_bad = [], 0
+    worst_score = 0.0
+    for i in range(n):
+        seg = slice(int(ptr[i]), int(ptr[i + 1]))
+        y = lab[seg]
+        o_sc = tab_np[cand[seg]] @ o_user[i]                            # run.py:351
+        worst_score = max(worst_score, float(np.abs(o_sc - scores[seg]).max() / (np.abs(o_sc).max() + 1e-12)))
+        m_own = omet.impression_metrics(y, scores[seg])                # oracle metrics on the kernel's scores
+        o_per.append(omet.impression_metrics(y, o_sc))
+        if m_own is None:
+            assert kinds[i] == 1 and not per[i, :4].any()              # skipped impression contributes zeros
+            continue
+        assert kinds[i] != 1
+        assert abs(per[i, 0] - m_own[0]) < 1e-12, (i, per[i], m_own)   # AUC: tie-aware, exact
+        if kinds[i] != 3:                                              # pos/neg ties: argsort order is unspecified
+            for j in (1, 2, 3):
+                if abs(per[i, j] - m_own[j]) >= 1e-12:
+                    exact_bad += 1
+    assert exact_bad == 0
+    _chk(f"evaluate.score_max_rel.ulm{int(ulm)}", worst_score, 1e-2)
+    o_mean, _ = omet.eval_reduce(o_per, n)                             # run.py:372-379: divide by ALL impressions
+    for j, nm in enumerate(("auc", "mrr", "ndcg5", "ndcg10")):
+        _chk(f"evaluate.mean_{nm}.ulm{int(ulm)}", abs(float(mean[j]) - float(o_mean[j])), 1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ table build
+def test_build_news_table_vs_per_row_encoder():
+    import tinyrec.model_bert as mb
+    import tinyrec.run as trun
+    import tinyrec.synth as synth
+    from oracle import model as om
+    layers, L, n_news = 2, 16, 149                                     # 150 rows: 64 + 64 + 22 (ragged last batch)
+    news = synth.news_table(n_news, L=L, seed=9)
+    sd = synth.model_bert_state("", layers, 4, noisy=True)
+    nsd = {k[len("news_encoder."):]: v for k, v in sd.items() if k.startswith("news_encoder.")}
+    ne = mb.NewsEncoder(synth.demo_args(num_student_layers=layers))
+    ne.load_state_dict(nsd, strict=True)
+    ne.cuda().eval()
+    tab = trun.build_news_table(ne, news, batch_size=64)
+    assert tuple(tab.shape) == (n_news + 1, 256) and tab.dtype == torch.float32
+    one = trun.build_news_table(ne, news, batch_size=4096)
+    assert torch.equal(tab, one)                                       # batching is invisible, bit for bit
+    with torch.no_grad():
+        direct = ne(torch.from_numpy(news.astype(np.int64)).cuda())
+        ref = om.news_encoder(sd, "news_encoder.", torch.from_numpy(news.astype(np.int64)), layers)
+    assert torch.equal(tab, direct)
+    assert torch.isfinite(tab).all()
+    _chk("build_news_table.rel", _rel(tab, ref), 1e-2)
+    _chk("build_news_table.row0_rel", _rel(tab[0], ref[0]), 1e-2)      # the all-pad news (preprocess.py:49-53)
+    rows = ((tab.cpu().double() - ref.double()).norm(dim=1) / ref.double().norm(dim=1)).max()
+    _chk("build_news_table.worst_row_rel", float(rows), 2e-2)
+
+
+# ------------------------------------------------------------------------------------------------ train loop
+def _train_problem(n_imp, B, H, K, L, M, D, layers, seed=21):
+    import tinyrec.synth as synth
+    n_news = 300
+    news = synth.news_table(n_news, L=L, seed=seed)
+    hist_idx, hmask, cand_idx, label = synth.train_impressions(n_imp, n_news, H, K, seed=seed + 1)
+    tables = synth.teacher_tables(n_news, M, D, seed=seed + 2)
+    sd = synth.kd_model_state(layers, M, seed + 3, noisy=True)
+    args = synth.demo_args(num_student_layers=layers, num_teachers=M, user_log_length=H, npratio=K - 1, batch_size=B,
+                           bert_trainable_layer=[layers - 1], lr=1e-3, epochs=1, max_steps_per_epoch=100, log_steps=2,
+                           enable_hvd=False, model_dir=None)
+    return news, hist_idx, hmask, cand_idx, label, tables, sd, args
+
+
+def _oracle_train(sd, args, news, hist_idx, hmask, cand_idx, label, tables, layers, steps, B):
+    """run.py:173-200 on the CPU oracle: forward, utils.acc, zero_grad, backward, Adam(amsgrad) step."""
+    from oracle import model as om, optim as oopt
+    sd = {k: v.clone() for k, v in sd.items()}
+    keys = om.trainable_keys(sd, list(args.bert_trainable_layer))
+    for k in keys:
+        sd[k].requires_grad_(True)
+    state = {k: [torch.zeros_like(sd[k]) for _ in range(3)] for k in keys}
+    log = []
+    for s in range(steps):
+        sl = slice(s * B, (s + 1) * B)
+        history = torch.from_numpy(news[hist_idx[sl]].astype(np.int64))
+        candidate = torch.from_numpy(news[cand_idx[sl]].astype(np.int64))
+        th = [torch.from_numpy(t[hist_idx[sl]]) for t in tables]
+        tc = [torch.from_numpy(t[cand_idx[sl]]) for t in tables]
+        lab = torch.from_numpy(label[sl])
+        for k in keys:
+            sd[k].grad = None
+        out = om.kd_model_forward(sd, history, torch.from_numpy(hmask[sl]), candidate, lab, th, tc, layers,
+                                  bool(args.user_log_mask), args.temperature, args.coef)
+        acc = om.accuracy(lab, out[4].detach())
+        out[0].backward()
+        with torch.no_grad():
+            for k in keys:
+                m_, v_, vm_ = state[k]
+                oopt.adam_amsgrad_step(sd[k], sd[k].grad, m_, v_, vm_, s + 1, lr=args.lr)
+        log.append(dict(total=float(out[0]), distill=float(out[1]), emb=float(out[2]), target=float(out[3]),
+                        acc=float(acc), score=out[4].detach().clone()))
+    return log, sd
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_train_driver_vs_oracle_loop(use_graph):
+    import tinyrec.model_bert as mb
+    import tinyrec.run as trun
+    B, H, K, L, M, D, layers, steps = 4, 6, 3, 12, 2, 256, 2, 3
+    news, hist_idx, hmask, cand_idx, label, tables, sd, args = _train_problem(steps * B + 2, B, H, K, L, M, D, layers)
+    model = mb.Model(args)
+    model.load_state_dict(sd, strict=True)
+    model.cuda().eval()                 # dropout off (the reference trains with it on: covered with injected masks elsewhere)
+    batches = trun.IndexBatches(hist_idx, hmask, cand_idx, label, B)
+    assert len(batches) == steps        # the 2 trailing impressions do not fill a batch
+    hist = []
+    trun.train(args, news, tables, batches, model=model, use_graph=use_graph, history=hist)
+    assert len(hist) == steps
+    ref, osd = _oracle_train(sd, args, news, hist_idx, hmask, cand_idx, label, tables, layers, steps, B)
+    tag = "graph" if use_graph else "eager"
+    for s in range(steps):
+        for nm in ("total", "distill", "emb", "target"):
+            got, want = float(hist[s][nm]), ref[s][nm]
+            _chk(f"train.{tag}.step{s}.{nm}", abs(got - want) / (abs(want) + 1e-3), 1e-2)
+        _chk(f"train.{tag}.step{s}.score", _rel(hist[s]["score"], ref[s]["score"]), 1e-2)
+        # utils.acc (utils.py:79-83): identical argmax unless two scores are closer than the bf16 noise
+        got_acc, want_acc = float(hist[s]["acc"]), ref[s]["acc"]
+        sc = ref[s]["score"]
+        top2 = sc.topk(2, dim=-1).values
+        ambiguous = int(((top2[:, 0] - top2[:, 1]).abs() < 2e-2 * sc.abs().max()).sum())
+        assert abs(got_acc - want_acc) <= ambiguous / B + 1e-6, (s, got_acc, want_acc)
+    # the parameters after 3 optimizer steps: movement measured against the oracle's movement
+    moved = diff = 0.0
+    got_sd = model.state_dict()
+    for k in osd:
+        if osd[k].requires_grad:
+            d0 = (osd[k].detach() - sd[k]).double()
+            moved += float(d0.pow(2).sum())
+            diff += float((got_sd[k].detach().cpu().double() - osd[k].detach().double()).pow(2).sum())
+    assert moved > 0
+    _chk(f"train.{tag}.param_move_rel", (diff / moved) ** 0.5, 0.1)     # Adam normalises: sign flips of ~0 gradients dominate
+
+
+def test_train_driver_line_batches_and_checkpoint(tmp_path):
+    """``LineBatches`` (behaviors_np4 lines -> index batches) through ``run.train`` for two epochs, epoch checkpoints
+    written in the reference's format (run.py:205-214) and read back by ``run.test``."""
+    import tinyrec.checkpoint as ckpt
+    import tinyrec.model_bert as mb
+    import tinyrec.run as trun
+    B, H, K, L, M, D, layers = 4, 6, 5, 12, 2, 256, 2
+    news, hist_idx, hmask, cand_idx, label, tables, sd, args = _train_problem(8, B, H, K, L, M, D, layers)
+    args.epochs, args.model_dir = 2, str(tmp_path / "model")
+    news_index = {f"N{i}": i for i in range(1, news.shape[0])}
+    rnd = random.Random(3)
+    lines = []
+    for i in range(9):                                     # 9 lines -> 2 batches of 4, the ninth is dropped
+        clicks = " ".join(f"N{rnd.randrange(1, news.shape[0])}" for _ in range(rnd.randrange(0, 9))) + " N-unknown"
+        pos = f"N{rnd.randrange(1, news.shape[0])}"
+        neg = " ".join(f"N{rnd.randrange(1, news.shape[0])}" for _ in range(K - 1))
+        lines.append(f"{i}\tU{i}\t11/11/2019\t{clicks}\t{pos}\t{neg}")
+    model = mb.Model(args)
+    model.load_state_dict(sd, strict=True)
+    model.cuda()                                           # training mode: dropout active, as run.py trains
+    before = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    batches = trun.batches_from_lines(lines, news_index, args)
+    hist = []
+    trun.train(args, news, tables, batches, model=model, history=hist)
+    assert len(hist) == 4 and [h["epoch"] for h in hist] == [0, 0, 1, 1]
+    assert all(np.isfinite(float(h["total"])) for h in hist)
+    for ep in (1, 2):
+        assert os.path.exists(os.path.join(args.model_dir, f"epoch-{ep}.pt"))
+    assert trun.latest_checkpoint(args.model_dir).endswith("epoch-2.pt")
+    saved = ckpt.load_checkpoint(os.path.join(args.model_dir, "epoch-2.pt"))
+    assert set(saved) == {"model_state_dict", "category_dict", "word_dict", "subcategory_dict"}
+    changed = [k for k, v in saved["model_state_dict"].items() if not torch.equal(v, before[k])]
+    assert any("encoder.layer.1." in k for k in changed) and not any("encoder.layer.0." in k for k in changed)
+    assert not any(k.startswith("teachers.") for k in changed)
+    # run.test from the checkpoint on disk (model=None): table build + doc-sim + scoring
+    import tinyrec.synth as synth
+    eh, em, ptr, cand, lab = synth.eval_impressions(50, news.shape[0] - 1, H, seed=2)
+    args.load_ckpt_name, args.doc_sim_pairs, args.user_log_mask = None, 1000, True
+    mean, total = trun.test(args, None, news, eh, em, ptr, cand, lab)
+    assert total == 50 and all(0.0 <= float(x) <= 1.0 for x in mean)
+    mean_b, _ = trun.test(args, model.eval(), news, eh, em, ptr, cand, lab)
+    assert torch.allclose(mean, mean_b, atol=1e-12)
+
+
+def test_get_teacher_emb_driver(tmp_path):
+    """run.py:382-460 through the on-disk formats: teacher checkpoints in, pickled float32 [N+1, D] tables out."""
+    import tinyrec.checkpoint as ckpt
+    import tinyrec.model_bert_2 as mb2
+    import tinyrec.run as trun
+    import tinyrec.synth as synth
+    from oracle import model as om
+    layers, L = 2, 12
+    news = synth.news_table(99, L=L, seed=2)
+    args = synth.demo_args(num_hidden_layers=layers, batch_size=1, enable_hvd=False)
+    paths, outs, sds = [], [], []
+    for i in range(2):
+        sd = synth.model_bert_state("", layers, 30 + i, noisy=True)
+        m = mb2.ModelBert(args)
+        m.load_state_dict(sd, strict=True)
+        p = str(tmp_path / f"teacher{i}.pt")
+        ckpt.save_checkpoint(p, m)
+        paths.append(p)
+        outs.append(str(tmp_path / f"teacher{i}.pkl"))
+        sds.append(sd)
+    args.teacher_ckpts, args.teacher_emb_paths = paths, outs
+    tables = trun.get_teacher_emb(args, None, news)
+    for i in range(2):
+        arr = ckpt.load_teacher_table(outs[i])
+        assert arr.dtype == np.float32 and arr.shape == (100, 256) and np.array_equal(arr, tables[i])
+        with torch.no_grad():
+            ref = om.news_encoder(sds[i], "news_encoder.", torch.from_numpy(news.astype(np.int64)), layers)
+        _chk(f"get_teacher_emb.table{i}", _rel(arr, ref), 1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ bench config
+def test_kd_step_at_benchmark_config_vs_oracle():
+    """BASELINE.json configs[1] exactly as bench.py runs it -- 4-layer student, layers {2,3} trainable, B=32, H=50, K=5,
+    L=30, M=4 (1 760 news, 52 800 tokens: CTA-pair GEMMs at M = 52 800, split-K weight gradients at K = 52 800) -- one
+    step against the CPU oracle: the five outputs and the gradients of all 51 trainable tensors."""
+    import tinyrec.model_bert as mb
+    import tinyrec.synth as synth
+    from oracle import model as om
+    B, H, K, L, M, D, layers, trainable = 32, 50, 5, 30, 4, 256, 4, [2, 3]
+    n_news = 5000
+    news = synth.news_table(n_news, L=L, seed=1234)
+    hist_idx, hmask, cand_idx, label = synth.train_impressions(B, n_news, H, K, seed=77)
+    tables = synth.teacher_tables(n_news, M, D, seed=1234)
+    history = torch.from_numpy(news[hist_idx].astype(np.int64))
+    candidate = torch.from_numpy(news[cand_idx].astype(np.int64))
+    th = [torch.from_numpy(t[hist_idx]) for t in tables]
+    tc = [torch.from_numpy(t[cand_idx]) for t in tables]
+    sd = synth.kd_model_state(layers, M, 0, noisy=True)
+    args = synth.demo_args(num_student_layers=layers, num_teachers=M, bert_trainable_layer=trainable)
+    model = mb.Model(args)
+    model.load_state_dict(sd, strict=True)
+    model.cuda().eval()
+    import tinyrec.run as trun
+    trun.apply_freeze_policy(model, trainable)
+    named = dict(model.named_parameters())
+    n_trainable = sum(1 for p in named.values() if p.requires_grad)
+    assert n_trainable == 51
+    dev = lambda t: t.cuda()  # noqa: E731
+    res = model(dev(history), dev(torch.from_numpy(hmask)), dev(candidate), dev(torch.from_numpy(label)),
+                [dev(t) for t in th], [dev(t) for t in tc])
+    res[0].backward()
+    torch.cuda.synchronize()
+    # ---- oracle (fp32 torch on the host cores; ~1 TFLOP forward + 0.8 TFLOP backward)
+    torch.set_num_threads(os.cpu_count() or 1)
+    osd = {k: v.clone() for k, v in sd.items()}
+    keys = om.trainable_keys(osd, trainable)
+    assert len(keys) == 51
+    for k in keys:
+        osd[k].requires_grad_(True)
+    ref = om.kd_model_forward(osd, history, torch.from_numpy(hmask), candidate, torch.from_numpy(label), th, tc, layers,
+                              False, args.temperature, args.coef)
+    ref[0].backward()
+    for v, r, nm in zip(res[:4], ref[:4], ("total", "distill", "emb", "target")):
+        _chk(f"kd4_bench_config.{nm}", abs(float(v) - float(r)) / (abs(float(r)) + 1e-6), 1e-2)
+    _chk("kd4_bench_config.score", _rel(res[4], ref[4].detach()), 1e-2)
+    from test_model_gpu import GRAD_TOL, _grad_err
+    worst = 0.0
+    for k in keys:
+        r = _grad_err(k, named[k].grad, osd[k].grad, named)
+        worst = max(worst, r)
+        _chk(f"kd4_bench_config.grad.{k}", r, GRAD_TOL)
+    report("kd4_bench_config.grad.worst", worst, GRAD_TOL)

@@ -316,3 +316,86 @@ def test_checkpoint_and_teacher_table_roundtrip(tmp_path):
     with open(tp, "rb") as f:
         assert np.array_equal(pickle.load(f), tab)                                                   # run.py:458-459
     assert np.array_equal(ck.load_teacher_table(str(tp)), tab)
+
+
+def test_batch_sources_shard_evenly_and_reiterate():
+    """run.IndexBatches / run.LineBatches (streaming.py:53-54 sharding): every rank gets the SAME number of batches
+    whatever the remainder (a ragged tail would un-pair the per-step all-reduces), ranks are disjoint, a second
+    pass (epoch) yields again, and parsed lines equal the oracle's batch assembly (dataloader.py:118-148)."""
+    import random
+    import tinyrec.run as trun
+    import tinyrec.synth as synth
+    from oracle import batching as ob
+    H, K, bs = 6, 5, 4
+    hist_idx, hmask, cand_idx, label = synth.train_impressions(4 * 11 + 3, 200, H, K, seed=3)      # 11 batches + 3 left over
+    for world in (1, 2, 3, 4):
+        seen, lens = [], []
+        for rank in range(world):
+            src = trun.IndexBatches(hist_idx, hmask, cand_idx, label, bs, rank=rank, world=world, device="cpu")
+            first = [tuple(t.clone() for t in b) for b in src]
+            second = [b for b in src]                                                             # re-iterable
+            assert len(first) == len(second) == len(src) == 11 // world
+            lens.append(len(first))
+            for b, b2 in zip(first, second):
+                assert all(torch.equal(x, y) for x, y in zip(b, b2))
+                assert b[0].dtype == torch.int32 and b[1].dtype == torch.float32 and b[3].dtype == torch.int64
+                seen.append(b[0].numpy().tobytes())
+        assert len(set(lens)) == 1 and len(set(seen)) == len(seen)                                # equal counts, disjoint
+    # LineBatches
+    args = synth.demo_args(user_log_length=H, npratio=K - 1, batch_size=bs)
+    news_index = {f"N{i}": i for i in range(1, 50)}
+    rnd = random.Random(0)
+    lines = []
+    for i in range(2 * 2 * bs + 3):
+        clicks = " ".join(f"N{rnd.randrange(1, 60)}" for _ in range(rnd.randrange(0, 10)))      # ids >= 50 are unknown -> 0
+        neg = " ".join(f"N{rnd.randrange(1, 50)}" for _ in range(K - 1))
+        lines.append(f"{i}\tU\tt\t{clicks}\tN{rnd.randrange(1, 50)}\t{neg}")
+    for rank in range(2):
+        src = trun.batches_from_lines(lines, news_index, args, rank=rank, world=2, device="cpu", seed=5)
+        ep0 = [tuple(t.clone() for t in b) for b in src]
+        ep1 = [tuple(t.clone() for t in b) for b in src]
+        assert len(ep0) == len(ep1) == 2                       # 19 lines // (2 ranks x 4) = 2 batches per rank
+        rng = random.Random(5)                                 # epoch 0 draws labels from Random(seed + 0)
+        for b, (h, m, c, lab) in enumerate(ep0):
+            for j in range(bs):
+                cols = lines[(b * bs + j) * 2 + rank].split("\t")
+                want_h, want_m = ob.pad_history(ob.to_index(cols[3].split(), news_index), H)
+                y = rng.randint(0, K - 1)
+                want_c = ob.insert_positive(ob.to_index(cols[4].split(), news_index), ob.to_index(cols[5].split(), news_index), y)
+                assert h[j].tolist() == want_h and m[j].tolist() == [float(x) for x in want_m]
+                assert c[j].tolist() == want_c and int(lab[j]) == y
+        assert all(torch.equal(a[0], b_[0]) for a, b_ in zip(ep0, ep1))      # same lines ...
+        assert any(not torch.equal(a[3], b_[3]) for a, b_ in zip(ep0, ep1))  # ... fresh positive slots per epoch
+
+
+def test_news_encoder_model_name_must_load(tmp_path):
+    """model_bert.py:114 ``from_pretrained(args.model_name)``: a set model_name is loaded (UniLM .bin conversion) or
+    is an error -- never a silent random init."""
+    import tinyrec.model_bert as mb
+    import tinyrec.synth as synth
+    from tinyrec._lib import TinyRecError
+    with pytest.raises(TinyRecError):
+        mb.NewsEncoder(synth.demo_args(num_student_layers=1, model_name=str(tmp_path / "missing.bin")))
+    src = synth.bert_model_state("", 2, 8)
+    fused = {}
+    for k, v in src.items():                                   # UniLM layout: fused qkv, q_bias / v_bias, no key bias
+        if k.endswith("attention.self.query.weight"):
+            base = k[:-len("query.weight")]
+            fused[base + "qkv_linear.weight"] = torch.cat([v, src[base + "key.weight"], src[base + "value.weight"]], 0)
+            fused[base + "q_bias"] = src[base + "query.bias"]
+            fused[base + "v_bias"] = src[base + "value.bias"]
+        elif ".attention.self." in k or k.startswith(("bert.pooler", "classifier")):
+            continue
+        elif k == "bert.rel_pos_bias.weight":
+            fused["bert.encoder.rel_pos_bias.weight"] = v
+        else:
+            fused[k] = v
+    path = str(tmp_path / "unilm.bin")
+    torch.save(fused, path)
+    ne = mb.NewsEncoder(synth.demo_args(num_student_layers=1, model_name=path))      # 2-layer file into a 1-layer student
+    got = ne.bert_model.state_dict()
+    assert torch.equal(got["bert.encoder.layer.0.attention.self.value.weight"], src["bert.encoder.layer.0.attention.self.value.weight"])
+    assert torch.equal(got["bert.embeddings.word_embeddings.weight"], src["bert.embeddings.word_embeddings.weight"])
+    assert torch.equal(got["bert.rel_pos_bias.weight"], src["bert.rel_pos_bias.weight"])
+    assert float(got["bert.encoder.layer.0.attention.self.key.bias"].abs().max()) == 0.0
+    assert all(k.startswith(("bert.pooler", "classifier")) for k in ne.pretrained_missing_keys)

@@ -3,8 +3,10 @@
 (b) the CPU oracle on seeded synthetic inputs.
 
 Tolerances: bf16 compute path -> 1e-2 relative (BASELINE.json north_star) on logits /
-embeddings / losses; gradients 3e-2 relative in norm (bf16 activations and grads);
-bit-exact for gathers; 1e-3 absolute for ranking metrics (they are exact in practice)."""
+embeddings / losses (SCORE_TOL); gradients per tensor relative in norm (GRAD_TOL: bf16 activations and
+activation gradients; every measured value is appended to gpurun_out/test_report.jsonl and the bounds are
+kept at about twice the worst one); bit-exact for gathers; 1e-3 absolute for ranking metrics (they are
+exact in practice)."""
 import math
 
 import numpy as np
@@ -12,6 +14,19 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+
+
+GRAD_TOL = 5e-2           # per-tensor relative gradient error (bf16 activations / activation gradients); see _chk
+GRAD_TOL_12L = 8e-2       # 12 bf16 layers in front of the loss
+SCORE_TOL = 1e-2          # north_star: logits / embeddings within 1e-2 relative on the bf16 path
+
+
+def _chk(label, value, bound):
+    """assert value < bound, recording the measured value (tests/conftest.py: gpurun_out/test_report.jsonl) so the
+    bounds in this file can be kept at ~2x what the kernels actually deliver."""
+    from conftest import report
+    report(label, float(value), float(bound))
+    assert value < bound, (label, value, bound)
 
 
 def _rel(got, ref):
@@ -94,7 +109,7 @@ def test_model_bert_vs_reference_golden(golden, tag, ulm):
     assert _rel(hv, g[f"hist_{tag}"]) < 1e-2
     assert _rel(cv, g[f"cand_{tag}"]) < 1e-2
     assert _rel(uv, g[f"user_{tag}"]) < 1e-2
-    assert _rel(score, g[f"score_{tag}"]) < 2e-2
+    _chk("test_model_bert_vs_reference_golden.score", _rel(score, g[f"score_{tag}"]), SCORE_TOL)
     if ulm:
         assert float(uv[1].abs().max()) == 0.0          # fully masked history -> exact zeros
 
@@ -113,7 +128,7 @@ def test_plmnr_loss_vs_reference_golden(golden):
         loss, score = m(torch.from_numpy(g["history"]).cuda(), torch.from_numpy(g["history_mask"]).cuda(),
                         torch.from_numpy(g["candidate"]).cuda(), torch.from_numpy(g["plmnr_label"]).cuda())
     assert abs(float(loss) - float(g["plmnr_loss"])) < 1e-2 * abs(float(g["plmnr_loss"])) + 1e-3
-    assert _rel(score, g["plmnr_score"]) < 2e-2
+    _chk("test_plmnr_loss_vs_reference_golden.score", _rel(score, g["plmnr_score"]), SCORE_TOL)
 
 
 def _kd_model(g, ulm):
@@ -141,7 +156,7 @@ def test_kd_forward_vs_reference_golden(golden, tag, ulm):
     for v, nm in zip(res[:4], ("total", "distill", "emb", "target")):
         ref = float(g[f"{nm}_{tag}"])
         assert abs(float(v) - ref) < 1e-2 * abs(ref) + 1e-4, (nm, float(v), ref)
-    assert _rel(res[4], g[f"score_{tag}"]) < 2e-2
+    _chk("test_kd_forward_vs_reference_golden.score", _rel(res[4], g[f"score_{tag}"]), SCORE_TOL)
 
 
 def test_kd_gradients_vs_reference_golden(golden):
@@ -161,7 +176,7 @@ def test_kd_gradients_vs_reference_golden(golden):
             ref = torch.from_numpy(g[f"gslice/{k}"])
             r = _grad_err(k, gr[:16, :16], ref, named)
         worst = max(worst, r)
-        assert r < 5e-2, (k, r)
+        _chk(f"test_kd_gradients_vs_reference_golden.grad.{k}", r, GRAD_TOL)
         ref_abs = float(g[f"gabs/{k}"])
         if not k.endswith(("key.bias", "att_fc2.bias")):
             assert abs(float(gr.double().abs().sum()) - ref_abs) < 3e-2 * ref_abs + 1e-7, k
@@ -203,7 +218,7 @@ def test_nrms_kd_vs_reference_golden(golden, tag, ulm):
     for v, nm in zip(res[:4], ("total", "distill", "emb", "target")):
         ref = float(g[f"{nm}_{tag}"])
         assert abs(float(v) - ref) < 1e-2 * abs(ref) + 1e-4, (nm, float(v), ref)
-    assert _rel(res[4], g[f"score_{tag}"]) < 2e-2
+    _chk("test_nrms_kd_vs_reference_golden.score", _rel(res[4], g[f"score_{tag}"]), SCORE_TOL)
     res[0].backward()
     named = dict(m.named_parameters())
     for k in [str(s) for s in g[f"trainable_names_{tag}"]]:
@@ -215,7 +230,7 @@ def test_nrms_kd_vs_reference_golden(golden, tag, ulm):
         else:
             ref = torch.from_numpy(g[f"{tag}/gslice/{k}"])
             r = _grad_err(k, gr[:16, :16], ref, named)
-        assert r < 5e-2, (k, r)
+        _chk(f"test_nrms_kd_vs_reference_golden.grad.{k}", r, GRAD_TOL)
     # the stand-alone user encoder (run.py:343) gives the same user vector as the training path
     st = m.train_state()
     hist = st.last["news"][:inputs[0].shape[0] * inputs[0].shape[1]].view(inputs[0].shape[0], inputs[0].shape[1], -1)
@@ -256,13 +271,13 @@ def test_nrms_step_vs_oracle_at_demo_shape():
                                   layers, ulm, args.temperature, args.coef)
         ref[0].backward()
         assert abs(float(res[0]) - float(ref[0])) < 1e-2 * abs(float(ref[0])) + 1e-4
-        assert _rel(res[4], ref[4].detach()) < 2e-2
+        _chk("test_nrms_step_vs_oracle_at_demo_shape.score", _rel(res[4], ref[4].detach()), SCORE_TOL)
         named = dict(m.named_parameters())
         for k in names:
             if osd[k].grad is None:                 # pad_doc in the user_log_mask branch
                 assert float(named[k].grad.abs().max()) == 0.0, k
                 continue
-            assert _grad_err(k, named[k].grad, osd[k].grad, named) < 5e-2, k
+            _chk(f"test_nrms_step_vs_oracle_at_demo_shape.grad.{k}", _grad_err(k, named[k].grad, osd[k].grad, named), GRAD_TOL)
 
 
 def test_kd_step_vs_oracle_at_demo_shape():
@@ -295,11 +310,11 @@ def test_kd_step_vs_oracle_at_demo_shape():
     ref[0].backward()
     for v, r, nm in zip(res[:4], ref[:4], ("total", "distill", "emb", "target")):
         assert abs(float(v) - float(r)) < 1e-2 * abs(float(r)) + 1e-4, (nm, float(v), float(r))
-    assert _rel(res[4], ref[4].detach()) < 2e-2
+    _chk("test_kd_step_vs_oracle_at_demo_shape.score", _rel(res[4], ref[4].detach()), SCORE_TOL)
     named = dict(m.named_parameters())
     for k in keys:
         r = _grad_err(k, named[k].grad, osd[k].grad, named)
-        assert r < 5e-2, (k, r)
+        _chk(f"test_kd_step_vs_oracle_at_demo_shape.grad.{k}", r, GRAD_TOL)
 
 
 def test_kd_training_mode_step_with_dropout_vs_oracle_with_injected_masks():
@@ -341,11 +356,11 @@ def test_kd_training_mode_step_with_dropout_vs_oracle_with_injected_masks():
     ref[0].backward()
     for v, r, nm in zip(res[:4], ref[:4], ("total", "distill", "emb", "target")):
         assert abs(float(v) - float(r)) < 1e-2 * abs(float(r)) + 1e-4, (nm, float(v), float(r))
-    assert _rel(res[4], ref[4].detach()) < 2e-2
+    _chk("test_kd_training_mode_step_with_dropout_vs_oracle_with_injected_masks.score", _rel(res[4], ref[4].detach()), SCORE_TOL)
     named = dict(m.named_parameters())
     for k in keys:
         r = _grad_err(k, named[k].grad, osd[k].grad, named)
-        assert r < 5e-2, (k, r)
+        _chk(f"test_kd_training_mode_step_with_dropout_vs_oracle_with_injected_masks.grad.{k}", r, GRAD_TOL)
     # eval() switches dropout off and a new step draws new masks
     with torch.no_grad():
         a1 = float(m(*gpu_in)[0])
@@ -528,10 +543,10 @@ def test_kd_step_long_sequence_vs_oracle():
                               layers, False, args.temperature, args.coef)
     ref[0].backward()
     assert abs(float(res[0]) - float(ref[0])) < 1e-2 * abs(float(ref[0])) + 1e-4
-    assert _rel(res[4], ref[4].detach()) < 2e-2
+    _chk("test_kd_step_long_sequence_vs_oracle.score", _rel(res[4], ref[4].detach()), SCORE_TOL)
     named = dict(m.named_parameters())
     for k in names:
-        assert _grad_err(k, named[k].grad, osd[k].grad, named) < 5e-2, k
+        _chk(f"test_kd_step_long_sequence_vs_oracle.grad.{k}", _grad_err(k, named[k].grad, osd[k].grad, named), GRAD_TOL)
 
 
 def test_doc_sim_matches_reference_loop():
@@ -584,14 +599,15 @@ def test_post_train_distill_model_vs_oracle():
     ref[0].backward()
     for got, want in zip(res[:4], ref[:4]):
         assert abs(float(got) - float(want)) < 1e-2 * abs(float(want)) + 1e-4, (float(got), float(want))
-    assert _rel(res[4], ref[4].detach()) < 2e-2
+    _chk("test_post_train_distill_model_vs_oracle.score", _rel(res[4], ref[4].detach()), SCORE_TOL)
     named = dict(m.named_parameters())
     for k in names:
-        assert _grad_err(k, named[k].grad, osd[k].grad, named) < 5e-2, k
+        _chk(f"test_post_train_distill_model_vs_oracle.grad.{k}", _grad_err(k, named[k].grad, osd[k].grad, named), GRAD_TOL)
     # inference form of cell 12
     with torch.no_grad():
         sc, te, be = m.student(title.cuda(), body.cuda())
-    assert _rel(sc, ref[4].detach()) < 2e-2 and tuple(te.shape) == (B, K1, D) and tuple(be.shape) == (B, D)
+    _chk("test_post_train_distill_model_vs_oracle.score_inference", _rel(sc, ref[4].detach()), SCORE_TOL)
+    assert tuple(te.shape) == (B, K1, D) and tuple(be.shape) == (B, D)
     # cell 18: bert_model at 1e-6, the rest at 1e-5
     opt = topt.Adam(m, lr=1e-5)
     ranges = m.lr_ranges(1e-6, 1e-5)
@@ -642,7 +658,7 @@ def test_domain_post_train_model_vs_reference_golden(golden):
         else:
             refg = torch.from_numpy(g[f"gslice/{k}"])
             r = _grad_err(k, gr[:16, :16], refg, named)
-        assert r < 8e-2, (k, r)             # 12 bf16 layers in front of the loss; the scores are ~60 with gaps of ~1
+        _chk(f"test_domain_post_train_model_vs_reference_golden.grad.{k}", r, GRAD_TOL_12L)             # 12 bf16 layers in front of the loss; the scores are ~60 with gaps of ~1
 
 
 def test_scoring_path_sees_parameters_updated_by_the_fused_adam(golden):

@@ -400,11 +400,7 @@ extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_fwd(const 
   const long long items = (long long)n_news * A;
   const int grid = (int)((items + ATT_WARPS - 1) / ATT_WARPS);
   const int smem = ATT_WARPS * ATT_FWD_SMEM_PER_WARP;
-  static bool attr_done = false;
-  if (!attr_done) {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
+  TNR_SET_SMEM(attn_fwd_kernel, smem);
   attn_fwd_kernel<<<grid, ATT_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relbias, reinterpret_cast<__nv_bfloat16*>(ctx_bf16),
       n_news, L, A, E, drop_or_none(drop));
@@ -423,11 +419,7 @@ extern "C" __attribute__((visibility("default"))) int tnr_attn_relpos_bwd(const 
   const long long items = (long long)n_news * A;
   const int grid = (int)((items + ATT_BWD_WARPS - 1) / ATT_BWD_WARPS);
   const int smem = ATT_BWD_WARPS * ATT_BWD_SMEM_PER_WARP;
-  static bool attr_done = false;
-  if (!attr_done) {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
+  TNR_SET_SMEM(attn_bwd_kernel, smem);
   attn_bwd_kernel<<<grid, ATT_BWD_WARPS * 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relbias,
       reinterpret_cast<const __nv_bfloat16*>(dctx_bf16), reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias_qkv, n_news, L,

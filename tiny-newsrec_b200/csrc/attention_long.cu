@@ -699,14 +699,8 @@ int attn_long_bwd_launch(const void* qkv_bf16, const int64_t* mask, int mask_ld,
   float* ws_delta = ws + (size_t)n_news * A * L;
   const int smem_dq = 6 * LQB * LTS * 2 + (k_chunks * LKB + 2 * L - 1 + LKB) * 4;
   const int smem_dkv = 8 * LQB * LTS * 2 + (LKB + 2 * L - 1 + LKB) * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(attn_long_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        6 * LQB * LTS * 2 + (LONG_LMAX + 2 * LONG_LMAX + LKB) * 4));
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(attn_long_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        8 * LQB * LTS * 2 + (LKB + 2 * LONG_LMAX + LKB) * 4));
-    attr_done = true;
-  }
+  TNR_SET_SMEM(attn_long_bwd_dq_kernel, 6 * LQB * LTS * 2 + (LONG_LMAX + 2 * LONG_LMAX + LKB) * 4);
+  TNR_SET_SMEM(attn_long_bwd_dkv_kernel, 8 * LQB * LTS * 2 + (LKB + 2 * LONG_LMAX + LKB) * 4);
   attn_long_bwd_dq_kernel<<<(unsigned)blocks, 128, smem_dq, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relbias, reinterpret_cast<const __nv_bfloat16*>(dctx_bf16),
       reinterpret_cast<__nv_bfloat16*>(dqkv_bf16), dbias, ws_lse, ws_delta, n_news, L, A, E, q_blocks, drop_or_none(drop));
@@ -727,12 +721,7 @@ int attn_long_fwd_launch(const void* qkv_bf16, const int64_t* mask, int mask_ld,
   const long long blocks = (long long)n_news * A * q_blocks;
   TNR_REQUIRE(blocks < (1ll << 31), "tnr_attn_relpos_fwd: too many blocks");
   const int smem = 5 * LQB * LTS * 2 + (k_chunks * LKB + 2 * L - 1 + LKB) * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(attn_long_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        5 * LQB * LTS * 2 + (LONG_LMAX + 2 * LONG_LMAX + LKB) * 4));
-    attr_done = true;
-  }
+  TNR_SET_SMEM(attn_long_fwd_kernel, 5 * LQB * LTS * 2 + (LONG_LMAX + 2 * LONG_LMAX + LKB) * 4);
   attn_long_fwd_kernel<<<(unsigned)blocks, 128, smem, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), mask, mask_ld, relbias, reinterpret_cast<__nv_bfloat16*>(ctx_bf16),
       n_news, L, A, E, q_blocks, drop_or_none(drop));

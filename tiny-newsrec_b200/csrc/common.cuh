@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <atomic>
 
 #include "../../include/tinyrec.h"
 
@@ -29,6 +30,22 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 #define TNR_LAUNCH_CHECK() TNR_CHECK_CUDA(cudaGetLastError())
+
+// Dynamic shared-memory opt-in of a kernel, done once PER DEVICE (cudaFuncSetAttribute applies to the current
+// device's copy of the function) and safe under concurrent host threads: a process that launches on a second
+// device, or from the loader thread, gets the attribute set there too.  `bytes` may grow between calls.
+constexpr int MAX_DEVICES = 64;
+#define TNR_SET_SMEM(kern, bytes)                                                                         \
+  do {                                                                                                    \
+    static std::atomic<int> tnr_smem_done_[::tnr::MAX_DEVICES];                                           \
+    int tnr_dev_ = -1;                                                                                    \
+    TNR_CHECK_CUDA(cudaGetDevice(&tnr_dev_));                                                             \
+    TNR_REQUIRE(tnr_dev_ >= 0 && tnr_dev_ < ::tnr::MAX_DEVICES, "device index %d out of range", tnr_dev_); \
+    if (tnr_smem_done_[tnr_dev_].load(std::memory_order_acquire) < (int)(bytes)) {                         \
+      TNR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      tnr_smem_done_[tnr_dev_].store((int)(bytes), std::memory_order_release);                            \
+    }                                                                                                     \
+  } while (0)
 
 int num_sms();           // cached SM count of the current device (148 on B200)
 

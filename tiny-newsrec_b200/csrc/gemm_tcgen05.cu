@@ -722,11 +722,7 @@ template <int BN, bool A_MN, bool B_MN, int ACT, bool EPI_TMA, bool CTA2 = false
 static int launch(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
   using C = Cfg<BN, EPI_TMA, CTA2>;
   auto kern = gemm_kernel<BN, A_MN, B_MN, ACT, EPI_TMA, CTA2>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
-  }
+  TNR_SET_SMEM(kern, C::SMEM_BYTES);
   if (CTA2) {
     // `grid` counts CTA pairs: launch them as clusters of 2 (the two SMs of one TPC)
     cudaLaunchConfig_t cfg = {};

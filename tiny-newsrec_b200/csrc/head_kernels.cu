@@ -55,7 +55,11 @@ kd_loss_kernel(const float* __restrict__ s_news, const float* __restrict__ s_use
   const size_t Rext = (size_t)R + B;
   const float* cand = s_news + ((size_t)B * H + (size_t)b * K) * D;
   const float* usr = s_user + (size_t)b * D;
-  const int lab = (int)label[b];
+  // a label outside 0..K-1 (torch's cross_entropy device-asserts on it) must not index shared memory out of bounds:
+  // it is read as 0 and the impression's target loss -- hence the batch losses -- become NaN
+  const long long lab_raw = label[b];
+  const bool lab_bad = lab_raw < 0 || lab_raw >= (long long)K;
+  const int lab = lab_bad ? 0 : (int)lab_raw;
   const float invB = 1.0f / (float)B;
 
   // scores: (1 + M) * K dot products of length D, one warp each
@@ -100,7 +104,7 @@ kd_loss_kernel(const float* __restrict__ s_news, const float* __restrict__ s_use
     float se = 0.f;
     for (int k = 0; k < K; ++k) se += expf(s_sc[k] - mx);
     const float lse = mx + logf(se);
-    const float target = lse - s_sc[lab];
+    const float target = lab_bad ? __int_as_float(0x7fc00000) : lse - s_sc[lab];
     float distill = 0.f, emb = 0.f;
     float pT[KD_MAXK];
     for (int k = 0; k < K; ++k) pT[k] = 0.f;

@@ -978,11 +978,7 @@ static int ue_fwd_launch(const tnr_user_encoder_io* enc, int n_enc, const float*
   for (int i = n_enc; i < UE_MAX_ENC; ++i) p.enc[i] = enc[0];
   p.mask = mask; p.idx = idx; p.n_rows = n_rows; p.use_mask = use_mask; p.H = H; p.D = D; p.Q = Q;
   const int smem = (UE_HMAX * (D + 4) + 2 * UE_HMAX + 2 * 256 * UE_WS) * 4 + UE_HMAX * 8;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(user_encoder_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  TNR_SET_SMEM(user_encoder_fwd_kernel, smem);
   user_encoder_fwd_kernel<<<dim3(B, n_enc), UE_THREADS, smem, st>>>(p);
   TNR_LAUNCH_CHECK();
   return 0;
@@ -1058,13 +1054,9 @@ TNR_API int tnr_user_encoder_score(const float* vecs, long long n_rows, const in
   p.logits = a_out; p.live = wsi + 4; p.n_live = wsi; p.c_pad = reinterpret_cast<float*>(wsi + 1);
   p.R = R; p.D = D; p.Q = Q;
   const int smem = (UL_HALF * (D + 4) + UL_STAGES * UL_ROWS * UL_XS + 2 * UL_HALF + D) * 4;
-  static bool attr = false;
-  if (!attr) {
-    const int max_smem = (UL_HALF * (UL_DMAX + 4) + UL_STAGES * UL_ROWS * UL_XS + 2 * UL_HALF + UL_DMAX) * 4;
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(ue_logits_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(ue_logits_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    attr = true;
-  }
+  const int max_smem = (UL_HALF * (UL_DMAX + 4) + UL_STAGES * UL_ROWS * UL_XS + 2 * UL_HALF + UL_DMAX) * 4;
+  TNR_SET_SMEM(ue_logits_kernel<true>, max_smem);
+  TNR_SET_SMEM(ue_logits_kernel<false>, max_smem);
   const int n_tiles = (R + UL_ROWS - 1) / UL_ROWS;        // upper bound: the live count is only known on the device
   const int pairs = n_tiles < num_sms() / 2 ? n_tiles : num_sms() / 2;
   const int grid = 2 * pairs;
@@ -1094,11 +1086,7 @@ TNR_API int tnr_user_encoder_bwd(const float* vecs, const float* mask, const flo
   if (B == 0) return 0;
   const int Qp = (Q + 7) & ~7;
   const int smem = (UE_HMAX * (D + 4) + UE_HMAX * (Qp + 4) + 3 * UE_HMAX + D) * 4;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(user_encoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  TNR_SET_SMEM(user_encoder_bwd_kernel, smem);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* dU = scratch;
   float* Vb = scratch + (size_t)B * H * Q;

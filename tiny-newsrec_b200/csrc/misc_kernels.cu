@@ -24,7 +24,8 @@ adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* _
     const float4 gg = *reinterpret_cast<const float4*>(g + i4);
     float4 mm = *reinterpret_cast<float4*>(m + i4);
     float4 vv = *reinterpret_cast<float4*>(v + i4);
-    float4 vx = *reinterpret_cast<float4*>(vmax + i4);
+    const bool ams = vmax != nullptr;          // vmax == NULL: plain Adam (torch amsgrad=False), denominator from v
+    float4 vx = ams ? *reinterpret_cast<float4*>(vmax + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
     float* P = reinterpret_cast<float*>(&pp);
     const float* G = reinterpret_cast<const float*>(&gg);
     float* Mm = reinterpret_cast<float*>(&mm);
@@ -41,7 +42,7 @@ adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* _
     *reinterpret_cast<float4*>(p + i4) = pp;
     *reinterpret_cast<float4*>(m + i4) = mm;
     *reinterpret_cast<float4*>(v + i4) = vv;
-    *reinterpret_cast<float4*>(vmax + i4) = vx;
+    if (ams) *reinterpret_cast<float4*>(vmax + i4) = vx;
     if (shadow != nullptr) {
       uint2 o;
       o.x = pack_bf16(P[0], P[1]);
@@ -53,8 +54,9 @@ adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* _
       const float gr = g[i] * grad_scale;
       m[i] = b1 * m[i] + (1.0f - b1) * gr;
       v[i] = b2 * v[i] + (1.0f - b2) * gr * gr;
-      vmax[i] = fmaxf(vmax[i], v[i]);
-      p[i] -= (lr / bc1) * m[i] / (sqrtf(vmax[i]) * rsqrt_bc2 + eps);
+      float vm = v[i];
+      if (vmax != nullptr) { vm = fmaxf(vmax[i], v[i]); vmax[i] = vm; }
+      p[i] -= (lr / bc1) * m[i] / (sqrtf(vm) * rsqrt_bc2 + eps);
       if (shadow != nullptr) shadow[i] = __float2bfloat16_rn(p[i]);
     }
   }
@@ -405,8 +407,7 @@ TNR_API int tnr_eval_metrics(const float* table, const float* user, const long l
   const int smem = (D + max_c) * 4 + ((max_c + 15) / 16) * 16;
   TNR_REQUIRE(smem <= 200 * 1024, "tnr_eval_metrics: max candidates %d too large", max_c);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (smem > 48 * 1024)
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(eval_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (smem > 48 * 1024) TNR_SET_SMEM(eval_metrics_kernel, smem);
   eval_metrics_kernel<<<(int)n_imp, EVAL_THREADS, smem, st>>>(table, user, ptr, cand, label, D, per_imp, score_out);
   TNR_LAUNCH_CHECK();
   if (sums != nullptr) {

@@ -334,11 +334,7 @@ TNR_API int tnr_nrms_attn_fwd(const float* q, const float* k, const float* v, co
   TNR_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)ctx) % 16 == 0, "tnr_nrms_attn_fwd: 16-byte alignment required");
   if (B == 0) return 0;
   const int smem = (NR_WARPS * 2 * NR_HMAX * NR_DK + NR_HMAX) * 4;
-  static bool attr = false;
-  if (!attr) {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(nrms_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  TNR_SET_SMEM(nrms_attn_fwd_kernel, smem);
   nrms_attn_fwd_kernel<<<B, NR_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(q, k, v, mask, ctx, H, n_heads);
   TNR_LAUNCH_CHECK();
   return 0;
@@ -351,11 +347,7 @@ TNR_API int tnr_nrms_attn_bwd(const float* q, const float* k, const float* v, co
               "tnr_nrms_attn_bwd: 16-byte alignment required");
   if (B == 0) return 0;
   const int smem = (NR_WARPS * (4 * NR_HMAX * NR_DK + 2 * NR_HMAX) + NR_HMAX) * 4;
-  static bool attr = false;
-  if (!attr) {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(nrms_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  TNR_SET_SMEM(nrms_attn_bwd_kernel, smem);
   nrms_attn_bwd_kernel<<<B, NR_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(q, k, v, mask, d_ctx, dq, dk, dv, H, n_heads);
   TNR_LAUNCH_CHECK();
   return 0;

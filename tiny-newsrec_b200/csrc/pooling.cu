@@ -260,11 +260,7 @@ template <int VPL>
 static int pool_fwd_launch(const void* x, const void* e, int ldq, int Q, const float* w2, const float* b2, const float* mask,
                            void* out, float* a_out, int n, int S, cudaStream_t st) {
   const int smem = PW_WARPS * (PW_RING * (VPL + 1) * 512 + POOL_SMAX * 4);
-  static bool attr = false;
-  if (!attr) {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(attnpool_fwd_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  TNR_SET_SMEM(attnpool_fwd_kernel<VPL>, smem);
   attnpool_fwd_kernel<VPL><<<(n + PW_WARPS - 1) / PW_WARPS, PW_THREADS, smem, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(e), ldq, Q, w2, b2, mask,
       reinterpret_cast<__nv_bfloat16*>(out), a_out, n, S);
@@ -276,11 +272,7 @@ template <int VPL>
 static int pool_bwd_launch(const void* x, const void* e, int ldq, int Q, const float* w2, const float* a_in, const float* dout,
                            void* dx, void* du, float* dw2, float* db2, int n, int S, cudaStream_t st) {
   const int smem = PW_WARPS * (PW_RING * VPL * 512 + 2 * POOL_SMAX * 4);
-  static bool attr = false;
-  if (!attr) {
-    TNR_CHECK_CUDA(cudaFuncSetAttribute(attnpool_bwd_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  TNR_SET_SMEM(attnpool_bwd_kernel<VPL>, smem);
   attnpool_bwd_kernel<VPL><<<(n + PW_WARPS - 1) / PW_WARPS, PW_THREADS, smem, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(e), ldq, Q, w2, a_in, dout,
       reinterpret_cast<__nv_bfloat16*>(dx), reinterpret_cast<__nv_bfloat16*>(du), dw2, db2, n, S);

@@ -42,6 +42,20 @@ class DropState:
     def make(self, site, p):
         return ops.make_drop(self.seed, site, p)
 
+    def offset(self, site_base):
+        """A view of this state whose tensor ids are shifted by ``site_base``: a second encoder pass of the same step
+        (the title pass after the body pass of the post-training models) draws masks independent of the first's, as
+        the reference's ``nn.Dropout`` does for every ``news_encoder`` call."""
+        return _DropView(self, site_base)
+
+
+class _DropView:
+    def __init__(self, state, site_base):
+        self.p_hidden, self.p_attn, self.seed, self.site_base = state.p_hidden, state.p_attn, state.seed, int(site_base)
+
+    def make(self, site, p):
+        return ops.make_drop(self.seed, site + self.site_base, p)
+
 
 def _align8(n):
     return (n + 7) // 8 * 8
@@ -178,6 +192,13 @@ class Encoder:
         self.F = self.layers[0].f1.weight.shape[0] if self.layers else 4 * self.E
         self.Q = news_encoder_module.attn.att_fc1.weight.shape[0]
         self.D = news_encoder_module.dense.weight.shape[0]
+        # numerics the reference reads from the bert config (tnlrv3/configuration_tnlrv3.py:61, modeling.py:458-461)
+        cfg = getattr(news_encoder_module, "bert_config", None) or {}
+        self.ln_eps = float(cfg.get("layer_norm_eps", LN_EPS))
+        self.rel_bins = int(cfg.get("rel_pos_bins", 32))
+        self.max_rel = int(cfg.get("max_rel_pos", 128))
+        if bert.rel_pos_bias.weight.shape[1] != self.rel_bins:
+            raise TinyRecError(f"rel_pos_bias has {bert.rel_pos_bias.weight.shape[1]} buckets, config says {self.rel_bins}")
         self.frozen = _Frozen()
         self.ws = {}
         self.scratch_ln = None
@@ -240,7 +261,7 @@ class Encoder:
         w = self.bert.rel_pos_bias.weight
 
         def build():
-            tab = rel_pos_bucket_table(L)                                   # [i, j] -> bucket(j - i)
+            tab = rel_pos_bucket_table(L, self.rel_bins, self.max_rel)                                 # [i, j] -> bucket(j - i)
             vec = torch.cat([tab[1:, 0].flip(0), tab[0, :]])                # d = -(L-1) .. L-1
             return w.detach().float()[:, vec.to(w.device)].contiguous()
         return self.frozen.get(("relpos", L), [w], build)
@@ -289,7 +310,7 @@ class Encoder:
         dmk = (lambda site, p: drop.make(site, p)) if drop is not None else (lambda site, p: None)
         ph, pa = (drop.p_hidden, drop.p_attn) if drop is not None else (0.0, 0.0)
         ops.embed_ln(x, L, self.word_table(), emb.position_embeddings.weight, emb.token_type_embeddings.weight[0],
-                     emb.LayerNorm.weight, emb.LayerNorm.bias, LN_EPS, cur, drop=dmk(SITE_EMB, ph))
+                     emb.LayerNorm.weight, emb.LayerNorm.bias, self.ln_eps, cur, drop=dmk(SITE_EMB, ph))
         for i, lr in enumerate(self.layers):
             wqkv, bqkv, wo, w1, w2 = self.layer_weights(flat, i)
             if i >= low:
@@ -302,11 +323,11 @@ class Encoder:
             ops.gemm(cur, wqkv, qkv, bias=bqkv)
             ops.attn_fwd(qkv, x, L, relpos, ctx, self.A, drop=dmk(drop_site(i, KIND_ATTN), pa))
             ops.gemm(ctx, wo, pre1, bias=lr.o.bias, residual=cur, drop=dmk(drop_site(i, KIND_ATT_OUT), ph))
-            ops.layernorm_fwd(pre1, lr.ln1.weight, lr.ln1.bias, LN_EPS, x1)
+            ops.layernorm_fwd(pre1, lr.ln1.weight, lr.ln1.bias, self.ln_eps, x1)
             # trained layers keep gelu'(z) (not z) for the backward: its dgrad epilogue is then a single multiply
             ops.gemm(x1, w1, h, bias=lr.f1.bias, act=ops.ACT_GELU_DAUX if z is not None else ops.ACT_GELU, aux=z)
             ops.gemm(h, w2, pre2, bias=lr.f2.bias, residual=x1, drop=dmk(drop_site(i, KIND_FFN_OUT), ph))
-            ops.layernorm_fwd(pre2, lr.ln2.weight, lr.ln2.bias, LN_EPS, xout)
+            ops.layernorm_fwd(pre2, lr.ln2.weight, lr.ln2.bias, self.ln_eps, xout)
             cur = xout
         at = self.mod.attn
         ops.gemm(cur, self._w(flat, at.att_fc1.weight), ws["e"], bias=at.att_fc1.bias, act=ops.ACT_TANH)
@@ -375,7 +396,7 @@ class Encoder:
             # dpre = grad at (dropout(dense) + residual); dd = grad at the dense output (mask re-applied)
             d2 = dmk(drop_site(i, KIND_FFN_OUT), ph)
             dd = ws["dpre_drop"] if d2 is not None else dpre
-            ops.layernorm_bwd(dx, sv["pre2"], lr.ln2.weight, LN_EPS, dpre, sg, sb,
+            ops.layernorm_bwd(dx, sv["pre2"], lr.ln2.weight, self.ln_eps, dpre, sg, sb,
                               dx_drop=dd if d2 is not None else None, drop=d2,
                               dsum=flat.g_view(lr.f2.bias) if train else None)       # + f2.bias gradient
             if train:
@@ -390,7 +411,7 @@ class Encoder:
             sg, sb = (flat.g_view(lr.ln1.weight), flat.g_view(lr.ln1.bias)) if train else (self.scratch_ln[:E], self.scratch_ln[E:])
             d1 = dmk(drop_site(i, KIND_ATT_OUT), ph)
             dd = ws["dpre_drop"] if d1 is not None else dpre
-            ops.layernorm_bwd(dx2, sv["pre1"], lr.ln1.weight, LN_EPS, dpre, sg, sb,
+            ops.layernorm_bwd(dx2, sv["pre1"], lr.ln1.weight, self.ln_eps, dpre, sg, sb,
                               dx_drop=dd if d1 is not None else None, drop=d1,
                               dsum=flat.g_view(lr.o.bias) if train else None)        # + attention.output.dense.bias gradient
             if train:

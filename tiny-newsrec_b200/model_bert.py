@@ -131,6 +131,19 @@ class NewsEncoder(nn.Module):
         self.pooling = args.pooling
         self.bert_config = load_bert_config(getattr(args, "config_name", None), num_hidden_layers=num_layers)
         self.bert_model = build_bert_model(self.bert_config, num_layers)
+        model_name = getattr(args, "model_name", None)
+        if model_name:
+            # model_bert.py:114 ``model_class.from_pretrained(args.model_name, config=...)``: the encoder starts from the
+            # UniLM / TNLRv3 ``.bin`` (layers beyond ``num_layers`` dropped, pooler / classifier keep their init).  A
+            # name that cannot be loaded is an error -- silently training a random-init encoder is not a drop-in.
+            import os
+            from . import checkpoint
+            if not os.path.isfile(model_name):
+                raise TinyRecError(f"args.model_name={model_name!r} is not a file: pass the UniLM/TNLRv3 .bin the reference "
+                                   "loads with from_pretrained, or model_name=None for a random-init encoder")
+            missing, _ = checkpoint.load_unilm_bin(self.bert_model, model_name,
+                                                   initializer_range=self.bert_config.get("initializer_range", 0.02))
+            self.pretrained_missing_keys = missing
         self.attn = AttentionPooling(self.bert_config["hidden_size"], args.news_query_vector_dim)
         self.dense = nn.Linear(self.bert_config["hidden_size"], args.news_dim)
         self._engine = None

@@ -499,7 +499,7 @@ def nrms_attn_bwd(qkv, mask, d_ctx, dqkv, B, H):
 @_timed
 def adam_amsgrad(p, g, m, v, vmax, shadow, lr, beta1, beta2, eps, step, grad_scale=1.0):
     lib = _ready(p)
-    for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v"), (vmax, "vmax")):
+    for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v")) + (((vmax, "vmax"),) if vmax is not None else ()):
         _chk(t, _f32, "adam." + nm)
     _lib.check(lib.tnr_adam_amsgrad(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(vmax), _ptr(shadow), p.numel(), lr, beta1,
                                     beta2, eps, step, grad_scale, _stream()), "tnr_adam_amsgrad")
@@ -509,7 +509,7 @@ def adam_amsgrad(p, g, m, v, vmax, shadow, lr, beta1, beta2, eps, step, grad_sca
 def adam_amsgrad_devstep(p, g, m, v, vmax, shadow, lr, beta1, beta2, eps, step_dev, bc_ws, grad_scale=1.0):
     """Adam(amsgrad) with the step counter on the device (int32 [1], incremented by the call): graph-capturable."""
     lib = _ready(p, 2)
-    for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v"), (vmax, "vmax"), (bc_ws, "bc_ws")):
+    for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v"), (bc_ws, "bc_ws")) + (((vmax, "vmax"),) if vmax is not None else ()):
         _chk(t, _f32, "adam." + nm)
     _chk(step_dev, torch.int32, "adam.step_dev")
     _lib.check(lib.tnr_adam_amsgrad_devstep(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(vmax), _ptr(shadow), p.numel(), lr, beta1,

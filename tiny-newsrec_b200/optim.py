@@ -16,8 +16,7 @@ class Adam:
     (fp32 master weights, m, v, vmax) that also refreshes the bf16 shadow weights the GEMMs read."""
 
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, amsgrad=True, capturable=False):
-        if not amsgrad:
-            raise TinyRecError("only amsgrad=True is implemented (what run.py:134 uses)")
+        self.amsgrad = bool(amsgrad)          # False: torch's default Adam (Post-train_KD.ipynb cell 18); True: run.py:134
         self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
         self.step_count = 0
         self.m = self.v = self.vmax = None
@@ -49,7 +48,7 @@ class Adam:
         if self.m is None or self.m.numel() != flat.numel or self.m.device != flat.data.device:
             self.m = torch.zeros_like(flat.data)
             self.v = torch.zeros_like(flat.data)
-            self.vmax = torch.zeros_like(flat.data)
+            self.vmax = torch.zeros_like(flat.data) if self.amsgrad else None
         if self.capturable and self.step_dev is None:
             self.step_dev = torch.tensor([self.step_count], device=flat.data.device, dtype=torch.int32)
             self.bc_ws = torch.zeros(2, device=flat.data.device, dtype=torch.float32)
@@ -71,7 +70,8 @@ class Adam:
             self.step_count += 1
             for lo, hi, lr in ranges:
                 if hi > lo:
-                    ops.adam_amsgrad(flat.data[lo:hi], flat.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], self.vmax[lo:hi],
+                    ops.adam_amsgrad(flat.data[lo:hi], flat.grad[lo:hi], self.m[lo:hi], self.v[lo:hi],
+                                     self.vmax[lo:hi] if self.vmax is not None else None,
                                      flat.shadow[lo:hi], lr, self.betas[0], self.betas[1], self.eps, self.step_count,
                                      self.grad_scale)
             return

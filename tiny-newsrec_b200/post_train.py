@@ -36,6 +36,9 @@ def _encoder_args(args):
                            news_dim=args.news_dim)
 
 
+TITLE_SITE_BASE = 1 << 12          # dropout tensor-id offset of the title pass (encoder ids stay below 8 * 26)
+
+
 class TitleBodySimModel(nn.Module):
     """Post-train_KD.ipynb cell 12 (inference semantics here; training goes through ``DistillModel``)."""
 
@@ -113,7 +116,10 @@ class _DistillState:
             drop.advance()
         body_emb = self.enc.forward(body, flat, save=want_grad, out=w["user"], drop=drop, tag="body")
         w["ws_body"] = self.enc.last_ws
-        title_emb = self.enc.forward(title.reshape(R, Wt), flat, save=want_grad, out=w["news"], drop=drop, tag="title")
+        # the title pass draws masks from its own Philox streams (tensor ids shifted): nn.Dropout in the reference is
+        # independent between the two news_encoder calls of a step
+        title_emb = self.enc.forward(title.reshape(R, Wt), flat, save=want_grad, out=w["news"],
+                                     drop=drop.offset(TITLE_SITE_BASE) if drop is not None else None, tag="title")
         w["ws_title"] = self.enc.last_ws
         T, TP, G = w["T"], w["TP"], w["G"]
         for i in range(M):

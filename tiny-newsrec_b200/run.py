@@ -75,53 +75,127 @@ def accuracy(y_true, y_hat):
     return (y_true == y_hat.argmax(dim=-1)).sum().float() / y_true.shape[0]
 
 
+class _PinnedRing:
+    """``depth`` slots of pinned host staging tensors: ``push(arrays)`` copies one batch of numpy arrays into the next
+    slot and starts its host->device copies (``non_blocking``, on the current stream); a slot is reused only after
+    the copies issued from it have completed (an event per slot), so the host can run ``depth - 1`` batches ahead
+    of the device -- the job of the reference loader's producer thread (dataloader.py:85-116).  Without CUDA
+    (``device='cpu'``: the host-logic tests) the arrays are passed through as tensors."""
+
+    def __init__(self, device, depth=3):
+        self.device = torch.device(device)
+        self.depth, self.slots, self.k = depth, [], 0
+
+    def push(self, arrays):
+        if self.device.type != "cuda":
+            return tuple(torch.from_numpy(np.ascontiguousarray(a)) for a in arrays)
+        i_slot = self.k % self.depth
+        self.k += 1
+        if len(self.slots) <= i_slot:
+            self.slots.append(dict(bufs=[None] * len(arrays), ev=None))
+        slot = self.slots[i_slot]
+        if slot["ev"] is not None:
+            slot["ev"].synchronize()
+        out = []
+        for i, a in enumerate(arrays):
+            a = np.asarray(a)
+            buf = slot["bufs"][i]
+            if buf is None or buf.dtype != torch.from_numpy(a[:0].reshape(-1)).dtype or buf.numel() < a.size:
+                buf = slot["bufs"][i] = torch.empty(max(a.size, 1), dtype=torch.from_numpy(a[:0].reshape(-1)).dtype,
+                                                    pin_memory=True)
+            view = buf[:a.size].view(a.shape)
+            np.copyto(view.numpy(), a)
+            out.append(view.to(self.device, non_blocking=True))
+        slot["ev"] = torch.cuda.Event()
+        slot["ev"].record()
+        return tuple(out)
+
+
 class IndexBatches:
-    """Iterator of pre-parsed training impressions -> device index tensors.
-    ``hist_idx`` int32 [n,H], ``hist_mask`` f32 [n,H], ``cand_idx`` int32 [n,K], ``label`` int64 [n];
-    rank r takes batches r, r+world, ... (impression sharding, streaming.py:53-54)."""
+    """Re-iterable source of pre-parsed training impressions -> device index tensors (one pass per epoch).
+    ``hist_idx`` int32 [n,H], ``hist_mask`` f32 [n,H], ``cand_idx`` int32 [n,K], ``label`` int64 [n].
+    Rank r takes batches r, r+world, ... (impression sharding, streaming.py:53-54) of the first
+    ``(n_batches // world) * world`` batches: every rank runs the SAME number of optimizer steps, so the per-step
+    gradient all-reduces of the ranks always pair up (a ragged tail would hang NCCL)."""
 
     def __init__(self, hist_idx, hist_mask, cand_idx, label, batch_size, rank=0, world=1, device="cuda"):
         self.arr = (hist_idx, hist_mask, cand_idx, label)
         self.bs, self.rank, self.world, self.device = batch_size, rank, world, device
+        self.ring = _PinnedRing(device)
+
+    def __len__(self):
+        return (self.arr[0].shape[0] // self.bs) // self.world
 
     def __iter__(self):
-        n = self.arr[0].shape[0] // self.bs
-        for b in range(self.rank, n, self.world):
+        for i in range(len(self)):
+            b = i * self.world + self.rank
             sl = slice(b * self.bs, (b + 1) * self.bs)
-            yield tuple(torch.from_numpy(np.ascontiguousarray(a[sl])).to(self.device, non_blocking=True) for a in self.arr)
+            yield self.ring.push([a[sl] for a in self.arr])
+
+
+class LineBatches:
+    """Re-iterable source that parses ``behaviors_np{K}_*.tsv`` lines (dataloader.py:118-148) into index batches.
+    ``lines``: a sequence of lines, or a zero-argument callable returning one (called once per epoch -- e.g. a
+    shuffled re-read of the rank's files).  Rank r parses lines r, r+world, ... (streaming.py:53-54 applied to lines)
+    and every rank stops after ``len(lines) // (world * batch_size)`` batches (equal step counts, see IndexBatches).
+    The positive's slot ``label = randint(0, npratio)`` (dataloader.py:135) is drawn from ``Random(seed + epoch)``."""
+
+    def __init__(self, lines, news_index, args, rank=0, world=1, device="cuda", seed=0):
+        self.lines, self.news_index, self.args = lines, news_index, args
+        self.rank, self.world, self.device, self.seed = rank, world, device, seed
+        self.epoch = 0
+        self.ring = _PinnedRing(device)
+
+    def _materialise(self):
+        lines = self.lines() if callable(self.lines) else self.lines
+        return lines if hasattr(lines, "__len__") and hasattr(lines, "__getitem__") else list(lines)
+
+    def __iter__(self):
+        a = self.args
+        H, K, bs = a.user_log_length, a.npratio + 1, a.batch_size
+        lines = self._materialise()
+        rng = random.Random(self.seed + self.epoch)
+        self.epoch += 1
+        n_batches = len(lines) // (self.world * bs)
+        for b in range(n_batches):
+            rows = [dl.parse_train_line(lines[(b * bs + j) * self.world + self.rank], self.news_index, H, a.npratio, rng)
+                    for j in range(bs)]
+            hist = np.array([r[0] for r in rows], dtype=np.int32)
+            mask = np.array([r[1] for r in rows], dtype=np.float32)
+            cand = np.array([r[2] for r in rows], dtype=np.int32).reshape(bs, K)
+            lab = np.array([r[3] for r in rows], dtype=np.int64)
+            yield self.ring.push([hist, mask, cand, lab])
 
 
 def batches_from_lines(lines, news_index, args, rank=0, world=1, device="cuda", seed=0):
-    """Parse ``behaviors_np{K}_*.tsv`` lines (dataloader.py:118-148) into index batches."""
-    rng = random.Random(seed)
-    H, K = args.user_log_length, args.npratio + 1
-    buf = []
-    for line in lines:
-        buf.append(dl.parse_train_line(line, news_index, H, args.npratio, rng))
-        if len(buf) == args.batch_size:
-            hist = np.array([b[0] for b in buf], dtype=np.int32)
-            mask = np.array([b[1] for b in buf], dtype=np.float32)
-            cand = np.array([b[2] for b in buf], dtype=np.int32).reshape(len(buf), K)
-            lab = np.array([b[3] for b in buf], dtype=np.int64)
-            buf = []
-            yield tuple(torch.from_numpy(a).to(device, non_blocking=True) for a in (hist, mask, cand, lab))
+    """Kept name: returns the re-iterable ``LineBatches`` (sharded by rank, one pass per epoch)."""
+    return LineBatches(lines, news_index, args, rank, world, device, seed)
 
 
 class GraphedTrainStep:
-    """The body of the reference train loop (run.py:178-197: forward, zero_grad, backward, optimizer step) captured
-    ONCE into a CUDA graph and replayed per batch: the ~100 kernel launches and ~40 small torch ops of a step become
-    one graph launch (no launch gaps, no Python between kernels).  Inputs are copied into static device buffers;
-    the dropout seed and the Adam step counter live on the device and advance inside the graph, so every replay
-    is a new step.  Warm-up steps needed before the capture run on a snapshot that is restored afterwards:
+    """The body of the reference train loop (run.py:178-197: forward, acc, zero_grad, backward, optimizer step)
+    captured ONCE into a CUDA graph and replayed per batch: the ~100 kernel launches and ~40 small torch ops of a
+    step become one graph launch (no launch gaps, no Python between kernels).  Inputs are copied into static device
+    buffers; the dropout seed and the Adam step counter live on the device and advance inside the graph, so every
+    replay is a new step.  Warm-up steps needed before the capture run on a snapshot that is restored afterwards:
     constructing this object does not train the model.
 
         step = GraphedTrainStep(model, optimizer, first_batch)
         total, distill, emb, target, score = step(history, mask, candidate, label, th_list, tc_list)
 
-    The returned tensors are static outputs overwritten by the next call."""
+    With ``batcher`` (a ``tinyrec.dataloader.TrainBatcher``) the batch is the four INDEX tensors of the loader
+    (hist_idx int32 [B,H], hist_mask f32 [B,H], cand_idx int32 [B,K], label int64 [B]) and the row gathers that
+    assemble the model inputs from the device-resident tables (dataloader.py:129-144) run inside the graph: only
+    ~7 KB of indices cross PCIe per step.
 
-    def __init__(self, model, optimizer, batch, warmup=3):
-        self.model, self.opt = model, optimizer
+        step = GraphedTrainStep(model, optimizer, (hist_idx, hist_mask, cand_idx, label), batcher=batcher)
+        total, distill, emb, target, score = step(hist_idx, hist_mask, cand_idx, label)
+
+    ``step.stats`` (fp32 [3] on the device) accumulates [sum of total_loss, sum of utils.acc, steps] inside the
+    graph (run.py:180-182); the returned tensors are static outputs overwritten by the next call."""
+
+    def __init__(self, model, optimizer, batch, warmup=3, batcher=None):
+        self.model, self.opt, self.batcher = model, optimizer, batcher
         inner = getattr(optimizer, "opt", optimizer)
         inner.make_capturable()
         self.static = self._clone(batch)
@@ -129,8 +203,10 @@ class GraphedTrainStep:
         inner.ensure_state()
         ne = model.student.news_encoder if hasattr(model, "student") else model.news_encoder
         drop = ne.drop_state(st.flat.data.device)
+        self.stats = torch.zeros(3, device=st.flat.data.device, dtype=torch.float32)
         snap = dict(data=st.flat.data.clone(), grad=st.flat.grad.clone(), m=inner.m.clone(), v=inner.v.clone(),
-                    vmax=inner.vmax.clone(), step=inner.step_dev.clone(), seed=drop.seed.clone())
+                    vmax=inner.vmax.clone() if inner.vmax is not None else None, step=inner.step_dev.clone(),
+                    seed=drop.seed.clone())
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -150,9 +226,11 @@ class GraphedTrainStep:
         st.flat.refresh_shadow()
         inner.m.copy_(snap["m"])
         inner.v.copy_(snap["v"])
-        inner.vmax.copy_(snap["vmax"])
+        if inner.vmax is not None:
+            inner.vmax.copy_(snap["vmax"])
         inner.step_dev.copy_(snap["step"])
         drop.seed.copy_(snap["seed"])
+        self.stats.zero_()
         torch.cuda.synchronize()
 
     def close(self):
@@ -164,40 +242,75 @@ class GraphedTrainStep:
 
     @staticmethod
     def _clone(batch):
-        h, m, c, l, th, tc = batch
         dev = lambda t: t.detach().to("cuda", copy=True) if not t.is_cuda else t.detach().clone()  # noqa: E731
-        return (dev(h), dev(m), dev(c), dev(l), [dev(t) for t in th], [dev(t) for t in tc])
+        return tuple([dev(t) for t in x] if isinstance(x, (list, tuple)) else dev(x) for x in batch)
 
     def _eager(self, batch):
+        if self.batcher is not None:
+            hist_idx, hist_mask, cand_idx, label = batch
+            history, candidate, th, tc = self.batcher.assemble(hist_idx, cand_idx)
+            batch = (history, hist_mask, candidate, label, th, tc)
         self.opt.zero_grad()
         out = self.model(*batch)
         out[0].backward()
         self.opt.step()
-        return tuple(o.detach() for o in out)
+        out = tuple(o.detach() for o in out)
+        self.stats[0] += out[0]
+        self.stats[1] += accuracy(batch[3], out[4])
+        self.stats[2] += 1.0
+        return out
 
-    def __call__(self, history, history_mask, candidate, label, teacher_history_embs, teacher_candidate_embs):
-        s = self.static
-        s[0].copy_(history, non_blocking=True)
-        s[1].copy_(history_mask, non_blocking=True)
-        s[2].copy_(candidate, non_blocking=True)
-        s[3].copy_(label, non_blocking=True)
-        for d, t in zip(s[4], teacher_history_embs):
-            d.copy_(t, non_blocking=True)
-        for d, t in zip(s[5], teacher_candidate_embs):
-            d.copy_(t, non_blocking=True)
+    def __call__(self, *batch):
+        if len(batch) != len(self.static):
+            raise TypeError(f"GraphedTrainStep takes {len(self.static)} inputs, got {len(batch)}")
+        for dst, src in zip(self.static, batch):
+            if isinstance(dst, list):
+                for d, t in zip(dst, src):
+                    d.copy_(t, non_blocking=True)
+            else:
+                dst.copy_(src, non_blocking=True)
         self.graph.replay()
         ops.bump_param_generation()          # the replay stepped the optimizer: cached parameter copies are stale
         return self.out
 
 
+def build_kd_model(args):
+    """run.py:54-88, :118-122: ``Model(args)`` (student encoder from ``args.model_name`` when set), the teachers'
+    user encoders from ``args.teacher_ckpts``, the first-stage student from ``args.pretrain_model_path`` when
+    ``args.use_pretrain_model``, then the whole model from ``model_dir/load_ckpt_name`` when given."""
+    model = Model(args)
+    tsds = []
+    for path in (getattr(args, "teacher_ckpts", None) or []):
+        tsds.append(torch.load(path, map_location="cpu")["model_state_dict"])
+    loaded = load_teacher_user_encoders(model, tsds)
+    if getattr(args, "use_pretrain_model", False):
+        sd = torch.load(args.pretrain_model_path, map_location="cpu")["model_state_dict"]
+        loaded += load_student_from_first_stage(model, sd)
+    logging.info(f"{len(loaded)} loaded parameters, {len(model.state_dict()) - len(loaded)} initialized parameters")
+    if getattr(args, "load_ckpt_name", None) is not None:
+        path = os.path.join(args.model_dir, args.load_ckpt_name)                       # utils.get_checkpoint
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        ckpt.load_checkpoint(path, model)
+        logging.info(f"Model loaded from {path}")
+    return model
+
+
 def train(args, news_combined, teacher_embs, batches, model=None, category_dict=None, subcategory_dict=None,
-          word_dict=None):
-    """run.py:20-216.  ``batches`` yields (hist_idx, hist_mask, cand_idx, label) device tensors
-    (see IndexBatches / batches_from_lines).  Returns the trained model."""
+          word_dict=None, use_graph=True, history=None):
+    """run.py:20-216.  ``batches``: a RE-ITERABLE source of (hist_idx, hist_mask, cand_idx, label) device tensors,
+    iterated once per epoch (``IndexBatches`` / ``LineBatches``; both give every rank the same number of steps).
+    ``teacher_embs``: the M [N+1, D] tables, or None to unpickle ``args.teacher_emb_paths`` (run.py:72-73).
+    ``model`` None builds it the way run.py:54-122 does (``build_kd_model``).  Full batches run as one replayed CUDA
+    graph each (``GraphedTrainStep`` with the loader's row gathers inside); ``use_graph=False`` or an odd-sized batch
+    launches the same kernels eagerly.  ``history``: optional list; per step a dict of the five outputs' scalars and
+    ``acc`` (device tensors) is appended.  Returns the trained model."""
     world, rank, local = par.init_distributed(getattr(args, "enable_hvd", True))
     device = torch.device("cuda", local)
     if model is None:
-        model = Model(args)
+        model = build_kd_model(args)
+    if teacher_embs is None:
+        teacher_embs = [ckpt.load_teacher_table(p) for p in args.teacher_emb_paths]
     model = model.to(device)
     apply_freeze_policy(model, list(args.bert_trainable_layer))
     optimizer = Adam(model, lr=args.lr, amsgrad=True)                       # run.py:134
@@ -207,29 +320,56 @@ def train(args, news_combined, teacher_embs, batches, model=None, category_dict=
     tables = dl.DeviceTables(news_combined, teacher_embs, device)
     K = args.npratio + 1
     batcher = dl.TrainBatcher(tables, args.batch_size, args.user_log_length, K)
+    stats = torch.zeros(3, device=device, dtype=torch.float32)             # [LOSS, ACC, steps] of the epoch's eager steps
+    gstep = None
     logging.info("Training...")
-    for ep in range(getattr(args, "start_epoch", 0), args.epochs):
-        loss_sum = torch.zeros((), device=device)
-        acc_sum = torch.zeros((), device=device)
-        cnt = -1
-        for cnt, (hist_idx, hist_mask, cand_idx, label) in enumerate(batches):
-            if cnt > args.max_steps_per_epoch:                              # run.py:176 (runs max+1 steps)
-                break
-            history, candidate, th, tc = batcher.assemble(hist_idx, cand_idx)
-            total, distill, emb, target, y = model(history, hist_mask, candidate, label, th, tc)
-            loss_sum += total.detach()
-            acc_sum += accuracy(label, y.detach())
-            optimizer.zero_grad()
-            total.backward()
-            optimizer.step()
-            if cnt % args.log_steps == 0 and cnt > 0:
-                logging.info("[{}] Ed: {}, train_loss: {:.5f}, acc: {:.5f}".format(
-                    rank, cnt * args.batch_size, float(loss_sum) / cnt, float(acc_sum) / cnt))
-        if rank == 0 and getattr(args, "model_dir", None):
-            os.makedirs(args.model_dir, exist_ok=True)
-            ckpt_path = os.path.join(args.model_dir, f"epoch-{ep + 1}.pt")
-            ckpt.save_checkpoint(ckpt_path, model, category_dict, word_dict, subcategory_dict)       # run.py:205-214
-            logging.info(f"Model saved to {ckpt_path}")
+    try:
+        for ep in range(getattr(args, "start_epoch", 0), args.epochs):
+            stats.zero_()
+            if gstep is not None:
+                gstep.stats.zero_()
+            n_steps = 0
+            for cnt, (hist_idx, hist_mask, cand_idx, label) in enumerate(batches):
+                if cnt > args.max_steps_per_epoch:                              # run.py:176 (runs max+1 steps)
+                    break
+                if use_graph and hist_idx.shape[0] == args.batch_size:
+                    if gstep is None:
+                        gstep = GraphedTrainStep(model, optimizer, (hist_idx, hist_mask, cand_idx, label), batcher=batcher)
+                    out = gstep(hist_idx, hist_mask, cand_idx, label)
+                    acc = None
+                else:
+                    history_t, candidate, th, tc = batcher.assemble(hist_idx, cand_idx) if hist_idx.shape[0] == args.batch_size \
+                        else dl.TrainBatcher(tables, hist_idx.shape[0], args.user_log_length, K).assemble(hist_idx, cand_idx)
+                    out = model(history_t, hist_mask, candidate, label, th, tc)
+                    acc = accuracy(label, out[4].detach())
+                    stats[0] += out[0].detach()
+                    stats[1] += acc
+                    stats[2] += 1.0
+                    optimizer.zero_grad()
+                    out[0].backward()
+                    optimizer.step()
+                n_steps += 1
+                if history is not None:
+                    if acc is None:
+                        acc = accuracy(label, out[4].detach())
+                    history.append(dict(epoch=ep, step=cnt, total=out[0].detach().clone(), distill=out[1].detach().clone(),
+                                        emb=out[2].detach().clone(), target=out[3].detach().clone(), acc=acc.clone(),
+                                        score=out[4].detach().clone()))
+                if cnt % args.log_steps == 0 and cnt > 0:
+                    loss_sum, acc_sum, _ = (stats + gstep.stats if gstep is not None else stats).tolist()
+                    logging.info("[{}] Ed: {}, train_loss: {:.5f}, acc: {:.5f}".format(
+                        rank, cnt * args.batch_size, loss_sum / cnt, acc_sum / cnt))
+            if n_steps == 0:
+                raise ValueError(f"epoch {ep + 1} produced no training steps: `batches` must be re-iterable and hold at "
+                                 "least world x batch_size impressions")
+            if rank == 0 and getattr(args, "model_dir", None):
+                os.makedirs(args.model_dir, exist_ok=True)
+                ckpt_path = os.path.join(args.model_dir, f"epoch-{ep + 1}.pt")
+                ckpt.save_checkpoint(ckpt_path, model, category_dict, word_dict, subcategory_dict)       # run.py:205-214
+                logging.info(f"Model saved to {ckpt_path}")
+    finally:
+        if gstep is not None:
+            gstep.close()
     return model
 
 
@@ -260,50 +400,82 @@ def evaluate(user_encoder, news_scoring, hist_idx, hist_mask, cand_ptr, cand_idx
     total impression count)."""
     device = news_scoring.device
     n = hist_idx.shape[0]
+    H = hist_idx.shape[1]
     world, rank = par.world_size(), par.get_rank()
     lo, hi = par.shard_rows(n, rank, world)
     sums = torch.zeros(5, device=device, dtype=torch.float64)
     per_all = []
     ptr_h = np.asarray(cand_ptr)
-    # Index batches go host -> pinned staging -> device on a copy stream, one batch ahead of the scoring kernels
-    # (the reference's loader thread did the same job with blocking copies, dataloader.py:303-314); nothing is read
-    # back until the final reduction.
+    hist_idx, hist_mask = np.asarray(hist_idx), np.asarray(hist_mask)
+    cand_idx, labels = np.asarray(cand_idx), np.asarray(labels)
+    # Index batches go host -> pinned staging -> device on a copy stream, ahead of the scoring kernels: staging
+    # threads (numpy copies release the GIL) fill pinned slots and issue the H2D copies while the main thread launches
+    # kernels -- the job of the reference's loader thread (dataloader.py:303-314), which used blocking copies.  Nothing
+    # is read back until the final reduction.  The slots (pinned + device buffers sized for the largest batch of this
+    # shard) are allocated ONCE: cudaHostAlloc per batch was what the round-1 loop spent its time in.
+    starts = np.arange(lo, hi, batch_size, dtype=np.int64)
+    ends = np.minimum(starts + batch_size, hi)
+    nb_total = len(starts)
+    nnz_max = int((ptr_h[ends] - ptr_h[starts]).max()) if nb_total else 0
+    counts = np.diff(ptr_h[lo:hi + 1])
+    max_cs = np.maximum.reduceat(counts, starts - lo) if nb_total else np.zeros(0, dtype=np.int64)
+    bs = int((ends - starts).max()) if nb_total else 0
     copy_stream = torch.cuda.Stream(device=device)
     main = torch.cuda.current_stream(device)
+    specs = ((bs * H, torch.int32), (bs * H, torch.float32), (bs + 1, torch.int64), (nnz_max, torch.int32),
+             (nnz_max, torch.int8))
+    n_slots = min(4, max(1, nb_total))
+    slots = [dict(pin=[torch.empty(max(m, 1), dtype=dt, pin_memory=True) for m, dt in specs],
+                  dev=[torch.empty(max(m, 1), dtype=dt, device=device) for m, dt in specs], done=None)
+             for _ in range(n_slots)]
+    per_buf = torch.empty(max(bs, 1), 5, device=device, dtype=torch.float64)
 
-    def stage(s):
-        e = min(hi, s + batch_size)
+    def stage(k):
+        torch.cuda.set_device(device)
+        s, e = int(starts[k]), int(ends[k])
         p0, p1 = int(ptr_h[s]), int(ptr_h[e])
-        host = (np.ascontiguousarray(hist_idx[s:e]), np.ascontiguousarray(hist_mask[s:e]),
-                np.ascontiguousarray(ptr_h[s:e + 1] - p0), np.ascontiguousarray(cand_idx[p0:p1]),
-                np.ascontiguousarray(labels[p0:p1]))
-        max_c = int(np.diff(host[2]).max()) if e > s else 0
+        slot = slots[k % n_slots]
+        if slot["done"] is not None:
+            slot["done"].synchronize()                   # the kernels that read this slot's device buffers have finished
+        nb, nz = e - s, p1 - p0
+        pin = slot["pin"]
+        np.copyto(pin[0][:nb * H].view(nb, H).numpy(), hist_idx[s:e])
+        np.copyto(pin[1][:nb * H].view(nb, H).numpy(), hist_mask[s:e])
+        np.subtract(ptr_h[s:e + 1], p0, out=pin[2][:nb + 1].numpy())
+        np.copyto(pin[3][:nz].numpy(), cand_idx[p0:p1])
+        np.copyto(pin[4][:nz].numpy(), labels[p0:p1])
+        sizes = (nb * H, nb * H, nb + 1, nz, nz)
         with torch.cuda.stream(copy_stream):
-            pinned = [torch.from_numpy(a).pin_memory() for a in host]
-            dev = [t.to(device, non_blocking=True) for t in pinned]
+            for d, p_, m in zip(slot["dev"], pin, sizes):
+                d[:m].copy_(p_[:m], non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(copy_stream)
-        return dict(e=e, dev=dev, pinned=pinned, max_c=max_c, ready=ready)
+        d = slot["dev"]
+        return dict(nb=nb, slot=slot, max_c=int(max_cs[k]), ready=ready,
+                    dev=(d[0][:nb * H].view(nb, H), d[1][:nb * H].view(nb, H), d[2][:nb + 1], d[3][:nz], d[4][:nz]))
 
-    nxt = stage(lo) if hi > lo else None
-    s = lo
-    while nxt is not None:
-        cur = nxt
-        e = cur["e"]
-        nxt = stage(e) if e < hi else None                       # next batch's copies overlap this batch's kernels
-        main.wait_event(cur["ready"])
-        hi_t, hm_t, ptr_t, cand_t, lab_t = cur["dev"]
-        for t in cur["dev"]:
-            t.record_stream(main)
-        if hasattr(user_encoder, "forward_gather"):      # news_scoring[log_ids] (dataloader.py:295) fused into the kernel
-            user = user_encoder.forward_gather(news_scoring, hi_t, hm_t)
-        else:
-            user = user_encoder(dl.gather_history_vecs(news_scoring, hi_t), hm_t)
-        per = torch.zeros(e - s, 5, device=device, dtype=torch.float64)
-        ops.eval_metrics(news_scoring, user, ptr_t, cand_t, lab_t, cur["max_c"], per, sums)
-        if return_per_impression:
-            per_all.append(per)
-        s = e
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, n_slots - 1)) as pool:
+        futs = {k: pool.submit(stage, k) for k in range(min(n_slots - 1, nb_total))} if n_slots > 1 else {}
+        for k in range(nb_total):
+            cur = futs.pop(k).result() if k in futs else stage(k)
+            main.wait_event(cur["ready"])
+            hi_t, hm_t, ptr_t, cand_t, lab_t = cur["dev"]
+            if hasattr(user_encoder, "forward_gather"):  # news_scoring[log_ids] (dataloader.py:295) fused into the kernel
+                user = user_encoder.forward_gather(news_scoring, hi_t, hm_t)
+            else:
+                user = user_encoder(dl.gather_history_vecs(news_scoring, hi_t), hm_t)
+            per = torch.empty(cur["nb"], 5, device=device, dtype=torch.float64) if return_per_impression \
+                else per_buf[:cur["nb"]]
+            ops.eval_metrics(news_scoring, user, ptr_t, cand_t, lab_t, cur["max_c"], per, sums)
+            done = torch.cuda.Event()
+            done.record(main)
+            cur["slot"]["done"] = done
+            if return_per_impression:
+                per_all.append(per)
+            nk = k + n_slots - 1                        # its slot was last read by batch k - 1
+            if n_slots > 1 and nk < nb_total:
+                futs[nk] = pool.submit(stage, nk)
     mean, total = par.reduce_eval_sums(hi - lo, sums[:4])
     if return_per_impression:
         return mean, total, torch.cat(per_all) if per_all else torch.zeros(0, 5, dtype=torch.float64)
@@ -324,9 +496,35 @@ def doc_sim(news_scoring, n_pairs=1000000, rng=random):
     return float(total.item()) / n_pairs
 
 
+def latest_checkpoint(directory):
+    """utils.py:127-137: the ``epoch-{n}.pt`` with the largest n, or None."""
+    if not directory or not os.path.exists(directory):
+        return None
+    found = {}
+    for x in os.listdir(directory):
+        try:
+            found[int(x.split(".")[-2].split("-")[-1])] = x
+        except (ValueError, IndexError):
+            continue
+    return os.path.join(directory, found[max(found)]) if found else None
+
+
 def test(args, model, news_combined, hist_idx, hist_mask, cand_ptr, cand_idx, labels):
-    """run.py:219-379: student news table, then impression scoring with user_log_mask as in args."""
+    """run.py:219-379: student news table, doc-sim diagnostic, then impression scoring with ``user_log_mask`` as in
+    args.  ``model`` None: ``Model(args)`` loaded from ``model_dir/load_ckpt_name`` or the latest ``epoch-{n}.pt``
+    (run.py:226-243) and broadcast from rank 0."""
     world, rank, local = par.init_distributed(getattr(args, "enable_hvd", True))
+    if model is None:
+        name = getattr(args, "load_ckpt_name", None)
+        path = os.path.join(args.model_dir, name) if name is not None else latest_checkpoint(args.model_dir)
+        if path is None or not os.path.exists(path):
+            raise FileNotFoundError("No ckpt found")                                            # run.py:231
+        model = Model(args)
+        ckpt.load_checkpoint(path, model)
+        logging.info(f"Model loaded from {path}")
+        model = model.to(torch.device("cuda", local))
+        if world > 1:
+            broadcast_parameters(model, root_rank=0)                                            # run.py:246-247
     model.eval()
     news_scoring = build_news_table(model.student.news_encoder, news_combined, batch_size=args.batch_size * 16)
     logging.info("news scoring num: {}".format(news_scoring.shape[0]))
@@ -339,10 +537,16 @@ def test(args, model, news_combined, hist_idx, hist_mask, cand_ptr, cand_idx, la
 
 
 def get_teacher_emb(args, teacher_state_dicts, news_combined, out_paths=None):
-    """run.py:382-460: one [N+1, D] float32 table per teacher checkpoint, pickled like the reference."""
+    """run.py:382-460: one [N+1, D] float32 table per teacher checkpoint, pickled like the reference.
+    ``teacher_state_dicts`` None: the ``model_state_dict`` of every file in ``args.teacher_ckpts`` (run.py:419-421);
+    ``out_paths`` None with ``args.teacher_emb_paths`` set: those paths (run.py:458-459)."""
     from .model_bert_2 import ModelBert
     world, rank, local = par.init_distributed(getattr(args, "enable_hvd", True))
     device = torch.device("cuda", local)
+    if teacher_state_dicts is None:
+        teacher_state_dicts = [torch.load(p_, map_location="cpu")["model_state_dict"] for p_ in args.teacher_ckpts]
+        if out_paths is None:
+            out_paths = getattr(args, "teacher_emb_paths", None)
     tables = []
     for i, tsd in enumerate(teacher_state_dicts):
         model = ModelBert(args)
@@ -352,6 +556,8 @@ def get_teacher_emb(args, teacher_state_dicts, news_combined, out_paths=None):
         table = build_news_table(model.news_encoder, news_combined, batch_size=args.batch_size * 64)
         arr = table.cpu().numpy()
         logging.info("news scoring num: {}".format(arr.shape[0]))
+        if rank == 0 and getattr(args, "doc_sim", False):
+            print(f"=== doc-sim: {doc_sim(table, getattr(args, 'doc_sim_pairs', 1000000))} ===")      # run.py:449-456
         if out_paths is not None and rank == 0:
             ckpt.save_teacher_table(out_paths[i], arr)                                          # run.py:458-459
             logging.info(f"teacher embedding saved at {out_paths[i]}")

@@ -31,9 +31,10 @@ def main():
     wl = bench.WORKLOADS[a.workload]
     model, _ = bench.make_model(wl["layers"], wl["trainable"], dev)
     opt = topt.Adam(model, lr=1e-4)
-    dev_batches, _ = bench.make_inputs(0, dev)
+    batcher, dev_batches, _ = bench.make_inputs(0, dev)
 
-    def step(b):
+    def step(idx_batch):
+        b = bench.assembled(batcher, idx_batch)
         opt.zero_grad()
         out = model(*b)
         out[0].backward()
