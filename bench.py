@@ -312,6 +312,8 @@ def run_tinyrec(a):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        import tinyrec.parallel as par
+        par.nccl_defaults()                                       # NCCL_MAX_CTAS: see tinyrec.optim.DistributedOptimizer
         dist.init_process_group("nccl", device_id=device)
     wl = WORKLOADS[a.workload]
     model, margs = make_model(wl["layers"], wl["trainable"], device)
@@ -506,6 +508,8 @@ def _dist_setup(a):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        import tinyrec.parallel as par
+        par.nccl_defaults()
         dist.init_process_group("nccl", device_id=device)
     return rank, world, local, device
 

@@ -29,12 +29,17 @@
 extern "C" {
 #endif
 
-#define TNR_ABI_VERSION 5
+#define TNR_ABI_VERSION 6
 
 const char* tnr_last_error(void);
 int tnr_abi_version(void);
 /* Fails unless the current device is compute capability 10.x. Returns SM count in *num_sms. */
 int tnr_device_check(int* num_sms);
+/* Leave `n_sms` SMs of the current device out of the persistent GEMM grids launched from now on (0 = use all).
+ * Data-parallel training sets it while gradient all-reduces are in flight (the replacement of Horovod's background
+ * exchange, Tiny-NewsRec/run.py:144-149): a persistent one-CTA-per-SM GEMM whose grid covers every SM makes the
+ * collective's CTAs wait for a whole GEMM, and the GEMM CTAs displaced by them then run as a second wave. */
+int tnr_set_sm_reserve(int n_sms);
 
 /* ------------------------------------------------------------------ dropout */
 /* Training-mode dropout (the reference trains with dropout 0.1 active: run.py never calls
@@ -246,11 +251,13 @@ int tnr_sgemm_nn(const float* A, const float* B, float* C, int M, int N, int K, 
 int tnr_adam_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, void* shadow_bf16,
                      long long n, float lr, float beta1, float beta2, float eps, int step,
                      float grad_scale, void* stream);
-/* The same with the step counter ON THE DEVICE (int32, incremented by the call; bc_ws: 2 floats of workspace for
- * the bias corrections): a captured CUDA graph of the train step replays with the right step number. */
+/* The same with the step counter ON THE DEVICE (int32; bc_ws: 2 floats of workspace for the bias corrections): a
+ * captured CUDA graph of the train step replays with the right step number.  advance != 0: ++step and refresh
+ * bc_ws first; advance == 0: update this range with the corrections of the current step (the optimiser steps the flat
+ * buffer in two ranges so that the last gradient all-reduce of the step overlaps the update of everything else). */
 int tnr_adam_amsgrad_devstep(float* p, const float* g, float* m, float* v, float* vmax, void* shadow_bf16,
                              long long n, float lr, float beta1, float beta2, float eps, int* step_dev,
-                             float* bc_ws, float grad_scale, void* stream);
+                             float* bc_ws, float grad_scale, int advance, void* stream);
 int tnr_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);
 
 /* ------------------------------------------------------------------ batch assembly */

@@ -38,7 +38,7 @@ def test_library_exports_every_header_symbol(built_lib):
     assert not missing, f"declared in tinyrec.h but not exported: {missing}"
     assert sorted(L.exported_names()) == declared, "ctypes binding table and header disagree"
     lib = L.load()
-    assert lib.tnr_abi_version() == 5
+    assert lib.tnr_abi_version() == 6
 
 
 def test_ctypes_signatures_match_header_declarations():

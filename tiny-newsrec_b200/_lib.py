@@ -47,6 +47,7 @@ P = c_void_p
 _SIGNATURES = {
     "tnr_abi_version": ([], c_int),
     "tnr_device_check": ([POINTER(c_int)], c_int),
+    "tnr_set_sm_reserve": ([c_int], c_int),
     "tnr_gemm_bf16": ([POINTER(GemmArgs), P], c_int),
     "tnr_dropout_mask": ([POINTER(Dropout), c_int64, P, P], c_int),
     "tnr_embed_ln_fwd": ([P, c_int, c_int, c_int, c_int, P, c_int, P, P, P, P, c_float, c_int, P, POINTER(Dropout), P], c_int),
@@ -75,7 +76,7 @@ _SIGNATURES = {
     "tnr_nrms_attn_bwd": ([P, P, P, P, P, P, P, P, c_int, c_int, c_int, P], c_int),
     "tnr_sgemm_nn": ([P, P, P, c_int, c_int, c_int, c_int, c_int64, c_int64, P], c_int),
     "tnr_adam_amsgrad": ([P, P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, c_float, P], c_int),
-    "tnr_adam_amsgrad_devstep": ([P, P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P, c_float, P], c_int),
+    "tnr_adam_amsgrad_devstep": ([P, P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P, c_float, c_int, P], c_int),
     "tnr_cast_f32_bf16": ([P, P, c_int64, P], c_int),
     "tnr_gather_rows_i32_i64": ([P, c_int64, P, c_int64, c_int, P, P], c_int),
     "tnr_gather_rows_f32": ([P, c_int64, P, c_int64, c_int, P, c_int64, P], c_int),
@@ -106,7 +107,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res
-    if lib.tnr_abi_version() != 5:
+    if lib.tnr_abi_version() != 6:
         raise TinyRecError("libtinyrec.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -48,6 +48,7 @@ constexpr int MAX_DEVICES = 64;
   } while (0)
 
 int num_sms();           // cached SM count of the current device (148 on B200)
+int sm_reserve();        // SMs the persistent GEMM grids leave free on the current device (tnr_set_sm_reserve)
 
 // ---- device helpers ---------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

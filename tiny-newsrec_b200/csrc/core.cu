@@ -18,6 +18,14 @@ int cuda_fail(cudaError_t e, const char* what) {
   return 2;
 }
 
+static std::atomic<int> g_sm_reserve[MAX_DEVICES];
+
+int sm_reserve() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return 0;
+  return g_sm_reserve[dev].load(std::memory_order_relaxed);
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -43,5 +51,14 @@ extern "C" __attribute__((visibility("default"))) int tnr_device_check(int* sms)
   TNR_REQUIRE(major == 10, "libtinyrec is built for sm_100a only; device %d is sm_%d%d (no fallback path)", dev, major,
               minor);
   if (sms) *sms = tnr::num_sms();
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int tnr_set_sm_reserve(int n_sms) {
+  int dev = 0;
+  TNR_CHECK_CUDA(cudaGetDevice(&dev));
+  TNR_REQUIRE(dev >= 0 && dev < tnr::MAX_DEVICES, "device index %d out of range", dev);
+  TNR_REQUIRE(n_sms >= 0 && n_sms <= 64 && n_sms % 2 == 0, "tnr_set_sm_reserve: 0 <= n_sms <= 64, even (CTA pairs), got %d", n_sms);
+  tnr::g_sm_reserve[dev].store(n_sms, std::memory_order_relaxed);
   return 0;
 }

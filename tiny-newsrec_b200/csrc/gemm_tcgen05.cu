@@ -871,8 +871,10 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
     }
   }
 
-  const int sms = num_sms();
+  int sms = num_sms();
   TNR_REQUIRE(sms > 0, "tnr_gemm_bf16: no CUDA device");
+  sms -= sm_reserve();          // SMs left to a concurrently running collective (tnr_set_sm_reserve)
+  TNR_REQUIRE(sms >= 2, "tnr_gemm_bf16: SM reserve leaves no SMs");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cta2) {
     const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles * p.splits;

@@ -346,12 +346,14 @@ __global__ void adam_step_prep_kernel(int* __restrict__ step_dev, float* __restr
 
 TNR_API int tnr_adam_amsgrad_devstep(float* p, const float* g, float* m, float* v, float* vmax, void* shadow_bf16,
                                      long long n, float lr, float beta1, float beta2, float eps, int* step_dev,
-                                     float* bc_ws, float grad_scale, void* stream) {
+                                     float* bc_ws, float grad_scale, int advance, void* stream) {
   TNR_REQUIRE(step_dev != nullptr && bc_ws != nullptr, "tnr_adam_amsgrad_devstep: step_dev (int32) and bc_ws (2 floats) are required");
-  if (n == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  adam_step_prep_kernel<<<1, 1, 0, st>>>(step_dev, bc_ws, beta1, beta2);
-  TNR_LAUNCH_CHECK();
+  if (advance) {
+    adam_step_prep_kernel<<<1, 1, 0, st>>>(step_dev, bc_ws, beta1, beta2);
+    TNR_LAUNCH_CHECK();
+  }
+  if (n == 0) return 0;
   const long long threads = (n + 3) / 4;
   const int grid = (int)((threads + 255) / 256);
   adam_amsgrad_kernel<<<grid, 256, 0, st>>>(p, g, m, v, vmax, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr, beta1,

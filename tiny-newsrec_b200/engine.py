@@ -353,10 +353,14 @@ class Encoder:
         g = flat.g_view(p) if rows is None else flat.grad[flat.off(p):flat.off(p) + rows * p.shape[1]].view(rows, p.shape[1])
         ops.gemm(dy, xin, g, a_t=True, b_t=True, split_k=self._splitk(M, xin.shape[1], dy.shape[0]), accumulate=True)
 
-    def backward(self, d_news, flat, on_layer_done=None, ws=None):
+    def backward(self, d_news, flat, on_layer_done=None, ws=None, on_grads_ready=None):
         """d_news fp32 [n, D] -> parameter gradients accumulated into ``flat.grad``.
         ``on_layer_done(i)`` is called after the last gradient kernel of encoder layer ``i`` was
-        enqueued (bucketed gradient all-reduce overlapping the rest of the backward)."""
+        enqueued (bucketed gradient all-reduce overlapping the rest of the backward).
+        ``on_grads_ready(first_param, last_param)``: finer notifications for the LOWEST trainable layer, whose
+        gradient exchange has no later backward work to hide behind: the contiguous flat-buffer range
+        [first_param .. last_param] is final.  With it the layer's weight gradients are issued so that the smallest
+        range (attention.output: 2.4 MB) is the one that finishes last."""
         ws = self.last_ws if ws is None else ws      # ws: the workspace of the forward pass this backward belongs to
         n, L, low, x = ws["n"], ws["L"], ws["low"], ws["x"]
         drop = ws.get("drop")
@@ -390,6 +394,7 @@ class Encoder:
         for i in range(nl - 1, low - 1, -1):
             lr, sv = self.layers[i], ws["saved"][i - low]
             train = flat.has(lr.q.weight)
+            fine = train and i == low and on_grads_ready is not None
             wqkv, bqkv, wo, w1, w2 = self.layer_weights(flat, i)
             dpre, dz, dqkv, dctx, dx2 = ws["dpre"], ws["dz"], ws["dqkv"], ws["dctx"], ws["dx2"]
             sg, sb = (flat.g_view(lr.ln2.weight), flat.g_view(lr.ln2.bias)) if train else (self.scratch_ln[:E], self.scratch_ln[E:])
@@ -401,12 +406,16 @@ class Encoder:
                               dsum=flat.g_view(lr.f2.bias) if train else None)       # + f2.bias gradient
             if train:
                 self._wgrad(flat, lr.f2.weight, dd, sv["h"])
+                if fine:
+                    on_grads_ready(lr.f2.weight, lr.ln2.bias)
             # dz = (dd @ W2) * gelu'(z); its column sums (the intermediate.dense bias gradient) come out of the
             # same epilogue
             ops.gemm(dd, w2, dz, b_t=True, act=ops.ACT_MULAUX, aux=sv["z"],
                      colsum=flat.g_view(lr.f1.bias) if train else None)
             if train:
                 self._wgrad(flat, lr.f1.weight, dz, sv["x1"])
+                if fine:
+                    on_grads_ready(lr.f1.weight, lr.f1.bias)
             ops.gemm(dz, w1, dx2, b_t=True, residual=dpre)                 # d x1
             sg, sb = (flat.g_view(lr.ln1.weight), flat.g_view(lr.ln1.bias)) if train else (self.scratch_ln[:E], self.scratch_ln[E:])
             d1 = dmk(drop_site(i, KIND_ATT_OUT), ph)
@@ -414,7 +423,7 @@ class Encoder:
             ops.layernorm_bwd(dx2, sv["pre1"], lr.ln1.weight, self.ln_eps, dpre, sg, sb,
                               dx_drop=dd if d1 is not None else None, drop=d1,
                               dsum=flat.g_view(lr.o.bias) if train else None)        # + attention.output.dense.bias gradient
-            if train:
+            if train and not fine:
                 self._wgrad(flat, lr.o.weight, dd, sv["ctx"])
             ops.gemm(dd, wo, dctx, b_t=True)
             dbq = None
@@ -425,6 +434,13 @@ class Encoder:
                          dbias=dbq)
             if train:
                 self._wgrad(flat, lr.q.weight, dqkv, sv["xin"], rows=3 * E)
+            if fine:
+                # lowest trainable layer: the QKV range (7 MB) goes out now; the attention.output weight gradient was
+                # held back (dd / ctx stay valid: no layer below overwrites them) so that the last exchange of the
+                # step is the smallest range
+                on_grads_ready(lr.q.weight, lr.v.bias)
+                self._wgrad(flat, lr.o.weight, dd, sv["ctx"])
+                on_grads_ready(lr.o.weight, lr.ln1.bias)
             if i > low:
                 ops.gemm(dqkv, wqkv, dx, b_t=True, residual=dpre)
             if on_layer_done is not None and train:

@@ -18,7 +18,7 @@ from torch import nn
 
 from . import ops
 from ._lib import TinyRecError
-from .engine import BF, F32, DropState, Encoder, FlatParams
+from .engine import BF, F32, DropState, Encoder, FlatParams, _align8
 from .synth import BERT_BASE
 
 # ------------------------------------------------------------------------------------
@@ -492,16 +492,43 @@ class TrainState:
             return
         # Bucketed exchange: the flat buffer is laid out [layer low | ... | layer top | pooling head | user
         # encoder | transform_matrix] and the backward finishes it from the END: once layer i is done,
-        # everything from its first parameter up to the previous bucket start is final.
+        # everything from its first parameter up to the previous bucket start is final.  The LOWEST trainable layer
+        # has no later backward work to overlap with, so it reports its four contiguous parameter ranges one by one
+        # (on_grads_ready) and only its smallest range trails the backward.
         done_to = [flat.numel]
+        sent = []                      # [lo, hi) ranges of the lowest layer already handed to the hook
 
         def layer_done(i):
             lo = flat.off(self.enc.layers[i].q.weight)
-            if lo < done_to[0]:
+            if lo >= done_to[0]:
+                return
+            if sent:                   # the lowest layer went out range by range: send what is left around them
+                cur = lo
+                for a, b in sorted(sent):
+                    if a > cur:
+                        self.comm_hook(flat, cur, a)
+                    cur = max(cur, b)
+                if done_to[0] > cur:
+                    self.comm_hook(flat, cur, done_to[0])
+            else:
                 self.comm_hook(flat, lo, done_to[0])
-                done_to[0] = lo
+            done_to[0] = lo
 
-        self.enc.backward(w["d_news"], flat, on_layer_done=layer_done)
+        def grads_ready(first, last):
+            if not sent:               # everything above this layer (a single trainable layer: the heads) is final
+                lr_low = self.enc.layers[self.enc.lowest_trainable_layer()]
+                top = _align8(flat.off(lr_low.ln2.bias) + lr_low.ln2.bias.numel())
+                if done_to[0] > top:
+                    self.comm_hook(flat, top, done_to[0])
+                    done_to[0] = top
+            lo, hi = flat.off(first), _align8(flat.off(last) + last.numel())
+            hi = min(hi, done_to[0])
+            if hi > lo:
+                self.comm_hook(flat, lo, hi)
+                sent.append((lo, hi))
+
+        self.enc.backward(w["d_news"], flat, on_layer_done=layer_done,
+                          on_grads_ready=grads_ready if getattr(self, "fine_grained_comm", True) else None)
         if done_to[0] > 0:
             self.comm_hook(flat, 0, done_to[0])
 

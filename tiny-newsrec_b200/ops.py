@@ -506,15 +506,27 @@ def adam_amsgrad(p, g, m, v, vmax, shadow, lr, beta1, beta2, eps, step, grad_sca
 
 
 @_timed
-def adam_amsgrad_devstep(p, g, m, v, vmax, shadow, lr, beta1, beta2, eps, step_dev, bc_ws, grad_scale=1.0):
-    """Adam(amsgrad) with the step counter on the device (int32 [1], incremented by the call): graph-capturable."""
-    lib = _ready(p, 2)
+def adam_amsgrad_devstep(p, g, m, v, vmax, shadow, lr, beta1, beta2, eps, step_dev, bc_ws, grad_scale=1.0, advance=True):
+    """Adam(amsgrad) with the step counter on the device (int32 [1]): graph-capturable.  ``advance`` increments the
+    counter and refreshes the bias corrections first; a second range of the same step passes ``advance=False``."""
+    lib = _ready(p, 2 if advance else 1)
     for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v"), (bc_ws, "bc_ws")) + (((vmax, "vmax"),) if vmax is not None else ()):
         _chk(t, _f32, "adam." + nm)
     _chk(step_dev, torch.int32, "adam.step_dev")
     _lib.check(lib.tnr_adam_amsgrad_devstep(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(vmax), _ptr(shadow), p.numel(), lr, beta1,
-                                            beta2, eps, _ptr(step_dev), _ptr(bc_ws), grad_scale, _stream()),
+                                            beta2, eps, _ptr(step_dev), _ptr(bc_ws), grad_scale, int(bool(advance)),
+                                            _stream()),
                "tnr_adam_amsgrad_devstep")
+
+
+def set_sm_reserve(n_sms, device=None):
+    """SMs the persistent GEMM grids leave free on ``device`` from now on (0 = all SMs): tnr_set_sm_reserve."""
+    lib = _lib.load()
+    if device is not None and torch.cuda.current_device() != torch.device(device).index:
+        with torch.cuda.device(device):
+            _lib.check(lib.tnr_set_sm_reserve(int(n_sms)), "tnr_set_sm_reserve")
+        return
+    _lib.check(lib.tnr_set_sm_reserve(int(n_sms)), "tnr_set_sm_reserve")
 
 
 @_timed

@@ -62,11 +62,11 @@ class Adam:
 
     def step(self):
         flat = self.ensure_state()
-        ops.bump_param_generation()
         ranges = getattr(self, "lr_ranges", None)
         if ranges:
             if self.capturable:
                 raise TinyRecError("lr ranges are not supported together with the device step counter")
+            ops.bump_param_generation()
             self.step_count += 1
             for lo, hi, lr in ranges:
                 if hi > lo:
@@ -75,13 +75,29 @@ class Adam:
                                      flat.shadow[lo:hi], lr, self.betas[0], self.betas[1], self.eps, self.step_count,
                                      self.grad_scale)
             return
-        if self.capturable:
-            ops.adam_amsgrad_devstep(flat.data, flat.grad, self.m, self.v, self.vmax, flat.shadow, self.lr, self.betas[0],
-                                     self.betas[1], self.eps, self.step_dev, self.bc_ws, self.grad_scale)
-            return
-        self.step_count += 1
-        ops.adam_amsgrad(flat.data, flat.grad, self.m, self.v, self.vmax, flat.shadow, self.lr, self.betas[0],
-                         self.betas[1], self.eps, self.step_count, self.grad_scale)
+        self.step_ranges([(0, flat.numel)], advance=True)
+
+    def step_ranges(self, ranges, advance=True):
+        """Update the element ranges ``[(lo, hi), ...]`` of the flat buffer (8-element aligned bounds) with the bias
+        corrections of ONE optimizer step: ``advance`` starts that step (counter + 1), further calls of the same step
+        pass ``advance=False``.  Adam is element-wise, so a step may be applied range by range."""
+        flat = self.ensure_state()
+        ops.bump_param_generation()
+        if advance and not self.capturable:
+            self.step_count += 1
+        for lo, hi in ranges:
+            if hi <= lo and not (advance and self.capturable):
+                continue
+            sl = slice(lo, hi)
+            vmax = self.vmax[sl] if self.vmax is not None else None
+            if self.capturable:
+                ops.adam_amsgrad_devstep(flat.data[sl], flat.grad[sl], self.m[sl], self.v[sl], vmax, flat.shadow[sl], self.lr,
+                                         self.betas[0], self.betas[1], self.eps, self.step_dev, self.bc_ws, self.grad_scale,
+                                         advance=advance)
+            else:
+                ops.adam_amsgrad(flat.data[sl], flat.grad[sl], self.m[sl], self.v[sl], vmax, flat.shadow[sl], self.lr,
+                                 self.betas[0], self.betas[1], self.eps, self.step_count, self.grad_scale)
+            advance = False
 
     def steps_done(self):
         return int(self.step_dev) if self.capturable and self.step_dev is not None else self.step_count
@@ -112,22 +128,36 @@ def broadcast_parameters(model, root_rank=0):
 class DistributedOptimizer:
     """Average the flat gradient buffer over ranks (NCCL all-reduce over NVLink), then step.
 
-    ``overlap=True`` launches one all-reduce per gradient bucket on a side stream as soon as the
-    backward has finished that bucket (TrainState.comm_hook: top encoder layer + heads first, lower
-    layers as they complete), so the exchange of layer i overlaps the backward of layer i-1 like
-    Horovod's per-tensor hooks did; ``step()`` waits for all of them."""
+    ``overlap=True`` launches one all-reduce per gradient bucket on a side stream as soon as the backward has
+    finished that bucket (TrainState.comm_hook: top encoder layer + heads first; the lowest trainable layer range by
+    range), so the exchange overlaps the remaining backward like Horovod's per-tensor hooks did.  ``step()`` waits
+    for all buckets but the LAST, updates everything outside it, then waits for the last one and updates that range:
+    the trailing exchange (2.4 MB) hides behind the Adam pass over the other 57 MB.
 
-    def __init__(self, optimizer, overlap=True):
+    While exchanges are in flight the persistent GEMM grids leave ``sm_reserve`` SMs free (``tnr_set_sm_reserve``) and
+    NCCL is capped at that many CTAs (``NCCL_MAX_CTAS``, set by ``tinyrec.parallel.init_distributed`` before the
+    communicator exists): otherwise a collective's CTAs wait for a whole one-CTA-per-SM GEMM, and the GEMM CTAs they
+    displace afterwards run as a second wave (+0.44 ms per step at 8 GPUs in round 1)."""
+
+    def __init__(self, optimizer, overlap=True, sm_reserve=None):
+        import os
         self.opt = optimizer
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.opt.grad_scale = 1.0 / self.world          # SUM all-reduce, scale folded into Adam
         self.stream = torch.cuda.Stream() if (self.world > 1 and overlap) else None
         self.pending = []
+        if sm_reserve is None:
+            sm_reserve = int(os.environ.get("TNR_COMM_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "0")) or 0)
+        self.sm_reserve = (sm_reserve + 1) // 2 * 2 if self.stream is not None else 0
+        self.reserved = False
         if self.stream is not None:
             self.opt.model.train_state().comm_hook = self._launch
 
     def _launch(self, flat, lo=0, hi=None):
         hi = flat.numel if hi is None else hi
+        if self.sm_reserve and not self.reserved:
+            ops.set_sm_reserve(self.sm_reserve)         # GEMMs enqueued from here to step() leave room for the collective
+            self.reserved = True
         ev = torch.cuda.Event()
         ev.record()
         self.stream.wait_event(ev)
@@ -135,7 +165,7 @@ class DistributedOptimizer:
             dist.all_reduce(flat.grad[lo:hi], op=dist.ReduceOp.SUM)
             done = torch.cuda.Event()
             done.record()
-        self.pending.append(done)
+        self.pending.append((lo, hi, done))
 
     def zero_grad(self, set_to_none=False):
         self.opt.zero_grad()
@@ -143,9 +173,22 @@ class DistributedOptimizer:
     def step(self):
         if self.world > 1:
             if self.stream is not None and self.pending:
-                for ev in self.pending:
-                    torch.cuda.current_stream().wait_event(ev)
-                self.pending = []
+                if self.reserved:
+                    ops.set_sm_reserve(0)
+                    self.reserved = False
+                cur = torch.cuda.current_stream()
+                pend, self.pending = self.pending, []
+                flat = self.opt._flat()
+                lo, hi, last = pend[-1]
+                splittable = len(pend) > 1 and not getattr(self.opt, "lr_ranges", None) and lo % 8 == 0 and hi % 8 == 0
+                for _, _, ev in pend[:-1]:
+                    cur.wait_event(ev)
+                if splittable:
+                    self.opt.step_ranges([(0, lo), (hi, flat.numel)], advance=True)
+                    cur.wait_event(last)
+                    self.opt.step_ranges([(lo, hi)], advance=False)
+                    return
+                cur.wait_event(last)
             else:
                 dist.all_reduce(self.opt._flat().grad, op=dist.ReduceOp.SUM)
         self.opt.step()
