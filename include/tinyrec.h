@@ -272,12 +272,14 @@ int tnr_gather_rows_f32(const float* table, long long n_rows_table, const int32_
 /* ------------------------------------------------------------------ impression scoring */
 /* Per impression b: score_c = table[cand[ptr[b]+c]] . user[b]; AUC / MRR / nDCG@5 / nDCG@10 with
  * binary labels; impressions with constant labels are skipped (valid = 0).
- * per_imp double [n_imp, 5] = {auc, mrr, ndcg5, ndcg10, valid}; sums double [5] += column sums
- * (NULL to skip); score_out fp32 [nnz] or NULL.
+ * ptr int64 [n_imp + 1] (CSR offsets, ptr[n_imp] == nnz), cand int32 [nnz] (ids outside 0..n_rows-1 read row 0),
+ * label int8 [nnz]; per_imp double [n_imp, 5] = {auc, mrr, ndcg5, ndcg10, valid}; sums double [5] += column sums
+ * (NULL to skip); scores fp32 [nnz]: REQUIRED, the dot scores (output, and the workspace between the flat scoring
+ * kernel and the per-impression ranking kernel); max_c >= the largest candidate count of the batch.
  * Replaces the Python loop at Tiny-NewsRec/run.py:346-361 + metrics.py:5-23 + sklearn roc_auc_score. */
-int tnr_eval_metrics(const float* table, const float* user, const long long* ptr, const int32_t* cand,
-                     const int8_t* label, long long n_imp, int D, int max_c, double* per_imp,
-                     double* sums, float* score_out, void* stream);
+int tnr_eval_metrics(const float* table, long long n_rows, const float* user, const long long* ptr,
+                     const int32_t* cand, const int8_t* label, long long n_imp, long long nnz, int D, int max_c,
+                     double* per_imp, double* sums, float* scores, void* stream);
 
 /* doc-sim diagnostic: *sum_out += sum over pairs (i, j) int32 [n_pairs, 2] with i != j of the fp32 cosine of
  * table rows i and j (pairs with i == j or out of range add 0, as the reference skips them).

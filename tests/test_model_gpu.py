@@ -16,8 +16,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-GRAD_TOL = 5e-2           # per-tensor relative gradient error (bf16 activations / activation gradients); see _chk
-GRAD_TOL_12L = 8e-2       # 12 bf16 layers in front of the loss
+# Per-tensor relative gradient error, bf16 activations / activation gradients with fp32 accumulation.  Bounds = about
+# twice the worst value measured on B200 (round 2, profiles/r02_test_report_summary.txt): 1.4e-2 over the 51 tensors of
+# the benchmark configuration, 2.1e-2 with the NRMS user encoder, 2.9e-2 at 100-token rows, 6.8e-2 behind 12 layers.
+GRAD_TOL = 3e-2
+GRAD_TOL_LONG = 6e-2      # 100-token rows: streamed-KV attention backward, three more bf16 round trips per layer
+GRAD_TOL_12L = 1e-1       # 12 bf16 layers in front of the loss; the scores are ~60 with gaps of ~1
 SCORE_TOL = 1e-2          # north_star: logits / embeddings within 1e-2 relative on the bf16 path
 
 
@@ -428,15 +432,15 @@ def test_gathers_bit_exact(golden):
 
 
 def test_eval_metrics_vs_reference_golden(golden):
-    """Scores are injected through a 1-D 'embedding' (D=4: table row = [score,0,0,0], user = e0)."""
+    """Scores are injected through a 1-D 'embedding' (D=32: table row = [score,0,...,0], user = e0)."""
     import tinyrec.ops as ops
     g = golden("metrics")
     ptr = torch.from_numpy(g["ptr"].astype(np.int64)).cuda()
     nnz = int(g["ptr"][-1])
-    table = torch.zeros(nnz, 4, device="cuda")
+    table = torch.zeros(nnz, 32, device="cuda")
     table[:, 0] = torch.from_numpy(g["score"]).cuda()
     n_imp = len(g["ptr"]) - 1
-    user = torch.zeros(n_imp, 4, device="cuda")
+    user = torch.zeros(n_imp, 32, device="cuda")
     user[:, 0] = 1.0
     cand = torch.arange(nnz, dtype=torch.int32, device="cuda")
     label = torch.from_numpy(g["label"].astype(np.int8)).cuda()
@@ -546,7 +550,7 @@ def test_kd_step_long_sequence_vs_oracle():
     _chk("test_kd_step_long_sequence_vs_oracle.score", _rel(res[4], ref[4].detach()), SCORE_TOL)
     named = dict(m.named_parameters())
     for k in names:
-        _chk(f"test_kd_step_long_sequence_vs_oracle.grad.{k}", _grad_err(k, named[k].grad, osd[k].grad, named), GRAD_TOL)
+        _chk(f"test_kd_step_long_sequence_vs_oracle.grad.{k}", _grad_err(k, named[k].grad, osd[k].grad, named), GRAD_TOL_LONG)
 
 
 def test_doc_sim_matches_reference_loop():

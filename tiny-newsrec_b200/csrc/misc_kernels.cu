@@ -166,121 +166,151 @@ doc_sim_kernel(const float* __restrict__ table, long long n_rows, const int32_t*
 
 // ---------------------------------------------------------------------------------
 // impression scoring + ranking metrics (reference: Tiny-NewsRec/run.py:346-361,
-// metrics.py:5-23, sklearn roc_auc_score).  One block per impression:
-//   score_c = table[cand_c] . user ;  skip if labels constant ;
-//   rank_c  = 1 + #{s_j > s_c} + #{s_j == s_c, j > c}     (= np.argsort(score)[::-1] order)
-//   AUC = (sum_pos #neg below + 0.5 #neg tied) / (P N);  MRR = sum_pos 1/rank / P
-//   nDCG@k = sum_{pos, rank<=k} 1/log2(rank+1) / sum_{r<=min(k,P)} 1/log2(r+1)   (binary labels)
+// metrics.py:5-23, sklearn roc_auc_score), two kernels:
+//   eval_score_kernel  FLAT over all candidates of the batch: score_i = table[cand_i] . user[imp(i)].  An 8-lane
+//                      group owns a candidate (its 1 KB row = 8 x 16 B per lane, all in flight together with the
+//                      user row of its impression, which comes from L1 / L2: consecutive candidates share it), a warp
+//                      four candidates per pass.  No per-impression blocks: impressions run from 2 to 300 candidates,
+//                      and the block-per-impression kernel this replaces left the SMs waiting on block barriers and on
+//                      the serial metric tail of every block (ncu: 2.7 barrier + 6.9 long-scoreboard stalls per issued
+//                      instruction, 20 % of HBM peak).
+//   eval_rank_kernel   warp per impression over the scores (L2-resident):  skip if labels constant (run.py:348);
+//                      rank_c = 1 + #{s_j > s_c} + #{s_j == s_c, j > c}     (= np.argsort(score)[::-1] order)
+//                      AUC = (sum_pos #neg below + 0.5 #neg tied) / (P N);  MRR = sum_pos 1/rank / P
+//                      nDCG@k = sum_{pos, rank<=k} 1/log2(rank+1) / sum_{r<=min(k,P)} 1/log2(r+1)   (binary labels)
 // out[imp] = {auc, mrr, ndcg5, ndcg10, valid}
 // ---------------------------------------------------------------------------------
-constexpr int EVAL_THREADS = 128;
 // 1 / log2(r + 1), r = 1..10: the only discounts nDCG@5 / nDCG@10 ever use (metrics.py:7-9); fp64 log2() on the device
-// is a long software routine and sat on the serial tail of every block
+// is a long software routine
 __constant__ double c_disc[10] = {1.0, 0.6309297535714575, 0.5, 0.43067655807339306, 0.38685280723454163,
                                   0.3562071871080222, 0.3333333333333333, 0.31546487678572877, 0.3010299956639812,
                                   0.2890648263178879};
 
-__global__ void __launch_bounds__(EVAL_THREADS)
-eval_metrics_kernel(const float* __restrict__ table, const float* __restrict__ user, const long long* __restrict__ ptr,
-                    const int32_t* __restrict__ cand, const int8_t* __restrict__ label, int D,
-                    double* __restrict__ out, float* __restrict__ score_out) {
+constexpr int ES_WARPS = 8;
+constexpr int ES_CPW = 32;            // candidates per warp work item (8 passes of 4)
+
+// VPL = float4 per lane of an 8-lane group and row: D = 32 * VPL floats (D = 256 -> 8); D % 32 == 0 required.
+template <int VPL>
+__global__ void __launch_bounds__(ES_WARPS * 32)
+eval_score_kernel(const float* __restrict__ table, long long n_rows, const float* __restrict__ user,
+                  const long long* __restrict__ ptr, const int32_t* __restrict__ cand, long long n_imp, long long nnz,
+                  float* __restrict__ score) {
+  const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
+  const long long warp_global = (long long)blockIdx.x * ES_WARPS + (threadIdx.x >> 5);
+  const long long n_items = (nnz + ES_CPW - 1) / ES_CPW;
+  constexpr int D = 32 * VPL;
+  for (long long item = warp_global; item < n_items; item += (long long)gridDim.x * ES_WARPS) {
+    const long long c0 = item * ES_CPW;
+    // lane l: candidate c0 + l -> its table row and its impression (largest b with ptr[b] <= i)
+    const long long ci = c0 + lane;
+    long long row = 0, imp = 0;
+    if (ci < nnz) {
+      const long long v = cand[ci];
+      row = (v >= 0 && v < n_rows) ? v : 0;                    // unknown id -> row 0 (dataloader.py:74)
+      long long lo = 0, hi = n_imp;                            // ptr[lo] <= ci < ptr[hi]
+      while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (__ldg(ptr + mid) <= ci) lo = mid; else hi = mid;
+      }
+      imp = lo;
+    }
+    float out = 0.f;
+#pragma unroll 2
+    for (int pass = 0; pass < ES_CPW / 4; ++pass) {
+      const int src = pass * 4 + grp;                          // the lane that holds this group's candidate
+      const long long r = __shfl_sync(0xffffffffu, row, src);
+      const long long b = __shfl_sync(0xffffffffu, imp, src);
+      const bool live = c0 + src < nnz;
+      const float4* xr = reinterpret_cast<const float4*>(table + r * D) + gl;
+      const float4* ur = reinterpret_cast<const float4*>(user + b * D) + gl;
+      float4 x[VPL], u[VPL];
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) x[v] = live ? __ldg(xr + v * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) u[v] = live ? __ldg(ur + v * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+      // the SAME summation tree for every candidate of a row id and user: duplicates of a candidate tie exactly
+      float t = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v)
+        t = fmaf(x[v].x, u[v].x, fmaf(x[v].y, u[v].y, fmaf(x[v].z, u[v].z, fmaf(x[v].w, u[v].w, t))));
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      // hand the score to the lane that owns the candidate: coalesced store of 32 scores at the end
+      const float mine = __shfl_sync(0xffffffffu, t, (lane & 3) * 8);   // lane l takes group (l & 3) of pass (l >> 2)
+      if ((lane >> 2) == pass) out = mine;
+    }
+    if (ci < nnz) score[ci] = out;
+  }
+}
+
+constexpr int ER_WARPS = 8;
+
+__global__ void __launch_bounds__(ER_WARPS * 32)
+eval_rank_kernel(const float* __restrict__ score, const long long* __restrict__ ptr, const int8_t* __restrict__ label,
+                 long long n_imp, int cap, double* __restrict__ out) {
   extern __shared__ __align__(16) float sm[];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const long long b = (long long)blockIdx.x * wpb + warp;
+  if (b >= n_imp) return;
+  float* s_score = sm + (size_t)warp * cap;                                   // [cap]
+  int8_t* s_lab = reinterpret_cast<int8_t*>(sm + (size_t)wpb * cap) + (size_t)warp * cap;
   const long long p0 = ptr[b];
   const int C = (int)(ptr[b + 1] - p0);
-  float* s_user = sm;                         // [D]
-  float* s_score = sm + D;                    // [C]
-  int8_t* s_lab = reinterpret_cast<int8_t*>(s_score + C);
-  __shared__ double red[4][EVAL_THREADS / 32];
-  __shared__ int s_pos;
-  for (int d = tid; d < D; d += EVAL_THREADS) s_user[d] = user[(size_t)b * D + d];
-  if (tid == 0) s_pos = 0;
-  __syncthreads();
-  int npos_local = 0;
-  // four candidates per warp and pass: their index loads, then their row loads, are all issued before the first
-  // reduction (one row in flight per warp left the kernel latency-bound: 1.4 TB/s of candidate rows)
-  constexpr int CPW = 4;
-  for (int c0 = warp * CPW; c0 < C; c0 += (EVAL_THREADS / 32) * CPW) {
-    const float* row[CPW];
+  int npos = 0;
+  for (int c = lane; c < C; c += 32) {
+    s_score[c] = score[p0 + c];
+    const int8_t y = label[p0 + c];
+    s_lab[c] = y;
+    npos += (y != 0);
+  }
 #pragma unroll
-    for (int k = 0; k < CPW; ++k) row[k] = table + (size_t)(c0 + k < C ? cand[p0 + c0 + k] : 0) * D;
-    float t[CPW];
-#pragma unroll
-    for (int k = 0; k < CPW; ++k) t[k] = 0.f;
-    for (int d = lane * 4; d < D; d += 128) {
-      float4 x[CPW];
-#pragma unroll
-      for (int k = 0; k < CPW; ++k) x[k] = *reinterpret_cast<const float4*>(row[k] + d);
-      const float4 u = *reinterpret_cast<const float4*>(s_user + d);
-#pragma unroll
-      for (int k = 0; k < CPW; ++k) t[k] = fmaf(x[k].x, u.x, fmaf(x[k].y, u.y, fmaf(x[k].z, u.z, fmaf(x[k].w, u.w, t[k]))));
+  for (int o = 16; o > 0; o >>= 1) npos += __shfl_xor_sync(0xffffffffu, npos, o);
+  __syncwarp();
+  const int P = npos, N = C - P;
+  if (P == 0 || N == 0) {                      // run.py:348 -- skipped impression
+    if (lane < 5) out[(size_t)b * 5 + lane] = 0.0;
+    return;
+  }
+  long long auc2 = 0;                          // 2 * (#neg below) + (#neg tied), summed over the positives: exact
+  double mrr = 0.0, d5 = 0.0, d10 = 0.0;       // lane 0 only, positives in index order
+  for (int c = 0; c < C; ++c) {
+    if (s_lab[c] == 0) continue;               // warp-uniform
+    const float sc = s_score[c];
+    int above = 0, a2 = 0;
+    for (int j = lane; j < C; j += 32) {
+      const float sj = s_score[j];
+      above += (sj > sc) || (sj == sc && j > c);
+      if (s_lab[j] == 0) a2 += 2 * (int)(sj < sc) + (int)(sj == sc);
     }
 #pragma unroll
-    for (int k = 0; k < CPW; ++k) t[k] = warp_sum(t[k]);
+    for (int o = 16; o > 0; o >>= 1) {
+      above += __shfl_xor_sync(0xffffffffu, above, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
     if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < CPW; ++k) {
-        const int c = c0 + k;
-        if (c < C) {
-          s_score[c] = t[k];
-          const int8_t y = label[p0 + c];
-          s_lab[c] = y;
-          npos_local += (y != 0);
-          if (score_out != nullptr) score_out[p0 + c] = t[k];
-        }
+      const int rank = above + 1;
+      auc2 += a2;
+      mrr += 1.0 / (double)rank;
+      if (rank <= 10) {
+        const double disc = c_disc[rank - 1];
+        if (rank <= 5) d5 += disc;
+        d10 += disc;
       }
     }
   }
-  if (lane == 0 && npos_local) atomicAdd(&s_pos, npos_local);
-  __syncthreads();
-  const int P = s_pos, N = C - P;
-  if (P == 0 || N == 0) {                      // run.py:348 -- skipped impression
-    if (tid < 5) out[(size_t)b * 5 + tid] = 0.0;
-    return;
-  }
-  double auc = 0.0, mrr = 0.0, d5 = 0.0, d10 = 0.0;
-  for (int c = tid; c < C; c += EVAL_THREADS) {
-    if (s_lab[c] == 0) continue;
-    const float sc = s_score[c];
-    int above = 0, neg_below = 0, neg_tied = 0;
-    for (int j = 0; j < C; ++j) {
-      const float sj = s_score[j];
-      above += (sj > sc) || (sj == sc && j > c);
-      if (s_lab[j] == 0) { neg_below += (sj < sc); neg_tied += (sj == sc); }
-    }
-    const int rank = above + 1;
-    auc += (double)neg_below + 0.5 * (double)neg_tied;
-    mrr += 1.0 / (double)rank;
-    if (rank <= 10) {
-      const double disc = c_disc[rank - 1];
-      if (rank <= 5) d5 += disc;
-      d10 += disc;
-    }
-  }
-  double vals[4] = {auc, mrr, d5, d10};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    double v = vals[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[k][warp] = v;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    double t[4] = {0, 0, 0, 0};
-    for (int k = 0; k < 4; ++k)
-      for (int w = 0; w < EVAL_THREADS / 32; ++w) t[k] += red[k][w];
+  if (lane == 0) {
     double i5 = 0.0, i10 = 0.0;
     for (int r = 1; r <= min(P, 10); ++r) {
       const double disc = c_disc[r - 1];
       if (r <= 5) i5 += disc;
       i10 += disc;
     }
-    out[(size_t)b * 5 + 0] = t[0] / ((double)P * (double)N);
-    out[(size_t)b * 5 + 1] = t[1] / (double)P;
-    out[(size_t)b * 5 + 2] = t[2] / i5;
-    out[(size_t)b * 5 + 3] = t[3] / i10;
+    out[(size_t)b * 5 + 0] = 0.5 * (double)auc2 / ((double)P * (double)N);
+    out[(size_t)b * 5 + 1] = mrr / (double)P;
+    out[(size_t)b * 5 + 2] = d5 / i5;
+    out[(size_t)b * 5 + 3] = d10 / i10;
     out[(size_t)b * 5 + 4] = 1.0;
   }
 }
@@ -401,16 +431,45 @@ TNR_API int tnr_doc_sim(const float* table, long long n_rows, const int32_t* pai
   return 0;
 }
 
-TNR_API int tnr_eval_metrics(const float* table, const float* user, const long long* ptr, const int32_t* cand,
-                             const int8_t* label, long long n_imp, int D, int max_c, double* per_imp, double* sums,
-                             float* score_out, void* stream) {
-  TNR_REQUIRE(D % 4 == 0, "tnr_eval_metrics: D must be a multiple of 4");
+template <int VPL>
+static void eval_score_launch(int grid, cudaStream_t st, const float* table, long long n_rows, const float* user,
+                              const long long* ptr, const int32_t* cand, long long n_imp, long long nnz, float* score) {
+  eval_score_kernel<VPL><<<grid, ES_WARPS * 32, 0, st>>>(table, n_rows, user, ptr, cand, n_imp, nnz, score);
+}
+
+TNR_API int tnr_eval_metrics(const float* table, long long n_rows, const float* user, const long long* ptr,
+                             const int32_t* cand, const int8_t* label, long long n_imp, long long nnz, int D, int max_c,
+                             double* per_imp, double* sums, float* scores, void* stream) {
+  TNR_REQUIRE(D % 32 == 0 && D >= 32 && D <= 512, "tnr_eval_metrics: D=%d must be a multiple of 32 in 32..512", D);
+  TNR_REQUIRE(scores != nullptr || nnz == 0, "tnr_eval_metrics: scores fp32 [nnz] is required (output and workspace)");
+  TNR_REQUIRE(n_rows >= 1, "tnr_eval_metrics: empty table");
   if (n_imp == 0) return 0;
-  const int smem = (D + max_c) * 4 + ((max_c + 15) / 16) * 16;
-  TNR_REQUIRE(smem <= 200 * 1024, "tnr_eval_metrics: max candidates %d too large", max_c);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (smem > 48 * 1024) TNR_SET_SMEM(eval_metrics_kernel, smem);
-  eval_metrics_kernel<<<(int)n_imp, EVAL_THREADS, smem, st>>>(table, user, ptr, cand, label, D, per_imp, score_out);
+  if (nnz > 0) {
+    const long long items = (nnz + ES_CPW - 1) / ES_CPW;
+    long long blocks = (items + ES_WARPS - 1) / ES_WARPS;
+    const long long cap_blocks = (long long)num_sms() * 8;
+    const int grid = (int)(blocks < cap_blocks ? blocks : cap_blocks);
+    switch (D / 32) {
+      case 1: eval_score_launch<1>(grid, st, table, n_rows, user, ptr, cand, n_imp, nnz, scores); break;
+      case 2: eval_score_launch<2>(grid, st, table, n_rows, user, ptr, cand, n_imp, nnz, scores); break;
+      case 4: eval_score_launch<4>(grid, st, table, n_rows, user, ptr, cand, n_imp, nnz, scores); break;
+      case 8: eval_score_launch<8>(grid, st, table, n_rows, user, ptr, cand, n_imp, nnz, scores); break;
+      case 16: eval_score_launch<16>(grid, st, table, n_rows, user, ptr, cand, n_imp, nnz, scores); break;
+      default:
+        set_error("tnr_eval_metrics: D=%d not instantiated (32, 64, 128, 256, 512)", D);
+        return 1;
+    }
+    TNR_LAUNCH_CHECK();
+  }
+  // rank kernel: a warp per impression holds its scores + labels in shared memory (5 bytes per candidate)
+  const int cap = ((max_c > 1 ? max_c : 1) + 15) / 16 * 16;
+  int wpb = ER_WARPS;
+  while (wpb > 1 && (size_t)wpb * cap * 5 > 160 * 1024) wpb >>= 1;
+  const size_t smem = (size_t)wpb * cap * 5;
+  TNR_REQUIRE(smem <= 200 * 1024, "tnr_eval_metrics: max candidates %d too large", max_c);
+  if (smem > 48 * 1024) TNR_SET_SMEM(eval_rank_kernel, smem);
+  eval_rank_kernel<<<(unsigned)((n_imp + wpb - 1) / wpb), wpb * 32, smem, st>>>(scores, ptr, label, n_imp, cap, per_imp);
   TNR_LAUNCH_CHECK();
   if (sums != nullptr) {
     int grid = (int)((n_imp + 255) / 256);

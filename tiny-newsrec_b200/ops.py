@@ -549,15 +549,32 @@ def gather_rows_f32(table, idx, out, out_ld=None):
     return out
 
 
+_eval_ws = {}
+
+
 @_timed
 def eval_metrics(table, user, ptr, cand, label, max_c, per_imp, sums=None, score_out=None):
-    """table fp32 [N, D]; user fp32 [n_imp, D]; ptr int64 [n_imp+1]; cand int32 [nnz]; label int8 [nnz]."""
-    lib = _ready(table)
+    """table fp32 [N, D]; user fp32 [n_imp, D]; ptr int64 [n_imp+1]; cand int32 [nnz]; label int8 [nnz];
+    ``score_out`` fp32 [nnz] receives the dot scores (a cached workspace is used when None)."""
+    lib = _ready(table, 3 if sums is not None else 2)
     _chk(table, _f32, "eval.table"); _chk(user, _f32, "eval.user"); _chk(ptr, torch.int64, "eval.ptr")
     _chk(cand, torch.int32, "eval.cand"); _chk(label, torch.int8, "eval.label"); _chk(per_imp, torch.float64, "eval.per_imp")
     n_imp = ptr.numel() - 1
-    _lib.check(lib.tnr_eval_metrics(_ptr(table), _ptr(user), _ptr(ptr), _ptr(cand), _ptr(label), n_imp, table.shape[1],
-                                    int(max_c), _ptr(per_imp), _ptr(sums), _ptr(score_out), _stream()), "tnr_eval_metrics")
+    nnz = cand.numel()
+    if label.numel() != nnz or user.shape[0] < n_imp or per_imp.numel() < 5 * n_imp or not table.is_contiguous():
+        raise _lib.TinyRecError("eval_metrics: shape / layout mismatch")
+    if score_out is None:
+        key = table.device
+        score_out = _eval_ws.get(key)
+        if score_out is None or score_out.numel() < nnz:
+            score_out = _eval_ws[key] = torch.empty(max(nnz, 1 << 16), device=table.device, dtype=_f32)
+    else:
+        _chk(score_out, _f32, "eval.score_out")
+        if score_out.numel() < nnz:
+            raise _lib.TinyRecError("eval_metrics: score_out must hold nnz floats")
+    _lib.check(lib.tnr_eval_metrics(_ptr(table), table.shape[0], _ptr(user), _ptr(ptr), _ptr(cand), _ptr(label), n_imp, nnz,
+                                    table.shape[1], int(max_c), _ptr(per_imp), _ptr(sums), _ptr(score_out), _stream()),
+               "tnr_eval_metrics")
     return per_imp
 
 
