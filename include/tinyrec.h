@@ -178,14 +178,17 @@ int tnr_user_encoder_fwd_gather(const float* table, long long n_rows, const int3
                                 const float* b2, int use_mask, float* user, float* a_out, int B, int H, int D,
                                 int Q, void* stream);
 /* Scoring path of the same encoder for thousands of impressions per launch (the eval loop, run.py:335-361):
- * the fc1 contraction runs as ONE flat TF32 GEMM over all B*H history rows (persistent CTAs, each keeping one
- * column half of W1 resident in shared memory, 256-row tiles) that emits the logits, then a warp per impression
- * normalises and pools.  `w1_packed`: tnr_user_encoder_packed_w1_floats(D) floats filled by
- * tnr_user_encoder_pack_w1 (re-pack when att_fc1.weight changes).  idx NULL: vecs is [B*H, D]; else vecs is the
- * [n_rows, D] table and idx int32 [B,H] (unknown ids read row 0).  a_out [B,H] is required (it holds the logits
- * between the two kernels).  D % 32 == 0, D <= 256, Q <= 208, H <= 64. */
+ * the fc1 contraction runs as ONE flat TF32 GEMM over the history rows with mask != 0 on the tcgen05 tensor cores
+ * (kind::tf32, CTA pairs, 256-row tiles, W1 resident in the pair's shared memory, rows gathered by index from the
+ * table) that emits the logits, then a warp per impression normalises and pools.  `w1_packed`:
+ * tnr_user_encoder_packed_w1_floats(D) floats filled by tnr_user_encoder_pack_w1 from att_fc1.weight / .bias,
+ * att_fc2.weight and pad_doc (re-pack when any of them changes): the swizzled TF32 image of W1, W1 pad_doc and the
+ * logit of a pad_doc row.  idx NULL: vecs is [B*H, D]; else vecs is the [n_rows, D] table and idx int32 [B,H]
+ * (unknown ids read row 0).  a_out [B,H] is required (it holds the logits between the two kernels).
+ * D % 32 == 0, D <= 256, Q <= 208, H <= 64. */
 long long tnr_user_encoder_packed_w1_floats(int D);
-int tnr_user_encoder_pack_w1(const float* W1, float* packed, int D, int Q, void* stream);
+int tnr_user_encoder_pack_w1(const float* W1, const float* pad_doc, const float* b1, const float* w2, float* packed,
+                             int D, int Q, void* stream);
 long long tnr_user_encoder_score_ws_bytes(int B, int H);
 int tnr_user_encoder_score(const float* vecs, long long n_rows, const int32_t* idx, const float* mask,
                            const float* pad_doc, const float* w1_packed, const float* b1, const float* w2,

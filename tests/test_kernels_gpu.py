@@ -650,9 +650,11 @@ def test_user_encoder_gather_equals_gather_then_encode(use_mask):
     ops.user_encoder_fwd_gather(table, idx, mask, pad, W1, b1, w2, b2, use_mask, u1, a1)
     assert _rel_err(a1, a0)[0] < 1e-5 and _rel_err(u1, u0)[0] < 1e-5
     u2, a2 = torch.empty(B, D, device="cuda"), torch.empty(B, H, device="cuda")        # the flat scoring path
-    ops.user_encoder_score(table, idx, mask, pad, ops.user_encoder_pack_w1(W1), Q, b1, w2, b2, use_mask, u2, a2, B, H)
-    assert _rel_err(a2, a0)[0] < 1e-5 and _rel_err(u2, u0)[0] < 1e-5
+    ops.user_encoder_score(table, idx, mask, pad, ops.user_encoder_pack_w1(W1, pad, b1, w2), Q, b1, w2, b2, use_mask, u2, a2, B, H)
+    # tcgen05 kind::tf32 TRUNCATES the fp32 history rows to TF32 (the per-impression kernel rounds them): 2^-11 per element
+    assert _rel_err(a2, a0)[0] < 2e-3 and _rel_err(u2, u0)[0] < 2e-3
     ref_u, _, _ = _ue_ref(vecs.view(B, H, D), mask, pad, W1, b1, w2, b2, use_mask)
+    assert _rel_err(u2, ref_u)[0] < 2e-3
     assert _rel_err(u1, ref_u)[0] < 2e-3
 
 
@@ -669,11 +671,13 @@ def test_user_encoder_scoring_path_vs_torch(use_mask, B, H, Q, D):
     mask[2] = 1
     mask[3, : H // 2] = 0                                  # front-padded history, as the loader builds them
     mask[3, H // 2:] = 1
+    mask[4] = 0.25                                         # a fractional mask: weight scaling / linear pad_doc blend
+    mask[5, ::2] = 0.5
     pad, W1 = _randn(D, dtype=f32, scale=0.5, seed=4), _randn(Q, D, dtype=f32, scale=0.06, seed=5)
     b1, w2, b2 = _randn(Q, dtype=f32, scale=0.1, seed=6), _randn(Q, dtype=f32, scale=0.1, seed=7), _randn(1, dtype=f32, seed=8)
     user, a = torch.empty(B, D, device="cuda"), torch.empty(B, H, device="cuda")
     assert ops.user_encoder_score_supported(B, H, D, Q)
-    ops.user_encoder_score(vecs.view(B * H, D), None, mask, pad, ops.user_encoder_pack_w1(W1), Q, b1, w2, b2, use_mask,
+    ops.user_encoder_score(vecs.view(B * H, D), None, mask, pad, ops.user_encoder_pack_w1(W1, pad, b1, w2), Q, b1, w2, b2, use_mask,
                            user, a, B, H)
     ref_u, ref_a, _ = _ue_ref(vecs, mask, pad, W1, b1, w2, b2, use_mask)
     assert _rel_err(a, ref_a)[0] < 2e-3

@@ -62,7 +62,7 @@ _SIGNATURES = {
     "tnr_user_encoder_fwd_multi": ([P, c_int, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
     "tnr_user_encoder_fwd_gather": ([P, c_int64, P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "tnr_user_encoder_packed_w1_floats": ([c_int], c_int64),
-    "tnr_user_encoder_pack_w1": ([P, P, c_int, c_int, P], c_int),
+    "tnr_user_encoder_pack_w1": ([P, P, P, P, P, c_int, c_int, P], c_int),
     "tnr_user_encoder_score_ws_bytes": ([c_int, c_int], c_int64),
     "tnr_user_encoder_score": ([P, c_int64, P, P, P, P, P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "tnr_user_encoder_bwd": ([P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),

@@ -9,6 +9,7 @@
 // Reference: Tiny-NewsRec/model_bert.py:155-176 (UserEncoder, NAML branches), :15-34
 // (AttentionPooling), :277-278,283 (transform_matrix), and their autograd backward.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace tnr {
 
@@ -379,35 +380,57 @@ user_encoder_fwd_kernel(const __grid_constant__ UeFwdParams p) {
 }
 
 // ----------------------------------------------------------------------------------
-// user encoder forward for SCORING (one encoder, thousands of impressions, no e_out): two kernels.
-//   (1) ue_logits_kernel: logit[r] = w2 . tanh(W1 x_r + b1) as ONE flat GEMM over all R = B * H history rows.
-//       Persistent, one CTA per SM, W1 RESIDENT in shared memory: CTA c keeps column half (c & 1) of W1 (104 of
-//       the 208 padded columns, TF32-rounded, 108 KB, one cp.async.bulk) and walks the 256-row tiles
-//       (c >> 1), (c >> 1) + 74, ...; the two halves of a row's logit meet in a global fp32 atomicAdd (two
-//       addends: order-free).  The history rows are gathered from the news table by index inside the kernel
-//       (cp.async, 128-byte pieces, 3-stage ring that runs on across tile boundaries) and blended with pad_doc
-//       at fragment-load time.  What this replaced, measured on the 4 096-impression eval step:
+// user encoder forward for SCORING (one encoder, thousands of impressions, no e_out): three kernels.
+//   (0) ue_compact_kernel: the ids of the history rows with mask != 0 (about half of all (b, h) are front padding).
+//   (1) ue_logits_kernel: logit[r] = w2 . tanh(W1 x_r + b1) as ONE flat TF32 GEMM over the live rows on the 5th-gen
+//       tensor cores: tcgen05.mma.cta_group::2.kind::tf32, M = 256 rows per CTA PAIR (128 per CTA), N = 208 (Q padded),
+//       K = D, fp32 accumulators in TMEM (2 x 256 columns: the epilogue of a tile overlaps the MMAs of the next).
+//       W1 is RESIDENT in shared memory for the whole kernel, split over the pair: each CTA holds 104 of the 208 padded
+//       output columns for all of K (104 x D x 4 B = 106 KB at D = 256, ONE cp.async.bulk of the pre-swizzled,
+//       TF32-rounded image made by ue_pack_w1_kernel) -- cta_group::2 reads the two halves of B from the two SMs, so
+//       every history row is fetched from HBM / L2 once, by the CTA that owns it.  The rows are GATHERED by index from
+//       the news table (dataloader.py:295 fused): four loader warps per CTA issue 16-byte cp.async copies straight into
+//       the 128B-swizzled K-major layout the MMA descriptors read (chunk c of row r lands at r * 128 + ((c ^ (r & 7))
+//       << 4) of a 32-float k-block), a 6-stage ring of 16 KB k-blocks that runs on across tiles; a stage is published
+//       to the pair leader's mbarrier after cp.async.wait_group + fence.proxy.async (the peer CTA's warps arrive
+//       remotely, release.cluster).  One elected thread of the leader issues the MMAs and multicasts the stage-free /
+//       accumulator-ready commits to both CTAs.  Epilogue: a thread owns a row (a TMEM lane), reads its 208
+//       accumulators 32 columns at a time (tcgen05.ld.32x32b.x32), applies + b1, tanh, . w2 in registers and writes
+//       the logit -- no atomics, no cross-lane reduction.  pad_doc branch: W1 (m v + (1 - m) pad) = m (W1 v) +
+//       (1 - m) (W1 pad): the blend is applied to the accumulators with P = W1 pad from the packed image.
+//       What this replaced, measured on the 4 096-impression eval step:
 //         v1 per-impression kernel, W1 fragments from L2 per k-step ......................... 519 us
-//         v2 the same with W1 chunks staged by cp.async, TF32 rounding by IADD .............. 463 us
 //         v3 flat GEMM, 64-row tiles, W1 chunks re-streamed per tile (852 MB of L2 reads) ... 545 us
-//       -- every one of them waits on W1 traffic (40 % of the stall samples at the chunk wait): the cure is not a
-//       better pipeline but not moving W1 at all.
+//         v5 mma.sync TF32, W1 halves resident, live-row list, logit halves by atomicAdd .... 109 us (tensor pipe 36 %)
 //   (2) ue_pool_kernel: warp per impression, alpha = exp(logit + b2) [* mask], a = alpha / (sum + 1e-8),
 //       user = sum_h a_h x_h over the fp32 rows (gathered again; HBM / L2 bound).
 // ----------------------------------------------------------------------------------
-constexpr int UL_ROWS = 256, UL_THREADS = 256, UL_NT = 13, UL_HALF = UL_NT * 8, UL_QT = 2 * UL_HALF, UL_STAGES = 3;
-constexpr int UL_KC = 32, UL_XS = UL_KC + 4;        // X chunk: 32 columns (one 128-byte line per row), padded rows
+constexpr int UL_ROWS = 128;                       // rows per CTA and tile (256 per pair)
+constexpr int UL_KB = 32;                          // floats per k-block: 128 B, one swizzle row
+constexpr int UL_QT = 208, UL_HALF = UL_QT / 2;    // padded query dim (UMMA N) and the W1 rows one CTA holds
+constexpr int UL_STAGES = 6, UL_LAG = 3;           // A ring depth; stages in flight before the oldest is published
 constexpr int UL_DMAX = 256;
+constexpr int UL_A_BYTES = UL_ROWS * 128;          // one k-block of the A tile: 16 KB
+constexpr int UL_W_KB_BYTES = UL_HALF * 128;       // one k-block of a W1 half: 13 KB (13 swizzle atoms)
+constexpr int UL_EPI_WARPS = 4, UL_LOAD_WARPS = 4;
+constexpr int UL_THREADS = 32 * (UL_EPI_WARPS + 2 + UL_LOAD_WARPS);      // epilogue 0-3, MMA 4, TMEM / W1 5, loaders 6-9
+constexpr int UL_TMEM_COLS = 512;                  // two accumulator stages of 256 columns (208 used)
+constexpr int UL_NBARS = 2 * UL_STAGES + 5;
+
+__host__ __device__ constexpr int ul_smem_bytes(int D) {
+  return (D / UL_KB) * UL_W_KB_BYTES + UL_STAGES * UL_A_BYTES + 3 * UL_QT * 4 + UL_NBARS * 8 + 16 + 1024 /*align slack*/;
+}
+// floats of the packed W1 image: the swizzled halves, then P = W1 pad [208], then c_pad = w2 . tanh(P + b1), padding
+__host__ __device__ constexpr long long ul_packed_floats(int D) { return (long long)UL_QT * D + UL_QT + 4; }
 
 struct UlParams {
   const float* vecs;          // [R, D] rows, or the [n_rows, D] table when idx != nullptr
   const int32_t* idx;         // [R] or nullptr
   long long n_rows;
-  const float *mask, *pad, *W1, *b1, *w2;     // W1: the PACKED copy (ue_pack_w1_kernel)
-  float* logits;              // [R], zero-initialised
+  const float *mask, *W1, *b1, *w2;           // W1: the PACKED image (ue_pack_w1_kernel)
+  float* logits;              // [R]; written for the live rows only
   const int32_t* live;        // [n_live] ids of the rows with mask != 0 (ue_compact_kernel; any order)
   const int32_t* n_live;      // device scalar
-  float* c_pad;               // device scalar, zero-initialised: logit of a pad_doc row (BLEND), two halves add into it
   int R, D, Q;
 };
 
@@ -425,213 +448,222 @@ ue_compact_kernel(const float* __restrict__ mask, int R, int32_t* __restrict__ l
   if (is_live) live[base + __popc(bal & ((1u << lane) - 1u))] = r;
 }
 
-// Wp[half][q][D + 4] = tf32(W1[half * 104 + q][d]) for d < D and half * 104 + q < Q, else 0: each half is one
-// contiguous block already in the padded shared-memory layout (conflict-free B-fragment reads) and already rounded.
+// Packed W1 image.  For CTA half h, k-block kb, row r < 104, 16-byte chunk c < 8, element e < 4 the value
+// tf32(W1[h * 104 + r][kb * 32 + c * 4 + e]) (0 past Q) sits at float offset
+//   h * 104 * D  +  kb * 104 * 32  +  (r >> 3) * 256  +  (r & 7) * 32  +  ((c ^ (r & 7)) << 2)  +  e :
+// exactly the SWIZZLE_128B K-major shared-memory image of the half, so one bulk copy brings it in.  Appended:
+// P[q] = sum_d W1[q][d] pad[d] (fp32, from the rounded weights) and c_pad = sum_q w2[q] tanh(P[q] + b1[q]), the logit of
+// a history row that IS pad_doc (every masked row of the user_log_mask = False branch, model_bert.py:168-175).
 __global__ void ue_pack_w1_kernel(const float* __restrict__ W1, float* __restrict__ Wp, int D, int Q) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int DS = D + 4;
-  if (i >= UL_QT * DS) return;
-  const int d = i % DS, q = i / DS;
+  if (i >= UL_QT * D) return;
+  const int q = i / D, d = i - q * D;
+  const int h = q / UL_HALF, r = q - h * UL_HALF, kb = d / UL_KB, c = (d % UL_KB) >> 2, e = d & 3;
   float v = 0.f;
-  if (d < D && q < Q) v = __uint_as_float(f2tf32(W1[(size_t)q * D + d]) & 0xffffe000u);
-  Wp[i] = v;
+  if (q < Q) v = __uint_as_float(f2tf32(W1[(size_t)q * D + d]) & 0xffffe000u);
+  Wp[(size_t)h * UL_HALF * D + (size_t)kb * UL_HALF * UL_KB + (r >> 3) * 256 + (r & 7) * 32 + ((c ^ (r & 7)) << 2) + e] = v;
 }
 
-__device__ __forceinline__ void hm_mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void hm_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void hm_mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "HM_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra HM_DONE;\n\t"
-      "bra HM_WAIT;\n\t"
-      "HM_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void hm_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__global__ void __launch_bounds__(256)
+ue_pack_pad_kernel(const float* __restrict__ W1, const float* __restrict__ pad, const float* __restrict__ b1,
+                   const float* __restrict__ w2, float* __restrict__ Wp, int D, int Q) {
+  __shared__ float red[8];
+  const int q = threadIdx.x;
+  float pq = 0.f;
+  if (q < Q)
+    for (int d = 0; d < D; ++d) pq = fmaf(__uint_as_float(f2tf32(W1[(size_t)q * D + d]) & 0xffffe000u), pad[d], pq);
+  float* P = Wp + (size_t)UL_QT * D;
+  if (q < UL_QT) P[q] = pq;
+  float t = q < Q ? w2[q] * tanh_exp(pq + b1[q]) : 0.f;
+  t = warp_sum(t);
+  if ((q & 31) == 0) red[q >> 5] = t;
+  __syncthreads();
+  if (q == 0) {
+    float c = 0.f;
+    for (int w = 0; w < 8; ++w) c += red[w];
+    P[UL_QT] = c;
+  }
 }
 
 template <bool BLEND>
 __global__ void __launch_bounds__(UL_THREADS, 1)
 ue_logits_kernel(const __grid_constant__ UlParams p) {
-  extern __shared__ __align__(128) float sm[];
-  __shared__ __align__(8) unsigned long long s_bar;
-  const int D = p.D, Q = p.Q, DS = D + 4;
-  float* sW = sm;                                        // [104][D + 4]   resident half of W1 (bulk-copy destination)
-  float* sX = sW + UL_HALF * DS;                         // [STAGES][256][UL_XS]
-  float* sB1 = sX + UL_STAGES * UL_ROWS * UL_XS;         // [104]
-  float* sW2 = sB1 + UL_HALF;                            // [104]
-  float* sPad = sW2 + UL_HALF;                           // [D]    (BLEND)
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int half = blockIdx.x & 1;
+  using namespace gemm;
+  extern __shared__ uint8_t ul_smem_raw[];
+  const int D = p.D, Q = p.Q, NKB = D / UL_KB;
+  const uint32_t smem_base = (smem_u32(ul_smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = ul_smem_raw + (smem_base - smem_u32(ul_smem_raw));
+  // [W1 half: NKB k-blocks of 13 KB][A ring: STAGES x 16 KB][b1 | w2 | P: 3 x 208 floats][barriers][tmem slot]
+  const uint32_t sW = smem_base;
+  const uint32_t sA = sW + (uint32_t)NKB * UL_W_KB_BYTES;
+  float* sVec = reinterpret_cast<float*>(smem_gen + NKB * UL_W_KB_BYTES + UL_STAGES * UL_A_BYTES);
+  const uint32_t bar_base = sA + UL_STAGES * UL_A_BYTES + 3 * UL_QT * 4;
+  auto full_bar = [&](int st) { return bar_base + 8u * st; };                       // leader: both CTAs' loader warps
+  auto empty_bar = [&](int st) { return bar_base + 8u * (UL_STAGES + st); };         // each CTA: MMA commit (multicast)
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * UL_STAGES + a); };       // each CTA: MMA commit (multicast)
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * UL_STAGES + 2 + a); };  // leader: both CTAs' epilogue warps
+  const uint32_t w_bar = bar_base + 8u * (2 * UL_STAGES + 4);                        // each CTA: its W1 half landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + NKB * UL_W_KB_BYTES + UL_STAGES * UL_A_BYTES +
+                                                    3 * UL_QT * 4 + UL_NBARS * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();                 // 0 = leader of the pair
   const int n_live = *p.n_live;
-  const int n_tiles = (n_live + UL_ROWS - 1) / UL_ROWS;
-  const int tile0 = blockIdx.x >> 1, tstride = gridDim.x >> 1;
-  const int my_tiles = tile0 < n_tiles ? (n_tiles - tile0 + tstride - 1) / tstride : 0;
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
-  if (tid == 0) {
-    hm_mbar_init(bar, 1);
+  const int n_tiles = (n_live + 2 * UL_ROWS - 1) / (2 * UL_ROWS);      // pair tiles of 256 live rows
+  const int t_first = (int)(blockIdx.x >> 1), t_stride = (int)(gridDim.x >> 1);
+
+  if (warp == 4 && lane == 0) {
+    for (int st = 0; st < UL_STAGES; ++st) { mbar_init(full_bar(st), 2 * UL_LOAD_WARPS); mbar_init(empty_bar(st), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * UL_EPI_WARPS); }
+    mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const uint32_t bytes = (uint32_t)(UL_HALF * DS * 4);
-    hm_mbar_expect_tx(bar, bytes);
-    hm_bulk_g2s((uint32_t)__cvta_generic_to_shared(sW), p.W1 + (size_t)half * UL_HALF * DS, bytes, bar);
   }
-  for (int q = tid; q < UL_HALF; q += UL_THREADS) {
-    const int col = half * UL_HALF + q;
-    sB1[q] = col < Q ? p.b1[col] : 0.f;
-    sW2[q] = col < Q ? p.w2[col] : 0.f;
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(UL_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-  if (BLEND)
-    for (int d = tid; d < D; d += UL_THREADS) sPad[d] = p.pad[d];
-  const int NK = D / UL_KC;
-  const int n_items = my_tiles * NK;                     // (tile, k chunk) pairs of this CTA, in order
-  // loader state: thread copies piece (tid & 7) of rows (tid >> 3) + 32 i of the tile being LOADED
-  const float* xsrc[8];
-  unsigned xok = 0;
-  auto set_tile = [&](int tl) {
-    const int r0 = (tile0 + tl * tstride) * UL_ROWS;
-    xok = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int li = r0 + (tid >> 3) + 32 * i;
-      // Rows with mask == 0 never get here (the tiles walk the compacted live list): they pool with weight 0
-      // (use_mask) or blend to pad_doc exactly (v * 0 + pad * 1), and they are the front padding of short histories --
-      // index 0 for half of all (b, h) at MIND's history lengths, i.e. one 1 KB table row hammered by every SM
-      // through L2 (cp.async.cg bypasses L1): that hot line, not the GEMM, set the time of the first four versions
-      // of this kernel (~500 us -> 190 us without it).
-      const bool ok = li < n_live;
-      size_t src = ok ? (size_t)p.live[li] : 0;
-      if (p.idx != nullptr && ok) {
-        const long long v = p.idx[src];
-        src = (v >= 0 && v < p.n_rows) ? (size_t)v : 0;  // unknown id -> row 0 (dataloader.py:74)
-      }
-      xsrc[i] = p.vecs + src * D + (tid & 7) * 4;
-      xok |= (ok ? 1u : 0u) << i;
-    }
-  };
-  auto load = [&](int item) {
-    if (item < n_items) {
-      const int tl = item / NK, kc = item - tl * NK;
-      if (kc == 0) set_tile(tl);
-      float* dx = sX + (item % UL_STAGES) * UL_ROWS * UL_XS;
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        cp_async16_zfill(dx + ((tid >> 3) + 32 * i) * UL_XS + (tid & 7) * 4, xsrc[i] + kc * UL_KC, (xok >> i) & 1u);
-    }
-    cp_async_commit();
-  };
-  load(0);
-  load(1);
-  float acc[2][UL_NT][4];
-  float rm[2][2], rom[2][2];                             // row mask and 1 - mask of this thread's 4 rows (BLEND)
-  int rid[2][2];                                         // their row ids (-1: past the live list)
-  hm_mbar_wait(bar, 0);                                  // W1 half resident
-  if (BLEND && blockIdx.x < 2 && warp == 0) {
-    // logit of a row that IS pad_doc (every masked row in this branch), this CTA's column half: one 16-row MMA tile
-    __syncwarp();
-    float pacc[UL_NT][4];
-#pragma unroll
-    for (int nt = 0; nt < UL_NT; ++nt)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) pacc[nt][c] = 0.f;
-    const uint32_t* wsp = reinterpret_cast<const uint32_t*>(sW);
-    for (int k8 = 0; k8 < D / 8; ++k8) {
-      const uint32_t p0 = f2tf32(p.pad[k8 * 8 + t]), p1 = f2tf32(p.pad[k8 * 8 + t + 4]);
-      const uint32_t a[4] = {p0, p0, p1, p1};
-#pragma unroll
-      for (int nt = 0; nt < UL_NT; ++nt) {
-        const uint32_t* wr = wsp + (nt * 8 + g) * DS + k8 * 8 + t;
-        mma_tf32(pacc[nt], a, wr[0], wr[4]);
-      }
-    }
-    float cp = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < UL_NT; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int col = half * UL_HALF + nt * 8 + 2 * t + e;
-        if (col < Q) cp = fmaf(tanh_exp(pacc[nt][e] + p.b1[col]), p.w2[col], cp);
-      }
-    cp += __shfl_xor_sync(0xffffffffu, cp, 1);
-    cp += __shfl_xor_sync(0xffffffffu, cp, 2);
-    if (lane == 0) atomicAdd(p.c_pad, cp);
+  for (int q = threadIdx.x; q < UL_QT; q += UL_THREADS) {
+    sVec[q] = q < Q ? p.b1[q] : 0.f;
+    sVec[UL_QT + q] = q < Q ? p.w2[q] : 0.f;
+    sVec[2 * UL_QT + q] = BLEND ? p.W1[(size_t)UL_QT * D + q] : 0.f;
   }
-  for (int item = 0; item < n_items; ++item) {
-    const int tl = item / NK, kc = item - tl * NK;
-    const int r0 = (tile0 + tl * tstride) * UL_ROWS;
-    cp_async_wait<1>();                                  // this thread's X pieces of this item
-    __syncthreads();                                     // everyone's pieces; everyone is done with item - 1
-    load(item + 2);
-    if (kc == 0) {
+  tc_fence_before();
+  cluster_sync_all();                                          // barriers of both CTAs initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    // ===================== this CTA's half of W1: one bulk copy of the packed image =====================
+    if (lane == 0 && t_first < n_tiles) {                      // only a pair with work loads (and later waits for) its W1
+      const uint32_t bytes = (uint32_t)NKB * UL_W_KB_BYTES;
+      mbar_expect_tx(w_bar, bytes);
+      bulk_g2s(sW, p.W1 + (size_t)cta_rank * UL_HALF * D, bytes, w_bar);
+    }
+  } else if (warp >= 6) {
+    // ===================== loaders: gather this CTA's 128 rows of every tile, k-block by k-block =====================
+    const int lt = threadIdx.x - 6 * 32;                       // 0..127
+    const int piece = lt & 7, rbase = lt >> 3;                 // 16-byte chunk of the k-block row; rows rbase + 16 i
+    const uint32_t dst_off = (uint32_t)rbase * 128u + (uint32_t)((piece ^ (rbase & 7)) << 4);    // (r & 7) == (rbase & 7)
+    const uint32_t full_remote = mapa_cluster(full_bar(0), 0);
+    const int my_tiles = t_first < n_tiles ? (n_tiles - t_first + t_stride - 1) / t_stride : 0;
+    const int n_items = my_tiles * NKB;
+    const float* xsrc[8];
+    unsigned xok = 0;
+    auto publish = [&](int item) {                             // this warp's copies of `item` have landed
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int st = item % UL_STAGES;
+        if (cta_rank == 0) mbar_arrive(full_bar(st));
+        else mbar_arrive_rel_cluster(full_remote + 8u * st);
+      }
+    };
+    if (n_items > 0) mbar_wait(w_bar, 0);                      // W1 half resident before the first stage is published
+    for (int item = 0; item < n_items; ++item) {
+      const int tl = item / NKB, kb = item - tl * NKB;
+      if (kb == 0) {
+        const int r0 = (t_first + tl * t_stride) * (2 * UL_ROWS) + (int)cta_rank * UL_ROWS;
+        xok = 0;
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
+        for (int i = 0; i < 8; ++i) {
+          const int li = r0 + rbase + 16 * i;
+          const bool ok = li < n_live;
+          size_t src = ok ? (size_t)p.live[li] : 0;
+          if (p.idx != nullptr && ok) {
+            const long long v = p.idx[src];
+            src = (v >= 0 && v < p.n_rows) ? (size_t)v : 0;    // unknown id -> row 0 (dataloader.py:74)
+          }
+          xsrc[i] = p.vecs + src * D + piece * 4;
+          xok |= (ok ? 1u : 0u) << i;
+        }
+      }
+      const int st = item % UL_STAGES;
+      mbar_wait(empty_bar(st), (((uint32_t)(item / UL_STAGES)) & 1u) ^ 1u);
+      const uint32_t dst = sA + (uint32_t)st * UL_A_BYTES + dst_off;
 #pragma unroll
-        for (int nt = 0; nt < UL_NT; ++nt)
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t sz = ((xok >> i) & 1u) ? 16u : 0u;       // rows past the live list: zero fill
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)i * 2048u),
+                     "l"(xsrc[i] + kb * UL_KB), "r"(sz) : "memory");
+      }
+      cp_async_commit();
+      if (item >= UL_LAG) {
+        cp_async_wait<UL_LAG>();
+        publish(item - UL_LAG);
+      }
+    }
+    cp_async_wait<0>();
+    for (int item = (n_items > UL_LAG ? n_items - UL_LAG : 0); item < n_items; ++item) publish(item);
+  } else if (warp == 4) {
+    // ===================== MMA issuer (the pair leader's elected thread) =====================
+    if (lane == 0 && cta_rank == 0) {
+      // D f32, A / B tf32 K-major, N = 208, M = 256 across the pair
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UL_QT >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int item = 0, acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = t_first; t < n_tiles; t += t_stride) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+        for (int kb = 0; kb < NKB; ++kb, ++item) {
+          const int st = item % UL_STAGES;
+          mbar_wait_acq_cluster(full_bar(st), ((uint32_t)(item / UL_STAGES)) & 1u);
+          tc_fence_after();
+          const uint64_t adesc = make_desc_kmajor_sw128(sA + (uint32_t)st * UL_A_BYTES);
+          const uint64_t bdesc = make_desc_kmajor_sw128(sW + (uint32_t)kb * UL_W_KB_BYTES);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
+          for (int k = 0; k < UL_KB / 8; ++k)                  // kind::tf32: K = 8 per instruction, +32 B inside the atom
+            tc_mma_tf32_cta2(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_commit_mc2(empty_bar(st), 3);                     // the stage is free in both CTAs once these MMAs retire
+        }
+        tc_commit_mc2(tfull_bar(acc), 3);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue: a thread owns a row (TMEM lane) =====================
+    const int quarter = warp;                                  // warps 0-3: TMEM lane quarter = warp id % 4
+    const float* sB1 = sVec;
+    const float* sW2 = sVec + UL_QT;
+    const float* sP = sVec + 2 * UL_QT;
+    const uint32_t tempty_remote = mapa_cluster(tempty_bar(0), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = t_first; t < n_tiles; t += t_stride) {
+      const int li = t * (2 * UL_ROWS) + (int)cta_rank * UL_ROWS + quarter * 32 + lane;
+      const int rid = li < n_live ? p.live[li] : -1;
+      float m = 1.f, om = 0.f;
+      if (BLEND && rid >= 0) { m = p.mask[rid]; om = 1.0f - m; }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      float logit = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < UL_QT; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + c0), r);
+        tmem_ld_wait();
+        const int nc = (UL_QT - c0) < 32 ? (UL_QT - c0) : 32;
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int hi = 0; hi < 2; ++hi) {
-          const int li = r0 + warp * 32 + mt * 16 + g + hi * 8;
-          rid[mt][hi] = li < n_live ? p.live[li] : -1;
-          if (BLEND) {
-            rm[mt][hi] = rid[mt][hi] >= 0 ? p.mask[rid[mt][hi]] : 0.f;
-            rom[mt][hi] = 1.0f - rm[mt][hi];
+        for (int j = 0; j < 32; ++j) {
+          if (j < nc) {
+            float v = __uint_as_float(r[j]);
+            if (BLEND) v = fmaf(m, v, om * sP[c0 + j]);        // W1 (m x + (1 - m) pad) = m (W1 x) + (1 - m) (W1 pad)
+            logit = fmaf(tanh_exp(v + sB1[c0 + j]), sW2[c0 + j], logit);
           }
         }
-    }
-    const float* xs = sX + (item % UL_STAGES) * UL_ROWS * UL_XS;
-    const uint32_t* ws = reinterpret_cast<const uint32_t*>(sW) + kc * UL_KC;
-#pragma unroll
-    for (int k8 = 0; k8 < UL_KC / 8; ++k8) {
-      uint32_t a[2][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const float* r = xs + (warp * 32 + mt * 16 + g) * UL_XS + k8 * 8 + t;
-        float x0 = r[0], x1 = r[8 * UL_XS], x2 = r[4], x3 = r[8 * UL_XS + 4];
-        if (BLEND) {
-          const float p0 = sPad[kc * UL_KC + k8 * 8 + t], p1 = sPad[kc * UL_KC + k8 * 8 + t + 4];
-          x0 = x0 * rm[mt][0] + p0 * rom[mt][0]; x1 = x1 * rm[mt][1] + p0 * rom[mt][1];
-          x2 = x2 * rm[mt][0] + p1 * rom[mt][0]; x3 = x3 * rm[mt][1] + p1 * rom[mt][1];
-        }
-        a[mt][0] = f2tf32(x0); a[mt][1] = f2tf32(x1); a[mt][2] = f2tf32(x2); a[mt][3] = f2tf32(x3);
       }
-#pragma unroll
-      for (int nt = 0; nt < UL_NT; ++nt) {
-        const uint32_t* wr = ws + (nt * 8 + g) * DS + k8 * 8 + t;
-        const uint32_t b0 = wr[0], b1 = wr[4];
-        mma_tf32(acc[0][nt], a[0], b0, b1);
-        mma_tf32(acc[1][nt], a[1], b0, b1);
-      }
-    }
-    if (kc == NK - 1) {
-      // tile epilogue: this thread's 4 rows over its 26 columns, then the t-quad, then the other column half (atomic)
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int hi = 0; hi < 2; ++hi) {
-          float part = 0.f;
-#pragma unroll
-          for (int nt = 0; nt < UL_NT; ++nt)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int col = nt * 8 + 2 * t + e;
-              part = fmaf(tanh_exp(acc[mt][nt][hi * 2 + e] + sB1[col]), sW2[col], part);
-            }
-          part += __shfl_xor_sync(0xffffffffu, part, 1);
-          part += __shfl_xor_sync(0xffffffffu, part, 2);
-          if (t == 0 && rid[mt][hi] >= 0) atomicAdd(p.logits + rid[mt][hi], part);
-        }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_remote + 8u * acc);      // this warp is done with the accumulator stage
+      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      if (rid >= 0) p.logits[rid] = logit;
     }
   }
-  cp_async_wait<0>();
+
+  tc_fence_before();
+  cluster_sync_all();                    // the leader's MMAs also write the peer's TMEM; remote arrives target live CTAs
+  if (warp == 5)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(UL_TMEM_COLS) : "memory");
 }
 
 constexpr int UP_WARPS = 4;
@@ -1012,23 +1044,44 @@ TNR_API int tnr_user_encoder_fwd(const float* vecs, const float* mask, const flo
 // ---- scoring path: flat logits GEMM + per-impression pooling (see ue_logits_kernel) -------------------
 static int ue_score_check(const char* who, int H, int D, int Q) {
   TNR_REQUIRE(H >= 1 && H <= UE_HMAX, "%s: history length %d not supported (1..%d)", who, H, UE_HMAX);
-  TNR_REQUIRE(D % UL_KC == 0 && D >= UL_KC && D <= UL_DMAX, "%s: D=%d must be a multiple of %d in %d..%d", who, D, UL_KC, UL_KC, UL_DMAX);
+  TNR_REQUIRE(D % UL_KB == 0 && D >= UL_KB && D <= UL_DMAX, "%s: D=%d must be a multiple of %d in %d..%d", who, D, UL_KB, UL_KB, UL_DMAX);
   TNR_REQUIRE(Q >= 1 && Q <= UL_QT, "%s: query dim %d not supported (1..%d)", who, Q, UL_QT);
   return 0;
 }
 
-TNR_API long long tnr_user_encoder_packed_w1_floats(int D) { return (long long)UL_QT * (D + 4); }
+TNR_API long long tnr_user_encoder_packed_w1_floats(int D) { return ul_packed_floats(D); }
 
-TNR_API int tnr_user_encoder_pack_w1(const float* W1, float* packed, int D, int Q, void* stream) {
+TNR_API int tnr_user_encoder_pack_w1(const float* W1, const float* pad_doc, const float* b1, const float* w2, float* packed,
+                                     int D, int Q, void* stream) {
   if (ue_score_check("tnr_user_encoder_pack_w1", 1, D, Q)) return 1;
   TNR_REQUIRE((uintptr_t)packed % 16 == 0, "tnr_user_encoder_pack_w1: packed must be 16-byte aligned");
-  const int total = UL_QT * (D + 4);
-  ue_pack_w1_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(W1, packed, D, Q);
+  TNR_REQUIRE(W1 != nullptr && pad_doc != nullptr && b1 != nullptr && w2 != nullptr, "tnr_user_encoder_pack_w1: null parameter");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int total = UL_QT * D;
+  ue_pack_w1_kernel<<<(total + 255) / 256, 256, 0, st>>>(W1, packed, D, Q);
+  TNR_LAUNCH_CHECK();
+  ue_pack_pad_kernel<<<1, 256, 0, st>>>(W1, pad_doc, b1, w2, packed, D, Q);
   TNR_LAUNCH_CHECK();
   return 0;
 }
 
 TNR_API long long tnr_user_encoder_score_ws_bytes(int B, int H) { return ((long long)B * H + 4) * 4; }
+
+template <bool BLEND>
+static int ue_logits_launch(const UlParams& p, int pairs, int smem, cudaStream_t st) {
+  TNR_SET_SMEM(ue_logits_kernel<BLEND>, ul_smem_bytes(UL_DMAX));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(UL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  TNR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ue_logits_kernel<BLEND>, p));
+  return 0;
+}
 
 TNR_API int tnr_user_encoder_score(const float* vecs, long long n_rows, const int32_t* idx, const float* mask,
                                    const float* pad_doc, const float* w1_packed, const float* b1, const float* w2,
@@ -1040,35 +1093,29 @@ TNR_API int tnr_user_encoder_score(const float* vecs, long long n_rows, const in
   TNR_REQUIRE(workspace != nullptr && (uintptr_t)workspace % 16 == 0,
               "tnr_user_encoder_score: workspace of tnr_user_encoder_score_ws_bytes(B, H) bytes required");
   TNR_REQUIRE(idx == nullptr || n_rows >= 1, "tnr_user_encoder_score: empty table");
+  TNR_REQUIRE((uintptr_t)vecs % 16 == 0, "tnr_user_encoder_score: rows must be 16-byte aligned");
   if (B == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int R = B * H;
-  // workspace: [0] n_live (int32), [1] c_pad (float), [4 ..] the live row list
+  // workspace: [0] n_live (int32), [4 ..] the live row list
   int32_t* wsi = reinterpret_cast<int32_t*>(workspace);
   TNR_CHECK_CUDA(cudaMemsetAsync(wsi, 0, 16, st));
-  TNR_CHECK_CUDA(cudaMemsetAsync(a_out, 0, (size_t)R * sizeof(float), st));       // the two column halves add into it
   ue_compact_kernel<<<(R + 255) / 256, 256, 0, st>>>(mask, R, wsi + 4, wsi);
   TNR_LAUNCH_CHECK();
   UlParams p;
-  p.vecs = vecs; p.idx = idx; p.n_rows = n_rows; p.mask = mask; p.pad = pad_doc; p.W1 = w1_packed; p.b1 = b1; p.w2 = w2;
-  p.logits = a_out; p.live = wsi + 4; p.n_live = wsi; p.c_pad = reinterpret_cast<float*>(wsi + 1);
+  p.vecs = vecs; p.idx = idx; p.n_rows = n_rows; p.mask = mask; p.W1 = w1_packed; p.b1 = b1; p.w2 = w2;
+  p.logits = a_out; p.live = wsi + 4; p.n_live = wsi;
   p.R = R; p.D = D; p.Q = Q;
-  const int smem = (UL_HALF * (D + 4) + UL_STAGES * UL_ROWS * UL_XS + 2 * UL_HALF + D) * 4;
-  const int max_smem = (UL_HALF * (UL_DMAX + 4) + UL_STAGES * UL_ROWS * UL_XS + 2 * UL_HALF + UL_DMAX) * 4;
-  TNR_SET_SMEM(ue_logits_kernel<true>, max_smem);
-  TNR_SET_SMEM(ue_logits_kernel<false>, max_smem);
-  const int n_tiles = (R + UL_ROWS - 1) / UL_ROWS;        // upper bound: the live count is only known on the device
+  const int smem = ul_smem_bytes(D);
+  const int n_tiles = (R + 2 * UL_ROWS - 1) / (2 * UL_ROWS);      // upper bound: the live count is only known on the device
   const int pairs = n_tiles < num_sms() / 2 ? n_tiles : num_sms() / 2;
-  const int grid = 2 * pairs;
   const int pgrid = (B + UP_WARPS - 1) / UP_WARPS;
-  const float* c_pad = reinterpret_cast<const float*>(wsi + 1);
+  const float* c_pad = w1_packed + (size_t)UL_QT * D + UL_QT;    // logit of a pad_doc row (ue_pack_pad_kernel)
   if (use_mask) {
-    ue_logits_kernel<false><<<grid, UL_THREADS, smem, st>>>(p);
-    TNR_LAUNCH_CHECK();
+    if (ue_logits_launch<false>(p, pairs, smem, st)) return 2;
     ue_pool_launch<false>(pgrid, st, vecs, idx, n_rows, mask, pad_doc, b2, c_pad, 1, a_out, user, B, H, D);
   } else {
-    ue_logits_kernel<true><<<grid, UL_THREADS, smem, st>>>(p);
-    TNR_LAUNCH_CHECK();
+    if (ue_logits_launch<true>(p, pairs, smem, st)) return 2;
     ue_pool_launch<true>(pgrid, st, vecs, idx, n_rows, mask, pad_doc, b2, c_pad, 0, a_out, user, B, H, D);
   }
   TNR_LAUNCH_CHECK();

@@ -261,12 +261,15 @@ class UserEncoder(nn.Module):
         self.pad_doc = nn.Parameter(torch.empty(1, args.news_dim).uniform_(-1, 1))
 
     def _packed_w1(self):
-        """Packed TF32 copy of att_fc1.weight for the scoring kernels, re-packed when the parameter changes."""
-        w = self.attn.att_fc1.weight
-        key = (w.data_ptr(), w._version, w.device, ops.param_generation)
+        """Packed TF32 image of att_fc1.weight (+ W1 pad_doc and the pad_doc logit) for the scoring kernels,
+        re-packed when any of the parameters it is made from changes."""
+        at = self.attn
+        src = (at.att_fc1.weight, self.pad_doc, at.att_fc1.bias, at.att_fc2.weight)
+        key = tuple((t.data_ptr(), t._version) for t in src) + (src[0].device, ops.param_generation)
         c = getattr(self, "_w1_pack", None)
         if c is None or c[0] != key:
-            c = (key, ops.user_encoder_pack_w1(w.detach()))
+            c = (key, ops.user_encoder_pack_w1(src[0].detach(), src[1].detach().view(-1), src[2].detach(),
+                                               src[3].detach().view(-1)))
             object.__setattr__(self, "_w1_pack", c)
         return c[1]
 

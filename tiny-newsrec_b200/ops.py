@@ -325,14 +325,18 @@ def user_encoder_score_supported(B, H, D, Q):
     return B >= 64 and H <= 64 and D % 32 == 0 and D <= 256 and Q <= 208
 
 
-def user_encoder_pack_w1(W1, packed=None):
-    """att_fc1.weight fp32 [Q, D] -> the packed, TF32-rounded, chunk-major copy tnr_user_encoder_score reads."""
-    lib = _ready(W1)
+def user_encoder_pack_w1(W1, pad_doc, b1, w2, packed=None):
+    """att_fc1.weight fp32 [Q, D] (+ pad_doc [D], att_fc1.bias [Q], att_fc2.weight [Q]) -> the packed image
+    tnr_user_encoder_score reads: W1 TF32-rounded in the swizzled shared-memory layout, W1 pad_doc, the pad_doc logit."""
+    lib = _ready(W1, 2)
     Q, D = W1.shape
     n = int(lib.tnr_user_encoder_packed_w1_floats(D))
     if packed is None or packed.numel() != n:
         packed = torch.empty(n, device=W1.device, dtype=_f32)
-    _lib.check(lib.tnr_user_encoder_pack_w1(_ptr(_chk(W1.contiguous(), _f32, "pack_w1.W1")), _ptr(packed), D, Q, _stream()),
+    for t, nm in ((W1, "W1"), (pad_doc, "pad_doc"), (b1, "b1"), (w2, "w2")):
+        _chk(t, _f32, "pack_w1." + nm)
+    _lib.check(lib.tnr_user_encoder_pack_w1(_ptr(W1.contiguous()), _ptr(pad_doc.contiguous()), _ptr(b1.contiguous()),
+                                            _ptr(w2.contiguous()), _ptr(packed), D, Q, _stream()),
                "tnr_user_encoder_pack_w1")
     return packed
 

@@ -34,7 +34,7 @@ def main():
     b1, w2, b2 = torch.randn(Q, device="cuda", generator=g) * 0.1, torch.randn(Q, device="cuda", generator=g) * 0.1, torch.zeros(1, device="cuda")
     user, a = torch.empty(B, D, device="cuda"), torch.empty(B, H, device="cuda")
     vecs = torch.empty(B * H, D, device="cuda")
-    wp = ops.user_encoder_pack_w1(W1)
+    wp = ops.user_encoder_pack_w1(W1, pad, b1, w2)
     for um in (False, True):
         print(f"use_mask={um}")
         print("  score, random gather      %8.1f us" % timed(lambda: ops.user_encoder_score(table, idx, mask, pad, wp, Q, b1, w2, b2, um, user, a, B, H)))
