@@ -687,13 +687,17 @@ def test_scoring_path_sees_parameters_updated_by_the_fused_adam(golden):
     m(*inputs)[0].backward()
     opt.step()
     u_after = ue(vecs, mask)
-    assert _rel(u_after, u_before) > 1e-4             # the weights moved
+    moved = _rel(u_after, u_before)
+    assert moved > 1e-3                               # the weights moved
     at = ue.attn
     ref = torch.empty(B, D, device="cuda")
     a = torch.empty(B, H, device="cuda")
     ops.user_encoder_fwd(vecs.view(B * H, D), mask, ue.pad_doc.view(-1), at.att_fc1.weight, at.att_fc1.bias,
                          at.att_fc2.weight.view(-1), at.att_fc2.bias, False, ref, a, None, B, H)
-    assert _rel(u_after, ref) < 1e-5
+    # the scoring GEMM truncates the history rows to TF32 (tcgen05 kind::tf32), the per-impression kernel rounds them:
+    # ~1e-4 between the two, far below the movement a stale packed copy would leave
+    err = _rel(u_after, ref)
+    assert err < 5e-4 and moved > 5 * err, (err, moved)
 
 
 def test_graphed_train_step_advances_dropout_seed_and_trains():
