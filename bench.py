@@ -447,6 +447,31 @@ def run_tinyrec(a):
     eager_ms = r0.elapsed_time(r1) / n_roof
     gemm_events, ops.stats.gemm_events = ops.stats.gemm_events, None
 
+    # ---- N > 1: CUDA-event timeline of the gradient exchange over eagerly launched steps (where each bucket's
+    # all-reduce starts and ends relative to the end of the backward; "exposed" = what the optimizer waits for)
+    comm = None
+    if world > 1 and hasattr(opt, "trace"):
+        opt.trace = []
+        for i in range(12):
+            step(dev_batches[i % N_BATCHES])
+        barrier()
+        tr, opt.trace = opt.trace[2:], None
+        med = lambda xs: float(np.median(xs)) if len(xs) else None  # noqa: E731
+        nb = min(len(t.get("buckets", [])) for t in tr)
+        buckets = []
+        for j in range(nb):
+            b0 = tr[0]["buckets"][j]
+            buckets.append({"mbytes": (b0["hi"] - b0["lo"]) * 4 / 1e6,
+                            "ready_ms_before_backward_end": med([t["buckets"][j]["ready"].elapsed_time(t["backward_end"]) for t in tr]),
+                            "start_ms_before_backward_end": med([t["buckets"][j]["start"].elapsed_time(t["backward_end"]) for t in tr]),
+                            "duration_ms": med([t["buckets"][j]["start"].elapsed_time(t["buckets"][j]["done"]) for t in tr]),
+                            "done_ms_after_backward_end": med([t["backward_end"].elapsed_time(t["buckets"][j]["done"]) for t in tr])})
+        comm = {"steps": len(tr), "launch": "eager", "step_ms": med([t["t0"].elapsed_time(t["step_end"]) for t in tr]),
+                "backward_end_to_step_end_ms": med([t["backward_end"].elapsed_time(t["step_end"]) for t in tr]),
+                "exposed_ms": med([max(0.0, max(t["backward_end"].elapsed_time(b["done"]) for b in t["buckets"])) for t in tr]),
+                "sm_reserve": getattr(opt, "sm_reserve", 0), "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"),
+                "buckets": buckets}
+
     if rank == 0:
         peak_tf, peak_bw, how = peaks()
         gflop = sum(f for f, _, _ in gemm_events)
@@ -465,6 +490,7 @@ def run_tinyrec(a):
                         "what": "pinned host index arrays (hist_idx, hist_mask, cand_idx, label) in, loader row gathers + "
                                 "train step on the device, loss read back"},
                 "e2e_preassembled": e2e_pre,
+                "comm_timeline": comm,
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "kernel": "tnr::gemm::gemm_kernel (tcgen05, all GEMM launches of the step)",
                              "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,

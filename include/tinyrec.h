@@ -40,6 +40,9 @@ int tnr_device_check(int* num_sms);
  * exchange, Tiny-NewsRec/run.py:144-149): a persistent one-CTA-per-SM GEMM whose grid covers every SM makes the
  * collective's CTAs wait for a whole GEMM, and the GEMM CTAs displaced by them then run as a second wave. */
 int tnr_set_sm_reserve(int n_sms);
+/* Host staging copy of the loaders: dst (pinned) <- src (pageable), split over up to n_threads host threads (1..16).
+ * No CUDA call inside.  The job of the reference loader's producer thread (Tiny-NewsRec/dataloader.py:303-314). */
+int tnr_host_copy_mt(void* dst, const void* src, long long bytes, int n_threads);
 
 /* ------------------------------------------------------------------ dropout */
 /* Training-mode dropout (the reference trains with dropout 0.1 active: run.py never calls

@@ -391,9 +391,12 @@ user_encoder_fwd_kernel(const __grid_constant__ UeFwdParams p) {
 //       every history row is fetched from HBM / L2 once, by the CTA that owns it.  The rows are GATHERED by index from
 //       the news table (dataloader.py:295 fused): four loader warps per CTA issue 16-byte cp.async copies straight into
 //       the 128B-swizzled K-major layout the MMA descriptors read (chunk c of row r lands at r * 128 + ((c ^ (r & 7))
-//       << 4) of a 32-float k-block), a 6-stage ring of 16 KB k-blocks that runs on across tiles; a stage is published
-//       to the pair leader's mbarrier after cp.async.wait_group + fence.proxy.async (the peer CTA's warps arrive
-//       remotely, release.cluster).  One elected thread of the leader issues the MMAs and multicasts the stage-free /
+//       << 4) of a 32-float k-block), a 6-stage ring of 16 KB k-blocks that runs on across tiles.  No thread ever waits
+//       for its copies: each loader thread posts cp.async.mbarrier.arrive.noinc on the stage's "landed" barrier, which
+//       fires when its copies have landed (a wait_group + fence + arrive per stage made the fence wait for EVERY copy
+//       in flight -- MEMBAR.ALL.CTA at 13 % of the stall samples, 77 us); the peer CTA's landed barriers are forwarded
+//       to the leader by one relay thread (release.cluster), and the next tile's row indices are looked up one tile
+//       ahead.  One elected thread of the leader issues the MMAs and multicasts the stage-free /
 //       accumulator-ready commits to both CTAs.  Epilogue: a thread owns a row (a TMEM lane), reads its 208
 //       accumulators 32 columns at a time (tcgen05.ld.32x32b.x32), applies + b1, tanh, . w2 in registers and writes
 //       the logit -- no atomics, no cross-lane reduction.  pad_doc branch: W1 (m v + (1 - m) pad) = m (W1 v) +
@@ -408,14 +411,14 @@ user_encoder_fwd_kernel(const __grid_constant__ UeFwdParams p) {
 constexpr int UL_ROWS = 128;                       // rows per CTA and tile (256 per pair)
 constexpr int UL_KB = 32;                          // floats per k-block: 128 B, one swizzle row
 constexpr int UL_QT = 208, UL_HALF = UL_QT / 2;    // padded query dim (UMMA N) and the W1 rows one CTA holds
-constexpr int UL_STAGES = 6, UL_LAG = 3;           // A ring depth; stages in flight before the oldest is published
+constexpr int UL_STAGES = 6;                       // A ring depth (k-blocks of 16 KB)
 constexpr int UL_DMAX = 256;
 constexpr int UL_A_BYTES = UL_ROWS * 128;          // one k-block of the A tile: 16 KB
 constexpr int UL_W_KB_BYTES = UL_HALF * 128;       // one k-block of a W1 half: 13 KB (13 swizzle atoms)
 constexpr int UL_EPI_WARPS = 4, UL_LOAD_WARPS = 4;
 constexpr int UL_THREADS = 32 * (UL_EPI_WARPS + 2 + UL_LOAD_WARPS);      // epilogue 0-3, MMA 4, TMEM / W1 5, loaders 6-9
 constexpr int UL_TMEM_COLS = 512;                  // two accumulator stages of 256 columns (208 used)
-constexpr int UL_NBARS = 2 * UL_STAGES + 5;
+constexpr int UL_NBARS = 3 * UL_STAGES + 5;
 
 __host__ __device__ constexpr int ul_smem_bytes(int D) {
   return (D / UL_KB) * UL_W_KB_BYTES + UL_STAGES * UL_A_BYTES + 3 * UL_QT * 4 + UL_NBARS * 8 + 16 + 1024 /*align slack*/;
@@ -498,11 +501,12 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
   const uint32_t sA = sW + (uint32_t)NKB * UL_W_KB_BYTES;
   float* sVec = reinterpret_cast<float*>(smem_gen + NKB * UL_W_KB_BYTES + UL_STAGES * UL_A_BYTES);
   const uint32_t bar_base = sA + UL_STAGES * UL_A_BYTES + 3 * UL_QT * 4;
-  auto full_bar = [&](int st) { return bar_base + 8u * st; };                       // leader: both CTAs' loader warps
-  auto empty_bar = [&](int st) { return bar_base + 8u * (UL_STAGES + st); };         // each CTA: MMA commit (multicast)
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * UL_STAGES + a); };       // each CTA: MMA commit (multicast)
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * UL_STAGES + 2 + a); };  // leader: both CTAs' epilogue warps
-  const uint32_t w_bar = bar_base + 8u * (2 * UL_STAGES + 4);                        // each CTA: its W1 half landed
+  auto landed_bar = [&](int st) { return bar_base + 8u * st; };                      // each CTA: its 128 loader threads' copies
+  auto peer_bar = [&](int st) { return bar_base + 8u * (UL_STAGES + st); };           // leader: "the peer's stage landed"
+  auto empty_bar = [&](int st) { return bar_base + 8u * (2 * UL_STAGES + st); };      // each CTA: MMA commit (multicast)
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * UL_STAGES + a); };        // each CTA: MMA commit (multicast)
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * UL_STAGES + 2 + a); };   // leader: both CTAs' epilogue warps
+  const uint32_t w_bar = bar_base + 8u * (3 * UL_STAGES + 4);                         // each CTA: its W1 half landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + NKB * UL_W_KB_BYTES + UL_STAGES * UL_A_BYTES +
                                                     3 * UL_QT * 4 + UL_NBARS * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -512,7 +516,11 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
   const int t_first = (int)(blockIdx.x >> 1), t_stride = (int)(gridDim.x >> 1);
 
   if (warp == 4 && lane == 0) {
-    for (int st = 0; st < UL_STAGES; ++st) { mbar_init(full_bar(st), 2 * UL_LOAD_WARPS); mbar_init(empty_bar(st), 1); }
+    for (int st = 0; st < UL_STAGES; ++st) {
+      mbar_init(landed_bar(st), UL_LOAD_WARPS * 32);
+      mbar_init(peer_bar(st), 1);
+      mbar_init(empty_bar(st), 1);
+    }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * UL_EPI_WARPS); }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -533,50 +541,75 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 5) {
-    // ===================== this CTA's half of W1: one bulk copy of the packed image =====================
+    // ===================== this CTA's half of W1: one bulk copy of the packed image; the PEER's relay =====================
     if (lane == 0 && t_first < n_tiles) {                      // only a pair with work loads (and later waits for) its W1
       const uint32_t bytes = (uint32_t)NKB * UL_W_KB_BYTES;
       mbar_expect_tx(w_bar, bytes);
       bulk_g2s(sW, p.W1 + (size_t)cta_rank * UL_HALF * D, bytes, w_bar);
+      if (cta_rank != 0) {
+        // The leader's MMA thread cannot wait on this CTA's barriers: forward "stage landed here" (and, before the
+        // first one, "W1 half landed here") to the leader's peer_bar.  This thread has no memory operations of its
+        // own in flight, so the release.cluster arrive costs it nothing but latency.
+        const int my_tiles = (n_tiles - t_first + t_stride - 1) / t_stride;
+        const int n_items = my_tiles * NKB;
+        const uint32_t peer_remote = mapa_cluster(peer_bar(0), 0);
+        mbar_wait(w_bar, 0);
+        for (int item = 0; item < n_items; ++item) {
+          const int st = item % UL_STAGES;
+          mbar_wait(landed_bar(st), ((uint32_t)(item / UL_STAGES)) & 1u);
+          fence_proxy_async_smem();                            // cp.async (generic proxy) writes -> the MMA's async-proxy reads
+          mbar_arrive_rel_cluster(peer_remote + 8u * st);
+        }
+      }
     }
   } else if (warp >= 6) {
     // ===================== loaders: gather this CTA's 128 rows of every tile, k-block by k-block =====================
     const int lt = threadIdx.x - 6 * 32;                       // 0..127
     const int piece = lt & 7, rbase = lt >> 3;                 // 16-byte chunk of the k-block row; rows rbase + 16 i
     const uint32_t dst_off = (uint32_t)rbase * 128u + (uint32_t)((piece ^ (rbase & 7)) << 4);    // (r & 7) == (rbase & 7)
-    const uint32_t full_remote = mapa_cluster(full_bar(0), 0);
     const int my_tiles = t_first < n_tiles ? (n_tiles - t_first + t_stride - 1) / t_stride : 0;
     const int n_items = my_tiles * NKB;
     const float* xsrc[8];
     unsigned xok = 0;
-    auto publish = [&](int item) {                             // this warp's copies of `item` have landed
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        const int st = item % UL_STAGES;
-        if (cta_rank == 0) mbar_arrive(full_bar(st));
-        else mbar_arrive_rel_cluster(full_remote + 8u * st);
+    // The next tile's rows are looked up while this tile streams: live[] ids at k-block 0, idx[] rows a few k-blocks
+    // later, pointers after that -- two DEPENDENT index loads per row that would otherwise sit between two tiles.
+    int nlive[8];
+    long long nrow[8];
+    unsigned nok = 0;
+    auto look_a = [&](int tl) {                                 // live-list ids of tile tl
+      const int r0 = (t_first + tl * t_stride) * (2 * UL_ROWS) + (int)cta_rank * UL_ROWS;
+      nok = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int li = r0 + rbase + 16 * i;
+        const bool ok = tl < my_tiles && li < n_live;
+        nlive[i] = ok ? p.live[li] : 0;
+        nok |= (ok ? 1u : 0u) << i;
       }
     };
-    if (n_items > 0) mbar_wait(w_bar, 0);                      // W1 half resident before the first stage is published
+    auto look_b = [&]() {                                       // table rows
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        long long v = nlive[i];
+        if (p.idx != nullptr && ((nok >> i) & 1u)) v = p.idx[nlive[i]];
+        nrow[i] = v;
+      }
+    };
+    auto look_c = [&]() {                                       // pointers; unknown id -> row 0 (dataloader.py:74)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long v = nrow[i];
+        const size_t src = (p.idx == nullptr || (v >= 0 && v < p.n_rows)) ? (size_t)v : 0;
+        xsrc[i] = p.vecs + src * D + piece * 4;
+      }
+      xok = nok;
+    };
+    const int kb_b = (3 * NKB) / 8, kb_c = (6 * NKB) / 8;
+    if (n_items > 0) { look_a(0); look_b(); }
     for (int item = 0; item < n_items; ++item) {
       const int tl = item / NKB, kb = item - tl * NKB;
-      if (kb == 0) {
-        const int r0 = (t_first + tl * t_stride) * (2 * UL_ROWS) + (int)cta_rank * UL_ROWS;
-        xok = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int li = r0 + rbase + 16 * i;
-          const bool ok = li < n_live;
-          size_t src = ok ? (size_t)p.live[li] : 0;
-          if (p.idx != nullptr && ok) {
-            const long long v = p.idx[src];
-            src = (v >= 0 && v < p.n_rows) ? (size_t)v : 0;    // unknown id -> row 0 (dataloader.py:74)
-          }
-          xsrc[i] = p.vecs + src * D + piece * 4;
-          xok |= (ok ? 1u : 0u) << i;
-        }
-      }
+      if (kb == 0) { look_c(); look_a(tl + 1); }
+      if (kb == kb_b) look_b();
       const int st = item % UL_STAGES;
       mbar_wait(empty_bar(st), (((uint32_t)(item / UL_STAGES)) & 1u) ^ 1u);
       const uint32_t dst = sA + (uint32_t)st * UL_A_BYTES + dst_off;
@@ -586,14 +619,10 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)i * 2048u),
                      "l"(xsrc[i] + kb * UL_KB), "r"(sz) : "memory");
       }
-      cp_async_commit();
-      if (item >= UL_LAG) {
-        cp_async_wait<UL_LAG>();
-        publish(item - UL_LAG);
-      }
+      // this thread's arrival on landed[st] fires when its copies above have landed: nothing here waits for them
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(landed_bar(st)) : "memory");
     }
-    cp_async_wait<0>();
-    for (int item = (n_items > UL_LAG ? n_items - UL_LAG : 0); item < n_items; ++item) publish(item);
+    (void)kb_c;
   } else if (warp == 4) {
     // ===================== MMA issuer (the pair leader's elected thread) =====================
     if (lane == 0 && cta_rank == 0) {
@@ -601,13 +630,17 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UL_QT >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int item = 0, acc = 0;
       uint32_t acc_phase = 0;
+      if (t_first < n_tiles) mbar_wait(w_bar, 0);              // this CTA's W1 half (the peer's comes with its first stage)
       for (int t = t_first; t < n_tiles; t += t_stride) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
         for (int kb = 0; kb < NKB; ++kb, ++item) {
           const int st = item % UL_STAGES;
-          mbar_wait_acq_cluster(full_bar(st), ((uint32_t)(item / UL_STAGES)) & 1u);
+          const uint32_t par = ((uint32_t)(item / UL_STAGES)) & 1u;
+          mbar_wait(landed_bar(st), par);                      // this CTA's 128 rows of the k-block
+          mbar_wait_acq_cluster(peer_bar(st), par);            // the peer's
+          fence_proxy_async_smem();
           tc_fence_after();
           const uint64_t adesc = make_desc_kmajor_sw128(sA + (uint32_t)st * UL_A_BYTES);
           const uint64_t bdesc = make_desc_kmajor_sw128(sW + (uint32_t)kb * UL_W_KB_BYTES);

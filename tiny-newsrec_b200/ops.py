@@ -523,6 +523,20 @@ def adam_amsgrad_devstep(p, g, m, v, vmax, shadow, lr, beta1, beta2, eps, step_d
                "tnr_adam_amsgrad_devstep")
 
 
+def host_copy(dst, src, n_threads=4):
+    """dst: CPU tensor (pinned staging) <- src: C-contiguous numpy array of the same dtype, element for element into
+    dst's first src.size elements; the bytes are split over ``n_threads`` host threads (tnr_host_copy_mt; the GIL is
+    released for the call)."""
+    import numpy as np
+    src = np.ascontiguousarray(src)
+    nbytes = src.size * src.itemsize
+    if dst.is_cuda or not dst.is_contiguous() or dst.numel() * dst.element_size() < nbytes or dst.element_size() != src.itemsize:
+        raise _lib.TinyRecError("host_copy: dst must be a contiguous CPU tensor of the source's element size, large enough")
+    _lib.check(_lib.load().tnr_host_copy_mt(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(src.ctypes.data), nbytes,
+                                            int(n_threads)), "tnr_host_copy_mt")
+    return dst
+
+
 def set_sm_reserve(n_sms, device=None):
     """SMs the persistent GEMM grids leave free on ``device`` from now on (0 = all SMs): tnr_set_sm_reserve."""
     lib = _lib.load()

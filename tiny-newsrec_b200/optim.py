@@ -150,6 +150,7 @@ class DistributedOptimizer:
             sm_reserve = int(os.environ.get("TNR_COMM_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "0")) or 0)
         self.sm_reserve = (sm_reserve + 1) // 2 * 2 if self.stream is not None else 0
         self.reserved = False
+        self.trace = None           # list -> per step a dict of CUDA events (bench.py --gpus N: comm timeline)
         if self.stream is not None:
             self.opt.model.train_state().comm_hook = self._launch
 
@@ -158,19 +159,42 @@ class DistributedOptimizer:
         if self.sm_reserve and not self.reserved:
             ops.set_sm_reserve(self.sm_reserve)         # GEMMs enqueued from here to step() leave room for the collective
             self.reserved = True
-        ev = torch.cuda.Event()
+        timed = self.trace is not None
+        ev = torch.cuda.Event(enable_timing=timed)
         ev.record()
         self.stream.wait_event(ev)
         with torch.cuda.stream(self.stream):
+            start = None
+            if timed:
+                start = torch.cuda.Event(enable_timing=True)
+                start.record()
             dist.all_reduce(flat.grad[lo:hi], op=dist.ReduceOp.SUM)
-            done = torch.cuda.Event()
+            done = torch.cuda.Event(enable_timing=timed)
             done.record()
         self.pending.append((lo, hi, done))
+        if timed:
+            self._cur.setdefault("buckets", []).append(dict(lo=lo, hi=hi, ready=ev, start=start, done=done))
 
     def zero_grad(self, set_to_none=False):
+        if self.trace is not None:          # a step starts here (run.py:193)
+            self._cur = dict(t0=torch.cuda.Event(enable_timing=True))
+            self._cur["t0"].record()
         self.opt.zero_grad()
 
+    def _mark(self, name):
+        if self.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._cur[name] = ev
+
     def step(self):
+        self._mark("backward_end")
+        self._step()
+        self._mark("step_end")
+        if self.trace is not None:
+            self.trace.append(self._cur)
+
+    def _step(self):
         if self.world > 1:
             if self.stream is not None and self.pending:
                 if self.reserved:

@@ -391,8 +391,27 @@ def build_news_table(news_encoder, news_combined, batch_size=2048, device=None, 
     return par.allgather_rows(out, n) if world > 1 else out
 
 
+_EVAL_STAGING = {}
+
+
+def _eval_staging(device, bs, H, nnz_max, n_slots):
+    """Pinned + device staging slots of ``evaluate`` (cached per device, grown on demand) -> (slots, copy stream,
+    per-impression metric buffer)."""
+    need = (bs * H, bs * H, bs + 1, nnz_max, nnz_max)
+    dts = (torch.int32, torch.float32, torch.int64, torch.int32, torch.int8)
+    c = _EVAL_STAGING.get(device)
+    if c is None or len(c["slots"]) < n_slots or any(a < b for a, b in zip(c["cap"], need)) or c["per"].shape[0] < bs:
+        cap = tuple(max(int(m * 1.25) + 16, 1) for m in need)
+        slots = [dict(pin=[torch.empty(m, dtype=dt, pin_memory=True) for m, dt in zip(cap, dts)],
+                      dev=[torch.empty(m, dtype=dt, device=device) for m, dt in zip(cap, dts)], done=None)
+                 for _ in range(n_slots)]
+        c = _EVAL_STAGING[device] = dict(slots=slots, cap=cap, stream=torch.cuda.Stream(device=device),
+                                         per=torch.empty(max(bs, 1), 5, device=device, dtype=torch.float64))
+    return c["slots"][:n_slots], c["stream"], c["per"]
+
+
 @torch.no_grad()
-def evaluate(user_encoder, news_scoring, hist_idx, hist_mask, cand_ptr, cand_idx, labels, batch_size=4096,
+def evaluate(user_encoder, news_scoring, hist_idx, hist_mask, cand_ptr, cand_idx, labels, batch_size=16384,
              return_per_impression=False):
     """run.py:301-379 on the device.  Impressions are CSR-packed: ``cand_ptr`` int64 [n+1],
     ``cand_idx`` int32 [nnz], ``labels`` int8 [nnz]; rank r scores impressions r-th contiguous slice.
@@ -408,11 +427,12 @@ def evaluate(user_encoder, news_scoring, hist_idx, hist_mask, cand_ptr, cand_idx
     ptr_h = np.asarray(cand_ptr)
     hist_idx, hist_mask = np.asarray(hist_idx), np.asarray(hist_mask)
     cand_idx, labels = np.asarray(cand_idx), np.asarray(labels)
-    # Index batches go host -> pinned staging -> device on a copy stream, ahead of the scoring kernels: staging
-    # threads (numpy copies release the GIL) fill pinned slots and issue the H2D copies while the main thread launches
-    # kernels -- the job of the reference's loader thread (dataloader.py:303-314), which used blocking copies.  Nothing
-    # is read back until the final reduction.  The slots (pinned + device buffers sized for the largest batch of this
-    # shard) are allocated ONCE: cudaHostAlloc per batch was what the round-1 loop spent its time in.
+    # Index batches go host -> pinned staging -> device on a copy stream, one batch ahead of the scoring kernels -- the
+    # job of the reference's loader thread (dataloader.py:303-314), which used blocking copies.  The staging copy of a
+    # batch (~10 MB of pageable numpy memory at the default batch size) is ONE multi-threaded native memcpy per array
+    # (tnr_host_copy_mt: no Python threads, hence no GIL hand-offs); the slots (pinned + device buffers sized for the
+    # largest batch of this shard) come from a per-process cache, so cudaHostAlloc is paid once, not per call.  Nothing
+    # is read back until the final reduction.
     starts = np.arange(lo, hi, batch_size, dtype=np.int64)
     ends = np.minimum(starts + batch_size, hi)
     nb_total = len(starts)
@@ -420,18 +440,14 @@ def evaluate(user_encoder, news_scoring, hist_idx, hist_mask, cand_ptr, cand_idx
     counts = np.diff(ptr_h[lo:hi + 1])
     max_cs = np.maximum.reduceat(counts, starts - lo) if nb_total else np.zeros(0, dtype=np.int64)
     bs = int((ends - starts).max()) if nb_total else 0
-    copy_stream = torch.cuda.Stream(device=device)
     main = torch.cuda.current_stream(device)
-    specs = ((bs * H, torch.int32), (bs * H, torch.float32), (bs + 1, torch.int64), (nnz_max, torch.int32),
-             (nnz_max, torch.int8))
-    n_slots = min(4, max(1, nb_total))
-    slots = [dict(pin=[torch.empty(max(m, 1), dtype=dt, pin_memory=True) for m, dt in specs],
-                  dev=[torch.empty(max(m, 1), dtype=dt, device=device) for m, dt in specs], done=None)
-             for _ in range(n_slots)]
-    per_buf = torch.empty(max(bs, 1), 5, device=device, dtype=torch.float64)
+    slots, copy_stream, per_buf = _eval_staging(device, bs, H, nnz_max, min(3, max(1, nb_total)))
+    n_slots = len(slots)
+    host_threads = max(1, min(8, (os.cpu_count() or 2) // 2))
+    for slot in slots:
+        slot["done"] = None
 
     def stage(k):
-        torch.cuda.set_device(device)
         s, e = int(starts[k]), int(ends[k])
         p0, p1 = int(ptr_h[s]), int(ptr_h[e])
         slot = slots[k % n_slots]
@@ -439,11 +455,11 @@ def evaluate(user_encoder, news_scoring, hist_idx, hist_mask, cand_ptr, cand_idx
             slot["done"].synchronize()                   # the kernels that read this slot's device buffers have finished
         nb, nz = e - s, p1 - p0
         pin = slot["pin"]
-        np.copyto(pin[0][:nb * H].view(nb, H).numpy(), hist_idx[s:e])
-        np.copyto(pin[1][:nb * H].view(nb, H).numpy(), hist_mask[s:e])
+        ops.host_copy(pin[0], hist_idx[s:e], host_threads)
+        ops.host_copy(pin[1], hist_mask[s:e], host_threads)
         np.subtract(ptr_h[s:e + 1], p0, out=pin[2][:nb + 1].numpy())
-        np.copyto(pin[3][:nz].numpy(), cand_idx[p0:p1])
-        np.copyto(pin[4][:nz].numpy(), labels[p0:p1])
+        ops.host_copy(pin[3], cand_idx[p0:p1], host_threads)
+        ops.host_copy(pin[4], labels[p0:p1], host_threads)
         sizes = (nb * H, nb * H, nb + 1, nz, nz)
         with torch.cuda.stream(copy_stream):
             for d, p_, m in zip(slot["dev"], pin, sizes):
@@ -454,28 +470,26 @@ def evaluate(user_encoder, news_scoring, hist_idx, hist_mask, cand_ptr, cand_idx
         return dict(nb=nb, slot=slot, max_c=int(max_cs[k]), ready=ready,
                     dev=(d[0][:nb * H].view(nb, H), d[1][:nb * H].view(nb, H), d[2][:nb + 1], d[3][:nz], d[4][:nz]))
 
-    from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=max(1, n_slots - 1)) as pool:
-        futs = {k: pool.submit(stage, k) for k in range(min(n_slots - 1, nb_total))} if n_slots > 1 else {}
-        for k in range(nb_total):
-            cur = futs.pop(k).result() if k in futs else stage(k)
-            main.wait_event(cur["ready"])
-            hi_t, hm_t, ptr_t, cand_t, lab_t = cur["dev"]
-            if hasattr(user_encoder, "forward_gather"):  # news_scoring[log_ids] (dataloader.py:295) fused into the kernel
-                user = user_encoder.forward_gather(news_scoring, hi_t, hm_t)
-            else:
-                user = user_encoder(dl.gather_history_vecs(news_scoring, hi_t), hm_t)
-            per = torch.empty(cur["nb"], 5, device=device, dtype=torch.float64) if return_per_impression \
-                else per_buf[:cur["nb"]]
-            ops.eval_metrics(news_scoring, user, ptr_t, cand_t, lab_t, cur["max_c"], per, sums)
-            done = torch.cuda.Event()
-            done.record(main)
-            cur["slot"]["done"] = done
-            if return_per_impression:
-                per_all.append(per)
-            nk = k + n_slots - 1                        # its slot was last read by batch k - 1
-            if n_slots > 1 and nk < nb_total:
-                futs[nk] = pool.submit(stage, nk)
+    copy_stream.wait_stream(main)
+    nxt = stage(0) if nb_total else None
+    for k in range(nb_total):
+        cur = nxt
+        main.wait_event(cur["ready"])
+        hi_t, hm_t, ptr_t, cand_t, lab_t = cur["dev"]
+        if hasattr(user_encoder, "forward_gather"):  # news_scoring[log_ids] (dataloader.py:295) fused into the kernel
+            user = user_encoder.forward_gather(news_scoring, hi_t, hm_t)
+        else:
+            user = user_encoder(dl.gather_history_vecs(news_scoring, hi_t), hm_t)
+        per = torch.empty(cur["nb"], 5, device=device, dtype=torch.float64) if return_per_impression \
+            else per_buf[:cur["nb"]]
+        ops.eval_metrics(news_scoring, user, ptr_t, cand_t, lab_t, cur["max_c"], per, sums)
+        done = torch.cuda.Event()
+        done.record(main)
+        cur["slot"]["done"] = done
+        if return_per_impression:
+            per_all.append(per)
+        # the next batch is staged AFTER this batch's kernels are queued: the host copies overlap them
+        nxt = stage(k + 1) if k + 1 < nb_total else None
     mean, total = par.reduce_eval_sums(hi - lo, sums[:4])
     if return_per_impression:
         return mean, total, torch.cat(per_all) if per_all else torch.zeros(0, 5, dtype=torch.float64)

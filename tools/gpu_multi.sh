@@ -1,0 +1,24 @@
+#!/bin/bash
+# Multi-GPU box visit.  Usage: gpurun --gpus N --timeout 1500 -- 'bash tools/gpu_multi.sh <tag> <N> [tests] [kd4] [kd2] [table] [table_long] [eval]'
+tag=$1; n=$2; shift; shift
+o=gpurun_out/$tag
+mkdir -p $o
+nvidia-smi --query-gpu=index,name,clocks.max.sm,power.limit --format=csv > $o/gpu.txt 2>&1
+nvidia-smi topo -m > $o/topo.txt 2>&1
+run() { # workload, extra args
+  wl=$1; shift
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus $n --workload $wl "$@" > $o/bench_${wl}_n$n.json 2> $o/bench_${wl}_n$n.err
+  echo "== $wl n=$n rc=$?"; tail -c 700 $o/bench_${wl}_n$n.json; tail -2 $o/bench_${wl}_n$n.err
+}
+for what in "$@"; do
+  case $what in
+    tests) timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -q -rA > $o/pytest_multi_gpu.log 2>&1; echo "pytest exit $?" >> $o/pytest_multi_gpu.log; tail -8 $o/pytest_multi_gpu.log ;;
+    kd4) run kd4 --steps 60 --warmup 5 --no-cpu-baseline ;;
+    kd4_nccl) NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,COLL run kd4 --steps 5 --warmup 3 --no-cpu-baseline; grep -i "nvls\|channels\|algo" $o/bench_kd4_n$n.err | head -20 > $o/nccl_info.txt ;;
+    kd2) run kd2 --steps 60 --warmup 5 --no-cpu-baseline ;;
+    table) run table --steps 20 --warmup 3 --no-cpu-baseline ;;
+    table_long) run table_long --steps 10 --warmup 3 --no-cpu-baseline ;;
+    eval) run eval --steps 40 --warmup 5 --no-cpu-baseline ;;
+  esac
+done
