@@ -760,7 +760,7 @@ def run_eval(a):
     import tinyrec.run as trun
     n_full = 376471
     fh, fm, fptr, fcand, flab = synth.eval_impressions(n_full, N_NEWS, H, seed=99)
-    trun.evaluate(ue, table, fh[:8192], fm[:8192], fptr[:8193], fcand[:int(fptr[8192])], flab[:int(fptr[8192])])    # warm-up
+    trun.evaluate(ue, table, fh, fm, fptr, fcand, flab)    # warm-up at the timed sizes: staging slots, workspaces, allocator
     barrier()
     t0 = time.perf_counter()
     full_mean, full_total = trun.evaluate(ue, table, fh, fm, fptr, fcand, flab)

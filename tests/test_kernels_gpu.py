@@ -463,7 +463,9 @@ def test_attnpool_fwd_bwd(with_mask):
     du_ref = ef.grad * (1 - ef.detach() ** 2)
     assert _rel_err(du, du_ref.reshape(n * S, Q))[0] < 6e-3
     assert _rel_err(dw2, w2f.grad)[0] < 1e-3
-    assert _rel_err(db2, b2f.grad)[0] < 1e-3 or float(b2f.grad.abs()) < 1e-5
+    # d loss / d b2 is zero in exact arithmetic (the weights are shift invariant up to the 1e-8 in the denominator):
+    # both sides hold rounding noise of the order of 1e-5 there
+    assert _rel_err(db2, b2f.grad)[0] < 1e-3 or float(b2f.grad.abs()) < 1e-4
 
 
 # ------------------------------------------------------------------ fp32 head (TF32 mma path)

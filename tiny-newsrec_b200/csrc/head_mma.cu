@@ -548,8 +548,7 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
       bulk_g2s(sW, p.W1 + (size_t)cta_rank * UL_HALF * D, bytes, w_bar);
       if (cta_rank != 0) {
         // The leader's MMA thread cannot wait on this CTA's barriers: forward "stage landed here" (and, before the
-        // first one, "W1 half landed here") to the leader's peer_bar.  This thread has no memory operations of its
-        // own in flight, so the release.cluster arrive costs it nothing but latency.
+        // first one, "W1 half landed here") to the leader's peer_bar.
         const int my_tiles = (n_tiles - t_first + t_stride - 1) / t_stride;
         const int n_items = my_tiles * NKB;
         const uint32_t peer_remote = mapa_cluster(peer_bar(0), 0);
@@ -558,7 +557,10 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
           const int st = item % UL_STAGES;
           mbar_wait(landed_bar(st), ((uint32_t)(item / UL_STAGES)) & 1u);
           fence_proxy_async_smem();                            // cp.async (generic proxy) writes -> the MMA's async-proxy reads
-          mbar_arrive_rel_cluster(peer_remote + 8u * st);
+          // relaxed: the data is in THIS SM's shared memory (nothing to publish through the memory hierarchy) and the
+          // arrive is control-dependent on the wait above; the release.cluster form costs MEMBAR.ALL.GPU per stage --
+          // ~1.5 us on this one thread, i.e. 12 us per tile: it was what the whole pair ran at (62 us)
+          mbar_arrive_cluster(peer_remote + 8u * st);
         }
       }
     }

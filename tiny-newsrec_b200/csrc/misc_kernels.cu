@@ -268,7 +268,8 @@ eval_rank_kernel(const float* __restrict__ score, const long long* __restrict__ 
   const long long p0 = ptr[b];
   const int C = (int)(ptr[b + 1] - p0);
   int P = 0;
-  for (int c0 = 0; c0 < C; c0 += 32) {
+  const int C4 = (C + 3) & ~3;                 // padded to whole float4 / char4 groups: -inf scores that rank below
+  for (int c0 = 0; c0 < C4; c0 += 32) {        // everything, "positive" labels that no AUC term counts
     const int c = c0 + lane;
     bool pos = false;
     if (c < C) {
@@ -276,6 +277,9 @@ eval_rank_kernel(const float* __restrict__ score, const long long* __restrict__ 
       const int8_t y = label[p0 + c];
       s_lab[c] = y;
       pos = y != 0;
+    } else if (c < C4) {
+      s_score[c] = -INFINITY;
+      s_lab[c] = 1;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, pos);
     if (pos) s_pos[P + __popc(bal & ((1u << lane) - 1u))] = c;                // index order is kept
@@ -292,12 +296,23 @@ eval_rank_kernel(const float* __restrict__ score, const long long* __restrict__ 
   for (int k = lane; k < P; k += 32) {
     const int c = s_pos[k];
     const float sc = s_score[c];
-    int above = 0, a2 = 0;
-    for (int j = 0; j < C; ++j) {
-      const float sj = s_score[j];
-      above += (sj > sc) || (sj == sc && j > c);
-      if (s_lab[j] == 0) a2 += 2 * (int)(sj < sc) + (int)(sj == sc);
+    // four candidates per step (one 16-byte and one 4-byte broadcast read), independent counters: the impressions
+    // with hundreds of candidates are single warps that everything else waits for
+    int ab[4] = {0, 0, 0, 0}, lt[4] = {0, 0, 0, 0}, eq[4] = {0, 0, 0, 0};
+    for (int j = 0; j < C4; j += 4) {
+      const float4 s4 = *reinterpret_cast<const float4*>(s_score + j);
+      const uint32_t l4 = *reinterpret_cast<const uint32_t*>(s_lab + j);
+      const float sj[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool neg = ((l4 >> (8 * u)) & 0xffu) == 0u;
+        ab[u] += (sj[u] > sc) || (sj[u] == sc && j + u > c);
+        lt[u] += neg && (sj[u] < sc);
+        eq[u] += neg && (sj[u] == sc);
+      }
     }
+    const int above = ab[0] + ab[1] + ab[2] + ab[3];
+    const int a2 = 2 * (lt[0] + lt[1] + lt[2] + lt[3]) + (eq[0] + eq[1] + eq[2] + eq[3]);
     const int rank = above + 1;
     auc2 += a2;
     mrr += 1.0 / (double)rank;

@@ -2,6 +2,7 @@
 // backward, column sums (bias gradients).  One warp per row, 16-byte vector loads, the row
 // lives in registers (E <= 1024), warp-shuffle reductions.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace tnr {
 
@@ -153,7 +154,7 @@ embed_ln_kernel(const int64_t* __restrict__ ids, int ids_ld, int L, int n_rows, 
 template <int VPL>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int rows, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y) {
+                     const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int reverse) {
   constexpr int E = VPL * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float g[VPL * 8], bt[VPL * 8];
@@ -171,17 +172,19 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int rows, const float*
   const int stride = gridDim.x * ROWS_PER_BLOCK;
   for (int r0 = blockIdx.x * ROWS_PER_BLOCK + warp; r0 < rows; r0 += 2 * stride) {
     const int r1 = r0 + stride;
+    // reverse: sweep the rows from the END -- the rows the producing GEMM wrote last are the ones still in L2
+    const int a0 = reverse ? rows - 1 - r0 : r0, a1 = reverse ? rows - 1 - r1 : r1;
     bf16x8 raw0[VPL], raw1[VPL];
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) raw0[v] = *reinterpret_cast<const bf16x8*>(x + (size_t)r0 * E + (v * 32 + lane) * 8);
+    for (int v = 0; v < VPL; ++v) raw0[v] = *reinterpret_cast<const bf16x8*>(x + (size_t)a0 * E + (v * 32 + lane) * 8);
     if (r1 < rows) {
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) raw1[v] = *reinterpret_cast<const bf16x8*>(x + (size_t)r1 * E + (v * 32 + lane) * 8);
+      for (int v = 0; v < VPL; ++v) raw1[v] = *reinterpret_cast<const bf16x8*>(x + (size_t)a1 * E + (v * 32 + lane) * 8);
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      const int r = k ? r1 : r0;
-      if (r >= rows) break;
+      if ((k ? r1 : r0) >= rows) break;
+      const int r = k ? a1 : a0;
       float xv[VPL * 8];
 #pragma unroll
       for (int v = 0; v < VPL; ++v) unpack8(k ? raw1[v] : raw0[v], &xv[v * 8]);
@@ -429,9 +432,10 @@ extern "C" __attribute__((visibility("default"))) int tnr_layernorm_fwd(const vo
   const int cap_f = num_sms() * 2;
   if (grid > cap_f) grid = cap_f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const int reverse = [] { const char* e = getenv("TNR_LN_REVERSE"); return e ? atoi(e) : 0; }();
   DISPATCH_VPL(E, (layernorm_fwd_kernel<VPL><<<grid, ROWS_PER_BLOCK * 32, 0, st>>>(
                       reinterpret_cast<const __nv_bfloat16*>(x_bf16), rows, gamma, beta, eps,
-                      reinterpret_cast<__nv_bfloat16*>(y_bf16))));
+                      reinterpret_cast<__nv_bfloat16*>(y_bf16), reverse)));
   TNR_LAUNCH_CHECK();
   return 0;
 }
