@@ -597,21 +597,36 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
         nrow[i] = v;
       }
     };
+    const float* xnext[8];
+    unsigned xok_next = 0;
     auto look_c = [&]() {                                       // pointers; unknown id -> row 0 (dataloader.py:74)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const long long v = nrow[i];
         const size_t src = (p.idx == nullptr || (v >= 0 && v < p.n_rows)) ? (size_t)v : 0;
-        xsrc[i] = p.vecs + src * D + piece * 4;
+        xnext[i] = p.vecs + src * D + piece * 4;
+        // Pull the WHOLE row towards L2 now, as one burst: the eight 128-byte k-block slices of a row are copied
+        // ~1.4 us apart, i.e. eight separate DRAM page openings for 1 KB if nothing asks for the row as a unit.  The
+        // eight threads that share a row each ask for one of its lines (piece p -> bytes [128 p, 128 p + 128)).
+        if ((nok >> i) & 1u) {
+          const float* line = p.vecs + src * D + piece * 32;
+          if (piece * 32 < D) asm volatile("prefetch.global.L2 [%0];" ::"l"(line) : "memory");
+        }
       }
-      xok = nok;
+      xok_next = nok;
     };
     const int kb_b = (3 * NKB) / 8, kb_c = (6 * NKB) / 8;
-    if (n_items > 0) { look_a(0); look_b(); }
+    if (n_items > 0) { look_a(0); look_b(); look_c(); }
     for (int item = 0; item < n_items; ++item) {
       const int tl = item / NKB, kb = item - tl * NKB;
-      if (kb == 0) { look_c(); look_a(tl + 1); }
+      if (kb == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xsrc[i] = xnext[i];
+        xok = xok_next;
+        look_a(tl + 1);
+      }
       if (kb == kb_b) look_b();
+      if (kb == kb_c && (kb_c > kb_b || NKB == 1)) look_c();
       const int st = item % UL_STAGES;
       mbar_wait(empty_bar(st), (((uint32_t)(item / UL_STAGES)) & 1u) ^ 1u);
       const uint32_t dst = sA + (uint32_t)st * UL_A_BYTES + dst_off;
@@ -623,8 +638,8 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
       }
       // this thread's arrival on landed[st] fires when its copies above have landed: nothing here waits for them
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(landed_bar(st)) : "memory");
+      if (kb == NKB - 1 && !(kb_c > kb_b || NKB == 1)) look_c();     // short K: everything at the end of the tile
     }
-    (void)kb_c;
   } else if (warp == 4) {
     // ===================== MMA issuer (the pair leader's elected thread) =====================
     if (lane == 0 && cta_rank == 0) {

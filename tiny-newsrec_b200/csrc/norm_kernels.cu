@@ -432,7 +432,7 @@ extern "C" __attribute__((visibility("default"))) int tnr_layernorm_fwd(const vo
   const int cap_f = num_sms() * 2;
   if (grid > cap_f) grid = cap_f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static const int reverse = [] { const char* e = getenv("TNR_LN_REVERSE"); return e ? atoi(e) : 0; }();
+  const int reverse = 0;   // sweeping from the end (to catch the producing GEMM's tail in L2) measured no gain: 0.270 -> 0.265 ms / 8 launches
   DISPATCH_VPL(E, (layernorm_fwd_kernel<VPL><<<grid, ROWS_PER_BLOCK * 32, 0, st>>>(
                       reinterpret_cast<const __nv_bfloat16*>(x_bf16), rows, gamma, beta, eps,
                       reinterpret_cast<__nv_bfloat16*>(y_bf16), reverse)));

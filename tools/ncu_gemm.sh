@@ -5,7 +5,7 @@ tag=${1:-gemm}
 out=gpurun_out/$tag
 mkdir -p $out
 timeout 700 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 111 -c 37 -o /tmp/gemm_step \
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/ncu.log 2>&1
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $out/ncu.log 2>&1
 ncu -i /tmp/gemm_step.ncu-rep --page raw --csv > $out/raw.csv 2>/dev/null
 ncu -i /tmp/gemm_step.ncu-rep --page source --csv --print-source sass > $out/source_sass.csv 2>/dev/null
 python - "$out" <<'PY'
