@@ -45,7 +45,8 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        extra = os.environ.get("TNR_EXTRA_NVCC_FLAGS", "").split()        # e.g. -DUL_TIMING (debug instrumentation)
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, r
 

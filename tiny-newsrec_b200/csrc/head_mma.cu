@@ -415,8 +415,9 @@ constexpr int UL_STAGES = 6;                       // A ring depth (k-blocks of 
 constexpr int UL_DMAX = 256;
 constexpr int UL_A_BYTES = UL_ROWS * 128;          // one k-block of the A tile: 16 KB
 constexpr int UL_W_KB_BYTES = UL_HALF * 128;       // one k-block of a W1 half: 13 KB (13 swizzle atoms)
-constexpr int UL_EPI_WARPS = 4, UL_LOAD_WARPS = 4;
-constexpr int UL_THREADS = 32 * (UL_EPI_WARPS + 2 + UL_LOAD_WARPS);      // epilogue 0-3, MMA 4, TMEM / W1 5, loaders 6-9
+constexpr int UL_EPI_WARPS = 4, UL_GROUP_WARPS = 4, UL_LOAD_WARPS = 2 * UL_GROUP_WARPS;
+constexpr int UL_THREADS = 32 * (UL_EPI_WARPS + 2 + UL_LOAD_WARPS);      // epilogue 0-3, MMA 4, TMEM / W1 5, loaders 6-13
+static_assert(UL_STAGES % 2 == 0, "the two loader groups own alternate stages");
 constexpr int UL_TMEM_COLS = 512;                  // two accumulator stages of 256 columns (208 used)
 constexpr int UL_NBARS = 3 * UL_STAGES + 5;
 
@@ -435,6 +436,9 @@ struct UlParams {
   const int32_t* live;        // [n_live] ids of the rows with mask != 0 (ue_compact_kernel; any order)
   const int32_t* n_live;      // device scalar
   int R, D, Q;
+#ifdef UL_TIMING
+  long long* dbg;             // debug build: clock64 stamps of CTA 0 (tools/ul_timing.py)
+#endif
 };
 
 // live[] <- the rows r < R with mask[r] != 0, in any order (warp-aggregated atomic append).  Only these go through
@@ -488,6 +492,41 @@ ue_pack_pad_kernel(const float* __restrict__ W1, const float* __restrict__ pad, 
   }
 }
 
+// tanh(x) = 1 - 2 / (1 + 2^(x * 2 log2 e)) on the two MUFU approximations, no range fix-ups (2^y overflows to +inf ->
+// rcp gives 0 -> 1; underflows to 0 -> -1): 5 instructions, |error| < 3e-7.  __expf / __fdividef add predicated
+// rescaling around each MUFU, and the row epilogue below is MUFU-bound as it is (2 per element, 16 per clock and SM).
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float r;
+  const float e = ex2_approx(x * 2.885390081777927f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return fmaf(-2.0f, r, 1.0f);
+}
+
+// NC accumulator columns [c0, c0 + NC) of one row -> sum_c w2[c] tanh(acc[c] (blended) + b1[c]); four independent chains
+template <bool BLEND, int NC>
+__device__ __forceinline__ float ul_row_chunk(const uint32_t (&r)[32], int c0, const float* __restrict__ sB1,
+                                              const float* __restrict__ sW2, const float* __restrict__ sP, float m, float om) {
+  float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < NC; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(sB1 + c0 + j);
+    const float4 w = *reinterpret_cast<const float4*>(sW2 + c0 + j);
+    const float bb[4] = {b.x, b.y, b.z, b.w}, ww[4] = {w.x, w.y, w.z, w.w};
+    float pp[4] = {0.f, 0.f, 0.f, 0.f};
+    if (BLEND) {
+      const float4 q = *reinterpret_cast<const float4*>(sP + c0 + j);
+      pp[0] = q.x; pp[1] = q.y; pp[2] = q.z; pp[3] = q.w;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float v = __uint_as_float(r[j + u]);
+      if (BLEND) v = fmaf(m, v, om * pp[u]);                   // W1 (m x + (1 - m) pad) = m (W1 x) + (1 - m) (W1 pad)
+      part[u] = fmaf(tanh_mufu(v + bb[u]), ww[u], part[u]);
+    }
+  }
+  return (part[0] + part[1]) + (part[2] + part[3]);
+}
+
 template <bool BLEND>
 __global__ void __launch_bounds__(UL_THREADS, 1)
 ue_logits_kernel(const __grid_constant__ UlParams p) {
@@ -517,7 +556,7 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
 
   if (warp == 4 && lane == 0) {
     for (int st = 0; st < UL_STAGES; ++st) {
-      mbar_init(landed_bar(st), UL_LOAD_WARPS * 32);
+      mbar_init(landed_bar(st), UL_GROUP_WARPS * 32);
       mbar_init(peer_bar(st), 1);
       mbar_init(empty_bar(st), 1);
     }
@@ -566,15 +605,21 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
     }
   } else if (warp >= 6) {
     // ===================== loaders: gather this CTA's 128 rows of every tile, k-block by k-block =====================
-    const int lt = threadIdx.x - 6 * 32;                       // 0..127
+    // Two groups of four warps take alternate (tile, k-block) items -- group g owns items g, g + 2, ... and, the ring
+    // depth being even, stages g, g + 2, g + 4.  One group spent ~750 cycles per stage (free-stage wait, eight copies,
+    // arrival, index bookkeeping) against the ~440 the MMAs of a k-block take: the loaders' issue rate, not memory,
+    // was the bound once the epilogue was out of the way.
+    const int grp = (warp - 6) / UL_GROUP_WARPS;
+    const int lt = (threadIdx.x - 6 * 32) & (UL_GROUP_WARPS * 32 - 1);      // 0..127 within the group
     const int piece = lt & 7, rbase = lt >> 3;                 // 16-byte chunk of the k-block row; rows rbase + 16 i
     const uint32_t dst_off = (uint32_t)rbase * 128u + (uint32_t)((piece ^ (rbase & 7)) << 4);    // (r & 7) == (rbase & 7)
     const int my_tiles = t_first < n_tiles ? (n_tiles - t_first + t_stride - 1) / t_stride : 0;
     const int n_items = my_tiles * NKB;
     const float* xsrc[8];
     unsigned xok = 0;
-    // The next tile's rows are looked up while this tile streams: live[] ids at k-block 0, idx[] rows a few k-blocks
-    // later, pointers after that -- two DEPENDENT index loads per row that would otherwise sit between two tiles.
+    // The rows of the group's NEXT tile are looked up while this tile streams: live[] ids at its first item, idx[] rows
+    // at the second, pointers (+ an L2 prefetch of the whole rows) at the last -- two DEPENDENT index loads per row
+    // that would otherwise sit between two tiles.
     int nlive[8];
     long long nrow[8];
     unsigned nok = 0;
@@ -599,36 +644,45 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
     };
     const float* xnext[8];
     unsigned xok_next = 0;
-    auto look_c = [&]() {                                       // pointers; unknown id -> row 0 (dataloader.py:74)
+    auto look_c = [&](bool prefetch) {                          // pointers; unknown id -> row 0 (dataloader.py:74)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const long long v = nrow[i];
         const size_t src = (p.idx == nullptr || (v >= 0 && v < p.n_rows)) ? (size_t)v : 0;
         xnext[i] = p.vecs + src * D + piece * 4;
-        // Pull the WHOLE row towards L2 now, as one burst: the eight 128-byte k-block slices of a row are copied
-        // ~1.4 us apart, i.e. eight separate DRAM page openings for 1 KB if nothing asks for the row as a unit.  The
-        // eight threads that share a row each ask for one of its lines (piece p -> bytes [128 p, 128 p + 128)).
-        if ((nok >> i) & 1u) {
-          const float* line = p.vecs + src * D + piece * 32;
-          if (piece * 32 < D) asm volatile("prefetch.global.L2 [%0];" ::"l"(line) : "memory");
-        }
+        // Pull the WHOLE row towards L2 now, as one burst: the 128-byte k-block slices of a row are copied ~0.5 us
+        // apart, i.e. separate DRAM page openings for 1 KB if nothing asks for the row as a unit.  The eight threads
+        // that share a row each ask for one of its lines (piece p -> bytes [128 p, 128 p + 128)).
+        if (prefetch && ((nok >> i) & 1u) && piece * 32 < D)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.vecs + src * D + piece * 32) : "memory");
       }
       xok_next = nok;
     };
-    const int kb_b = (3 * NKB) / 8, kb_c = (6 * NKB) / 8;
-    if (n_items > 0) { look_a(0); look_b(); look_c(); }
-    for (int item = 0; item < n_items; ++item) {
-      const int tl = item / NKB, kb = item - tl * NKB;
-      if (kb == 0) {
+    int item = grp;
+    int tl = item / NKB, kb = item - tl * NKB;
+    int st = grp;                                              // item % UL_STAGES, advanced by 2
+    uint32_t phase = 0;
+    if (item < n_items) { look_a(tl); look_b(); look_c(true); }
+    bool new_tile = true;
+    int j = 0, J = 1;                                          // this group's item number within the tile, and how many
+    for (; item < n_items; item += 2) {
+      if (new_tile) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) xsrc[i] = xnext[i];
         xok = xok_next;
-        look_a(tl + 1);
+        J = (NKB - kb + 1) >> 1;
+        j = 0;
+        look_a((item + 2 * J) / NKB);                          // the tile this group works on after this one
+        new_tile = false;
       }
-      if (kb == kb_b) look_b();
-      if (kb == kb_c && (kb_c > kb_b || NKB == 1)) look_c();
-      const int st = item % UL_STAGES;
-      mbar_wait(empty_bar(st), (((uint32_t)(item / UL_STAGES)) & 1u) ^ 1u);
+      if (j == (J > 1 ? 1 : 0)) look_b();
+#ifdef UL_TIMING
+      if (blockIdx.x == 0 && lt == 0 && item < 64) p.dbg[256 + item * 4 + 0] = clock64();
+#endif
+      mbar_wait(empty_bar(st), phase ^ 1u);
+#ifdef UL_TIMING
+      if (blockIdx.x == 0 && lt == 0 && item < 64) p.dbg[256 + item * 4 + 1] = clock64();
+#endif
       const uint32_t dst = sA + (uint32_t)st * UL_A_BYTES + dst_off;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -638,7 +692,18 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
       }
       // this thread's arrival on landed[st] fires when its copies above have landed: nothing here waits for them
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(landed_bar(st)) : "memory");
-      if (kb == NKB - 1 && !(kb_c > kb_b || NKB == 1)) look_c();     // short K: everything at the end of the tile
+#ifdef UL_TIMING
+      if (blockIdx.x == 0 && lt == 0 && item < 64) p.dbg[256 + item * 4 + 2] = clock64();
+#endif
+      if (j == J - 1) {                                        // last item of the tile for this group
+        const int tn = (item + 2) / NKB;                       // == the tile look_a asked about
+        look_c(((tn * NKB) & 1) == grp);                       // the group that owns the tile's first k-block prefetches
+      }
+      ++j;
+      kb += 2;
+      while (kb >= NKB) { kb -= NKB; ++tl; new_tile = true; }
+      st += 2;
+      if (st >= UL_STAGES) { st -= UL_STAGES; phase ^= 1u; }
     }
   } else if (warp == 4) {
     // ===================== MMA issuer (the pair leader's elected thread) =====================
@@ -656,7 +721,14 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
           const int st = item % UL_STAGES;
           const uint32_t par = ((uint32_t)(item / UL_STAGES)) & 1u;
           mbar_wait(landed_bar(st), par);                      // this CTA's 128 rows of the k-block
-          mbar_wait_acq_cluster(peer_bar(st), par);            // the peer's
+#ifdef UL_TIMING
+          if (blockIdx.x == 0 && item < 64) p.dbg[item * 4 + 0] = clock64();
+#endif
+          mbar_wait(peer_bar(st), par);                        // the peer's (its data sits in ITS shared memory: no acquire at
+                                                               // cluster scope, which costs an L1 invalidate per stage)
+#ifdef UL_TIMING
+          if (blockIdx.x == 0 && item < 64) p.dbg[item * 4 + 1] = clock64();
+#endif
           fence_proxy_async_smem();
           tc_fence_after();
           const uint64_t adesc = make_desc_kmajor_sw128(sA + (uint32_t)st * UL_A_BYTES);
@@ -665,6 +737,9 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
           for (int k = 0; k < UL_KB / 8; ++k)                  // kind::tf32: K = 8 per instruction, +32 B inside the atom
             tc_mma_tf32_cta2(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           tc_commit_mc2(empty_bar(st), 3);                     // the stage is free in both CTAs once these MMAs retire
+#ifdef UL_TIMING
+          if (blockIdx.x == 0 && item < 64) p.dbg[item * 4 + 2] = clock64();
+#endif
         }
         tc_commit_mc2(tfull_bar(acc), 3);
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
@@ -684,27 +759,39 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
       const int rid = li < n_live ? p.live[li] : -1;
       float m = 1.f, om = 0.f;
       if (BLEND && rid >= 0) { m = p.mask[rid]; om = 1.0f - m; }
+#ifdef UL_TIMING
+      const int tl_dbg = (t - t_first) / t_stride;
+      if (blockIdx.x == 0 && warp == 0 && lane == 0 && tl_dbg < 8) p.dbg[512 + tl_dbg * 4 + 0] = clock64();
+#endif
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+#ifdef UL_TIMING
+      if (blockIdx.x == 0 && warp == 0 && lane == 0 && tl_dbg < 8) p.dbg[512 + tl_dbg * 4 + 1] = clock64();
+#endif
+      // 208 columns = six chunks of 32 and one of 16, two register buffers: the next chunk's tcgen05.ld is in flight
+      // while this one is evaluated (one load at a time put ~1 000 cycles of TMEM latency in front of every chunk, and
+      // a single dependent chain per row made the tile epilogue 15 000 cycles: it, not the loads, set the kernel's time)
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+      uint32_t ra[32], rb[32];
       float logit = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < UL_QT; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + c0), r);
-        tmem_ld_wait();
-        const int nc = (UL_QT - c0) < 32 ? (UL_QT - c0) : 32;
+      tmem_ld32(t_row, ra);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < nc) {
-            float v = __uint_as_float(r[j]);
-            if (BLEND) v = fmaf(m, v, om * sP[c0 + j]);        // W1 (m x + (1 - m) pad) = m (W1 x) + (1 - m) (W1 pad)
-            logit = fmaf(tanh_exp(v + sB1[c0 + j]), sW2[c0 + j], logit);
-          }
-        }
+      for (int c0 = 0; c0 < 192; c0 += 64) {
+        tmem_ld_wait();
+        tmem_ld32(t_row + (uint32_t)(c0 + 32), rb);
+        logit += ul_row_chunk<BLEND, 32>(ra, c0, sB1, sW2, sP, m, om);
+        tmem_ld_wait();
+        tmem_ld32(t_row + (uint32_t)(c0 + 64), ra);            // the last one (c0 + 64 = 192) is the 16-column tail
+        logit += ul_row_chunk<BLEND, 32>(rb, c0 + 32, sB1, sW2, sP, m, om);
       }
+      tmem_ld_wait();
+      logit += ul_row_chunk<BLEND, UL_QT - 192>(ra, 192, sB1, sW2, sP, m, om);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_remote + 8u * acc);      // this warp is done with the accumulator stage
+#ifdef UL_TIMING
+      if (blockIdx.x == 0 && warp == 0 && lane == 0 && tl_dbg < 8) p.dbg[512 + tl_dbg * 4 + 2] = clock64();
+#endif
       acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       if (rid >= 0) p.logits[rid] = logit;
     }
@@ -1115,7 +1202,11 @@ TNR_API int tnr_user_encoder_pack_w1(const float* W1, const float* pad_doc, cons
   return 0;
 }
 
+#ifdef UL_TIMING
+TNR_API long long tnr_user_encoder_score_ws_bytes(int B, int H) { return ((long long)B * H + 4) * 4 + 8192; }
+#else
 TNR_API long long tnr_user_encoder_score_ws_bytes(int B, int H) { return ((long long)B * H + 4) * 4; }
+#endif
 
 template <bool BLEND>
 static int ue_logits_launch(const UlParams& p, int pairs, int smem, cudaStream_t st) {
@@ -1156,6 +1247,9 @@ TNR_API int tnr_user_encoder_score(const float* vecs, long long n_rows, const in
   p.vecs = vecs; p.idx = idx; p.n_rows = n_rows; p.mask = mask; p.W1 = w1_packed; p.b1 = b1; p.w2 = w2;
   p.logits = a_out; p.live = wsi + 4; p.n_live = wsi;
   p.R = R; p.D = D; p.Q = Q;
+#ifdef UL_TIMING
+  p.dbg = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) + ((size_t)R + 4) * 4);
+#endif
   const int smem = ul_smem_bytes(D);
   const int n_tiles = (R + 2 * UL_ROWS - 1) / (2 * UL_ROWS);      // upper bound: the live count is only known on the device
   const int pairs = n_tiles < num_sms() / 2 ? n_tiles : num_sms() / 2;

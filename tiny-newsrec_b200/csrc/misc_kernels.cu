@@ -244,7 +244,7 @@ eval_score_kernel(const float* __restrict__ table, long long n_rows, const float
   }
 }
 
-constexpr int ER_WARPS = 8;
+constexpr int ER_WARPS = 4;          // small blocks: an SM picks up new impressions as soon as four are done
 
 __device__ __forceinline__ double shfl_xor_f64(double v, int o) {
   return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), o), __shfl_xor_sync(0xffffffffu, __double2loint(v), o));
@@ -275,20 +275,21 @@ eval_rank_kernel(const float* __restrict__ score, const long long* __restrict__ 
   int8_t* s_lab = reinterpret_cast<int8_t*>(sm + (size_t)2 * wpb * cap) + (size_t)warp * cap;
   const long long p0 = ptr[b];
   const int C = (int)(ptr[b + 1] - p0);
-  int P = 0;
   const int C4 = (C + 3) & ~3;                 // padded to whole 4-candidate groups: key 0 ranks below every real score
-  for (int c0 = 0; c0 < C4; c0 += 32) {        // (no finite or infinite float maps to key 0), label "positive": no AUC term
-    const int c = c0 + lane;
-    bool pos = false;
-    if (c < C) {
+  for (int c = lane; c < C4; c += 32) {        // (no float maps to key 0), label "positive": no AUC term.  All loads of
+    if (c < C) {                               // this loop are independent (the compaction below reads shared memory)
       s_key[c] = order_key(score[p0 + c]);
-      const int8_t y = label[p0 + c];
-      s_lab[c] = y;
-      pos = y != 0;
-    } else if (c < C4) {
+      s_lab[c] = label[p0 + c];
+    } else {
       s_key[c] = 0u;
       s_lab[c] = 1;
     }
+  }
+  __syncwarp();
+  int P = 0;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + lane;
+    const bool pos = c < C && s_lab[c] != 0;
     const unsigned bal = __ballot_sync(0xffffffffu, pos);
     if (pos) s_pos[P + __popc(bal & ((1u << lane) - 1u))] = c;                // index order is kept
     P += __popc(bal);
