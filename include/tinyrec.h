@@ -266,6 +266,19 @@ int tnr_adam_amsgrad_devstep(float* p, const float* g, float* m, float* v, float
                              float* bc_ws, float grad_scale, int advance, void* stream);
 int tnr_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);
 
+/* ------------------------------------------------------------------ gradient exchange over peer memory */
+/* In-place SUM all-reduce of floats [off, off + n) of a symmetric fp32 buffer across the `world` GPUs of one NVSwitch
+ * node, over peer-mapped memory in ONE kernel of n_ctas CTAs (two-shot: rank r reduces slice r from every peer in rank
+ * order and stores the sum into every peer's buffer; flag barriers before and after; bit-identical results on all
+ * ranks).  ptrs_dev / flags_dev: DEVICE arrays of `world` pointers -- rank r's copy of the buffer and of a zero-
+ * initialised flag page of tnr_allreduce_p2p_flag_words() uint32 (both symmetric allocations, e.g.
+ * torch.distributed._symmetric_memory).  Every rank must launch it with the same (off, n, n_ctas) in the same order;
+ * it is graph-capturable (no host-side sequence state).  Replaces the Horovod gradient all-reduce of
+ * Tiny-NewsRec/run.py:144-149 (hvd.DistributedOptimizer, op=Average: the 1/world is folded into the Adam kernel). */
+long long tnr_allreduce_p2p_flag_words(void);
+int tnr_allreduce_p2p(void* const* ptrs_dev, void* const* flags_dev, int rank, int world, long long off,
+                      long long n, int n_ctas, void* stream);
+
 /* ------------------------------------------------------------------ batch assembly */
 /* out[r,:] = (int64) table[idx[r], :]   (news_combined[idx] -> LongTensor, dataloader.py:131,138,152-156);
  * idx outside [0, n_rows_table) maps to row 0 (dataloader.py:74).  Bit-exact. */

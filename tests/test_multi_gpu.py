@@ -78,6 +78,7 @@ def _worker(rank, world, port, out):
     flat = m.train_state().flat
     if rank == 0:
         torch.save(flat.data.cpu(), out)
+        print("gradient exchange:", "tnr_allreduce_p2p" if flat.symm is not None and opt.use_p2p else f"nccl ({flat.symm_error})")
     gathered = [torch.empty_like(flat.data) for _ in range(world)]
     dist.all_gather(gathered, flat.data)
     assert all(torch.equal(g, gathered[0]) for g in gathered), "replicas diverged"

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "tnr_device_check": ([POINTER(c_int)], c_int),
     "tnr_set_sm_reserve": ([c_int], c_int),
     "tnr_host_copy_mt": ([P, P, c_int64, c_int], c_int),
+    "tnr_allreduce_p2p_flag_words": ([], c_int64),
+    "tnr_allreduce_p2p": ([P, P, c_int, c_int, c_int64, c_int64, c_int, P], c_int),
     "tnr_gemm_bf16": ([POINTER(GemmArgs), P], c_int),
     "tnr_dropout_mask": ([POINTER(Dropout), c_int64, P, P], c_int),
     "tnr_embed_ln_fwd": ([P, c_int, c_int, c_int, c_int, P, c_int, P, P, P, P, c_float, c_int, P, POINTER(Dropout), P], c_int),

@@ -108,7 +108,17 @@ class FlatParams:
             off = _align8(off)
         self.numel = off
         self.data = torch.zeros(off, device=device, dtype=F32)
-        self.grad = torch.zeros(off, device=device, dtype=F32)
+        # Data-parallel runs keep the gradient buffer in symmetric (peer-mapped) memory so that the exchange can be one
+        # kernel over NVLink peer memory (tinyrec.parallel.SymmetricGradBuffer / tnr_allreduce_p2p); any failure to set
+        # that up leaves a plain buffer and the NCCL all-reduce.
+        self.symm, self.symm_error = None, None
+        from . import parallel as _par
+        if _par.SymmetricGradBuffer.wanted() and torch.device(device).type == "cuda":
+            try:
+                self.symm = _par.SymmetricGradBuffer(off, torch.device(device))
+            except Exception as exc:  # noqa: BLE001  (reported by bench.py / the tests, not hidden)
+                self.symm, self.symm_error = None, f"{type(exc).__name__}: {exc}"
+        self.grad = self.symm.grad if self.symm is not None else torch.zeros(off, device=device, dtype=F32)
         self.shadow = torch.zeros(off, device=device, dtype=BF)
         for p, o in zip(ordered_params, self.offsets):
             view = self.data[o:o + p.numel()].view(p.shape)

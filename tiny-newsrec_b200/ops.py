@@ -537,6 +537,15 @@ def host_copy(dst, src, n_threads=4):
     return dst
 
 
+def allreduce_p2p(ptrs_dev, flags_dev, rank, world, off, n, n_ctas):
+    """In-place sum all-reduce of floats [off, off + n) of a symmetric fp32 buffer over NVLink peer memory
+    (tnr_allreduce_p2p); ``ptrs_dev`` / ``flags_dev`` are device addresses of the per-rank pointer tables."""
+    lib = _lib.load()
+    stats.launches += 1
+    _lib.check(lib.tnr_allreduce_p2p(ctypes.c_void_p(int(ptrs_dev)), ctypes.c_void_p(int(flags_dev)), int(rank), int(world),
+                                     int(off), int(n), int(n_ctas), _stream()), "tnr_allreduce_p2p")
+
+
 def set_sm_reserve(n_sms, device=None):
     """SMs the persistent GEMM grids leave free on ``device`` from now on (0 = all SMs): tnr_set_sm_reserve."""
     lib = _lib.load()

@@ -151,6 +151,8 @@ class DistributedOptimizer:
         self.sm_reserve = (sm_reserve + 1) // 2 * 2 if self.stream is not None else 0
         self.reserved = False
         self.trace = None           # list -> per step a dict of CUDA events (bench.py --gpus N: comm timeline)
+        self.use_p2p = os.environ.get("TNR_P2P_ALLREDUCE", "1") != "0"
+        self.comm_ctas = max(1, self.sm_reserve or int(os.environ.get("NCCL_MAX_CTAS", "8") or 8))
         if self.stream is not None:
             self.opt.model.train_state().comm_hook = self._launch
 
@@ -168,7 +170,10 @@ class DistributedOptimizer:
             if timed:
                 start = torch.cuda.Event(enable_timing=True)
                 start.record()
-            dist.all_reduce(flat.grad[lo:hi], op=dist.ReduceOp.SUM)
+            if flat.symm is not None and self.use_p2p:
+                flat.symm.all_reduce(lo, hi, self.comm_ctas)        # one kernel over NVLink peer memory
+            else:
+                dist.all_reduce(flat.grad[lo:hi], op=dist.ReduceOp.SUM)
             done = torch.cuda.Event(enable_timing=timed)
             done.record()
         self.pending.append((lo, hi, done))

@@ -102,3 +102,41 @@ def allgather_rows(local_rows, n_rows):
     out = torch.empty(w * per, D, device=local_rows.device, dtype=local_rows.dtype)
     dist.all_gather_into_tensor(out, pad)
     return out[:n_rows]
+
+
+class SymmetricGradBuffer:
+    """The flat fp32 gradient buffer of a data-parallel model as a SYMMETRIC allocation (every rank's copy is mapped
+    into every process over NVLink: ``torch.distributed._symmetric_memory``), plus a flag page, for the one-kernel
+    peer-memory all-reduce ``tnr_allreduce_p2p``.  Construction is a collective (all ranks, same order, same size).
+    ``available(...)`` says whether this process can use it; ``TNR_P2P_ALLREDUCE=0`` keeps NCCL."""
+
+    def __init__(self, numel, device):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        group = dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:  # noqa: BLE001  (newer torch enables it implicitly)
+            pass
+        self.grad = symm.empty(numel, dtype=torch.float32, device=device)
+        self.grad.zero_()
+        self.grad_hdl = symm.rendezvous(self.grad, group)
+        words = int(_lib.load().tnr_allreduce_p2p_flag_words())
+        self.flags = symm.empty(words, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.flags_hdl = symm.rendezvous(self.flags, group)
+        self.ptrs_dev = int(self.grad_hdl.buffer_ptrs_dev)
+        self.flags_dev = int(self.flags_hdl.buffer_ptrs_dev)
+        torch.cuda.synchronize(device)
+        dist.barrier()                       # every rank's flag page is zero before anyone's first kernel
+
+    @staticmethod
+    def wanted():
+        return (os.environ.get("TNR_P2P_ALLREDUCE", "1") != "0" and dist.is_available() and dist.is_initialized()
+                and dist.get_world_size() > 1 and dist.get_backend() == "nccl")
+
+    def all_reduce(self, lo, hi, n_ctas):
+        """sum-all-reduce self.grad[lo:hi] in place on the current stream"""
+        from . import ops
+        ops.allreduce_p2p(self.ptrs_dev, self.flags_dev, self.rank, self.world, lo, hi - lo, n_ctas)
