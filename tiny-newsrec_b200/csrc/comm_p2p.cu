@@ -53,9 +53,14 @@ __device__ __forceinline__ void ar_barrier(uint32_t* const* flags, int rank, int
   __syncthreads();
 }
 
+// WORLD > 0: compile-time world size (the rank loop unrolls: all U x WORLD loads of a thread are in flight together --
+// with a runtime loop each rank's loads waited for the previous rank's adds, ~3 us of NVLink latency per rank and pass);
+// WORLD == 0: any world size up to AR_MAX_WORLD.
+template <int WORLD>
 __global__ void __launch_bounds__(AR_THREADS)
-allreduce_p2p_kernel(float* const* __restrict__ ptrs, uint32_t* const* __restrict__ flags, int rank, int world,
+allreduce_p2p_kernel(float* const* __restrict__ ptrs, uint32_t* const* __restrict__ flags, int rank, int world_rt,
                      long long off4, long long n4) {
+  const int world = WORLD > 0 ? WORLD : world_rt;
   __shared__ float4* s_ptr[AR_MAX_WORLD];
   __shared__ uint32_t* s_flag[AR_MAX_WORLD];
   __shared__ uint32_t s_seq;
@@ -75,26 +80,57 @@ allreduce_p2p_kernel(float* const* __restrict__ ptrs, uint32_t* const* __restric
   const long long per = (n4 + world - 1) / world;
   const long long lo = (long long)rank * per, hi = (lo + per < n4) ? lo + per : n4;
   const long long stride = (long long)gridDim.x * AR_THREADS;
-  constexpr int U = 4;                               // elements in flight per thread: U x world 16-byte loads
+  constexpr int U = WORLD > 0 ? (WORLD <= 2 ? 8 : (WORLD <= 4 ? 4 : 2)) : 2;      // U x WORLD 16-byte loads in flight per thread
+  float4* pr[WORLD > 0 ? WORLD : 1];
+  if (WORLD > 0) {
+#pragma unroll
+    for (int r = 0; r < WORLD; ++r) pr[r] = s_ptr[r];
+  }
   for (long long i0 = lo + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i0 < hi; i0 += U * stride) {
     float4 acc[U];
+    if (WORLD > 0) {
+      float4 v[WORLD > 0 ? WORLD : 1][U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < world; ++r) {                // rank order: the same sum on every replica
-      float4 v[U];
+      for (int r = 0; r < WORLD; ++r)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * stride;
+          v[r][u] = i < hi ? ld_peer(pr[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const long long i = i0 + u * stride;
-        v[u] = i < hi ? ld_peer(s_ptr[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc[u] = v[0][u];
+#pragma unroll
+        for (int r = 1; r < WORLD; ++r) {               // rank order: the same sum on every replica
+          acc[u].x += v[r][u].x; acc[u].y += v[r][u].y; acc[u].z += v[r][u].z; acc[u].w += v[r][u].w;
+        }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
-    }
-    for (int r = 0; r < world; ++r) {
+      for (int r = 0; r < WORLD; ++r)
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long i = i0 + u * stride;
-        if (i < hi) s_ptr[r][i] = acc[u];
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < hi) pr[r][i] = acc[u];
+        }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < world; ++r) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * stride;
+          v[u] = i < hi ? ld_peer(s_ptr[r] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+      }
+      for (int r = 0; r < world; ++r) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * stride;
+          if (i < hi) s_ptr[r][i] = acc[u];
+        }
       }
     }
   }
@@ -115,8 +151,15 @@ TNR_API int tnr_allreduce_p2p(void* const* ptrs_dev, void* const* flags_dev, int
   TNR_REQUIRE(off % 4 == 0 && n % 4 == 0 && off >= 0 && n >= 0, "tnr_allreduce_p2p: offset and count must be multiples of 4 floats");
   TNR_REQUIRE(n_ctas >= 1 && n_ctas <= AR_MAX_CTAS, "tnr_allreduce_p2p: 1 <= n_ctas <= %d", AR_MAX_CTAS);
   if (n == 0 || world == 1) return 0;
-  allreduce_p2p_kernel<<<n_ctas, AR_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<float* const*>(ptrs_dev), reinterpret_cast<uint32_t* const*>(flags_dev), rank, world, off / 4, n / 4);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* const* pp = reinterpret_cast<float* const*>(ptrs_dev);
+  uint32_t* const* ff = reinterpret_cast<uint32_t* const*>(flags_dev);
+  switch (world) {
+    case 2: allreduce_p2p_kernel<2><<<n_ctas, AR_THREADS, 0, st>>>(pp, ff, rank, world, off / 4, n / 4); break;
+    case 4: allreduce_p2p_kernel<4><<<n_ctas, AR_THREADS, 0, st>>>(pp, ff, rank, world, off / 4, n / 4); break;
+    case 8: allreduce_p2p_kernel<8><<<n_ctas, AR_THREADS, 0, st>>>(pp, ff, rank, world, off / 4, n / 4); break;
+    default: allreduce_p2p_kernel<0><<<n_ctas, AR_THREADS, 0, st>>>(pp, ff, rank, world, off / 4, n / 4); break;
+  }
   TNR_LAUNCH_CHECK();
   return 0;
 }
