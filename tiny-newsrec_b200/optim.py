@@ -146,13 +146,20 @@ class DistributedOptimizer:
         self.opt.grad_scale = 1.0 / self.world          # SUM all-reduce, scale folded into Adam
         self.stream = torch.cuda.Stream() if (self.world > 1 and overlap) else None
         self.pending = []
+        self.use_p2p = os.environ.get("TNR_P2P_ALLREDUCE", "1") != "0"
+        p2p = False
+        if self.stream is not None:
+            flat = self.opt.model.train_state().flat
+            p2p = self.use_p2p and flat is not None and getattr(flat, "symm", None) is not None
         if sm_reserve is None:
-            sm_reserve = int(os.environ.get("TNR_COMM_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "0")) or 0)
+            # the peer-memory kernel needs few CTAs (it is latency-, not bandwidth-bound at these bucket sizes and runs
+            # hidden behind the backward); NCCL gets what NCCL_MAX_CTAS allows it
+            default = "4" if p2p else os.environ.get("NCCL_MAX_CTAS", "0")
+            sm_reserve = int(os.environ.get("TNR_COMM_SM_RESERVE", default) or 0)
         self.sm_reserve = (sm_reserve + 1) // 2 * 2 if self.stream is not None else 0
         self.reserved = False
         self.trace = None           # list -> per step a dict of CUDA events (bench.py --gpus N: comm timeline)
-        self.use_p2p = os.environ.get("TNR_P2P_ALLREDUCE", "1") != "0"
-        self.comm_ctas = max(1, self.sm_reserve or int(os.environ.get("NCCL_MAX_CTAS", "8") or 8))
+        self.comm_ctas = max(1, self.sm_reserve or 4)
         if self.stream is not None:
             self.opt.model.train_state().comm_hook = self._launch
 

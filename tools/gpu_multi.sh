@@ -15,6 +15,8 @@ for what in "$@"; do
   case $what in
     tests) timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -q -rA > $o/pytest_multi_gpu.log 2>&1; echo "pytest exit $?" >> $o/pytest_multi_gpu.log; tail -8 $o/pytest_multi_gpu.log ;;
     kd4) run kd4 --steps 60 --warmup 5 --no-cpu-baseline ;;
+    kd4_1) timeout 400 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-preassembled > $o/bench_kd4_n1.json 2> $o/bench_kd4_n1.err; echo "== kd4 n=1 rc=$?"; tail -c 300 $o/bench_kd4_n1.json ;;
+    kd4_nccl_only) TNR_P2P_ALLREDUCE=0 run kd4 --steps 60 --warmup 5 --no-cpu-baseline; mv $o/bench_kd4_n$n.json $o/bench_kd4_n${n}_nccl.json ;;
     kd4_nccl) NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,COLL run kd4 --steps 5 --warmup 3 --no-cpu-baseline; grep -i "nvls\|channels\|algo" $o/bench_kd4_n$n.err | head -20 > $o/nccl_info.txt ;;
     kd2) run kd2 --steps 60 --warmup 5 --no-cpu-baseline ;;
     table) run table --steps 20 --warmup 3 --no-cpu-baseline ;;
