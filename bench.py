@@ -470,7 +470,9 @@ def run_tinyrec(a):
                 "backward_end_to_step_end_ms": med([t["backward_end"].elapsed_time(t["step_end"]) for t in tr]),
                 "exposed_ms": med([max(0.0, max(t["backward_end"].elapsed_time(b["done"]) for b in t["buckets"])) for t in tr]),
                 "sm_reserve": getattr(opt, "sm_reserve", 0), "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"),
-                "collective": ("tnr_allreduce_p2p (one kernel per bucket over NVLink peer memory)"
+                "collective": (("tnr_allreduce_p2p, NVLS multimem.ld_reduce / multimem.st (one kernel per bucket)"
+                                if getattr(model.train_state().flat.symm, "mc_ptr", 0) else
+                                "tnr_allreduce_p2p (one kernel per bucket over NVLink peer memory)")
                                if model.train_state().flat.symm is not None and getattr(opt, "use_p2p", False)
                                else f"nccl all_reduce ({model.train_state().flat.symm_error or 'TNR_P2P_ALLREDUCE=0'})"),
                 "buckets": buckets}

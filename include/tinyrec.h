@@ -91,8 +91,19 @@ typedef struct {
   const tnr_dropout* drop;   /* v = dropout(acc + bias) before the residual add; NULL = off (plain epilogue only) */
   float* colsum;             /* if != NULL (bf16 output only): colsum[n] += sum_m C[m,n] of the rounded bf16 output --
                                 the bias gradient of the layer in front (fp32 atomics), fused into the dgrad epilogue */
+  /* Fused LayerNorm epilogue -- LN(dropout(dense(h)) + input) of BertSelfOutput / BertOutput (transformers, used at
+   * tnlrv3/modeling.py:287,306): with ln_gamma != NULL, C <- (v - mean_row(v)) * rstd_row(v) * gamma[n] + beta[n] where v is
+   * the plain epilogue's value rounded to bf16, statistics over all N columns of the row (fp32; the 64-column slices of a
+   * row meet through ln_ws).  ln_pre != NULL also stores v itself (what the LayerNorm backward recomputes from).
+   * Needs tnr_gemm_ln_supported(M, N), bf16 C, act NONE, no split-K; ln_ws: tnr_gemm_ln_ws_bytes(M, N) bytes whose first
+   * ((M + 127) / 128) * 16 bytes were zeroed ONCE when it was allocated (monotonic arrival counters). */
+  const float* ln_gamma; const float* ln_beta; float ln_eps;
+  void* ln_pre; int ld_pre;
+  void* ln_ws;
 } tnr_gemm_args;
 int tnr_gemm_bf16(const tnr_gemm_args* args, void* stream);
+int tnr_gemm_ln_supported(int M, int N);
+long long tnr_gemm_ln_ws_bytes(int M, int N);
 
 /* ------------------------------------------------- encoder row kernels (HBM-bound) */
 /* out[t,:] = LayerNorm_eps( word[ids[t]] + pos[t % L] + type0 )  ->  bf16 [n_rows*L, E].
@@ -272,12 +283,14 @@ int tnr_cast_f32_bf16(const float* x, void* y_bf16, long long n, void* stream);
  * order and stores the sum into every peer's buffer; flag barriers before and after; bit-identical results on all
  * ranks).  ptrs_dev / flags_dev: DEVICE arrays of `world` pointers -- rank r's copy of the buffer and of a zero-
  * initialised flag page of tnr_allreduce_p2p_flag_words() uint32 (both symmetric allocations, e.g.
- * torch.distributed._symmetric_memory).  Every rank must launch it with the same (off, n, n_ctas) in the same order;
+ * torch.distributed._symmetric_memory).  multicast_ptr != NULL: the NVLS multicast mapping of the same buffer -- the
+ * reduce becomes multimem.ld_reduce (sum inside the NVSwitch) + multimem.st (one store reaches every rank); NULL: peer
+ * loads / stores.  Every rank must launch it with the same (off, n, n_ctas) in the same order;
  * it is graph-capturable (no host-side sequence state).  Replaces the Horovod gradient all-reduce of
  * Tiny-NewsRec/run.py:144-149 (hvd.DistributedOptimizer, op=Average: the 1/world is folded into the Adam kernel). */
 long long tnr_allreduce_p2p_flag_words(void);
-int tnr_allreduce_p2p(void* const* ptrs_dev, void* const* flags_dev, int rank, int world, long long off,
-                      long long n, int n_ctas, void* stream);
+int tnr_allreduce_p2p(void* const* ptrs_dev, void* multicast_ptr, void* const* flags_dev, int rank, int world,
+                      long long off, long long n, int n_ctas, void* stream);
 
 /* ------------------------------------------------------------------ batch assembly */
 /* out[r,:] = (int64) table[idx[r], :]   (news_combined[idx] -> LongTensor, dataloader.py:131,138,152-156);

@@ -56,6 +56,57 @@ __device__ __forceinline__ void ar_barrier(uint32_t* const* flags, int rank, int
 // WORLD > 0: compile-time world size (the rank loop unrolls: all U x WORLD loads of a thread are in flight together --
 // with a runtime loop each rank's loads waited for the previous rank's adds, ~3 us of NVLink latency per rank and pass);
 // WORLD == 0: any world size up to AR_MAX_WORLD.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float4* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// NVLS form of the same two-shot exchange: the buffer is also mapped at a MULTICAST address; one multimem.ld_reduce
+// returns the sum of an element over all ranks, added inside the NVSwitch, and one multimem.st writes the result to
+// every rank -- world x fewer requests per thread than the peer-load loop below, which at 8 GPUs could not keep
+// enough bytes in flight from 4 CTAs (31 MB in 1.1 ms).  A slice is still reduced by exactly one rank: replicas get
+// bit-identical sums.
+__global__ void __launch_bounds__(AR_THREADS)
+allreduce_nvls_kernel(float4* __restrict__ mc, uint32_t* const* __restrict__ flags, int rank, int world, long long off4,
+                      long long n4) {
+  __shared__ uint32_t* s_flag[AR_MAX_WORLD];
+  __shared__ uint32_t s_seq;
+  if ((int)threadIdx.x < world) s_flag[threadIdx.x] = flags[threadIdx.x];
+  if (threadIdx.x == 0) {
+    uint32_t* cnt = flags[rank] + 2 * AR_MAX_CTAS * AR_MAX_WORLD + blockIdx.x;
+    s_seq = *cnt + 1u;
+    *cnt = s_seq;
+  }
+  __syncthreads();
+  const uint32_t seq = s_seq;
+  ar_barrier(s_flag, rank, world, 0, seq);
+  const long long per = (n4 + world - 1) / world;
+  const long long lo = (long long)rank * per, hi = (lo + per < n4) ? lo + per : n4;
+  const long long stride = (long long)gridDim.x * AR_THREADS;
+  float4* base = mc + off4;
+  constexpr int U = 8;
+  for (long long i0 = lo + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i0 < hi; i0 += U * stride) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < hi) v[u] = multimem_ld_reduce_add(base + i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < hi) multimem_st(base + i, v[u]);
+    }
+  }
+  ar_barrier(s_flag, rank, world, 1, seq);
+}
+
 template <int WORLD>
 __global__ void __launch_bounds__(AR_THREADS)
 allreduce_p2p_kernel(float* const* __restrict__ ptrs, uint32_t* const* __restrict__ flags, int rank, int world_rt,
@@ -144,8 +195,8 @@ using namespace tnr;
 
 TNR_API long long tnr_allreduce_p2p_flag_words(void) { return AR_FLAG_WORDS; }
 
-TNR_API int tnr_allreduce_p2p(void* const* ptrs_dev, void* const* flags_dev, int rank, int world, long long off,
-                              long long n, int n_ctas, void* stream) {
+TNR_API int tnr_allreduce_p2p(void* const* ptrs_dev, void* multicast_ptr, void* const* flags_dev, int rank, int world,
+                              long long off, long long n, int n_ctas, void* stream) {
   TNR_REQUIRE(ptrs_dev != nullptr && flags_dev != nullptr, "tnr_allreduce_p2p: null pointer tables");
   TNR_REQUIRE(world >= 1 && world <= AR_MAX_WORLD && rank >= 0 && rank < world, "tnr_allreduce_p2p: rank %d / world %d", rank, world);
   TNR_REQUIRE(off % 4 == 0 && n % 4 == 0 && off >= 0 && n >= 0, "tnr_allreduce_p2p: offset and count must be multiples of 4 floats");
@@ -154,6 +205,12 @@ TNR_API int tnr_allreduce_p2p(void* const* ptrs_dev, void* const* flags_dev, int
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* const* pp = reinterpret_cast<float* const*>(ptrs_dev);
   uint32_t* const* ff = reinterpret_cast<uint32_t* const*>(flags_dev);
+  if (multicast_ptr != nullptr) {
+    TNR_REQUIRE((uintptr_t)multicast_ptr % 16 == 0, "tnr_allreduce_p2p: multicast pointer must be 16-byte aligned");
+    allreduce_nvls_kernel<<<n_ctas, AR_THREADS, 0, st>>>(reinterpret_cast<float4*>(multicast_ptr), ff, rank, world, off / 4, n / 4);
+    TNR_LAUNCH_CHECK();
+    return 0;
+  }
   switch (world) {
     case 2: allreduce_p2p_kernel<2><<<n_ctas, AR_THREADS, 0, st>>>(pp, ff, rank, world, off / 4, n / 4); break;
     case 4: allreduce_p2p_kernel<4><<<n_ctas, AR_THREADS, 0, st>>>(pp, ff, rank, world, off / 4, n / 4); break;

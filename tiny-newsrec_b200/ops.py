@@ -96,7 +96,8 @@ def _timed(fn):
                   {ACT_NONE: "", ACT_GELU: "+gelu", ACT_TANH: "+tanh", ACT_DGELU: "+dgelu", ACT_GELU_DAUX: "+gelu",
                    ACT_MULAUX: "+mulaux"}[k.get("act", ACT_NONE)] + \
                   ("+aux" if k.get("aux") is not None and k.get("act") in (ACT_GELU, ACT_GELU_DAUX) else "") + \
-                  ("+res" if k.get("residual") is not None else "") + ("+bias" if k.get("bias") is not None else "")
+                  ("+res" if k.get("residual") is not None else "") + ("+bias" if k.get("bias") is not None else "") + \
+                  ("+ln" if k.get("ln") is not None else "")
         stats.op_events.append((fn.__name__, tag, e0, e1))
         return r
     return wrap
@@ -108,13 +109,33 @@ def _ready(t, kernels=1):
     return _lib.load()
 
 
+_ln_ws = {}
+
+
+def gemm_ln_supported(M, N):
+    """Shapes the fused LayerNorm epilogue of tnr_gemm_bf16 takes (CTA-pair kernels: M >= 4096, N a multiple of 256)."""
+    return bool(_lib.load().tnr_gemm_ln_supported(int(M), int(N)))
+
+
+def _ln_workspace(device, M, N):
+    """Workspace of the fused LayerNorm epilogue, one per (device, N), grown on demand; the arrival counters at its
+    front are zeroed when it is allocated and kept consistent by the kernels afterwards."""
+    need = int(_lib.load().tnr_gemm_ln_ws_bytes(int(M), int(N)))
+    key = (device, N)
+    ws = _ln_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _ln_ws[key] = torch.zeros(need, device=device, dtype=torch.uint8)
+    return ws
+
+
 @_timed
 def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, aux=None,
-         split_k=1, accumulate=False, drop=None, colsum=None):
+         split_k=1, accumulate=False, drop=None, colsum=None, ln=None, ln_pre=None):
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).
 
     a: bf16 [M,K] (or [K,M] when ``a_t``); b: bf16 [N,K] (or [K,N] when ``b_t``); 2-D, unit
-    inner stride.  out: bf16 or fp32 [M,N].  See tnr_gemm_bf16 in include/tinyrec.h.
+    inner stride.  out: bf16 or fp32 [M,N].  ``ln=(gamma, beta, eps)``: the epilogue's value goes through a LayerNorm over
+    the row (fused; ``ln_pre`` optionally receives the un-normalised value).  See tnr_gemm_bf16 in include/tinyrec.h.
     """
     lib = _ready(a)
     _chk(a, _bf16, "gemm.a"); _chk(b, _bf16, "gemm.b")
@@ -150,6 +171,16 @@ def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_N
         g.drop = ctypes.pointer(drop)
     if colsum is not None:
         g.colsum = _chk(colsum, _f32, "gemm.colsum").data_ptr()
+    if ln is not None:
+        gamma, beta, eps = ln
+        g.ln_gamma = _chk(gamma, _f32, "gemm.ln_gamma").data_ptr()
+        g.ln_beta = _chk(beta, _f32, "gemm.ln_beta").data_ptr()
+        g.ln_eps = float(eps)
+        if ln_pre is not None:
+            _chk(ln_pre, _bf16, "gemm.ln_pre")
+            g.ln_pre, g.ld_pre = ln_pre.data_ptr(), ln_pre.stride(0)
+        ws = _ln_workspace(a.device, M, N)         # keep a reference: the launch is asynchronous
+        g.ln_ws = ws.data_ptr()
     if stats.gemm_events is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -537,13 +568,15 @@ def host_copy(dst, src, n_threads=4):
     return dst
 
 
-def allreduce_p2p(ptrs_dev, flags_dev, rank, world, off, n, n_ctas):
+def allreduce_p2p(ptrs_dev, multicast_ptr, flags_dev, rank, world, off, n, n_ctas):
     """In-place sum all-reduce of floats [off, off + n) of a symmetric fp32 buffer over NVLink peer memory
-    (tnr_allreduce_p2p); ``ptrs_dev`` / ``flags_dev`` are device addresses of the per-rank pointer tables."""
+    (tnr_allreduce_p2p); ``ptrs_dev`` / ``flags_dev`` are device addresses of the per-rank pointer tables,
+    ``multicast_ptr`` the NVLS multicast address of the buffer (0: peer loads / stores)."""
     lib = _lib.load()
     stats.launches += 1
-    _lib.check(lib.tnr_allreduce_p2p(ctypes.c_void_p(int(ptrs_dev)), ctypes.c_void_p(int(flags_dev)), int(rank), int(world),
-                                     int(off), int(n), int(n_ctas), _stream()), "tnr_allreduce_p2p")
+    _lib.check(lib.tnr_allreduce_p2p(ctypes.c_void_p(int(ptrs_dev)), ctypes.c_void_p(int(multicast_ptr) or None),
+                                     ctypes.c_void_p(int(flags_dev)), int(rank), int(world), int(off), int(n), int(n_ctas),
+                                     _stream()), "tnr_allreduce_p2p")
 
 
 def set_sm_reserve(n_sms, device=None):

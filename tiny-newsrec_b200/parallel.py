@@ -128,6 +128,13 @@ class SymmetricGradBuffer:
         self.flags_hdl = symm.rendezvous(self.flags, group)
         self.ptrs_dev = int(self.grad_hdl.buffer_ptrs_dev)
         self.flags_dev = int(self.flags_hdl.buffer_ptrs_dev)
+        # NVLS: the same buffer at a multicast address (reduce in the switch); 0 when the fabric has no multicast
+        self.mc_ptr = 0
+        if os.environ.get("TNR_NVLS", "1") != "0":
+            try:
+                self.mc_ptr = int(self.grad_hdl.multicast_ptr or 0)
+            except Exception:  # noqa: BLE001
+                self.mc_ptr = 0
         torch.cuda.synchronize(device)
         dist.barrier()                       # every rank's flag page is zero before anyone's first kernel
 
@@ -139,4 +146,4 @@ class SymmetricGradBuffer:
     def all_reduce(self, lo, hi, n_ctas):
         """sum-all-reduce self.grad[lo:hi] in place on the current stream"""
         from . import ops
-        ops.allreduce_p2p(self.ptrs_dev, self.flags_dev, self.rank, self.world, lo, hi - lo, n_ctas)
+        ops.allreduce_p2p(self.ptrs_dev, self.mc_ptr, self.flags_dev, self.rank, self.world, lo, hi - lo, n_ctas)
