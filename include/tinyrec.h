@@ -91,19 +91,8 @@ typedef struct {
   const tnr_dropout* drop;   /* v = dropout(acc + bias) before the residual add; NULL = off (plain epilogue only) */
   float* colsum;             /* if != NULL (bf16 output only): colsum[n] += sum_m C[m,n] of the rounded bf16 output --
                                 the bias gradient of the layer in front (fp32 atomics), fused into the dgrad epilogue */
-  /* Fused LayerNorm epilogue -- LN(dropout(dense(h)) + input) of BertSelfOutput / BertOutput (transformers, used at
-   * tnlrv3/modeling.py:287,306): with ln_gamma != NULL, C <- (v - mean_row(v)) * rstd_row(v) * gamma[n] + beta[n] where v is
-   * the plain epilogue's value rounded to bf16, statistics over all N columns of the row (fp32; the 64-column slices of a
-   * row meet through ln_ws).  ln_pre != NULL also stores v itself (what the LayerNorm backward recomputes from).
-   * Needs tnr_gemm_ln_supported(M, N), bf16 C, act NONE, no split-K; ln_ws: tnr_gemm_ln_ws_bytes(M, N) bytes whose first
-   * ((M + 127) / 128) * 16 bytes were zeroed ONCE when it was allocated (monotonic arrival counters). */
-  const float* ln_gamma; const float* ln_beta; float ln_eps;
-  void* ln_pre; int ld_pre;
-  void* ln_ws;
 } tnr_gemm_args;
 int tnr_gemm_bf16(const tnr_gemm_args* args, void* stream);
-int tnr_gemm_ln_supported(int M, int N);
-long long tnr_gemm_ln_ws_bytes(int M, int N);
 
 /* ------------------------------------------------- encoder row kernels (HBM-bound) */
 /* out[t,:] = LayerNorm_eps( word[ids[t]] + pos[t % L] + type0 )  ->  bf16 [n_rows*L, E].

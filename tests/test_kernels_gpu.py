@@ -39,45 +39,6 @@ def test_gemm_nt_plain(M, N, K):
     assert rel < 5e-3, (rel, mx)
 
 
-@pytest.mark.parametrize("M,N,K,with_pre,with_drop", [(4100, 768, 768, True, False), (5000, 768, 3072, False, False),
-                                                      (8192, 768, 768, True, True), (4097, 256, 128, False, False),
-                                                      (4608, 1024, 256, True, False)])
-def test_gemm_fused_layernorm_epilogue(M, N, K, with_pre, with_drop):
-    """LN(dropout(A W^T + b) + residual) inside the GEMM epilogue (BertSelfOutput / BertOutput, transformers via
-    tnlrv3/modeling.py:287,306) == the un-fused GEMM followed by tnr_layernorm_fwd, and == torch; ragged last row tile,
-    repeated launches on the same workspace (monotonic arrival counters), the optional un-normalised output."""
-    ops = _ops()
-    assert ops.gemm_ln_supported(M, N) and not ops.gemm_ln_supported(4095, N) and not ops.gemm_ln_supported(M, 200)
-    a, b = _randn(M, K, seed=1), _randn(N, K, scale=0.05, seed=2)
-    bias = _randn(N, dtype=torch.float32, scale=0.2, seed=3)
-    res = _randn(M, N, seed=4)
-    gamma = 1.0 + _randn(N, dtype=torch.float32, scale=0.1, seed=5)
-    beta = _randn(N, dtype=torch.float32, scale=0.1, seed=6)
-    seed = torch.tensor([1234], device="cuda", dtype=torch.int64)
-    drop = ops.make_drop(seed, 17, 0.1) if with_drop else None
-    eps = 1e-12
-    # un-fused reference path of the same library
-    pre_ref = torch.empty(M, N, device="cuda", dtype=BF)
-    ops.gemm(a, b, pre_ref, bias=bias, residual=res, drop=drop)
-    y_ref = torch.empty_like(pre_ref)
-    ops.layernorm_fwd(pre_ref, gamma, beta, eps, y_ref)
-    for rep in range(3):                               # the workspace counters must stay consistent across launches
-        y = torch.full((M, N), float("nan"), device="cuda", dtype=BF)
-        pre = torch.full((M, N), float("nan"), device="cuda", dtype=BF) if with_pre else None
-        ops.gemm(a, b, y, bias=bias, residual=res, drop=drop, ln=(gamma, beta, eps), ln_pre=pre)
-        torch.cuda.synchronize()
-        assert torch.isfinite(y.float()).all()
-        if with_pre:
-            assert torch.equal(pre, pre_ref)           # same arithmetic, same rounding
-        # statistics are summed in a different order than the row kernel's: one bf16 ulp at most
-        rel, mx = _rel_err(y, y_ref)
-        assert rel < 3e-3 and mx < 0.07, (rep, rel, mx)
-    if not with_drop:
-        z = a.float() @ b.float().t() + bias + res.float()
-        ref = torch.nn.functional.layer_norm(z, (N,), gamma, beta, eps)
-        assert _rel_err(y, ref)[0] < 6e-3
-
-
 def test_gemm_fp32_out_bias_residual():
     ops = _ops()
     M, N, K = 777, 768, 768

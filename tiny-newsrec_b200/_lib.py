@@ -40,10 +40,7 @@ class GemmArgs(Structure):
                 ("split_k", c_int),
                 ("accumulate", c_int),
                 ("drop", POINTER(Dropout)),
-                ("colsum", c_void_p),
-                ("ln_gamma", c_void_p), ("ln_beta", c_void_p), ("ln_eps", c_float),
-                ("ln_pre", c_void_p), ("ld_pre", c_int),
-                ("ln_ws", c_void_p)]
+                ("colsum", c_void_p)]
 
 
 P = c_void_p
@@ -55,8 +52,6 @@ _SIGNATURES = {
     "tnr_allreduce_p2p_flag_words": ([], c_int64),
     "tnr_allreduce_p2p": ([P, P, P, c_int, c_int, c_int64, c_int64, c_int, P], c_int),
     "tnr_gemm_bf16": ([POINTER(GemmArgs), P], c_int),
-    "tnr_gemm_ln_supported": ([c_int, c_int], c_int),
-    "tnr_gemm_ln_ws_bytes": ([c_int, c_int], c_int64),
     "tnr_dropout_mask": ([POINTER(Dropout), c_int64, P, P], c_int),
     "tnr_embed_ln_fwd": ([P, c_int, c_int, c_int, c_int, P, c_int, P, P, P, P, c_float, c_int, P, POINTER(Dropout), P], c_int),
     "tnr_layernorm_fwd": ([P, c_int, c_int, P, P, c_float, P, P], c_int),

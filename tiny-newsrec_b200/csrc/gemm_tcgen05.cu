@@ -48,11 +48,6 @@ struct Params {
   int in_mode;        // 0 none, 1 residual box prefetched by TMA, 2 dGELU pre-activation box
   int aux_out;        // GELU pre-activation written through TMA
   float* colsum;      // column sums of the bf16 output (bias gradient), fp32 atomics; NULL = off
-  // fused LayerNorm epilogue (LN template flag): C <- LN(v) gamma + beta over the N columns of a row
-  const float* ln_gamma; const float* ln_beta; float ln_eps;
-  int pre_out;                 // the un-normalised v (bf16) also goes out (tmap_aux): what the LN backward recomputes from
-  unsigned int* ln_cnt;        // [m_tiles * 4] arrival counters, monotonic (never reset: 4 * n_tiles arrivals per launch each)
-  float2* ln_part;             // [m_tiles * 4][4 * n_tiles][32] partial (mean, M2) of a row over a 64-column slice
 };
 
 // Shared-memory matrix descriptor (sm_100 format, version 1, SWIZZLE_128B).
@@ -271,63 +266,8 @@ __device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg&
   *reinterpret_cast<bf16x8*>(out_box + swz) = o;
 }
 
-// Fused-LayerNorm epilogue, first pass over 8 columns: v = dropout(acc + bias) + residual rounded to bf16 (the value the
-// separate LayerNorm kernel would have read back from HBM), left as fp32 in acc[] and, if asked for, as bf16 in the box.
-__device__ __forceinline__ void epilogue_ln_pre8(const Params& p, const DropCfg& dc, uint32_t* acc, int row, int col,
-                                                 uint8_t* box, uint32_t swz) {
-  f32x2 v[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = pk2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-  if (p.bias != nullptr) {
-    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
-    v[0] = add2(v[0], pk2(b0.x, b0.y)); v[1] = add2(v[1], pk2(b0.z, b0.w));
-    v[2] = add2(v[2], pk2(b1.x, b1.y)); v[3] = add2(v[3], pk2(b1.z, b1.w));
-  }
-  if (dc.thr16 != 0) {
-    const uint32_t keep = dropout_keep8(dc, ((uint64_t)row * (uint64_t)p.N + (uint64_t)col) >> 3);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      v[i] = mul2(v[i], pk2(((keep >> (2 * i)) & 1u) ? dc.scale : 0.f, ((keep >> (2 * i + 1)) & 1u) ? dc.scale : 0.f));
-  }
-  if (p.in_mode == 1) {
-    const bf16x8 rr = *reinterpret_cast<const bf16x8*>(box + swz);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = add2(v[i], pk2(bf16_lo(rr.u[i]), bf16_hi(rr.u[i])));
-  }
-  bf16x8 o;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float lo, hi;
-    upk2(v[i], lo, hi);
-    o.u[i] = pack_bf16(lo, hi);
-    acc[2 * i] = __float_as_uint(bf16_lo(o.u[i]));
-    acc[2 * i + 1] = __float_as_uint(bf16_hi(o.u[i]));
-  }
-  if (p.pre_out) *reinterpret_cast<bf16x8*>(box + swz) = o;
-}
-
-// second pass: (v - mean) * rstd * gamma + beta -> bf16 box
-__device__ __forceinline__ void epilogue_ln_norm8(const Params& p, const uint32_t* acc, float mean, float rstd, int col,
-                                                  uint8_t* box, uint32_t swz) {
-  const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col));
-  const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col + 4));
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col));
-  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col + 4));
-  const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-  const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-  bf16x8 o;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float y0 = fmaf((__uint_as_float(acc[2 * i]) - mean) * rstd, g[2 * i], b[2 * i]);
-    const float y1 = fmaf((__uint_as_float(acc[2 * i + 1]) - mean) * rstd, g[2 * i + 1], b[2 * i + 1]);
-    o.u[i] = pack_bf16(y0, y1);
-  }
-  *reinterpret_cast<bf16x8*>(box + swz) = o;
-}
-
 // ---------------------------------------------------------------- kernel
-template <int BN, bool A_MN, bool B_MN, int ACT, bool EPI_TMA, bool CTA2, bool LN = false>
+template <int BN, bool A_MN, bool B_MN, int ACT, bool EPI_TMA, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_in,
@@ -538,73 +478,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           __syncwarp();
         }
         const int row = row0 + lane;
-        if (LN) {
-          // ---- fused LayerNorm (BertSelfOutput / BertOutput: LN(dropout(dense) + input)).  A row's N columns span
-          // n_tiles x 4 of these 64-column warp blocks, held by as many warps in up to n_tiles CTAs: every warp publishes
-          // the (mean, M2) of its slice, arrives on the row block's counter, waits for the others (tiles of one row block
-          // have consecutive indices, so they are in flight in the same or the next round of the persistent grid) and
-          // combines the partials with the equal-count form of Chan's formula.
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            epilogue_ln_pre8(p, dc, r + c * 8, row, col0 + c * 8, box, swz_row + (uint32_t)((c ^ (lane & 7)) << 4));
-          if (p.pre_out) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmap_aux, box_u32, col0, row0);
-              bulk_commit();
-            }
-          }
-          float sum = 0.f;
-#pragma unroll
-          for (int i = 0; i < 64; ++i) sum += __uint_as_float(r[i]);
-          const float mean_l = sum * (1.0f / 64.0f);
-          float m2 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 64; ++i) { const float d = __uint_as_float(r[i]) - mean_l; m2 = fmaf(d, d, m2); }
-          const int n_slices = 4 * p.n_tiles;
-          const int rb = m_blk * 4 + quarter;                               // row block: 32 rows
-          float2* part = p.ln_part + ((size_t)rb * n_slices) * 32;
-          __stcg(part + (size_t)(n_blk * 4 + slice) * 32 + lane, make_float2(mean_l, m2));
-          __syncwarp();
-          unsigned int target = 0;
-          if (lane == 0) {
-            __threadfence();
-            const unsigned int old = atomicAdd(p.ln_cnt + rb, 1u);
-            target = (old / (unsigned)n_slices + 1u) * (unsigned)n_slices;   // the count at which this launch's arrivals are in
-            unsigned int spins = 0;
-            while ((int)(*reinterpret_cast<volatile unsigned int*>(p.ln_cnt + rb) - target) < 0) {
-              __nanosleep(32);
-              if (++spins > (1u << 24)) __trap();                           // a protocol bug must be an error, not a hang
-            }
-            __threadfence();
-          }
-          __syncwarp();
-          float msum = 0.f, m2sum = 0.f, msq = 0.f;
-          for (int s = 0; s < n_slices; ++s) {
-            const float2 q = __ldcg(part + (size_t)s * 32 + lane);
-            msum += q.x; m2sum += q.y; msq = fmaf(q.x, q.x, msq);
-          }
-          const float inv_s = 1.0f / (float)n_slices;
-          const float mean = msum * inv_s;
-          // M2 = sum M2_i + 64 sum (mean_i - mean)^2 ;  sum (mean_i - mean)^2 = sum mean_i^2 - n mean^2
-          const float var = (m2sum + 64.0f * fmaxf(msq - (float)n_slices * mean * mean, 0.f)) / (64.0f * (float)n_slices);
-          const float rstd = rsqrtf(var + p.ln_eps);
-          if (p.pre_out) {                                                  // the box is still being read by the pre store
-            if (lane == 0) bulk_wait_read<0>();
-            __syncwarp();
-          }
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            epilogue_ln_norm8(p, r + c * 8, mean, rstd, col0 + c * 8, box, swz_row + (uint32_t)((c ^ (lane & 7)) << 4));
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmap_c, box_u32, col0, row0);
-            bulk_commit();
-          }
-          continue;
-        }
         if ((ACT == TNR_ACT_GELU || ACT == TNR_ACT_GELU_DAUX) && p.aux_out) {
           // pre-activation z = acc + bias (GELU) or gelu'(z) (GELU_DAUX) goes out first through the same box
 #pragma unroll
@@ -725,10 +598,10 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t 
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN, int ACT, bool EPI_TMA, bool CTA2 = false, bool LN = false>
+template <int BN, bool A_MN, bool B_MN, int ACT, bool EPI_TMA, bool CTA2 = false>
 static int launch(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
   using C = Cfg<BN, EPI_TMA, CTA2>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, ACT, EPI_TMA, CTA2, LN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, ACT, EPI_TMA, CTA2>;
   TNR_SET_SMEM(kern, C::SMEM_BYTES);
   if (CTA2) {
     // `grid` counts CTA pairs: launch them as clusters of 2 (the two SMs of one TPC)
@@ -797,17 +670,6 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* maps, const P
 }  // namespace gemm
 }  // namespace tnr
 
-extern "C" __attribute__((visibility("default"))) int tnr_gemm_ln_supported(int M, int N) {
-  return M >= 4096 && N % 256 == 0 && N >= 256 && N <= 1024;
-}
-
-// workspace of the fused LayerNorm epilogue: [m_tiles * 4] uint32 arrival counters (ZERO them once, when the buffer is
-// allocated; the kernels keep them consistent), then [m_tiles * 4][N / 64][32] float2 partial statistics
-extern "C" __attribute__((visibility("default"))) long long tnr_gemm_ln_ws_bytes(int M, int N) {
-  const long long m_tiles = (M + tnr::gemm::BM - 1) / tnr::gemm::BM;
-  return ((m_tiles * 4 * 4 + 255) / 256) * 256 + m_tiles * 4 * (long long)(N / 64) * 32 * 8;
-}
-
 extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_gemm_args* a, void* stream) {
   using namespace tnr;
   using namespace tnr::gemm;
@@ -858,19 +720,6 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
   p.colsum = a->colsum;
   TNR_REQUIRE(a->colsum == nullptr || (a->c_dtype == TNR_BF16 && !atomic),
               "tnr_gemm_bf16: colsum needs a bf16 (TMA-staged) output");
-  p.ln_gamma = a->ln_gamma; p.ln_beta = a->ln_beta; p.ln_eps = a->ln_eps; p.pre_out = 0;
-  p.ln_cnt = nullptr; p.ln_part = nullptr;
-  if (a->ln_gamma != nullptr) {
-    TNR_REQUIRE(tnr_gemm_ln_supported(a->M, a->N) && !a_mn && !atomic && a->c_dtype == TNR_BF16 && a->act == TNR_ACT_NONE &&
-                    a->colsum == nullptr && a->ln_beta != nullptr && a->ln_ws != nullptr && cta2_env != 0,
-                "tnr_gemm_bf16: the fused LayerNorm epilogue needs a bf16 output, the plain (bias / dropout / residual) "
-                "epilogue, M >= 4096, N a multiple of 256 up to 1024, gamma, beta and a workspace (tnr_gemm_ln_ws_bytes)");
-    TNR_REQUIRE((uintptr_t)a->ln_gamma % 16 == 0 && (uintptr_t)a->ln_beta % 16 == 0 && (uintptr_t)a->ln_ws % 16 == 0,
-                "tnr_gemm_bf16: LayerNorm parameters / workspace must be 16-byte aligned");
-    const int m_tiles = (a->M + BM - 1) / BM;
-    p.ln_cnt = reinterpret_cast<unsigned int*>(a->ln_ws);
-    p.ln_part = reinterpret_cast<float2*>(reinterpret_cast<char*>(a->ln_ws) + (((size_t)m_tiles * 4 * 4 + 255) / 256) * 256);
-  }
   TNR_REQUIRE(p.drop.seed == nullptr || !(p.drop.p > 0.f) || (!atomic && a->act == TNR_ACT_NONE),
               "tnr_gemm_bf16: dropout is supported with the plain (bias + residual) epilogue only");
 
@@ -900,11 +749,6 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
       p.aux_out = 1;
       if (make_map(&maps[4], a->aux, a->N, a->M, a->ldaux, 64, 32)) return 1;
     }
-    if (a->ln_gamma != nullptr && a->ln_pre != nullptr) {
-      TNR_REQUIRE(a->ld_pre % 8 == 0 && (uintptr_t)a->ln_pre % 16 == 0, "tnr_gemm_bf16: ln_pre alignment");
-      p.pre_out = 1;
-      if (make_map(&maps[4], a->ln_pre, a->N, a->M, a->ld_pre, 64, 32)) return 1;
-    }
   }
 
   int sms = num_sms();
@@ -915,9 +759,6 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
   if (cta2) {
     const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles * p.splits;
     const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
-    if (a->ln_gamma != nullptr)
-      return b_mn ? launch<256, false, true, TNR_ACT_NONE, true, true, true>(maps, p, pairs, st)
-                  : launch<256, false, false, TNR_ACT_NONE, true, true, true>(maps, p, pairs, st);
     if (a_mn) return launch<256, true, true, TNR_ACT_NONE, false, true>(maps, p, pairs, st);
     return b_mn ? dispatch_act_cta2<true>(maps, p, pairs, st) : dispatch_act_cta2<false>(maps, p, pairs, st);
   }

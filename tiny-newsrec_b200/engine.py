@@ -15,9 +15,6 @@ from ._lib import TinyRecError
 BF = torch.bfloat16
 F32 = torch.float32
 LN_EPS = 1e-12            # tnlrv3/configuration_tnlrv3.py:61
-import os as _os
-FUSE_LN = _os.environ.get("TNR_FUSE_LN", "1") != "0"          # LayerNorm inside the O-proj / FFN2 GEMM epilogues
-FUSE_LN_SITES = _os.environ.get("TNR_FUSE_LN_SITES", "12")   # which of the two per-layer sites ("1": attention output, "2": FFN output)
 
 # dropout tensor ids ("sites", include/tinyrec.h tnr_dropout.site): one Philox stream per tensor
 SITE_EMB = 0              # embeddings output, tnlrv3/modeling.py:177
@@ -320,8 +317,6 @@ class Encoder:
         emb = self.bert.embeddings
         relpos = self.relpos(L)
         cur = ws["x0"]
-        fuse = FUSE_LN and ops.gemm_ln_supported(n * L, self.E)
-        fuse_ln1, fuse_ln2 = fuse and "1" in FUSE_LN_SITES, fuse and "2" in FUSE_LN_SITES
         dmk = (lambda site, p: drop.make(site, p)) if drop is not None else (lambda site, p: None)
         ph, pa = (drop.p_hidden, drop.p_attn) if drop is not None else (0.0, 0.0)
         ops.embed_ln(x, L, self.word_table(), emb.position_embeddings.weight, emb.token_type_embeddings.weight[0],
@@ -337,24 +332,12 @@ class Encoder:
                 xout = ws["xb"] if cur is ws["xa"] else ws["xa"]
             ops.gemm(cur, wqkv, qkv, bias=bqkv)
             ops.attn_fwd(qkv, x, L, relpos, ctx, self.A, drop=dmk(drop_site(i, KIND_ATTN), pa))
-            # BertSelfOutput / BertOutput: LN(dropout(dense) + input).  Large batches run the LayerNorm INSIDE the GEMM
-            # epilogue (the 64-column slices of a row exchange their statistics through a small workspace); the
-            # un-normalised sums are stored only where the backward needs them (trained layers).
-            saved = i >= low
-            if fuse_ln1:
-                ops.gemm(ctx, wo, x1, bias=lr.o.bias, residual=cur, drop=dmk(drop_site(i, KIND_ATT_OUT), ph),
-                         ln=(lr.ln1.weight, lr.ln1.bias, self.ln_eps), ln_pre=pre1 if saved else None)
-            else:
-                ops.gemm(ctx, wo, pre1, bias=lr.o.bias, residual=cur, drop=dmk(drop_site(i, KIND_ATT_OUT), ph))
-                ops.layernorm_fwd(pre1, lr.ln1.weight, lr.ln1.bias, self.ln_eps, x1)
+            ops.gemm(ctx, wo, pre1, bias=lr.o.bias, residual=cur, drop=dmk(drop_site(i, KIND_ATT_OUT), ph))
+            ops.layernorm_fwd(pre1, lr.ln1.weight, lr.ln1.bias, self.ln_eps, x1)
             # trained layers keep gelu'(z) (not z) for the backward: its dgrad epilogue is then a single multiply
             ops.gemm(x1, w1, h, bias=lr.f1.bias, act=ops.ACT_GELU_DAUX if z is not None else ops.ACT_GELU, aux=z)
-            if fuse_ln2:
-                ops.gemm(h, w2, xout, bias=lr.f2.bias, residual=x1, drop=dmk(drop_site(i, KIND_FFN_OUT), ph),
-                         ln=(lr.ln2.weight, lr.ln2.bias, self.ln_eps), ln_pre=pre2 if saved else None)
-            else:
-                ops.gemm(h, w2, pre2, bias=lr.f2.bias, residual=x1, drop=dmk(drop_site(i, KIND_FFN_OUT), ph))
-                ops.layernorm_fwd(pre2, lr.ln2.weight, lr.ln2.bias, self.ln_eps, xout)
+            ops.gemm(h, w2, pre2, bias=lr.f2.bias, residual=x1, drop=dmk(drop_site(i, KIND_FFN_OUT), ph))
+            ops.layernorm_fwd(pre2, lr.ln2.weight, lr.ln2.bias, self.ln_eps, xout)
             cur = xout
         at = self.mod.attn
         ops.gemm(cur, self._w(flat, at.att_fc1.weight), ws["e"], bias=at.att_fc1.bias, act=ops.ACT_TANH)

@@ -96,8 +96,7 @@ def _timed(fn):
                   {ACT_NONE: "", ACT_GELU: "+gelu", ACT_TANH: "+tanh", ACT_DGELU: "+dgelu", ACT_GELU_DAUX: "+gelu",
                    ACT_MULAUX: "+mulaux"}[k.get("act", ACT_NONE)] + \
                   ("+aux" if k.get("aux") is not None and k.get("act") in (ACT_GELU, ACT_GELU_DAUX) else "") + \
-                  ("+res" if k.get("residual") is not None else "") + ("+bias" if k.get("bias") is not None else "") + \
-                  ("+ln" if k.get("ln") is not None else "")
+                  ("+res" if k.get("residual") is not None else "") + ("+bias" if k.get("bias") is not None else "")
         stats.op_events.append((fn.__name__, tag, e0, e1))
         return r
     return wrap
@@ -109,33 +108,13 @@ def _ready(t, kernels=1):
     return _lib.load()
 
 
-_ln_ws = {}
-
-
-def gemm_ln_supported(M, N):
-    """Shapes the fused LayerNorm epilogue of tnr_gemm_bf16 takes (CTA-pair kernels: M >= 4096, N a multiple of 256)."""
-    return bool(_lib.load().tnr_gemm_ln_supported(int(M), int(N)))
-
-
-def _ln_workspace(device, M, N):
-    """Workspace of the fused LayerNorm epilogue, one per (device, N), grown on demand; the arrival counters at its
-    front are zeroed when it is allocated and kept consistent by the kernels afterwards."""
-    need = int(_lib.load().tnr_gemm_ln_ws_bytes(int(M), int(N)))
-    key = (device, N)
-    ws = _ln_ws.get(key)
-    if ws is None or ws.numel() < need:
-        ws = _ln_ws[key] = torch.zeros(need, device=device, dtype=torch.uint8)
-    return ws
-
-
 @_timed
 def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_NONE, aux=None,
-         split_k=1, accumulate=False, drop=None, colsum=None, ln=None, ln_pre=None):
+         split_k=1, accumulate=False, drop=None, colsum=None):
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).
 
     a: bf16 [M,K] (or [K,M] when ``a_t``); b: bf16 [N,K] (or [K,N] when ``b_t``); 2-D, unit
-    inner stride.  out: bf16 or fp32 [M,N].  ``ln=(gamma, beta, eps)``: the epilogue's value goes through a LayerNorm over
-    the row (fused; ``ln_pre`` optionally receives the un-normalised value).  See tnr_gemm_bf16 in include/tinyrec.h.
+    inner stride.  out: bf16 or fp32 [M,N].  See tnr_gemm_bf16 in include/tinyrec.h.
     """
     lib = _ready(a)
     _chk(a, _bf16, "gemm.a"); _chk(b, _bf16, "gemm.b")
@@ -171,16 +150,6 @@ def gemm(a, b, out, *, a_t=False, b_t=False, bias=None, residual=None, act=ACT_N
         g.drop = ctypes.pointer(drop)
     if colsum is not None:
         g.colsum = _chk(colsum, _f32, "gemm.colsum").data_ptr()
-    if ln is not None:
-        gamma, beta, eps = ln
-        g.ln_gamma = _chk(gamma, _f32, "gemm.ln_gamma").data_ptr()
-        g.ln_beta = _chk(beta, _f32, "gemm.ln_beta").data_ptr()
-        g.ln_eps = float(eps)
-        if ln_pre is not None:
-            _chk(ln_pre, _bf16, "gemm.ln_pre")
-            g.ln_pre, g.ld_pre = ln_pre.data_ptr(), ln_pre.stride(0)
-        ws = _ln_workspace(a.device, M, N)         # keep a reference: the launch is asynchronous
-        g.ln_ws = ws.data_ptr()
     if stats.gemm_events is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
