@@ -286,6 +286,14 @@ int tnr_allreduce_p2p(void* const* ptrs_dev, void* multicast_ptr, void* const* f
  * idx outside [0, n_rows_table) maps to row 0 (dataloader.py:74).  Bit-exact. */
 int tnr_gather_rows_i32_i64(const int32_t* table, long long n_rows_table, const int32_t* idx,
                             long long n, int W, int64_t* out, void* stream);
+/* A whole training batch from its index arrays in one launch (dataloader.py:129-144): rows [history | candidates] of
+ * tokens_out int64 [n_hist + n_cand, W] = news[idx] widened, and for each of the M <= 8 teacher tables (host arrays of
+ * device pointers) teacher_out[i][r, :D] (row stride out_ld floats) = teacher_tables[i][idx[r], :].  Unknown ids read
+ * row 0.  Bit-exact copies. */
+int tnr_train_batch_gather(const int32_t* news, long long n_rows, int W, const float* const* teacher_tables,
+                           float* const* teacher_out, int M, int D, long long out_ld, const int32_t* hist_idx,
+                           long long n_hist, const int32_t* cand_idx, long long n_cand, long long* tokens_out,
+                           void* stream);
 /* out[r, :D] = table[idx[r], :]  fp32 (teacher_embs[i][idx], dataloader.py:142,144; news_scoring[idx] :295,301). */
 int tnr_gather_rows_f32(const float* table, long long n_rows_table, const int32_t* idx, long long n,
                         int D, float* out, long long out_ld, void* stream);

@@ -83,6 +83,8 @@ _SIGNATURES = {
     "tnr_cast_f32_bf16": ([P, P, c_int64, P], c_int),
     "tnr_gather_rows_i32_i64": ([P, c_int64, P, c_int64, c_int, P, P], c_int),
     "tnr_gather_rows_f32": ([P, c_int64, P, c_int64, c_int, P, c_int64, P], c_int),
+    "tnr_train_batch_gather": ([P, c_int64, c_int, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int64, P, c_int64, P,
+                                c_int64, P, P], c_int),
     "tnr_doc_sim": ([P, c_int64, P, c_int64, c_int, P, P], c_int),
     "tnr_eval_metrics": ([P, c_int64, P, P, P, P, c_int64, c_int64, c_int, c_int, P, P, P, P], c_int),
 }

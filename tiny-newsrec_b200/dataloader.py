@@ -70,29 +70,40 @@ class DeviceTables:
         self.device = self.news.device
 
 
+class TeacherViews(list):
+    """The per-teacher [B, H, D] / [B, K, D] views ``TrainBatcher.assemble`` returns, remembering the buffer they are
+    views of (``ext`` fp32 [M, B (H + K) + B, D]: history rows | candidate rows | room for the teachers' user vectors) --
+    exactly the layout ``Model.forward`` keeps its teacher matrices in, so the model adopts it instead of copying."""
+    ext = None
+
+
 class TrainBatcher:
-    """indices -> the six tensors ``Model.forward`` takes, gathered on the device."""
+    """indices -> the six tensors ``Model.forward`` takes, gathered on the device by ONE kernel launch."""
 
     def __init__(self, tables, B, H, K):
         self.t, self.B, self.H, self.K = tables, B, H, K
         dev, W = tables.device, tables.news.shape[1]
         M = len(tables.teachers)
-        D = tables.teachers[0].shape[1] if M else 0
-        self.history = torch.empty(B, H, W, device=dev, dtype=torch.int64)
-        self.candidate = torch.empty(B, K, W, device=dev, dtype=torch.int64)
-        self.th = torch.empty(max(M, 1), B, H, max(D, 4), device=dev, dtype=torch.float32)
-        self.tc = torch.empty(max(M, 1), B, K, max(D, 4), device=dev, dtype=torch.float32)
+        D = tables.teachers[0].shape[1] if M else 4
+        R = B * (H + K)
+        self.tokens = torch.empty(R, W, device=dev, dtype=torch.int64)            # [history rows | candidate rows]
+        self.history = self.tokens[:B * H].view(B, H, W)
+        self.candidate = self.tokens[B * H:].view(B, K, W)
+        self.ext = torch.zeros(max(M, 1), R + B, D, device=dev, dtype=torch.float32)
+        self.th, self.tc = TeacherViews(), TeacherViews()
+        for i in range(M):
+            self.th.append(self.ext[i, :B * H].view(B, H, D))
+            self.tc.append(self.ext[i, B * H:R].view(B, K, D))
+        self.th.ext = self.tc.ext = self.ext
         self.M = M
 
     def assemble(self, hist_idx, cand_idx):
         """hist_idx int32 [B,H], cand_idx int32 [B,K] (CUDA) -> history, candidate, [th], [tc]."""
-        hi, ci = hist_idx.reshape(-1), cand_idx.reshape(-1)
-        ops.gather_rows_i32_i64(self.t.news, hi, self.history.view(-1, self.history.shape[-1]))
-        ops.gather_rows_i32_i64(self.t.news, ci, self.candidate.view(-1, self.candidate.shape[-1]))
-        for i, tab in enumerate(self.t.teachers):
-            ops.gather_rows_f32(tab, hi, self.th[i].view(-1, tab.shape[1]))
-            ops.gather_rows_f32(tab, ci, self.tc[i].view(-1, tab.shape[1]))
-        return self.history, self.candidate, [self.th[i] for i in range(self.M)], [self.tc[i] for i in range(self.M)]
+        if hist_idx.numel() != self.B * self.H or cand_idx.numel() != self.B * self.K:
+            raise TinyRecError("TrainBatcher.assemble: index shapes do not match the batcher's (B, H, K)")
+        ops.train_batch_gather(self.t.news, self.t.teachers, hist_idx.reshape(-1), cand_idx.reshape(-1), self.tokens,
+                               [self.ext[i] for i in range(self.M)])
+        return self.history, self.candidate, self.th, self.tc
 
 
 def gather_history_vecs(news_scoring, hist_idx, out=None):

@@ -386,7 +386,7 @@ class TrainState:
                 flat.refresh_shadow()
             if want_grad:
                 flat.reattach_grads()
-        x = torch.cat([history.reshape(B * H, W), candidate.reshape(B * K, W)], 0)
+        x = _rows_of(history, candidate)
         D = self.enc.D
         Q = self.ue.attn.att_fc1.weight.shape[0]
         w = self.head_ws(B, H, K, M, D, Q, dev)
@@ -400,6 +400,12 @@ class TrainState:
         label = label.contiguous()
         at = self.ue.attn
         T, TP, G = w["T"], w["TP"], w["G"]
+        # teacher rows that the device loader already gathered into the [M, R + B, D] layout are used where they are
+        ext = getattr(th_list, "ext", None)
+        adopted = (M > 0 and ext is not None and ext is getattr(tc_list, "ext", None) and ext.is_cuda
+                   and tuple(ext.shape) == tuple(T.shape) and ext.dtype == F32 and ext.is_contiguous())
+        if adopted:
+            T = ext
         pool_vecs, pool_mask, pool_use_mask = news[:B * H], mask, use_mask
         if self.nrms:       # self-attention in front of every pooling (model_bert.py:162-164, :171-173)
             nb = w.setdefault("nrms", [dict() for _ in range(1 + M)])
@@ -411,8 +417,9 @@ class TrainState:
         encs = [dict(vecs=pool_vecs, pad_doc=self.ue.pad_doc.view(-1), W1=at.att_fc1.weight, b1=at.att_fc1.bias,
                      w2=at.att_fc2.weight.view(-1), b2=at.att_fc2.bias, user=w["user"], a=w["a"], e=w["e"])]
         for i in range(M):
-            T[i, :B * H].copy_(th_list[i].reshape(B * H, D))
-            T[i, B * H:R].copy_(tc_list[i].reshape(B * K, D))
+            if not adopted:
+                T[i, :B * H].copy_(th_list[i].reshape(B * H, D))
+                T[i, B * H:R].copy_(tc_list[i].reshape(B * K, D))
             t = self.teachers[i]
             tv = T[i, :B * H]
             if self.nrms:
@@ -536,6 +543,18 @@ class TrainState:
             self.comm_hook(flat, 0, done_to[0])
 
 
+def _rows_of(history, candidate):
+    """[history rows | candidate rows] as one int64 [B (H + K), 2L] matrix: the tensors themselves when the device
+    loader produced them adjacent in one buffer (tinyrec.dataloader.TrainBatcher), else a concatenated copy."""
+    B, H, W = history.shape
+    K = candidate.shape[1]
+    if (history.is_contiguous() and candidate.is_contiguous() and history.dtype == candidate.dtype
+            and history.untyped_storage().data_ptr() == candidate.untyped_storage().data_ptr()
+            and candidate.storage_offset() == history.storage_offset() + B * H * W):
+        return torch.as_strided(history, (B * (H + K), W), (W, 1))
+    return torch.cat([history.reshape(B * H, W), candidate.reshape(B * K, W)], 0)
+
+
 def _const_stride(tensors):
     """Element stride between consecutive fp32 tensors of a list if it is constant and 16-byte
     aligned (the flat buffer keeps transform_matrix.{i} that way), else None."""
@@ -646,7 +665,8 @@ class Model(nn.Module):
     def forward(self, history, history_mask, candidate, label, teacher_history_embs, teacher_candidate_embs):
         st = self.train_state()
         want_grad = torch.is_grad_enabled() and st.flat is not None
-        args = (history, history_mask, candidate, label, list(teacher_history_embs), list(teacher_candidate_embs),
+        keep = lambda t: t if isinstance(t, list) else list(t)  # noqa: E731  (TeacherViews carries the loader's buffer)
+        args = (history, history_mask, candidate, label, keep(teacher_history_embs), keep(teacher_candidate_embs),
                 float(self.args.temperature), float(self.args.coef), bool(self.args.user_log_mask), want_grad,
                 bool(self.training))
         if want_grad:

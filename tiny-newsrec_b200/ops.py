@@ -569,6 +569,31 @@ def gather_rows_i32_i64(table, idx, out):
 
 
 @_timed
+def train_batch_gather(news, teacher_tables, hist_idx, cand_idx, tokens_out, teacher_out):
+    """One launch: tokens_out int64 [n_hist + n_cand, W] = news[idx] and teacher_out[i][r, :] = teacher_tables[i][idx[r]]
+    for idx = [hist_idx | cand_idx] (tnr_train_batch_gather).  teacher_out: tensors [n_hist + n_cand (+ extra), D]."""
+    lib = _ready(news)
+    _chk(news, torch.int32, "batch_gather.news"); _chk(hist_idx, torch.int32, "batch_gather.hist_idx")
+    _chk(cand_idx, torch.int32, "batch_gather.cand_idx"); _chk(tokens_out, torch.int64, "batch_gather.tokens")
+    M = len(teacher_tables)
+    nh, nc, W = hist_idx.numel(), cand_idx.numel(), news.shape[1]
+    if tokens_out.numel() != (nh + nc) * W or not tokens_out.is_contiguous() or len(teacher_out) != M:
+        raise _lib.TinyRecError("train_batch_gather: shape / layout mismatch")
+    D = teacher_tables[0].shape[1] if M else 4
+    tabs = (ctypes.c_void_p * max(M, 1))()
+    outs = (ctypes.c_void_p * max(M, 1))()
+    ld = D
+    for i in range(M):
+        _chk(teacher_tables[i], _f32, "batch_gather.teacher"); _chk(teacher_out[i], _f32, "batch_gather.teacher_out")
+        if teacher_tables[i].shape[1] != D or teacher_out[i].shape[-1] != D or teacher_out[i].stride(-1) != 1:
+            raise _lib.TinyRecError("train_batch_gather: teacher tables / outputs must share the row width")
+        tabs[i], outs[i] = teacher_tables[i].data_ptr(), teacher_out[i].data_ptr()
+        ld = teacher_out[i].stride(-2)
+    _lib.check(lib.tnr_train_batch_gather(_ptr(news), news.shape[0], W, tabs, outs, M, D, ld, _ptr(hist_idx), nh, _ptr(cand_idx), nc,
+                                          _ptr(tokens_out), _stream()), "tnr_train_batch_gather")
+
+
+@_timed
 def gather_rows_f32(table, idx, out, out_ld=None):
     lib = _ready(table)
     _chk(table, _f32, "gather.table"); _chk(idx, torch.int32, "gather.idx"); _chk(out, _f32, "gather.out")
