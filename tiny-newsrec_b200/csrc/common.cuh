@@ -204,7 +204,7 @@ __device__ __forceinline__ DropCfg load_drop(const tnr_dropout& d) {
   c.site = d.site;
   if (d.seed == nullptr || !(d.p > 0.f)) { c.seed = 0; c.thr16 = 0; c.scale = 1.f; return c; }
   c.seed = *d.seed;
-  c.thr16 = (uint32_t)(d.p * 65536.0f + 0.5f);
+  c.thr16 = min((uint32_t)(d.p * 65536.0f + 0.5f), 65535u);
   c.scale = 1.0f / (1.0f - d.p);
   return c;
 }
@@ -221,6 +221,20 @@ __device__ __forceinline__ uint32_t dropout_keep8(const DropCfg& c, uint64_t g) 
     m |= ((w[i] >> 16) >= c.thr16 ? 1u : 0u) << (2 * i + 1);
   }
   return m;
+}
+
+// the same keep flags as dropout_keep8(), delivered as the four packed multiplier pairs (scale or 0) an epilogue applies
+// with one FMUL2 / FFMA2 per pair: the high lane of a word compares in place against thr16 << 16 (its low bits
+// cannot change the outcome), the low lane after one shift -- 2.5 instructions per element instead of 3.5.
+// thr16 <= 65535 (load_drop).
+__device__ __forceinline__ void dropout_mul8(const DropCfg& c, uint64_t g, f32x2* m) {
+  const uint4 r = philox4x32_7(make_uint4((uint32_t)g, (uint32_t)(g >> 32), c.site, 0u),
+                               make_uint2((uint32_t)c.seed, (uint32_t)(c.seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  const uint32_t thr_hi = c.thr16 << 16;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    m[i] = pk2((w[i] << 16) >= thr_hi ? c.scale : 0.f, w[i] >= thr_hi ? c.scale : 0.f);
 }
 
 inline tnr_dropout drop_or_none(const tnr_dropout* d) {

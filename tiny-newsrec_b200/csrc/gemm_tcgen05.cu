@@ -172,9 +172,10 @@ __device__ __forceinline__ void epilogue_preact8(const Params& p, const uint32_t
   f32x2 v[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = pk2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-  if (p.bias != nullptr && col < p.N) {
-    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+  if (p.bias != nullptr) {
+    const float* bp = p.bias + min(col, p.N - 8);
+    const float4 b0 = *reinterpret_cast<const float4*>(bp);
+    const float4 b1 = *reinterpret_cast<const float4*>(bp + 4);
     v[0] = add2(v[0], pk2(b0.x, b0.y)); v[1] = add2(v[1], pk2(b0.z, b0.w));
     v[2] = add2(v[2], pk2(b1.x, b1.y)); v[3] = add2(v[3], pk2(b1.z, b1.w));
   }
@@ -191,9 +192,10 @@ __device__ __forceinline__ void epilogue_gelu_both8(const Params& p, uint32_t* a
   f32x2 v[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = pk2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-  if (p.bias != nullptr && col < p.N) {
-    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+  if (p.bias != nullptr) {
+    const float* bp = p.bias + min(col, p.N - 8);
+    const float4 b0 = *reinterpret_cast<const float4*>(bp);
+    const float4 b1 = *reinterpret_cast<const float4*>(bp + 4);
     v[0] = add2(v[0], pk2(b0.x, b0.y)); v[1] = add2(v[1], pk2(b0.z, b0.w));
     v[2] = add2(v[2], pk2(b1.x, b1.y)); v[3] = add2(v[3], pk2(b1.z, b1.w));
   }
@@ -219,15 +221,17 @@ __device__ __forceinline__ void epilogue_gelu_both8(const Params& p, uint32_t* a
 }
 
 template <int ACT>
-__device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg& dc, const uint32_t* acc, int row, int col,
-                                                 uint8_t* out_box, uint8_t* in_box, uint32_t swz) {
+__device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg& dc, const uint32_t* acc, uint64_t drop_group,
+                                                 int col, uint8_t* out_box, uint8_t* in_box, uint32_t swz) {
   // four packed fp32 pairs (FFMA2 path, common.cuh)
   f32x2 v[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = pk2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
-  if (p.bias != nullptr && col < p.N) {
-    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col);
-    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col + 4);
+  if (p.bias != nullptr) {
+    // N % 8 == 0 (host check): a live chunk is entirely inside the row; dead columns re-read the last chunk
+    const float* bp = p.bias + min(col, p.N - 8);
+    const float4 b0 = *reinterpret_cast<const float4*>(bp);
+    const float4 b1 = *reinterpret_cast<const float4*>(bp + 4);
     v[0] = add2(v[0], pk2(b0.x, b0.y)); v[1] = add2(v[1], pk2(b0.z, b0.w));
     v[2] = add2(v[2], pk2(b1.x, b1.y)); v[3] = add2(v[3], pk2(b1.z, b1.w));
   }
@@ -249,13 +253,19 @@ __device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg&
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = gelu_erf2(v[i]);       // only reached without an aux output
   }
+  const bool has_res = ACT != TNR_ACT_DGELU && ACT != TNR_ACT_MULAUX && p.in_mode == 1;
   if (dc.thr16 != 0) {
-    const uint32_t keep = dropout_keep8(dc, ((uint64_t)row * (uint64_t)p.N + (uint64_t)col) >> 3);
+    f32x2 m[4];
+    dropout_mul8(dc, drop_group, m);
+    if (has_res) {                                            // residual + dropout(v): one FFMA2 per pair
+      const bf16x8 rr = *reinterpret_cast<const bf16x8*>(in_box + swz);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      v[i] = mul2(v[i], pk2(((keep >> (2 * i)) & 1u) ? dc.scale : 0.f, ((keep >> (2 * i + 1)) & 1u) ? dc.scale : 0.f));
-  }
-  if (ACT != TNR_ACT_DGELU && ACT != TNR_ACT_MULAUX && p.in_mode == 1) {
+      for (int i = 0; i < 4; ++i) v[i] = fma2(v[i], m[i], pk2(bf16_lo(rr.u[i]), bf16_hi(rr.u[i])));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = mul2(v[i], m[i]);
+    }
+  } else if (has_res) {
     const bf16x8 rr = *reinterpret_cast<const bf16x8*>(in_box + swz);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = add2(v[i], pk2(bf16_lo(rr.u[i]), bf16_hi(rr.u[i])));
@@ -265,6 +275,13 @@ __device__ __forceinline__ void epilogue_staged8(const Params& p, const DropCfg&
   for (int i = 0; i < 4; ++i) { float lo, hi; upk2(v[i], lo, hi); o.u[i] = pack_bf16(lo, hi); }
   *reinterpret_cast<bf16x8*>(out_box + swz) = o;
 }
+
+#ifdef GEMM_TIMING
+__device__ long long g_gemm_dbg[8192];       // debug build: clock64 stamps of CTA 0 (tools/gemm_timing.py)
+#define GEMM_STAMP(slot) do { if (blockIdx.x == 0 && (slot) < 8192) g_gemm_dbg[(slot)] = clock64(); } while (0)
+#else
+#define GEMM_STAMP(slot) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------- kernel
 template <int BN, bool A_MN, bool B_MN, int ACT, bool EPI_TMA, bool CTA2>
@@ -327,7 +344,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {                                             // whole warp walks the loop, one elected lane issues (see the MMA warp)
       int stage = 0; uint32_t phase = 0;
       for (int t = t_first; t < total_tiles; t += t_stride) {
         const int n_blk = t % p.n_tiles;
@@ -341,7 +358,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
-          if (CTA2) {
+          if (!elect_one()) {
+          } else if (CTA2) {
             // both CTAs' bytes land on the leader's barrier; only the leader arrives on it
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
             const uint32_t fb = mapa_cluster(full_bar(stage), 0);
@@ -376,44 +394,63 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 tma_load_2d(sb + i * (BK * 128), &tmap_b, full_bar(stage), n0 + i * 64, kb * BK);
             }
           }
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && cta_rank == 0) {             // CTA2: the leader issues for the pair
+    // The whole warp walks the loop (barrier waits included) and one elected lane issues: with warp-uniform
+    // control flow the descriptors, the TMEM address and the barrier addresses live in uniform registers, so a
+    // tcgen05.mma costs one UTCHMMA instead of an ELECT + R2UR broadcast chain per operand (measured with
+    // -DGEMM_TIMING: ~75 cycles per issue before, the issue thread -- not the tensor pipe -- paced a k-block).
+    if (cta_rank == 0) {                          // CTA2: the leader issues for the pair
       constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN, CTA2>();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = t_first; t < total_tiles; t += t_stride) {
         const int ks = t / (p.n_tiles * m_units);
         const int kb0 = ks * p.k_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.k_per_split);
+#ifdef GEMM_TIMING
+        const int tl_dbg = (t - t_first) / t_stride;
+#endif
+        if (lane == 0) GEMM_STAMP(tl_dbg * 32 + 0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        if (lane == 0) GEMM_STAMP(tl_dbg * 32 + 1);
+        const uint32_t tmem_d = tmem_u + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (lane == 0 && kb - kb0 < 14) GEMM_STAMP(tl_dbg * 32 + 2 + 2 * (kb - kb0));
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
           const uint64_t adesc = make_desc(sa, A_MN);
           const uint64_t bdesc = make_desc(sb, B_MN);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance inside the swizzle atom: K-major +32 B per UMMA_K, MN-major +16 rows * 128 B
-            const uint64_t aoff = (uint64_t)((A_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
-            const uint64_t boff = (uint64_t)((B_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
-            if (CTA2) tc_mma_bf16_cta2(tmem_d, adesc + aoff, bdesc + boff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else tc_mma_bf16(tmem_d, adesc + aoff, bdesc + boff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance inside the swizzle atom: K-major +32 B per UMMA_K, MN-major +16 rows * 128 B
+              const uint64_t aoff = (uint64_t)((A_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
+              const uint64_t boff = (uint64_t)((B_MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
+              if (CTA2) tc_mma_bf16_cta2(tmem_d, adesc + aoff, bdesc + boff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else tc_mma_bf16(tmem_d, adesc + aoff, bdesc + boff, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+            if (CTA2) tc_commit_mc2(empty_bar(stage), 3); else tc_commit(empty_bar(stage));
           }
-          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
-          if (CTA2) tc_commit_mc2(empty_bar(stage), 3); else tc_commit(empty_bar(stage));
+          __syncwarp();
+          if (lane == 0 && kb - kb0 < 14) GEMM_STAMP(tl_dbg * 32 + 3 + 2 * (kb - kb0));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
         // accumulator ready for the epilogue warps (of both CTAs)
-        if (CTA2) tc_commit_mc2(tfull_bar(acc), 3); else tc_commit(tfull_bar(acc));
+        if (elect_one()) {
+          if (CTA2) tc_commit_mc2(tfull_bar(acc), 3); else tc_commit(tfull_bar(acc));
+        }
+        __syncwarp();
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       }
     }
@@ -456,8 +493,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           __syncwarp();
         }
+#ifdef GEMM_TIMING
+        const int tle_dbg = (t - t_first) / t_stride;
+        if (e == 0 && lane == 0) GEMM_STAMP(4096 + tle_dbg * 8 + 0);
+#endif
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
+#ifdef GEMM_TIMING
+        if (e == 0 && lane == 0) GEMM_STAMP(4096 + tle_dbg * 8 + 1);
+#endif
         uint32_t r[64];
         if (slice_live) {
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + slice * 64);
@@ -468,6 +512,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) release_acc(acc);             // accumulator block is in registers
+#ifdef GEMM_TIMING
+        if (e == 0 && lane == 0) GEMM_STAMP(4096 + tle_dbg * 8 + 2);
+#endif
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
         if (!live) continue;
         if (p.in_mode) {
@@ -477,7 +524,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (lane == 0) bulk_wait_read<0>();
           __syncwarp();
         }
-        const int row = row0 + lane;
+        // dropout groups of this thread's row: 8 consecutive columns each, N % 8 == 0 (host check)
+        const uint64_t drop_g0 = ((uint64_t)(row0 + lane) * (uint64_t)p.N + (uint64_t)col0) >> 3;
         if ((ACT == TNR_ACT_GELU || ACT == TNR_ACT_GELU_DAUX) && p.aux_out) {
           // pre-activation z = acc + bias (GELU) or gelu'(z) (GELU_DAUX) goes out first through the same box
 #pragma unroll
@@ -504,7 +552,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int i = 0; i < 4; ++i) o.u[i] = r[c * 8 + i];
             *reinterpret_cast<bf16x8*>(box + swz) = o;
           } else {
-            epilogue_staged8<ACT>(p, dc, r + c * 8, row, col0 + c * 8, box, box, swz);
+            epilogue_staged8<ACT>(p, dc, r + c * 8, drop_g0 + (uint64_t)c, col0 + c * 8, box, box, swz);
           }
         }
         fence_proxy_async_smem();
@@ -513,6 +561,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tma_store_2d(&tmap_c, box_u32, col0, row0);
           bulk_commit();
         }
+#ifdef GEMM_TIMING
+        if (e == 0 && lane == 0) GEMM_STAMP(4096 + tle_dbg * 8 + 3);
+#endif
         if (p.colsum != nullptr) {
           // columns 2*lane, 2*lane+1 of the staged 32 x 64 box (128B-swizzled rows); rows past M are skipped
           const int rows_ok = min(32, p.M - row0);
@@ -670,6 +721,12 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap* maps, const P
 }  // namespace gemm
 }  // namespace tnr
 
+#ifdef GEMM_TIMING
+extern "C" __attribute__((visibility("default"))) int tnr_debug_gemm_stamps(long long* host_out, int n) {
+  return (int)cudaMemcpyFromSymbol(host_out, tnr::gemm::g_gemm_dbg, sizeof(long long) * (size_t)n);
+}
+#endif
+
 extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_gemm_args* a, void* stream) {
   using namespace tnr;
   using namespace tnr::gemm;
@@ -722,6 +779,7 @@ extern "C" __attribute__((visibility("default"))) int tnr_gemm_bf16(const tnr_ge
               "tnr_gemm_bf16: colsum needs a bf16 (TMA-staged) output");
   TNR_REQUIRE(p.drop.seed == nullptr || !(p.drop.p > 0.f) || (!atomic && a->act == TNR_ACT_NONE),
               "tnr_gemm_bf16: dropout is supported with the plain (bias + residual) epilogue only");
+  TNR_REQUIRE(a->c_dtype != TNR_BF16 || atomic || a->N % 8 == 0, "tnr_gemm_bf16: a bf16 output needs N %% 8 == 0");
 
   CUtensorMap maps[5];
   CUtensorMap &ta = maps[0], &tb = maps[1];

@@ -707,7 +707,8 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
     }
   } else if (warp == 4) {
     // ===================== MMA issuer (the pair leader's elected thread) =====================
-    if (lane == 0 && cta_rank == 0) {
+    // the whole warp walks the loop and one elected lane issues: operands stay in uniform registers (see gemm_tcgen05.cu)
+    if (cta_rank == 0) {
       // D f32, A / B tf32 K-major, N = 208, M = 256 across the pair
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UL_QT >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int item = 0, acc = 0;
@@ -716,32 +717,36 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
       for (int t = t_first; t < n_tiles; t += t_stride) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+        const uint32_t tmem_d = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)(acc * 256);
         for (int kb = 0; kb < NKB; ++kb, ++item) {
           const int st = item % UL_STAGES;
           const uint32_t par = ((uint32_t)(item / UL_STAGES)) & 1u;
           mbar_wait(landed_bar(st), par);                      // this CTA's 128 rows of the k-block
 #ifdef UL_TIMING
-          if (blockIdx.x == 0 && item < 64) p.dbg[item * 4 + 0] = clock64();
+          if (lane == 0 && blockIdx.x == 0 && item < 64) p.dbg[item * 4 + 0] = clock64();
 #endif
           mbar_wait(peer_bar(st), par);                        // the peer's (its data sits in ITS shared memory: no acquire at
                                                                // cluster scope, which costs an L1 invalidate per stage)
 #ifdef UL_TIMING
-          if (blockIdx.x == 0 && item < 64) p.dbg[item * 4 + 1] = clock64();
+          if (lane == 0 && blockIdx.x == 0 && item < 64) p.dbg[item * 4 + 1] = clock64();
 #endif
           fence_proxy_async_smem();
           tc_fence_after();
           const uint64_t adesc = make_desc_kmajor_sw128(sA + (uint32_t)st * UL_A_BYTES);
           const uint64_t bdesc = make_desc_kmajor_sw128(sW + (uint32_t)kb * UL_W_KB_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < UL_KB / 8; ++k)                  // kind::tf32: K = 8 per instruction, +32 B inside the atom
-            tc_mma_tf32_cta2(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          tc_commit_mc2(empty_bar(st), 3);                     // the stage is free in both CTAs once these MMAs retire
+            for (int k = 0; k < UL_KB / 8; ++k)                // kind::tf32: K = 8 per instruction, +32 B inside the atom
+              tc_mma_tf32_cta2(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_commit_mc2(empty_bar(st), 3);                   // the stage is free in both CTAs once these MMAs retire
+          }
+          __syncwarp();
 #ifdef UL_TIMING
-          if (blockIdx.x == 0 && item < 64) p.dbg[item * 4 + 2] = clock64();
+          if (lane == 0 && blockIdx.x == 0 && item < 64) p.dbg[item * 4 + 2] = clock64();
 #endif
         }
-        tc_commit_mc2(tfull_bar(acc), 3);
+        if (elect_one()) tc_commit_mc2(tfull_bar(acc), 3);
+        __syncwarp();
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       }
     }
