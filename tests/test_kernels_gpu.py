@@ -768,12 +768,13 @@ def test_attention_long_dropout_adjoint(L):
         assert _rel_err(dqkv[:, sl], qf.grad[:, sl])[0] < 8e-3, nm
 
 
-@pytest.mark.parametrize("M", [500, 4200])
-def test_gemm_gelu_daux_and_mulaux(M):
+@pytest.mark.parametrize("M,N", [(500, 3072), (4200, 3072), (4200, 296), (4133, 1000)])
+def test_gemm_gelu_daux_and_mulaux(M, N):
     """FFN1 of a trained layer: C = gelu(z), aux = gelu'(z) (ACT_GELU_DAUX); its backward: dz = (dy W2) * aux
-    (ACT_MULAUX) with the fused bias column sums.  M = 500: single-CTA kernels, M = 4 200: CTA-pair kernels."""
+    (ACT_MULAUX) with the fused bias column sums.  M = 500: single-CTA kernels, M >= 4 133: CTA-pair kernels (both
+    outputs through rotating 32 x 32 half boxes; N = 296 / 1 000 leave a clipped last half box, M = 4 133 ragged rows)."""
     ops = _ops()
-    N, K = 3072, 768
+    K = 768
     a, b = _randn(M, K, seed=7), _randn(N, K, scale=0.03, seed=8)
     bias = _randn(N, dtype=torch.float32, scale=0.1, seed=9)
     out = torch.empty(M, N, device="cuda", dtype=BF)

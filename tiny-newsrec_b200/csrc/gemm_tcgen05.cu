@@ -77,13 +77,15 @@ __host__ __device__ constexpr uint32_t make_idesc() {
          | ((uint32_t)((CTA2 ? 2 * BM : BM) >> 4) << 24); // M (256 across the CTA pair)
 }
 
-template <int BN, bool EPI_TMA, bool CTA2 = false>
+template <int BN, bool EPI_TMA, bool CTA2 = false, bool LEAN = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;    // B rows (of N) staged by one CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = CTA2 ? ((BN == 256) ? (EPI_TMA ? 5 : 6) : (EPI_TMA ? 6 : 8))
+  // CTA pair, BN = 256, bf16 output: 5 stages; the two-output GELU + GELU' epilogue (LEAN) runs 3.5 % faster with 4 (same-box
+  // A/B in profiles/r02_gemm_issue_loop.txt); every other epilogue is 1-2 % slower
+  static constexpr int STAGES = CTA2 ? ((BN == 256) ? (EPI_TMA ? (LEAN ? 4 : 5) : 6) : (EPI_TMA ? 6 : 8))
                                      : ((BN == 256) ? (EPI_TMA ? 3 : 4) : (EPI_TMA ? 4 : 6));
   static constexpr int TMEM_COLS = 2 * BN;             // 2 accumulator stages (power of 2 >= 32)
   static constexpr int EPI_BOX_BYTES = 32 * 128;       // 32 rows x 64 bf16, SWIZZLE_128B
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_in,
             const __grid_constant__ CUtensorMap tmap_aux, const Params p) {
-  using C = Cfg<BN, EPI_TMA, CTA2>;
+  using C = Cfg<BN, EPI_TMA, CTA2, CTA2 && ACT == TNR_ACT_GELU_DAUX>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -651,7 +653,7 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t 
 
 template <int BN, bool A_MN, bool B_MN, int ACT, bool EPI_TMA, bool CTA2 = false>
 static int launch(const CUtensorMap* maps, const Params& p, int grid, cudaStream_t st) {
-  using C = Cfg<BN, EPI_TMA, CTA2>;
+  using C = Cfg<BN, EPI_TMA, CTA2, CTA2 && ACT == TNR_ACT_GELU_DAUX>;
   auto kern = gemm_kernel<BN, A_MN, B_MN, ACT, EPI_TMA, CTA2>;
   TNR_SET_SMEM(kern, C::SMEM_BYTES);
   if (CTA2) {

@@ -15,7 +15,14 @@ import tinyrec.ops as ops  # noqa: E402
 
 
 def main():
-    which = sys.argv[1] if len(sys.argv) > 1 else "qkv"
+    if len(sys.argv) > 2:                        # several shapes: launch times only, one process
+        for w in sys.argv[1:]:
+            one(w, stamps=False)
+        return
+    one(sys.argv[1] if len(sys.argv) > 1 else "qkv")
+
+
+def one(which, stamps=True):
     M = 52800
     N, K, res, drop = {"qkv": (2304, 768, False, False), "oproj": (768, 768, True, True), "ffn2": (768, 3072, True, True),
                        "ffn1": (3072, 768, False, False), "ffn1_frozen": (3072, 768, False, False), "dffn2": (3072, 768, False, False)}[which]
@@ -36,16 +43,17 @@ def main():
         act, aux, bias = ops.ACT_MULAUX, torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16), None
         b = b.t().contiguous()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    for i in range(6):
+    n_rep = 3 if stamps else 20
+    for i in range(3 + n_rep):
         if i == 3:
             ev[0].record()
         ops.gemm(a, b, out, bias=bias, residual=r, drop=d, act=act, aux=aux, b_t=(which == "dffn2"))
     ev[1].record()
     torch.cuda.synchronize()
-    us = ev[0].elapsed_time(ev[1]) / 3 * 1e3
+    us = ev[0].elapsed_time(ev[1]) / n_rep * 1e3
     print(f"{which}: {us:.1f} us per launch, {2.0 * M * N * K / us * 1e-6:.0f} TFLOP/s")
     lib = L.load()
-    if not hasattr(lib, "tnr_debug_gemm_stamps"):
+    if not stamps or not hasattr(lib, "tnr_debug_gemm_stamps"):
         return                                   # production build: only the launch time
     buf = (ctypes.c_longlong * 8192)()
     lib.tnr_debug_gemm_stamps.argtypes = [ctypes.c_void_p, ctypes.c_int]
