@@ -227,7 +227,7 @@ def oracle_train_step_fn(layers, trainable, b_sample, seed=0):
             for k in keys:
                 m_, v_, vm_ = state[k]
                 oopt.adam_amsgrad_step(sd[k], sd[k].grad, m_, v_, vm_, step[0], lr=1e-4)
-        return float(total)
+        return float(total.detach())
     return run
 
 

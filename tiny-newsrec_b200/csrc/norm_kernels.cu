@@ -7,40 +7,9 @@
 namespace tnr {
 
 constexpr int ROWS_PER_BLOCK = 8;   // 8 warps
-
-template <int VPL>   // 8-element vectors per lane: E = VPL * 256
-__device__ __forceinline__ void ln_row(float (&x)[VPL * 8], const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, float eps, int lane,
-                                       __nv_bfloat16* __restrict__ out, const DropCfg& dc, uint64_t row) {
-  constexpr int E = VPL * 256;
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL * 8; ++i) s += x[i];
-  const float mean = warp_sum(s) * (1.0f / E);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL * 8; ++i) { const float d = x[i] - mean; q += d * d; }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / E) + eps);
-#pragma unroll
-  for (int v = 0; v < VPL; ++v) {
-    const int col = (v * 32 + lane) * 8;
-    const float4 g0 = *reinterpret_cast<const float4*>(gamma + col);
-    const float4 g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(beta + col);
-    const float4 b1 = *reinterpret_cast<const float4*>(beta + col + 4);
-    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float y[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = (x[v * 8 + i] - mean) * rstd * g[i] + b[i];
-    if (dc.thr16 != 0) {
-      const uint32_t keep = dropout_keep8(dc, (row * (uint64_t)E + (uint64_t)col) >> 3);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = ((keep >> i) & 1u) ? y[i] * dc.scale : 0.f;
-    }
-    *reinterpret_cast<bf16x8*>(out + col) = pack8(y);
-  }
-}
+#ifndef LNF_ROWS
+#define LNF_ROWS 3     // rows in flight per warp of the LayerNorm forward: 1 -> 69.6 %, 2 -> 78.9 %, 3 -> 80.7 % of HBM peak (128 registers)
+#endif
 
 // out[t, :] = dropout(LN(word[id[t]] + pos[t % L] + type[0]))         (tnlrv3/modeling.py:168-177)
 // ids: int64, row n at ids + n * ids_ld, L tokens per row.  word table bf16 or fp32.
@@ -79,7 +48,8 @@ embed_ln_kernel(const int64_t* __restrict__ ids, int ids_ld, int L, int n_rows, 
   const int l = w % L, grp = w / L;
   if (grp >= groups) return;
   const DropCfg dc = load_drop(drop);
-  float g[VPL * 8], bt[VPL * 8], pt[VPL * 8];
+  // packed fp32 pairs (FFMA2 / FADD2): pair i of vector v = columns (v*32+lane)*8 + 2i, +1
+  f32x2 g[VPL * 4], bt[VPL * 4], pt[VPL * 4];
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
     const int col = (v * 32 + lane) * 8;
@@ -89,12 +59,11 @@ embed_ln_kernel(const int64_t* __restrict__ ids, int ids_ld, int L, int n_rows, 
       const float4 bb = *reinterpret_cast<const float4*>(beta + col + 4 * h);
       const float4 pp = *reinterpret_cast<const float4*>(pos + (size_t)l * E + col + 4 * h);
       const float4 tt = *reinterpret_cast<const float4*>(type0 + col + 4 * h);
-      g[v * 8 + 4 * h + 0] = gg.x; g[v * 8 + 4 * h + 1] = gg.y; g[v * 8 + 4 * h + 2] = gg.z; g[v * 8 + 4 * h + 3] = gg.w;
-      bt[v * 8 + 4 * h + 0] = bb.x; bt[v * 8 + 4 * h + 1] = bb.y; bt[v * 8 + 4 * h + 2] = bb.z; bt[v * 8 + 4 * h + 3] = bb.w;
+      g[v * 4 + 2 * h] = pk2(gg.x, gg.y); g[v * 4 + 2 * h + 1] = pk2(gg.z, gg.w);
+      bt[v * 4 + 2 * h] = pk2(bb.x, bb.y); bt[v * 4 + 2 * h + 1] = pk2(bb.z, bb.w);
       // batch-invariant part folded once: w + (p + t) vs the reference's (w + p) + t differ by an fp32
       // ulp at most, far below the bf16 output resolution
-      pt[v * 8 + 4 * h + 0] = pp.x + tt.x; pt[v * 8 + 4 * h + 1] = pp.y + tt.y;
-      pt[v * 8 + 4 * h + 2] = pp.z + tt.z; pt[v * 8 + 4 * h + 3] = pp.w + tt.w;
+      pt[v * 4 + 2 * h] = pk2(pp.x + tt.x, pp.y + tt.y); pt[v * 4 + 2 * h + 1] = pk2(pp.z + tt.z, pp.w + tt.w);
     }
   }
   for (int n0 = grp; n0 < n_rows; n0 += 2 * groups) {
@@ -110,39 +79,50 @@ embed_ln_kernel(const int64_t* __restrict__ ids, int ids_ld, int L, int n_rows, 
     for (int k = 0; k < 2; ++k) {
       const int n = k ? n1 : n0;
       if (n >= n_rows) break;
-      float x[VPL * 8];
+      f32x2 x[VPL * 4];
+      f32x2 s2 = pk2(0.f, 0.f);
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        if (WORD_BF16) {
-          unpack8(k ? raw1[v] : raw0[v], &x[v * 8]);
-        } else {
+      for (int v = 0; v < VPL; ++v)
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) x[v * 8 + 4 * h + i] = __uint_as_float((k ? raw1 : raw0)[2 * v + h].u[i]);
+        for (int i = 0; i < 4; ++i) {
+          f32x2 w2;
+          if (WORD_BF16) {
+            const uint32_t u = (k ? raw1[v] : raw0[v]).u[i];
+            w2 = pk2(bf16_lo(u), bf16_hi(u));
+          } else {
+            const bf16x8& rr = (k ? raw1 : raw0)[2 * v + (i >> 1)];
+            w2 = pk2(__uint_as_float(rr.u[(i & 1) * 2]), __uint_as_float(rr.u[(i & 1) * 2 + 1]));
+          }
+          x[v * 4 + i] = add2(w2, pt[v * 4 + i]);
+          s2 = add2(s2, x[v * 4 + i]);
         }
-      }
-      float s = 0.f;
+      float s0, s1;
+      upk2(s2, s0, s1);
+      const float mean = warp_sum(s0 + s1) * (1.0f / E);
+      const f32x2 nmean2 = pk2(-mean, -mean);
+      f32x2 q2 = pk2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < VPL * 8; ++i) { x[i] += pt[i]; s += x[i]; }
-      const float mean = warp_sum(s) * (1.0f / E);
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < VPL * 8; ++i) { const float d = x[i] - mean; q += d * d; }
-      const float rstd = rsqrtf(warp_sum(q) * (1.0f / E) + eps);
+      for (int i = 0; i < VPL * 4; ++i) { const f32x2 d = add2(x[i], nmean2); q2 = fma2(d, d, q2); }
+      upk2(q2, s0, s1);
+      const float rstd = rsqrtf(warp_sum(s0 + s1) * (1.0f / E) + eps);
+      const f32x2 rstd2 = pk2(rstd, rstd), nmr2 = pk2(-mean * rstd, -mean * rstd);
       const size_t t = (size_t)n * L + l;
 #pragma unroll
       for (int v = 0; v < VPL; ++v) {
         const int col = (v * 32 + lane) * 8;
-        float y[8];
+        f32x2 yv[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = (x[v * 8 + i] - mean) * rstd * g[v * 8 + i] + bt[v * 8 + i];
+        for (int i = 0; i < 4; ++i) yv[i] = fma2(fma2(x[v * 4 + i], rstd2, nmr2), g[v * 4 + i], bt[v * 4 + i]);
         if (dc.thr16 != 0) {
-          const uint32_t keep = dropout_keep8(dc, ((uint64_t)t * (uint64_t)E + (uint64_t)col) >> 3);
+          f32x2 m[4];
+          dropout_mul8(dc, ((uint64_t)t * (uint64_t)E + (uint64_t)col) >> 3, m);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = ((keep >> i) & 1u) ? y[i] * dc.scale : 0.f;
+          for (int i = 0; i < 4; ++i) yv[i] = mul2(yv[i], m[i]);
         }
-        *reinterpret_cast<bf16x8*>(out + t * E + col) = pack8(y);
+        bf16x8 o;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float lo, hi; upk2(yv[i], lo, hi); o.u[i] = pack_bf16(lo, hi); }
+        *reinterpret_cast<bf16x8*>(out + t * E + col) = o;
       }
     }
   }
@@ -156,8 +136,10 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int rows, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int reverse) {
   constexpr int E = VPL * 256;
+  constexpr int NR = LNF_ROWS;                    // rows in flight per warp (registers)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float g[VPL * 8], bt[VPL * 8];
+  // packed fp32 pairs (FFMA2 / FADD2): pair i of vector v = columns (v*32+lane)*8 + 2i, +1
+  f32x2 g[VPL * 4], bt[VPL * 4];
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
     const int col = (v * 32 + lane) * 8;
@@ -165,43 +147,57 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int rows, const float*
     for (int h = 0; h < 2; ++h) {
       const float4 gg = *reinterpret_cast<const float4*>(gamma + col + 4 * h);
       const float4 bb = *reinterpret_cast<const float4*>(beta + col + 4 * h);
-      g[v * 8 + 4 * h + 0] = gg.x; g[v * 8 + 4 * h + 1] = gg.y; g[v * 8 + 4 * h + 2] = gg.z; g[v * 8 + 4 * h + 3] = gg.w;
-      bt[v * 8 + 4 * h + 0] = bb.x; bt[v * 8 + 4 * h + 1] = bb.y; bt[v * 8 + 4 * h + 2] = bb.z; bt[v * 8 + 4 * h + 3] = bb.w;
+      g[v * 4 + 2 * h] = pk2(gg.x, gg.y); g[v * 4 + 2 * h + 1] = pk2(gg.z, gg.w);
+      bt[v * 4 + 2 * h] = pk2(bb.x, bb.y); bt[v * 4 + 2 * h + 1] = pk2(bb.z, bb.w);
     }
   }
   const int stride = gridDim.x * ROWS_PER_BLOCK;
-  for (int r0 = blockIdx.x * ROWS_PER_BLOCK + warp; r0 < rows; r0 += 2 * stride) {
-    const int r1 = r0 + stride;
+  for (int r0 = blockIdx.x * ROWS_PER_BLOCK + warp; r0 < rows; r0 += NR * stride) {
     // reverse: sweep the rows from the END -- the rows the producing GEMM wrote last are the ones still in L2
-    const int a0 = reverse ? rows - 1 - r0 : r0, a1 = reverse ? rows - 1 - r1 : r1;
-    bf16x8 raw0[VPL], raw1[VPL];
+    bf16x8 raw[NR][VPL];
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) raw0[v] = *reinterpret_cast<const bf16x8*>(x + (size_t)a0 * E + (v * 32 + lane) * 8);
-    if (r1 < rows) {
+    for (int k = 0; k < NR; ++k) {
+      const int rk = r0 + k * stride;
+      if (rk < rows) {
+        const int a = reverse ? rows - 1 - rk : rk;
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) raw1[v] = *reinterpret_cast<const bf16x8*>(x + (size_t)a1 * E + (v * 32 + lane) * 8);
+        for (int v = 0; v < VPL; ++v) raw[k][v] = *reinterpret_cast<const bf16x8*>(x + (size_t)a * E + (v * 32 + lane) * 8);
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if ((k ? r1 : r0) >= rows) break;
-      const int r = k ? a1 : a0;
-      float xv[VPL * 8];
+    for (int k = 0; k < NR; ++k) {
+      const int rk = r0 + k * stride;
+      if (rk >= rows) break;
+      const int r = reverse ? rows - 1 - rk : rk;
+      f32x2 xv[VPL * 4];
+      f32x2 s2 = pk2(0.f, 0.f);
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) unpack8(k ? raw1[v] : raw0[v], &xv[v * 8]);
-      float s = 0.f;
+      for (int v = 0; v < VPL; ++v)
 #pragma unroll
-      for (int i = 0; i < VPL * 8; ++i) s += xv[i];
-      const float mean = warp_sum(s) * (1.0f / E);
-      float q = 0.f;
+        for (int i = 0; i < 4; ++i) {
+          xv[v * 4 + i] = pk2(bf16_lo(raw[k][v].u[i]), bf16_hi(raw[k][v].u[i]));
+          s2 = add2(s2, xv[v * 4 + i]);
+        }
+      float s0, s1;
+      upk2(s2, s0, s1);
+      const float mean = warp_sum(s0 + s1) * (1.0f / E);
+      const f32x2 nmean2 = pk2(-mean, -mean);
+      f32x2 q2 = pk2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < VPL * 8; ++i) { const float d = xv[i] - mean; q += d * d; }
-      const float rstd = rsqrtf(warp_sum(q) * (1.0f / E) + eps);
+      for (int i = 0; i < VPL * 4; ++i) { const f32x2 d = add2(xv[i], nmean2); q2 = fma2(d, d, q2); }
+      upk2(q2, s0, s1);
+      const float rstd = rsqrtf(warp_sum(s0 + s1) * (1.0f / E) + eps);
+      const f32x2 rstd2 = pk2(rstd, rstd), nmr2 = pk2(-mean * rstd, -mean * rstd);
 #pragma unroll
       for (int v = 0; v < VPL; ++v) {
-        float o[8];
+        bf16x8 o;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = (xv[v * 8 + i] - mean) * rstd * g[v * 8 + i] + bt[v * 8 + i];
-        *reinterpret_cast<bf16x8*>(y + (size_t)r * E + (v * 32 + lane) * 8) = pack8(o);
+        for (int i = 0; i < 4; ++i) {
+          float lo, hi;
+          upk2(fma2(fma2(xv[v * 4 + i], rstd2, nmr2), g[v * 4 + i], bt[v * 4 + i]), lo, hi);
+          o.u[i] = pack_bf16(lo, hi);
+        }
+        *reinterpret_cast<bf16x8*>(y + (size_t)r * E + (v * 32 + lane) * 8) = o;
       }
     }
   }
@@ -222,7 +218,10 @@ __device__ __forceinline__ void ln_cp_async16(void* smem_dst, const void* src) {
 }
 
 constexpr int LNB_WARPS = 12;      // 384 threads, <= 168 registers: one block per SM
-constexpr int LNB_STAGES = 3;
+#ifndef LNB_STAGES_X
+#define LNB_STAGES_X 3
+#endif
+constexpr int LNB_STAGES = LNB_STAGES_X;
 
 template <int VPL>
 __global__ void __launch_bounds__(LNB_WARPS * 32, 1)
@@ -239,17 +238,18 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(ln_smem + 3 * E * 4) + (size_t)warp * LNB_STAGES * 2 * E;
   for (int i = threadIdx.x; i < 3 * E; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
-  float gm[VPL * 8], acc_dg[VPL * 8], acc_db[VPL * 8], acc_ds[VPL * 8];
+  // packed fp32 pairs (FFMA2 / FADD2 / FMUL2, common.cuh): element pair i of vector v is columns (v*32+lane)*8 + 2i, +1
+  f32x2 gm[VPL * 4], acc_dg[VPL * 4], acc_db[VPL * 4], acc_ds[VPL * 4];
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
     const int col = (v * 32 + lane) * 8;
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
     const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
-    gm[v * 8 + 0] = g0.x; gm[v * 8 + 1] = g0.y; gm[v * 8 + 2] = g0.z; gm[v * 8 + 3] = g0.w;
-    gm[v * 8 + 4] = g1.x; gm[v * 8 + 5] = g1.y; gm[v * 8 + 6] = g1.z; gm[v * 8 + 7] = g1.w;
+    gm[v * 4 + 0] = pk2(g0.x, g0.y); gm[v * 4 + 1] = pk2(g0.z, g0.w);
+    gm[v * 4 + 2] = pk2(g1.x, g1.y); gm[v * 4 + 3] = pk2(g1.z, g1.w);
   }
 #pragma unroll
-  for (int i = 0; i < VPL * 8; ++i) { acc_dg[i] = 0.f; acc_db[i] = 0.f; acc_ds[i] = 0.f; }
+  for (int i = 0; i < VPL * 4; ++i) { acc_dg[i] = pk2(0.f, 0.f); acc_db[i] = pk2(0.f, 0.f); acc_ds[i] = pk2(0.f, 0.f); }
   const int stride = gridDim.x * LNB_WARPS;
   auto prefetch = [&](int st, int r) {
     if (r < rows) {
@@ -264,13 +264,13 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     asm volatile("cp.async.commit_group;" ::: "memory");       // one group per slot, empty past the end
   };
   int r = blockIdx.x * LNB_WARPS + warp;
-  prefetch(0, r);
-  prefetch(1, r + stride);
+#pragma unroll
+  for (int i = 0; i < LNB_STAGES - 1; ++i) prefetch(i, r + i * stride);
   int st = 0;
   for (; r < rows; r += stride) {
-    int st2 = st + 2; if (st2 >= LNB_STAGES) st2 -= LNB_STAGES;
-    prefetch(st2, r + 2 * stride);
-    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    int st2 = st + LNB_STAGES - 1; if (st2 >= LNB_STAGES) st2 -= LNB_STAGES;
+    prefetch(st2, r + (LNB_STAGES - 1) * stride);
+    asm volatile("cp.async.wait_group %0;" ::"n"(LNB_STAGES - 1) : "memory");
     __syncwarp();
     bf16x8 rx[VPL], rd[VPL];
     {
@@ -283,70 +283,97 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     }
     __syncwarp();                      // stage consumed: a later prefetch may overwrite it
     if (++st == LNB_STAGES) st = 0;
-    float s = 0.f;
+    // mean and variance from one sweep: sum and sum of squares of the row SHIFTED by its first element (the shift removes
+    // the cancellation a large mean would cause; bf16 inputs, fp32 sums, E <= 1024), the two warp reductions interleaved
+    const float shift = __shfl_sync(0xffffffffu, bf16_lo(rx[0].u[0]), 0);
+    const f32x2 nshift2 = pk2(-shift, -shift);
+    f32x2 s2 = pk2(0.f, 0.f), q2 = pk2(0.f, 0.f);
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      float t[8];
-      unpack8(rx[v], t);
+    for (int v = 0; v < VPL; ++v)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += t[i];
-    }
-    const float mean = warp_sum(s) * (1.0f / E);
-    float q = 0.f;
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      float t[8];
-      unpack8(rx[v], t);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = t[i] - mean; q += d * d; }
-    }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / E) + eps);
-    float sg = 0.f, sgx = 0.f;
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      float t[8], d[8];
-      unpack8(rx[v], t);
-      unpack8(rd[v], d);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xh = (t[i] - mean) * rstd;
-        acc_dg[v * 8 + i] = fmaf(d[i], xh, acc_dg[v * 8 + i]);
-        acc_db[v * 8 + i] += d[i];
-        const float gg = d[i] * gm[v * 8 + i];
-        sg += gg;
-        sgx = fmaf(gg, xh, sgx);
+      for (int i = 0; i < 4; ++i) {
+        const f32x2 d = add2(pk2(bf16_lo(rx[v].u[i]), bf16_hi(rx[v].u[i])), nshift2);
+        s2 = add2(s2, d);
+        q2 = fma2(d, d, q2);
       }
+    float s, q;
+    { float a0, a1; upk2(s2, a0, a1); s = a0 + a1; upk2(q2, a0, a1); q = a0 + a1; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
     }
-    sg = warp_sum(sg) * (1.0f / E);
-    sgx = warp_sum(sgx) * (1.0f / E);
+    const float ms = s * (1.0f / E);
+    const float mean = shift + ms;
+    const float rstd = rsqrtf(fmaxf(q * (1.0f / E) - ms * ms, 0.f) + eps);
+    // xhat = x * rstd - mean * rstd (one FFMA2 per pair)
+    const f32x2 rstd2 = pk2(rstd, rstd), nmr2 = pk2(-mean * rstd, -mean * rstd);
+    f32x2 sg2 = pk2(0.f, 0.f), sgx2 = pk2(0.f, 0.f);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const f32x2 xh = fma2(pk2(bf16_lo(rx[v].u[i]), bf16_hi(rx[v].u[i])), rstd2, nmr2);
+        const f32x2 d = pk2(bf16_lo(rd[v].u[i]), bf16_hi(rd[v].u[i]));
+        acc_dg[v * 4 + i] = fma2(d, xh, acc_dg[v * 4 + i]);
+        acc_db[v * 4 + i] = add2(acc_db[v * 4 + i], d);
+        const f32x2 gg = mul2(d, gm[v * 4 + i]);
+        sg2 = add2(sg2, gg);
+        sgx2 = fma2(gg, xh, sgx2);
+      }
+    float sg, sgx;
+    { float a0, a1; upk2(sg2, a0, a1); sg = a0 + a1; upk2(sgx2, a0, a1); sgx = a0 + a1; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+    }
+    sg *= (1.0f / E);
+    sgx *= (1.0f / E);
+    // dx = rstd * g - rstd * mean(g) - xhat * rstd * mean(g xhat): two FFMA2 per pair on top of g and xhat
+    const f32x2 c0 = pk2(-rstd * sg, -rstd * sg), c1 = pk2(-rstd * sgx, -rstd * sgx);
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-      float t[8], d[8], o[8];
       const int col = (v * 32 + lane) * 8;
-      unpack8(rx[v], t);
-      unpack8(rd[v], d);
+      f32x2 o[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = rstd * (d[i] * gm[v * 8 + i] - sg - (t[i] - mean) * rstd * sgx);
-      *reinterpret_cast<bf16x8*>(dx + (size_t)r * E + col) = pack8(o);
-      if (dc.thr16 != 0) {
-        const uint32_t keep = dropout_keep8(dc, ((uint64_t)r * (uint64_t)E + (uint64_t)col) >> 3);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * dc.scale : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const f32x2 xh = fma2(pk2(bf16_lo(rx[v].u[i]), bf16_hi(rx[v].u[i])), rstd2, nmr2);
+        const f32x2 gg = mul2(pk2(bf16_lo(rd[v].u[i]), bf16_hi(rd[v].u[i])), gm[v * 4 + i]);
+        o[i] = fma2(xh, c1, fma2(gg, rstd2, c0));
       }
-      if (dx_drop != nullptr) *reinterpret_cast<bf16x8*>(dx_drop + (size_t)r * E + col) = pack8(o);
+      bf16x8 ob;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc_ds[v * 8 + i] += o[i];
+      for (int i = 0; i < 4; ++i) { float lo, hi; upk2(o[i], lo, hi); ob.u[i] = pack_bf16(lo, hi); }
+      *reinterpret_cast<bf16x8*>(dx + (size_t)r * E + col) = ob;
+      if (dc.thr16 != 0) {
+        f32x2 m[4];
+        dropout_mul8(dc, ((uint64_t)r * (uint64_t)E + (uint64_t)col) >> 3, m);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = mul2(o[i], m[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float lo, hi; upk2(o[i], lo, hi); ob.u[i] = pack_bf16(lo, hi); }
+      }
+      if (dx_drop != nullptr) *reinterpret_cast<bf16x8*>(dx_drop + (size_t)r * E + col) = ob;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc_ds[v * 4 + i] = add2(acc_ds[v * 4 + i], o[i]);
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int v = 0; v < VPL; ++v)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int col = (v * 32 + lane) * 8 + i;
-      atomicAdd(&s_acc[col], acc_dg[v * 8 + i]);
-      atomicAdd(&s_acc[E + col], acc_db[v * 8 + i]);
-      if (dsum != nullptr) atomicAdd(&s_acc[2 * E + col], acc_ds[v * 8 + i]);
+    for (int i = 0; i < 4; ++i) {
+      const int col = (v * 32 + lane) * 8 + 2 * i;
+      float lo, hi;
+      upk2(acc_dg[v * 4 + i], lo, hi);
+      atomicAdd(&s_acc[col], lo); atomicAdd(&s_acc[col + 1], hi);
+      upk2(acc_db[v * 4 + i], lo, hi);
+      atomicAdd(&s_acc[E + col], lo); atomicAdd(&s_acc[E + col + 1], hi);
+      if (dsum != nullptr) {
+        upk2(acc_ds[v * 4 + i], lo, hi);
+        atomicAdd(&s_acc[2 * E + col], lo); atomicAdd(&s_acc[2 * E + col + 1], hi);
+      }
     }
   __syncthreads();
   for (int i = threadIdx.x; i < E; i += blockDim.x) {
