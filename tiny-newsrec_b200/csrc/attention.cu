@@ -25,10 +25,13 @@ constexpr int PS = 40;            // smem row stride (bf16) of the 32 x 32 P / d
 constexpr int TILE_BYTES = LMAX * TS * 2;
 constexpr int PT_BYTES = LMAX * PS * 2;
 constexpr int ATT_FWD_SMEM_PER_WARP = 3 * TILE_BYTES + LMAX * 4 + 2 * LMAX * 4;        // tiles, key mask, rel-pos vector
-// backward: Q, K, V, dO tiles + the dS tile; the dropout(P) tile ALIASES the V tile (V is dead once dP = dO V^T is in
-// registers), which brings a warp to 21.4 KB and five warps per block to two blocks = 10 warps per SM (was 8)
-constexpr int ATT_BWD_WARPS = 5;
-constexpr int ATT_BWD_SMEM_PER_WARP = 4 * TILE_BYTES + PT_BYTES + LMAX * 4 + 2 * LMAX * 4;
+// backward: Q, K, V, dO as UNPADDED 32 x 128-byte tiles whose 16-byte chunks are XOR-swizzled with the row (ldmatrix,
+// cp.async, staging and row stores all conflict-free without the 16 pad bytes per row); the dropout(P) and dS tiles
+// (32 x 64 bytes each, swizzled the same way) ALIAS the V tile, which is dead once dP = dO V^T is in registers.
+// 16.4 KB per warp: six warps per block, two blocks = 12 warps per SM (padded tiles + a separate dS tile: 21.4 KB, 10).
+constexpr int ATT_BWD_WARPS = 6;
+constexpr int SW_TILE_BYTES = LMAX * 128;
+constexpr int ATT_BWD_SMEM_PER_WARP = 4 * SW_TILE_BYTES + LMAX * 4 + 2 * LMAX * 4;
 
 int attn_long_bwd_launch(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias, const void* dctx_bf16,
                          void* dqkv_bf16, float* dbias, float* ws, int n_news, int L, int A, int E, const tnr_dropout* drop,
@@ -256,32 +259,131 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
   store_tile(ctx + (size_t)n * L * E + h * DH, sQ, L, E, lane);
 }
 
-__global__ void __launch_bounds__(ATT_BWD_WARPS * 32)
+// ---- swizzled tiles of the backward kernel ------------------------------------------------------------------
+// 32 x 64 bf16 tile, 128-byte rows: element (r, c) at r*128 + ((c/8 ^ (r & 7)) * 16) + (c % 8) * 2 bytes
+__device__ __forceinline__ uint32_t sw_off(int r, int chunk) { return (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4)); }
+// 32 x 32 bf16 tile, 64-byte rows (two rows per 128-byte line): chunk (0..3) XOR ((r >> 1) & 3)
+__device__ __forceinline__ uint32_t pt_off(int r, int chunk) { return (uint32_t)(r * 64 + ((chunk ^ ((r >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ void load_tile_async_sw(uint8_t* s, const __nv_bfloat16* g, int L, int ld, int lane) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = lane + 32 * it, r = idx >> 3, c = idx & 7;
+    if (r < L) cp_async16(smem_addr(s + sw_off(r, c)), g + (size_t)r * ld + c * 8);
+    else *reinterpret_cast<uint4*>(s + sw_off(r, c)) = make_uint4(0, 0, 0, 0);
+  }
+}
+__device__ __forceinline__ void store_tile_sw(__nv_bfloat16* g, const uint8_t* s, int L, int ld, int lane) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = lane + 32 * it, r = idx >> 3, c = idx & 7;
+    if (r < L) *reinterpret_cast<uint4*>(g + (size_t)r * ld + c * 8) = *reinterpret_cast<const uint4*>(s + sw_off(r, c));
+  }
+}
+__device__ __forceinline__ void stage_c64_sw(uint8_t* s, const float (&o)[2][8][4], int lane) {
+  const int m = lane >> 3;                       // matrix of the x4 store this lane addresses: rows (m & 1) * 8.., chunk +(m >> 1)
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      const uint32_t r[4] = {pack_bf16(o[mt][2 * np][0], o[mt][2 * np][1]), pack_bf16(o[mt][2 * np][2], o[mt][2 * np][3]),
+                             pack_bf16(o[mt][2 * np + 1][0], o[mt][2 * np + 1][1]),
+                             pack_bf16(o[mt][2 * np + 1][2], o[mt][2 * np + 1][3])};
+      stsm_x4(smem_addr(s + sw_off(mt * 16 + (m & 1) * 8 + (lane & 7), 2 * np + (m >> 1))), r);
+    }
+}
+// A-fragment-shaped registers of a 32 x 32 bf16 tile (c_to_a) -> swizzled 64-byte-row tile
+__device__ __forceinline__ void stage_p32_sw(uint8_t* s, const uint32_t (&pa)[2][2][4], int lane) {
+  const int m = lane >> 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+      stsm_x4(smem_addr(s + pt_off(mt * 16 + (m & 1) * 8 + (lane & 7), 2 * ks + (m >> 1))), pa[mt][ks]);
+}
+// column sums of a staged 32 x 64 tile on the tensor path: ones(16 x 32) . tile; every accumulator row holds the sums,
+// lane (g, t) adds those of columns g*8 + 2t, +1 (rows >= L of the staged gradients are exact zeros)
+__device__ __forceinline__ void tile_colsum_mma(float* __restrict__ out, const uint8_t* s, int lane) {
+  const uint32_t ones[4] = {0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u};
+  const int g = lane >> 2, t = lane & 3;
+  float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    uint32_t b[4];
+    ldsm_x4_t(smem_addr(s + sw_off(lane, nt)), b);
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16(c, ones, b[0], b[1]);
+    mma_bf16(c, ones, b[2], b[3]);
+    if (nt == g) { v0 = c[0]; v1 = c[1]; }
+  }
+  atomicAdd(reinterpret_cast<float2*>(out + g * 8 + 2 * t), make_float2(v0, v1));      // one 8-byte RED (sm_90+)
+}
+// acc (32 x 32) = X . Y^T, both 32 x 64 swizzled tiles
+__device__ __forceinline__ void mma_xyT_sw(float (&acc)[2][4][4], const uint8_t* sX, const uint8_t* sY, int lane) {
+  uint32_t yb[4][2][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+      ldsm_x4(smem_addr(sY + sw_off(nt * 8 + (lane & 7), half * 4 + (lane >> 3))), yb[nt][half]);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a[4];
+      ldsm_x4(smem_addr(sX + sw_off(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4))), a);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_bf16(acc[mt][nt], a, yb[nt][ks >> 1][(ks & 1) * 2], yb[nt][ks >> 1][(ks & 1) * 2 + 1]);
+    }
+}
+// out (32 x 64) += P (32 x 32, A fragments) . Y (32 x 64 swizzled tile)
+__device__ __forceinline__ void mma_pY_sw(float (&out)[2][8][4], const uint32_t (&pa)[2][2][4], const uint8_t* sY, int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    uint32_t b[4];
+    ldsm_x4_t(smem_addr(sY + sw_off(lane, nt)), b);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      mma_bf16(out[mt][nt], pa[mt][0], b[0], b[1]);
+      mma_bf16(out[mt][nt], pa[mt][1], b[2], b[3]);
+    }
+  }
+}
+// A fragments of X^T, X a 32 x 32 swizzled (64-byte rows) tile
+__device__ __forceinline__ void load_xT_frags_sw(uint32_t (&pa)[2][2][4], const uint8_t* sX, int lane) {
+  const int mi = lane >> 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+      ldsm_x4_t(smem_addr(sX + pt_off(ks * 16 + (lane & 7) + (mi >> 1) * 8, mt * 2 + (mi & 1))), pa[mt][ks]);
+}
+
+__global__ void __launch_bounds__(ATT_BWD_WARPS * 32, 2)
 attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ mask, int mask_ld,
                 const float* __restrict__ relbias, const __nv_bfloat16* __restrict__ dctx,
                 __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int n_news, int L, int A, int E,
                 const tnr_dropout drop) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * ATT_BWD_WARPS + warp;
   if (item >= (long long)n_news * A) return;
-  uint8_t* wbase = smem + (size_t)warp * ATT_BWD_SMEM_PER_WARP;
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(wbase);
-  __nv_bfloat16* sK = sQ + LMAX * TS;
-  __nv_bfloat16* sV = sK + LMAX * TS;
-  __nv_bfloat16* sO = sV + LMAX * TS;
-  __nv_bfloat16* sS = sO + LMAX * TS;
-  __nv_bfloat16* sP = sV;                         // aliases V: written only after the dP product has consumed it
-  float* smadd = reinterpret_cast<float*>(sS + LMAX * PS);
+  uint8_t* sQ = smem + (size_t)warp * ATT_BWD_SMEM_PER_WARP;
+  uint8_t* sK = sQ + SW_TILE_BYTES;
+  uint8_t* sV = sK + SW_TILE_BYTES;
+  uint8_t* sO = sV + SW_TILE_BYTES;
+  uint8_t* sP = sV;                               // dropout(P) and dS alias V: written only after the dP product has consumed it
+  uint8_t* sS = sV + LMAX * 64;
+  float* smadd = reinterpret_cast<float*>(sO + SW_TILE_BYTES);
   float* srel = smadd + LMAX;
   const int n = (int)(item / A), h = (int)(item % A);
   const int ld = 3 * E;
   const int g = lane >> 2, t = lane & 3;
   const __nv_bfloat16* base = qkv + (size_t)n * L * ld + h * DH;
-  load_tile_async(sQ, base, L, ld, lane);
-  load_tile_async(sK, base + E, L, ld, lane);
-  load_tile_async(sV, base + 2 * E, L, ld, lane);
-  load_tile_async(sO, dctx + (size_t)n * L * E + h * DH, L, E, lane);
+  load_tile_async_sw(sQ, base, L, ld, lane);
+  load_tile_async_sw(sK, base + E, L, ld, lane);
+  load_tile_async_sw(sV, base + 2 * E, L, ld, lane);
+  load_tile_async_sw(sO, dctx + (size_t)n * L * E + h * DH, L, E, lane);
   smadd[lane] = lane < L ? (1.0f - (float)mask[(size_t)n * mask_ld + lane]) * -10000.0f : 0.f;
   load_relbias(srel, relbias, h, L, lane);
   const DropCfg dc = load_drop(drop);
@@ -295,10 +397,10 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
       for (int c = 0; c < 4; ++c) { p[mt][nt][c] = 0.f; dp[mt][nt][c] = 0.f; }
-  mma_xyT(p, sQ, sK, lane);
+  mma_xyT_sw(p, sQ, sK, lane);
   softmax_frag(p, smadd, srel, L, lane);
-  mma_xyT(dp, sO, sV, lane);                    // dP = dO V^T
-  __syncwarp();                                 // every lane is done reading V before dropout(P) goes into its tile
+  mma_xyT_sw(dp, sO, sV, lane);                 // dP = dO V^T
+  __syncwarp();                                 // every lane is done reading V before dropout(P) / dS go into its tile
   // dS = P o (dP_eff - delta) / 8, P_drop = P o keep * scale; both to smem (bf16) for the transposed products
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
@@ -329,55 +431,58 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
           pd[e] = pv * k;
           ds[e] = pv * (dp[mt][nt][hi * 2 + e] - delta) * 0.125f;
           dp[mt][nt][hi * 2 + e] = ds[e];
+          p[mt][nt][hi * 2 + e] = pd[e];
         }
-        *reinterpret_cast<uint32_t*>(sP + i * PS + nt * 8 + 2 * t) = pack_bf16(pd[0], pd[1]);
-        *reinterpret_cast<uint32_t*>(sS + i * PS + nt * 8 + 2 * t) = pack_bf16(ds[0], ds[1]);
       }
     }
   __nv_bfloat16* dbase = dqkv + (size_t)n * L * ld + h * DH;
   float acc[2][8][4];
   uint32_t pa[2][2][4];
+  c_to_a(pa, p);
+  stage_p32_sw(sP, pa, lane);                     // dropout(P), bf16
   // dQ = dS K
   c_to_a(pa, dp);
+  stage_p32_sw(sS, pa, lane);                     // dS, bf16 (the same registers are the A fragments of dS K)
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
-  mma_pY(acc, pa, sK, lane);
+  mma_pY_sw(acc, pa, sK, lane);
   __syncwarp();                                   // all lanes done reading sK; sP / sS visible
-  stage_c64(sK, acc, lane);
+  stage_c64_sw(sK, acc, lane);
   __syncwarp();
-  store_tile(dbase, sK, L, ld, lane);
-  if (dbias != nullptr) tile_colsum(dbias + h * DH, sK, L, lane);
-  // dV = P_drop^T dO
-  load_xT_frags(pa, sP, lane);
+  store_tile_sw(dbase, sK, L, ld, lane);
+  if (dbias != nullptr) tile_colsum_mma(dbias + h * DH, sK, lane);
+  // dV = P_drop^T dO, staged over dO once every lane has its fragments
+  load_xT_frags_sw(pa, sP, lane);
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
-  mma_pY(acc, pa, sO, lane);
-  stage_c64(sV, acc, lane);                       // V was last read by the dP product
+  mma_pY_sw(acc, pa, sO, lane);
   __syncwarp();
-  store_tile(dbase + 2 * E, sV, L, ld, lane);
-  if (dbias != nullptr) tile_colsum(dbias + 2 * E + h * DH, sV, L, lane);
+  stage_c64_sw(sO, acc, lane);
+  __syncwarp();
+  store_tile_sw(dbase + 2 * E, sO, L, ld, lane);
+  if (dbias != nullptr) tile_colsum_mma(dbias + 2 * E + h * DH, sO, lane);
   // dK = dS^T Q
-  load_xT_frags(pa, sS, lane);
+  load_xT_frags_sw(pa, sS, lane);
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
-  mma_pY(acc, pa, sQ, lane);
+  mma_pY_sw(acc, pa, sQ, lane);
   __syncwarp();
-  stage_c64(sQ, acc, lane);
+  stage_c64_sw(sQ, acc, lane);
   __syncwarp();
-  store_tile(dbase + E, sQ, L, ld, lane);
-  if (dbias != nullptr) tile_colsum(dbias + E + h * DH, sQ, L, lane);
+  store_tile_sw(dbase + E, sQ, L, ld, lane);
+  if (dbias != nullptr) tile_colsum_mma(dbias + E + h * DH, sQ, lane);
 }
 
 }  // namespace tnr

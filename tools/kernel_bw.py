@@ -104,6 +104,9 @@ def main():
     dqkv = torch.empty(T, 3 * E, device=dev, dtype=BF)
     sec = timed(lambda i: ops.attn_bwd(qkv[i], xs[i], L, relpos, dy[i], dqkv, 12, drop=ops.make_drop(seed, 8, 0.1)), NV)
     rec("tnr_attn_relpos_bwd+dropout", T * 7 * E * 2, sec)
+    dbq = torch.zeros(3 * E, device=dev)
+    sec = timed(lambda i: ops.attn_bwd(qkv[i], xs[i], L, relpos, dy[i], dqkv, 12, drop=ops.make_drop(seed, 8, 0.1), dbias=dbq), NV)
+    rec("tnr_attn_relpos_bwd+dropout+dbias", T * 7 * E * 2, sec, "as the train step calls it: + column sums of dqkv (the QKV bias gradient)")
 
     # ---- column sums (bias gradients)
     dz = [rn(T, F) for _ in range(2)]
