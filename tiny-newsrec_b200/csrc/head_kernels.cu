@@ -13,18 +13,6 @@ namespace tnr {
 // parallelism to add is inside the block -- with 256 threads the launch took 90 us for 7.6 MB.
 constexpr int UE_THREADS = 1024;
 
-__device__ __forceinline__ float block_sum_256(float v, float* red /*[UE_THREADS / 32]*/) {
-  v = warp_sum(v);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();
-  if (lane == 0) red[warp] = v;
-  __syncthreads();
-  float t = 0.f;
-#pragma unroll
-  for (int i = 0; i < UE_THREADS / 32; ++i) t += red[i];
-  return t;
-}
-
 // ----------------------------------------------------------------------------------
 // click scoring + CE + multi-teacher KD loss, forward and gradients in one pass.
 // Row layout of every [R, D] news matrix (student news vecs, T_ext, TP_ext, G_ext, d_news):
@@ -47,7 +35,7 @@ kd_loss_kernel(const float* __restrict__ s_news, const float* __restrict__ s_use
   __shared__ float s_w[KD_MAXM];                  // teacher weights
   __shared__ float s_ds[KD_MAXK];                 // d loss / d student score
   __shared__ float s_mse[KD_MAXM];                // NE_i + UE_i
-  __shared__ float red[UE_THREADS / 32];
+  __shared__ float s_part[KD_MAXM][UE_THREADS / 32];   // per-warp partial MSEs
   __shared__ int s_last;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -77,24 +65,41 @@ kd_loss_kernel(const float* __restrict__ s_news, const float* __restrict__ s_use
     t = warp_sum(t);
     if (lane == 0) { if (i == 0) s_sc[k] = t; else s_tsc[i - 1][k] = t; }
   }
-  // embedding MSEs per teacher: NE_i (mean over (H+K)*D) + UE_i (mean over D)
-  for (int i = 0; i < M; ++i) {
-    const float* TPi = TP_ext + (size_t)i * Rext * D;
-    float acc = 0.f;
+  // embedding MSEs per teacher: NE_i (mean over (H+K)*D) + UE_i (mean over D).  One sweep over the impression's rows
+  // with all M teachers' loads in flight and ONE block reduction of the 2M partial sums (a sweep and two block
+  // reductions per teacher cost 4M barriers and M dependent rounds of global loads)
+  {
+    float ne[KD_MAXM], ue[KD_MAXM];
+#pragma unroll
+    for (int i = 0; i < KD_MAXM; ++i) { ne[i] = 0.f; ue[i] = 0.f; }
     for (int idx = tid; idx < (H + K) * D; idx += UE_THREADS) {
       const int r = idx / D, d = idx - r * D;
       const size_t row = r < H ? (size_t)b * H + r : (size_t)B * H + (size_t)b * K + (r - H);
-      const float diff = s_news[row * D + d] - TPi[row * D + d];
-      acc = fmaf(diff, diff, acc);
+      const float sv = s_news[row * D + d];
+#pragma unroll
+      for (int i = 0; i < KD_MAXM; ++i)
+        if (i < M) { const float diff = sv - TP_ext[((size_t)i * Rext + row) * D + d]; ne[i] = fmaf(diff, diff, ne[i]); }
     }
-    float ne = block_sum_256(acc, red) / (float)((H + K) * D);
-    float acc2 = 0.f;
     for (int d = tid; d < D; d += UE_THREADS) {
-      const float diff = usr[d] - TPi[((size_t)R + b) * D + d];
-      acc2 = fmaf(diff, diff, acc2);
+      const float uv = usr[d];
+#pragma unroll
+      for (int i = 0; i < KD_MAXM; ++i)
+        if (i < M) { const float diff = uv - TP_ext[((size_t)i * Rext + R + b) * D + d]; ue[i] = fmaf(diff, diff, ue[i]); }
     }
-    float ue = block_sum_256(acc2, red) / (float)D;
-    if (tid == 0) s_mse[i] = ne + ue;
+#pragma unroll
+    for (int i = 0; i < KD_MAXM; ++i)
+      if (i < M) {
+        ne[i] = warp_sum(ne[i]);
+        ue[i] = warp_sum(ue[i]);
+        if (lane == 0) { s_part[i][warp] = ne[i] / (float)((H + K) * D) + ue[i] / (float)D; }
+      }
+    __syncthreads();
+    if (tid < M) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < UE_THREADS / 32; ++w) t += s_part[tid][w];      // fixed order: deterministic
+      s_mse[tid] = t;
+    }
   }
   __syncthreads();
   if (tid == 0) {

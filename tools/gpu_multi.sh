@@ -19,6 +19,7 @@ for what in "$@"; do
     kd4) run kd4 --steps 60 --warmup 5 --no-cpu-baseline ;;
     kd4_1) timeout 400 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-preassembled > $o/bench_kd4_n1.json 2> $o/bench_kd4_n1.err; echo "== kd4 n=1 rc=$?"; grep '^{' $o/bench_kd4_n1.json | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(d['value'], d['unit'], d['ms_per_step'], 'ms/step; sustained', d['sustained']['value'])" ;;
     kd4_nccl_only) suffix=_nccl; TNR_P2P_ALLREDUCE=0 run kd4 --steps 60 --warmup 5 --no-cpu-baseline; suffix="" ;;
+    kd4_r2) suffix=_reserve2; TNR_COMM_SM_RESERVE=2 run kd4 --steps 60 --warmup 5 --no-cpu-baseline; suffix="" ;;
     kd4_nccl) NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,COLL run kd4 --steps 5 --warmup 3 --no-cpu-baseline; grep -i "nvls\|channels\|algo" $o/bench_kd4_n$n.err | head -20 > $o/nccl_info.txt ;;
     kd2) run kd2 --steps 60 --warmup 5 --no-cpu-baseline ;;
     table) run table --steps 20 --warmup 3 --no-cpu-baseline ;;
