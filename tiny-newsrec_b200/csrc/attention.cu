@@ -10,8 +10,8 @@
 // runs the two small contractions on the warp-level tensor path (ldmatrix + mma.sync m16n8k16,
 // bf16 in / fp32 accumulate; the 30x30x64 tiles are far below a tcgen05 128-row atom), keeps
 // scores / probabilities in registers and writes the result through shared memory as full
-// 128-byte rows.  The backward recomputes P from Q,K (nothing but QKV is saved) and regenerates
-// the dropout mask from the Philox counter.
+// 128-byte rows.  The backward recomputes P from Q,K (nothing but QKV is saved), regenerates
+// the dropout mask from the Philox counter and keeps its tiles unpadded and XOR-swizzled (12 warps per SM).
 #include "common.cuh"
 #include "mma_sync.cuh"
 
@@ -21,9 +21,7 @@ constexpr int DH = 64;
 constexpr int LMAX = 32;
 constexpr int ATT_WARPS = 4;
 constexpr int TS = 72;            // smem row stride (bf16) of a 32 x 64 tile: 144 B, ldmatrix conflict-free
-constexpr int PS = 40;            // smem row stride (bf16) of the 32 x 32 P / dS tiles: 80 B
 constexpr int TILE_BYTES = LMAX * TS * 2;
-constexpr int PT_BYTES = LMAX * PS * 2;
 constexpr int ATT_FWD_SMEM_PER_WARP = 3 * TILE_BYTES + LMAX * 4 + 2 * LMAX * 4;        // tiles, key mask, rel-pos vector
 // backward: Q, K, V, dO as UNPADDED 32 x 128-byte tiles whose 16-byte chunks are XOR-swizzled with the row (ldmatrix,
 // cp.async, staging and row stores all conflict-free without the 16 pad bytes per row); the dropout(P) and dS tiles
@@ -56,19 +54,6 @@ __device__ __forceinline__ void store_tile(__nv_bfloat16* g, const __nv_bfloat16
     const int idx = lane + 32 * it, r = idx >> 3, c = idx & 7;
     if (r < L) *reinterpret_cast<uint4*>(g + (size_t)r * ld + c * 8) = *reinterpret_cast<const uint4*>(s + r * TS + c * 8);
   }
-}
-
-// out[c] += sum over the first L rows of the staged bf16 tile (columns 2*lane, 2*lane+1): the bias gradient
-// contribution of this (news, head) block, from the same rounded values that go to dqkv
-__device__ __forceinline__ void tile_colsum(float* __restrict__ out, const __nv_bfloat16* s, int L, int lane) {
-  float a0 = 0.f, a1 = 0.f;
-  for (int r = 0; r < L; ++r) {
-    const uint32_t u = *reinterpret_cast<const uint32_t*>(s + r * TS + 2 * lane);
-    a0 += bf16_lo(u);
-    a1 += bf16_hi(u);
-  }
-  atomicAdd(out + 2 * lane, a0);
-  atomicAdd(out + 2 * lane + 1, a1);
 }
 
 // C fragments (2 m-tiles x 8 n-tiles of a 32 x 64 fp32 result) -> bf16 smem tile
@@ -114,16 +99,6 @@ __device__ __forceinline__ void mma_pY(float (&out)[2][8][4], const uint32_t (&p
       mma_bf16(out[mt][nt], pa[mt][1], b[2], b[3]);
     }
   }
-}
-
-// A fragments of X^T where X is a 32 x 32 bf16 tile stored row-major (stride PS)
-__device__ __forceinline__ void load_xT_frags(uint32_t (&pa)[2][2][4], const __nv_bfloat16* sX, int lane) {
-  const int mi = lane >> 3;
-#pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
-      ldsm_x4_t(smem_addr(sX + (ks * 16 + (lane & 7) + (mi >> 1) * 8) * PS + mt * 16 + (mi & 1) * 8), pa[mt][ks]);
 }
 
 // C-layout fp32 32x32 -> bf16 A fragments
