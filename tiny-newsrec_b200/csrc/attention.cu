@@ -37,23 +37,32 @@ int attn_long_bwd_launch(const void* qkv_bf16, const int64_t* mask, int mask_ld,
 int attn_long_fwd_launch(const void* qkv_bf16, const int64_t* mask, int mask_ld, const float* relbias, void* ctx_bf16,
                          int n_news, int L, int A, int E, const tnr_dropout* drop, cudaStream_t st);
 
-// L rows x 64 bf16 from global (row stride ld) -> padded smem tile; rows >= L are zero-filled
+// L rows x 64 bf16 from global (row stride ld) -> padded smem tile; rows >= L are zero-filled.  A lane keeps its 16-byte
+// column c = lane % 8 and walks rows r0, r0 + 4, ...: one 64-bit multiply-add per copy for the global address and an
+// immediate for the shared one (indexing by idx = lane + 32 it cost 9 - 13 instructions per 16-byte copy: a quarter of
+// the backward kernel's instructions were tile addressing)
 __device__ __forceinline__ void load_tile_async(__nv_bfloat16* s, const __nv_bfloat16* g, int L, int ld, int lane) {
+  const int r0 = lane >> 3, c = lane & 7;
+  uint8_t* sp = reinterpret_cast<uint8_t*>(s + r0 * TS + c * 8);
+  const uint32_t sa = smem_addr(sp);
+  const uint8_t* gp = reinterpret_cast<const uint8_t*>(g + (size_t)r0 * ld + c * 8);
+  const size_t gs = (size_t)ld * 8;              // four rows further, in bytes
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const int idx = lane + 32 * it, r = idx >> 3, c = idx & 7;
-    if (r < L) cp_async16(smem_addr(s + r * TS + c * 8), g + (size_t)r * ld + c * 8);
-    else *reinterpret_cast<uint4*>(s + r * TS + c * 8) = make_uint4(0, 0, 0, 0);
+    if (r0 + 4 * it < L) cp_async16(sa + it * (4 * TS * 2), gp + it * gs);
+    else *reinterpret_cast<uint4*>(sp + it * (4 * TS * 2)) = make_uint4(0, 0, 0, 0);
   }
 }
 
 // padded smem tile -> global rows (full 128-byte rows, 16 B per lane)
 __device__ __forceinline__ void store_tile(__nv_bfloat16* g, const __nv_bfloat16* s, int L, int ld, int lane) {
+  const int r0 = lane >> 3, c = lane & 7;
+  const uint8_t* sp = reinterpret_cast<const uint8_t*>(s + r0 * TS + c * 8);
+  uint8_t* gp = reinterpret_cast<uint8_t*>(g + (size_t)r0 * ld + c * 8);
+  const size_t gs = (size_t)ld * 8;
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int idx = lane + 32 * it, r = idx >> 3, c = idx & 7;
-    if (r < L) *reinterpret_cast<uint4*>(g + (size_t)r * ld + c * 8) = *reinterpret_cast<const uint4*>(s + r * TS + c * 8);
-  }
+  for (int it = 0; it < 8; ++it)
+    if (r0 + 4 * it < L) *reinterpret_cast<uint4*>(gp + it * gs) = *reinterpret_cast<const uint4*>(sp + it * (4 * TS * 2));
 }
 
 // C fragments (2 m-tiles x 8 n-tiles of a 32 x 64 fp32 result) -> bf16 smem tile
@@ -117,44 +126,53 @@ __device__ __forceinline__ void c_to_a(uint32_t (&pa)[2][2][4], const float (&p)
 // per-head rel-pos bias vector [2L-1] (index (j - i) + L - 1) -> this warp's shared-memory copy
 __device__ __forceinline__ void load_relbias(float* srel, const float* __restrict__ relbias, int h, int L, int lane) {
   const float* src = relbias + (size_t)h * (2 * L - 1);
-  if (lane < 2 * L - 1) srel[lane] = __ldg(src + lane);
-  if (lane + 32 < 2 * L - 1) srel[lane + 32] = __ldg(src + lane + 32);
+  srel[lane] = lane < 2 * L - 1 ? __ldg(src + lane) : 0.f;                 // all 2 * LMAX entries defined: columns >= L read
+  srel[lane + 32] = lane + 32 < 2 * L - 1 ? __ldg(src + lane + 32) : 0.f;   // them (and are masked with -inf)
 }
 
 // raw QK^T accumulators -> normalised probabilities (C layout; columns >= L become 0)
 __device__ __forceinline__ void softmax_frag(float (&s)[2][4][4], const float* smadd, const float* srel, int L, int lane) {
   const int g = lane >> 2, t = lane & 3;
+  // the key-side addend of this lane's eight columns (row independent): mask term, -inf past L
+  float mb[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = nt * 8 + 2 * t + e;
+      mb[nt][e] = j < L ? smadd[j] : -INFINITY;
+    }
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int hi = 0; hi < 2; ++hi) {
       const int i = mt * 16 + g + hi * 8;
-      const float* relrow = srel + (L - 1 - (i < L ? i : L - 1));      // relrow[j] = bias of key j for query i
+      const float* relrow = srel + (L - 1 - (i < L ? i : L - 1)) + 2 * t;      // relrow[nt*8 + e] = bias of key j for query i
       float mx = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int j = nt * 8 + 2 * t + e;
-          float v = -INFINITY;
-          if (j < L) v = s[mt][nt][hi * 2 + e] * 0.125f + smadd[j] + relrow[j];
+          const float v = fmaf(s[mt][nt][hi * 2 + e], 0.125f, mb[nt][e] + relrow[nt * 8 + e]);
           s[mt][nt][hi * 2 + e] = v;
           mx = fmaxf(mx, v);
         }
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      // exp(v - mx) = 2^(v log2e - mx log2e): one FFMA + one MUFU (column 0 is always live, so mx is finite)
+      const float nm = -mx * 1.4426950408889634f;
       float sum = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const float p = __expf(s[mt][nt][hi * 2 + e] - mx);
+          const float p = ex2_approx(fmaf(s[mt][nt][hi * 2 + e], 1.4426950408889634f, nm));
           s[mt][nt][hi * 2 + e] = p;
           sum += p;
         }
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      const float inv = 1.0f / sum;
+      const float inv = __fdividef(1.0f, sum);
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -240,20 +258,33 @@ __device__ __forceinline__ uint32_t sw_off(int r, int chunk) { return (uint32_t)
 // 32 x 32 bf16 tile, 64-byte rows (two rows per 128-byte line): chunk (0..3) XOR ((r >> 1) & 3)
 __device__ __forceinline__ uint32_t pt_off(int r, int chunk) { return (uint32_t)(r * 64 + ((chunk ^ ((r >> 1) & 3)) << 4)); }
 
+// a lane keeps its 16-byte column c and walks rows r0 + 4 it (r0 = lane / 8 < 4): r & 7 alternates between r0 and r0 + 4,
+// so the swizzled chunk alternates between x0 and x0 ^ 64 bytes and every shared address is base + immediate
 __device__ __forceinline__ void load_tile_async_sw(uint8_t* s, const __nv_bfloat16* g, int L, int ld, int lane) {
+  const int r0 = lane >> 3, c = lane & 7;
+  const uint32_t x0 = (uint32_t)((c ^ r0) << 4);
+  uint8_t* sp0 = s + r0 * 128 + x0;
+  uint8_t* sp1 = s + r0 * 128 + (x0 ^ 64u);
+  const uint32_t sa0 = smem_addr(sp0), sa1 = smem_addr(sp1);
+  const uint8_t* gp = reinterpret_cast<const uint8_t*>(g + (size_t)r0 * ld + c * 8);
+  const size_t gs = (size_t)ld * 8;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const int idx = lane + 32 * it, r = idx >> 3, c = idx & 7;
-    if (r < L) cp_async16(smem_addr(s + sw_off(r, c)), g + (size_t)r * ld + c * 8);
-    else *reinterpret_cast<uint4*>(s + sw_off(r, c)) = make_uint4(0, 0, 0, 0);
+    if (r0 + 4 * it < L) cp_async16(((it & 1) ? sa1 : sa0) + it * 512, gp + it * gs);
+    else *reinterpret_cast<uint4*>(((it & 1) ? sp1 : sp0) + it * 512) = make_uint4(0, 0, 0, 0);
   }
 }
 __device__ __forceinline__ void store_tile_sw(__nv_bfloat16* g, const uint8_t* s, int L, int ld, int lane) {
+  const int r0 = lane >> 3, c = lane & 7;
+  const uint32_t x0 = (uint32_t)((c ^ r0) << 4);
+  const uint8_t* sp0 = s + r0 * 128 + x0;
+  const uint8_t* sp1 = s + r0 * 128 + (x0 ^ 64u);
+  uint8_t* gp = reinterpret_cast<uint8_t*>(g + (size_t)r0 * ld + c * 8);
+  const size_t gs = (size_t)ld * 8;
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int idx = lane + 32 * it, r = idx >> 3, c = idx & 7;
-    if (r < L) *reinterpret_cast<uint4*>(g + (size_t)r * ld + c * 8) = *reinterpret_cast<const uint4*>(s + sw_off(r, c));
-  }
+  for (int it = 0; it < 8; ++it)
+    if (r0 + 4 * it < L)
+      *reinterpret_cast<uint4*>(gp + it * gs) = *reinterpret_cast<const uint4*>(((it & 1) ? sp1 : sp0) + it * 512);
 }
 __device__ __forceinline__ void stage_c64_sw(uint8_t* s, const float (&o)[2][8][4], int lane) {
   const int m = lane >> 3;                       // matrix of the x4 store this lane addresses: rows (m & 1) * 8.., chunk +(m >> 1)
