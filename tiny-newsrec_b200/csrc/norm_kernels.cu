@@ -233,11 +233,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   extern __shared__ __align__(16) uint8_t ln_smem[];
   const DropCfg dc = load_drop(drop);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* s_acc = reinterpret_cast<float*>(ln_smem);                       // [3][E] block totals of dgamma, dbeta, dsum
   // per warp: LNB_STAGES x {x row, dy row} bf16
-  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(ln_smem + 3 * E * 4) + (size_t)warp * LNB_STAGES * 2 * E;
-  for (int i = threadIdx.x; i < 3 * E; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
+  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(ln_smem) + (size_t)warp * LNB_STAGES * 2 * E;
   // packed fp32 pairs (FFMA2 / FADD2 / FMUL2, common.cuh): element pair i of vector v is columns (v*32+lane)*8 + 2i, +1
   f32x2 gm[VPL * 4], acc_dg[VPL * 4], acc_db[VPL * 4], acc_ds[VPL * 4];
 #pragma unroll
@@ -360,26 +357,37 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  // block totals without shared-memory float atomics (CAS loops: 10 instructions each, 72 per lane, contended by 12
+  // warps): every warp parks its three accumulator rows in its own -- now idle -- ring (3 stages x 2 rows x 2 B = 3 x 4 B
+  // per column), then a thread adds the 12 partials of its columns in warp order and issues one global RED per total
+  static_assert(LNB_STAGES >= 3, "the ring doubles as the per-warp accumulator slot");
+  {
+    float* mine = reinterpret_cast<float*>(stage);
 #pragma unroll
-  for (int v = 0; v < VPL; ++v)
+    for (int v = 0; v < VPL; ++v)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int col = (v * 32 + lane) * 8 + 2 * i;
-      float lo, hi;
-      upk2(acc_dg[v * 4 + i], lo, hi);
-      atomicAdd(&s_acc[col], lo); atomicAdd(&s_acc[col + 1], hi);
-      upk2(acc_db[v * 4 + i], lo, hi);
-      atomicAdd(&s_acc[E + col], lo); atomicAdd(&s_acc[E + col + 1], hi);
-      if (dsum != nullptr) {
+      for (int i = 0; i < 4; ++i) {
+        const int col = (v * 32 + lane) * 8 + 2 * i;
+        float lo, hi;
+        upk2(acc_dg[v * 4 + i], lo, hi);
+        *reinterpret_cast<float2*>(mine + col) = make_float2(lo, hi);
+        upk2(acc_db[v * 4 + i], lo, hi);
+        *reinterpret_cast<float2*>(mine + E + col) = make_float2(lo, hi);
         upk2(acc_ds[v * 4 + i], lo, hi);
-        atomicAdd(&s_acc[2 * E + col], lo); atomicAdd(&s_acc[2 * E + col + 1], hi);
+        *reinterpret_cast<float2*>(mine + 2 * E + col) = make_float2(lo, hi);
       }
-    }
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < E; i += blockDim.x) {
-    atomicAdd(dgamma + i, s_acc[i]);
-    atomicAdd(dbeta + i, s_acc[E + i]);
-    if (dsum != nullptr) atomicAdd(dsum + i, s_acc[2 * E + i]);
+  const float* part0 = reinterpret_cast<const float*>(ln_smem);
+  constexpr int PART_STRIDE = LNB_STAGES * 2 * E * 2 / 4;          // floats between two warps' slots
+  for (int i = threadIdx.x; i < 3 * E; i += blockDim.x) {
+    if (i >= 2 * E && dsum == nullptr) break;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < LNB_WARPS; ++w) t += part0[w * PART_STRIDE + i];
+    float* dst = i < E ? dgamma + i : (i < 2 * E ? dbeta + (i - E) : dsum + (i - 2 * E));
+    atomicAdd(dst, t);
   }
 }
 
@@ -475,7 +483,7 @@ extern "C" __attribute__((visibility("default"))) int tnr_layernorm_bwd(const vo
   const int cap = num_sms();
   if (grid > cap) grid = cap;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int smem = 3 * E * 4 + LNB_WARPS * LNB_STAGES * 2 * E * 2;
+  const int smem = LNB_WARPS * LNB_STAGES * 2 * E * 2;
   DISPATCH_VPL(E, (cudaFuncSetAttribute(layernorm_bwd_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)));
   DISPATCH_VPL(E, (layernorm_bwd_kernel<VPL><<<grid, LNB_WARPS * 32, smem, st>>>(
                       reinterpret_cast<const __nv_bfloat16*>(dy_bf16), reinterpret_cast<const __nv_bfloat16*>(x_bf16),
