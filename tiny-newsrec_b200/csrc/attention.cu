@@ -192,7 +192,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
                 const float* __restrict__ relbias, __nv_bfloat16* __restrict__ ctx, int n_news, int L, int A, int E,
                 const tnr_dropout drop) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * ATT_WARPS + warp;
   if (item >= (long long)n_news * A) return;
   uint8_t* wbase = smem + (size_t)warp * ATT_FWD_SMEM_PER_WARP;
@@ -371,7 +371,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict
                 __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int n_news, int L, int A, int E,
                 const tnr_dropout drop) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * ATT_BWD_WARPS + warp;
   if (item >= (long long)n_news * A) return;
   uint8_t* sQ = smem + (size_t)warp * ATT_BWD_SMEM_PER_WARP;

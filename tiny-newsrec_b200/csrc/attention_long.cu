@@ -49,7 +49,7 @@ attn_long_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __res
   float* s_rel = s_madd + k_chunks * LKB;                         // [2L - 1 (+ 64 zeros)], pre-multiplied by log2(e)
   __shared__ int s_live[LONG_LMAX / LKB];                         // chunk holds at least one unmasked key
   __shared__ int s_any;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const long long item = blockIdx.x / q_blocks;
   const int qb = blockIdx.x % q_blocks;
@@ -374,7 +374,7 @@ attn_long_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __
   float* s_rel = s_madd + k_chunks * LKB;                         // [2L - 1 (+ 64 zeros)]
   __shared__ int s_live[LONG_LMAX / LKB];
   __shared__ int s_any;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const long long item = blockIdx.x / q_blocks;
   const int qb = blockIdx.x % q_blocks;
@@ -540,7 +540,7 @@ attn_long_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* _
   float* s_madd = reinterpret_cast<float*>(sS + LQB * LTS);       // [64] this key block
   float* s_rel = s_madd + LKB;                                    // [2L - 1 (+ 64 zeros)]
   __shared__ int s_any, s_live;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const long long item = blockIdx.x / k_blocks;
   const int kb = blockIdx.x % k_blocks;

@@ -51,6 +51,10 @@ int num_sms();           // cached SM count of the current device (148 on B200)
 int sm_reserve();        // SMs the persistent GEMM grids leave free on the current device (tnr_set_sm_reserve)
 
 // ---- device helpers ---------------------------------------------------------
+// threadIdx.x / 32 read through a shuffle: the compiler then treats the warp index -- and every row / item index derived
+// from it -- as warp-uniform, and stops wrapping the warp collectives behind `if (row < rows)` in divergence handling
+// (BRA.DIV + WARPSYNC per shuffle: a quarter of the LayerNorm forward's instructions)
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -305,7 +305,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   auto ld_bar = [&](int w) { return bar_base + 8u * (2 * C::STAGES + 4 + w); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES + 8 * C::NUM_BARS);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;     // 0 = leader of the CTA pair
 

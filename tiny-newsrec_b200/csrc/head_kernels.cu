@@ -38,7 +38,7 @@ kd_loss_kernel(const float* __restrict__ s_news, const float* __restrict__ s_use
   __shared__ float s_part[KD_MAXM][UE_THREADS / 32];   // per-warp partial MSEs
   __shared__ int s_last;
   const int b = blockIdx.x, tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
+  const int warp = uniform_warp_id(), lane = tid & 31;
   const int R = B * (H + K);
   const size_t Rext = (size_t)R + B;
   const float* cand = s_news + ((size_t)B * H + (size_t)b * K) * D;

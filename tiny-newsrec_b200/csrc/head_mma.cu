@@ -51,7 +51,7 @@ sgemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ Bm, const
   __shared__ __align__(16) float Bs[2][SG_T][SG_K + 4];
   A += blockIdx.z * sA; Bm += blockIdx.z * sB; C += blockIdx.z * sC;
   if (bias) bias += blockIdx.z * sbias;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int wm = warp >> 1, wn = warp & 1;
   const int m0 = blockIdx.y * SG_T, n0 = blockIdx.x * SG_T;
   float acc[2][4][4] = {};
@@ -120,7 +120,7 @@ sgemm_tn_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float
   const int batch = blockIdx.z / splits, split = blockIdx.z - batch * splits;
   A += batch * sA; Bm += batch * sB; C += batch * sC;
   if (cbias) cbias += batch * sbias;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int wm = warp >> 1, wn = warp & 1;
   const int i0 = blockIdx.y * SG_T, j0 = blockIdx.x * SG_T;
   const int r_begin = split * rows_per_split;
@@ -548,7 +548,7 @@ ue_logits_kernel(const __grid_constant__ UlParams p) {
   const uint32_t w_bar = bar_base + 8u * (3 * UL_STAGES + 4);                         // each CTA: its W1 half landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + NKB * UL_W_KB_BYTES + UL_STAGES * UL_A_BYTES +
                                                     3 * UL_QT * 4 + UL_NBARS * 8);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();                 // 0 = leader of the pair
   const int n_live = *p.n_live;
   const int n_tiles = (n_live + 2 * UL_ROWS - 1) / (2 * UL_ROWS);      // pair tiles of 256 live rows
@@ -822,7 +822,7 @@ ue_pool_kernel(const float* __restrict__ vecs, const int32_t* __restrict__ idx, 
   __shared__ float s_al[UP_WARPS][UE_HMAX];              // compacted: weight of live row k
   __shared__ float s_m[UP_WARPS][UE_HMAX];               // compacted: its mask value
   __shared__ size_t s_row[UP_WARPS][UE_HMAX];            // compacted: its row offset
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int b = blockIdx.x * UP_WARPS + warp;
   if (b >= B) return;
   const float bias2 = b2[0];
@@ -936,7 +936,7 @@ user_encoder_bwd_kernel(const float* __restrict__ vecs, const float* __restrict_
   float* smk = sdz + UE_HMAX;             // [64]
   float* sdusr = smk + UE_HMAX;           // [D]
   __shared__ float s_dot;
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31, g = lane >> 2, t = lane & 3;
   // grid.y column slices: the batch is the grid (32 blocks at the demo shape on 148 SMs), so each impression is cut
   // into S blocks that repeat the cheap part (dz, du) and split the n-tiles of the dv product; slice 0 alone
   // writes dU / Vb and adds the parameter gradients.

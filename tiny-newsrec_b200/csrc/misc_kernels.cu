@@ -87,7 +87,7 @@ constexpr int GI_ROWS = 4;          // rows per warp: four index loads, then fou
 __global__ void __launch_bounds__(256)
 gather_rows_i32_i64_kernel(const int32_t* __restrict__ table, long long n_rows_table, const int32_t* __restrict__ idx,
                            long long n, int W, int64_t* __restrict__ out) {
-  const long long r0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * GI_ROWS;
+  const long long r0 = ((long long)blockIdx.x * 8 + uniform_warp_id()) * GI_ROWS;
   if (r0 >= n) return;
   const int lane = threadIdx.x & 31;
   long long src[GI_ROWS];
@@ -116,7 +116,7 @@ gather_rows_i32_i64_kernel(const int32_t* __restrict__ table, long long n_rows_t
 __global__ void __launch_bounds__(256)
 gather_rows_f32_kernel(const float* __restrict__ table, long long n_rows_table, const int32_t* __restrict__ idx,
                        long long n, int D, float* __restrict__ out, long long out_ld) {
-  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long r = (long long)blockIdx.x * 8 + uniform_warp_id();
   if (r >= n) return;
   long long src = idx[r];
   if (src < 0 || src >= n_rows_table) src = 0;
@@ -143,7 +143,7 @@ struct TrainBatchGather {
 
 __global__ void __launch_bounds__(256)
 train_batch_gather_kernel(const __grid_constant__ TrainBatchGather g) {
-  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long r = (long long)blockIdx.x * 8 + uniform_warp_id();
   if (r >= g.n_hist + g.n_cand) return;
   const int lane = threadIdx.x & 31, job = blockIdx.y;
   long long src = r < g.n_hist ? g.hist_idx[r] : g.cand_idx[r - g.n_hist];
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256)
 doc_sim_kernel(const float* __restrict__ table, long long n_rows, const int32_t* __restrict__ pairs, long long n_pairs,
                int D, double* __restrict__ sum_out) {
   __shared__ double s_part[8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const long long pidx = (long long)blockIdx.x * 8 + warp;
   double c = 0.0;
   if (pidx < n_pairs) {
@@ -229,7 +229,7 @@ eval_score_kernel(const float* __restrict__ table, long long n_rows, const float
                   const long long* __restrict__ ptr, const int32_t* __restrict__ cand, long long n_imp, long long nnz,
                   float* __restrict__ score) {
   const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
-  const long long warp_global = (long long)blockIdx.x * ES_WARPS + (threadIdx.x >> 5);
+  const long long warp_global = (long long)blockIdx.x * ES_WARPS + uniform_warp_id();
   const long long n_items = (nnz + ES_CPW - 1) / ES_CPW;
   constexpr int D = 32 * VPL;
   for (long long item = warp_global; item < n_items; item += (long long)gridDim.x * ES_WARPS) {
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(ER_WARPS * 32)
 eval_rank_kernel(const float* __restrict__ score, const long long* __restrict__ ptr, const int8_t* __restrict__ label,
                  long long n_imp, int cap, double* __restrict__ out) {
   extern __shared__ __align__(16) float sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const long long b = (long long)blockIdx.x * wpb + warp;
   if (b >= n_imp) return;

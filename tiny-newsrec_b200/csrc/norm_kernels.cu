@@ -43,7 +43,7 @@ embed_ln_kernel(const int64_t* __restrict__ ids, int ids_ld, int L, int n_rows, 
                 __nv_bfloat16* __restrict__ out, const tnr_dropout drop) {
   constexpr int E = VPL * 256;
   constexpr int NRAW = VPL * (WORD_BF16 ? 1 : 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int w = blockIdx.x * EMB_WARPS + warp;
   const int l = w % L, grp = w / L;
   if (grp >= groups) return;
@@ -137,7 +137,7 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int rows, const float*
                      const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int reverse) {
   constexpr int E = VPL * 256;
   constexpr int NR = LNF_ROWS;                    // rows in flight per warp (registers)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   // packed fp32 pairs (FFMA2 / FADD2): pair i of vector v = columns (v*32+lane)*8 + 2i, +1
   f32x2 g[VPL * 4], bt[VPL * 4];
 #pragma unroll
@@ -232,7 +232,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   constexpr int E = VPL * 256;
   extern __shared__ __align__(16) uint8_t ln_smem[];
   const DropCfg dc = load_drop(drop);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   // per warp: LNB_STAGES x {x row, dy row} bf16
   __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(ln_smem) + (size_t)warp * LNB_STAGES * 2 * E;
   // packed fp32 pairs (FFMA2 / FADD2 / FMUL2, common.cuh): element pair i of vector v is columns (v*32+lane)*8 + 2i, +1

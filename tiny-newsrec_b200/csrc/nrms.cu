@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(NR_THREADS)
 nrms_attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                      const float* __restrict__ mask, float* __restrict__ ctx, int H, int n_heads) {
   extern __shared__ __align__(16) float nr_sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31, b = blockIdx.x;
   const int Dh = n_heads * NR_DK;
   float* sk = nr_sm + warp * (2 * NR_HMAX * NR_DK);
   float* sv = sk + NR_HMAX * NR_DK;
@@ -125,7 +125,7 @@ nrms_attn_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, c
                      const float* __restrict__ mask, const float* __restrict__ dctx, float* __restrict__ dq,
                      float* __restrict__ dk, float* __restrict__ dv, int H, int n_heads) {
   extern __shared__ __align__(16) float nr_sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31, b = blockIdx.x;
   const int Dh = n_heads * NR_DK;
   constexpr int PER_WARP = 4 * NR_HMAX * NR_DK + 2 * NR_HMAX;
   float* sq = nr_sm + warp * PER_WARP;          // q / 4
@@ -223,7 +223,7 @@ sgemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float
                 int parts, long long sA, long long sB) {
   __shared__ __align__(16) float As[2][SN_T][SN_K + 4];
   __shared__ __align__(16) float Bs[2][SN_K][SN_T + 8];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int wm = warp >> 1, wn = warp & 1;
   const int m0 = blockIdx.y * SN_T, n0 = blockIdx.x * SN_T;
   float acc[2][4][4] = {};

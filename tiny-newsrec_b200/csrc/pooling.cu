@@ -36,7 +36,7 @@ attnpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
   constexpr int C = VPL * 256;
   constexpr int ROW16 = (VPL + 1) * 32;                 // 16-byte pieces per ring row: VPL x 32 of x, 32 of e
   extern __shared__ __align__(16) unsigned char pw_sm[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int n = blockIdx.x * PW_WARPS + warp;
   if (n >= n_news) return;                               // no block-level barrier below
   bf16x8* ring = reinterpret_cast<bf16x8*>(pw_sm) + (size_t)warp * PW_RING * ROW16;
@@ -125,7 +125,7 @@ attnpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
   extern __shared__ __align__(16) unsigned char pw_sm[];
   __shared__ float s_gw[PW_WARPS][256];
   __shared__ float s_gb[PW_WARPS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const int n = blockIdx.x * PW_WARPS + warp;
   const bool active = n < n_news;
   bf16x8* ring = reinterpret_cast<bf16x8*>(pw_sm) + (size_t)warp * PW_RING * ROW16;
