@@ -1,9 +1,9 @@
 // bf16 GEMM on 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in TMEM), operands
 // staged by TMA into 128B-swizzled shared memory, warp-specialised persistent kernel:
-//   warp 0      TMA producer (one elected lane)
-//   warp 1      MMA issuer   (one elected lane, tcgen05.mma cta_group::1, 128 x BN x 16)
+//   warp 0      TMA producer   } the whole warp walks the loop and waits on the mbarriers converged, one elect.sync
+//   warp 1      MMA issuer     } lane issues (operands in uniform registers); tcgen05.mma cta_group::1, 128 x BN x 16
 //   warp 2      TMEM allocator / deallocator
-//   warps 4-11  epilogue: tcgen05.ld -> bias / GELU / tanh / dGELU / dropout / residual
+//   warps 4-19  epilogue: tcgen05.ld -> bias / GELU / tanh / dGELU / dropout / residual
 //               bf16 outputs: each warp stages 32 x 64 boxes in 128B-swizzled shared memory and
 //               writes them with TMA stores; the residual (or the dGELU pre-activation) box is
 //               prefetched by TMA at tile start.  (Per-thread-row 16 B global accesses made the
