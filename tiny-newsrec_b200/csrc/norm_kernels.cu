@@ -7,9 +7,7 @@
 namespace tnr {
 
 constexpr int ROWS_PER_BLOCK = 8;   // 8 warps
-#ifndef LNF_ROWS
-#define LNF_ROWS 3     // rows in flight per warp of the LayerNorm forward: 1 -> 69.6 %, 2 -> 78.9 %, 3 -> 80.7 % of HBM peak (128 registers)
-#endif
+constexpr int LNF_ROWS = 3;         // rows in flight per warp of the LayerNorm forward: 1 -> 69.6 %, 2 -> 78.9 %, 3 -> 80.7 % of HBM peak (128 registers)
 
 // out[t, :] = dropout(LN(word[id[t]] + pos[t % L] + type[0]))         (tnlrv3/modeling.py:168-177)
 // ids: int64, row n at ids + n * ids_ld, L tokens per row.  word table bf16 or fp32.
@@ -218,10 +216,7 @@ __device__ __forceinline__ void ln_cp_async16(void* smem_dst, const void* src) {
 }
 
 constexpr int LNB_WARPS = 12;      // 384 threads, <= 168 registers: one block per SM
-#ifndef LNB_STAGES_X
-#define LNB_STAGES_X 3
-#endif
-constexpr int LNB_STAGES = LNB_STAGES_X;
+constexpr int LNB_STAGES = 3;       // ring depth 2 / 3 / 4 measure the same (the kernel is not latency-bound); 3 also sizes the tail's slots
 
 template <int VPL>
 __global__ void __launch_bounds__(LNB_WARPS * 32, 1)
