@@ -11,14 +11,13 @@ Reference: Tiny-NewsRec/model_bert.py:8-34 (AttentionPooling), :103-137 (NewsEnc
 tnlrv3/modeling.py:133-476,713-801 for the encoder parameter tree.
 """
 import json
-import math
 
 import torch
 from torch import nn
 
 from . import ops
 from ._lib import TinyRecError
-from .engine import BF, F32, DropState, Encoder, FlatParams, _align8
+from .engine import F32, DropState, Encoder, FlatParams, _align8
 from .synth import BERT_BASE
 
 # ------------------------------------------------------------------------------------
