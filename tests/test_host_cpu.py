@@ -399,3 +399,37 @@ def test_news_encoder_model_name_must_load(tmp_path):
     assert torch.equal(got["bert.rel_pos_bias.weight"], src["bert.rel_pos_bias.weight"])
     assert float(got["bert.encoder.layer.0.attention.self.key.bias"].abs().max()) == 0.0
     assert all(k.startswith(("bert.pooler", "classifier")) for k in ne.pretrained_missing_keys)
+
+
+def test_sass_is_blackwell_native(built_lib):
+    """Static check of the shipped library (no GPU): the GEMM / scoring kernels really are tcgen05 + TMEM + TMA
+    (UTCHMMA, LDTM, UTMALDG / UTMASTG in their SASS; the CTA-pair variants issue UTCHMMA.2CTA), the MMA issue loops keep
+    their operands in uniform registers (no R2UR.BROADCAST waterfall around the UTCHMMAs -- that was 75 cycles per MMA),
+    the NVLS exchange kernel reduces in the switch (LDGMC...ADD = multimem.ld_reduce) and the attention backward stages
+    its fragments with stmatrix (STSM)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", built_lib], capture_output=True, text=True, check=True).stdout
+    funcs = {}
+    for blk in re.split(r"\n\s*Function : ", sass)[1:]:
+        name, _, body = blk.partition("\n")
+        funcs[name.strip()] = body
+    gemms = {n: b for n, b in funcs.items() if "gemm_kernel" in n and "sgemm" not in n}
+    assert len(gemms) >= 40, len(gemms)                                  # every (BN, layout, epilogue, CTA-pair) variant
+    for n, b in gemms.items():
+        assert b.count("UTCHMMA") == 4 and "LDTM" in b and "UTMALDG" in b, n
+        assert "R2UR.BROADCAST" not in b, n
+        cta2 = n.split("gemm_kernelI")[1].split("EEEv")[0].endswith("Lb1")       # last template argument: CTA2
+        assert ("UTCHMMA.2CTA" in b) == cta2, n
+        epi_tma = "ELb1ELb" in n.split("gemm_kernelI")[1][-12:]
+        if epi_tma:
+            assert "UTMASTG" in b, n
+    logits = [b for n, b in funcs.items() if "ue_logits_kernel" in n]
+    assert len(logits) == 2 and all("UTCHMMA.2CTA" in b and "LDTM" in b and "R2UR.BROADCAST" not in b for b in logits)
+    nvls = [b for n, b in funcs.items() if "allreduce_nvls_kernel" in n]
+    assert len(nvls) == 1 and "LDGMC" in nvls[0]
+    attn_bwd = [b for n, b in funcs.items() if "tnr15attn_bwd_kernel" in n]       # (not nrms_attn_bwd_kernel)
+    assert len(attn_bwd) == 1 and "STSM" in attn_bwd[0] and "HMMA" in attn_bwd[0]
