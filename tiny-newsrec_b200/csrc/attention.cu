@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, const int64_t* __restrict__ mask, int mask_ld,
                 const float* __restrict__ relbias, __nv_bfloat16* __restrict__ ctx, int n_news, int L, int A, int E,
                 const tnr_dropout drop) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * ATT_WARPS + warp;
   if (item >= (long long)n_news * A) return;
